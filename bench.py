@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py — SRBD NMPC QP solves/sec (BASELINE.json metric) on N B200s of one node.
+
+One "step" = one pass of the hot path (K1 linearize -> K2 assemble -> K3 OCP-QP IPM solve to tol 1e-8)
+over one batch of synthetic SRBD problems: BASELINE config 3 (65536 QPs per GPU, horizon N=20, randomized
+contact schedules, hard friction-cone / force-box rows).  Independent QPs shard over ranks with no
+data-path collective (weak scaling: 65536 QPs per GPU); NCCL only gathers the per-rank statistics block.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the CPU restatement of the reference path on the host cores
+
+Prints ONE JSON line (rank 0).  `value` = device-timed throughput with inputs resident in HBM;
+`e2e` = the same metric through the C-ABI with pinned HOST buffers (H2D + solve + D2H in the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SETTINGS = dict(iter_max=30, alpha_min=1e-8, mu0=1e2, tol_stat=1e-8, tol_eq=1e-8, tol_ineq=1e-8, tol_comp=1e-8,
+                reg_prim=1e-12, warm_start=0, pred_corr=1, ric_alg=0, split_step=1)
+METRIC = "SRBD NMPC QP solves/sec, batch 64k, N=20"
+UNIT = "solves/s"
+HORIZON = 20
+
+
+def stage_flops(N, nx=12, nu=12, ng=24):
+    """Algorithmic flops of SURVEY.md §8d: returns (F_it with c=2 KKT vector solves, F_res) per QP."""
+    f_it, f_res = 0.0, 0.0
+    for k in range(N + 1):
+        nuk, nxk = (nu if k < N else 0), (nx if k > 0 else 0)
+        n, nxn, ngk = nuk + nxk, (nx if k < N else 0), (ng if k < N else 0)
+        fact = nxn * nxn * (n + 1) + n * (n + 1) * (nxn + ngk) + n ** 3 / 3.0 + n * n + n * ngk
+        vec = 2.0 * (n * n + 2 * n * nxn + 2 * nxn * nxn) + 2.0 * n * ngk
+        res = 2.0 * n * n + 4.0 * n * nxn + 4.0 * n * ngk
+        f_it += fact + 2.0 * vec + res
+        f_res += res
+    return f_it, f_res
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_run(pkg, batch, threads=0, seed_start=0, contact="gait"):
+    """Times the CPU oracle (restatement of the reference path) on `batch` QPs.  Returns (solves/s, cores, out)."""
+    from oracle import oracle as orc
+    w = pkg.workload.srbd_batch(batch, N=HORIZON, contact_mode=contact, start=seed_start)
+    m, a = orc.model_params(HORIZON), orc.ipm_args(**SETTINGS)
+    nthr = orc.num_threads() if threads <= 0 else threads
+    t0 = time.perf_counter()
+    out = orc.pipeline(m, a, HORIZON, pkg.capi.SRBD_HARD_INEQ, w["x"], w["u"], w["xref"], w["x0"], w["contact"],
+                       threads=nthr, duals=False)
+    dt = time.perf_counter() - t0
+    return batch / dt, nthr, out, dt
+
+
+def run_reference(args, pkg, rank, world):
+    """--impl reference: the reference's CPU implementation of the path.  The reference itself cannot be built
+    offline (Eigen / yaml-cpp / HPIPM / BLASFEO absent), so this is the oracle port (kind = "port")."""
+    if rank != 0:
+        return
+    sample = args.cpu_sample
+    for _ in range(args.warmup):
+        cpu_reference_run(pkg, min(sample, 512))
+    times, cores = [], 1
+    for s in range(args.steps):
+        v, cores, out, dt = cpu_reference_run(pkg, sample, seed_start=s * sample)
+        times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    val = sample / (ms * 1e-3)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "BASELINE config 3: SRBD QPs N=20, randomized contact schedules, HARD_INEQ, IPM tol 1e-8",
+                       "qps_per_step": sample, "horizon": HORIZON},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{sample} QPs per step x {args.steps} steps, OpenMP over QPs, all host threads; "
+                                       "CPU oracle port (reference HPIPM/BLASFEO/Eigen not buildable offline)"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=65536, help="QPs per GPU")
+    ap.add_argument("--contact", default="gait", choices=["gait", "stance"])
+    ap.add_argument("--cpu-sample", type=int, default=8192, help="QPs per step of the CPU baseline / reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    import srbd_pkg
+    pkg = srbd_pkg.load()
+
+    if args.impl == "reference":
+        run_reference(args, pkg, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    B = args.batch
+    w = pkg.workload.srbd_batch(B, N=HORIZON, contact_mode=args.contact, start=rank * B)
+    ctx = pkg.Context(B, device=local_rank)
+    ctx.set_model(pkg.default_model_params(HORIZON))
+    ctx.set_ipm_args(pkg.default_ipm_args(**SETTINGS))
+    ctx.upload_traj(w["x"], w["u"], w["xref"], w["x0"], w["contact"])
+    ctx.sync()
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+    mode = pkg.capi.SRBD_HARD_INEQ
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    def step(evs=None):
+        if evs:
+            evs[0].record(stream)
+        ctx.linearize()
+        if evs:
+            evs[1].record(stream)
+        ctx.assemble(mode)
+        if evs:
+            evs[2].record(stream)
+        ctx.qp_solve()
+        if evs:
+            evs[3].record(stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    ctx.sync()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    l0 = ctx.launch_count
+    all_evs = [[ev() for _ in range(4)] for _ in range(args.steps)]
+    for s in range(args.steps):
+        step(all_evs[s])
+    barrier()
+    launches = ctx.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = all_evs[0][0].elapsed_time(all_evs[-1][3])
+    k_ms = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(3)] for e in all_evs])  # K1, K2, K3 per step
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    ms_per_step = total_ms_max / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    # per-rank statistics block (fused epilogue of K3), gathered over NCCL
+    bs = ctx.batch_stats()
+    st = ctx.download_stats()
+    stats_vec = torch.tensor([bs["solves"], bs["iter_sum"]] + bs["status_count"] + bs["iter_hist"], dtype=torch.int64,
+                             device="cuda")
+    if world > 1:
+        gathered = [torch.zeros_like(stats_vec) for _ in range(world)]
+        dist.all_gather(gathered, stats_vec)
+        stats_all = torch.stack(gathered).sum(0).cpu().numpy()
+    else:
+        stats_all = stats_vec.cpu().numpy()
+
+    # ---- e2e: host buffers through the C-ABI (pinned), H2D + K1 + K2 + K3 + D2H per step ---------------
+    def pinned(a):
+        tt = torch.from_numpy(a).pin_memory()
+        return tt, tt.numpy()
+    keep, hb = [], {}
+    for k in ("x", "u", "xref", "x0", "contact"):
+        tt, hb[k] = pinned(w[k])
+        keep.append(tt)
+    t_sx, h_sx = pinned(np.zeros((B, HORIZON + 1, 12)))
+    t_su, h_su = pinned(np.zeros((B, HORIZON, 12)))
+    t_it, h_it = pinned(np.zeros(B, dtype=np.int32))
+    t_st, h_st = pinned(np.zeros(B, dtype=np.int32))
+    ctx.solve_host(mode, hb["x"], hb["u"], hb["xref"], hb["x0"], hb["contact"], h_sx, h_su, h_it, h_st)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        ctx.solve_host(mode, hb["x"], hb["u"], hb["xref"], hb["x0"], hb["contact"], h_sx, h_su, h_it, h_st)
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / args.e2e_steps
+    te = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B / (float(te.item()) * 1e-3)
+    h2d = sum(int(hb[k].nbytes) for k in hb)
+    d2h = int(h_sx.nbytes + h_su.nbytes + h_it.nbytes + h_st.nbytes)
+    assert (h_st == 0).all() and np.array_equal(h_it, st["iter"]), "e2e path disagrees with the device-resident path"
+
+    if rank == 0:
+        # roofline of the dominant kernel (K3): algorithmic FP64 flops with the ACTUAL iteration counts
+        f_it, f_res = stage_flops(HORIZON)
+        flops_launch = float(st["iter"].sum()) * f_it + B * f_res
+        k3_ms = float(k_ms[:, 2].mean())
+        achieved = flops_launch / (k3_ms * 1e-3) / 1e12
+        peak = ctx.fp64_peak() / 1e12
+        roofline = {"bound": "fp64", "kernel": "ipm_solve_kernel (K3)", "achieved": achieved, "peak": peak,
+                    "unit": "TFLOP/s", "frac": achieved / peak if peak > 0 else None, "traffic": None,
+                    "peak_source": "measured live: DFMA-saturating microbenchmark srbd_fp64_peak() (MEASURED_PEAKS.json "
+                                   "carries no FP64 figure)",
+                    "flops_per_launch": flops_launch, "kernel_ms": k3_ms,
+                    "kernel_share_of_step": k3_ms / float(k_ms.sum(1).mean()),
+                    "k1_ms": float(k_ms[:, 0].mean()), "k2_ms": float(k_ms[:, 1].mean())}
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        hbm_peak = json.load(open(peaks_path))["hbm_gbs"] if os.path.exists(peaks_path) else 6650.0
+        # HBM view of K1/K2 (write-bound kernels): dense packed records written per step
+        k1_bytes = B * HORIZON * (336 + 12) * 8 + B * (HORIZON * 2 + 1) * 12 * 8
+        k2_bytes = B * (HORIZON + 1) * (672 + 96) * 8 + B * HORIZON * 576 * 8
+        roofline["k1_hbm_frac"] = k1_bytes / (roofline["k1_ms"] * 1e-3) / 1e9 / hbm_peak
+        roofline["k2_hbm_frac"] = k2_bytes / (roofline["k2_ms"] * 1e-3) / 1e9 / hbm_peak
+        roofline["hbm_peak_gbs"] = hbm_peak
+        cpu_baseline = None
+        if not args.no_cpu_baseline:
+            v, cores, out, dt = cpu_reference_run(pkg, args.cpu_sample)
+            same = bool(np.array_equal(out["iter"], st["iter"][:args.cpu_sample])) if args.cpu_sample <= B else None
+            cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": f"first {args.cpu_sample} QPs of rank 0's shard, one pass ({dt:.1f} s), OpenMP over QPs; "
+                                      "CPU oracle port (reference HPIPM/BLASFEO/Eigen not buildable offline)",
+                            "iteration_counts_equal_gpu": same}
+        it = st["iter"]
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "BASELINE config 3: 65536 SRBD QPs per GPU, N=20, randomized contact schedules, "
+                                       "hard friction-cone/force-box rows (HARD_INEQ), full IPM to tol 1e-8, ric_alg=0",
+                           "qps_per_gpu": B, "global_batch": world * B, "horizon": HORIZON, "contact": args.contact,
+                           "l2": "inputs larger than L2 (packed QP data 18.5 GB per step, trajectories 0.4 GB)",
+                           "parallelism": f"dp{world} (independent QPs, no data-path collective)"},
+                "clocks": clocks, "gpu_launches": int(launches),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": float(te.item()), "steps": args.e2e_steps},
+                "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "ipm": {"iter_mean": float(it.mean()), "iter_min": int(it.min()), "iter_max": int(it.max()),
+                        "status_counts_all_ranks": [int(v) for v in stats_all[2:7]],
+                        "solves_all_ranks": int(stats_all[0]), "iter_sum_all_ranks": int(stats_all[1])}}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

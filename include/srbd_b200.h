@@ -224,6 +224,9 @@ int srbd_ctx_destroy(srbd_ctx* ctx);
 const char* srbd_last_error(const srbd_ctx* ctx);
 int srbd_set_model(srbd_ctx* ctx, const srbd_model_params* p);
 int srbd_set_ipm_args(srbd_ctx* ctx, const srbd_ipm_args* a);
+/* optional outputs of the solve (off by default: they cost HBM): Riccati P,p,K,k (+ pi[0], which the
+ * reference reconstructs from them, ocp_qp_ipm_solver.cpp:349-373) and the 18-column statistics table */
+int srbd_set_outputs(srbd_ctx* ctx, int export_ric, int export_stat);
 int srbd_ctx_stat_rows(const srbd_ctx* ctx);
 void* srbd_ctx_stream(const srbd_ctx* ctx);
 int srbd_ctx_device_ptr(srbd_ctx* ctx, int buf, void** ptr, size_t* bytes);

@@ -118,6 +118,9 @@ class Context:
         self._args = a
         self._ck(self._L.srbd_set_ipm_args(self._h, C.byref(a)))
 
+    def set_outputs(self, export_ric=False, export_stat=False):
+        self._ck(self._L.srbd_set_outputs(self._h, int(bool(export_ric)), int(bool(export_stat))))
+
     # -- NMPC level ------------------------------------------------------------------------------
     def upload_traj(self, x, u, xref, x0, contact=None):
         f = lambda a: np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731

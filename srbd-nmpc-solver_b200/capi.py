@@ -117,7 +117,8 @@ def make_qp_host(arrays):
 
 _EXPORTS = [
     "srbd_model_params_default", "srbd_ipm_args_default", "srbd_qp_nct", "srbd_ctx_create",
-    "srbd_ctx_destroy", "srbd_last_error", "srbd_set_model", "srbd_set_ipm_args", "srbd_ctx_stat_rows",
+    "srbd_ctx_destroy", "srbd_last_error", "srbd_set_model", "srbd_set_ipm_args", "srbd_set_outputs",
+    "srbd_ctx_stat_rows",
     "srbd_ctx_stream", "srbd_ctx_device_ptr", "srbd_ctx_sync", "srbd_ctx_launch_count",
     "srbd_upload_traj", "srbd_download_traj", "srbd_linearize", "srbd_assemble",
     "srbd_download_linearization", "srbd_download_qp", "srbd_qp_upload", "srbd_qp_solve",
@@ -152,6 +153,7 @@ def lib():
     L.srbd_last_error.restype = C.c_char_p
     L.srbd_set_model.argtypes = [vp, C.POINTER(ModelParams)]
     L.srbd_set_ipm_args.argtypes = [vp, C.POINTER(IpmArgs)]
+    L.srbd_set_outputs.argtypes = [vp, C.c_int, C.c_int]
     L.srbd_ctx_stat_rows.argtypes = [vp]
     L.srbd_ctx_stream.argtypes = [vp]
     L.srbd_ctx_stream.restype = vp

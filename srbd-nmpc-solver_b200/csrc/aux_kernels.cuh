@@ -1,0 +1,331 @@
+// aux_kernels.cuh — pack (d_ocp_qp_set_all analog), K4 (filter line search) and the FP64 peak probe.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "ipm_solve.cuh"
+#include "srbd_model.cuh"
+
+namespace srbd {
+
+// ---------------------------------------------------------------------------------------------------
+// pack: column-major hpipm-cpp OcpQp fields -> packed panel-major stage records, with the x0 embedding
+// b0 <- A0 x0 + b0, r0 <- S0 x0 + r0, nx[0] := 0, nbx[0] := 0
+// (hpipm-cpp/src/ocp_qp_ipm_solver.cpp:128-130,225,236; d_ocp_qp_set_all hpipm_d_ocp_qp.h:90 and the
+// six mask setters :124-162; upper bounds are stored negated like HPIPM's d vector).
+// One warp per (QP, stage); every store is coalesced over the dense record.
+// ---------------------------------------------------------------------------------------------------
+struct PackParams {
+  QpLayout L;
+  int B;
+  srbd_qp_host qp;  // DEVICE pointers (same shapes as the host view)
+  double *babt, *rsq, *dct, *d, *dmask, *raw0;
+  int raw0_stride;
+};
+
+__global__ void __launch_bounds__(128) pack_kernel(const PackParams p) {
+  const QpLayout& L = p.L;
+  const int lane = threadIdx.x & 31;
+  const long long it = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int S = L.N + 1;
+  if (it >= (long long)p.B * S) return;
+  const int q = (int)(it / S), k = (int)(it % S);
+  const int N = L.N, nx = L.nx, nu = L.nu;
+  const int nuk = stage_nu(L, k), nxk = stage_nx(L, k), n = nuk + nxk;
+  const size_t qN = (size_t)q * N + k, qS = (size_t)q * S + k;
+  const double* x0 = p.qp.x0 + (size_t)q * nx;
+  // ---- BAbt ----
+  if (k < N) {
+    const double* A = p.qp.A + qN * nx * nx;
+    const double* Bm = p.qp.Bm + qN * nx * nu;
+    const double* b = p.qp.b + qN * nx;
+    double* dst = p.babt + qN * L.babt_stride;
+    const int cn = L.babt_cn;
+    for (int e = lane; e < L.babt_stride; e += 32) {
+      const int pnl = e / (4 * cn), rem = e - pnl * 4 * cn;
+      const int j = rem >> 2, i = 4 * pnl + (rem & 3);
+      double v = 0.0;
+      if (j < nx) {
+        if (i < nuk) v = Bm[j + nx * i];
+        else if (i < n) v = A[j + nx * (i - nuk)];
+        else if (i == n) {
+          v = b[j];
+          if (k == 0) {
+            double s = 0.0;
+            for (int l = 0; l < nx; ++l) s += A[j + nx * l] * x0[l];
+            v = s + b[j];
+          }
+        }
+      }
+      dst[e] = v;
+    }
+  }
+  // ---- RSQrq ----
+  {
+    const double* Q = p.qp.Q + qS * nx * nx;
+    const double* qq = p.qp.q + qS * nx;
+    const double* R = k < N ? p.qp.R + qN * nu * nu : nullptr;
+    const double* r = k < N ? p.qp.r + qN * nu : nullptr;
+    const double* Sm = (k < N && p.qp.S) ? p.qp.S + qN * nu * nx : nullptr;
+    double* dst = p.rsq + qS * L.rsq_stride;
+    const int cn = L.rsq_cn;
+    for (int e = lane; e < L.rsq_stride; e += 32) {
+      const int pnl = e / (4 * cn), rem = e - pnl * 4 * cn;
+      const int j = rem >> 2, i = 4 * pnl + (rem & 3);
+      double v = 0.0;
+      if (j < n) {
+        if (i < n) {
+          if (i < nuk && j < nuk) v = R[i + nu * j];
+          else if (i >= nuk && j >= nuk) v = Q[(i - nuk) + nx * (j - nuk)];
+          else if (Sm) v = (i >= nuk) ? Sm[j + nu * (i - nuk)] : Sm[i + nu * (j - nuk)];
+        } else if (i == n) {
+          if (j < nuk) {
+            v = r[j];
+            if (k == 0 && Sm) {
+              double s = 0.0;
+              for (int l = 0; l < nx; ++l) s += Sm[j + nu * l] * x0[l];
+              v = s + r[j];
+            }
+          } else {
+            v = qq[j - nuk];
+          }
+        }
+      }
+      dst[e] = v;
+    }
+  }
+  // ---- DCt, d, masks ----
+  {
+    const int nbu = k < N ? L.nbu : 0, nbx = k > 0 ? L.nbx : 0, nb = nbu + nbx;
+    const int ng = stage_ng(L, k);
+    double* dst = p.dct + qS * L.dct_stride;
+    const int cn = L.dct_cn;
+    const double* Dm = (k < N && ng > 0) ? p.qp.D + qN * L.ng * nu : nullptr;
+    const double* Cm = nullptr;
+    int ldc = L.ng;
+    if (ng > 0) {
+      if (k < N) Cm = (k > 0 && p.qp.C) ? p.qp.C + qN * L.ng * nx : nullptr;  // C0 is dropped (nx[0] := 0)
+      else { Cm = p.qp.CN + (size_t)q * L.ngN * nx; ldc = L.ngN; }
+    }
+    for (int e = lane; e < L.dct_stride; e += 32) {
+      const int pnl = e / (4 * cn), rem = e - pnl * 4 * cn;
+      const int g = rem >> 2, i = 4 * pnl + (rem & 3);
+      double v = 0.0;
+      if (g < ng && i < n) {
+        if (i < nuk) v = Dm ? Dm[g + L.ng * i] : 0.0;
+        else v = Cm ? Cm[g + ldc * (i - nuk)] : 0.0;
+      }
+      dst[e] = v;
+    }
+    double* dv = p.d + qS * L.d_stride;
+    double* dk = p.dmask + qS * L.d_stride;
+    for (int e = lane; e < L.d_stride; e += 32) {
+      const bool lower = e < L.ncm;
+      const int j = lower ? e : e - L.ncm;
+      double v = 0.0, m = 0.0;
+      if (j < nb + ng) {
+        const double *lo, *up, *ml, *mu;
+        size_t o;
+        if (j < nbu) { o = qN * L.nbu + j; lo = p.qp.lbu; up = p.qp.ubu; ml = p.qp.lbu_mask; mu = p.qp.ubu_mask; }
+        else if (j < nb) { o = qS * L.nbx + (j - nbu); lo = p.qp.lbx; up = p.qp.ubx; ml = p.qp.lbx_mask; mu = p.qp.ubx_mask; }
+        else if (k < N) { o = qN * L.ng + (j - nb); lo = p.qp.lg; up = p.qp.ug; ml = p.qp.lg_mask; mu = p.qp.ug_mask; }
+        else { o = (size_t)q * L.ngN + (j - nb); lo = p.qp.lgN; up = p.qp.ugN; ml = p.qp.lgN_mask; mu = p.qp.ugN_mask; }
+        v = lower ? lo[o] : -up[o];
+        const double* mk = lower ? ml : mu;
+        m = mk ? (mk[o] != 0.0 ? 1.0 : 0.0) : 1.0;
+      }
+      dv[e] = v;
+      dk[e] = m;
+    }
+  }
+  // ---- raw stage-0 blocks for the facade's stage-0 reconstruction ----
+  if (k == 0) {
+    double* raw = p.raw0 + (size_t)q * p.raw0_stride;
+    const int oA = 0, oB = nx * nx, ob = oB + nx * nu, oS = ob + nx, oQ = oS + nu * nx, oq = oQ + nx * nx;
+    const size_t q0N = (size_t)q * N, q0S = (size_t)q * S;
+    for (int e = lane; e < nx * nx; e += 32) { raw[oA + e] = p.qp.A[q0N * nx * nx + e]; raw[oQ + e] = p.qp.Q[q0S * nx * nx + e]; }
+    for (int e = lane; e < nx * nu; e += 32) {
+      raw[oB + e] = p.qp.Bm[q0N * nx * nu + e];
+      raw[oS + e] = p.qp.S ? p.qp.S[q0N * nu * nx + e] : 0.0;
+    }
+    for (int e = lane; e < nx; e += 32) { raw[ob + e] = p.qp.b[q0N * nx + e]; raw[oq + e] = p.qp.q[q0S * nx + e]; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K4: filter line search (NMPCSolver::linearSearch, NMPC_solver.cpp:149-274).  One warp per QP, one
+// lane per stage (strided for N+1 > 32); merit / violation / directional derivative are warp sums.
+// alpha is carried per QP across calls exactly like the member alpha_ (NMPC_solver.h:104).
+// ---------------------------------------------------------------------------------------------------
+struct LsParams {
+  int B, N;
+  double* x;             // [B][N+1][12] in/out
+  double* u;             // [B][N][12]   in/out
+  const double* xref;
+  const uint8_t* contact;
+  const double* dx;      // QP solution x [B][N+1][12]
+  const double* du;      // [B][N][12]
+  double* alpha;         // [B]
+  int* converged;        // [B]
+  double* merit;         // [B][3] phi, dphi, theta
+};
+
+// phi / theta (and optionally the cost gradient dotted with the step) of one stage at (x + a dx, u + a du)
+__device__ __forceinline__ void stage_merit(const srbd_model_params& m, const double* Ac, const LsParams& p, int q,
+                                            int k, double a, double& phi, double& theta, double* dphi) {
+  const int N = p.N;
+  double x[12], e[12];
+  const size_t ox = ((size_t)q * (N + 1) + k) * 12;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    x[i] = p.x[ox + i] + a * p.dx[ox + i];
+    e[i] = x[i] - p.xref[ox + i];
+  }
+  if (k == N) {
+    double s = 0.0, dd = 0.0;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      s += e[i] * (m.Qf[i] * e[i]);
+      dd += p.dx[ox + i] * (m.Qf[i] * e[i]);
+    }
+    phi += 0.5 * s;
+    if (dphi) *dphi += dd;
+    return;
+  }
+  double xn[12], u[12];
+  const size_t ou = ((size_t)q * N + k) * 12;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    xn[i] = p.x[ox + 12 + i] + a * p.dx[ox + 12 + i];
+    u[i] = p.u[ou + i] + a * p.du[ou + i];
+  }
+  double k1[12], k2[12], k3[12], k4[12], xt[12];
+  const double dt = m.dt;
+  srbd_f(m, x, u, k1, nullptr, nullptr, nullptr, nullptr);
+#pragma unroll
+  for (int i = 0; i < 12; ++i) xt[i] = x[i] + (0.5 * dt) * k1[i];
+  srbd_f(m, xt, u, k2, nullptr, nullptr, nullptr, nullptr);
+#pragma unroll
+  for (int i = 0; i < 12; ++i) xt[i] = x[i] + (0.5 * dt) * k2[i];
+  srbd_f(m, xt, u, k3, nullptr, nullptr, nullptr, nullptr);
+#pragma unroll
+  for (int i = 0; i < 12; ++i) xt[i] = x[i] + dt * k3[i];
+  srbd_f(m, xt, u, k4, nullptr, nullptr, nullptr, nullptr);
+  double ss = 0.0, s = 0.0, dd = 0.0;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    const double xg = x[i] + (dt / 6.0) * (((k1[i] + 2.0 * k2[i]) + 2.0 * k3[i]) + k4[i]);
+    const double f = xn[i] - xg;
+    ss += f * f;
+    s += e[i] * (m.Q[i] * e[i]);
+    dd += p.dx[ox + i] * (m.Q[i] * e[i]);
+  }
+  theta += 0.5 * ss;
+  phi += 0.5 * s;
+  double bsum = 0.0, Ju[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) Ju[i] = 0.0;
+  for (int g = 0; g < 24; ++g) {
+    double v = 0.0;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) v += Ac[g * 12 + j] * u[j];
+    const int leg = g / 12, rr = g % 12;
+    if (rr == 4) v += (p.contact ? (int)p.contact[((size_t)q * N + k) * 2 + leg] : 1) ? m.fmax : m.swing_fmax;
+    else if (rr == 5) v += -m.fmin;
+    double b, db;
+    if (v > m.theta_b) {
+      b = -m.mu_b * log(v);
+      db = -m.mu_b / v;
+    } else {
+      const double t = (v - 2.0 * m.theta_b) / m.theta_b;
+      b = 0.5 * m.mu_b * (t * t - 1.0) - m.mu_b * log(m.theta_b);
+      db = m.mu_b * (v - 2.0 * m.theta_b) / (m.theta_b * m.theta_b);
+    }
+    bsum += b;
+    if (dphi) {
+#pragma unroll
+      for (int j = 0; j < 12; ++j) Ju[j] += Ac[g * 12 + j] * db;
+    }
+  }
+  double uu = 0.0;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) uu += u[i] * (m.R * u[i]);
+  phi += bsum + 0.5 * uu;
+  if (dphi) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) t += p.du[ou + i] * (Ju[i] + m.R * u[i]);
+    *dphi += dd + t;
+  }
+}
+
+__global__ void __launch_bounds__(128) line_search_kernel(const LsParams p, const ModelDev* __restrict__ md) {
+  __shared__ srbd_model_params sm;
+  __shared__ double sAc[288];
+  {
+    const int nw = sizeof(srbd_model_params) / sizeof(double);
+    const double* src = reinterpret_cast<const double*>(&md->m);
+    double* dst = reinterpret_cast<double*>(&sm);
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
+    for (int i = threadIdx.x; i < 288; i += blockDim.x) sAc[i] = md->Ac[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (q >= p.B) return;
+  const int N = p.N;
+  const double theta_max = 1e-6, theta_min = 5e-10, eta = 1e-4, byta_phi = 1e-6, byta_theta = 1e-6,
+               byta_alpha = 0.5, alpha_min = 1e-4;  // NMPC_solver.h:97-103
+  double phi = 0.0, theta = 0.0, dphi = 0.0;
+  for (int k = lane; k <= N; k += 32) stage_merit(sm, sAc, p, q, k, 0.0, phi, theta, &dphi);
+  phi = warp_sum(phi); theta = warp_sum(theta); dphi = warp_sum(dphi);
+  double alpha = p.alpha[q];
+  while (alpha > alpha_min) {
+    double phi_a = 0.0, theta_a = 0.0;
+    for (int k = lane; k <= N; k += 32) stage_merit(sm, sAc, p, q, k, alpha, phi_a, theta_a, nullptr);
+    phi_a = warp_sum(phi_a); theta_a = warp_sum(theta_a);
+    bool accept = false;
+    if (theta_a > theta_max) {
+      accept = theta_a < (1.0 - byta_theta) * theta;
+    } else if ((fmax(theta_a, theta) < theta_min) && (dphi < 0.0)) {
+      accept = phi_a < phi + eta * alpha * dphi;
+    } else {
+      accept = (phi_a < phi - byta_phi * theta) || (theta_a < (1.0 - byta_theta) * theta);
+    }
+    if (accept) {
+      for (int e = lane; e < (N + 1) * 12; e += 32) {
+        const size_t o = (size_t)q * (N + 1) * 12 + e;
+        p.x[o] = p.x[o] + alpha * p.dx[o];
+      }
+      for (int e = lane; e < N * 12; e += 32) {
+        const size_t o = (size_t)q * N * 12 + e;
+        p.u[o] = p.u[o] + alpha * p.du[o];
+      }
+      break;
+    }
+    alpha = byta_alpha * alpha;
+  }
+  if (lane == 0) {
+    p.alpha[q] = alpha;
+    p.converged[q] = (dphi > -1e-3 && theta < 1e-6) ? 1 : 0;  // NMPC_solver.cpp:267
+    p.merit[3 * (size_t)q + 0] = phi;
+    p.merit[3 * (size_t)q + 1] = dphi;
+    p.merit[3 * (size_t)q + 2] = theta;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// FP64 FMA peak probe (the roofline denominator MEASURED_PEAKS.json does not carry):
+// 8 independent DFMA chains per thread, enough resident warps to saturate the FP64 pipe.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double seed) {
+  double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace srbd

@@ -1,0 +1,706 @@
+// capi.cu — the C-ABI of include/srbd_b200.h over the sm_100a kernels.  No CPU fallback: without a
+// usable CUDA device every compute entry point fails with SRBD_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "aux_kernels.cuh"
+#include "ipm_solve.cuh"
+#include "srbd_model.cuh"
+
+using namespace srbd;
+
+struct srbd_ctx {
+  int device = 0, B = 0;
+  srbd_qp_dims dims{};
+  QpLayout L{};
+  bool is_srbd = false;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  srbd_model_params model{};
+  srbd_ipm_args args{};
+  ModelDev* d_model = nullptr;
+  // NMPC level
+  double *d_x = nullptr, *d_u = nullptr, *d_xref = nullptr, *d_x0abs = nullptr, *d_defect = nullptr;
+  uint8_t* d_contact = nullptr;
+  bool have_contact = false;
+  double* d_alpha = nullptr; int* d_conv = nullptr; double* d_merit = nullptr;
+  // packed QP
+  double *d_babt = nullptr, *d_rsq = nullptr, *d_dct = nullptr, *d_d = nullptr, *d_dmask = nullptr, *d_raw0 = nullptr;
+  double* d_x0 = nullptr;  // [B][nx] QP-level initial state (delta form on the NMPC path)
+  double *d_xinit = nullptr, *d_uinit = nullptr;
+  bool have_init = false, packed = false, solved = false;
+  // raw QP-level staging (lazy)
+  std::vector<void*> raw_dev;
+  srbd_qp_host d_qp{};
+  bool raw_alloc = false;
+  // outputs
+  double *d_sol_x = nullptr, *d_sol_u = nullptr, *d_sol_pi = nullptr, *d_sol_lam = nullptr, *d_sol_t = nullptr;
+  double *d_P = nullptr, *d_p = nullptr, *d_K = nullptr, *d_k = nullptr, *d_stat = nullptr;
+  int *d_iter = nullptr, *d_status = nullptr, *d_counter = nullptr;
+  double* d_resmax = nullptr;
+  srbd_batch_stats* d_bstats = nullptr;
+  double* d_ws = nullptr;
+  int grid = 0, stat_rows = 0;
+  bool export_ric = false, export_stat = false;
+  long long launches = 0;
+  std::string err;
+  int sm_count = 0;
+};
+
+namespace {
+
+int fail(srbd_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(ctx, SRBD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+  } while (0)
+
+template <class T>
+cudaError_t dalloc(T** p, size_t n) {
+  return cudaMalloc(reinterpret_cast<void**>(p), (n ? n : 1) * sizeof(T));
+}
+
+void fill_Ac(const srbd_model_params& m, double* Ac) {  // SRBD_model.cpp:244-255, row-major [g][j]
+  std::memset(Ac, 0, sizeof(double) * 288);
+  for (int leg = 0; leg < 2; ++leg) {
+    const double* Rf = m.foot_rot + 9 * leg;
+    const double *cx = Rf, *cy = Rf + 3, *cz = Rf + 6;
+    auto A = [&](int i, int j) -> double& { return Ac[(12 * leg + i) * 12 + 6 * leg + j]; };
+    A(0, 0) = -1; A(0, 2) = m.mu;
+    A(1, 1) = -1; A(1, 2) = m.mu;
+    A(2, 0) = 1;  A(2, 2) = m.mu;
+    A(3, 1) = 1;  A(3, 2) = m.mu;
+    A(4, 2) = -1;
+    A(5, 2) = 1;
+    for (int j = 0; j < 3; ++j) {
+      A(6, j) = m.Lfx * cz[j];  A(6, 3 + j) = -cy[j];
+      A(7, j) = m.Lfx * cz[j];  A(7, 3 + j) = cy[j];
+      A(8, j) = m.Lfz * cz[j];  A(8, 3 + j) = -cz[j];
+      A(9, j) = m.Lfz * cz[j];  A(9, 3 + j) = cz[j];
+      A(10, 3 + j) = -cx[j];
+      A(11, 3 + j) = cx[j];
+    }
+  }
+}
+
+typedef void (*ipm_kernel_t)(const IpmParams);
+struct KernelChoice {
+  ipm_kernel_t fn;
+  const char* name;
+};
+using SrbdDims = SDims<12, 12, 0, 0, 24, 0>;
+using QuadDims = SDims<12, 4, 3, 4, 0, 0>;
+using Rnd0Dims = SDims<5, 3, 0, 0, 0, 0>;
+using Rnd1Dims = SDims<5, 3, 2, 3, 2, 2>;
+
+KernelChoice pick_kernel(const QpLayout& L) {
+  if (SrbdDims::matches(L)) return {ipm_solve_kernel<SrbdDims>, "srbd"};
+  if (QuadDims::matches(L)) return {ipm_solve_kernel<QuadDims>, "quadcopter"};
+  if (Rnd0Dims::matches(L)) return {ipm_solve_kernel<Rnd0Dims>, "rnd0"};
+  if (Rnd1Dims::matches(L)) return {ipm_solve_kernel<Rnd1Dims>, "rnd1"};
+  return {ipm_solve_kernel<DDims>, "dynamic"};
+}
+
+int raw0_stride(const QpLayout& L) { return 2 * L.nx * L.nx + 2 * L.nx * L.nu + 2 * L.nx; }
+
+}  // namespace
+
+extern "C" {
+
+void srbd_model_params_default(srbd_model_params* p, int horizon) {
+  std::memset(p, 0, sizeof(*p));
+  p->mass = 15.0;                                           // NMPC_solver.cpp:334
+  p->dt = 0.015;                                            // config/mpc_option.yaml:5
+  const double Ib[3] = {0.541667, 0.516667, 1.0416667};     // mpc_option.yaml:10 (stored inverted, SRBD_model.cpp:46-49)
+  for (int i = 0; i < 3; ++i) p->inertia_inv[i + 3 * i] = 1.0 / Ib[i];
+  p->foot_pos[1] = -0.1;                                    // NMPC_solver.cpp:337
+  p->foot_pos[4] = 0.1;
+  for (int leg = 0; leg < 2; ++leg)
+    for (int i = 0; i < 3; ++i) p->foot_rot[9 * leg + i + 3 * i] = 1.0;
+  p->mu = 0.5; p->Lfx = 0.05; p->Lfz = 0.05; p->fmax = 1000.0; p->fmin = 0.0;  // SRBD_model.cpp:13-17
+  p->gravity[2] = -9.8;                                     // SRBD_model.cpp:98
+  p->Q[11] = 10.0;                                          // mpc_option.yaml:2
+  const double Qf[12] = {0.5, 0.5, 0.5, 0.01, 0.01, 0.01, 100, 100, 100, 0.0, 0.0, 100};
+  for (int i = 0; i < 12; ++i) p->Qf[i] = (double)horizon * Qf[i];  // NMPC_solver.cpp:58
+  p->R = 1e-4;
+  p->mu_b = 0.1; p->theta_b = 5.0;
+  p->swing_fmax = 1.0;
+}
+
+void srbd_ipm_args_default(srbd_ipm_args* a) {
+  std::memset(a, 0, sizeof(*a));
+  a->iter_max = 15; a->alpha_min = 1e-8; a->mu0 = 1e2;     // ocp_qp_ipm_solver_settings.hpp:26-86
+  a->tol_stat = a->tol_eq = a->tol_ineq = a->tol_comp = 1e-8;
+  a->reg_prim = 1e-12; a->warm_start = 0; a->pred_corr = 1; a->ric_alg = 1; a->split_step = 0;
+  a->cond_pred_corr = 1; a->cond_factor = 2.0; a->thr0 = 0.1;  // HPIPM SPEED-mode hidden defaults
+  a->lam_min = a->t_min = a->tau_min = 1e-16; a->t_lam_min = 2; a->alpha_shorten = 1;
+}
+
+size_t srbd_qp_nct(const srbd_qp_dims* d) {
+  size_t n = 0;
+  for (int k = 0; k <= d->N; ++k) {
+    const int nb = (k < d->N ? d->nbu : 0) + (k > 0 ? d->nbx : 0);
+    const int ng = k < d->N ? d->ng : d->ngN;
+    n += 2 * (size_t)(nb + ng);
+  }
+  return n;
+}
+
+const char* srbd_last_error(const srbd_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int srbd_ctx_create(int device, int batch, const srbd_qp_dims* dims, void* stream, srbd_ctx** out) {
+  if (!out || !dims || batch < 1) return SRBD_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || device < 0 || device >= ndev) return SRBD_ERR_CUDA;
+  srbd_ctx* ctx = new srbd_ctx();
+  ctx->device = device;
+  ctx->B = batch;
+  ctx->dims = *dims;
+  if (make_layout(*dims, nullptr, nullptr, &ctx->L) != 0) { delete ctx; return SRBD_ERR_ARG; }
+  ctx->is_srbd = dims->nx == 12 && dims->nu == 12 && dims->ng == 24 && dims->nbx == 0 && dims->nbu == 0 && dims->ngN == 0;
+  auto bail = [&](int code) { srbd_ctx_destroy(ctx); return code; };
+  if (cudaSetDevice(device) != cudaSuccess) return bail(SRBD_ERR_CUDA);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(SRBD_ERR_CUDA);
+  ctx->sm_count = prop.multiProcessorCount;
+  if (stream) ctx->stream = (cudaStream_t)stream;
+  else {
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(SRBD_ERR_CUDA);
+    ctx->own_stream = true;
+  }
+  const QpLayout& L = ctx->L;
+  const size_t B = batch, S = L.N + 1, N = L.N;
+  bool ok = true;
+  auto A = [&](cudaError_t e) { ok = ok && (e == cudaSuccess); };
+  A(dalloc(&ctx->d_model, 1));
+  if (ctx->is_srbd) {
+    A(dalloc(&ctx->d_x, B * S * 12)); A(dalloc(&ctx->d_u, B * N * 12)); A(dalloc(&ctx->d_xref, B * S * 12));
+    A(dalloc(&ctx->d_x0abs, B * 12)); A(dalloc(&ctx->d_defect, B * N * 12)); A(dalloc(&ctx->d_contact, B * N * 2));
+    A(dalloc(&ctx->d_alpha, B)); A(dalloc(&ctx->d_conv, B)); A(dalloc(&ctx->d_merit, B * 3));
+  }
+  A(dalloc(&ctx->d_babt, B * N * L.babt_stride)); A(dalloc(&ctx->d_rsq, B * S * L.rsq_stride));
+  A(dalloc(&ctx->d_dct, B * S * L.dct_stride)); A(dalloc(&ctx->d_d, B * S * L.d_stride));
+  A(dalloc(&ctx->d_dmask, B * S * L.d_stride)); A(dalloc(&ctx->d_raw0, B * raw0_stride(L)));
+  A(dalloc(&ctx->d_x0, B * L.nx)); A(dalloc(&ctx->d_xinit, B * S * L.nx)); A(dalloc(&ctx->d_uinit, B * N * L.nu));
+  A(dalloc(&ctx->d_sol_x, B * S * L.nx)); A(dalloc(&ctx->d_sol_u, B * N * L.nu)); A(dalloc(&ctx->d_sol_pi, B * S * L.nx));
+  A(dalloc(&ctx->d_sol_lam, B * (size_t)L.nct)); A(dalloc(&ctx->d_sol_t, B * (size_t)L.nct));
+  A(dalloc(&ctx->d_iter, B)); A(dalloc(&ctx->d_status, B)); A(dalloc(&ctx->d_resmax, B * 4));
+  A(dalloc(&ctx->d_counter, 1)); A(dalloc(&ctx->d_bstats, 1));
+  if (!ok) return bail(SRBD_ERR_CUDA);
+  // persistent grid: every resident warp gets a private workspace
+  KernelChoice kc = pick_kernel(L);
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kc.fn, 32, 0) != cudaSuccess || occ < 1) return bail(SRBD_ERR_CUDA);
+  long long g = (long long)occ * ctx->sm_count;
+  if (g > batch) g = batch;
+  ctx->grid = (int)g;
+  if (dalloc(&ctx->d_ws, (size_t)ctx->grid * L.ws_size) != cudaSuccess) return bail(SRBD_ERR_CUDA);
+  if (cudaMemsetAsync(ctx->d_sol_pi, 0, B * S * L.nx * sizeof(double), ctx->stream) != cudaSuccess) return bail(SRBD_ERR_CUDA);
+  srbd_model_params mp;
+  srbd_model_params_default(&mp, L.N);
+  srbd_ipm_args ia;
+  srbd_ipm_args_default(&ia);
+  ctx->args = ia;
+  ctx->stat_rows = ia.iter_max + 2;
+  if (srbd_set_model(ctx, &mp) != 0) return bail(SRBD_ERR_CUDA);
+  if (ctx->is_srbd) {
+    std::vector<double> ones(B, 1.0);
+    if (cudaMemcpyAsync(ctx->d_alpha, ones.data(), B * sizeof(double), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+        cudaMemsetAsync(ctx->d_conv, 0, B * sizeof(int), ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+      return bail(SRBD_ERR_CUDA);
+  }
+  *out = ctx;
+  return SRBD_OK;
+}
+
+int srbd_ctx_destroy(srbd_ctx* ctx) {
+  if (!ctx) return SRBD_OK;
+  cudaSetDevice(ctx->device);
+  void* ptrs[] = {ctx->d_model, ctx->d_x, ctx->d_u, ctx->d_xref, ctx->d_x0abs, ctx->d_defect, ctx->d_contact,
+                  ctx->d_alpha, ctx->d_conv, ctx->d_merit, ctx->d_babt, ctx->d_rsq, ctx->d_dct, ctx->d_d,
+                  ctx->d_dmask, ctx->d_raw0, ctx->d_x0, ctx->d_xinit, ctx->d_uinit, ctx->d_sol_x, ctx->d_sol_u,
+                  ctx->d_sol_pi, ctx->d_sol_lam, ctx->d_sol_t, ctx->d_P, ctx->d_p, ctx->d_K, ctx->d_k,
+                  ctx->d_stat, ctx->d_iter, ctx->d_status, ctx->d_counter, ctx->d_resmax, ctx->d_bstats, ctx->d_ws};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  for (void* p : ctx->raw_dev)
+    if (p) cudaFree(p);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return SRBD_OK;
+}
+
+int srbd_set_model(srbd_ctx* ctx, const srbd_model_params* p) {
+  if (!ctx || !p) return SRBD_ERR_ARG;
+  ctx->model = *p;
+  ModelDev md;
+  md.m = *p;
+  fill_Ac(*p, md.Ac);
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(ctx->d_model, &md, sizeof(md), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SRBD_OK;
+}
+
+int srbd_set_ipm_args(srbd_ctx* ctx, const srbd_ipm_args* a) {
+  if (!ctx || !a) return SRBD_ERR_ARG;
+  if (a->iter_max < 0 || a->iter_max > 1000) return fail(ctx, SRBD_ERR_ARG, "iter_max out of range");
+  if (a->ric_alg != 0)
+    return fail(ctx, SRBD_ERR_UNSUPPORTED,
+                "ric_alg=1 (square-root Riccati) is not implemented on the GPU path yet; use ric_alg=0 "
+                "(classical, what NMPC_solver.cpp:81 selects)");
+  ctx->args = *a;
+  const int rows = a->iter_max + 2;
+  if (rows != ctx->stat_rows) {
+    ctx->stat_rows = rows;
+    if (ctx->d_stat) { cudaFree(ctx->d_stat); ctx->d_stat = nullptr; }
+  }
+  return SRBD_OK;
+}
+
+int srbd_set_outputs(srbd_ctx* ctx, int export_ric, int export_stat) {
+  if (!ctx) return SRBD_ERR_ARG;
+  ctx->export_ric = export_ric != 0;
+  ctx->export_stat = export_stat != 0;
+  return SRBD_OK;
+}
+
+int srbd_ctx_stat_rows(const srbd_ctx* ctx) { return ctx ? ctx->stat_rows : 0; }
+void* srbd_ctx_stream(const srbd_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+long long srbd_ctx_launch_count(const srbd_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int srbd_ctx_sync(srbd_ctx* ctx) {
+  if (!ctx) return SRBD_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SRBD_OK;
+}
+
+int srbd_ctx_device_ptr(srbd_ctx* ctx, int buf, void** ptr, size_t* bytes) {
+  if (!ctx || !ptr || !bytes) return SRBD_ERR_ARG;
+  const QpLayout& L = ctx->L;
+  const size_t B = ctx->B, S = L.N + 1, N = L.N, D = sizeof(double);
+  void* p = nullptr;
+  size_t n = 0;
+  switch (buf) {
+    case SRBD_BUF_TRAJ_X: p = ctx->d_x; n = B * S * 12 * D; break;
+    case SRBD_BUF_TRAJ_U: p = ctx->d_u; n = B * N * 12 * D; break;
+    case SRBD_BUF_TRAJ_XREF: p = ctx->d_xref; n = B * S * 12 * D; break;
+    case SRBD_BUF_X0: p = ctx->d_x0abs; n = B * 12 * D; break;
+    case SRBD_BUF_CONTACT: p = ctx->d_contact; n = B * N * 2; break;
+    case SRBD_BUF_SOL_X: p = ctx->d_sol_x; n = B * S * L.nx * D; break;
+    case SRBD_BUF_SOL_U: p = ctx->d_sol_u; n = B * N * L.nu * D; break;
+    case SRBD_BUF_SOL_PI: p = ctx->d_sol_pi; n = B * S * L.nx * D; break;
+    case SRBD_BUF_SOL_LAM: p = ctx->d_sol_lam; n = B * (size_t)L.nct * D; break;
+    case SRBD_BUF_SOL_T: p = ctx->d_sol_t; n = B * (size_t)L.nct * D; break;
+    case SRBD_BUF_ITER: p = ctx->d_iter; n = B * sizeof(int); break;
+    case SRBD_BUF_STATUS: p = ctx->d_status; n = B * sizeof(int); break;
+    case SRBD_BUF_RESMAX: p = ctx->d_resmax; n = B * 4 * D; break;
+    case SRBD_BUF_BABT: p = ctx->d_babt; n = B * N * L.babt_stride * D; break;
+    case SRBD_BUF_RSQRQ: p = ctx->d_rsq; n = B * S * L.rsq_stride * D; break;
+    case SRBD_BUF_DCT: p = ctx->d_dct; n = B * S * L.dct_stride * D; break;
+    case SRBD_BUF_D: p = ctx->d_d; n = B * S * L.d_stride * D; break;
+    case SRBD_BUF_DMASK: p = ctx->d_dmask; n = B * S * L.d_stride * D; break;
+    case SRBD_BUF_DEFECT: p = ctx->d_defect; n = B * N * 12 * D; break;
+    default: return fail(ctx, SRBD_ERR_ARG, "unknown buffer id");
+  }
+  if (!p) return fail(ctx, SRBD_ERR_STATE, "buffer not allocated for these dimensions");
+  *ptr = p;
+  *bytes = n;
+  return SRBD_OK;
+}
+
+// ---- NMPC level ----------------------------------------------------------------------------------
+static int require_srbd(srbd_ctx* ctx) {
+  if (!ctx) return SRBD_ERR_ARG;
+  if (!ctx->is_srbd) return fail(ctx, SRBD_ERR_ARG, "NMPC-level calls need nx=nu=12, ng=24, no box constraints");
+  return SRBD_OK;
+}
+
+int srbd_upload_traj(srbd_ctx* ctx, const double* x, const double* u, const double* xref, const double* x0,
+                     const uint8_t* contact) {
+  if (int rc = require_srbd(ctx)) return rc;
+  if (!x || !u || !xref || !x0) return fail(ctx, SRBD_ERR_ARG, "null trajectory pointer");
+  const size_t B = ctx->B, S = ctx->L.N + 1, N = ctx->L.N, D = sizeof(double);
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(ctx->d_x, x, B * S * 12 * D, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_u, u, B * N * 12 * D, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_xref, xref, B * S * 12 * D, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_x0abs, x0, B * 12 * D, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->have_contact = contact != nullptr;
+  if (contact) CU(cudaMemcpyAsync(ctx->d_contact, contact, B * N * 2, cudaMemcpyHostToDevice, ctx->stream));
+  return SRBD_OK;
+}
+
+int srbd_download_traj(srbd_ctx* ctx, double* x, double* u) {
+  if (int rc = require_srbd(ctx)) return rc;
+  const size_t B = ctx->B, S = ctx->L.N + 1, N = ctx->L.N, D = sizeof(double);
+  CU(cudaSetDevice(ctx->device));
+  if (x) CU(cudaMemcpyAsync(x, ctx->d_x, B * S * 12 * D, cudaMemcpyDeviceToHost, ctx->stream));
+  if (u) CU(cudaMemcpyAsync(u, ctx->d_u, B * N * 12 * D, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SRBD_OK;
+}
+
+int srbd_linearize(srbd_ctx* ctx) {
+  if (int rc = require_srbd(ctx)) return rc;
+  CU(cudaSetDevice(ctx->device));
+  LinParams p{};
+  p.B = ctx->B; p.N = ctx->L.N;
+  p.x = ctx->d_x; p.u = ctx->d_u; p.x0 = ctx->d_x0abs;
+  p.babt = ctx->d_babt; p.defect = ctx->d_defect; p.raw0 = ctx->d_raw0; p.dx0 = ctx->d_x0;
+  const long long total = (long long)p.B * p.N;
+  const int grid = (int)((total + kLinThreads - 1) / kLinThreads);
+  linearize_kernel<<<grid, kLinThreads, 0, ctx->stream>>>(p, ctx->d_model);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return SRBD_OK;
+}
+
+int srbd_assemble(srbd_ctx* ctx, int mode) {
+  if (int rc = require_srbd(ctx)) return rc;
+  if (mode != SRBD_BARRIER_SOFT && mode != SRBD_HARD_INEQ) return fail(ctx, SRBD_ERR_ARG, "bad assemble mode");
+  CU(cudaSetDevice(ctx->device));
+  AsmParams p{};
+  p.B = ctx->B; p.N = ctx->L.N; p.mode = mode;
+  p.x = ctx->d_x; p.u = ctx->d_u; p.xref = ctx->d_xref; p.contact = ctx->have_contact ? ctx->d_contact : nullptr;
+  p.rsq = ctx->d_rsq; p.dct = ctx->d_dct; p.d = ctx->d_d; p.dmask = ctx->d_dmask; p.raw0 = ctx->d_raw0; p.fcon = nullptr;
+  const long long total = (long long)p.B * (p.N + 1);
+  const int grid = (int)((total + kAsmThreads - 1) / kAsmThreads);
+  assemble_kernel<<<grid, kAsmThreads, 0, ctx->stream>>>(p, ctx->d_model);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  ctx->packed = true;
+  ctx->have_init = false;
+  return SRBD_OK;
+}
+
+int srbd_download_linearization(srbd_ctx* ctx, double* A, double* Bm, double* b, double* defect) {
+  if (int rc = require_srbd(ctx)) return rc;
+  const QpLayout& L = ctx->L;
+  const size_t B = ctx->B, N = L.N;
+  std::vector<double> h(B * N * L.babt_stride);
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(h.data(), ctx->d_babt, h.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (defect) CU(cudaMemcpyAsync(defect, ctx->d_defect, B * N * 12 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (size_t q = 0; q < B; ++q)
+    for (size_t k = 0; k < N; ++k) {
+      const double* r = h.data() + (q * N + k) * L.babt_stride;
+      const int nuk = 12, nxk = k > 0 ? 12 : 0, n = nuk + nxk;
+      for (int j = 0; j < 12; ++j) {
+        for (int i = 0; i < 12; ++i) {
+          if (Bm) Bm[(q * N + k) * 144 + j + 12 * i] = r[pm_index(i, j, L.babt_cn)];
+          // stage 0 carries no A^T rows (nx[0] := 0): report A0 from the raw block instead (below)
+          if (A && k > 0) A[(q * N + k) * 144 + j + 12 * i] = r[pm_index(nuk + i, j, L.babt_cn)];
+        }
+        if (b) b[(q * N + k) * 12 + j] = r[pm_index(n, j, L.babt_cn)];
+      }
+    }
+  if (A || b) {  // stage 0: raw A0 and the un-embedded b0
+    std::vector<double> raw(B * kRaw0Stride);
+    CU(cudaMemcpy(raw.data(), ctx->d_raw0, raw.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (size_t q = 0; q < B; ++q) {
+      if (A) std::memcpy(A + q * N * 144, raw.data() + q * kRaw0Stride, 144 * sizeof(double));
+      if (b) std::memcpy(b + q * N * 12, raw.data() + q * kRaw0Stride + 288, 12 * sizeof(double));
+    }
+  }
+  return SRBD_OK;
+}
+
+int srbd_download_qp(srbd_ctx* ctx, double* Q, double* S, double* R, double* q, double* r, double* D, double* lg,
+                     double* lg_mask) {
+  if (int rc = require_srbd(ctx)) return rc;
+  if (!ctx->packed) return fail(ctx, SRBD_ERR_STATE, "assemble first");
+  const QpLayout& L = ctx->L;
+  const size_t B = ctx->B, N = L.N, S1 = N + 1;
+  std::vector<double> hr(B * S1 * L.rsq_stride), hd(B * S1 * L.dct_stride), hv(B * S1 * L.d_stride), hm(B * S1 * L.d_stride);
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(hr.data(), ctx->d_rsq, hr.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(hd.data(), ctx->d_dct, hd.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(hv.data(), ctx->d_d, hv.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(hm.data(), ctx->d_dmask, hm.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (size_t b = 0; b < B; ++b)
+    for (size_t k = 0; k <= N; ++k) {
+      const double* rs = hr.data() + (b * S1 + k) * L.rsq_stride;
+      const int nuk = k < N ? 12 : 0, nxk = k > 0 ? 12 : 0, n = nuk + nxk;
+      for (int j = 0; j < 12; ++j) {
+        for (int i = 0; i < 12; ++i) {
+          if (k < N && R) R[(b * N + k) * 144 + i + 12 * j] = rs[pm_index(i >= j ? i : j, i >= j ? j : i, L.rsq_cn)];
+          if (Q) {  // stage 0 has no state block in the packed record: Q0 does not enter the embedded QP
+            double v = 0.0;
+            if (nxk) v = rs[pm_index(nuk + (i >= j ? i : j), nuk + (i >= j ? j : i), L.rsq_cn)];
+            else v = (i == j) ? ctx->model.Q[i] : 0.0;
+            Q[(b * S1 + k) * 144 + i + 12 * j] = v;
+          }
+          if (k < N && S) S[(b * N + k) * 144 + i + 12 * j] = (nxk ? rs[pm_index(nuk + j, i, L.rsq_cn)] : 0.0);
+        }
+        if (k < N && r) r[(b * N + k) * 12 + j] = rs[pm_index(n, j, L.rsq_cn)];
+        if (q && nxk) q[(b * S1 + k) * 12 + j] = rs[pm_index(n, nuk + j, L.rsq_cn)];
+      }
+      if (k < N) {
+        const double* dc = hd.data() + (b * S1 + k) * L.dct_stride;
+        for (int g = 0; g < 24; ++g) {
+          for (int i = 0; i < 12; ++i)
+            if (D) D[(b * N + k) * 288 + g + 24 * i] = dc[pm_index(i, g, L.dct_cn)];
+          if (lg) lg[(b * N + k) * 24 + g] = hv[(b * S1 + k) * L.d_stride + g];
+          if (lg_mask) lg_mask[(b * N + k) * 24 + g] = hm[(b * S1 + k) * L.d_stride + g];
+        }
+      }
+    }
+  if (q) {  // q0 from the raw block
+    std::vector<double> raw(B * kRaw0Stride);
+    CU(cudaMemcpy(raw.data(), ctx->d_raw0, raw.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (size_t b = 0; b < B; ++b) std::memcpy(q + b * S1 * 12, raw.data() + b * kRaw0Stride + 588, 12 * sizeof(double));
+  }
+  return SRBD_OK;
+}
+
+// ---- QP level -------------------------------------------------------------------------------------
+int srbd_qp_upload(srbd_ctx* ctx, const srbd_qp_host* qp) {
+  if (!ctx || !qp) return SRBD_ERR_ARG;
+  const QpLayout& L0 = ctx->L;
+  const srbd_qp_dims& d = ctx->dims;
+  if (!qp->A || !qp->Bm || !qp->b || !qp->Q || !qp->R || !qp->q || !qp->r || !qp->x0)
+    return fail(ctx, SRBD_ERR_ARG, "A, B, b, Q, R, q, r and x0 are required");
+  if (d.nbx > 0 && (!qp->idxbx || !qp->lbx || !qp->ubx)) return fail(ctx, SRBD_ERR_ARG, "nbx > 0 needs idxbx, lbx, ubx");
+  if (d.nbu > 0 && (!qp->idxbu || !qp->lbu || !qp->ubu)) return fail(ctx, SRBD_ERR_ARG, "nbu > 0 needs idxbu, lbu, ubu");
+  if (d.ng > 0 && (!qp->D || !qp->lg || !qp->ug)) return fail(ctx, SRBD_ERR_ARG, "ng > 0 needs D, lg, ug");
+  if (d.ngN > 0 && (!qp->CN || !qp->lgN || !qp->ugN)) return fail(ctx, SRBD_ERR_ARG, "ngN > 0 needs CN, lgN, ugN");
+  QpLayout L;
+  if (make_layout(d, qp->idxbx, qp->idxbu, &L) != 0) return fail(ctx, SRBD_ERR_ARG, "bad idxbx / idxbu");
+  ctx->L = L;
+  (void)L0;
+  CU(cudaSetDevice(ctx->device));
+  const size_t B = ctx->B, N = L.N, S = N + 1, nx = L.nx, nu = L.nu;
+  struct F { const double* srbd_qp_host::*m; size_t n; };
+  const F fields[] = {
+      {&srbd_qp_host::A, B * N * nx * nx}, {&srbd_qp_host::Bm, B * N * nx * nu}, {&srbd_qp_host::b, B * N * nx},
+      {&srbd_qp_host::Q, B * S * nx * nx}, {&srbd_qp_host::S, B * N * nu * nx}, {&srbd_qp_host::R, B * N * nu * nu},
+      {&srbd_qp_host::q, B * S * nx}, {&srbd_qp_host::r, B * N * nu},
+      {&srbd_qp_host::lbx, B * S * L.nbx}, {&srbd_qp_host::ubx, B * S * L.nbx},
+      {&srbd_qp_host::lbx_mask, B * S * L.nbx}, {&srbd_qp_host::ubx_mask, B * S * L.nbx},
+      {&srbd_qp_host::lbu, B * N * L.nbu}, {&srbd_qp_host::ubu, B * N * L.nbu},
+      {&srbd_qp_host::lbu_mask, B * N * L.nbu}, {&srbd_qp_host::ubu_mask, B * N * L.nbu},
+      {&srbd_qp_host::C, B * N * L.ng * nx}, {&srbd_qp_host::D, B * N * L.ng * nu},
+      {&srbd_qp_host::lg, B * N * L.ng}, {&srbd_qp_host::ug, B * N * L.ng},
+      {&srbd_qp_host::lg_mask, B * N * L.ng}, {&srbd_qp_host::ug_mask, B * N * L.ng},
+      {&srbd_qp_host::CN, B * L.ngN * nx}, {&srbd_qp_host::lgN, B * L.ngN}, {&srbd_qp_host::ugN, B * L.ngN},
+      {&srbd_qp_host::lgN_mask, B * L.ngN}, {&srbd_qp_host::ugN_mask, B * L.ngN},
+      {&srbd_qp_host::x0, B * nx}};
+  const int nf = sizeof(fields) / sizeof(fields[0]);
+  if (!ctx->raw_alloc) {
+    ctx->raw_dev.assign(nf, nullptr);
+    for (int i = 0; i < nf; ++i)
+      if (fields[i].n) CU(cudaMalloc(&ctx->raw_dev[i], fields[i].n * sizeof(double)));
+    ctx->raw_alloc = true;
+  }
+  srbd_qp_host dq{};
+  for (int i = 0; i < nf; ++i) {
+    const double* src = qp->*(fields[i].m);
+    if (src && fields[i].n) {
+      CU(cudaMemcpyAsync(ctx->raw_dev[i], src, fields[i].n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      dq.*(fields[i].m) = (const double*)ctx->raw_dev[i];
+    }
+  }
+  CU(cudaMemcpyAsync(ctx->d_x0, qp->x0, B * nx * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->have_init = false;
+  if (qp->x_init && qp->u_init) {
+    CU(cudaMemcpyAsync(ctx->d_xinit, qp->x_init, B * S * nx * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_uinit, qp->u_init, B * N * nu * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->have_init = true;
+  }
+  PackParams p{};
+  p.L = L; p.B = ctx->B; p.qp = dq;
+  p.babt = ctx->d_babt; p.rsq = ctx->d_rsq; p.dct = ctx->d_dct; p.d = ctx->d_d; p.dmask = ctx->d_dmask;
+  p.raw0 = ctx->d_raw0; p.raw0_stride = raw0_stride(L);
+  const long long total = (long long)ctx->B * (L.N + 1);
+  pack_kernel<<<(int)((total + 3) / 4), 128, 0, ctx->stream>>>(p);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  ctx->packed = true;
+  return SRBD_OK;
+}
+
+int srbd_qp_solve(srbd_ctx* ctx) {
+  if (!ctx) return SRBD_ERR_ARG;
+  if (!ctx->packed) return fail(ctx, SRBD_ERR_STATE, "no QP data: call srbd_qp_upload or srbd_assemble first");
+  if (ctx->args.warm_start && !ctx->have_init && !ctx->is_srbd)
+    return fail(ctx, SRBD_ERR_ARG, "warm_start=1 needs x_init/u_init (qp_sol[i].x / .u must be pre-sized, "
+                                   "hpipm-cpp/src/ocp_qp_ipm_solver.cpp:190-207)");
+  CU(cudaSetDevice(ctx->device));
+  const QpLayout& L = ctx->L;
+  const size_t B = ctx->B, S = L.N + 1, N = L.N;
+  if (ctx->export_ric && !ctx->d_P) {
+    CU(dalloc(&ctx->d_P, B * S * L.nx * L.nx)); CU(dalloc(&ctx->d_p, B * S * L.nx));
+    CU(dalloc(&ctx->d_K, B * N * L.nu * L.nx)); CU(dalloc(&ctx->d_k, B * N * L.nu));
+  }
+  if (ctx->export_stat && !ctx->d_stat) CU(dalloc(&ctx->d_stat, B * (size_t)ctx->stat_rows * SRBD_STAT_M));
+  IpmParams p{};
+  p.L = L; p.a = ctx->args; p.B = ctx->B;
+  p.babt = ctx->d_babt; p.rsq = ctx->d_rsq; p.dct = ctx->d_dct; p.d = ctx->d_d; p.dmask = ctx->d_dmask;
+  p.x_init = ctx->have_init ? ctx->d_xinit : nullptr;
+  p.u_init = ctx->have_init ? ctx->d_uinit : nullptr;
+  p.x0 = ctx->d_x0; p.raw0 = ctx->d_raw0; p.ws = ctx->d_ws; p.counter = ctx->d_counter;
+  p.sol_x = ctx->d_sol_x; p.sol_u = ctx->d_sol_u; p.sol_pi = ctx->d_sol_pi; p.sol_lam = ctx->d_sol_lam; p.sol_t = ctx->d_sol_t;
+  if (ctx->export_ric) { p.ric_P = ctx->d_P; p.ric_p = ctx->d_p; p.ric_K = ctx->d_K; p.ric_k = ctx->d_k; }
+  p.iter = ctx->d_iter; p.status = ctx->d_status; p.res_max = ctx->d_resmax;
+  p.stat = ctx->export_stat ? ctx->d_stat : nullptr;
+  p.stat_rows = ctx->stat_rows;
+  p.bstats = ctx->d_bstats;
+  CU(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_bstats, 0, sizeof(srbd_batch_stats), ctx->stream));
+  KernelChoice kc = pick_kernel(L);
+  kc.fn<<<ctx->grid, 32, 0, ctx->stream>>>(p);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  ctx->solved = true;
+  return SRBD_OK;
+}
+
+int srbd_download_solution(srbd_ctx* ctx, const srbd_sol_host* sol) {
+  if (!ctx || !sol) return SRBD_ERR_ARG;
+  if (!ctx->solved) return fail(ctx, SRBD_ERR_STATE, "solve first");
+  const QpLayout& L = ctx->L;
+  const size_t B = ctx->B, S = L.N + 1, N = L.N, D = sizeof(double);
+  CU(cudaSetDevice(ctx->device));
+  auto dl = [&](double* dst, const double* src, size_t n) -> cudaError_t {
+    return dst ? cudaMemcpyAsync(dst, src, n * D, cudaMemcpyDeviceToHost, ctx->stream) : cudaSuccess;
+  };
+  if ((sol->P || sol->p || sol->K || sol->k) && !ctx->d_P)
+    return fail(ctx, SRBD_ERR_STATE, "Riccati outputs were not exported: call srbd_set_outputs(ctx, 1, ..) before the solve");
+  CU(dl(sol->x, ctx->d_sol_x, B * S * L.nx)); CU(dl(sol->u, ctx->d_sol_u, B * N * L.nu));
+  CU(dl(sol->pi, ctx->d_sol_pi, B * S * L.nx));
+  CU(dl(sol->lam, ctx->d_sol_lam, B * (size_t)L.nct)); CU(dl(sol->t, ctx->d_sol_t, B * (size_t)L.nct));
+  CU(dl(sol->P, ctx->d_P, B * S * L.nx * L.nx)); CU(dl(sol->p, ctx->d_p, B * S * L.nx));
+  CU(dl(sol->K, ctx->d_K, B * N * L.nu * L.nx)); CU(dl(sol->k, ctx->d_k, B * N * L.nu));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SRBD_OK;
+}
+
+int srbd_download_stats(srbd_ctx* ctx, const srbd_stats_host* st) {
+  if (!ctx || !st) return SRBD_ERR_ARG;
+  if (!ctx->solved) return fail(ctx, SRBD_ERR_STATE, "solve first");
+  const size_t B = ctx->B;
+  CU(cudaSetDevice(ctx->device));
+  if (st->iter) CU(cudaMemcpyAsync(st->iter, ctx->d_iter, B * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  if (st->status) CU(cudaMemcpyAsync(st->status, ctx->d_status, B * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  if (st->res_max) CU(cudaMemcpyAsync(st->res_max, ctx->d_resmax, B * 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (st->stat) {
+    if (!ctx->d_stat) return fail(ctx, SRBD_ERR_STATE, "statistics table was not exported: srbd_set_outputs(ctx, .., 1)");
+    CU(cudaMemcpyAsync(st->stat, ctx->d_stat, B * (size_t)ctx->stat_rows * SRBD_STAT_M * sizeof(double),
+                       cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SRBD_OK;
+}
+
+int srbd_batch_stats_get(srbd_ctx* ctx, srbd_batch_stats* out) {
+  if (!ctx || !out) return SRBD_ERR_ARG;
+  if (!ctx->solved) return fail(ctx, SRBD_ERR_STATE, "solve first");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(out, ctx->d_bstats, sizeof(*out), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SRBD_OK;
+}
+
+// ---- SQP level ------------------------------------------------------------------------------------
+int srbd_line_search(srbd_ctx* ctx) {
+  if (int rc = require_srbd(ctx)) return rc;
+  if (!ctx->solved) return fail(ctx, SRBD_ERR_STATE, "solve first");
+  CU(cudaSetDevice(ctx->device));
+  LsParams p{};
+  p.B = ctx->B; p.N = ctx->L.N;
+  p.x = ctx->d_x; p.u = ctx->d_u; p.xref = ctx->d_xref; p.contact = ctx->have_contact ? ctx->d_contact : nullptr;
+  p.dx = ctx->d_sol_x; p.du = ctx->d_sol_u; p.alpha = ctx->d_alpha; p.converged = ctx->d_conv; p.merit = ctx->d_merit;
+  line_search_kernel<<<(ctx->B + 3) / 4, 128, 0, ctx->stream>>>(p, ctx->d_model);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return SRBD_OK;
+}
+
+int srbd_download_sqp_state(srbd_ctx* ctx, double* alpha, int* converged, double* merit) {
+  if (int rc = require_srbd(ctx)) return rc;
+  const size_t B = ctx->B;
+  CU(cudaSetDevice(ctx->device));
+  if (alpha) CU(cudaMemcpyAsync(alpha, ctx->d_alpha, B * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (converged) CU(cudaMemcpyAsync(converged, ctx->d_conv, B * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  if (merit) CU(cudaMemcpyAsync(merit, ctx->d_merit, B * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SRBD_OK;
+}
+
+int srbd_reset_sqp_state(srbd_ctx* ctx) {
+  if (int rc = require_srbd(ctx)) return rc;
+  std::vector<double> ones(ctx->B, 1.0);
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(ctx->d_alpha, ones.data(), ones.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_conv, 0, ctx->B * sizeof(int), ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SRBD_OK;
+}
+
+int srbd_sqp_iterate(srbd_ctx* ctx, int mode, int do_line_search) {
+  if (int rc = srbd_linearize(ctx)) return rc;
+  if (int rc = srbd_assemble(ctx, mode)) return rc;
+  if (int rc = srbd_qp_solve(ctx)) return rc;
+  if (do_line_search)
+    if (int rc = srbd_line_search(ctx)) return rc;
+  return SRBD_OK;
+}
+
+int srbd_solve_host(srbd_ctx* ctx, int mode, const double* x, const double* u, const double* xref, const double* x0,
+                    const uint8_t* contact, double* sol_x, double* sol_u, int* iter, int* status) {
+  if (int rc = srbd_upload_traj(ctx, x, u, xref, x0, contact)) return rc;
+  if (int rc = srbd_sqp_iterate(ctx, mode, 0)) return rc;
+  const size_t B = ctx->B, S = ctx->L.N + 1, N = ctx->L.N, D = sizeof(double);
+  if (sol_x) CU(cudaMemcpyAsync(sol_x, ctx->d_sol_x, B * S * 12 * D, cudaMemcpyDeviceToHost, ctx->stream));
+  if (sol_u) CU(cudaMemcpyAsync(sol_u, ctx->d_sol_u, B * N * 12 * D, cudaMemcpyDeviceToHost, ctx->stream));
+  if (iter) CU(cudaMemcpyAsync(iter, ctx->d_iter, B * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  if (status) CU(cudaMemcpyAsync(status, ctx->d_status, B * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SRBD_OK;
+}
+
+int srbd_fp64_peak(srbd_ctx* ctx, double* flops_per_s) {
+  if (!ctx || !flops_per_s) return SRBD_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  const int blocks = ctx->sm_count * 8, threads = 256, iters = 20000;
+  double* d_out = nullptr;
+  CU(dalloc(&d_out, (size_t)blocks * threads));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CU(cudaEventRecord(e0, ctx->stream));
+    fp64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d_out, iters, 1.0 + rep);
+    ctx->launches++;
+    CU(cudaEventRecord(e1, ctx->stream));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    const double fl = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3);
+    if (rep > 0 && fl > best) best = fl;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_out);
+  *flops_per_s = best;
+  return SRBD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,290 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C-ABI, against the CPU oracle on the same
+seeded inputs, against the reference's golden vectors, and through size-independent properties.
+
+Tolerances (BASELINE.json north_star): relative error <= 1e-9 on primal and dual iterates (normwise per
+QP, like Eigen's isApprox in the reference's own tests) and the same IPM iteration count per QP.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SETTINGS = dict(iter_max=30, alpha_min=1e-8, mu0=1e2, tol_stat=1e-8, tol_eq=1e-8, tol_ineq=1e-8, tol_comp=1e-8,
+                reg_prim=1e-12, warm_start=0, pred_corr=1, ric_alg=0, split_step=1)
+TOL = 1e-9
+
+
+def relerr(a, b):
+    a, b = a.reshape(a.shape[0], -1), b.reshape(b.shape[0], -1)
+    return np.linalg.norm(a - b, axis=1) / np.maximum(np.linalg.norm(b, axis=1), 1e-300)
+
+
+def is_approx(a, b, prec):
+    return np.linalg.norm(a - b) <= prec * min(np.linalg.norm(a), np.linalg.norm(b))
+
+
+def perturbed_workload(pkg, B, N, mode, seed=3):
+    """config-2/3 inputs with a non-trivial trajectory (so that every Jacobian block is exercised)."""
+    w = pkg.workload.srbd_batch(B, N=N, contact_mode=mode)
+    rng = np.random.default_rng(seed)
+    w["x"] = w["x"] + 0.05 * rng.standard_normal(w["x"].shape)
+    w["u"] = w["u"] + 5.0 * rng.standard_normal(w["u"].shape)
+    w["x0"] = w["x"][:, 0] + 0.01 * rng.standard_normal(w["x0"].shape)
+    return w
+
+
+def make_ctx(pkg, B, N=20, settings=SETTINGS, dims=None, **dkw):
+    from srbd_nmpc_solver_b200.binding import make_dims
+    ctx = pkg.Context(B, dims if dims is not None else make_dims(N=N, **dkw))
+    ctx.set_model(pkg.default_model_params(N))
+    ctx.set_ipm_args(pkg.default_ipm_args(**settings))
+    return ctx
+
+
+def test_linearize_parity(pkg, orc):
+    """K1 vs SRBDModel::GetShootingDynamic restated (oracle): A, B, b, defect."""
+    B, N = 96, 20
+    w = perturbed_workload(pkg, B, N, "gait")
+    with make_ctx(pkg, B, N) as ctx:
+        ctx.upload_traj(w["x"], w["u"], w["xref"], w["x0"], w["contact"])
+        ctx.linearize()
+        g = ctx.download_linearization()
+    o = orc.assemble(orc.model_params(N), N, 0, w["x"], w["u"], w["xref"], w["contact"])
+    for k in ("A", "Bm", "b", "defect"):
+        assert np.allclose(g[k], o[k], rtol=1e-12, atol=1e-13), (k, np.abs(g[k] - o[k]).max())
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_assemble_parity(pkg, orc, mode):
+    """K2 vs GetConstrain / Barrier / prepareQpStructures restated (oracle)."""
+    B, N = 64, 20
+    w = perturbed_workload(pkg, B, N, "gait")
+    with make_ctx(pkg, B, N) as ctx:
+        ctx.upload_traj(w["x"], w["u"], w["xref"], w["x0"], w["contact"])
+        ctx.linearize()
+        ctx.assemble(mode)
+        g = ctx.download_qp()
+    o = orc.assemble(orc.model_params(N), N, mode, w["x"], w["u"], w["xref"], w["contact"])
+    keys = ["Q", "S", "R", "q", "r"] + (["D", "lg", "lg_mask"] if mode == 1 else [])
+    for k in keys:
+        assert np.allclose(g[k], o[k], rtol=1e-12, atol=1e-12), (k, np.abs(g[k] - o[k]).max())
+
+
+@pytest.mark.parametrize("mode,contact", [(1, "stance"), (1, "gait")])
+def test_srbd_pipeline_parity(pkg, orc, mode, contact):
+    """linearize -> assemble -> IPM solve (BASELINE configs 2 / 3 at a size the oracle finishes in seconds):
+    primal and dual iterates within 1e-9 of the oracle, same iteration count and status per QP."""
+    B, N = 512, 20
+    w = pkg.workload.srbd_batch(B, N=N, contact_mode=contact)
+    with make_ctx(pkg, B, N) as ctx:
+        ctx.upload_traj(w["x"], w["u"], w["xref"], w["x0"], w["contact"])
+        ctx.sqp_iterate(mode)
+        sol = ctx.download_solution(want=("x", "u", "pi", "lam", "t"))
+        st = ctx.download_stats()
+        bs = ctx.batch_stats()
+    ref = orc.pipeline(orc.model_params(N), orc.ipm_args(**SETTINGS), N, mode, w["x"], w["u"], w["xref"], w["x0"],
+                       w["contact"])
+    assert (st["status"] == ref["status"]).all() and (st["status"] == 0).all()
+    assert (st["iter"] == ref["iter"]).all(), np.flatnonzero(st["iter"] != ref["iter"])
+    for k in ("x", "u", "lam", "t"):
+        assert relerr(sol[k], ref[k]).max() <= TOL, (k, relerr(sol[k], ref[k]).max())
+    assert relerr(sol["pi"][:, 1:], ref["pi"][:, 1:]).max() <= TOL
+    assert np.allclose(st["res_max"], ref["res_max"], rtol=1e-3, atol=1e-12)
+    # fused batch statistics (the block that is gathered over NCCL at N>1)
+    assert bs["solves"] == B and bs["iter_sum"] == int(st["iter"].sum()) and bs["status_count"][0] == B
+    assert bs["iter_hist"][:32] == list(np.bincount(st["iter"], minlength=32)[:32])
+
+
+def test_soft_mode_is_single_riccati_pass(pkg, orc):
+    """The reference's own workload: constraints folded into R,r => nb=ng active rows = 0 => iter == 0
+    (hpipm-cpp/test/ocp_qp_ipm_solver.cpp:56)."""
+    B, N = 64, 20
+    w = perturbed_workload(pkg, B, N, "stance")
+    with make_ctx(pkg, B, N) as ctx:
+        ctx.upload_traj(w["x"], w["u"], w["xref"], w["x0"], w["contact"])
+        ctx.sqp_iterate(0)
+        sol = ctx.download_solution(want=("x", "u", "pi"))
+        st = ctx.download_stats()
+    ref = orc.pipeline(orc.model_params(N), orc.ipm_args(**SETTINGS), N, 0, w["x"], w["u"], w["xref"], w["x0"], w["contact"])
+    assert (st["iter"] == 0).all() and (st["status"] == 0).all()
+    for k in ("x", "u"):
+        assert relerr(sol[k], ref[k]).max() <= TOL
+    assert relerr(sol["pi"][:, 1:], ref["pi"][:, 1:]).max() <= TOL
+
+
+def test_reference_sqp_loop_on_gpu(pkg, orc):
+    """Config 1 = controlLoop() of the reference (NMPC_solver.cpp:353-380): SQP with the K4 line search on the
+    device, against the oracle's loop (11 iterations, alpha pattern, converged u0)."""
+    N = 20
+    w = pkg.workload.reference_nmpc_problem(N)
+    ref_settings = dict(SETTINGS, tol_stat=1e-4, tol_eq=1e-4, tol_ineq=1e-4, tol_comp=1e-4)
+    m = orc.model_params(N)
+    ox, ou, oalpha = w["x"][0].copy(), w["u"][0].copy(), 1.0
+    with make_ctx(pkg, 1, N, settings=ref_settings) as ctx:
+        ctx.upload_traj(w["x"], w["u"], w["xref"], w["x0"], w["contact"])
+        conv_it = None
+        for it in range(15):
+            ctx.sqp_iterate(0, do_line_search=True)
+            alpha, conv, merit = ctx.download_sqp_state()
+            o = orc.pipeline(m, orc.ipm_args(**ref_settings), N, 0, ox[None], ou[None], w["xref"], w["x0"])
+            ox, ou, oalpha, oconv, omerit = orc.line_search(m, N, ox, ou, w["xref"][0], o["x"][0], o["u"][0], oalpha)
+            gx, gu = ctx.download_traj()
+            assert alpha[0] == oalpha and conv[0] == oconv
+            assert np.allclose(merit[0], omerit, rtol=1e-9, atol=1e-12)
+            assert relerr(gx, ox[None]).max() <= TOL and relerr(gu, ou[None]).max() <= TOL
+            if conv[0]:
+                conv_it = it + 1
+                break
+    assert conv_it == 11
+    assert np.allclose(gu[0, 0], [54.37, 48.28, 100.32, 4.46, 24.94, 5.55, 63.53, 59.05, 122.50, 4.46, 25.97, 6.28], atol=0.02)
+
+
+def test_compare_results_golden_on_gpu(pkg, orc, golden_quadcopter):
+    """hpipm-cpp/test/ocp_qp_ipm_solver.cpp:170-315 through the C-ABI: every closed-loop step matches
+    sol{t}.txt with isApprox(1e-9), and the oracle's iterates/iteration counts."""
+    from srbd_nmpc_solver_b200.binding import make_dims
+    dims_d, arrays, settings, A, Bm = pkg.workload.quadcopter_mpc()
+    dims = make_dims(**dims_d)
+    x = np.zeros(12)
+    with make_ctx(pkg, 1, dims=dims, settings=settings) as ctx:
+        for t in range(15):
+            arrays["x0"] = x[None, :].copy()
+            ctx.qp_upload(arrays)
+            ctx.qp_solve()
+            sol = ctx.download_solution(want=("x", "u", "pi", "lam", "t"))
+            st = ctx.download_stats()
+            ref = orc.qp_solve(dims, orc.ipm_args(**settings), arrays, 1)
+            assert st["status"][0] == 0
+            cat = np.concatenate([sol["x"][0].reshape(-1), sol["u"][0].reshape(-1)])
+            assert is_approx(cat, golden_quadcopter[t], 1e-9), t
+            assert st["iter"][0] == ref["iter"][0], (t, st["iter"], ref["iter"])
+            for k in ("x", "u", "lam", "t"):
+                assert relerr(sol[k], ref[k]).max() <= 1e-8, (t, k, relerr(sol[k], ref[k]).max())
+            arrays["x_init"], arrays["u_init"] = sol["x"].copy(), sol["u"].copy()
+            x = A @ x + Bm @ sol["u"][0, 0]
+
+
+def test_unconstrained_analytic_on_gpu(pkg, orc):
+    """hpipm-cpp/test/ocp_qp_ipm_solver.cpp:22-110: iter == 0 and x,u,pi,P,p,K,k at isApprox(1e-10) vs the
+    oracle (which is itself pinned to the textbook Riccati recursion in tests/test_oracle_qp.py)."""
+    from srbd_nmpc_solver_b200.binding import make_dims
+    B = 8
+    dims_d, arrays = pkg.workload.random_qp(B, N=20, nx=5, nu=3, seed=7)
+    dims = make_dims(**dims_d)
+    with make_ctx(pkg, B, dims=dims, settings=dict(SETTINGS, iter_max=15)) as ctx:
+        ctx.set_outputs(export_ric=True, export_stat=True)
+        ctx.qp_upload(arrays)
+        ctx.qp_solve()
+        sol = ctx.download_solution()
+        st = ctx.download_stats(with_table=True)
+    ref = orc.qp_solve(dims, orc.ipm_args(ric_alg=0), arrays, B)
+    assert (st["iter"] == 0).all() and (st["status"] == 0).all()
+    for k in ("x", "u", "pi", "P", "p", "K", "k"):
+        for i in range(B):
+            for s in range(sol[k].shape[1]):
+                assert is_approx(sol[k][i, s], ref[k][i, s], 1e-10), (k, i, s)
+
+
+@pytest.mark.parametrize("shape", [dict(nx=5, nu=3, ng=2, nbx=2, nbu=3),      # compiled instantiation
+                                   dict(nx=6, nu=2, ng=3, nbx=1, nbu=2),      # run-time dims fallback
+                                   dict(nx=4, nu=4, ng=0, nbx=0, nbu=4)])
+def test_constrained_random_on_gpu(pkg, orc, shape):
+    """hpipm-cpp/test/ocp_qp_ipm_solver.cpp:112-168 shapes (box on u, box on x, general rows, terminal
+    general rows): GPU vs oracle iterates, iteration counts, statistics table, Riccati exports."""
+    from srbd_nmpc_solver_b200.binding import make_dims
+    B = 16
+    dims_d, arrays = pkg.workload.random_qp(B, N=12, seed=11, a_scale=0.4, **shape)
+    dims = make_dims(**dims_d)
+    settings = dict(SETTINGS, iter_max=40, tol_stat=1e-6)
+    with make_ctx(pkg, B, dims=dims, settings=settings) as ctx:
+        ctx.set_outputs(export_ric=True, export_stat=True)
+        ctx.qp_upload(arrays)
+        ctx.qp_solve()
+        sol = ctx.download_solution()
+        st = ctx.download_stats(with_table=True)
+    ref = orc.qp_solve(dims, orc.ipm_args(**settings), arrays, B, stat_rows=42)
+    assert (st["status"] == ref["status"]).all() and (st["status"] == 0).all()
+    assert (st["iter"] == ref["iter"]).all()
+    for k in ("x", "u", "pi", "lam", "t"):
+        assert relerr(sol[k], ref[k]).max() <= 1e-8, (k, relerr(sol[k], ref[k]).max())
+    for k in ("P", "K", "p", "k"):
+        assert relerr(sol[k], ref[k]).max() <= 1e-6, (k, relerr(sol[k], ref[k]).max())
+    # statistics table: step lengths, sigma, mu and residual columns of every iteration
+    assert np.allclose(st["stat"][:, :, :6], ref["stat"][:, :, :6], rtol=1e-6, atol=1e-12)
+
+
+def test_masks_and_warm_start(pkg, orc):
+    from srbd_nmpc_solver_b200.binding import make_dims
+    B = 8
+    dims_d, arrays = pkg.workload.random_qp(B, N=10, nx=5, nu=3, ng=2, nbx=2, nbu=3, seed=21, a_scale=0.4)
+    rng = np.random.default_rng(0)
+    arrays["lbu_mask"] = (rng.uniform(size=arrays["lbu"].shape) > 0.3).astype(float)
+    arrays["ug_mask"] = (rng.uniform(size=arrays["ug"].shape) > 0.5).astype(float)
+    arrays["ubx_mask"] = np.zeros_like(arrays["ubx"])
+    arrays["x_init"] = 0.1 * rng.standard_normal((B, 11, 5))
+    arrays["u_init"] = 0.1 * rng.standard_normal((B, 10, 3))
+    dims = make_dims(**dims_d)
+    settings = dict(SETTINGS, iter_max=40, tol_stat=1e-6, warm_start=1)
+    with make_ctx(pkg, B, dims=dims, settings=settings) as ctx:
+        ctx.qp_upload(arrays)
+        ctx.qp_solve()
+        sol = ctx.download_solution(want=("x", "u", "pi", "lam", "t"))
+        st = ctx.download_stats()
+    ref = orc.qp_solve(dims, orc.ipm_args(**settings), arrays, B)
+    assert (st["iter"] == ref["iter"]).all() and (st["status"] == ref["status"]).all()
+    for k in ("x", "u", "lam", "t"):
+        assert relerr(sol[k], ref[k]).max() <= 1e-8, k
+    # masked rows keep lam == 0
+    assert (sol["lam"][ref["lam"] == 0.0] == 0.0).all()
+
+
+def test_full_size_properties(pkg):
+    """BASELINE config 3 at a large shard (oracle would take minutes): size-independent properties —
+    every QP converged to tol, the returned primal satisfies the linearized dynamics it was solved for,
+    inequality rows are satisfied, complementarity holds, and the iteration histogram adds up."""
+    B, N = 16384, 20
+    w = pkg.workload.srbd_batch(B, N=N, contact_mode="gait")
+    with make_ctx(pkg, B, N) as ctx:
+        ctx.upload_traj(w["x"], w["u"], w["xref"], w["x0"], w["contact"])
+        ctx.sqp_iterate(1)
+        sol = ctx.download_solution(want=("x", "u", "lam", "t"))
+        st = ctx.download_stats()
+        bs = ctx.batch_stats()
+        lin = ctx.download_linearization()
+        qp = ctx.download_qp()
+    assert (st["status"] == 0).all()
+    assert (st["res_max"] <= 1e-8).all()
+    assert bs["solves"] == B and sum(bs["iter_hist"]) == B and bs["iter_sum"] == int(st["iter"].sum())
+    A = lin["A"].reshape(B, N, 12, 12).transpose(0, 1, 3, 2)
+    Bm = lin["Bm"].reshape(B, N, 12, 12).transpose(0, 1, 3, 2)
+    xn = np.einsum("bkij,bkj->bki", A, sol["x"][:, :N]) + np.einsum("bkij,bkj->bki", Bm, sol["u"]) + lin["b"]
+    assert np.abs(xn - sol["x"][:, 1:]).max() <= 1e-8
+    D = qp["D"].reshape(B, N, 12, 24).transpose(0, 1, 3, 2)
+    v = np.einsum("bkgj,bkj->bkg", D, sol["u"]) - qp["lg"]
+    hard = qp["lg_mask"] != 0
+    assert v[hard].min() >= -1e-8
+    lam_l = sol["lam"].reshape(B, N, 48)[:, :, :24]
+    t_l = sol["t"].reshape(B, N, 48)[:, :, :24]
+    assert np.abs((lam_l * t_l)[hard]).max() <= 1e-8
+    assert np.abs(t_l[hard] - v[hard]).max() <= 1e-8
+
+
+def test_c_abi_error_behaviour(pkg):
+    """usage errors come back as negative codes + message (the facades rethrow std::runtime_error like
+    hpipm-cpp/src/ocp_qp_dim.cpp:33-34, ocp_qp_ipm_solver.cpp:190-207)."""
+    from srbd_nmpc_solver_b200.binding import SrbdError, make_dims
+    with pytest.raises(SrbdError):
+        pkg.Context(4, make_dims(N=5, nx=40, nu=3, ng=0))  # beyond the compiled maxima
+    with make_ctx(pkg, 2, 5) as ctx:
+        with pytest.raises(SrbdError, match="no QP data"):
+            ctx.qp_solve()
+        with pytest.raises(SrbdError, match="ric_alg"):
+            ctx.set_ipm_args(pkg.default_ipm_args(ric_alg=1))
+    dims_d, arrays = pkg.workload.random_qp(2, N=5, nx=5, nu=3, nbu=3, seed=1)
+    with make_ctx(pkg, 2, dims=make_dims(**dims_d), settings=dict(SETTINGS, warm_start=1)) as ctx:
+        ctx.qp_upload(arrays)
+        with pytest.raises(SrbdError, match="warm_start"):
+            ctx.qp_solve()
+        del arrays["lbu"]
+        with pytest.raises(SrbdError, match="nbu"):
+            ctx.qp_upload(arrays)
