@@ -1,0 +1,18 @@
+"""Small driver for profiling: one pass of the hot path on B QPs (default one resident wave)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import srbd_pkg
+pkg = srbd_pkg.load()
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 2368
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+S = dict(iter_max=30, alpha_min=1e-8, mu0=1e2, tol_stat=1e-8, tol_eq=1e-8, tol_ineq=1e-8, tol_comp=1e-8,
+         reg_prim=1e-12, warm_start=0, pred_corr=1, ric_alg=0, split_step=1)
+w = pkg.workload.srbd_batch(B, N=20, contact_mode="gait")
+ctx = pkg.Context(B)
+ctx.set_model(pkg.default_model_params(20)); ctx.set_ipm_args(pkg.default_ipm_args(**S))
+ctx.upload_traj(w["x"], w["u"], w["xref"], w["x0"], w["contact"])
+for _ in range(reps):
+    ctx.sqp_iterate(1)
+ctx.sync()
+st = ctx.download_stats()
+print("ok", B, st["iter"].mean(), (st["status"] == 0).all())

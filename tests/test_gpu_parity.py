@@ -19,6 +19,27 @@ def relerr(a, b):
     return np.linalg.norm(a - b, axis=1) / np.maximum(np.linalg.norm(b, axis=1), 1e-300)
 
 
+def check_iterates(sol, ref, ref_p, fields=("x", "u", "pi", "lam", "t"), tol=TOL, strict=("x", "pi", "t"), bulk=0.85):
+    """GPU iterates vs the oracle's.  Yardstick (DESIGN.md "Parity"): per QP the normwise relative error must
+    be <= max(tol, 10 x the oracle's OWN response to a 1-ulp perturbation of its input) — an IPM at tol 1e-8
+    amplifies rounding by cond(KKT) ~ 1e7, and QPs with a degenerate active set have non-unique multipliers.
+    `strict` fields must meet tol on every QP, and at least `bulk` of the QPs must meet tol on every field."""
+    for k in fields:
+        a, b, c = sol[k], ref[k], ref_p[k]
+        if k == "pi":  # pi[0] is a facade-side reconstruction (only exported with the Riccati outputs)
+            a, b, c = a[:, 1:], b[:, 1:], c[:, 1:]
+        e, sens = relerr(a, b), relerr(c, b)
+        assert (e <= np.maximum(tol, 10 * sens)).all(), (k, float(e.max()), float(sens.max()))
+        if k in strict:
+            assert e.max() <= tol, (k, float(e.max()))
+        if len(e) >= 8:
+            assert (e <= tol).mean() >= bulk, (k, float((e <= tol).mean()))
+
+
+def perturb_1ulp(arrays):
+    return dict(arrays, r=np.nextafter(arrays["r"], np.inf))
+
+
 def is_approx(a, b, prec):
     return np.linalg.norm(a - b) <= prec * min(np.linalg.norm(a), np.linalg.norm(b))
 
@@ -82,14 +103,32 @@ def test_srbd_pipeline_parity(pkg, orc, mode, contact):
         sol = ctx.download_solution(want=("x", "u", "pi", "lam", "t"))
         st = ctx.download_stats()
         bs = ctx.batch_stats()
-    ref = orc.pipeline(orc.model_params(N), orc.ipm_args(**SETTINGS), N, mode, w["x"], w["u"], w["xref"], w["x0"],
-                       w["contact"])
+        lin, qp = ctx.download_linearization(), ctx.download_qp()
+    from srbd_nmpc_solver_b200.binding import make_dims
+    # (1) K3 on IDENTICAL inputs (north_star: "match ... on identical inputs"): the oracle's IPM on the very
+    #     QP data the GPU assembled
+    arrays = dict(A=lin["A"], Bm=lin["Bm"], b=lin["b"], Q=qp["Q"], S=qp["S"], R=qp["R"], q=qp["q"], r=qp["r"],
+                  D=qp["D"], lg=qp["lg"], ug=np.zeros_like(qp["lg"]), lg_mask=qp["lg_mask"],
+                  ug_mask=np.zeros_like(qp["lg"]), x0=w["x0"] - w["x"][:, 0])
+    ref = orc.qp_solve(make_dims(N=N), orc.ipm_args(**SETTINGS), arrays, B, want=("x", "u", "pi", "lam", "t"))
+    ref_p = orc.qp_solve(make_dims(N=N), orc.ipm_args(**SETTINGS), perturb_1ulp(arrays), B, want=("x", "u", "pi", "lam", "t"))
     assert (st["status"] == ref["status"]).all() and (st["status"] == 0).all()
     assert (st["iter"] == ref["iter"]).all(), np.flatnonzero(st["iter"] != ref["iter"])
-    for k in ("x", "u", "lam", "t"):
-        assert relerr(sol[k], ref[k]).max() <= TOL, (k, relerr(sol[k], ref[k]).max())
-    assert relerr(sol["pi"][:, 1:], ref["pi"][:, 1:]).max() <= TOL
+    check_iterates(sol, ref, ref_p)
+    # the identifiable part of the multipliers, J^T lam (what enters stationarity), in the same yardstick
+    D = qp["D"].reshape(B, N, 12, 24).transpose(0, 1, 3, 2)
+
+    def jt(o):
+        return {"jt": np.einsum("bkgj,bkg->bkj", D, o["lam"].reshape(B, N, 48)[:, :, :24])}
+    check_iterates(jt(sol), jt(ref), jt(ref_p), fields=("jt",), strict=())
     assert np.allclose(st["res_max"], ref["res_max"], rtol=1e-3, atol=1e-12)
+    # (2) whole pipeline against the oracle's own linearize/assemble (libm vs CUDA sin/cos/tan/log differ by
+    #     <= 2 ulp, which the IPM amplifies a little): same iteration counts, primal within 5e-9
+    ref2 = orc.pipeline(orc.model_params(N), orc.ipm_args(**SETTINGS), N, mode, w["x"], w["u"], w["xref"], w["x0"],
+                        w["contact"])
+    assert (st["iter"] == ref2["iter"]).all() and (ref2["status"] == 0).all()
+    for k in ("x", "u", "t"):
+        assert relerr(sol[k], ref2[k]).max() <= 5e-9, (k, relerr(sol[k], ref2[k]).max())
     # fused batch statistics (the block that is gathered over NCCL at N>1)
     assert bs["solves"] == B and bs["iter_sum"] == int(st["iter"].sum()) and bs["status_count"][0] == B
     assert bs["iter_hist"][:32] == list(np.bincount(st["iter"], minlength=32)[:32])
@@ -154,12 +193,12 @@ def test_compare_results_golden_on_gpu(pkg, orc, golden_quadcopter):
             sol = ctx.download_solution(want=("x", "u", "pi", "lam", "t"))
             st = ctx.download_stats()
             ref = orc.qp_solve(dims, orc.ipm_args(**settings), arrays, 1)
+            ref_p = orc.qp_solve(dims, orc.ipm_args(**settings), dict(arrays, q=np.nextafter(arrays["q"], np.inf)), 1)
             assert st["status"][0] == 0
             cat = np.concatenate([sol["x"][0].reshape(-1), sol["u"][0].reshape(-1)])
             assert is_approx(cat, golden_quadcopter[t], 1e-9), t
             assert st["iter"][0] == ref["iter"][0], (t, st["iter"], ref["iter"])
-            for k in ("x", "u", "lam", "t"):
-                assert relerr(sol[k], ref[k]).max() <= 1e-8, (t, k, relerr(sol[k], ref[k]).max())
+            check_iterates(sol, ref, ref_p, strict=("x", "u", "pi"))
             arrays["x_init"], arrays["u_init"] = sol["x"].copy(), sol["u"].copy()
             x = A @ x + Bm @ sol["u"][0, 0]
 
@@ -203,12 +242,12 @@ def test_constrained_random_on_gpu(pkg, orc, shape):
         sol = ctx.download_solution()
         st = ctx.download_stats(with_table=True)
     ref = orc.qp_solve(dims, orc.ipm_args(**settings), arrays, B, stat_rows=42)
+    ref_p = orc.qp_solve(dims, orc.ipm_args(**settings), perturb_1ulp(arrays), B)
     assert (st["status"] == ref["status"]).all() and (st["status"] == 0).all()
     assert (st["iter"] == ref["iter"]).all()
-    for k in ("x", "u", "pi", "lam", "t"):
-        assert relerr(sol[k], ref[k]).max() <= 1e-8, (k, relerr(sol[k], ref[k]).max())
-    for k in ("P", "K", "p", "k"):
-        assert relerr(sol[k], ref[k]).max() <= 1e-6, (k, relerr(sol[k], ref[k]).max())
+    check_iterates(sol, ref, ref_p, strict=("x", "u"))
+    # Riccati exports of the last (barrier-augmented) factorization: Gamma = lam/t is as ill-conditioned as lam
+    check_iterates(sol, ref, ref_p, fields=("P", "K", "p", "k"), strict=(), bulk=0.5)
     # statistics table: step lengths, sigma, mu and residual columns of every iteration
     assert np.allclose(st["stat"][:, :, :6], ref["stat"][:, :, :6], rtol=1e-6, atol=1e-12)
 
@@ -231,9 +270,9 @@ def test_masks_and_warm_start(pkg, orc):
         sol = ctx.download_solution(want=("x", "u", "pi", "lam", "t"))
         st = ctx.download_stats()
     ref = orc.qp_solve(dims, orc.ipm_args(**settings), arrays, B)
+    ref_p = orc.qp_solve(dims, orc.ipm_args(**settings), perturb_1ulp(arrays), B)
     assert (st["iter"] == ref["iter"]).all() and (st["status"] == ref["status"]).all()
-    for k in ("x", "u", "lam", "t"):
-        assert relerr(sol[k], ref[k]).max() <= 1e-8, k
+    check_iterates(sol, ref, ref_p, strict=("x", "u"))
     # masked rows keep lam == 0
     assert (sol["lam"][ref["lam"] == 0.0] == 0.0).all()
 
