@@ -220,24 +220,14 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     total_ms = all_evs[0][0].elapsed_time(all_evs[-1][3])
     k_ms = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(3)] for e in all_evs])  # K1, K2, K3 per step
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
+    total_ms_max = pkg.sharding.max_over_ranks(total_ms)  # device time, max over ranks
     ms_per_step = total_ms_max / args.steps
     value = world * B / (ms_per_step * 1e-3)
 
     # per-rank statistics block (fused epilogue of K3), gathered over NCCL
     bs = ctx.batch_stats()
     st = ctx.download_stats()
-    stats_vec = torch.tensor([bs["solves"], bs["iter_sum"]] + bs["status_count"] + bs["iter_hist"], dtype=torch.int64,
-                             device="cuda")
-    if world > 1:
-        gathered = [torch.zeros_like(stats_vec) for _ in range(world)]
-        dist.all_gather(gathered, stats_vec)
-        stats_all = torch.stack(gathered).sum(0).cpu().numpy()
-    else:
-        stats_all = stats_vec.cpu().numpy()
+    stats_all, _ = pkg.sharding.gather_batch_stats(bs)
 
     # ---- e2e: host buffers through the C-ABI (pinned), H2D + K1 + K2 + K3 + D2H per step ---------------
     def pinned(a):
@@ -258,10 +248,8 @@ def main():
         ctx.solve_host(mode, hb["x"], hb["u"], hb["xref"], hb["x0"], hb["contact"], h_sx, h_su, h_it, h_st)
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t0) / args.e2e_steps
-    te = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * B / (float(te.item()) * 1e-3)
+    e2e_ms_max = pkg.sharding.max_over_ranks(e2e_ms)
+    e2e_value = world * B / (e2e_ms_max * 1e-3)
     h2d = sum(int(hb[k].nbytes) for k in hb)
     d2h = int(h_sx.nbytes + h_su.nbytes + h_it.nbytes + h_st.nbytes)
     assert (h_st == 0).all() and np.array_equal(h_it, st["iter"]), "e2e path disagrees with the device-resident path"
@@ -273,8 +261,14 @@ def main():
         k3_ms = float(k_ms[:, 2].mean())
         achieved = flops_launch / (k3_ms * 1e-3) / 1e12
         peak = ctx.fp64_peak() / 1e12
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "k3_traffic.json")
+        if os.path.exists(tpath):  # dram bytes of K3 from the committed `ncu --set full` capture, scaled per QP
+            tj = json.load(open(tpath))
+            traffic, traffic_src = tj["dram_bytes_per_qp"] * B, tj["source"]
         roofline = {"bound": "fp64", "kernel": "ipm_solve_kernel (K3)", "achieved": achieved, "peak": peak,
-                    "unit": "TFLOP/s", "frac": achieved / peak if peak > 0 else None, "traffic": None,
+                    "unit": "TFLOP/s", "frac": achieved / peak if peak > 0 else None, "traffic": traffic,
+                    "traffic_source": traffic_src,
                     "peak_source": "measured live: DFMA-saturating microbenchmark srbd_fp64_peak() (MEASURED_PEAKS.json "
                                    "carries no FP64 figure)",
                     "flops_per_launch": flops_launch, "kernel_ms": k3_ms,
@@ -307,11 +301,11 @@ def main():
                            "parallelism": f"dp{world} (independent QPs, no data-path collective)"},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": float(te.item()), "steps": args.e2e_steps},
+                        "ms_per_step": e2e_ms_max, "steps": args.e2e_steps},
                 "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "ipm": {"iter_mean": float(it.mean()), "iter_min": int(it.min()), "iter_max": int(it.max()),
-                        "status_counts_all_ranks": [int(v) for v in stats_all[2:7]],
-                        "solves_all_ranks": int(stats_all[0]), "iter_sum_all_ranks": int(stats_all[1])}}
+                        "status_counts_all_ranks": stats_all["status_count"], "solves_all_ranks": stats_all["solves"],
+                        "iter_sum_all_ranks": stats_all["iter_sum"], "res_max_all_ranks": stats_all["res_max"]}}
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

@@ -6,5 +6,6 @@ and a thin ctypes binding used by the tests and bench.py.  Importing the package
 library; the first call does, and fails loudly if it was not built (no CPU fallback).
 """
 from . import capi  # noqa: F401
+from . import sharding  # noqa: F401
 from . import workload  # noqa: F401
 from .binding import Context, default_ipm_args, default_model_params  # noqa: F401

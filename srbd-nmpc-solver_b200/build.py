@@ -35,6 +35,30 @@ def build(force=False, verbose=False):
     return OUT
 
 
+HOST_TEST = os.path.join(HERE, "host", "tests", "test_facades")
+
+
+def build_host_tests(force=False):
+    """C++ host facades (host/*.hpp) + the reference's own host tests re-written against them."""
+    src = os.path.join(HERE, "host", "tests", "test_facades.cpp")
+    deps = [src] + [os.path.join(HERE, "host", f) for f in ("NMPC_solver.hpp", "SRBD_model.hpp", "eigen_shim.hpp",
+                                                             os.path.join("hpipm-cpp", "hpipm-cpp.hpp"))]
+    if (not force and os.path.exists(HOST_TEST) and
+            all(os.path.getmtime(HOST_TEST) >= os.path.getmtime(d) for d in deps + [OUT])):
+        return HOST_TEST
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [gxx, "-std=c++17", "-O2", "-Wall", "-Wextra", src, "-o", HOST_TEST, "-L" + HERE, "-lsrbd_b200",
+           "-Wl,-rpath," + HERE, "-Wl,-rpath,$ORIGIN/../.."]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed for the host facade test")
+    if r.stderr.strip():
+        sys.stderr.write(r.stderr)
+    return HOST_TEST
+
+
 if __name__ == "__main__":
     build(force=True, verbose="-v" in sys.argv)
+    build_host_tests(force=True)
     print(OUT)

@@ -1,0 +1,282 @@
+// test_facades.cpp — the reference's own host-level tests, re-written against the B200-backed facades:
+//   hpipm-cpp/test/ocp_qp_ipm_solver.cpp:22-110  (unconstrained: iter == 0, analytic Riccati, 1e-10)
+//   hpipm-cpp/test/ocp_qp_ipm_solver.cpp:112-168 (constrained: Success, x[0] == x0)
+//   hpipm-cpp/test/ocp_qp_ipm_solver.cpp:170-315 (compareResults: 15 golden vectors, isApprox 1e-9)
+// plus SRBDModel / NMPCSolver drop-in checks (config 1: 11 SQP iterations) and the
+// std::runtime_error behaviour of hpipm-cpp/src/ocp_qp_dim.cpp.  Needs a CUDA device (run by pytest -m gpu).
+// usage: test_facades <tests/golden/quadcopter_sol.txt>
+#include <cmath>
+#include <cstdio>
+#include <fstream>
+#include <functional>
+#include <sstream>
+
+#include "../NMPC_solver.hpp"
+#include "../SRBD_model.hpp"
+#include "../hpipm-cpp/hpipm-cpp.hpp"
+
+using Eigen::MatrixXd;
+using Eigen::VectorXd;
+static int g_fail = 0;
+#define CHECK(c) do { if (!(c)) { std::printf("CHECK FAILED %s:%d: %s\n", __FILE__, __LINE__, #c); ++g_fail; } } while (0)
+
+// ---- tiny dense helpers (the shim has no arithmetic) ----------------------------------------------------
+static uint64_t g_seed = 88172645463325252ull;
+static double rnd() { g_seed ^= g_seed << 13; g_seed ^= g_seed >> 7; g_seed ^= g_seed << 17; return (double)(g_seed >> 11) / 9007199254740992.0 * 2.0 - 1.0; }
+static MatrixXd Rnd(int r, int c) { MatrixXd m(r, c); for (int i = 0; i < r * c; ++i) m.data()[i] = rnd(); return m; }
+static VectorXd RndV(int n) { VectorXd v(n); for (int i = 0; i < n; ++i) v(i) = rnd(); return v; }
+static MatrixXd mul(const MatrixXd& A, const MatrixXd& B) {
+  MatrixXd C(A.rows(), B.cols());
+  for (int i = 0; i < A.rows(); ++i) for (int j = 0; j < B.cols(); ++j) { double s = 0; for (int k = 0; k < A.cols(); ++k) s += A(i, k) * B(k, j); C(i, j) = s; }
+  return C;
+}
+static MatrixXd tr(const MatrixXd& A) { MatrixXd T(A.cols(), A.rows()); for (int i = 0; i < A.rows(); ++i) for (int j = 0; j < A.cols(); ++j) T(j, i) = A(i, j); return T; }
+static MatrixXd add(const MatrixXd& A, const MatrixXd& B, double s = 1.0) { MatrixXd C(A.rows(), A.cols()); for (int i = 0; i < A.size(); ++i) C.data()[i] = A.data()[i] + s * B.data()[i]; return C; }
+static MatrixXd col(const VectorXd& v) { MatrixXd m(v.size(), 1); for (int i = 0; i < v.size(); ++i) m(i, 0) = v(i); return m; }
+static VectorXd vec(const MatrixXd& m) { VectorXd v(m.rows()); for (int i = 0; i < m.rows(); ++i) v(i) = m(i, 0); return v; }
+static MatrixXd inv(MatrixXd A) {
+  const int n = (int)A.rows();
+  MatrixXd I = MatrixXd::Identity(n, n);
+  for (int c = 0; c < n; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < n; ++r) if (std::fabs(A(r, c)) > std::fabs(A(piv, c))) piv = r;
+    for (int j = 0; j < n; ++j) { std::swap(A(c, j), A(piv, j)); std::swap(I(c, j), I(piv, j)); }
+    const double d = A(c, c);
+    for (int j = 0; j < n; ++j) { A(c, j) /= d; I(c, j) /= d; }
+    for (int r = 0; r < n; ++r) if (r != c) { const double f = A(r, c); for (int j = 0; j < n; ++j) { A(r, j) -= f * A(c, j); I(r, j) -= f * I(c, j); } }
+  }
+  return I;
+}
+static double nrm(const double* a, int n) { double s = 0; for (int i = 0; i < n; ++i) s += a[i] * a[i]; return std::sqrt(s); }
+static bool approx(const double* a, const double* b, int n, double prec) {  // Eigen isApprox
+  double d = 0; for (int i = 0; i < n; ++i) d += (a[i] - b[i]) * (a[i] - b[i]);
+  return std::sqrt(d) <= prec * std::min(nrm(a, n), nrm(b, n));
+}
+static bool approxM(const MatrixXd& a, const MatrixXd& b, double p) { return a.size() == b.size() && approx(a.data(), b.data(), (int)a.size(), p); }
+static bool approxV(const VectorXd& a, const VectorXd& b, double p) { return a.size() == b.size() && approx(a.data(), b.data(), (int)a.size(), p); }
+static MatrixXd block(const MatrixXd& H, int r0, int c0, int r, int c) { MatrixXd m(r, c); for (int i = 0; i < r; ++i) for (int j = 0; j < c; ++j) m(i, j) = H(r0 + i, c0 + j); return m; }
+
+static std::vector<hpipm::OcpQp> randomQp(int nx, int nu, int N, double a_scale, bool boost_R) {
+  std::vector<hpipm::OcpQp> qp(N + 1);
+  for (int i = 0; i < N; ++i) {
+    qp[i].A = Rnd(nx, nx); for (int k = 0; k < nx * nx; ++k) qp[i].A.data()[k] *= a_scale;
+    qp[i].B = Rnd(nx, nu); qp[i].b = RndV(nx);
+    const MatrixXd H = Rnd(nx + nu, nx + nu), HH = mul(H, tr(H));
+    qp[i].Q = block(HH, nu, nu, nx, nx); qp[i].S = block(HH, 0, nu, nu, nx); qp[i].R = block(HH, 0, 0, nu, nu);
+    if (boost_R) for (int k = 0; k < nu; ++k) qp[i].R(k, k) += std::fabs(rnd());
+    qp[i].q = RndV(nx); qp[i].r = RndV(nu);
+  }
+  const MatrixXd H = Rnd(nx, nx);
+  qp[N].Q = mul(H, tr(H)); qp[N].q = RndV(nx);
+  return qp;
+}
+
+static void test_unconstrained() {
+  const int nx = 5, nu = 3, N = 20;
+  auto qp = randomQp(nx, nu, N, 1.0, true);
+  const VectorXd x0 = RndV(nx);
+  hpipm::OcpQpIpmSolverSettings s;
+  s.ric_alg = 0;  // the GPU path implements the classical Riccati (what NMPC_solver.cpp:81 selects)
+  std::vector<hpipm::OcpQpSolution> sol(N + 1);
+  hpipm::OcpQpIpmSolver solver(qp, s);
+  const auto status = solver.solve(x0, qp, sol);
+  CHECK(status == hpipm::HpipmStatus::Success);
+  CHECK(solver.getSolverStatistics().iter == 0);
+  CHECK(approxV(sol[0].x, x0, 1e-12));
+  std::vector<MatrixXd> P(N + 1), K(N), sv(N + 1), kv(N);
+  P[N] = qp[N].Q; sv[N] = col(qp[N].q); for (int i = 0; i < nx; ++i) sv[N](i, 0) = -sv[N](i, 0);
+  for (int i = N - 1; i >= 0; --i) {
+    const MatrixXd At = tr(qp[i].A), Bt = tr(qp[i].B);
+    const MatrixXd F = add(qp[i].Q, mul(mul(At, P[i + 1]), qp[i].A));
+    const MatrixXd H = add(qp[i].S, mul(mul(Bt, P[i + 1]), qp[i].A));
+    const MatrixXd G = add(qp[i].R, mul(mul(Bt, P[i + 1]), qp[i].B));
+    const MatrixXd Gi = inv(G);
+    K[i] = mul(Gi, H); for (int k = 0; k < K[i].size(); ++k) K[i].data()[k] = -K[i].data()[k];
+    MatrixXd t = add(add(mul(mul(Bt, P[i + 1]), col(qp[i].b)), mul(Bt, sv[i + 1]), -1.0), col(qp[i].r));
+    kv[i] = mul(Gi, t); for (int k = 0; k < nu; ++k) kv[i](k, 0) = -kv[i](k, 0);
+    P[i] = add(F, mul(mul(tr(K[i]), G), K[i]), -1.0);
+    sv[i] = add(add(mul(At, add(sv[i + 1], mul(P[i + 1], col(qp[i].b)), -1.0)), col(qp[i].q), -1.0), mul(tr(H), kv[i]), -1.0);
+  }
+  std::vector<MatrixXd> x(N + 1), u(N);
+  x[0] = col(x0);
+  for (int i = 0; i < N; ++i) {
+    u[i] = add(mul(K[i], x[i]), kv[i]);
+    x[i + 1] = add(add(mul(qp[i].A, x[i]), mul(qp[i].B, u[i])), col(qp[i].b));
+  }
+  const double prec = 1e-10;
+  for (int i = 0; i <= N; ++i) {
+    CHECK(approxV(vec(x[i]), sol[i].x, prec));
+    CHECK(approxV(vec(add(mul(P[i], x[i]), sv[i], -1.0)), sol[i].pi, prec));
+    CHECK(approxM(P[i], sol[i].P, prec));
+    VectorXd mp(nx); for (int k = 0; k < nx; ++k) mp(k) = -sol[i].p(k);
+    CHECK(approxV(vec(sv[i]), mp, prec));
+  }
+  for (int i = 0; i < N; ++i) {
+    CHECK(approxV(vec(u[i]), sol[i].u, prec));
+    CHECK(approxM(K[i], sol[i].K, prec));
+    CHECK(approxV(vec(kv[i]), sol[i].k, prec));
+  }
+  std::printf("unconstrained: done\n");
+}
+
+static void test_constrained() {
+  const int nx = 5, nu = 3, ng = 2, N = 20;
+  auto qp = randomQp(nx, nu, N, 0.4, true);
+  const VectorXd x0 = RndV(nx);
+  auto absv = [](VectorXd v, double s, double off) { for (int i = 0; i < v.size(); ++i) v(i) = s * (off + std::fabs(v(i))); return v; };
+  for (int i = 0; i < N; ++i) {
+    qp[i].idxbu = {0, 1, 2};
+    qp[i].lbu = absv(RndV(3), -1.0, 0.5); qp[i].ubu = absv(RndV(3), 1.0, 0.5);
+    qp[i].C = Rnd(ng, nx); qp[i].D = Rnd(ng, nu);
+    qp[i].lg = absv(RndV(ng), -10.0, 0.5); qp[i].ug = absv(RndV(ng), 10.0, 0.5);
+  }
+  for (int i = 1; i <= N; ++i) {
+    qp[i].idxbx = {1, 3};
+    qp[i].lbx = absv(RndV(2), -10.0, 0.5); qp[i].ubx = absv(RndV(2), 10.0, 0.5);
+    qp[i].lbx(0) += x0(1); qp[i].lbx(1) += x0(3); qp[i].ubx(0) += x0(1); qp[i].ubx(1) += x0(3);
+  }
+  qp[N].C = Rnd(ng, nx); qp[N].lg = absv(RndV(ng), -10.0, 0.5); qp[N].ug = absv(RndV(ng), 10.0, 0.5);
+  hpipm::OcpQpIpmSolverSettings s;
+  s.ric_alg = 0; s.iter_max = 40; s.tol_stat = 1e-6;
+  std::vector<hpipm::OcpQpSolution> sol(N + 1);
+  hpipm::OcpQpIpmSolver solver(qp, s);
+  const auto status = solver.solve(x0, qp, sol);
+  CHECK(status == hpipm::HpipmStatus::Success);
+  CHECK(approxV(sol[0].x, x0, 1e-12));
+  CHECK(solver.getSolverStatistics().iter > 0);
+  CHECK((int)solver.getSolverStatistics().mu.size() == solver.getSolverStatistics().iter + 2);
+  for (int i = 0; i < N; ++i) for (int k = 0; k < 3; ++k) CHECK(sol[i].u(k) >= qp[i].lbu(k) - 1e-7 && sol[i].u(k) <= qp[i].ubu(k) + 1e-7);
+  std::printf("constrained: done (%d iterations)\n", solver.getSolverStatistics().iter);
+}
+
+static void test_compare_results(const std::string& golden) {
+  const int N = 10;
+  std::vector<hpipm::OcpQp> qp(N + 1);
+  const double Ad[12][12] = {
+      {1., 0., 0., 0., 0., 0., 0.1, 0., 0., 0., 0., 0.}, {0., 1., 0., 0., 0., 0., 0., 0.1, 0., 0., 0., 0.},
+      {0., 0., 1., 0., 0., 0., 0., 0., 0.1, 0., 0., 0.}, {0.0488, 0., 0., 1., 0., 0., 0.0016, 0., 0., 0.0992, 0., 0.},
+      {0., -0.0488, 0., 0., 1., 0., 0., -0.0016, 0., 0., 0.0992, 0.}, {0., 0., 0., 0., 0., 1., 0., 0., 0., 0., 0., 0.0992},
+      {0., 0., 0., 0., 0., 0., 1., 0., 0., 0., 0., 0.}, {0., 0., 0., 0., 0., 0., 0., 1., 0., 0., 0., 0.},
+      {0., 0., 0., 0., 0., 0., 0., 0., 1., 0., 0., 0.}, {0.9734, 0., 0., 0., 0., 0., 0.0488, 0., 0., 0.9846, 0., 0.},
+      {0., -0.9734, 0., 0., 0., 0., 0., -0.0488, 0., 0., 0.9846, 0.}, {0., 0., 0., 0., 0., 0., 0., 0., 0., 0., 0., 0.9846}};
+  const double Bd[12][4] = {{0., -0.0726, 0., 0.0726}, {-0.0726, 0., 0.0726, 0.}, {-0.0152, 0.0152, -0.0152, 0.0152},
+                            {-0., -0.0006, -0., 0.0006}, {0.0006, 0., -0.0006, 0.0000}, {0.0106, 0.0106, 0.0106, 0.0106},
+                            {0, -1.4512, 0., 1.4512}, {-1.4512, 0., 1.4512, 0.}, {-0.3049, 0.3049, -0.3049, 0.3049},
+                            {-0., -0.0236, 0., 0.0236}, {0.0236, 0., -0.0236, 0.}, {0.2107, 0.2107, 0.2107, 0.2107}};
+  MatrixXd A(12, 12), B(12, 4), Q(12, 12), S(4, 12), R(4, 4);
+  for (int i = 0; i < 12; ++i) { for (int j = 0; j < 12; ++j) A(i, j) = Ad[i][j]; for (int j = 0; j < 4; ++j) B(i, j) = Bd[i][j]; }
+  const double qd[12] = {0, 0, 10., 10., 10., 10., 0, 0, 0, 5., 5., 5.};
+  for (int i = 0; i < 12; ++i) Q(i, i) = qd[i];
+  for (int i = 0; i < 4; ++i) R(i, i) = 0.1;
+  VectorXd q(12); q(2) = -10.0;  // -Q * x_ref, x_ref = e_2
+  const double u0 = 10.5916, PI6 = M_PI / 6.0;
+  for (int i = 0; i <= N; ++i) {
+    qp[i].Q = Q; qp[i].q = q;
+    if (i < N) { qp[i].A = A; qp[i].B = B; qp[i].b = VectorXd(12); qp[i].R = R; qp[i].S = S; qp[i].r = VectorXd(4); }
+    if (i >= 1) {
+      qp[i].idxbx = {0, 1, 5};
+      qp[i].lbx = VectorXd(3); qp[i].ubx = VectorXd(3); qp[i].ubx_mask = VectorXd(3);
+      qp[i].lbx(0) = -PI6; qp[i].lbx(1) = -PI6; qp[i].lbx(2) = -1.0;
+      qp[i].ubx(0) = PI6; qp[i].ubx(1) = PI6; qp[i].ubx(2) = 1.0e10;
+      qp[i].ubx_mask(0) = 1.0; qp[i].ubx_mask(1) = 1.0; qp[i].ubx_mask(2) = 0.0;  // disables ubx[2] (:232)
+    }
+    if (i < N) {
+      qp[i].idxbu = {0, 1, 2, 3};
+      qp[i].lbu = VectorXd(4); qp[i].ubu = VectorXd(4);
+      qp[i].lbu.fill(9.6 - u0); qp[i].ubu.fill(13.0 - u0);
+    }
+  }
+  hpipm::OcpQpIpmSolverSettings s;
+  s.mode = hpipm::HpipmMode::Balance; s.iter_max = 30; s.alpha_min = 1e-8; s.mu0 = 1e2;
+  s.tol_stat = s.tol_eq = s.tol_ineq = s.tol_comp = 1e-10;
+  s.reg_prim = 1e-12; s.warm_start = 1; s.pred_corr = 1; s.ric_alg = 0; s.split_step = 1;
+  std::vector<hpipm::OcpQpSolution> sol(N + 1);
+  hpipm::OcpQpIpmSolver solver(qp, s);
+  VectorXd x(12);
+  for (int i = 0; i <= N; ++i) { sol[i].x = x; if (i < N) { sol[i].u = VectorXd(4); sol[i].u.fill(u0); } }
+  std::ifstream in(golden);
+  CHECK(in.good());
+  for (int t = 0; t < 15; ++t) {
+    const VectorXd x0 = x;
+    CHECK(solver.solve(x0, qp, sol) == hpipm::HpipmStatus::Success);
+    std::vector<double> cat, gold(172);
+    for (int i = 0; i <= N; ++i) for (int k = 0; k < 12; ++k) cat.push_back(sol[i].x(k));
+    for (int i = 0; i < N; ++i) for (int k = 0; k < 4; ++k) cat.push_back(sol[i].u(k));
+    for (double& v : gold) in >> v;
+    CHECK(approx(cat.data(), gold.data(), 172, 1.0e-09));
+    VectorXd xn(12);
+    for (int i = 0; i < 12; ++i) { double sacc = 0; for (int j = 0; j < 12; ++j) sacc += A(i, j) * x(j); for (int j = 0; j < 4; ++j) sacc += B(i, j) * sol[0].u(j); xn(i) = sacc; }
+    x = xn;
+  }
+  std::printf("compareResults: done\n");
+}
+
+static void test_errors() {
+  auto qp = randomQp(5, 3, 4, 1.0, true);
+  bool thrown = false;
+  try { qp[1].A = Rnd(4, 5); hpipm::OcpQpDim d(qp); } catch (const std::runtime_error& e) { thrown = std::string(e.what()).find("ocp_qp[1].A.rows() must be 5") != std::string::npos; }
+  CHECK(thrown);
+  thrown = false;
+  try { std::vector<hpipm::OcpQp> e; hpipm::OcpQpDim d(e); } catch (const std::runtime_error&) { thrown = true; }
+  CHECK(thrown);
+  thrown = false;
+  qp = randomQp(5, 3, 4, 1.0, true);
+  hpipm::OcpQpIpmSolverSettings s; s.ric_alg = 0; s.warm_start = 1;
+  try { hpipm::OcpQpIpmSolver solver(qp, s); std::vector<hpipm::OcpQpSolution> sol(5); solver.solve(RndV(5), qp, sol); }
+  catch (const std::runtime_error& e) { thrown = std::string(e.what()).find("qp_sol[0].x.size() must be 5") != std::string::npos; }
+  CHECK(thrown);
+  thrown = false;
+  try { hpipm::OcpQpIpmSolverSettings b; b.mu0 = -1; b.checkSettings(); } catch (const std::runtime_error&) { thrown = true; }
+  CHECK(thrown);
+  std::printf("errors: done\n");
+}
+
+static void test_srbd_model() {
+  SRBDModel m;
+  m.SetMass(15.0); m.SetMPCdt(0.015);
+  MatrixXd L(3, 3); L(0, 0) = 0.541667; L(1, 1) = 0.516667; L(2, 2) = 1.0416667;
+  m.SetInertia(L);
+  VectorXd pr(3), pl(3); pr(1) = -0.1; pl(1) = 0.1;
+  m.SetFoot(pr, pl, MatrixXd::Identity(3, 3), MatrixXd::Identity(3, 3));
+  VectorXd x(12), xn(12), u(12);
+  x(8) = 1.0; xn(8) = 1.0; u.fill(100.0);
+  MatrixXd A, B, b, f;
+  m.GetShootingDynamic(x, xn, u, &A, &B, &b, &f);
+  CHECK(std::fabs(B(9, 0) - 0.015 / 15.0) < 1e-15 && std::fabs(A(6, 9) - 0.015) < 1e-15 && A(0, 0) > 0.99);
+  // pdot = v: x_get(8) = 1 + dt*v integrated from vdot = 200/15 - 9.8 -> defect of p_z is -(dt^2/2)*vdot
+  CHECK(std::fabs(f(8, 0) + 0.5 * 0.015 * 0.015 * (200.0 / 15.0 - 9.8)) < 1e-12);
+  for (int i = 0; i < 12; ++i) CHECK(b(i, 0) == -f(i, 0));
+  MatrixXd Ac, fc;
+  m.GetConstrain(u, Ac, fc);
+  CHECK(Ac.rows() == 24 && Ac.cols() == 12);
+  CHECK(std::fabs(fc(0, 0) - (-100.0 + 0.5 * 100.0)) < 1e-12 && std::fabs(fc(4, 0) - 900.0) < 1e-12 && std::fabs(fc(5, 0) - 100.0) < 1e-12);
+  std::printf("SRBDModel: done\n");
+}
+
+static void test_nmpc_solver() {
+  NMPCConfig cfg;
+  cfg.N_rep = 1;
+  NMPCSolver nmpc("../mpc_option.yaml", cfg);
+  nmpc.controlLoop();
+  CHECK(nmpc.lastSqpIterations() == 11);
+  const double u0[12] = {54.37, 48.28, 100.32, 4.46, 24.94, 5.55, 63.53, 59.05, 122.50, 4.46, 25.97, 6.28};
+  for (int i = 0; i < 12; ++i) CHECK(std::fabs(nmpc.u()[i] - u0[i]) < 0.02);
+  std::printf("NMPCSolver: done\n");
+}
+
+int main(int argc, char** argv) {
+  const std::string golden = argc > 1 ? argv[1] : "tests/golden/quadcopter_sol.txt";
+  try {
+    test_errors();
+    test_unconstrained();
+    test_constrained();
+    test_compare_results(golden);
+    test_srbd_model();
+    test_nmpc_solver();
+  } catch (const std::exception& e) {
+    std::printf("An exception occurred: %s\n", e.what());
+    return 2;
+  }
+  std::printf(g_fail ? "FAILED (%d checks)\n" : "ALL OK\n", g_fail);
+  return g_fail ? 1 : 0;
+}

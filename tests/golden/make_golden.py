@@ -17,4 +17,5 @@ if __name__ == "__main__":
     sols = np.stack([np.loadtxt(os.path.join(REF, f"sol{t}.txt")) for t in range(15)])
     assert sols.shape == (15, 172)
     np.savez(os.path.join(HERE, "quadcopter_sol.npz"), sol=sols)
+    np.savetxt(os.path.join(HERE, "quadcopter_sol.txt"), sols, fmt="%.18e")  # same data for the C++ facade test
     print("wrote", sols.shape)

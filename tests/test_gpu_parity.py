@@ -327,3 +327,19 @@ def test_c_abi_error_behaviour(pkg):
         del arrays["lbu"]
         with pytest.raises(SrbdError, match="nbu"):
             ctx.qp_upload(arrays)
+
+
+def test_cpp_host_facades(pkg):
+    """The C++ drop-in facades (hpipm::OcpQp / OcpQpIpmSolver, SRBDModel, NMPCSolver) run the reference's own
+    host tests (hpipm-cpp/test/ocp_qp_ipm_solver.cpp) plus the config-1 control loop on the GPU."""
+    import importlib.util
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("_srbd_build", os.path.join(root, "srbd-nmpc-solver_b200", "build.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    exe = b.build_host_tests()
+    r = subprocess.run([exe, os.path.join(root, "tests", "golden", "quadcopter_sol.txt")], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
