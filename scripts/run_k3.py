@@ -1,5 +1,5 @@
-"""Small driver for profiling: one pass of the hot path on B QPs (default one resident wave)."""
-import sys, os
+"""Small driver for profiling / timing: passes of the hot path on B QPs (default one resident wave)."""
+import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import srbd_pkg
 pkg = srbd_pkg.load()
@@ -11,8 +11,11 @@ w = pkg.workload.srbd_batch(B, N=20, contact_mode="gait")
 ctx = pkg.Context(B)
 ctx.set_model(pkg.default_model_params(20)); ctx.set_ipm_args(pkg.default_ipm_args(**S))
 ctx.upload_traj(w["x"], w["u"], w["xref"], w["x0"], w["contact"])
+ctx.linearize(); ctx.assemble(1); ctx.qp_solve(); ctx.sync()
+ts = []
 for _ in range(reps):
-    ctx.sqp_iterate(1)
-ctx.sync()
+    t0 = time.perf_counter(); ctx.qp_solve(); ctx.sync(); ts.append(time.perf_counter() - t0)
 st = ctx.download_stats()
-print("ok", B, st["iter"].mean(), (st["status"] == 0).all())
+t = min(ts)
+print("ok B=%d iters=%.3f allconv=%s  K3 %.2f ms  -> %.0f solves/s (generic=%s)" % (
+    B, st["iter"].mean(), (st["status"] == 0).all(), 1e3 * t, B / t, os.environ.get("SRBD_K3_GENERIC", "0")))

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libsrbd_b200.so")
 SOURCES = ["capi.cu"]
-HEADERS = ["layout.cuh", "ipm_solve.cuh", "srbd_model.cuh", "aux_kernels.cuh"]
+HEADERS = ["layout.cuh", "ipm_solve.cuh", "ipm_srbd.cuh", "srbd_model.cuh", "aux_kernels.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr"]
 

@@ -4,12 +4,14 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "aux_kernels.cuh"
 #include "ipm_solve.cuh"
+#include "ipm_srbd.cuh"
 #include "srbd_model.cuh"
 
 using namespace srbd;
@@ -45,6 +47,9 @@ struct srbd_ctx {
   double* d_resmax = nullptr;
   srbd_batch_stats* d_bstats = nullptr;
   double* d_ws = nullptr;
+  double* d_ws2 = nullptr;   // workspace of the SRBD throughput variant of K3 (ipm_srbd.cuh)
+  int grid2 = 0;
+  int assembled_mode = -1;   // >= 0: the packed QP came from srbd_assemble (K2) in that mode
   int grid = 0, stat_rows = 0;
   bool export_ric = false, export_stat = false;
   long long launches = 0;
@@ -232,7 +237,8 @@ int srbd_ctx_destroy(srbd_ctx* ctx) {
                   ctx->d_alpha, ctx->d_conv, ctx->d_merit, ctx->d_babt, ctx->d_rsq, ctx->d_dct, ctx->d_d,
                   ctx->d_dmask, ctx->d_raw0, ctx->d_x0, ctx->d_xinit, ctx->d_uinit, ctx->d_sol_x, ctx->d_sol_u,
                   ctx->d_sol_pi, ctx->d_sol_lam, ctx->d_sol_t, ctx->d_P, ctx->d_p, ctx->d_K, ctx->d_k,
-                  ctx->d_stat, ctx->d_iter, ctx->d_status, ctx->d_counter, ctx->d_resmax, ctx->d_bstats, ctx->d_ws};
+                  ctx->d_stat, ctx->d_iter, ctx->d_status, ctx->d_counter, ctx->d_resmax, ctx->d_bstats, ctx->d_ws,
+                  ctx->d_ws2};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (void* p : ctx->raw_dev)
@@ -384,6 +390,7 @@ int srbd_assemble(srbd_ctx* ctx, int mode) {
   CU(cudaGetLastError());
   ctx->packed = true;
   ctx->have_init = false;
+  ctx->assembled_mode = mode;
   return SRBD_OK;
 }
 
@@ -532,6 +539,36 @@ int srbd_qp_upload(srbd_ctx* ctx, const srbd_qp_host* qp) {
   ctx->launches++;
   CU(cudaGetLastError());
   ctx->packed = true;
+  ctx->assembled_mode = -1;
+  return SRBD_OK;
+}
+
+// K3 for QPs assembled by K2 in HARD_INEQ mode: the SRBD throughput variant (same algorithm as the generic kernel)
+static int solve_srbd_variant(srbd_ctx* ctx) {
+  const QpLayout& L = ctx->L;
+  if (!ctx->d_ws2) {
+    CU(cudaFuncSetAttribute(ipm_srbd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes));
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ipm_srbd_kernel, 128, v2::kSmemBytes));
+    if (occ < 1) return fail(ctx, SRBD_ERR_CUDA, "ipm_srbd_kernel does not fit on this device");
+    long long g = (long long)occ * ctx->sm_count;
+    const long long need = (ctx->B + v2::kWarps - 1) / v2::kWarps;
+    if (g > need) g = need;
+    ctx->grid2 = (int)g;
+    CU(dalloc(&ctx->d_ws2, (size_t)ctx->grid2 * v2::kWarps * (size_t)(L.N + 1) * v2::kStage));
+  }
+  SrbdIpmParams p{};
+  p.B = ctx->B; p.N = L.N; p.a = ctx->args;
+  p.babt = ctx->d_babt; p.rsq = ctx->d_rsq; p.d = ctx->d_d; p.dmask = ctx->d_dmask; p.x0 = ctx->d_x0;
+  p.model = ctx->d_model; p.ws = ctx->d_ws2; p.ws_size = (L.N + 1) * v2::kStage; p.counter = ctx->d_counter;
+  p.sol_x = ctx->d_sol_x; p.sol_u = ctx->d_sol_u; p.sol_pi = ctx->d_sol_pi; p.sol_lam = ctx->d_sol_lam; p.sol_t = ctx->d_sol_t;
+  p.iter = ctx->d_iter; p.status = ctx->d_status; p.res_max = ctx->d_resmax; p.bstats = ctx->d_bstats;
+  CU(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_bstats, 0, sizeof(srbd_batch_stats), ctx->stream));
+  ipm_srbd_kernel<<<ctx->grid2, 128, v2::kSmemBytes, ctx->stream>>>(p);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  ctx->solved = true;
   return SRBD_OK;
 }
 
@@ -542,6 +579,13 @@ int srbd_qp_solve(srbd_ctx* ctx) {
     return fail(ctx, SRBD_ERR_ARG, "warm_start=1 needs x_init/u_init (qp_sol[i].x / .u must be pre-sized, "
                                    "hpipm-cpp/src/ocp_qp_ipm_solver.cpp:190-207)");
   CU(cudaSetDevice(ctx->device));
+  {
+    const char* force = std::getenv("SRBD_K3_GENERIC");
+    const bool generic = force && force[0] == '1';
+    if (!generic && ctx->is_srbd && ctx->assembled_mode == SRBD_HARD_INEQ && !ctx->args.warm_start &&
+        !ctx->export_ric && !ctx->export_stat)
+      return solve_srbd_variant(ctx);
+  }
   const QpLayout& L = ctx->L;
   const size_t B = ctx->B, S = L.N + 1, N = L.N;
   if (ctx->export_ric && !ctx->d_P) {
