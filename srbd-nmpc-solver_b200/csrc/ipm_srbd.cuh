@@ -656,7 +656,7 @@ struct SrbdSolver {
   }
 };
 
-__global__ void __launch_bounds__(128) ipm_srbd_kernel(const SrbdIpmParams p) {
+__global__ void __launch_bounds__(128, 4) ipm_srbd_kernel(const SrbdIpmParams p) {
   extern __shared__ double2 smem2[];
   double* smem = reinterpret_cast<double*>(smem2);
   __shared__ int s_next[v2::kWarps];
