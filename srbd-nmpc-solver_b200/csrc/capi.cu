@@ -582,7 +582,14 @@ int srbd_qp_solve(srbd_ctx* ctx) {
   {
     const char* force = std::getenv("SRBD_K3_GENERIC");
     const bool generic = force && force[0] == '1';
-    if (!generic && ctx->is_srbd && ctx->assembled_mode == SRBD_HARD_INEQ && !ctx->args.warm_start &&
+    // the variant relies on Ac being two 12x6 blocks (SRBD_model.cpp:244: Ac.block<12,6>(12*leg, 6*leg))
+    double Ac[288];
+    fill_Ac(ctx->model, Ac);
+    bool blocks = true;
+    for (int g = 0; g < 24; ++g)
+      for (int j = 0; j < 12; ++j)
+        if (Ac[g * 12 + j] != 0.0 && (j / 6) != (g / 12)) blocks = false;
+    if (!generic && blocks && ctx->is_srbd && ctx->assembled_mode == SRBD_HARD_INEQ && !ctx->args.warm_start &&
         !ctx->export_ric && !ctx->export_stat)
       return solve_srbd_variant(ctx);
   }
