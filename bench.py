@@ -266,7 +266,7 @@ def main():
         if os.path.exists(tpath):  # dram bytes of K3 from the committed `ncu --set full` capture, scaled per QP
             tj = json.load(open(tpath))
             traffic, traffic_src = tj["dram_bytes_per_qp"] * B, tj["source"]
-        roofline = {"bound": "fp64", "kernel": "ipm_solve_kernel (K3)", "achieved": achieved, "peak": peak,
+        roofline = {"bound": "fp64", "kernel": "ipm_srbd_kernel (K3)", "achieved": achieved, "peak": peak,
                     "unit": "TFLOP/s", "frac": achieved / peak if peak > 0 else None, "traffic": traffic,
                     "traffic_source": traffic_src,
                     "peak_source": "measured live: DFMA-saturating microbenchmark srbd_fp64_peak() (MEASURED_PEAKS.json "
