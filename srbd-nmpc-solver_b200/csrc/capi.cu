@@ -263,10 +263,7 @@ int srbd_set_model(srbd_ctx* ctx, const srbd_model_params* p) {
 int srbd_set_ipm_args(srbd_ctx* ctx, const srbd_ipm_args* a) {
   if (!ctx || !a) return SRBD_ERR_ARG;
   if (a->iter_max < 0 || a->iter_max > 1000) return fail(ctx, SRBD_ERR_ARG, "iter_max out of range");
-  if (a->ric_alg != 0)
-    return fail(ctx, SRBD_ERR_UNSUPPORTED,
-                "ric_alg=1 (square-root Riccati) is not implemented on the GPU path yet; use ric_alg=0 "
-                "(classical, what NMPC_solver.cpp:81 selects)");
+  if (a->ric_alg != 0 && a->ric_alg != 1) return fail(ctx, SRBD_ERR_ARG, "ric_alg must be 0 (classical) or 1 (square root)");
   ctx->args = *a;
   const int rows = a->iter_max + 2;
   if (rows != ctx->stat_rows) {
@@ -590,6 +587,7 @@ int srbd_qp_solve(srbd_ctx* ctx) {
       for (int j = 0; j < 12; ++j)
         if (Ac[g * 12 + j] != 0.0 && (j / 6) != (g / 12)) blocks = false;
     if (!generic && blocks && ctx->is_srbd && ctx->assembled_mode == SRBD_HARD_INEQ && !ctx->args.warm_start &&
+        ctx->args.ric_alg == 0 &&
         !ctx->export_ric && !ctx->export_stat)
       return solve_srbd_variant(ctx);
   }

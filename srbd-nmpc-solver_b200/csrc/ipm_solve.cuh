@@ -115,7 +115,7 @@ struct Solver {
   static constexpr int LDP = ((D::kNX + 1) & 1) ? (D::kNX + 1) : (D::kNX + 2);
   static constexpr int LDI = (D::kNU & 1) ? D::kNU : (D::kNU + 1);
   static constexpr int kSmemDoubles = 2 * (D::kNM + 1) * LD + (D::kNX + 1) * LDP + D::kNU * LDI +
-                                      2 * D::kNCM + 4 * (D::kNM + 1) + 2 * (D::kNX + 1);
+                                      2 * D::kNCM + 4 * (D::kNM + 1) + 2 * (D::kNX + 1) + D::kNX * LDP;
   struct St {
     int k, nu, nx, n, nb, ng, nc, nxn, nun;
     const int* idxb;
@@ -126,7 +126,7 @@ struct Solver {
   D dm;
   int lane, q, N;
   double* W;
-  double *sM, *sB, *sP, *sLi, *sQx, *sqx, *sg, *st, *sx, *sxn, *sdinv, *spn;
+  double *sM, *sB, *sP, *sLi, *sQx, *sqx, *sg, *st, *sx, *sxn, *sdinv, *spn, *sLx;
   int* sIdx;
 
   __device__ Solver(const IpmParams& p_, double* smem, int* sidx)
@@ -144,6 +144,7 @@ struct Solver {
     sdinv = sx + (D::kNM + 1);     // kNM+1
     sxn = sdinv + (D::kNM + 1);    // kNX+1
     spn = sxn + (D::kNX + 1);      // kNX+1
+    sLx = spn + (D::kNX + 1);      // kNX * LDP: Lxx_{k+1} (square-root Riccati, ric_alg = 1)
     sIdx = sidx;
     for (int j = lane; j < kMaxNB; j += 32) {
       sIdx[j] = L.idxb0[j];
@@ -258,6 +259,7 @@ struct Solver {
   // packed data) instead of the step QP (rhs = res_g, res_b from the workspace).
   // ------------------------------------------------------------------------------------------------
   __device__ void backward(bool fact, bool constr, bool absolute) {
+    const bool sq = p.a.ric_alg == 1;
     for (int k = N; k >= 0; --k) {
       const St s = stage(k);
       const int n = s.n, nu = s.nu, nx = s.nx, nxn = s.nxn;
@@ -308,21 +310,24 @@ struct Solver {
           __syncwarp();
         }
         if (k < N) {
-          // [G | AL]: G (n x nxn) from BAbt, AL = G P_{k+1}
+          // [G | AL]: G (n x nxn) from BAbt.  classical (ric_alg 0): AL = G P_{k+1}, M += AL G^T (gemm_nt +
+          // syrk_ln_mn); square root (ric_alg 1): AL = G Lxx_{k+1} (trmm_rlnn), M += AL AL^T (syrk_dpotrf_ln_mn)
           load_pm(sB, LD, gBAbt(k), n, nxn, babt_cn());
           __syncwarp();
           if (lane < n) {
             for (int j = 0; j < nxn; ++j) {
               double acc = 0.0;
-              for (int l = 0; l < nxn; ++l) acc += sB[lane * LD + l] * sP[l * LDP + j];
+              if (sq) { for (int l = j; l < nxn; ++l) acc += sB[lane * LD + l] * sLx[l * LDP + j]; }
+              else { for (int l = 0; l < nxn; ++l) acc += sB[lane * LD + l] * sP[l * LDP + j]; }
               sB[lane * LD + nxn + j] = acc;
             }
           }
           __syncwarp();
           if (lane < n) {
+            const int off = sq ? nxn : 0;
             for (int c = 0; c <= lane; ++c) {
               double acc = 0.0;
-              for (int l = 0; l < nxn; ++l) acc += sB[lane * LD + nxn + l] * sB[c * LD + l];
+              for (int l = 0; l < nxn; ++l) acc += sB[lane * LD + nxn + l] * sB[c * LD + off + l];
               sM[lane * LD + c] += acc;
             }
           }
@@ -350,8 +355,10 @@ struct Solver {
         // gradient row n of M (the "+1 row" of potrf_l_mn)
         if (lane < n) sM[n * LD + lane] = sg[lane];
         __syncwarp();
-        // ---- partial Cholesky of the leading nu columns over rows 0..n (left-looking, row-parallel)
-        for (int j = 0; j < nu; ++j) {
+        // ---- Cholesky over rows 0..n (left-looking, row-parallel): the leading nu columns (classical:
+        //      potrf_l_mn(n+1, nu)) or all n columns (square root)
+        const int ncol = sq ? n : nu;
+        for (int j = 0; j < ncol; ++j) {
           double sacc = 0.0;
           if (lane >= j && lane <= n) {
             sacc = sM[lane * LD + j];
@@ -361,7 +368,7 @@ struct Solver {
           const double inv = dj > 0.0 ? rsqrt(dj) : 0.0;
           if (lane == j) {
             sM[j * LD + j] = dj * inv;
-            sdinv[j] = inv;
+            if (j < nu) sdinv[j] = inv;
           } else if (lane > j && lane <= n) {
             sM[lane * LD + j] = sacc * inv;
           }
@@ -386,10 +393,22 @@ struct Solver {
             const int i = e / nx, c = e - i * nx;  // i == nx: gradient row
             // lower triangle of M holds the data: element (a,b) with a >= b
             const int a = nu + i, b = nu + c;
-            double acc = (i == nx || i >= c) ? sM[a * LD + b] : sM[b * LD + a];
-            for (int l = 0; l < nu; ++l) acc -= sM[a * LD + l] * sM[b * LD + l];
+            double acc;
+            if (sq) {  // P = Lxx Lxx^T, p = Lxx l_x  (M now holds the full factor)
+              acc = 0.0;
+              const int lmax = (i == nx) ? c : (i < c ? i : c);
+              for (int l = 0; l <= lmax; ++l) acc += sM[a * LD + nu + l] * sM[b * LD + nu + l];
+            } else {
+              acc = (i == nx || i >= c) ? sM[a * LD + b] : sM[b * LD + a];
+              for (int l = 0; l < nu; ++l) acc -= sM[a * LD + l] * sM[b * LD + l];
+            }
             sP[i * LDP + c] = acc;
           }
+          if (sq)
+            for (int e = lane; e < nx * nx; e += 32) {
+              const int i = e / nx, c = e - i * nx;
+              sLx[i * LDP + c] = (c <= i) ? sM[(nu + i) * LD + nu + c] : 0.0;
+            }
         }
         __syncwarp();
         // ---- store factors ------------------------------------------------------------------------------

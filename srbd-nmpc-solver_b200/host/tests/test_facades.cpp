@@ -75,8 +75,7 @@ static void test_unconstrained() {
   const int nx = 5, nu = 3, N = 20;
   auto qp = randomQp(nx, nu, N, 1.0, true);
   const VectorXd x0 = RndV(nx);
-  hpipm::OcpQpIpmSolverSettings s;
-  s.ric_alg = 0;  // the GPU path implements the classical Riccati (what NMPC_solver.cpp:81 selects)
+  hpipm::OcpQpIpmSolverSettings s;  // defaults like the reference test: ric_alg = 1 (square-root Riccati)
   std::vector<hpipm::OcpQpSolution> sol(N + 1);
   hpipm::OcpQpIpmSolver solver(qp, s);
   const auto status = solver.solve(x0, qp, sol);

@@ -206,20 +206,21 @@ def test_compare_results_golden_on_gpu(pkg, orc, golden_quadcopter):
             x = A @ x + Bm @ sol["u"][0, 0]
 
 
-def test_unconstrained_analytic_on_gpu(pkg, orc):
+@pytest.mark.parametrize("ric_alg", [0, 1])
+def test_unconstrained_analytic_on_gpu(pkg, orc, ric_alg):
     """hpipm-cpp/test/ocp_qp_ipm_solver.cpp:22-110: iter == 0 and x,u,pi,P,p,K,k at isApprox(1e-10) vs the
     oracle (which is itself pinned to the textbook Riccati recursion in tests/test_oracle_qp.py)."""
     from srbd_nmpc_solver_b200.binding import make_dims
     B = 8
     dims_d, arrays = pkg.workload.random_qp(B, N=20, nx=5, nu=3, seed=7)
     dims = make_dims(**dims_d)
-    with make_ctx(pkg, B, dims=dims, settings=dict(SETTINGS, iter_max=15)) as ctx:
+    with make_ctx(pkg, B, dims=dims, settings=dict(SETTINGS, iter_max=15, ric_alg=ric_alg)) as ctx:
         ctx.set_outputs(export_ric=True, export_stat=True)
         ctx.qp_upload(arrays)
         ctx.qp_solve()
         sol = ctx.download_solution()
         st = ctx.download_stats(with_table=True)
-    ref = orc.qp_solve(dims, orc.ipm_args(ric_alg=0), arrays, B)
+    ref = orc.qp_solve(dims, orc.ipm_args(ric_alg=ric_alg), arrays, B)
     assert (st["iter"] == 0).all() and (st["status"] == 0).all()
     for k in ("x", "u", "pi", "P", "p", "K", "k"):
         for i in range(B):
@@ -230,14 +231,15 @@ def test_unconstrained_analytic_on_gpu(pkg, orc):
 @pytest.mark.parametrize("shape", [dict(nx=5, nu=3, ng=2, nbx=2, nbu=3),      # compiled instantiation
                                    dict(nx=6, nu=2, ng=3, nbx=1, nbu=2),      # run-time dims fallback
                                    dict(nx=4, nu=4, ng=0, nbx=0, nbu=4)])
-def test_constrained_random_on_gpu(pkg, orc, shape):
+@pytest.mark.parametrize("ric_alg", [0, 1])
+def test_constrained_random_on_gpu(pkg, orc, shape, ric_alg):
     """hpipm-cpp/test/ocp_qp_ipm_solver.cpp:112-168 shapes (box on u, box on x, general rows, terminal
     general rows): GPU vs oracle iterates, iteration counts, statistics table, Riccati exports."""
     from srbd_nmpc_solver_b200.binding import make_dims
     B = 16
     dims_d, arrays = pkg.workload.random_qp(B, N=12, seed=11, a_scale=0.4, **shape)
     dims = make_dims(**dims_d)
-    settings = dict(SETTINGS, iter_max=40, tol_stat=1e-6)
+    settings = dict(SETTINGS, iter_max=40, tol_stat=1e-6, ric_alg=ric_alg)
     with make_ctx(pkg, B, dims=dims, settings=settings) as ctx:
         ctx.set_outputs(export_ric=True, export_stat=True)
         ctx.qp_upload(arrays)
@@ -321,7 +323,7 @@ def test_c_abi_error_behaviour(pkg):
         with pytest.raises(SrbdError, match="no QP data"):
             ctx.qp_solve()
         with pytest.raises(SrbdError, match="ric_alg"):
-            ctx.set_ipm_args(pkg.default_ipm_args(ric_alg=1))
+            ctx.set_ipm_args(pkg.default_ipm_args(ric_alg=2))
     dims_d, arrays = pkg.workload.random_qp(2, N=5, nx=5, nu=3, nbu=3, seed=1)
     with make_ctx(pkg, 2, dims=make_dims(**dims_d), settings=dict(SETTINGS, warm_start=1)) as ctx:
         ctx.qp_upload(arrays)
