@@ -7,16 +7,27 @@
 //     contact)                       -> Ac lives in shared memory; D^T Gamma D = sum_g Gamma_g W_g with the 21
 //                                       lower-triangle products W_g of each row's 6-vector precomputed per CTA;
 //   * only the lower side of the rows is active (ug masked), no box constraints, cold start.
-// Mapping: 4 independent warps per CTA, one QP per warp, persistent grid + atomic work counter.  Row i of the
-// stage matrix [H~; g~^T] lives in the REGISTERS of lane i (m[24]), G rows too; broadcast operands come from
-// shared memory four at a time (BLASFEO-style 4-wide panels, LDS.128): AL = G P, M += AL G^T, the Schur
-// complement and the left-looking row-parallel Cholesky.
-// Memory: the solve is a sequence of sweeps over the stages (S1 backward factorization, S2 forward rollout
-// fused with dlam/dt and the step length, S3 mu_aff, S4 vector-only backward with the centering correction
-// applied on the fly, S5 = S2, S6 variable update fused with the residuals).  Every sweep is SOFTWARE
-// PIPELINED: while stage k is computed, the tiles of the next stage (BAbt record, P / L^-1 / Ls^T factors,
-// the R block of RSQrq) stream into the other half of a shared-memory double buffer with cp.async, and the
-// next stage's per-row vectors are prefetched into registers, so HBM/L2 latency overlaps the FP64 work.
+// Mapping: 4 independent warps per CTA, one QP per warp, persistent grid + atomic work counter.
+// S1, the Riccati factorization sweep, runs on the FP64 tensor cores (mma.sync m8n8k4 f64, "DMMA"): one
+// instruction is 256 FMAs, i.e. 8 warp-wide DFMAs plus their shared-memory operand fetches in ONE issue slot
+// (scripts/microbench/fp64_pipes.cu: DMMA and DFMA share the FP64 pipe on B200, 36.9 vs 35.8 TFLOP/s, so the
+// gain is issue slots, not peak).  The stage matrix lives in the registers as 8x4 FRAGMENTS
+//     F[I][p] : lane (r = lane>>2, t = lane&3) holds M[8I + r][4p + t]
+// which is at the same time the A-operand layout (row r, k = t), the B-operand layout of the transposed tile and,
+// when the B operand's rows are permuted by pi(r) = (r>>1) + 4(r&1), the two halves of the accumulator tile:
+//     D(8x8) = A(8x4) . B(4x8)^T-rows-permuted  ->  c0 = F[I][2J], c1 = F[I][2J+1].
+// So AL = G P, M = H + AL G^T and the trailing updates of the blocked (4-column BLASFEO-style panels) Cholesky
+// chain without any register shuffles: 18 + 18 + 15 DMMA per stage.  The 4-column panels themselves are solved
+// row-per-lane through a [37][4] shared-memory panel (every lane factors the 4x4 diagonal block redundantly, then
+// substitutes its own row); 12 appended identity rows turn the same substitution into L^-T (what the vector sweeps
+// need), and the gradient ("+1 row" of potrf_l_mn) rides along as row 24.
+// The vector sweeps (S2/S5 forward rollout fused with dlam/dt and the step length, S4 vector-only backward with
+// the centering correction on the fly, S6 variable update fused with the residuals) are FP64 FMA loops with
+// row-per-lane registers and broadcast operands from shared memory.
+// Memory: every sweep is SOFTWARE PIPELINED: while stage k is computed, the tiles of the next stage (BAbt record,
+// P / factor panels, the R block of RSQrq) stream into the other half of a shared-memory double buffer with
+// cp.async, and the next stage's per-row vectors are prefetched into registers, so HBM/L2 latency overlaps the
+// FP64 work.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -48,16 +59,18 @@ namespace v2 {
 constexpr int kWarps = 4;
 // per-stage workspace block (doubles)
 constexpr int oZ = 0, oDZ = 24, oRG = 48, oLAM = 72, oT = 96, oDLAM = 120, oDT = 144, oRD = 168, oRM = 192, oRMB = 216,
-              oPI = 240, oDPI = 252, oRB = 264, oPV = 276, oLV = 288, oP = 300, oLI = 444, oLST = 588, kStage = 732;
+              oPI = 240, oDPI = 252, oRB = 264, oPV = 276, oLV = 288, oP = 300, oFT = 444, kStage = 744;
+// factor tile of a stage: 3 column panels x [25 rows][4]: rows 0..11 = rows of L^-T (E rows), 12..23 = Ls, 24 = lv
+constexpr int kPanF = 100;         // doubles of a panel that the vector sweeps need (rows 0..24)
+constexpr int kPan = 148;          // the full panel during the factorization: + rows 25..36 = rows 0..11 of L
 // shared memory (doubles)
 constexpr int kGP = 52;            // padded panel stride of the BAbt tile (4 rows x 12 cols + 4)
-constexpr int kLT = 26;            // row stride of L^T
 constexpr int kW2 = 22;            // row stride of W (21 lower-triangle products of a constraint row's 6-vector)
 constexpr int sAC = 0;             // [24][12] constraint Jacobian, row-major
 constexpr int sW = sAC + 288;      // [24][22]
 constexpr int kCtaShared = sW + 24 * kW2;
 constexpr int kGT = 7 * kGP;       // 364: one BAbt tile
-constexpr int kFT = 432;           // [P 144 | Linv 144 | Ls^T 144]
+constexpr int kFT = 144 + 3 * kPanF;  // 444: [P 144 | factor panels 300]
 constexpr int kRT = 132;           // [R lower-panel prefixes 96 | Q diag 12 | rq row 24]
 constexpr int wG0 = 0, wG1 = kGT;
 constexpr int wF0 = 2 * kGT, wF1 = wF0 + kFT;
@@ -70,13 +83,13 @@ constexpr int wSX = wSG + 24;      // 24 z of the current stage
 constexpr int wXN = wSX + 24;      // 12 x_{k+1} / pi_k
 constexpr int wT = wXN + 12;       // 12 t / lv
 constexpr int wPV = wT + 12;       // 12 p_{k+1}
-constexpr int wDI = wPV + 12;      // 12 1/L_jj
+constexpr int wDI = wPV + 12;      // 12 (spare)
 constexpr int wLAM = wDI + 12;     // 24 lam (residual sweep)
 constexpr int kWarpShared = wLAM + 24;
 constexpr int kSmemBytes = (kCtaShared + kWarps * kWarpShared) * 8;
-// in the factorization sweep the factor buffers are free: L^T and the running P_{k+1} live there
-constexpr int wLT = wF0;           // [12][26] = 312 <= 432
-constexpr int wP = wF1;            // [13][12] = 156 <= 432
+// in the factorization sweep the factor buffers are free: the running P_{k+1} and the three panels live there
+constexpr int wP = wF0;            // [12][12] + p (12)          156 -> 160
+constexpr int wPAN = wF0 + 160;    // 3 x [37][4]                444      (604 <= 2 * 444)
 }  // namespace v2
 
 __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
@@ -91,6 +104,27 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 
+// D(8x8) = A(8x4) * B(4x8) + C on the FP64 tensor cores; fragment layout in the header comment
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b, double c0, double c1) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};\n"
+      : "=d"(d0), "=d"(d1)
+      : "d"(a), "d"(b), "d"(c0), "d"(c1));
+}
+// sqrt(x) and 1/sqrt(x) for a positive pivot: MUFU.RSQ64H seed + two Goldschmidt steps (no special-case
+// branches; a non-positive pivot gives s = inv = 0 like BLASFEO's potrf, cf. oracle/ocp_qp_ipm.c potrf_l_mn)
+__device__ __forceinline__ void sqrt_rsqrt(double x, double& s, double& inv) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;\n" : "=d"(y) : "d"(x));
+  double g = x * y, h = 0.5 * y;
+  double r = fma(-g, h, 0.5);
+  g = fma(g, r, g); h = fma(h, r, h);
+  r = fma(-g, h, 0.5);
+  g = fma(g, r, g); h = fma(h, r, h);
+  const bool ok = x > 0.0;
+  s = ok ? g : 0.0;
+  inv = ok ? h + h : 0.0;
+}
+
 struct SrbdSolver {
   const SrbdIpmParams& p;
   int lane, q, N;
@@ -101,6 +135,9 @@ struct SrbdSolver {
   const double* sG;   // current BAbt tile
   const double* sF;   // current factor tile
   const double* sR;   // current R tile
+  // fragment coordinates of this lane (see the header comment)
+  int fr, ft, fpi;
+  int offS[5];        // index into the 42 D^T Gamma D sums of this lane's element of the u-block fragments, or -1
 
   __device__ SrbdSolver(const SrbdIpmParams& p_, double* cta, double* warp_sm, int warp_global)
       : p(p_), lane(threadIdx.x & 31), q(0), N(p_.N) {
@@ -109,6 +146,19 @@ struct SrbdSolver {
     cW = cta + v2::sW;
     sm = warp_sm;
     sG = sm; sF = sm + v2::wF0; sR = sm + v2::wR0;
+    fr = lane >> 2; ft = lane & 3; fpi = (fr >> 1) + 4 * (fr & 1);
+    // u-block fragments in the order (I,p) = (0,0) (0,1) (1,0) (1,1) (1,2)
+#pragma unroll
+    for (int f = 0; f < 5; ++f) {
+      const int I = f < 2 ? 0 : 1, pp = f < 2 ? f : f - 2;
+      const int i = 8 * I + fr, c = 4 * pp + ft;
+      int o = -1;
+      if (i < 12 && c <= i && (i / 6) == (c / 6)) {
+        const int leg = i / 6, ii = i - 6 * leg, cc = c - 6 * leg;
+        o = 21 * leg + ii * (ii + 1) / 2 + cc;
+      }
+      offS[f] = o;
+    }
   }
   __device__ __forceinline__ double* ws(int k, int off) const { return W + (size_t)k * v2::kStage + off; }
   __device__ __forceinline__ const double* gBAbt(int k) const { return p.babt + ((size_t)q * N + k) * 336; }
@@ -130,16 +180,16 @@ struct SrbdSolver {
       }
     }
   }
-  // P_{kP} and Linv | Ls^T of stage kL (contiguous 288 doubles in the workspace)
+  // P_{kP} (144) and the factor panels of stage kL (3 x 100)
   __device__ __forceinline__ void prefetch_F(int kP, int kL, int b) {
     double* dst = sm + (b ? v2::wF1 : v2::wF0);
     const double* Ps = ws(kP, v2::oP);
-    const double* Ls = ws(kL, v2::oLI);
+    const double* Ls = ws(kL, v2::oFT);
 #pragma unroll
     for (int i = 0; i < 7; ++i) {
       const int c = lane + 32 * i;
       if (c < 72) cp_async16(dst + 2 * c, Ps + 2 * c);
-      else if (c < 216) cp_async16(dst + 2 * c, Ls + 2 * (c - 72));
+      else if (c < 222) cp_async16(dst + 2 * c, Ls + 2 * (c - 72));
     }
   }
   // R block of RSQrq (rows 0..11, lower: prefixes of panels 0..2), the diagonal of Q, the gradient row n
@@ -189,7 +239,19 @@ struct SrbdSolver {
   __device__ void sweep_factor() {
     const double reg = p.a.reg_prim;
     double* sP = sm + v2::wP;
-    double* sLt = sm + v2::wLT;
+    double* sPan = sm + v2::wPAN;
+    const int r = fr, t = ft, pi = fpi;
+    // per-lane fragment offsets: BAbt tile (A operand rows r, B operand rows pi(r)), panel rows (M row m lives in
+    // panel row (m < 12 ? 25 + m : m), E row i in row i, the gradient in row 24)
+    const int gA = (r >> 2) * v2::kGP + 4 * t + (r & 3);
+    const int gB = (pi >> 2) * v2::kGP + 4 * t + (pi & 3);
+    const int prA0 = (25 + r) * 4 + t, prA1 = (r < 4 ? 33 + r : 8 + r) * 4 + t, prA2 = (16 + r) * 4 + t;
+    const int prB0 = (25 + pi) * 4 + t, prB1 = (pi < 4 ? 33 + pi : 8 + pi) * 4 + t, prB2 = (16 + pi) * 4 + t;
+    const int prE0 = r * 4 + t;
+    const bool dg0 = (r == t), dg1 = (r == 4 + t);
+    const double regd0 = dg0 ? reg : 0.0, regd1 = dg1 ? reg : 0.0;
+    const int rel0 = ((r >> 2) ? 16 : 0) + (r & 3) + 4 * t;  // R(i, c) of rows 0..7:  + 16 * (c >> 2)
+    const int rel1 = 48 + (r & 3) + 4 * t;                   // rows 8..11 (r < 4)
     // start streaming stage N-1 while stage N is handled
     prefetch_G(N - 1, 0);
     prefetch_R(N - 1, 0);
@@ -215,7 +277,8 @@ struct SrbdSolver {
     }
     for (int k = N - 1; k >= 0; --k) {
       const int b = (N - 1 - k) & 1;
-      const int nx = k > 0 ? 12 : 0, n = 12 + nx;  // nu = 12; gradient row lives in lane n
+      const bool xr = k > 0;                 // the stage has x rows (rows 12..23)
+      const int n = xr ? 24 : 12;
       cp_async_wait_all();
       __syncwarp();  // stage k's tiles have landed; every lane is done with the other buffers
       set_bufs(b);
@@ -225,40 +288,48 @@ struct SrbdSolver {
         prefetch_R(k - 1, b ^ 1);
         nxt = load_s1(k - 1);
       }
-      // ---- own row of H (lower): R block rows from the tile, Q diagonal on the x rows ---------------------
-      double m[24];
-#pragma unroll
-      for (int c = 0; c < 24; ++c) m[c] = 0.0;
-      if (lane < 12) {
-#pragma unroll
-        for (int c = 0; c < 12; ++c)
-          if (c <= lane) m[c] = Rel(lane, c);
-      } else if (lane < n) {
-#pragma unroll
-        for (int c = 12; c < 24; ++c)
-          if (c == lane) m[c] = sR[96 + (c - 12)];
-      }
       if (lane < 24) {
         const double ti = 1.0 / cur.t;
         sm[v2::wQX + lane] = (ti * cur.lam) * cur.mk;
         sm[v2::wqx + lane] = (ti * (cur.rm - cur.lam * cur.rd)) * cur.mk;
       }
-      double grow = (lane < n) ? cur.rg : 0.0;  // gradient entry c = lane
-      const double rbv = (lane < 12) ? cur.rb : 0.0;
+      if (lane < 12) sm[v2::wXN + lane] = cur.rb;
+      double grow = (lane < n) ? cur.rg : 0.0;  // gradient entry of row `lane`
       __syncwarp();
-      // ---- gradient: rg + D^T gamma (u part; a contact's rows only touch its own 6 inputs) ------------------
+      // ---- operand fragments: G (A operand), G rows permuted (B operand), P_{k+1} (B operand) -------------------
+      double GF[3][3], GPF[3][3], PPF[2][3];
+      {
+        const bool okA1 = xr || r < 4, okB1 = xr || pi < 4;
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {
+          GF[0][kt] = sG[gA + 16 * kt];
+          const double a1 = sG[gA + 2 * v2::kGP + 16 * kt], a2 = sG[gA + 4 * v2::kGP + 16 * kt];
+          GF[1][kt] = okA1 ? a1 : 0.0;
+          GF[2][kt] = xr ? a2 : 0.0;
+          GPF[0][kt] = sG[gB + 16 * kt];
+          const double b1 = sG[gB + 2 * v2::kGP + 16 * kt], b2 = sG[gB + 4 * v2::kGP + 16 * kt];
+          GPF[1][kt] = okB1 ? b1 : 0.0;
+          GPF[2][kt] = xr ? b2 : 0.0;
+          PPF[0][kt] = sP[pi * 12 + 4 * kt + t];
+          const double p1 = sP[(8 + (pi & 3)) * 12 + 4 * kt + t];
+          PPF[1][kt] = pi < 4 ? p1 : 0.0;
+        }
+      }
+      // ---- vector stream: t = P_{k+1} rb + p_{k+1}; gradient += D^T gamma; the 42 sums of D^T Gamma D ----------
       if (lane < 12) {
-        const int g0 = lane < 6 ? 0 : 12;
         double acc = 0.0;
 #pragma unroll
-        for (int g = 0; g < 12; ++g) acc += cAc[(g0 + g) * 12 + lane] * sm[v2::wqx + g0 + g];
-        grow += acc;
-      }
-      if (lane < n) sm[v2::wSG + lane] = grow;
-      // ---- D^T Gamma D: two 6x6 blocks, 21 lower-triangle entries each, spread over the warp -----------------
+        for (int j = 0; j < 12; ++j) acc += sP[lane * 12 + j] * sm[v2::wXN + j];
+        sm[v2::wT + lane] = acc + sP[144 + lane];
+        const int g0 = lane < 6 ? 0 : 12;
+        double a2 = 0.0;
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int e2 = lane + 32 * r;
+        for (int g = 0; g < 12; ++g) a2 += cAc[(g0 + g) * 12 + lane] * sm[v2::wqx + g0 + g];
+        grow += a2;
+      }
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int e2 = lane + 32 * rr;
         if (e2 < 42) {
           const int leg = e2 >= 21 ? 1 : 0, e = e2 - 21 * leg;
           double acc = 0.0;
@@ -267,125 +338,168 @@ struct SrbdSolver {
           sm[v2::wS + e2] = acc;
         }
       }
-      __syncwarp();
-      if (lane == n) {
+      // ---- AL = G P_{k+1}: fragments ALF[I][0..2] (columns 0..3, 4..7, 8..11) -------------------------------------
+      double ALF[3][3];
 #pragma unroll
-        for (int c = 0; c < 24; ++c) m[c] = (c < n) ? sm[v2::wSG + c] : 0.0;
-      }
-      if (lane < 12) {
-        const int leg = lane < 6 ? 0 : 1, ii = lane - 6 * leg;
-        const int base = 21 * leg + ii * (ii + 1) / 2;
+      for (int I = 0; I < 3; ++I) {
+        if (I < 2 || xr) {
+          double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
 #pragma unroll
-        for (int c = 0; c < 12; ++c) {
-          const int cc = c - 6 * leg;
-          if (cc >= 0 && cc <= ii) m[c] += sm[v2::wS + base + cc];
-        }
-      }
-      // ---- own G row (lane n: the rb row), AL = G P_{k+1} (+ p_{k+1} on the gradient row) ------------------------
-      double g[12], al[12];
-#pragma unroll
-      for (int l = 0; l < 12; ++l) g[l] = (lane < n) ? Gel(lane, l) : 0.0;
-#pragma unroll
-      for (int l = 0; l < 12; ++l) {
-        const double rbl = __shfl_sync(kFull, rbv, l);
-        if (lane == n) g[l] = rbl;
-      }
-#pragma unroll
-      for (int j = 0; j < 12; ++j) al[j] = (lane == n) ? sP[144 + j] : 0.0;
-#pragma unroll
-      for (int l = 0; l < 12; ++l) {
-#pragma unroll
-        for (int j4 = 0; j4 < 3; ++j4) {
-          const double2 p01 = *reinterpret_cast<const double2*>(sP + l * 12 + 4 * j4);
-          const double2 p23 = *reinterpret_cast<const double2*>(sP + l * 12 + 4 * j4 + 2);
-          al[4 * j4 + 0] += g[l] * p01.x;
-          al[4 * j4 + 1] += g[l] * p01.y;
-          al[4 * j4 + 2] += g[l] * p23.x;
-          al[4 * j4 + 3] += g[l] * p23.y;
-        }
-      }
-      // ---- M += AL G^T, four columns (= four G rows of one panel) per pair of LDS.128 ------------------------
-#pragma unroll
-      for (int pc = 0; pc < 6; ++pc) {
-        if (4 * pc < n) {
-          double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll
-          for (int l = 0; l < 12; ++l) {
-            const double2 g01 = *reinterpret_cast<const double2*>(sG + pc * v2::kGP + 4 * l);
-            const double2 g23 = *reinterpret_cast<const double2*>(sG + pc * v2::kGP + 4 * l + 2);
-            a0 += al[l] * g01.x; a1 += al[l] * g01.y; a2 += al[l] * g23.x; a3 += al[l] * g23.y;
+          for (int kt = 0; kt < 3; ++kt) {
+            dmma(c0, c1, GF[I][kt], PPF[0][kt], c0, c1);
+            dmma(e0, e1, GF[I][kt], PPF[1][kt], e0, e1);
           }
-          m[4 * pc + 0] += a0; m[4 * pc + 1] += a1; m[4 * pc + 2] += a2; m[4 * pc + 3] += a3;
+          ALF[I][0] = c0; ALF[I][1] = c1; ALF[I][2] = e0;
+        } else {
+          ALF[I][0] = 0.0; ALF[I][1] = 0.0; ALF[I][2] = 0.0;
         }
       }
+      // ---- M = (H + D^T Gamma D) + AL G^T + reg I: lower 8x8 tiles, MF[I][2J], MF[I][2J+1] ------------------------
+      double MF[3][6];
 #pragma unroll
-      for (int c = 0; c < 24; ++c)
-        if (c == lane && lane < n) m[c] += reg;
-      // ---- partial Cholesky of the 12 u-columns over rows 0..n (left-looking, row-parallel) -------------------
+      for (int I = 0; I < 3; ++I)
 #pragma unroll
-      for (int j = 0; j < 12; ++j) {
-        double s = m[j];
+        for (int J = 0; J <= I; ++J) {
+          double c0 = 0.0, c1 = 0.0;
+          if (I < 2 || xr) {
 #pragma unroll
-        for (int l = 0; l < j; ++l) s -= m[l] * sLt[l * v2::kLT + j];
-        const double dj = __shfl_sync(kFull, s, j);
-        const double inv = dj > 0.0 ? rsqrt(dj) : 0.0;
-        const double val = (lane == j) ? dj * inv : s * inv;
-        m[j] = val;
-        if (lane >= j && lane <= n) sLt[j * v2::kLT + lane] = val;
-        if (lane == j) sm[v2::wDI + j] = inv;
-        __syncwarp();
-      }
-      // ---- Linv (column-parallel substitution on the identity), straight to the workspace -----------------------
-      if (lane < 12) {
-        double xc[12];
-#pragma unroll
-        for (int i = 0; i < 12; ++i) xc[i] = (i == lane) ? sm[v2::wDI + i] : 0.0;
-#pragma unroll
-        for (int i = 1; i < 12; ++i) {
-          double acc = 0.0;
-#pragma unroll
-          for (int l = 0; l < i; ++l) acc += sLt[l * v2::kLT + i] * xc[l];
-          if (i > lane) xc[i] = -acc * sm[v2::wDI + i];
-        }
-        double* Li = ws(k, v2::oLI);
-#pragma unroll
-        for (int i = 0; i < 12; ++i) Li[i * 12 + lane] = xc[i];
-        ws(k, v2::oLV)[lane] = sLt[lane * v2::kLT + n];  // lv = row n of L
-      }
-      // ---- Schur complement on the x rows (lanes 12..23) and the gradient row (lane n) --------------------------
-      if (nx > 0) {
-        double pr[12];
-#pragma unroll
-        for (int c = 0; c < 12; ++c) pr[c] = m[12 + c];
-        if (lane >= 12 && lane <= n) {
-#pragma unroll
-          for (int c4 = 0; c4 < 3; ++c4) {
-#pragma unroll
-            for (int l = 0; l < 12; ++l) {
-              const double2 l01 = *reinterpret_cast<const double2*>(sLt + l * v2::kLT + 12 + 4 * c4);
-              const double2 l23 = *reinterpret_cast<const double2*>(sLt + l * v2::kLT + 12 + 4 * c4 + 2);
-              pr[4 * c4 + 0] -= m[l] * l01.x; pr[4 * c4 + 1] -= m[l] * l01.y;
-              pr[4 * c4 + 2] -= m[l] * l23.x; pr[4 * c4 + 3] -= m[l] * l23.y;
-            }
+            for (int kt = 0; kt < 3; ++kt) dmma(c0, c1, ALF[I][kt], GPF[J][kt], c0, c1);
           }
+          MF[I][2 * J] = c0; MF[I][2 * J + 1] = c1;
         }
-        __syncwarp();  // everyone is done reading P_{k+1}
-        if (lane >= 12 && lane < 24) {
-          const int i = lane - 12;
+      __syncwarp();  // wS, wT visible
+      if (lane < n) {
+        double acc = 0.0;
 #pragma unroll
-          for (int c = 0; c < 12; ++c)
-            if (c <= i) { sP[i * 12 + c] = pr[c]; sP[c * 12 + i] = pr[c]; }
-        } else if (lane == 24) {
+        for (int l = 0; l < 12; ++l) acc += Gel(lane, l) * sm[v2::wT + l];
+        grow += acc;
+      }
+      {
+        // u block (rows < 12): R lower + D^T Gamma D, fragments (0,0) (0,1) (1,0) (1,1) (1,2)
+        double hf[5];
 #pragma unroll
-          for (int c = 0; c < 12; ++c) sP[144 + c] = pr[c];
+        for (int f = 0; f < 5; ++f) {
+          const int I = f < 2 ? 0 : 1, pp = f < 2 ? f : f - 2;
+          const bool valid = (8 * I + r < 12) && (4 * pp + t <= 8 * I + r);
+          double v = 0.0;
+          if (valid) v = sR[(I == 0 ? rel0 : rel1) + 16 * pp];
+          if (offS[f] >= 0) v += sm[v2::wS + offS[f]];
+          hf[f] = v;
         }
+        MF[0][0] = (hf[0] + MF[0][0]) + regd0;
+        MF[0][1] = (hf[1] + MF[0][1]) + regd1;
+        MF[1][0] = hf[2] + MF[1][0];
+        MF[1][1] = hf[3] + MF[1][1];
+        MF[1][2] = (hf[4] + MF[1][2]) + regd0;
+        // x block: diagonal of Q (rows 12..23)
+        const double q3 = (xr && dg1) ? sR[96 + t] : 0.0;
+        const double q4 = (xr && dg0) ? sR[100 + t] : 0.0;
+        const double q5 = (xr && dg1) ? sR[104 + t] : 0.0;
+        MF[1][3] = (q3 + MF[1][3]) + regd1;
+        MF[2][4] = (q4 + MF[2][4]) + regd0;
+        MF[2][5] = (q5 + MF[2][5]) + regd1;
+      }
+      // ---- blocked Cholesky of the 12 u columns: three 4-column panels ------------------------------------------
+      double EF1 = dg1 ? 1.0 : 0.0, EF2 = 0.0;  // E rows 0..7 (identity), columns 4..7 and 8..11
+#pragma unroll
+      for (int pp = 0; pp < 3; ++pp) {
+        double* pan = sPan + pp * v2::kPan;
+        if (pp < 2) pan[prA0] = MF[0][pp];
+        pan[prA1] = MF[1][pp];
+        pan[prA2] = MF[2][pp];
+        pan[prE0] = pp == 0 ? (dg0 ? 1.0 : 0.0) : (pp == 1 ? EF1 : EF2);
+        if (r < 4) pan[(8 + r) * 4 + t] = (pp == 2 && dg0) ? 1.0 : 0.0;  // E rows 8..11
+        if (lane >= 4 * pp && lane < 4 * pp + 4) pan[96 + lane - 4 * pp] = grow;
         __syncwarp();
-        for (int e = lane; e < 144; e += 32) {
-          ws(k, v2::oP)[e] = sP[e];
-          ws(k, v2::oLST)[e] = sLt[(e / 12) * v2::kLT + 12 + (e % 12)];  // Ls^T[l][i]
+        // every lane factors the 4x4 diagonal block (rows 25+4pp..) redundantly ...
+        const double* dgb = pan + (25 + 4 * pp) * 4;
+        const double a00 = dgb[0];
+        const double2 a1x = *reinterpret_cast<const double2*>(dgb + 4);
+        const double2 a2x = *reinterpret_cast<const double2*>(dgb + 8);
+        const double a22 = dgb[10];
+        const double2 a3x = *reinterpret_cast<const double2*>(dgb + 12);
+        const double2 a3y = *reinterpret_cast<const double2*>(dgb + 14);
+        // ... and substitutes its own row: M rows 4pp..23, the gradient (lane 24), E rows 0..4pp+3
+        const int prow = lane < 4 * pp ? 4 + lane : (lane < 12 ? 25 + lane : (lane < 25 ? lane : lane - 25));
+        double2* own = reinterpret_cast<double2*>(pan + prow * 4);
+        const double2 x01 = own[0], x23 = own[1];
+        double sq, i0, i1, i2, i3;
+        sqrt_rsqrt(a00, sq, i0);
+        const double L10 = a1x.x * i0, L20 = a2x.x * i0, L30 = a3x.x * i0;
+        sqrt_rsqrt(fma(-L10, L10, a1x.y), sq, i1);
+        const double L21 = fma(-L20, L10, a2x.y) * i1, L31 = fma(-L30, L10, a3x.y) * i1;
+        sqrt_rsqrt(fma(-L21, L21, fma(-L20, L20, a22)), sq, i2);
+        const double L32 = fma(-L31, L21, fma(-L30, L20, a3y.x)) * i2;
+        sqrt_rsqrt(fma(-L32, L32, fma(-L31, L31, fma(-L30, L30, a3y.y))), sq, i3);
+        const double l0 = x01.x * i0;
+        const double l1 = fma(-l0, L10, x01.y) * i1;
+        const double l2 = fma(-l1, L21, fma(-l0, L20, x23.x)) * i2;
+        const double l3 = fma(-l2, L32, fma(-l1, L31, fma(-l0, L30, x23.y))) * i3;
+        own[0] = make_double2(l0, l1);
+        own[1] = make_double2(l2, l3);
+        __syncwarp();
+        // gradient row: g[c] -= sum_l lv[l] L[c][l] for the rows below the panel
+        {
+          const double2 v01 = *reinterpret_cast<const double2*>(pan + 96);
+          const double2 v23 = *reinterpret_cast<const double2*>(pan + 98);
+          if (lane >= 4 * pp + 4 && lane < 24)
+            grow = fma(-v23.y, l3, fma(-v23.x, l2, fma(-v01.y, l1, fma(-v01.x, l0, grow))));
         }
+        // trailing updates M -= Lp Lp^T on the tensor cores (A = -L panel fragment, B = permuted fragment)
+        double dum;
+        if (pp == 0) {
+          const double nA0 = -pan[prA0], nA1 = -pan[prA1], nA2 = -pan[prA2], nAE = -pan[prE0];
+          const double B0 = pan[prB0], B1 = pan[prB1], B2 = pan[prB2];
+          dmma(dum, MF[0][1], nA0, B0, MF[0][0], MF[0][1]);
+          dmma(dum, MF[1][1], nA1, B0, MF[1][0], MF[1][1]);
+          dmma(MF[1][2], MF[1][3], nA1, B1, MF[1][2], MF[1][3]);
+          if (xr) {
+            dmma(dum, MF[2][1], nA2, B0, MF[2][0], MF[2][1]);
+            dmma(MF[2][2], MF[2][3], nA2, B1, MF[2][2], MF[2][3]);
+            dmma(MF[2][4], MF[2][5], nA2, B2, MF[2][4], MF[2][5]);
+          }
+          dmma(dum, EF1, nAE, B0, 0.0, EF1);
+          dmma(EF2, dum, nAE, B1, EF2, 0.0);
+        } else if (pp == 1) {
+          const double nA1 = -pan[prA1], nA2 = -pan[prA2], nAE = -pan[prE0];
+          const double B1 = pan[prB1], B2 = pan[prB2];
+          dmma(MF[1][2], MF[1][3], nA1, B1, MF[1][2], MF[1][3]);
+          if (xr) {
+            dmma(MF[2][2], MF[2][3], nA2, B1, MF[2][2], MF[2][3]);
+            dmma(MF[2][4], MF[2][5], nA2, B2, MF[2][4], MF[2][5]);
+          }
+          dmma(EF2, dum, nAE, B1, EF2, 0.0);
+        } else if (xr) {
+          const double nA1 = -pan[prA1], nA2 = -pan[prA2];
+          const double B1 = pan[prB1], B2 = pan[prB2];
+          dmma(dum, MF[1][3], nA1, B1, MF[1][2], MF[1][3]);
+          dmma(dum, MF[2][3], nA2, B1, MF[2][2], MF[2][3]);
+          dmma(MF[2][4], MF[2][5], nA2, B2, MF[2][4], MF[2][5]);
+        }
+      }
+      // ---- outputs: P_k (both triangles) and p_k for the next stage and the vector sweeps --------------------------
+      if (xr) {
+        // fragments (1,3): rows 12..15 x cols 12..15 (r >= 4); (2,3): rows 16..23 x cols 12..15;
+        // (2,4): x cols 16..19; (2,5): x cols 20..23
+        if (r >= 4 && t <= r - 4) { sP[(r - 4) * 12 + t] = MF[1][3]; sP[t * 12 + (r - 4)] = MF[1][3]; }
+        sP[(4 + r) * 12 + t] = MF[2][3]; sP[t * 12 + (4 + r)] = MF[2][3];
+        if (t <= r) { sP[(4 + r) * 12 + 4 + t] = MF[2][4]; sP[(4 + t) * 12 + 4 + r] = MF[2][4]; }
+        if (4 + t <= r) { sP[(4 + r) * 12 + 8 + t] = MF[2][5]; sP[(8 + t) * 12 + 4 + r] = MF[2][5]; }
+        if (lane >= 12 && lane < 24) sP[144 + lane - 12] = grow;
+        __syncwarp();
+        for (int e = lane; e < 72; e += 32)
+          reinterpret_cast<double2*>(ws(k, v2::oP))[e] = reinterpret_cast<const double2*>(sP)[e];
         if (lane < 12) ws(k, v2::oPV)[lane] = sP[144 + lane];
       }
+      // factor panels (rows 0..24: L^-T, Ls, lv) -> workspace
+#pragma unroll
+      for (int pp = 0; pp < 3; ++pp) {
+        const double2* src = reinterpret_cast<const double2*>(sPan + pp * v2::kPan);
+        double2* dst = reinterpret_cast<double2*>(ws(k, v2::oFT) + pp * v2::kPanF);
+        dst[lane] = src[lane];
+        if (lane < 18) dst[32 + lane] = src[32 + lane];
+      }
+      if (lane < 12) ws(k, v2::oLV)[lane] = sPan[(lane >> 2) * v2::kPan + 96 + (lane & 3)];
       cur = nxt;
     }
     __syncwarp();
@@ -458,19 +572,26 @@ struct SrbdSolver {
         sm[v2::wSG + lane] = grow + acc;
       }
       __syncwarp();
-      if (lane < 12) {  // lv = Linv g_u
+      if (lane < 12) {  // lv = Linv g_u   (Linv[i][j] = panel i/4, row j, column i%4; exact zeros above the diagonal)
+        const double* Li = sF + 144 + (lane >> 2) * v2::kPanF + (lane & 3);
         double acc = 0.0;
 #pragma unroll
-        for (int j = 0; j < 12; ++j)
-          if (j <= lane) acc += sF[144 + lane * 12 + j] * sm[v2::wSG + j];
+        for (int j = 0; j < 12; ++j) acc += Li[4 * j] * sm[v2::wSG + j];
         sm[v2::wT + lane] = acc;
         ws(k, v2::oLV)[lane] = acc;
       }
       __syncwarp();
-      if (lane < 12 && nx > 0) {  // p = g_x - Ls lv   (Ls[i][l] = LsT[l][i])
+      if (lane < 12 && nx > 0) {  // p = g_x - Ls lv   (Ls[i][l] = panel l/4, row 12+i, column l%4)
         double acc = sm[v2::wSG + 12 + lane];
 #pragma unroll
-        for (int l = 0; l < 12; ++l) acc -= sF[288 + l * 12 + lane] * sm[v2::wT + l];
+        for (int pp = 0; pp < 3; ++pp) {
+          const double2 l01 = *reinterpret_cast<const double2*>(sF + 144 + pp * v2::kPanF + (12 + lane) * 4);
+          const double2 l23 = *reinterpret_cast<const double2*>(sF + 144 + pp * v2::kPanF + (12 + lane) * 4 + 2);
+          acc -= l01.x * sm[v2::wT + 4 * pp];
+          acc -= l01.y * sm[v2::wT + 4 * pp + 1];
+          acc -= l23.x * sm[v2::wT + 4 * pp + 2];
+          acc -= l23.y * sm[v2::wT + 4 * pp + 3];
+        }
         sPV[lane] = acc;
         ws(k, v2::oPV)[lane] = acc;
       }
@@ -518,17 +639,24 @@ struct SrbdSolver {
       if (lane < 12) {  // t = Ls^T x + lv
         double acc = 0.0;
         if (nx > 0) {
+          const double* Lc = sF + 144 + (lane >> 2) * v2::kPanF + 48 + (lane & 3);
 #pragma unroll
-          for (int i = 0; i < 12; ++i) acc += sF[288 + lane * 12 + i] * sm[v2::wSX + 12 + i];
+          for (int i = 0; i < 12; ++i) acc += Lc[4 * i] * sm[v2::wSX + 12 + i];
         }
         sm[v2::wT + lane] = acc + cur.lv;
       }
       __syncwarp();
-      if (lane < 12) {  // u = -Linv^T t
+      if (lane < 12) {  // u = -Linv^T t   (row `lane` of L^-T: 4 contiguous values per panel, zeros left of the diagonal)
         double acc = 0.0;
 #pragma unroll
-        for (int j = 0; j < 12; ++j)
-          if (j >= lane) acc += sF[144 + j * 12 + lane] * sm[v2::wT + j];
+        for (int pp = 0; pp < 3; ++pp) {
+          const double2 l01 = *reinterpret_cast<const double2*>(sF + 144 + pp * v2::kPanF + lane * 4);
+          const double2 l23 = *reinterpret_cast<const double2*>(sF + 144 + pp * v2::kPanF + lane * 4 + 2);
+          acc += l01.x * sm[v2::wT + 4 * pp];
+          acc += l01.y * sm[v2::wT + 4 * pp + 1];
+          acc += l23.x * sm[v2::wT + 4 * pp + 2];
+          acc += l23.y * sm[v2::wT + 4 * pp + 3];
+        }
         sm[v2::wSX + lane] = -acc;
         ws(k, v2::oDZ)[lane] = -acc;
       }
