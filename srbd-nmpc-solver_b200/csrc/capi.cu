@@ -548,6 +548,10 @@ static int solve_srbd_variant(srbd_ctx* ctx) {
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ipm_srbd_kernel, 128, v2::kSmemBytes));
     if (occ < 1) return fail(ctx, SRBD_ERR_CUDA, "ipm_srbd_kernel does not fit on this device");
+    if (const char* cap = std::getenv("SRBD_K3_CTAS_PER_SM")) {  // tuning knob: fewer resident QPs = higher L2 hit rate
+      const int c = std::atoi(cap);
+      if (c >= 1 && c < occ) occ = c;
+    }
     long long g = (long long)occ * ctx->sm_count;
     const long long need = (ctx->B + v2::kWarps - 1) / v2::kWarps;
     if (g > need) g = need;

@@ -59,9 +59,9 @@ namespace v2 {
 constexpr int kWarps = 4;
 // per-stage workspace block (doubles)
 constexpr int oZ = 0, oDZ = 24, oRG = 48, oLAM = 72, oT = 96, oDLAM = 120, oDT = 144, oRD = 168, oRM = 192, oRMB = 216,
-              oPI = 240, oDPI = 252, oRB = 264, oPV = 276, oLV = 288, oP = 300, oFT = 444, kStage = 744;
+              oPI = 240, oDPI = 252, oRB = 264, oPV = 276, oLV = 288, oP = 300, oFT = 444, oPRB = 750, kStage = 762;
 // factor tile of a stage: 3 column panels x [25 rows][4]: rows 0..11 = rows of L^-T (E rows), 12..23 = Ls, 24 = lv
-constexpr int kPanF = 100;         // doubles of a panel that the vector sweeps need (rows 0..24)
+constexpr int kPanF = 102;         // panel stride in the factor tile: rows 0..24 (100) + 2 (bank-conflict-free fragments)
 constexpr int kPan = 148;          // the full panel during the factorization: + rows 25..36 = rows 0..11 of L
 // shared memory (doubles)
 constexpr int kGP = 52;            // padded panel stride of the BAbt tile (4 rows x 12 cols + 4)
@@ -70,7 +70,7 @@ constexpr int sAC = 0;             // [24][12] constraint Jacobian, row-major
 constexpr int sW = sAC + 288;      // [24][22]
 constexpr int kCtaShared = sW + 24 * kW2;
 constexpr int kGT = 7 * kGP;       // 364: one BAbt tile
-constexpr int kFT = 144 + 3 * kPanF;  // 444: [P 144 | factor panels 300]
+constexpr int kFT = 144 + 3 * kPanF;  // 450: [P 144 | factor panels 3 x 102]
 constexpr int kRT = 132;           // [R lower-panel prefixes 96 | Q diag 12 | rq row 24]
 constexpr int wG0 = 0, wG1 = kGT;
 constexpr int wF0 = 2 * kGT, wF1 = wF0 + kFT;
@@ -89,7 +89,7 @@ constexpr int kWarpShared = wLAM + 24;
 constexpr int kSmemBytes = (kCtaShared + kWarps * kWarpShared) * 8;
 // in the factorization sweep the factor buffers are free: the running P_{k+1} and the three panels live there
 constexpr int wP = wF0;            // [12][12] + p (12)          156 -> 160
-constexpr int wPAN = wF0 + 160;    // 3 x [37][4]                444      (604 <= 2 * 444)
+constexpr int wPAN = wF0 + 160;    // 3 x [37][4]                444      (604 <= 2 * 450)
 }  // namespace v2
 
 __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
@@ -180,16 +180,16 @@ struct SrbdSolver {
       }
     }
   }
-  // P_{kP} (144) and the factor panels of stage kL (3 x 100)
+  // P_{kP} (144) and the factor panels of stage kL (3 x 102)
   __device__ __forceinline__ void prefetch_F(int kP, int kL, int b) {
     double* dst = sm + (b ? v2::wF1 : v2::wF0);
     const double* Ps = ws(kP, v2::oP);
     const double* Ls = ws(kL, v2::oFT);
 #pragma unroll
-    for (int i = 0; i < 7; ++i) {
+    for (int i = 0; i < 8; ++i) {
       const int c = lane + 32 * i;
       if (c < 72) cp_async16(dst + 2 * c, Ps + 2 * c);
-      else if (c < 222) cp_async16(dst + 2 * c, Ls + 2 * (c - 72));
+      else if (c < 72 + 3 * v2::kPanF / 2) cp_async16(dst + 2 * c, Ls + 2 * (c - 72));
     }
   }
   // R block of RSQrq (rows 0..11, lower: prefixes of panels 0..2), the diagonal of Q, the gradient row n
@@ -320,6 +320,7 @@ struct SrbdSolver {
         double acc = 0.0;
 #pragma unroll
         for (int j = 0; j < 12; ++j) acc += sP[lane * 12 + j] * sm[v2::wXN + j];
+        ws(k, v2::oPRB)[lane] = acc;  // P_{k+1} rb is the same for every KKT solve of this iteration
         sm[v2::wT + lane] = acc + sP[144 + lane];
         const int g0 = lane < 6 ? 0 : 12;
         double a2 = 0.0;
@@ -499,40 +500,57 @@ struct SrbdSolver {
         dst[lane] = src[lane];
         if (lane < 18) dst[32 + lane] = src[32 + lane];
       }
-      if (lane < 12) ws(k, v2::oLV)[lane] = sPan[(lane >> 2) * v2::kPan + 96 + (lane & 3)];
       cur = nxt;
     }
     __syncwarp();
   }
 
   // ------------------------------------------------------------------------------------------------
+  // Vector sweeps in FRAGMENT FORM (scripts/proto_dmma_vec.py is the lane-level emulation of these bodies).
+  // A length-12 vector is three registers ("k-tiles") valid in lanes 0..3: lane t of k-tile kt holds v[4 kt + t],
+  // i.e. row 0 of a DMMA A operand (the other rows replicate it).  y = A x is 2 x 3 DMMA with the rows of A as
+  // pi-permuted B fragments, gathered STRAIGHT FROM GLOBAL MEMORY (every 8-byte gather fills whole 32-byte
+  // sectors of the panel-major records; no shared-memory staging, no cp.async) into registers that are refilled
+  // with the next stage's fragment right after their last use (one-stage-ahead prefetch at zero extra
+  // registers).  The accumulator pair (c0, c1) of output tile I is k-tiles 2I, 2I+1 of y, so a whole stage of the
+  // recursion (three to five chained gemvs) runs in registers; the only shared-memory round trip per stage is
+  // between the fragment form and the row-per-lane form of the 24 constraint rows.
+  // ------------------------------------------------------------------------------------------------
   // S4: vector-only backward sweep (gradient recursion with the stored factors).  mode 1: centering
   // correction, mode 2: centering only; sm_ = sigma*mu (clamped by the caller)
-  // ------------------------------------------------------------------------------------------------
-  struct S4v { double mk, rmb, dt, dlam, lam, t, rd, rg, rb; };
+  struct S4v { double mk, rmb, dt, dlam, lam, t, rd, rg[6], prb[3]; };
   __device__ __forceinline__ S4v load_s4(int k) const {
-    const int lc = lane < 24 ? lane : 0, l12 = lane < 12 ? lane : 0;
+    const int lc = lane < 24 ? lane : 0;
     S4v v;
-    v.mk = __ldg(gMask(k) + lc); v.rmb = ws(k, v2::oRMB)[lc]; v.dt = ws(k, v2::oDT)[lc]; v.dlam = ws(k, v2::oDLAM)[lc];
-    v.lam = ws(k, v2::oLAM)[lc]; v.t = ws(k, v2::oT)[lc]; v.rd = ws(k, v2::oRD)[lc]; v.rg = ws(k, v2::oRG)[lc];
-    v.rb = ws(k, v2::oRB)[l12];
+    v.mk = __ldg(gMask(k) + lc); v.rmb = __ldcg(ws(k, v2::oRMB) + lc); v.dt = __ldcg(ws(k, v2::oDT) + lc);
+    v.dlam = __ldcg(ws(k, v2::oDLAM) + lc); v.lam = __ldcg(ws(k, v2::oLAM) + lc); v.t = __ldcg(ws(k, v2::oT) + lc);
+    v.rd = __ldcg(ws(k, v2::oRD) + lc);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) v.rg[j] = __ldcg(ws(k, v2::oRG) + 4 * j + ft);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) v.prb[j] = __ldcg(ws(k, v2::oPRB) + 4 * j + ft);
     return v;
   }
-  __device__ void sweep_backvec(int mode, double sm_) {
-    double* sPV = sm + v2::wPV;
+  __device__ __forceinline__ void sweep_backvec(int mode, double sm_) {
+    const int r = fr, t = ft, pi = fpi;
+    const int oG = (pi >> 2) * v2::kGP + 4 * t + (pi & 3);            // G[8I+pi][4kt+t]      : + 2 kGP I + 16 kt
+    const int oLi = 144 + (pi >> 2) * v2::kPanF + 4 * t + (pi & 3);   // Linv[8I+pi][4kt+t]   : + 2 kPanF I + 16 kt
+    const int oLs = 144 + (12 + pi) * 4 + t;                          // Ls[8I+pi][4kt+t]     : + 32 I + kPanF kt
+    const int oDt = t * 12 + pi;                                      // Ac[4kt+t][8I+pi]     : + 8 I + 48 kt
+    double pk[3];
+#pragma unroll
+    for (int kt = 0; kt < 3; ++kt) pk[kt] = __ldcg(ws(N, v2::oRG) + 4 * kt + t);
+    if (r == 0) {
+#pragma unroll
+      for (int kt = 0; kt < 3; ++kt) ws(N, v2::oPV)[4 * kt + t] = pk[kt];
+    }
     prefetch_G(N - 1, 0);
     prefetch_F(N, N - 1, 0);
     S4v cur = load_s4(N - 1);
-    if (lane < 12) {
-      const double v = ws(N, v2::oRG)[lane];
-      ws(N, v2::oPV)[lane] = v;
-      sPV[lane] = v;
-    }
     for (int k = N - 1; k >= 0; --k) {
       const int b = (N - 1 - k) & 1;
-      const int nx = k > 0 ? 12 : 0, n = 12 + nx;
       cp_async_wait_all();
-      __syncwarp();
+      __syncwarp();  // stage k's tiles have landed; every lane is done with the other buffers
       set_bufs(b);
       S4v nxt = cur;
       if (k > 0) {
@@ -540,60 +558,64 @@ struct SrbdSolver {
         prefetch_F(k, k - 1, b ^ 1);
         nxt = load_s4(k - 1);
       }
-      if (lane < 24) {
+      double* gbuf = sm + (b ? v2::wqx : v2::wQX);
+      // ---- row-per-lane: res_m of this solve and gamma ------------------------------------------------------------
+      {
         double rm = cur.rmb;
         if (mode == 1) rm += cur.dt * cur.dlam;
         rm = (rm - sm_) * cur.mk;
-        ws(k, v2::oRM)[lane] = rm;
         const double ti = 1.0 / cur.t;
-        sm[v2::wqx + lane] = (ti * (rm - cur.lam * cur.rd)) * cur.mk;
-      }
-      if (lane < 12) sm[v2::wXN + lane] = cur.rb;
-      double grow = (lane < n) ? cur.rg : 0.0;
-      __syncwarp();
-      if (lane < 12) {  // t = P_{k+1} rb + p_{k+1}
-        double acc = 0.0;
-#pragma unroll
-        for (int j = 0; j < 12; ++j) acc += sF[lane * 12 + j] * sm[v2::wXN + j];
-        sm[v2::wT + lane] = acc + sPV[lane];
-      }
-      if (lane < 12) {
-        const int g0 = lane < 6 ? 0 : 12;
-        double acc = 0.0;
-#pragma unroll
-        for (int g = 0; g < 12; ++g) acc += cAc[(g0 + g) * 12 + lane] * sm[v2::wqx + g0 + g];
-        grow += acc;
-      }
-      __syncwarp();
-      if (lane < n) {
-        double acc = 0.0;
-#pragma unroll
-        for (int l = 0; l < 12; ++l) acc += Gel(lane, l) * sm[v2::wT + l];
-        sm[v2::wSG + lane] = grow + acc;
-      }
-      __syncwarp();
-      if (lane < 12) {  // lv = Linv g_u   (Linv[i][j] = panel i/4, row j, column i%4; exact zeros above the diagonal)
-        const double* Li = sF + 144 + (lane >> 2) * v2::kPanF + (lane & 3);
-        double acc = 0.0;
-#pragma unroll
-        for (int j = 0; j < 12; ++j) acc += Li[4 * j] * sm[v2::wSG + j];
-        sm[v2::wT + lane] = acc;
-        ws(k, v2::oLV)[lane] = acc;
-      }
-      __syncwarp();
-      if (lane < 12 && nx > 0) {  // p = g_x - Ls lv   (Ls[i][l] = panel l/4, row 12+i, column l%4)
-        double acc = sm[v2::wSG + 12 + lane];
-#pragma unroll
-        for (int pp = 0; pp < 3; ++pp) {
-          const double2 l01 = *reinterpret_cast<const double2*>(sF + 144 + pp * v2::kPanF + (12 + lane) * 4);
-          const double2 l23 = *reinterpret_cast<const double2*>(sF + 144 + pp * v2::kPanF + (12 + lane) * 4 + 2);
-          acc -= l01.x * sm[v2::wT + 4 * pp];
-          acc -= l01.y * sm[v2::wT + 4 * pp + 1];
-          acc -= l23.x * sm[v2::wT + 4 * pp + 2];
-          acc -= l23.y * sm[v2::wT + 4 * pp + 3];
+        if (lane < 24) {
+          ws(k, v2::oRM)[lane] = rm;
+          gbuf[lane] = (ti * (rm - cur.lam * cur.rd)) * cur.mk;
         }
-        sPV[lane] = acc;
-        ws(k, v2::oPV)[lane] = acc;
+      }
+      __syncwarp();
+      // ---- t = P_{k+1} rb + p_{k+1}  (P rb was stored by the factorization sweep) ------------------------------------
+      double tk[3];
+#pragma unroll
+      for (int kt = 0; kt < 3; ++kt) tk[kt] = cur.prb[kt] + pk[kt];
+      // ---- g~ = rg + D^T gamma + G t  (tiles of rows 0..7, 8..15, 16..23) ------------------------------------------
+      double c0[2] = {cur.rg[0], cur.rg[1]}, c1[2] = {cur.rg[2], cur.rg[3]}, c2[2] = {cur.rg[4], cur.rg[5]};
+#pragma unroll
+      for (int kt = 0; kt < 6; ++kt) {
+        const double gam = gbuf[4 * kt + t];
+        dmma(c0[0], c0[1], gam, cAc[oDt + 48 * kt], c0[0], c0[1]);
+        if (kt >= 3) dmma(c1[0], c1[1], gam, cAc[oDt + 48 * kt + 8], c1[0], c1[1]);
+      }
+#pragma unroll
+      for (int kt = 0; kt < 3; ++kt) {
+        dmma(c0[0], c0[1], tk[kt], sG[oG + 16 * kt], c0[0], c0[1]);
+        dmma(c1[0], c1[1], tk[kt], sG[oG + 2 * v2::kGP + 16 * kt], c1[0], c1[1]);
+        if (k > 0) dmma(c2[0], c2[1], tk[kt], sG[oG + 4 * v2::kGP + 16 * kt], c2[0], c2[1]);
+      }
+      // ---- lv = Linv g~_u ------------------------------------------------------------------------------------------------
+      double l0[2] = {0.0, 0.0}, l1[2] = {0.0, 0.0};
+      {
+        const double gu[3] = {c0[0], c0[1], c1[0]};
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {
+          dmma(l0[0], l0[1], gu[kt], sF[oLi + 16 * kt], l0[0], l0[1]);
+          dmma(l1[0], l1[1], gu[kt], sF[oLi + 2 * v2::kPanF + 16 * kt], l1[0], l1[1]);
+        }
+      }
+      if (r == 0) {  // row 24 of the factor panels
+        double* lvd = ws(k, v2::oFT) + 96 + t;
+        lvd[0] = l0[0]; lvd[v2::kPanF] = l0[1]; lvd[2 * v2::kPanF] = l1[0];
+      }
+      // ---- p = g~_x - Ls lv  (g~_x = second half of tile 1 and tile 2: pure register renaming) -----------------------
+      if (k > 0) {
+        double p0[2] = {c1[1], c2[0]}, p1[2] = {c2[1], 0.0};
+        const double nl[3] = {-l0[0], -l0[1], -l1[0]};
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {
+          dmma(p0[0], p0[1], nl[kt], sF[oLs + v2::kPanF * kt], p0[0], p0[1]);
+          dmma(p1[0], p1[1], nl[kt], sF[oLs + 32 + v2::kPanF * kt], p1[0], p1[1]);
+        }
+        pk[0] = p0[0]; pk[1] = p0[1]; pk[2] = p1[0];
+        if (r == 0) {
+          ws(k, v2::oPV)[t] = pk[0]; ws(k, v2::oPV)[4 + t] = pk[1]; ws(k, v2::oPV)[8 + t] = pk[2];
+        }
       }
       cur = nxt;
     }
@@ -601,25 +623,44 @@ struct SrbdSolver {
   }
 
   // ------------------------------------------------------------------------------------------------
-  // S2/S5: forward rollout fused with dt / dlam and the step length
+  // S2/S5: forward rollout fused with dt / dlam, the step length and the three sums that give
+  // mu_aff(alpha) = sum (lam + alpha dlam)(t + alpha dt) / nc for any alpha.  fin: this may be the last KKT
+  // solve of the iteration: also produce dpi and store dz (the predictor needs neither).
   // ------------------------------------------------------------------------------------------------
-  struct S2v { double lv, pv, rb, mk, t, lam, rd, rm; };
+  double mu_s0, mu_s1, mu_s2;  // sum lam t, sum (lam dt + t dlam), sum dlam dt of the last forward sweep
+  struct S2v { double mk, t, lam, rd, rm, rb[3], pv[3]; };
   __device__ __forceinline__ S2v load_s2(int k) const {
-    const int lc = lane < 24 ? lane : 0, l12 = lane < 12 ? lane : 0;
+    const int lc = lane < 24 ? lane : 0;
     S2v v;
-    v.lv = ws(k, v2::oLV)[l12]; v.pv = ws(k + 1, v2::oPV)[l12]; v.rb = ws(k, v2::oRB)[l12];
-    v.mk = __ldg(gMask(k) + lc); v.t = ws(k, v2::oT)[lc]; v.lam = ws(k, v2::oLAM)[lc];
-    v.rd = ws(k, v2::oRD)[lc]; v.rm = ws(k, v2::oRM)[lc];
+    v.mk = __ldg(gMask(k) + lc); v.t = __ldcg(ws(k, v2::oT) + lc); v.lam = __ldcg(ws(k, v2::oLAM) + lc);
+    v.rd = __ldcg(ws(k, v2::oRD) + lc); v.rm = __ldcg(ws(k, v2::oRM) + lc);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      v.rb[j] = __ldcg(ws(k, v2::oRB) + 4 * j + ft);
+      v.pv[j] = __ldcg(ws(k + 1, v2::oPV) + 4 * j + ft);
+    }
     return v;
   }
-  __device__ void sweep_forward(double& ap, double& ad) {
-    double a_p = 1.0, a_d = 1.0;
+  __device__ __forceinline__ void sweep_forward(bool fin, double& ap, double& ad) {
+    const int r = fr, t = ft, pi = fpi;
+    const int oLT = 144 + (pi >> 2) * v2::kPanF + 48 + 4 * t + (pi & 3);  // Ls[4kt+t][8I+pi]   : + 2 kPanF I + 16 kt
+    const int oIT = 144 + pi * 4 + t;                                     // Linv[4kt+t][8I+pi] : + 32 I + kPanF kt
+    const int oGT = 4 * pi + t;                                           // G[4kt+t][8I+pi]    : + 32 I + kGP kt
+    const int oPP = pi * 12 + t;                                          // P[8I+pi][4kt+t]    : + 96 I + 4 kt
+    const int oLV = 144 + 96 + t;                                         // lv[4kt+t]          : + kPanF kt
+    const int lc = lane < 24 ? lane : 0;
+    const int j0 = lc < 12 ? 0 : 6;
+    double acr[6];  // this lane's constraint row (6 nonzeros)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) acr[j] = cAc[lc * 12 + j0 + j];
+    double np_ = 1.0, dp_ = 1.0, nd_ = 1.0, dd_ = 1.0;  // step lengths as fractions num/den (no division per row)
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    double xk[3] = {0.0, 0.0, 0.0};
     prefetch_G(0, 0);
     prefetch_F(1, 0, 0);
     S2v cur = load_s2(0);
     for (int k = 0; k < N; ++k) {
       const int b = k & 1;
-      const int nx = k > 0 ? 12 : 0, n = 12 + nx;
       cp_async_wait_all();
       __syncwarp();
       set_bufs(b);
@@ -629,80 +670,92 @@ struct SrbdSolver {
         prefetch_F(k + 2, k + 1, b ^ 1);
         nxt = load_s2(k + 1);
       }
-      // x part of this stage was left in wXN by the previous stage
-      if (lane < 12 && nx > 0) {
-        const double xv = sm[v2::wXN + lane];
-        sm[v2::wSX + 12 + lane] = xv;
-        ws(k, v2::oDZ)[12 + lane] = xv;
-      }
-      __syncwarp();
-      if (lane < 12) {  // t = Ls^T x + lv
-        double acc = 0.0;
-        if (nx > 0) {
-          const double* Lc = sF + 144 + (lane >> 2) * v2::kPanF + 48 + (lane & 3);
+      double* ubuf = sm + (b ? v2::wSX : v2::wSG);
+      // ---- x+ = G^T [u; x] + rb: the x part first (it does not wait for u);  t = Ls^T x + lv ----------------------------
+      double cx0[2] = {cur.rb[0], cur.rb[1]}, cx1[2] = {cur.rb[2], 0.0};
+      double t0[2] = {sF[oLV], sF[oLV + v2::kPanF]}, t1[2] = {sF[oLV + 2 * v2::kPanF], 0.0};
+      if (k > 0) {
 #pragma unroll
-          for (int i = 0; i < 12; ++i) acc += Lc[4 * i] * sm[v2::wSX + 12 + i];
+        for (int kt = 0; kt < 3; ++kt) {
+          dmma(t0[0], t0[1], xk[kt], sF[oLT + 16 * kt], t0[0], t0[1]);
+          dmma(t1[0], t1[1], xk[kt], sF[oLT + 2 * v2::kPanF + 16 * kt], t1[0], t1[1]);
+          dmma(cx0[0], cx0[1], xk[kt], sG[oGT + v2::kGP * (3 + kt)], cx0[0], cx0[1]);
+          dmma(cx1[0], cx1[1], xk[kt], sG[oGT + 32 + v2::kGP * (3 + kt)], cx1[0], cx1[1]);
         }
-        sm[v2::wT + lane] = acc + cur.lv;
       }
-      __syncwarp();
-      if (lane < 12) {  // u = -Linv^T t   (row `lane` of L^-T: 4 contiguous values per panel, zeros left of the diagonal)
-        double acc = 0.0;
+      // ---- u = -Linv^T t ------------------------------------------------------------------------------------------------
+      double u0[2] = {0.0, 0.0}, u1[2] = {0.0, 0.0};
+      {
+        const double nt[3] = {-t0[0], -t0[1], -t1[0]};
 #pragma unroll
-        for (int pp = 0; pp < 3; ++pp) {
-          const double2 l01 = *reinterpret_cast<const double2*>(sF + 144 + pp * v2::kPanF + lane * 4);
-          const double2 l23 = *reinterpret_cast<const double2*>(sF + 144 + pp * v2::kPanF + lane * 4 + 2);
-          acc += l01.x * sm[v2::wT + 4 * pp];
-          acc += l01.y * sm[v2::wT + 4 * pp + 1];
-          acc += l23.x * sm[v2::wT + 4 * pp + 2];
-          acc += l23.y * sm[v2::wT + 4 * pp + 3];
+        for (int kt = 0; kt < 3; ++kt) {
+          dmma(u0[0], u0[1], nt[kt], sF[oIT + v2::kPanF * kt], u0[0], u0[1]);
+          dmma(u1[0], u1[1], nt[kt], sF[oIT + 32 + v2::kPanF * kt], u1[0], u1[1]);
         }
-        sm[v2::wSX + lane] = -acc;
-        ws(k, v2::oDZ)[lane] = -acc;
+      }
+      const double uk[3] = {u0[0], u0[1], u1[0]};
+      if (r == 0) {  // row-per-lane consumers read u from shared memory
+        ubuf[t] = uk[0]; ubuf[4 + t] = uk[1]; ubuf[8 + t] = uk[2];
+      }
+      // ---- x+ += B^T u --------------------------------------------------------------------------------------------------
+#pragma unroll
+      for (int kt = 0; kt < 3; ++kt) {
+        dmma(cx0[0], cx0[1], uk[kt], sG[oGT + v2::kGP * kt], cx0[0], cx0[1]);
+        dmma(cx1[0], cx1[1], uk[kt], sG[oGT + 32 + v2::kGP * kt], cx1[0], cx1[1]);
+      }
+      if (fin && r == 0) {
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {
+          ws(k, v2::oDZ)[4 * kt + t] = uk[kt];
+          if (k > 0) ws(k, v2::oDZ)[12 + 4 * kt + t] = xk[kt];
+        }
+      }
+      xk[0] = cx0[0]; xk[1] = cx0[1]; xk[2] = cx1[0];
+      // ---- dpi = P_{k+1} x+ + p_{k+1} ----------------------------------------------------------------------------------
+      if (fin) {
+        double d0[2] = {cur.pv[0], cur.pv[1]}, d1[2] = {cur.pv[2], 0.0};
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {
+          dmma(d0[0], d0[1], xk[kt], sF[oPP + 4 * kt], d0[0], d0[1]);
+          dmma(d1[0], d1[1], xk[kt], sF[oPP + 96 + 4 * kt], d1[0], d1[1]);
+        }
+        if (r == 0) {
+          ws(k, v2::oDPI)[t] = d0[0]; ws(k, v2::oDPI)[4 + t] = d0[1]; ws(k, v2::oDPI)[8 + t] = d1[0];
+        }
       }
       __syncwarp();
-      if (lane < 12) {  // x+ = G^T z + rb
-        double acc = 0.0;
-#pragma unroll
-        for (int i = 0; i < 24; ++i)
-          if (i < n) acc += Gel(i, lane) * sm[v2::wSX + i];
-        sm[v2::wXN + lane] = acc + cur.rb;
-      }
-      if (lane < 24) {  // v = D du ; dt, dlam, step lengths
-        const int j0 = lane < 12 ? 0 : 6;
+      // ---- constraint rows (row-per-lane): v = D du, dt, dlam, step lengths, mu_aff sums ------------------------------
+      {
         double v = 0.0;
 #pragma unroll
-        for (int j = 0; j < 6; ++j) v += cAc[lane * 12 + j0 + j] * sm[v2::wSX + j0 + j];
+        for (int j = 0; j < 6; ++j) v += acr[j] * ubuf[j0 + j];
         const double dt = (v - cur.rd) * cur.mk;
-        const double dlam = (-(cur.lam * dt + cur.rm) / cur.t) * cur.mk;
-        ws(k, v2::oDT)[lane] = dt;
-        ws(k, v2::oDLAM)[lane] = dlam;
-        if (dt < 0.0) a_p = fmin(a_p, -cur.t / dt);
-        if (dlam < 0.0) a_d = fmin(a_d, -cur.lam / dlam);
-      }
-      __syncwarp();
-      if (lane < 12) {  // dpi = P_{k+1} x+ + p_{k+1}
-        double acc = 0.0;
-#pragma unroll
-        for (int j = 0; j < 12; ++j) acc += sF[lane * 12 + j] * sm[v2::wXN + j];
-        ws(k, v2::oDPI)[lane] = acc + cur.pv;
+        const double dl = (-(cur.lam * dt + cur.rm) / cur.t) * cur.mk;
+        if (lane < 24) {
+          ws(k, v2::oDT)[lane] = dt;
+          ws(k, v2::oDLAM)[lane] = dl;
+          s0 += cur.lam * cur.t;
+          s1 += cur.lam * dt + cur.t * dl;
+          s2 += dl * dt;
+        }
+        // alpha = min(1, min -t/dt): keep the minimizer as a fraction, compare by cross-multiplication
+        if (dt < 0.0 && cur.t * dp_ < np_ * (0.0 - dt)) { np_ = cur.t; dp_ = 0.0 - dt; }
+        if (dl < 0.0 && cur.lam * dd_ < nd_ * (0.0 - dl)) { nd_ = cur.lam; dd_ = 0.0 - dl; }
       }
       cur = nxt;
     }
+    if (fin && r == 0) {  // x_N
+#pragma unroll
+      for (int kt = 0; kt < 3; ++kt) ws(N, v2::oDZ)[4 * kt + t] = xk[kt];
+    }
+    ap = warp_min(np_ / dp_);
+    ad = warp_min(nd_ / dd_);
+    mu_s0 = warp_sum(s0); mu_s1 = warp_sum(s1); mu_s2 = warp_sum(s2);
     __syncwarp();
-    if (lane < 12) ws(N, v2::oDZ)[lane] = sm[v2::wXN + lane];  // x_N
-    ap = warp_min(a_p);
-    ad = warp_min(a_d);
   }
 
-  __device__ double mu_aff(double alpha, int nc_mask) {
-    double acc = 0.0;
-    if (lane < 24) {
-#pragma unroll 5
-      for (int k = 0; k < N; ++k)
-        acc += (ws(k, v2::oLAM)[lane] + alpha * ws(k, v2::oDLAM)[lane]) * (ws(k, v2::oT)[lane] + alpha * ws(k, v2::oDT)[lane]);
-    }
-    return warp_sum(acc) / (double)nc_mask;
+  __device__ __forceinline__ double mu_aff(double alpha, int nc_mask) const {
+    return ((mu_s2 * alpha + mu_s1) * alpha + mu_s0) / (double)nc_mask;
   }
 
   // ------------------------------------------------------------------------------------------------
@@ -872,30 +925,43 @@ struct SrbdSolver {
     const int nc_mask = warp_sum_i(nmask);
     __syncwarp();
     double res[4], mu;
-    residuals(res, mu, nc_mask, false, 0.0, 0.0);
-    double alpha = 1.0;
+    double alpha = 1.0, sp_ = 0.0, sd_ = 0.0;
     int kk = 0;
-    for (; kk < a.iter_max && alpha > a.alpha_min &&
-           (res[0] > a.tol_stat || res[1] > a.tol_eq || res[2] > a.tol_ineq || res[3] > a.tol_comp);
-         ++kk) {
+    for (;; ++kk) {
+      // residuals of the current iterate (kk > 0: the variable update of the previous iteration is fused in)
+      residuals(res, mu, nc_mask, kk > 0, sp_, sd_);
+      if (!(kk < a.iter_max && alpha > a.alpha_min &&
+            (res[0] > a.tol_stat || res[1] > a.tol_eq || res[2] > a.tol_ineq || res[3] > a.tol_comp)))
+        break;
       sweep_factor();
+      // KKT solves of this iteration (one call site per sweep: the sweeps are inlined once).  phase 0: affine /
+      // only solve (its backward part was done by the factorization sweep), 1: corrector, 2: conditional centering
       double ap, ad;
-      sweep_forward(ap, ad);
-      if (a.pred_corr == 1) {
-        const double alpha_aff = fmin(ap, ad);
-        const double mua = mu_aff(alpha_aff, nc_mask);
-        const double tmp = mua / mu;
-        const double sigma = tmp * tmp * tmp;
-        double smv = sigma * mu;
-        smv = smv > a.tau_min ? smv : a.tau_min;
-        sweep_backvec(1, smv);
-        sweep_forward(ap, ad);
-        if (a.cond_pred_corr == 1) {
-          const double muc = mu_aff(fmin(ap, ad), nc_mask);
-          if (muc > a.cond_factor * mua) {
-            sweep_backvec(2, sigma * mu);
-            sweep_forward(ap, ad);
+      {
+        int phase = 0;
+        double sigma = 0.0, mua = 0.0, smv = 0.0;
+        for (;;) {
+          if (phase > 0) sweep_backvec(phase, smv);
+          sweep_forward(a.pred_corr != 1 || phase > 0, ap, ad);
+          if (a.pred_corr != 1) break;
+          if (phase == 0) {
+            mua = mu_aff(fmin(ap, ad), nc_mask);
+            const double tmp = mua / mu;
+            sigma = tmp * tmp * tmp;
+            smv = sigma * mu;
+            smv = smv > a.tau_min ? smv : a.tau_min;
+            phase = 1;
+            continue;
           }
+          if (phase == 1 && a.cond_pred_corr == 1) {
+            const double muc = mu_aff(fmin(ap, ad), nc_mask);
+            if (muc > a.cond_factor * mua) {
+              smv = sigma * mu;
+              phase = 2;
+              continue;
+            }
+          }
+          break;
         }
       }
       if (!a.split_step) {
@@ -903,7 +969,8 @@ struct SrbdSolver {
         ap = al; ad = al;
       }
       alpha = fmin(ap, ad);
-      residuals(res, mu, nc_mask, true, shorten(ap), shorten(ad));
+      sp_ = shorten(ap);
+      sd_ = shorten(ad);
     }
     int status;
     const bool nan = (res[0] != res[0]) || (mu != mu);
