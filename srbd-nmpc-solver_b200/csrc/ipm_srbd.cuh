@@ -68,7 +68,8 @@ constexpr int kGP = 52;            // padded panel stride of the BAbt tile (4 ro
 constexpr int kW2 = 22;            // row stride of W (21 lower-triangle products of a constraint row's 6-vector)
 constexpr int sAC = 0;             // [24][12] constraint Jacobian, row-major
 constexpr int sW = sAC + 288;      // [24][22]
-constexpr int kCtaShared = sW + 24 * kW2;
+constexpr int sQ = sW + 24 * kW2;  // diag(Q) (12), R (1), pad
+constexpr int kCtaShared = sQ + 16;
 constexpr int kGT = 7 * kGP;       // 364: one BAbt tile
 constexpr int kFT = 144 + 3 * kPanF;  // 450: [P 144 | factor panels 3 x 102]
 constexpr int kRT = 132;           // [R lower-panel prefixes 96 | Q diag 12 | rq row 24]
@@ -131,6 +132,7 @@ struct SrbdSolver {
   double* W;          // workspace of this warp
   const double* cAc;  // shared: Ac [24][12]
   const double* cW;   // shared: W [24][22]
+  const double* cQ;   // shared: diag(Q) (12), R
   double* sm;         // this warp's shared block
   const double* sG;   // current BAbt tile
   const double* sF;   // current factor tile
@@ -144,6 +146,7 @@ struct SrbdSolver {
     W = p.ws + (size_t)warp_global * p.ws_size;
     cAc = cta + v2::sAC;
     cW = cta + v2::sW;
+    cQ = cta + v2::sQ;
     sm = warp_sm;
     sG = sm; sF = sm + v2::wF0; sR = sm + v2::wR0;
     fr = lane >> 2; ft = lane & 3; fpi = (fr >> 1) + 4 * (fr & 1);
@@ -192,6 +195,16 @@ struct SrbdSolver {
       else if (c < 72 + 3 * v2::kPanF / 2) cp_async16(dst + 2 * c, Ls + 2 * (c - 72));
     }
   }
+  // R block of RSQrq only (rows 0..11, lower: prefixes of panels 0..2 = 8 + 16 + 24 16-byte chunks).  R_k is NOT a
+  // constant: the rows that stay a relaxed barrier in HARD_INEQ mode add Ac^T diag(b'') Ac (NMPC_solver.cpp:308)
+  __device__ __forceinline__ void prefetch_Rblk(int k, int b) {
+    const double* src = gRSQ(k);
+    double* dst = sm + (b ? v2::wR1 : v2::wR0);
+    const int pnl = lane < 8 ? 0 : (lane < 24 ? 1 : 2);
+    const int o = lane - (pnl == 0 ? 0 : (pnl == 1 ? 8 : 24));
+    cp_async16(dst + (pnl == 0 ? 0 : (pnl == 1 ? 16 : 48)) + 2 * o, src + pnl * 96 + 2 * o);
+    if (lane < 16) cp_async16(dst + 48 + 2 * (lane + 8), src + 192 + 2 * (lane + 8));
+  }
   // R block of RSQrq (rows 0..11, lower: prefixes of panels 0..2), the diagonal of Q, the gradient row n
   __device__ __forceinline__ void prefetch_R(int k, int b) {
     const double* src = gRSQ(k);
@@ -228,13 +241,32 @@ struct SrbdSolver {
   // ------------------------------------------------------------------------------------------------
   // S1: backward Riccati factorization sweep
   // ------------------------------------------------------------------------------------------------
-  struct S1v { double mk, lam, t, rm, rd, rg, rb; };
+  // The whole stage runs in fragment form: the gradient recursion (the "+1 row" of potrf_l_mn) is the S4 body on
+  // the same fragments (P rb, D^T gamma, G t as DMMA gemvs; its trailing updates reuse the B fragments of the
+  // matrix update); Q = diag(Q) is a model constant for k < N (NMPC_solver.cpp:305), R_k is read from RSQrq.
+  struct S1v { double mk, lam, t, rm, rd, rg[6], rb[3]; };
   __device__ __forceinline__ S1v load_s1(int k) const {
-    const int lc = lane < 24 ? lane : 0, l12 = lane < 12 ? lane : 0;
+    const int lc = lane < 24 ? lane : 0;
     S1v v;
-    v.mk = __ldg(gMask(k) + lc); v.lam = ws(k, v2::oLAM)[lc]; v.t = ws(k, v2::oT)[lc];
-    v.rm = ws(k, v2::oRM)[lc]; v.rd = ws(k, v2::oRD)[lc]; v.rg = ws(k, v2::oRG)[lc]; v.rb = ws(k, v2::oRB)[l12];
+    v.mk = __ldg(gMask(k) + lc); v.lam = __ldcg(ws(k, v2::oLAM) + lc); v.t = __ldcg(ws(k, v2::oT) + lc);
+    v.rm = __ldcg(ws(k, v2::oRM) + lc); v.rd = __ldcg(ws(k, v2::oRD) + lc);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) v.rg[j] = __ldcg(ws(k, v2::oRG) + 4 * j + ft);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) v.rb[j] = __ldcg(ws(k, v2::oRB) + 4 * j + ft);
     return v;
+  }
+  // 1/sqrt(x) of a positive pivot: MUFU.RSQ64H seed (rel. error < 2^-20) + one third-order step
+  // y (1 + e/2 + 3 e^2/8), e = 1 - x y^2  (error ~ e^3); a non-positive pivot gives 0 like BLASFEO's potrf
+  // (oracle/ocp_qp_ipm.c potrf_l_mn)
+  static __device__ __forceinline__ double rsqrt_pivot(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;\n" : "=d"(y) : "d"(x));
+    const double tt = x * y;
+    const double e = fma(-tt, y, 1.0);
+    const double q = e * fma(0.375, e, 0.5);
+    y = fma(y, q, y);
+    return x > 0.0 ? y : 0.0;
   }
   __device__ void sweep_factor() {
     const double reg = p.a.reg_prim;
@@ -248,15 +280,18 @@ struct SrbdSolver {
     const int prA0 = (25 + r) * 4 + t, prA1 = (r < 4 ? 33 + r : 8 + r) * 4 + t, prA2 = (16 + r) * 4 + t;
     const int prB0 = (25 + pi) * 4 + t, prB1 = (pi < 4 ? 33 + pi : 8 + pi) * 4 + t, prB2 = (16 + pi) * 4 + t;
     const int prE0 = r * 4 + t;
+    const int oDt = t * 12 + pi;  // Ac[4kt+t][8I+pi] : + 8 I + 48 kt
     const bool dg0 = (r == t), dg1 = (r == 4 + t);
     const double regd0 = dg0 ? reg : 0.0, regd1 = dg1 ? reg : 0.0;
-    const int rel0 = ((r >> 2) ? 16 : 0) + (r & 3) + 4 * t;  // R(i, c) of rows 0..7:  + 16 * (c >> 2)
+    const int rel0 = ((r >> 2) ? 16 : 0) + (r & 3) + 4 * t;  // R(i, c) of rows 0..7 in the R tile:  + 16 * (c >> 2)
     const int rel1 = 48 + (r & 3) + 4 * t;                   // rows 8..11 (r < 4)
+    const double qd3 = dg1 ? cQ[t] : 0.0, qd4 = dg0 ? cQ[4 + t] : 0.0, qd5 = dg1 ? cQ[8 + t] : 0.0;  // diag(Q)
     // start streaming stage N-1 while stage N is handled
     prefetch_G(N - 1, 0);
-    prefetch_R(N - 1, 0);
+    prefetch_Rblk(N - 1, 0);
     S1v cur = load_s1(N - 1);
     // ---- stage N: P_N = Q_N + reg I, p_N = rg_N ------------------------------------------------------
+    double pk[3];
     {
       const double* rs = gRSQ(N);
       if (lane < 12) {
@@ -269,32 +304,35 @@ struct SrbdSolver {
             sP[c * 12 + lane] = v;
           }
         }
-        sP[144 + lane] = ws(N, v2::oRG)[lane];
       }
+#pragma unroll
+      for (int kt = 0; kt < 3; ++kt) pk[kt] = __ldcg(ws(N, v2::oRG) + 4 * kt + t);
       __syncwarp();
       for (int e = lane; e < 144; e += 32) ws(N, v2::oP)[e] = sP[e];
-      if (lane < 12) ws(N, v2::oPV)[lane] = sP[144 + lane];
+      if (r == 0) {
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) ws(N, v2::oPV)[4 * kt + t] = pk[kt];
+      }
     }
     for (int k = N - 1; k >= 0; --k) {
       const int b = (N - 1 - k) & 1;
       const bool xr = k > 0;                 // the stage has x rows (rows 12..23)
-      const int n = xr ? 24 : 12;
       cp_async_wait_all();
       __syncwarp();  // stage k's tiles have landed; every lane is done with the other buffers
       set_bufs(b);
       S1v nxt = cur;
       if (k > 0) {
         prefetch_G(k - 1, b ^ 1);
-        prefetch_R(k - 1, b ^ 1);
+        prefetch_Rblk(k - 1, b ^ 1);
         nxt = load_s1(k - 1);
       }
+      double* gbuf = sm + (b ? v2::wqx : v2::wQX);
+      double* Gbuf = sm + (b ? v2::wSG : v2::wSX);
       if (lane < 24) {
         const double ti = 1.0 / cur.t;
-        sm[v2::wQX + lane] = (ti * cur.lam) * cur.mk;
-        sm[v2::wqx + lane] = (ti * (cur.rm - cur.lam * cur.rd)) * cur.mk;
+        Gbuf[lane] = (ti * cur.lam) * cur.mk;
+        gbuf[lane] = (ti * (cur.rm - cur.lam * cur.rd)) * cur.mk;
       }
-      if (lane < 12) sm[v2::wXN + lane] = cur.rb;
-      double grow = (lane < n) ? cur.rg : 0.0;  // gradient entry of row `lane`
       __syncwarp();
       // ---- operand fragments: G (A operand), G rows permuted (B operand), P_{k+1} (B operand) -------------------
       double GF[3][3], GPF[3][3], PPF[2][3];
@@ -315,19 +353,7 @@ struct SrbdSolver {
           PPF[1][kt] = pi < 4 ? p1 : 0.0;
         }
       }
-      // ---- vector stream: t = P_{k+1} rb + p_{k+1}; gradient += D^T gamma; the 42 sums of D^T Gamma D ----------
-      if (lane < 12) {
-        double acc = 0.0;
-#pragma unroll
-        for (int j = 0; j < 12; ++j) acc += sP[lane * 12 + j] * sm[v2::wXN + j];
-        ws(k, v2::oPRB)[lane] = acc;  // P_{k+1} rb is the same for every KKT solve of this iteration
-        sm[v2::wT + lane] = acc + sP[144 + lane];
-        const int g0 = lane < 6 ? 0 : 12;
-        double a2 = 0.0;
-#pragma unroll
-        for (int g = 0; g < 12; ++g) a2 += cAc[(g0 + g) * 12 + lane] * sm[v2::wqx + g0 + g];
-        grow += a2;
-      }
+      // ---- the 42 sums of D^T Gamma D (two 6x6 blocks, lower triangles) -------------------------------------------
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
         const int e2 = lane + 32 * rr;
@@ -335,8 +361,34 @@ struct SrbdSolver {
           const int leg = e2 >= 21 ? 1 : 0, e = e2 - 21 * leg;
           double acc = 0.0;
 #pragma unroll
-          for (int g = 0; g < 12; ++g) acc += sm[v2::wQX + 12 * leg + g] * cW[(12 * leg + g) * v2::kW2 + e];
+          for (int g = 0; g < 12; ++g) acc += Gbuf[12 * leg + g] * cW[(12 * leg + g) * v2::kW2 + e];
           sm[v2::wS + e2] = acc;
+        }
+      }
+      // ---- gradient, fragment form: t = P_{k+1} rb + p_{k+1};  g~ = rg + D^T gamma + G t ----------------------------
+      double c0[2] = {cur.rg[0], cur.rg[1]}, c1[2] = {cur.rg[2], cur.rg[3]}, c2[2] = {cur.rg[4], cur.rg[5]};
+      {
+        double d0[2] = {0.0, 0.0}, d1[2] = {0.0, 0.0};
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {
+          dmma(d0[0], d0[1], cur.rb[kt], PPF[0][kt], d0[0], d0[1]);
+          dmma(d1[0], d1[1], cur.rb[kt], PPF[1][kt], d1[0], d1[1]);
+        }
+        if (r == 0) {  // P_{k+1} rb is the same for every KKT solve of this iteration
+          ws(k, v2::oPRB)[t] = d0[0]; ws(k, v2::oPRB)[4 + t] = d0[1]; ws(k, v2::oPRB)[8 + t] = d1[0];
+        }
+        const double tk[3] = {d0[0] + pk[0], d0[1] + pk[1], d1[0] + pk[2]};
+#pragma unroll
+        for (int kt = 0; kt < 6; ++kt) {
+          const double gam = gbuf[4 * kt + t];
+          dmma(c0[0], c0[1], gam, cAc[oDt + 48 * kt], c0[0], c0[1]);
+          if (kt >= 3) dmma(c1[0], c1[1], gam, cAc[oDt + 48 * kt + 8], c1[0], c1[1]);
+        }
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {
+          dmma(c0[0], c0[1], tk[kt], GPF[0][kt], c0[0], c0[1]);
+          dmma(c1[0], c1[1], tk[kt], GPF[1][kt], c1[0], c1[1]);
+          if (xr) dmma(c2[0], c2[1], tk[kt], GPF[2][kt], c2[0], c2[1]);
         }
       }
       // ---- AL = G P_{k+1}: fragments ALF[I][0..2] (columns 0..3, 4..7, 8..11) -------------------------------------
@@ -344,13 +396,13 @@ struct SrbdSolver {
 #pragma unroll
       for (int I = 0; I < 3; ++I) {
         if (I < 2 || xr) {
-          double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
+          double a0 = 0.0, a1 = 0.0, e0 = 0.0, e1 = 0.0;
 #pragma unroll
           for (int kt = 0; kt < 3; ++kt) {
-            dmma(c0, c1, GF[I][kt], PPF[0][kt], c0, c1);
+            dmma(a0, a1, GF[I][kt], PPF[0][kt], a0, a1);
             dmma(e0, e1, GF[I][kt], PPF[1][kt], e0, e1);
           }
-          ALF[I][0] = c0; ALF[I][1] = c1; ALF[I][2] = e0;
+          ALF[I][0] = a0; ALF[I][1] = a1; ALF[I][2] = e0;
         } else {
           ALF[I][0] = 0.0; ALF[I][1] = 0.0; ALF[I][2] = 0.0;
         }
@@ -361,22 +413,16 @@ struct SrbdSolver {
       for (int I = 0; I < 3; ++I)
 #pragma unroll
         for (int J = 0; J <= I; ++J) {
-          double c0 = 0.0, c1 = 0.0;
+          double a0 = 0.0, a1 = 0.0;
           if (I < 2 || xr) {
 #pragma unroll
-            for (int kt = 0; kt < 3; ++kt) dmma(c0, c1, ALF[I][kt], GPF[J][kt], c0, c1);
+            for (int kt = 0; kt < 3; ++kt) dmma(a0, a1, ALF[I][kt], GPF[J][kt], a0, a1);
           }
-          MF[I][2 * J] = c0; MF[I][2 * J + 1] = c1;
+          MF[I][2 * J] = a0; MF[I][2 * J + 1] = a1;
         }
-      __syncwarp();  // wS, wT visible
-      if (lane < n) {
-        double acc = 0.0;
-#pragma unroll
-        for (int l = 0; l < 12; ++l) acc += Gel(lane, l) * sm[v2::wT + l];
-        grow += acc;
-      }
+      __syncwarp();  // wS visible
       {
-        // u block (rows < 12): R lower + D^T Gamma D, fragments (0,0) (0,1) (1,0) (1,1) (1,2)
+        // u block (rows < 12): R_k (lower) + D^T Gamma D, fragments (0,0) (0,1) (1,0) (1,1) (1,2)
         double hf[5];
 #pragma unroll
         for (int f = 0; f < 5; ++f) {
@@ -393,12 +439,9 @@ struct SrbdSolver {
         MF[1][1] = hf[3] + MF[1][1];
         MF[1][2] = (hf[4] + MF[1][2]) + regd0;
         // x block: diagonal of Q (rows 12..23)
-        const double q3 = (xr && dg1) ? sR[96 + t] : 0.0;
-        const double q4 = (xr && dg0) ? sR[100 + t] : 0.0;
-        const double q5 = (xr && dg1) ? sR[104 + t] : 0.0;
-        MF[1][3] = (q3 + MF[1][3]) + regd1;
-        MF[2][4] = (q4 + MF[2][4]) + regd0;
-        MF[2][5] = (q5 + MF[2][5]) + regd1;
+        MF[1][3] = ((xr ? qd3 : 0.0) + MF[1][3]) + regd1;
+        MF[2][4] = ((xr ? qd4 : 0.0) + MF[2][4]) + regd0;
+        MF[2][5] = ((xr ? qd5 : 0.0) + MF[2][5]) + regd1;
       }
       // ---- blocked Cholesky of the 12 u columns: three 4-column panels ------------------------------------------
       double EF1 = dg1 ? 1.0 : 0.0, EF2 = 0.0;  // E rows 0..7 (identity), columns 4..7 and 8..11
@@ -410,7 +453,7 @@ struct SrbdSolver {
         pan[prA2] = MF[2][pp];
         pan[prE0] = pp == 0 ? (dg0 ? 1.0 : 0.0) : (pp == 1 ? EF1 : EF2);
         if (r < 4) pan[(8 + r) * 4 + t] = (pp == 2 && dg0) ? 1.0 : 0.0;  // E rows 8..11
-        if (lane >= 4 * pp && lane < 4 * pp + 4) pan[96 + lane - 4 * pp] = grow;
+        if (r == 0) pan[96 + t] = pp == 0 ? c0[0] : (pp == 1 ? c0[1] : c1[0]);  // gradient row: g~[4pp + t]
         __syncwarp();
         // every lane factors the 4x4 diagonal block (rows 25+4pp..) redundantly ...
         const double* dgb = pan + (25 + 4 * pp) * 4;
@@ -424,14 +467,13 @@ struct SrbdSolver {
         const int prow = lane < 4 * pp ? 4 + lane : (lane < 12 ? 25 + lane : (lane < 25 ? lane : lane - 25));
         double2* own = reinterpret_cast<double2*>(pan + prow * 4);
         const double2 x01 = own[0], x23 = own[1];
-        double sq, i0, i1, i2, i3;
-        sqrt_rsqrt(a00, sq, i0);
+        const double i0 = rsqrt_pivot(a00);
         const double L10 = a1x.x * i0, L20 = a2x.x * i0, L30 = a3x.x * i0;
-        sqrt_rsqrt(fma(-L10, L10, a1x.y), sq, i1);
+        const double i1 = rsqrt_pivot(fma(-L10, L10, a1x.y));
         const double L21 = fma(-L20, L10, a2x.y) * i1, L31 = fma(-L30, L10, a3x.y) * i1;
-        sqrt_rsqrt(fma(-L21, L21, fma(-L20, L20, a22)), sq, i2);
+        const double i2 = rsqrt_pivot(fma(-L21, L21, fma(-L20, L20, a22)));
         const double L32 = fma(-L31, L21, fma(-L30, L20, a3y.x)) * i2;
-        sqrt_rsqrt(fma(-L32, L32, fma(-L31, L31, fma(-L30, L30, a3y.y))), sq, i3);
+        const double i3 = rsqrt_pivot(fma(-L32, L32, fma(-L31, L31, fma(-L30, L30, a3y.y))));
         const double l0 = x01.x * i0;
         const double l1 = fma(-l0, L10, x01.y) * i1;
         const double l2 = fma(-l1, L21, fma(-l0, L20, x23.x)) * i2;
@@ -439,14 +481,9 @@ struct SrbdSolver {
         own[0] = make_double2(l0, l1);
         own[1] = make_double2(l2, l3);
         __syncwarp();
-        // gradient row: g[c] -= sum_l lv[l] L[c][l] for the rows below the panel
-        {
-          const double2 v01 = *reinterpret_cast<const double2*>(pan + 96);
-          const double2 v23 = *reinterpret_cast<const double2*>(pan + 98);
-          if (lane >= 4 * pp + 4 && lane < 24)
-            grow = fma(-v23.y, l3, fma(-v23.x, l2, fma(-v01.y, l1, fma(-v01.x, l0, grow))));
-        }
-        // trailing updates M -= Lp Lp^T on the tensor cores (A = -L panel fragment, B = permuted fragment)
+        // trailing updates M -= Lp Lp^T and g~ -= Lp lv_p on the tensor cores (A = -L panel fragment / -lv_p in
+        // row 0, B = permuted fragment of the panel)
+        const double nlv = -pan[96 + t];
         double dum;
         if (pp == 0) {
           const double nA0 = -pan[prA0], nA1 = -pan[prA1], nA2 = -pan[prA2], nAE = -pan[prE0];
@@ -454,10 +491,13 @@ struct SrbdSolver {
           dmma(dum, MF[0][1], nA0, B0, MF[0][0], MF[0][1]);
           dmma(dum, MF[1][1], nA1, B0, MF[1][0], MF[1][1]);
           dmma(MF[1][2], MF[1][3], nA1, B1, MF[1][2], MF[1][3]);
+          dmma(dum, c0[1], nlv, B0, c0[0], c0[1]);
+          dmma(c1[0], c1[1], nlv, B1, c1[0], c1[1]);
           if (xr) {
             dmma(dum, MF[2][1], nA2, B0, MF[2][0], MF[2][1]);
             dmma(MF[2][2], MF[2][3], nA2, B1, MF[2][2], MF[2][3]);
             dmma(MF[2][4], MF[2][5], nA2, B2, MF[2][4], MF[2][5]);
+            dmma(c2[0], c2[1], nlv, B2, c2[0], c2[1]);
           }
           dmma(dum, EF1, nAE, B0, 0.0, EF1);
           dmma(EF2, dum, nAE, B1, EF2, 0.0);
@@ -465,9 +505,11 @@ struct SrbdSolver {
           const double nA1 = -pan[prA1], nA2 = -pan[prA2], nAE = -pan[prE0];
           const double B1 = pan[prB1], B2 = pan[prB2];
           dmma(MF[1][2], MF[1][3], nA1, B1, MF[1][2], MF[1][3]);
+          dmma(c1[0], c1[1], nlv, B1, c1[0], c1[1]);
           if (xr) {
             dmma(MF[2][2], MF[2][3], nA2, B1, MF[2][2], MF[2][3]);
             dmma(MF[2][4], MF[2][5], nA2, B2, MF[2][4], MF[2][5]);
+            dmma(c2[0], c2[1], nlv, B2, c2[0], c2[1]);
           }
           dmma(EF2, dum, nAE, B1, EF2, 0.0);
         } else if (xr) {
@@ -476,6 +518,8 @@ struct SrbdSolver {
           dmma(dum, MF[1][3], nA1, B1, MF[1][2], MF[1][3]);
           dmma(dum, MF[2][3], nA2, B1, MF[2][2], MF[2][3]);
           dmma(MF[2][4], MF[2][5], nA2, B2, MF[2][4], MF[2][5]);
+          dmma(dum, c1[1], nlv, B1, c1[0], c1[1]);
+          dmma(c2[0], c2[1], nlv, B2, c2[0], c2[1]);
         }
       }
       // ---- outputs: P_k (both triangles) and p_k for the next stage and the vector sweeps --------------------------
@@ -486,11 +530,13 @@ struct SrbdSolver {
         sP[(4 + r) * 12 + t] = MF[2][3]; sP[t * 12 + (4 + r)] = MF[2][3];
         if (t <= r) { sP[(4 + r) * 12 + 4 + t] = MF[2][4]; sP[(4 + t) * 12 + 4 + r] = MF[2][4]; }
         if (4 + t <= r) { sP[(4 + r) * 12 + 8 + t] = MF[2][5]; sP[(8 + t) * 12 + 4 + r] = MF[2][5]; }
-        if (lane >= 12 && lane < 24) sP[144 + lane - 12] = grow;
+        pk[0] = c1[1]; pk[1] = c2[0]; pk[2] = c2[1];   // p_k = g~_x after the three panels
+        if (r == 0) {
+          ws(k, v2::oPV)[t] = pk[0]; ws(k, v2::oPV)[4 + t] = pk[1]; ws(k, v2::oPV)[8 + t] = pk[2];
+        }
         __syncwarp();
         for (int e = lane; e < 72; e += 32)
           reinterpret_cast<double2*>(ws(k, v2::oP))[e] = reinterpret_cast<const double2*>(sP)[e];
-        if (lane < 12) ws(k, v2::oPV)[lane] = sP[144 + lane];
       }
       // factor panels (rows 0..24: L^-T, Ls, lv) -> workspace
 #pragma unroll
@@ -1009,6 +1055,8 @@ __global__ void __launch_bounds__(128, 3) ipm_srbd_kernel(const SrbdIpmParams p)
   __shared__ int s_next[v2::kWarps];
   // CTA-shared constants: Ac and, per constraint row g, the 21 lower-triangle products of its 6-vector
   for (int i = threadIdx.x; i < 288; i += blockDim.x) smem[v2::sAC + i] = p.model->Ac[i];
+  if (threadIdx.x < 12) smem[v2::sQ + threadIdx.x] = p.model->m.Q[threadIdx.x];
+  if (threadIdx.x == 12) smem[v2::sQ + 12] = p.model->m.R;
   __syncthreads();
   for (int i = threadIdx.x; i < 24 * v2::kW2; i += blockDim.x) {
     const int g = i / v2::kW2, e = i - g * v2::kW2;
