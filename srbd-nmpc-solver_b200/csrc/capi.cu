@@ -553,6 +553,10 @@ static int solve_srbd_variant(srbd_ctx* ctx) {
       if (c >= 1 && c < occ) occ = c;
     }
     long long g = (long long)occ * ctx->sm_count;
+    if (const char* gs = std::getenv("SRBD_K3_GRID")) {  // tuning knob: number of resident CTAs (4 QPs each)
+      const long long c = std::atoll(gs);
+      if (c >= 1 && c < g) g = c;
+    }
     const long long need = (ctx->B + v2::kWarps - 1) / v2::kWarps;
     if (g > need) g = need;
     ctx->grid2 = (int)g;

@@ -170,28 +170,28 @@ struct SrbdSolver {
   __device__ __forceinline__ const double* gMask(int k) const { return p.dmask + ((size_t)q * (N + 1) + k) * 48; }
 
   // ---- asynchronous tile prefetch (cp.async, no registers) -------------------------------------------
-  // BAbt record (7 panels of 48 doubles) -> padded panels (bank-conflict-free row access)
-  __device__ __forceinline__ void prefetch_G(int k, int b) {
+  // BAbt record (panels of 4 rows x 12 = 48 doubles) -> padded panels; np = 6: rows 0..23, 7: + the b row
+  __device__ __forceinline__ void prefetch_G(int k, int b, int np = 6) {
     const double* src = gBAbt(k);
     double* dst = sm + (b ? v2::wG1 : v2::wG0);
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       const int c = lane + 32 * i;
-      if (c < 168) {
+      if (c < 24 * np) {
         const int pnl = c / 24, o = c - pnl * 24;
         cp_async16(dst + pnl * v2::kGP + 2 * o, src + 2 * c);
       }
     }
   }
-  // P_{kP} (144) and the factor panels of stage kL (3 x 102)
-  __device__ __forceinline__ void prefetch_F(int kP, int kL, int b) {
+  // the factor panels of stage kL (3 x 102) and, if asked for, P_{kP} (144) in front of them
+  __device__ __forceinline__ void prefetch_F(int kP, int kL, int b, bool with_P) {
     double* dst = sm + (b ? v2::wF1 : v2::wF0);
     const double* Ps = ws(kP, v2::oP);
     const double* Ls = ws(kL, v2::oFT);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int c = lane + 32 * i;
-      if (c < 72) cp_async16(dst + 2 * c, Ps + 2 * c);
+      if (c < 72) { if (with_P) cp_async16(dst + 2 * c, Ps + 2 * c); }
       else if (c < 72 + 3 * v2::kPanF / 2) cp_async16(dst + 2 * c, Ls + 2 * (c - 72));
     }
   }
@@ -591,7 +591,7 @@ struct SrbdSolver {
       for (int kt = 0; kt < 3; ++kt) ws(N, v2::oPV)[4 * kt + t] = pk[kt];
     }
     prefetch_G(N - 1, 0);
-    prefetch_F(N, N - 1, 0);
+    prefetch_F(N, N - 1, 0, false);
     S4v cur = load_s4(N - 1);
     for (int k = N - 1; k >= 0; --k) {
       const int b = (N - 1 - k) & 1;
@@ -601,7 +601,7 @@ struct SrbdSolver {
       S4v nxt = cur;
       if (k > 0) {
         prefetch_G(k - 1, b ^ 1);
-        prefetch_F(k, k - 1, b ^ 1);
+        prefetch_F(k, k - 1, b ^ 1, false);
         nxt = load_s4(k - 1);
       }
       double* gbuf = sm + (b ? v2::wqx : v2::wQX);
@@ -703,7 +703,7 @@ struct SrbdSolver {
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
     double xk[3] = {0.0, 0.0, 0.0};
     prefetch_G(0, 0);
-    prefetch_F(1, 0, 0);
+    prefetch_F(1, 0, 0, fin);
     S2v cur = load_s2(0);
     for (int k = 0; k < N; ++k) {
       const int b = k & 1;
@@ -713,7 +713,7 @@ struct SrbdSolver {
       S2v nxt = cur;
       if (k + 1 < N) {
         prefetch_G(k + 1, b ^ 1);
-        prefetch_F(k + 2, k + 1, b ^ 1);
+        prefetch_F(k + 2, k + 1, b ^ 1, fin);
         nxt = load_s2(k + 1);
       }
       double* ubuf = sm + (b ? v2::wSX : v2::wSG);
@@ -837,7 +837,7 @@ struct SrbdSolver {
   }
   __device__ void residuals(double res[4], double& mu, int nc_mask, bool do_update, double sp, double sd) {
     double ng_ = 0.0, nb_ = 0.0, nd_ = 0.0, nm_ = 0.0, smu = 0.0;
-    prefetch_G(0, 0);
+    prefetch_G(0, 0, 7);
     prefetch_R(0, 0);
     S6v cur = load_s6(0, do_update, sp, sd);
     double pi_prev = 0.0;  // updated pi_{k-1}, held by lanes < 12
@@ -849,7 +849,7 @@ struct SrbdSolver {
       set_bufs(b);
       S6v nxt = cur;
       if (k < N) {
-        if (k + 1 < N) prefetch_G(k + 1, b ^ 1);
+        if (k + 1 < N) prefetch_G(k + 1, b ^ 1, 7);
         prefetch_R(k + 1, b ^ 1);
         nxt = load_s6(k + 1, do_update, sp, sd);
       }
