@@ -170,30 +170,30 @@ struct SrbdSolver {
   __device__ __forceinline__ const double* gMask(int k) const { return p.dmask + ((size_t)q * (N + 1) + k) * 48; }
 
   // ---- asynchronous tile prefetch (cp.async, no registers) -------------------------------------------
-  // BAbt record (panels of 4 rows x 12 = 48 doubles) -> padded panels; np = 6: rows 0..23, 7: + the b row
+  // BAbt record (panels of 4 rows x 12 = 48 doubles) -> padded panels; np = 6: rows 0..23, 7: + the b row.
+  // One 24-lane instruction per panel: every address is base + immediate.
   __device__ __forceinline__ void prefetch_G(int k, int b, int np = 6) {
-    const double* src = gBAbt(k);
-    double* dst = sm + (b ? v2::wG1 : v2::wG0);
+    const double* src = gBAbt(k) + 2 * lane;
+    double* dst = sm + (b ? v2::wG1 : v2::wG0) + 2 * lane;
+    if (lane < 24) {
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      const int c = lane + 32 * i;
-      if (c < 24 * np) {
-        const int pnl = c / 24, o = c - pnl * 24;
-        cp_async16(dst + pnl * v2::kGP + 2 * o, src + 2 * c);
-      }
+      for (int pnl = 0; pnl < 7; ++pnl)
+        if (pnl < np) cp_async16(dst + pnl * v2::kGP, src + pnl * 48);
     }
   }
-  // the factor panels of stage kL (3 x 102) and, if asked for, P_{kP} (144) in front of them
-  __device__ __forceinline__ void prefetch_F(int kP, int kL, int b, bool with_P) {
-    double* dst = sm + (b ? v2::wF1 : v2::wF0);
-    const double* Ps = ws(kP, v2::oP);
-    const double* Ls = ws(kL, v2::oFT);
+  // [P_{k+1} (144) |] factor panels of stage k (3 x 102): contiguous in the workspace (P_{k+1} lives in block k)
+  __device__ __forceinline__ void prefetch_F(int k, int b, bool with_P) {
+    double* dst = sm + (b ? v2::wF1 : v2::wF0) + 2 * lane;
+    const double* src = ws(k, v2::oP) + 2 * lane;
+    if (with_P) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = lane + 32 * i;
-      if (c < 72) { if (with_P) cp_async16(dst + 2 * c, Ps + 2 * c); }
-      else if (c < 72 + 3 * v2::kPanF / 2) cp_async16(dst + 2 * c, Ls + 2 * (c - 72));
+      for (int i = 0; i < 2; ++i) cp_async16(dst + 64 * i, src + 64 * i);
+      if (lane < 8) cp_async16(dst + 128, src + 128);
     }
+    // chunks 72 .. 224
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cp_async16(dst + 144 + 64 * i, src + 144 + 64 * i);
+    if (lane < 25) cp_async16(dst + 144 + 256, src + 144 + 256);
   }
   // R block of RSQrq only (rows 0..11, lower: prefixes of panels 0..2 = 8 + 16 + 24 16-byte chunks).  R_k is NOT a
   // constant: the rows that stay a relaxed barrier in HARD_INEQ mode add Ac^T diag(b'') Ac (NMPC_solver.cpp:308)
@@ -308,7 +308,7 @@ struct SrbdSolver {
 #pragma unroll
       for (int kt = 0; kt < 3; ++kt) pk[kt] = __ldcg(ws(N, v2::oRG) + 4 * kt + t);
       __syncwarp();
-      for (int e = lane; e < 144; e += 32) ws(N, v2::oP)[e] = sP[e];
+      for (int e = lane; e < 144; e += 32) ws(N - 1, v2::oP)[e] = sP[e];  // P_k lives in block k-1 (next to FT_{k-1})
       if (r == 0) {
 #pragma unroll
         for (int kt = 0; kt < 3; ++kt) ws(N, v2::oPV)[4 * kt + t] = pk[kt];
@@ -536,7 +536,7 @@ struct SrbdSolver {
         }
         __syncwarp();
         for (int e = lane; e < 72; e += 32)
-          reinterpret_cast<double2*>(ws(k, v2::oP))[e] = reinterpret_cast<const double2*>(sP)[e];
+          reinterpret_cast<double2*>(ws(k - 1, v2::oP))[e] = reinterpret_cast<const double2*>(sP)[e];
       }
       // factor panels (rows 0..24: L^-T, Ls, lv) -> workspace
 #pragma unroll
@@ -591,7 +591,7 @@ struct SrbdSolver {
       for (int kt = 0; kt < 3; ++kt) ws(N, v2::oPV)[4 * kt + t] = pk[kt];
     }
     prefetch_G(N - 1, 0);
-    prefetch_F(N, N - 1, 0, false);
+    prefetch_F(N - 1, 0, false);
     S4v cur = load_s4(N - 1);
     for (int k = N - 1; k >= 0; --k) {
       const int b = (N - 1 - k) & 1;
@@ -601,7 +601,7 @@ struct SrbdSolver {
       S4v nxt = cur;
       if (k > 0) {
         prefetch_G(k - 1, b ^ 1);
-        prefetch_F(k, k - 1, b ^ 1, false);
+        prefetch_F(k - 1, b ^ 1, false);
         nxt = load_s4(k - 1);
       }
       double* gbuf = sm + (b ? v2::wqx : v2::wQX);
@@ -703,7 +703,7 @@ struct SrbdSolver {
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
     double xk[3] = {0.0, 0.0, 0.0};
     prefetch_G(0, 0);
-    prefetch_F(1, 0, 0, fin);
+    prefetch_F(0, 0, fin);
     S2v cur = load_s2(0);
     for (int k = 0; k < N; ++k) {
       const int b = k & 1;
@@ -713,7 +713,7 @@ struct SrbdSolver {
       S2v nxt = cur;
       if (k + 1 < N) {
         prefetch_G(k + 1, b ^ 1);
-        prefetch_F(k + 2, k + 1, b ^ 1, fin);
+        prefetch_F(k + 1, b ^ 1, fin);
         nxt = load_s2(k + 1);
       }
       double* ubuf = sm + (b ? v2::wSX : v2::wSG);
@@ -776,7 +776,9 @@ struct SrbdSolver {
 #pragma unroll
         for (int j = 0; j < 6; ++j) v += acr[j] * ubuf[j0 + j];
         const double dt = (v - cur.rd) * cur.mk;
-        const double dl = (-(cur.lam * dt + cur.rm) / cur.t) * cur.mk;
+        // (masked rows: a zero numerator would send these lanes through the division's slow path every stage)
+        const double num = cur.mk != 0.0 ? -(cur.lam * dt + cur.rm) : 1.0;
+        const double dl = (num / cur.t) * cur.mk;
         if (lane < 24) {
           ws(k, v2::oDT)[lane] = dt;
           ws(k, v2::oDLAM)[lane] = dl;
