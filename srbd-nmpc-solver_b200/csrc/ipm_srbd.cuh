@@ -838,11 +838,31 @@ struct SrbdSolver {
     return v;
   }
   __device__ void residuals(double res[4], double& mu, int nc_mask, bool do_update, double sp, double sd) {
+    const int r = fr, t = ft, pi = fpi;
+    const int gB = (pi >> 2) * v2::kGP + 4 * t + (pi & 3);   // G[8I+pi][4kt+t]   : + 2 kGP I + 16 kt
+    const int oGT = 4 * pi + t;                              // G[4kt+t][8I+pi]   : + 32 I + kGP kt
+    const int oDt = t * 12 + pi;                             // Ac[4kt+t][8I+pi]  : + 8 I + 48 kt
+    // the symmetric R block (Q_N at stage N) as B fragments from the lower-triangle tile: element (8I+pi, 4kt+t)
+    int oRs[2][3];
+#pragma unroll
+    for (int I = 0; I < 2; ++I)
+#pragma unroll
+      for (int kt = 0; kt < 3; ++kt) {
+        const int i0 = 8 * I + (I == 1 ? (pi & 3) : pi), c0 = 4 * kt + t;
+        const int i = i0 >= c0 ? i0 : c0, c = i0 >= c0 ? c0 : i0;
+        const int pnl = i >> 2;
+        oRs[I][kt] = (pnl == 0 ? 0 : (pnl == 1 ? 16 : 48)) + 4 * c + (i & 3);
+      }
+    const int lc = lane < 24 ? lane : 0;
+    const int j0 = lc < 12 ? 0 : 6;
+    double acr[6];  // this lane's constraint row (6 nonzeros)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) acr[j] = cAc[lc * 12 + j0 + j];
     double ng_ = 0.0, nb_ = 0.0, nd_ = 0.0, nm_ = 0.0, smu = 0.0;
     prefetch_G(0, 0, 7);
     prefetch_R(0, 0);
     S6v cur = load_s6(0, do_update, sp, sd);
-    double pi_prev = 0.0;  // updated pi_{k-1}, held by lanes < 12
+    double pp[3] = {0.0, 0.0, 0.0};  // updated pi_{k-1}, fragment form
     for (int k = 0; k <= N; ++k) {
       const int b = k & 1;
       const int nu = k < N ? 12 : 0, nx = k > 0 ? 12 : 0, n = nu + nx;
@@ -855,12 +875,13 @@ struct SrbdSolver {
         prefetch_R(k + 1, b ^ 1);
         nxt = load_s6(k + 1, do_update, sp, sd);
       }
-      // pi_{k-1} for the x rows (lane nu + l takes it from lane l)
-      const double pim = __shfl_sync(kFull, pi_prev, (lane - nu) & 31);
-      if (lane < n) sm[v2::wSX + lane] = cur.z;
+      double* zb = sm + (b ? v2::wSX : v2::wSG);       // z (24)
+      double* lb = sm + (b ? v2::wqx : v2::wQX);       // lam (24)
+      double* pb = sm + v2::wXN + (b ? 24 : 0);        // pi (12) | x_{k+1} (12)   (wXN..wDI: 48 doubles)
+      if (lane < 24) zb[lane] = lane < n ? cur.z : 0.0;
       if (k < N) {
-        if (lane < 12) sm[v2::wXN + lane] = cur.pi;
-        if (lane < 24) sm[v2::wLAM + lane] = cur.lam;
+        if (lane < 12) { pb[lane] = cur.pi; pb[12 + lane] = cur.xn; }
+        if (lane < 24) lb[lane] = cur.lam;
       }
       if (do_update) {
         if (lane < n) ws(k, v2::oZ)[lane] = cur.z;
@@ -870,54 +891,77 @@ struct SrbdSolver {
         }
       }
       __syncwarp();
-      if (lane < n) {
-        // H z: the R block (k < N: rows 0..11) or Q_N's block (k == N) is dense lower; Q is diagonal, S = 0
-        double acc = 0.0;
-        const bool dense_rows = (k == N) || (lane < 12);
-        if (dense_rows) {
+      // ---- fragment form: res_g = H z + g + G pi - [0; pi_{k-1}] - D^T lam ;  res_b = G^T z + b - x_{k+1} ----------
+      double zk[6];
 #pragma unroll
-          for (int j = 0; j < 12; ++j) {
-            const int a = lane >= j ? lane : j, c = lane >= j ? j : lane;
-            acc += Rel(a, c) * sm[v2::wSX + j];
-          }
-        } else {
-          acc = sR[96 + (lane - 12)] * sm[v2::wSX + lane];
-        }
-        double r = acc + sR[108 + lane];
-        if (k < N) {
-          double a2 = 0.0;
+      for (int j = 0; j < 6; ++j) zk[j] = zb[4 * j + t];
+      double c0[2] = {sR[108 + t], sR[112 + t]}, c1[2] = {sR[116 + t], sR[120 + t]}, c2[2] = {sR[124 + t], sR[128 + t]};
+      if (n < 24) { c1[1] = 0.0; c2[0] = 0.0; c2[1] = 0.0; }
+      // dense lower block of rows 0..11 (R_k, or Q_N at stage N)
 #pragma unroll
-          for (int l = 0; l < 12; ++l) a2 += Gel(lane, l) * sm[v2::wXN + l];
-          r += a2;
-        }
-        if (k > 0 && lane >= nu) r -= pim;
-        if (k < N && lane < 12) {  // J^T (lam_u - lam_l) = -D^T lam
-          const int g0 = lane < 6 ? 0 : 12;
-          double a3 = 0.0;
-#pragma unroll
-          for (int g = 0; g < 12; ++g) a3 += cAc[(g0 + g) * 12 + lane] * (0.0 - sm[v2::wLAM + g0 + g]);
-          r += a3;
-        }
-        ws(k, v2::oRG)[lane] = r;
-        ng_ = amax_nan(ng_, r);
+      for (int kt = 0; kt < 3; ++kt) {
+        dmma(c0[0], c0[1], zk[kt], sR[oRs[0][kt]], c0[0], c0[1]);
+        const double r1 = sR[oRs[1][kt]];
+        dmma(c1[0], c1[1], zk[kt], pi < 4 ? r1 : 0.0, c1[0], c1[1]);
       }
       if (k < N) {
-        if (lane < 12) {
-          double acc = 0.0;
-#pragma unroll
-          for (int i = 0; i < 24; ++i)
-            if (i < n) acc += Gel(i, lane) * sm[v2::wSX + i];
-          const double r = (acc + Gel(n, lane)) - cur.xn;
-          ws(k, v2::oRB)[lane] = r;
-          nb_ = amax_nan(nb_, r);
+        if (k > 0) {  // diag(Q) on the x rows 12..23
+          c1[1] = fma(cQ[t], zk[3], c1[1]);
+          c2[0] = fma(cQ[4 + t], zk[4], c2[0]);
+          c2[1] = fma(cQ[8 + t], zk[5], c2[1]);
         }
-        if (lane < 24) {
-          const int j0 = lane < 12 ? 0 : 6;
-          double v = 0.0;
+        double pk_[3], nl[6];
 #pragma unroll
-          for (int j = 0; j < 6; ++j) v += cAc[lane * 12 + j0 + j] * sm[v2::wSX + j0 + j];
-          const double rd = ((cur.lo - v) + cur.t) * cur.mk;
-          const double rm = (cur.lam * cur.t) * cur.mk;
+        for (int j = 0; j < 3; ++j) pk_[j] = pb[4 * j + t];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) nl[j] = 0.0 - lb[4 * j + t];
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {  // + G pi
+          dmma(c0[0], c0[1], pk_[kt], sG[gB + 16 * kt], c0[0], c0[1]);
+          dmma(c1[0], c1[1], pk_[kt], sG[gB + 2 * v2::kGP + 16 * kt], c1[0], c1[1]);
+          if (k > 0) dmma(c2[0], c2[1], pk_[kt], sG[gB + 4 * v2::kGP + 16 * kt], c2[0], c2[1]);
+        }
+        if (k > 0) { c1[1] -= pp[0]; c2[0] -= pp[1]; c2[1] -= pp[2]; }
+#pragma unroll
+        for (int kt = 0; kt < 6; ++kt) {  // J^T (lam_u - lam_l) = -D^T lam
+          dmma(c0[0], c0[1], nl[kt], cAc[oDt + 48 * kt], c0[0], c0[1]);
+          if (kt >= 3) dmma(c1[0], c1[1], nl[kt], cAc[oDt + 48 * kt + 8], c1[0], c1[1]);
+        }
+        // res_b
+        const int pbr = (k > 0 ? 6 : 3) * v2::kGP + 4 * t;  // the b row of BAbt: row n
+        double b0[2] = {sG[pbr], sG[pbr + 16]}, b1[2] = {sG[pbr + 32], 0.0};
+#pragma unroll
+        for (int kt = 0; kt < 6; ++kt) {
+          if (kt < 3 || k > 0) {
+            dmma(b0[0], b0[1], zk[kt], sG[oGT + v2::kGP * kt], b0[0], b0[1]);
+            dmma(b1[0], b1[1], zk[kt], sG[oGT + 32 + v2::kGP * kt], b1[0], b1[1]);
+          }
+        }
+        b0[0] -= pb[12 + t]; b0[1] -= pb[16 + t]; b1[0] -= pb[20 + t];
+        if (r == 0) {
+          ws(k, v2::oRB)[t] = b0[0]; ws(k, v2::oRB)[4 + t] = b0[1]; ws(k, v2::oRB)[8 + t] = b1[0];
+        }
+        nb_ = amax_nan(amax_nan(amax_nan(nb_, b0[0]), b0[1]), b1[0]);
+        pp[0] = pk_[0]; pp[1] = pk_[1]; pp[2] = pk_[2];
+      } else {
+        c0[0] -= pp[0]; c0[1] -= pp[1]; c1[0] -= pp[2];  // stage N: the x rows are rows 0..11
+      }
+      if (r == 0) {
+        ws(k, v2::oRG)[t] = c0[0]; ws(k, v2::oRG)[4 + t] = c0[1]; ws(k, v2::oRG)[8 + t] = c1[0];
+        if (n == 24) {
+          ws(k, v2::oRG)[12 + t] = c1[1]; ws(k, v2::oRG)[16 + t] = c2[0]; ws(k, v2::oRG)[20 + t] = c2[1];
+        }
+      }
+      ng_ = amax_nan(amax_nan(amax_nan(ng_, c0[0]), c0[1]), c1[0]);
+      if (n == 24) ng_ = amax_nan(amax_nan(amax_nan(ng_, c1[1]), c2[0]), c2[1]);
+      // ---- constraint rows (row-per-lane) ------------------------------------------------------------------------------
+      if (k < N) {
+        double v = 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) v += acr[j] * zb[j0 + j];
+        const double rd = ((cur.lo - v) + cur.t) * cur.mk;
+        const double rm = (cur.lam * cur.t) * cur.mk;
+        if (lane < 24) {
           ws(k, v2::oRD)[lane] = rd;
           ws(k, v2::oRM)[lane] = rm;
           ws(k, v2::oRMB)[lane] = rm;
@@ -926,7 +970,6 @@ struct SrbdSolver {
           nm_ = amax_nan(nm_, rm);
         }
       }
-      pi_prev = cur.pi;
       cur = nxt;
     }
     const double flag = warp_sum((ng_ != ng_ || nb_ != nb_ || nd_ != nd_ || nm_ != nm_) ? 1.0 : 0.0);
