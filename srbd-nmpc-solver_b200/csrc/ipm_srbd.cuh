@@ -64,20 +64,27 @@ constexpr int oZ = 0, oDZ = 24, oRG = 48, oLAM = 72, oT = 96, oDLAM = 120, oDT =
 constexpr int kPanF = 102;         // panel stride in the factor tile: rows 0..24 (100) + 2 (bank-conflict-free fragments)
 constexpr int kPan = 148;          // the full panel during the factorization: + rows 25..36 = rows 0..11 of L
 // shared memory (doubles)
-constexpr int kGP = 52;            // padded panel stride of the BAbt tile (4 rows x 12 cols + 4)
+constexpr int kGP = 54;            // padded panel stride of the BAbt tile (4 rows x 12 cols + 6): = 2 mod 4, so that the
+                                   // row-permuted B fragments (rows pi and pi+4 in one half-warp) are bank-conflict free
 constexpr int kW2 = 22;            // row stride of W (21 lower-triangle products of a constraint row's 6-vector)
 constexpr int sAC = 0;             // [24][12] constraint Jacobian, row-major
 constexpr int sW = sAC + 288;      // [24][22]
 constexpr int sQ = sW + 24 * kW2;  // diag(Q) (12), R (1), pad
-constexpr int kCtaShared = sQ + 16;
-constexpr int kGT = 7 * kGP;       // 364: one BAbt tile
-constexpr int kFT = 144 + 3 * kPanF;  // 450: [P 144 | factor panels 3 x 102]
-constexpr int kRT = 132;           // [R lower-panel prefixes 96 | Q diag 12 | rq row 24]
+constexpr int kCtaShared = sQ + 16;    // 832 doubles = 52 x 128 B
+// every tile starts on a 128-byte line (16 doubles): a 512-byte cp.async instruction then writes 4 wavefronts, not 5
+constexpr int kGT = 384;           // one BAbt tile: 7 x 54 = 378 -> 384
+constexpr int kFT = 464;           // [P 144 | factor panels 3 x 102 = 306] = 450 -> 464
+constexpr int kRT = 144;           // [R lower-panel prefixes 96 | Q diag 12 | rq row 24] = 132 -> 144
 constexpr int wG0 = 0, wG1 = kGT;
 constexpr int wF0 = 2 * kGT, wF1 = wF0 + kFT;
-constexpr int wR0 = wF1 + kFT, wR1 = wR0 + kRT;
-constexpr int wS = wR1 + kRT;      // 44
-constexpr int wQX = wS + 44;       // 24 Gamma
+// the factorization / residual sweeps do not use the factor tiles: the running P_{k+1}, the three Cholesky panels
+// and both R tiles live in that region
+constexpr int wP = wF0;            // [12][12]                   144 -> 160
+constexpr int wPAN = wF0 + 160;    // 3 x [37][4]                444 -> 608
+constexpr int wR0 = wF0 + 608, wR1 = wR0 + kRT;
+static_assert(wR1 + kRT <= wF0 + 2 * kFT, "R tiles do not fit behind the factorization scratch");
+constexpr int wS = wF0 + 2 * kFT;  // 44 -> 48
+constexpr int wQX = wS + 48;       // 24 Gamma
 constexpr int wqx = wQX + 24;      // 24 gamma
 constexpr int wSG = wqx + 24;      // 24 gradient
 constexpr int wSX = wSG + 24;      // 24 z of the current stage
@@ -86,11 +93,9 @@ constexpr int wT = wXN + 12;       // 12 t / lv
 constexpr int wPV = wT + 12;       // 12 p_{k+1}
 constexpr int wDI = wPV + 12;      // 12 (spare)
 constexpr int wLAM = wDI + 12;     // 24 lam (residual sweep)
-constexpr int kWarpShared = wLAM + 24;
+constexpr int kWarpShared = wLAM + 24 + 8;   // multiple of 16
+static_assert(kWarpShared % 16 == 0 && kCtaShared % 16 == 0, "tiles must start on 128-byte lines");
 constexpr int kSmemBytes = (kCtaShared + kWarps * kWarpShared) * 8;
-// in the factorization sweep the factor buffers are free: the running P_{k+1} and the three panels live there
-constexpr int wP = wF0;            // [12][12] + p (12)          156 -> 160
-constexpr int wPAN = wF0 + 160;    // 3 x [37][4]                444      (604 <= 2 * 450)
 }  // namespace v2
 
 __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
@@ -1095,9 +1100,9 @@ struct SrbdSolver {
 };
 
 __global__ void __launch_bounds__(128, 3) ipm_srbd_kernel(const SrbdIpmParams p) {
-  extern __shared__ double2 smem2[];
+  extern __shared__ __align__(128) double2 smem2[];  // no static shared memory: the tiles start on 128-byte lines
   double* smem = reinterpret_cast<double*>(smem2);
-  __shared__ int s_next[v2::kWarps];
+  int* s_next = reinterpret_cast<int*>(smem + v2::sQ + 14);  // 4 ints in the pad behind diag(Q), R
   // CTA-shared constants: Ac and, per constraint row g, the 21 lower-triangle products of its 6-vector
   for (int i = threadIdx.x; i < 288; i += blockDim.x) smem[v2::sAC + i] = p.model->Ac[i];
   if (threadIdx.x < 12) smem[v2::sQ + threadIdx.x] = p.model->m.Q[threadIdx.x];
