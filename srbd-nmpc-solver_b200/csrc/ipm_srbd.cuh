@@ -449,14 +449,15 @@ struct SrbdSolver {
         MF[2][5] = ((xr ? qd5 : 0.0) + MF[2][5]) + regd1;
       }
       // ---- blocked Cholesky of the 12 u columns: three 4-column panels ------------------------------------------
-      double EF1 = dg1 ? 1.0 : 0.0, EF2 = 0.0;  // E rows 0..7 (identity), columns 4..7 and 8..11
 #pragma unroll
       for (int pp = 0; pp < 3; ++pp) {
         double* pan = sPan + pp * v2::kPan;
         if (pp < 2) pan[prA0] = MF[0][pp];
         pan[prA1] = MF[1][pp];
         pan[prA2] = MF[2][pp];
-        pan[prE0] = pp == 0 ? (dg0 ? 1.0 : 0.0) : (pp == 1 ? EF1 : EF2);
+        // E rows: the identity block of rows 4pp..4pp+3 -> the substitution leaves L_pp^-T there (the diagonal
+        // blocks of the blocked triangular solves of the vector sweeps); the other E rows are zero
+        pan[prE0] = pp == 0 ? (dg0 ? 1.0 : 0.0) : ((pp == 1 && dg1) ? 1.0 : 0.0);
         if (r < 4) pan[(8 + r) * 4 + t] = (pp == 2 && dg0) ? 1.0 : 0.0;  // E rows 8..11
         if (r == 0) pan[96 + t] = pp == 0 ? c0[0] : (pp == 1 ? c0[1] : c1[0]);  // gradient row: g~[4pp + t]
         __syncwarp();
@@ -491,7 +492,7 @@ struct SrbdSolver {
         const double nlv = -pan[96 + t];
         double dum;
         if (pp == 0) {
-          const double nA0 = -pan[prA0], nA1 = -pan[prA1], nA2 = -pan[prA2], nAE = -pan[prE0];
+          const double nA0 = -pan[prA0], nA1 = -pan[prA1], nA2 = -pan[prA2];
           const double B0 = pan[prB0], B1 = pan[prB1], B2 = pan[prB2];
           dmma(dum, MF[0][1], nA0, B0, MF[0][0], MF[0][1]);
           dmma(dum, MF[1][1], nA1, B0, MF[1][0], MF[1][1]);
@@ -504,10 +505,8 @@ struct SrbdSolver {
             dmma(MF[2][4], MF[2][5], nA2, B2, MF[2][4], MF[2][5]);
             dmma(c2[0], c2[1], nlv, B2, c2[0], c2[1]);
           }
-          dmma(dum, EF1, nAE, B0, 0.0, EF1);
-          dmma(EF2, dum, nAE, B1, EF2, 0.0);
         } else if (pp == 1) {
-          const double nA1 = -pan[prA1], nA2 = -pan[prA2], nAE = -pan[prE0];
+          const double nA1 = -pan[prA1], nA2 = -pan[prA2];
           const double B1 = pan[prB1], B2 = pan[prB2];
           dmma(MF[1][2], MF[1][3], nA1, B1, MF[1][2], MF[1][3]);
           dmma(c1[0], c1[1], nlv, B1, c1[0], c1[1]);
@@ -516,7 +515,6 @@ struct SrbdSolver {
             dmma(MF[2][4], MF[2][5], nA2, B2, MF[2][4], MF[2][5]);
             dmma(c2[0], c2[1], nlv, B2, c2[0], c2[1]);
           }
-          dmma(EF2, dum, nAE, B1, EF2, 0.0);
         } else if (xr) {
           const double nA1 = -pan[prA1], nA2 = -pan[prA2];
           const double B1 = pan[prB1], B2 = pan[prB2];
@@ -543,12 +541,14 @@ struct SrbdSolver {
         for (int e = lane; e < 72; e += 32)
           reinterpret_cast<double2*>(ws(k - 1, v2::oP))[e] = reinterpret_cast<const double2*>(sP)[e];
       }
-      // factor panels (rows 0..24: L^-T, Ls, lv) -> workspace
+      // factor panels -> workspace.  Panel pp, rows 0..11: row i in [4pp, 4pp+4) = L_pp^-T (E rows), row i >= 4pp+4 =
+      // L[i][4pp..4pp+3] (panel rows 25+i); rows 12..23 = Ls, row 24 = lv
 #pragma unroll
       for (int pp = 0; pp < 3; ++pp) {
         const double2* src = reinterpret_cast<const double2*>(sPan + pp * v2::kPan);
         double2* dst = reinterpret_cast<double2*>(ws(k, v2::oFT) + pp * v2::kPanF);
-        dst[lane] = src[lane];
+        const int row = lane >> 1;
+        dst[lane] = src[(row < 12 && row >= 4 * pp + 4) ? lane + 50 : lane];
         if (lane < 18) dst[32 + lane] = src[32 + lane];
       }
       cur = nxt;
@@ -585,7 +585,8 @@ struct SrbdSolver {
   __device__ __forceinline__ void sweep_backvec(int mode, double sm_) {
     const int r = fr, t = ft, pi = fpi;
     const int oG = (pi >> 2) * v2::kGP + 4 * t + (pi & 3);            // G[8I+pi][4kt+t]      : + 2 kGP I + 16 kt
-    const int oLi = 144 + (pi >> 2) * v2::kPanF + 4 * t + (pi & 3);   // Linv[8I+pi][4kt+t]   : + 2 kPanF I + 16 kt
+    // 4x4 blocks of the factor panels as B fragments: row index t / column pi, and row pi / column t
+    const int bA = 144 + 4 * t + (pi & 3), bB = 144 + 4 * (pi & 3) + t;   // + kPanF * (column panel) + 16 * (row block)
     const int oLs = 144 + (12 + pi) * 4 + t;                          // Ls[8I+pi][4kt+t]     : + 32 I + kPanF kt
     const int oDt = t * 12 + pi;                                      // Ac[4kt+t][8I+pi]     : + 8 I + 48 kt
     double pk[3];
@@ -640,24 +641,27 @@ struct SrbdSolver {
         dmma(c1[0], c1[1], tk[kt], sG[oG + 2 * v2::kGP + 16 * kt], c1[0], c1[1]);
         if (k > 0) dmma(c2[0], c2[1], tk[kt], sG[oG + 4 * v2::kGP + 16 * kt], c2[0], c2[1]);
       }
-      // ---- lv = Linv g~_u ------------------------------------------------------------------------------------------------
-      double l0[2] = {0.0, 0.0}, l1[2] = {0.0, 0.0};
+      // ---- lv = L^-1 g~_u: blocked forward substitution (4x4 diagonal blocks by their inverses L_pp^-1, which the
+      // factorization left in the E rows; same operation order as trsv up to the blocks) ----------------------------------
+      double lv0, lv1, lv2, junk;
       {
-        const double gu[3] = {c0[0], c0[1], c1[0]};
-#pragma unroll
-        for (int kt = 0; kt < 3; ++kt) {
-          dmma(l0[0], l0[1], gu[kt], sF[oLi + 16 * kt], l0[0], l0[1]);
-          dmma(l1[0], l1[1], gu[kt], sF[oLi + 2 * v2::kPanF + 16 * kt], l1[0], l1[1]);
-        }
+        const int P1 = v2::kPanF, P2 = 2 * v2::kPanF;
+        double g1, g2;
+        dmma(lv0, junk, c0[0], sF[bA], 0.0, 0.0);                       // lv0 = X0 g0
+        dmma(g1, junk, -lv0, sF[bB + 16], c0[1], 0.0);                  // g1 - L10 lv0
+        dmma(g2, junk, -lv0, sF[bB + 32], c1[0], 0.0);                  // g2 - L20 lv0
+        dmma(lv1, junk, g1, sF[bA + P1 + 16], 0.0, 0.0);                // lv1 = X1 (.)
+        dmma(g2, junk, -lv1, sF[bB + P1 + 32], g2, 0.0);                // ... - L21 lv1
+        dmma(lv2, junk, g2, sF[bA + P2 + 32], 0.0, 0.0);                // lv2 = X2 (.)
       }
       if (r == 0) {  // row 24 of the factor panels
         double* lvd = ws(k, v2::oFT) + 96 + t;
-        lvd[0] = l0[0]; lvd[v2::kPanF] = l0[1]; lvd[2 * v2::kPanF] = l1[0];
+        lvd[0] = lv0; lvd[v2::kPanF] = lv1; lvd[2 * v2::kPanF] = lv2;
       }
       // ---- p = g~_x - Ls lv  (g~_x = second half of tile 1 and tile 2: pure register renaming) -----------------------
       if (k > 0) {
         double p0[2] = {c1[1], c2[0]}, p1[2] = {c2[1], 0.0};
-        const double nl[3] = {-l0[0], -l0[1], -l1[0]};
+        const double nl[3] = {-lv0, -lv1, -lv2};
 #pragma unroll
         for (int kt = 0; kt < 3; ++kt) {
           dmma(p0[0], p0[1], nl[kt], sF[oLs + v2::kPanF * kt], p0[0], p0[1]);
@@ -695,7 +699,8 @@ struct SrbdSolver {
   __device__ __forceinline__ void sweep_forward(bool fin, double& ap, double& ad) {
     const int r = fr, t = ft, pi = fpi;
     const int oLT = 144 + (pi >> 2) * v2::kPanF + 48 + 4 * t + (pi & 3);  // Ls[4kt+t][8I+pi]   : + 2 kPanF I + 16 kt
-    const int oIT = 144 + pi * 4 + t;                                     // Linv[4kt+t][8I+pi] : + 32 I + kPanF kt
+    // 4x4 blocks of the factor panels as B fragments: row index t / column pi, and row pi / column t
+    const int bA = 144 + 4 * t + (pi & 3), bB = 144 + 4 * (pi & 3) + t;   // + kPanF * (column panel) + 16 * (row block)
     const int oGT = 4 * pi + t;                                           // G[4kt+t][8I+pi]    : + 32 I + kGP kt
     const int oPP = pi * 12 + t;                                          // P[8I+pi][4kt+t]    : + 96 I + 4 kt
     const int oLV = 144 + 96 + t;                                         // lv[4kt+t]          : + kPanF kt
@@ -734,17 +739,18 @@ struct SrbdSolver {
           dmma(cx1[0], cx1[1], xk[kt], sG[oGT + 32 + v2::kGP * (3 + kt)], cx1[0], cx1[1]);
         }
       }
-      // ---- u = -Linv^T t ------------------------------------------------------------------------------------------------
-      double u0[2] = {0.0, 0.0}, u1[2] = {0.0, 0.0};
+      // ---- u = -L^-T t: blocked back substitution (diagonal blocks by L_pp^-T) ---------------------------------------
+      double uk[3];
       {
-        const double nt[3] = {-t0[0], -t0[1], -t1[0]};
-#pragma unroll
-        for (int kt = 0; kt < 3; ++kt) {
-          dmma(u0[0], u0[1], nt[kt], sF[oIT + v2::kPanF * kt], u0[0], u0[1]);
-          dmma(u1[0], u1[1], nt[kt], sF[oIT + 32 + v2::kPanF * kt], u1[0], u1[1]);
-        }
+        const int P1 = v2::kPanF, P2 = 2 * v2::kPanF;
+        double w0, w1, junk;
+        dmma(uk[2], junk, -t1[0], sF[bB + P2 + 32], 0.0, 0.0);           // u2 = X2^T (-t2)
+        dmma(w1, junk, -uk[2], sF[bA + P1 + 32], -t0[1], 0.0);           // -t1 - L21^T u2
+        dmma(w0, junk, -uk[2], sF[bA + 32], -t0[0], 0.0);                // -t0 - L20^T u2
+        dmma(uk[1], junk, w1, sF[bB + P1 + 16], 0.0, 0.0);               // u1 = X1^T (.)
+        dmma(w0, junk, -uk[1], sF[bA + 16], w0, 0.0);                    // ... - L10^T u1
+        dmma(uk[0], junk, w0, sF[bB], 0.0, 0.0);                         // u0 = X0^T (.)
       }
-      const double uk[3] = {u0[0], u0[1], u1[0]};
       if (r == 0) {  // row-per-lane consumers read u from shared memory
         ubuf[t] = uk[0]; ubuf[4 + t] = uk[1]; ubuf[8 + t] = uk[2];
       }
