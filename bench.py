@@ -163,6 +163,8 @@ def main():
         run_reference(args, pkg, rank, world)
         return
 
+    # NCCL prints its version banner on STDOUT when NCCL_DEBUG is VERSION/INFO: stdout carries exactly one JSON line
+    os.environ["NCCL_DEBUG"] = os.environ.get("SRBD_NCCL_DEBUG", "WARN")
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -252,7 +254,11 @@ def main():
     e2e_value = world * B / (e2e_ms_max * 1e-3)
     h2d = sum(int(hb[k].nbytes) for k in hb)
     d2h = int(h_sx.nbytes + h_su.nbytes + h_it.nbytes + h_st.nbytes)
-    assert (h_st == 0).all() and np.array_equal(h_it, st["iter"]), "e2e path disagrees with the device-resident path"
+    # both paths run the same kernels on the same inputs: results must be identical.  (Not every QP has to converge:
+    # at tol 1e-8 the IPM sits on its rounding floor for roughly 1 QP in 30000 -- in the CPU oracle as well, on other
+    # QPs, see DESIGN.md section 2 -- the status counts are reported below.)
+    assert np.array_equal(h_st, st["status"]) and np.array_equal(h_it, st["iter"]), \
+        "e2e path disagrees with the device-resident path"
 
     if rank == 0:
         # roofline of the dominant kernel (K3): algorithmic FP64 flops with the ACTUAL iteration counts

@@ -4,7 +4,7 @@ fragment layout of mma.m8n8k4.f64 (A: row = lane>>2, col = lane&3; B: row = lane
 C/D: row = lane>>2, cols 2*(lane&3)+{0,1}).  Validates the fragment / permutation bookkeeping on the CPU
 against a plain numpy Riccati step before it is transcribed to CUDA.
 
-    python scripts/proto_dmma_factor.py
+    python scripts/proto_dmma_factor.py        (also run by tests/test_fragment_protos.py)
 """
 import numpy as np
 
@@ -78,8 +78,9 @@ def factor_stage(G, Pn, Hinit, gt, n, reg):
         for p in (2 * I, 2 * I + 1):
             diag = (8 * I + R_) == (4 * p + T_)
             MF[I][p] = MF[I][p] + np.where(diag & (8 * I + R_ < n), reg, 0.0)
-    # ---- E rows (identity): tile E0 = rows 0..7, E1 = rows 8..11; EF[e][p] p = 0..2 ----
+    # ---- E rows: per panel p the identity block of rows 4p..4p+3 (the substitution turns it into L_pp^-T) ----
     EF = [[np.where((8 * e + R_ == 4 * p + T_) & (8 * e + R_ < 12), 1.0, 0.0) for p in range(3)] for e in range(2)]
+    FT = np.zeros((3, 25, 4))
     # panel buffer rows: 0..23 M rows, 24 gradient, 25..36 E rows
     g = gt.copy()  # lane c holds g[c] (row-per-lane), here a plain vector
     Lrows = np.zeros((37, 12))
@@ -110,7 +111,7 @@ def factor_stage(G, Pn, Hinit, gt, n, reg):
                 L44[i, j] = s * iv[j]
         inv_diag[4 * p:4 * p + 4] = iv
         # ---- own-row substitution: rows 4p..23 (M), 24 (gradient), E rows 0..4p+3 ----
-        rows = [i for i in range(4 * p, n)] + [24] + [25 + i for i in range(4 * p + 4)]
+        rows = [i for i in range(4 * p, n)] + [24] + [25 + i for i in range(4 * p, 4 * p + 4)]
         for row in rows:
             a0 = pan[row]
             l = np.zeros(4)
@@ -148,15 +149,29 @@ def factor_stage(G, Pn, Hinit, gt, n, reg):
                     MF[I][2 * J] = d0
                 if 2 * J + 1 > p:
                     MF[I][2 * J + 1] = d1
-        # E tile 0 (rows 0..7 of E): columns 4p+4 .. 11
-        if p == 0:
-            d0, d1 = dmma(EF[0][0], EF[0][1], Afrag(25), Bfrag(0)); EF[0][1] = d1
-            d0, d1 = dmma(EF[0][2], np.zeros(32), Afrag(25), Bfrag(1)); EF[0][2] = d0
-        if p == 1:
-            d0, d1 = dmma(EF[0][2], np.zeros(32), Afrag(25), Bfrag(1)); EF[0][2] = d0
+        # factor panel p as the kernel exports it: rows 4p..4p+3 = L_pp^-T (E rows), rows > 4p+3 (< 12) = L rows,
+        # rows 12..23 = Ls, row 24 = lv
+        for i in range(12):
+            if 4 * p <= i < 4 * p + 4:
+                FT[p, i] = pan[25 + i]
+            elif i >= 4 * p + 4:
+                FT[p, i] = pan[i]
+        FT[p, 12:24] = pan[12:24] if n == 24 else 0.0
+        FT[p, 24] = pan[24]
     L = Lrows[:n, :]
-    LinvT = Lrows[25:37, :]  # E_L = Lr^-T : [i][j] = Linv[j][i]
     lv = Lrows[24, :]
+    # what the vector sweeps do with the panels: blocked forward substitution = L^-1 (checked column by column)
+    Linv = np.zeros((12, 12))
+    for c in range(12):
+        e_c = np.zeros(12); e_c[c] = 1.0
+        out = np.zeros(12)
+        for pb in range(3):
+            gp = e_c[4 * pb:4 * pb + 4].copy()
+            for qb in range(pb):
+                gp -= FT[qb, 4 * pb:4 * pb + 4, :] @ out[4 * qb:4 * qb + 4]      # L_pq block
+            out[4 * pb:4 * pb + 4] = FT[pb, 4 * pb:4 * pb + 4, :].T @ gp        # (L_pp^-T)^T
+        Linv[:, c] = out
+    LinvT = Linv.T
     if n == 24:
         P = np.zeros((12, 12))
         for I, p in ((1, 3), (2, 3), (2, 4), (2, 5)):

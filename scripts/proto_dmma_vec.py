@@ -4,12 +4,16 @@
 row-permuted B fragments, and the accumulator (c0, c1) of output tile I IS the next A operand (k-tiles 2I, 2I+1).
 Checks the fragment gather addresses (factor panels, P, BAbt panel-major) against plain numpy.
 
-    python scripts/proto_dmma_vec.py
+    python scripts/proto_dmma_vec.py        (also run by tests/test_fragment_protos.py)
 """
 import numpy as np
-from proto_dmma_factor import dmma, R_, T_, PI
+import os
+import sys
 
-KPANF = 100
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from proto_dmma_factor import dmma, R_, T_, PI  # noqa: E402
+
+KPANF = 102
 
 
 def vfrag(v, kt):
@@ -42,12 +46,20 @@ def main():
     X = rng.normal(size=(12, 12)); P = X @ X.T
     G = rng.normal(size=(24, 12))
     # ---- storage: factor panels FT[3][25][4], P row-major, BAbt panel-major (28 x 12) ----
+    # factor panels as the factorization exports them: panel p, rows 0..11: rows 4p..4p+3 = L_pp^-T, rows > 4p+3 = L rows;
+    # rows 12..23 = Ls, row 24 = lv  (L = inverse of the random Linv)
+    Lm = np.linalg.inv(Linv)
     FT = np.zeros(3 * KPANF)
-    for l in range(12):
-        for i in range(12):
-            FT[(l >> 2) * KPANF + i * 4 + (l & 3)] = Linv[l][i]          # E row i, column l = Linv^T[i][l]
-            FT[(l >> 2) * KPANF + (12 + i) * 4 + (l & 3)] = Ls[i][l]
-        FT[(l >> 2) * KPANF + 96 + (l & 3)] = lv[l]
+    for pb in range(3):
+        Xp = np.linalg.inv(Lm[4 * pb:4 * pb + 4, 4 * pb:4 * pb + 4])
+        for c in range(4):
+            for i in range(4 * pb, 4 * pb + 4):
+                FT[pb * KPANF + i * 4 + c] = Xp.T[i - 4 * pb][c]
+            for i in range(4 * pb + 4, 12):
+                FT[pb * KPANF + i * 4 + c] = Lm[i][4 * pb + c]
+            for i in range(12):
+                FT[pb * KPANF + (12 + i) * 4 + c] = Ls[i][4 * pb + c]
+            FT[pb * KPANF + 96 + c] = lv[4 * pb + c]
     Pm = P.reshape(-1).copy()
     BAbt = np.zeros(336)
     for i in range(24):
@@ -60,10 +72,12 @@ def main():
     # output row index i = 8I + pi(r), input index j = 4kt + t
     i_of = lambda I: 8 * I + pi
     ok12 = lambda I, kt: i_of(I) < 12
-    F_Linv = frags(lambda I, kt: (i_of(I) >> 2) * KPANF + (4 * kt + t) * 4 + (i_of(I) & 3), FT, 2, 3, ok12)
     F_Ls = frags(lambda I, kt: kt * KPANF + (12 + i_of(I)) * 4 + t, FT, 2, 3, ok12)
     F_LsT = frags(lambda I, kt: (i_of(I) >> 2) * KPANF + (12 + 4 * kt + t) * 4 + (i_of(I) & 3), FT, 2, 3, ok12)
-    F_LinvT = frags(lambda I, kt: kt * KPANF + i_of(I) * 4 + t, FT, 2, 3, ok12)
+    # 4x4 blocks of the panels (the kernel's bA / bB offsets): row index t / column pi, and row pi / column t
+    bA = 4 * t + (pi & 3); bB = 4 * (pi & 3) + t; ok4 = pi < 4
+    blkA = lambda col_panel, row_block: gather(FT, bA + col_panel * KPANF + 16 * row_block, ok4)
+    blkB = lambda col_panel, row_block: gather(FT, bB + col_panel * KPANF + 16 * row_block, ok4)
     F_P = frags(lambda I, kt: i_of(I) * 12 + 4 * kt + t, Pm, 2, 3, ok12)
     F_G = frags(lambda I, kt: (i_of(I) >> 2) * 48 + 4 * (4 * kt + t) + (i_of(I) & 3), BAbt, 3, 3, lambda I, kt: i_of(I) < 24)
     F_GT = frags(lambda I, kt: kt * 48 + 4 * i_of(I) + t, BAbt, 2, 6, ok12)   # G^T: out j = 8I+pi, in i = 4kt+t
@@ -97,9 +111,15 @@ def main():
     gt = gemv(F_G, [vfrag(tvec, kt) for kt in range(3)], gt, 3)          # g~ = rg + G t
     g_ref = rg + G @ tvec
     assert np.allclose(to_vec(gt, 24), g_ref)
-    # lv = Linv g_u : A operand k-tiles = (tile0.c0, tile0.c1, tile1.c0)
+    # lv = L^-1 g_u: blocked forward substitution; one DMMA per 4x4 block, c0 of the accumulator = the k-tile
     gu = [gt[0][0], gt[0][1], gt[1][0]]
-    lvt = gemv(F_Linv, gu, [(Z, Z), (Z, Z)], 2)
+    lv0, _ = dmma(Z, Z, gu[0], blkA(0, 0))
+    g1, _ = dmma(gu[1], Z, -lv0, blkB(0, 1))
+    g2, _ = dmma(gu[2], Z, -lv0, blkB(0, 2))
+    lv1, _ = dmma(Z, Z, g1, blkA(1, 1))
+    g2, _ = dmma(g2, Z, -lv1, blkB(1, 2))
+    lv2, _ = dmma(Z, Z, g2, blkA(2, 2))
+    lvt = [(lv0, lv1), (lv2, Z)]
     lv_ref = Linv @ g_ref[:12]
     assert np.allclose(to_vec(lvt, 12), lv_ref)
     # p = g_x - Ls lv : C init = (tile1.c1, tile2.c0), (tile2.c1, -)
@@ -114,7 +134,14 @@ def main():
     t_ref = Ls.T @ x + lv
     assert np.allclose(to_vec(tt, 12), t_ref)
     nt = [-tt[0][0], -tt[0][1], -tt[1][0]]
-    ut = gemv(F_LinvT, nt, [(Z, Z), (Z, Z)], 2)                          # u = -Linv^T t
+    # u = -L^-T t: blocked back substitution
+    u2, _ = dmma(Z, Z, nt[2], blkB(2, 2))
+    w1, _ = dmma(nt[1], Z, -u2, blkA(1, 2))
+    w0, _ = dmma(nt[0], Z, -u2, blkA(0, 2))
+    u1, _ = dmma(Z, Z, w1, blkB(1, 1))
+    w0, _ = dmma(w0, Z, -u1, blkA(0, 1))
+    u0, _ = dmma(Z, Z, w0, blkB(0, 0))
+    ut = [(u0, u1), (u2, Z)]
     u_ref = -Linv.T @ t_ref
     assert np.allclose(to_vec(ut, 12), u_ref)
     zk = [ut[0][0], ut[0][1], ut[1][0]] + xk                             # z = [u; x] as 6 k-tiles
@@ -124,7 +151,7 @@ def main():
     xnk = [xn[0][0], xn[0][1], xn[1][0]]
     dpi = gemv(F_P, xnk, [cfrag(pn, 0), cfrag(pn, 1)], 2)                # dpi = P x+ + p
     assert np.allclose(to_vec(dpi, 12), P @ xn_ref + pn)
-    print("S4 / S2 fragment-form bodies OK")
+    print("S4 / S2 fragment-form bodies OK (blocked triangular solves)")
 
 
 if __name__ == "__main__":

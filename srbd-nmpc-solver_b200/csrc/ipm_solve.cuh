@@ -193,6 +193,7 @@ struct Solver {
   __device__ __forceinline__ double* wX(int off, int k) const { return W + off + k * dm.nx(); }
   __device__ __forceinline__ double* wC(int off, int k) const { return W + off + k * ncm(); }
   __device__ __forceinline__ double* wLi(int k) const { return W + L.ws_Li + k * dm.nu() * dm.nu(); }
+  __device__ __forceinline__ double* wLr(int k) const { return W + L.ws_Lr + k * dm.nu() * dm.nu(); }
   __device__ __forceinline__ double* wLs(int k) const { return W + L.ws_Ls + k * dm.nx() * dm.nu(); }
   __device__ __forceinline__ double* wlv(int k) const { return W + L.ws_lv + k * dm.nu(); }
   __device__ __forceinline__ double* wP(int k) const { return W + L.ws_P + k * dm.nx() * dm.nx(); }
@@ -417,6 +418,8 @@ struct Solver {
           double* Ls = wLs(k);
           double* Pk = wP(k);
           for (int e = lane; e < nu * nu; e += 32) Li[e] = sLi[(e / nu) * LDI + (e % nu)];   // row-major
+          double* Lrk = wLr(k);  // the triangular factor itself: the vector solves substitute with it (trsv)
+          for (int e = lane; e < nu * nu; e += 32) Lrk[e] = sM[(e / nu) * LD + (e % nu)];
           for (int e = lane; e < nx * nu; e += 32) Ls[e] = sM[(nu + e / nu) * LD + (e % nu)];  // row-major nx x nu
           for (int e = lane; e < nx * nx; e += 32) Pk[e] = sP[(e / nx) * LDP + (e % nx)];
           if (lane < nu) wlv(k)[lane] = sM[n * LD + lane];
@@ -425,15 +428,23 @@ struct Solver {
         __syncwarp();
       } else {
         // ---- vector part only: lv = Linv g_u ; p = g_x - Ls lv -------------------------------------------
-        const double* Li = wLi(k);
+        // lv = Lr^-1 g_u by forward substitution with Lr itself, row by row in the oracle's (BLASFEO trsv)
+        // operation order: an explicit Lr^-1 leaves a residual ~ eps cond(H~uu) |g| in the Newton system, which at
+        // tol 1e-8 decides between convergence and stagnation on the rounding floor
+        const double* Lrk = wLr(k);
         const double* Ls = wLs(k);
-        if (lane < nu) {
-          double acc = 0.0;
-          for (int j = 0; j <= lane; ++j) acc += Li[lane * nu + j] * sg[j];
-          st[lane] = acc;
-          wlv(k)[lane] = acc;
-        }
+        for (int e = lane; e < nu * nu; e += 32) sLi[(e / nu) * LDI + (e % nu)] = Lrk[e];
         __syncwarp();
+        for (int i = 0; i < nu; ++i) {
+          if (lane == i) {
+            double acc = sg[i];
+            for (int j = 0; j < i; ++j) acc -= sLi[i * LDI + j] * st[j];
+            acc = acc / sLi[i * LDI + i];
+            st[i] = acc;
+            wlv(k)[i] = acc;
+          }
+          __syncwarp();
+        }
         if (lane < nx) {
           double acc = sg[nu + lane];
           for (int l = 0; l < nu; ++l) acc -= Ls[lane * nu + l] * st[l];
@@ -452,10 +463,11 @@ struct Solver {
       const St s = stage(k);
       const int n = s.n, nu = s.nu, nx = s.nx, nxn = s.nxn;
       double* z = wN(off_z, k);
-      const double* Li = wLi(k);
+      const double* Lrk = wLr(k);
       const double* Ls = wLs(k);
       // sx[nu..n) = x part (written by the previous stage into z)
       if (lane < nx) sx[nu + lane] = z[nu + lane];
+      for (int e = lane; e < nu * nu; e += 32) sLi[(e / nu) * LDI + (e % nu)] = Lrk[e];
       __syncwarp();
       if (lane < nu) {  // t = Ls^T x + lv
         double acc = 0.0;
@@ -463,9 +475,17 @@ struct Solver {
         st[lane] = acc + wlv(k)[lane];
       }
       __syncwarp();
-      if (lane < nu) {  // u = -Linv^T t
-        double acc = 0.0;
-        for (int j = lane; j < nu; ++j) acc += Li[j * nu + lane] * st[j];
+      // u = -Lr^-T t by back substitution (row by row, ascending inner index like the oracle / trsv)
+      for (int i = nu - 1; i >= 0; --i) {
+        if (lane == i) {
+          double acc = st[i];
+          for (int j = i + 1; j < nu; ++j) acc -= sLi[j * LDI + i] * st[j];
+          st[i] = acc / sLi[i * LDI + i];
+        }
+        __syncwarp();
+      }
+      if (lane < nu) {
+        const double acc = st[lane];
         sx[lane] = -acc;
         z[lane] = -acc;
       }
