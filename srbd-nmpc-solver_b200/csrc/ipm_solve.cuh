@@ -428,7 +428,7 @@ struct Solver {
         __syncwarp();
       } else {
         // ---- vector part only: lv = Linv g_u ; p = g_x - Ls lv -------------------------------------------
-        // lv = Lr^-1 g_u by forward substitution with Lr itself, row by row in the oracle's (BLASFEO trsv)
+        // lv = Lr^-1 g_u by forward substitution with Lr itself, row by row in BLASFEO's trsv
         // operation order: an explicit Lr^-1 leaves a residual ~ eps cond(H~uu) |g| in the Newton system, which at
         // tol 1e-8 decides between convergence and stagnation on the rounding floor
         const double* Lrk = wLr(k);
@@ -475,7 +475,7 @@ struct Solver {
         st[lane] = acc + wlv(k)[lane];
       }
       __syncwarp();
-      // u = -Lr^-T t by back substitution (row by row, ascending inner index like the oracle / trsv)
+      // u = -Lr^-T t by back substitution (row by row, ascending inner index like BLASFEO's trsv)
       for (int i = nu - 1; i >= 0; --i) {
         if (lane == i) {
           double acc = st[i];

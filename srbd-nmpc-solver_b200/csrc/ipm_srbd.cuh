@@ -116,21 +116,6 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b,
       : "=d"(d0), "=d"(d1)
       : "d"(a), "d"(b), "d"(c0), "d"(c1));
 }
-// sqrt(x) and 1/sqrt(x) for a positive pivot: MUFU.RSQ64H seed + two Goldschmidt steps (no special-case
-// branches; a non-positive pivot gives s = inv = 0 like BLASFEO's potrf, cf. oracle/ocp_qp_ipm.c potrf_l_mn)
-__device__ __forceinline__ void sqrt_rsqrt(double x, double& s, double& inv) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;\n" : "=d"(y) : "d"(x));
-  double g = x * y, h = 0.5 * y;
-  double r = fma(-g, h, 0.5);
-  g = fma(g, r, g); h = fma(h, r, h);
-  r = fma(-g, h, 0.5);
-  g = fma(g, r, g); h = fma(h, r, h);
-  const bool ok = x > 0.0;
-  s = ok ? g : 0.0;
-  inv = ok ? h + h : 0.0;
-}
-
 struct SrbdSolver {
   const SrbdIpmParams& p;
   int lane, q, N;
@@ -231,12 +216,6 @@ struct SrbdSolver {
       }
     }
   }
-  __device__ __forceinline__ double Gel(int i, int l) const { return sG[(i >> 2) * v2::kGP + 4 * l + (i & 3)]; }
-  // R(i,c), i >= c, i < 12
-  __device__ __forceinline__ double Rel(int i, int c) const {
-    const int pnl = i >> 2;
-    return sR[(pnl == 0 ? 0 : (pnl == 1 ? 16 : 48)) + 4 * c + (i & 3)];
-  }
   __device__ __forceinline__ void set_bufs(int b) {
     sG = sm + (b ? v2::wG1 : v2::wG0);
     sF = sm + (b ? v2::wF1 : v2::wF0);
@@ -263,7 +242,7 @@ struct SrbdSolver {
   }
   // 1/sqrt(x) of a positive pivot: MUFU.RSQ64H seed (rel. error < 2^-20) + one third-order step
   // y (1 + e/2 + 3 e^2/8), e = 1 - x y^2  (error ~ e^3); a non-positive pivot gives 0 like BLASFEO's potrf
-  // (oracle/ocp_qp_ipm.c potrf_l_mn)
+  // (BLASFEO potrf_l_mn semantics)
   static __device__ __forceinline__ double rsqrt_pivot(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;\n" : "=d"(y) : "d"(x));
