@@ -135,10 +135,33 @@ def run_reference(args, pkg, rank, world):
                              "sample": f"{sample} QPs per step x {args.steps} steps, OpenMP over QPs, all host threads; "
                                        "CPU oracle port (reference HPIPM/BLASFEO/Eigen not buildable offline)"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit_json(line)
+
+
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: everything else any library prints there (the NCCL version banner comes
+    from C code, whatever NCCL_DEBUG says) is sent to stderr; emit_json() writes to the saved descriptor."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -312,7 +335,7 @@ def main():
                 "ipm": {"iter_mean": float(it.mean()), "iter_min": int(it.min()), "iter_max": int(it.max()),
                         "status_counts_all_ranks": stats_all["status_count"], "solves_all_ranks": stats_all["solves"],
                         "iter_sum_all_ranks": stats_all["iter_sum"], "res_max_all_ranks": stats_all["res_max"]}}
-        print(json.dumps(line), flush=True)
+        emit_json(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
