@@ -290,14 +290,15 @@ def main():
         k3_ms = float(k_ms[:, 2].mean())
         achieved = flops_launch / (k3_ms * 1e-3) / 1e12
         peak = ctx.fp64_peak() / 1e12
-        traffic, traffic_src = None, None
+        traffic, traffic_src, pipes_ncu = None, None, None
         tpath = os.path.join(ROOT, "profiles", "k3_traffic.json")
         if os.path.exists(tpath):  # dram bytes of K3 from the committed `ncu --set full` capture, scaled per QP
             tj = json.load(open(tpath))
             traffic, traffic_src = tj["dram_bytes_per_qp"] * B, tj["source"]
+            pipes_ncu = tj.get("pipes_ncu")
         roofline = {"bound": "fp64", "kernel": "ipm_srbd_kernel (K3)", "achieved": achieved, "peak": peak,
                     "unit": "TFLOP/s", "frac": achieved / peak if peak > 0 else None, "traffic": traffic,
-                    "traffic_source": traffic_src,
+                    "traffic_source": traffic_src, "pipes_ncu": pipes_ncu,
                     "peak_source": "measured live: DFMA-saturating microbenchmark srbd_fp64_peak() (MEASURED_PEAKS.json "
                                    "carries no FP64 figure)",
                     "flops_per_launch": flops_launch, "kernel_ms": k3_ms,
