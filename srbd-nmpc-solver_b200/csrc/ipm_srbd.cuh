@@ -195,26 +195,11 @@ struct SrbdSolver {
     cp_async16(dst + (pnl == 0 ? 0 : (pnl == 1 ? 16 : 48)) + 2 * o, src + pnl * 96 + 2 * o);
     if (lane < 16) cp_async16(dst + 48 + 2 * (lane + 8), src + 192 + 2 * (lane + 8));
   }
-  // R block of RSQrq (rows 0..11, lower: prefixes of panels 0..2), the diagonal of Q, the gradient row n
+  // R block of RSQrq and the gradient row n = [r; q] (24 scattered doubles: row n of the panel-major record)
   __device__ __forceinline__ void prefetch_R(int k, int b) {
-    const double* src = gRSQ(k);
-    double* dst = sm + (b ? v2::wR1 : v2::wR0);
+    prefetch_Rblk(k, b);
     const int n = (k < N ? 12 : 0) + (k > 0 ? 12 : 0);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const int c = lane + 32 * i;
-      if (c < 48) {
-        const int pnl = c < 8 ? 0 : (c < 24 ? 1 : 2);
-        const int o = c - (pnl == 0 ? 0 : (pnl == 1 ? 8 : 24));
-        cp_async16(dst + (pnl == 0 ? 0 : (pnl == 1 ? 16 : 48)) + 2 * o, src + pnl * 96 + 2 * o);
-      } else if (c < 60) {
-        const int i2 = 12 + (c - 48);
-        if (n == 24) cp_async8(dst + 96 + (c - 48), src + pm_index(i2, i2, 24));
-      } else if (c < 84) {
-        const int cc = c - 60;
-        if (cc < n) cp_async8(dst + 108 + cc, src + pm_index(n, cc, 24));
-      }
-    }
+    if (lane < n) cp_async8(sm + (b ? v2::wR1 : v2::wR0) + 108 + lane, gRSQ(k) + (n >> 2) * 96 + 4 * lane + (n & 3));
   }
   __device__ __forceinline__ void set_bufs(int b) {
     sG = sm + (b ? v2::wG1 : v2::wG0);
@@ -802,27 +787,44 @@ struct SrbdSolver {
   // stored), so the update costs no extra pass; res_m is backed up (BACKUP_RES_M) in the same pass.
   // ------------------------------------------------------------------------------------------------
   struct S6v { double z, pi, lam, t, xn, lo, mk; };
-  __device__ __forceinline__ S6v load_s6(int k, bool do_update, double sp, double sd) const {
+  // raw loads of a stage (issued one stage ahead: NO arithmetic on them here, or the warp would wait for the loads at
+  // the prefetch point) ...
+  struct S6raw { double z, pi, lam, t, xn, lo, mk, dz, dpi, dlam, dt, dxn; };
+  __device__ __forceinline__ S6raw load_s6(int k, bool do_update) const {
     const int lc = lane < 24 ? lane : 0, l12 = lane < 12 ? lane : 0;
-    S6v v;
-    v.z = ws(k, v2::oZ)[lc];
+    S6raw v;
+    v.z = __ldcg(ws(k, v2::oZ) + lc);
     v.pi = 0.0; v.lam = 0.0; v.t = 1.0; v.xn = 0.0; v.lo = 0.0; v.mk = 0.0;
+    v.dz = 0.0; v.dpi = 0.0; v.dlam = 0.0; v.dt = 0.0; v.dxn = 0.0;
     const int xo = (k + 1 < N ? 12 : 0);
     if (k < N) {
-      v.pi = ws(k, v2::oPI)[l12]; v.lam = ws(k, v2::oLAM)[lc]; v.t = ws(k, v2::oT)[lc];
-      v.xn = ws(k + 1, v2::oZ)[xo + l12]; v.lo = __ldg(gD(k) + lc); v.mk = __ldg(gMask(k) + lc);
+      v.pi = __ldcg(ws(k, v2::oPI) + l12); v.lam = __ldcg(ws(k, v2::oLAM) + lc); v.t = __ldcg(ws(k, v2::oT) + lc);
+      v.xn = __ldcg(ws(k + 1, v2::oZ) + xo + l12); v.lo = __ldg(gD(k) + lc); v.mk = __ldg(gMask(k) + lc);
     }
     if (do_update) {
-      v.z += sp * ws(k, v2::oDZ)[lc];
+      v.dz = __ldcg(ws(k, v2::oDZ) + lc);
       if (k < N) {
-        v.pi += sd * ws(k, v2::oDPI)[l12];
-        v.xn += sp * ws(k + 1, v2::oDZ)[xo + l12];
-        v.t += sp * ws(k, v2::oDT)[lc];
-        v.lam += sd * ws(k, v2::oDLAM)[lc];
-        if (p.a.t_lam_min == 2 && v.mk != 0.0) {
-          v.t = v.t < p.a.t_min ? p.a.t_min : v.t;
-          v.lam = v.lam < p.a.lam_min ? p.a.lam_min : v.lam;
-        }
+        v.dpi = __ldcg(ws(k, v2::oDPI) + l12);
+        v.dxn = __ldcg(ws(k + 1, v2::oDZ) + xo + l12);
+        v.dt = __ldcg(ws(k, v2::oDT) + lc);
+        v.dlam = __ldcg(ws(k, v2::oDLAM) + lc);
+      }
+    }
+    return v;
+  }
+  // ... and the variable update d_update_var_qp applied to them when the stage is processed
+  __device__ __forceinline__ S6v updated(const S6raw& w, bool do_update, double sp, double sd) const {
+    S6v v;
+    v.z = w.z; v.pi = w.pi; v.lam = w.lam; v.t = w.t; v.xn = w.xn; v.lo = w.lo; v.mk = w.mk;
+    if (do_update) {
+      v.z += sp * w.dz;
+      v.pi += sd * w.dpi;
+      v.xn += sp * w.dxn;
+      v.t += sp * w.dt;
+      v.lam += sd * w.dlam;
+      if (p.a.t_lam_min == 2 && v.mk != 0.0) {
+        v.t = v.t < p.a.t_min ? p.a.t_min : v.t;
+        v.lam = v.lam < p.a.lam_min ? p.a.lam_min : v.lam;
       }
     }
     return v;
@@ -851,7 +853,7 @@ struct SrbdSolver {
     double ng_ = 0.0, nb_ = 0.0, nd_ = 0.0, nm_ = 0.0, smu = 0.0;
     prefetch_G(0, 0, 7);
     prefetch_R(0, 0);
-    S6v cur = load_s6(0, do_update, sp, sd);
+    S6raw raw = load_s6(0, do_update);
     double pp[3] = {0.0, 0.0, 0.0};  // updated pi_{k-1}, fragment form
     for (int k = 0; k <= N; ++k) {
       const int b = k & 1;
@@ -859,11 +861,11 @@ struct SrbdSolver {
       cp_async_wait_all();
       __syncwarp();
       set_bufs(b);
-      S6v nxt = cur;
+      const S6v cur = updated(raw, do_update, sp, sd);
       if (k < N) {
         if (k + 1 < N) prefetch_G(k + 1, b ^ 1, 7);
         prefetch_R(k + 1, b ^ 1);
-        nxt = load_s6(k + 1, do_update, sp, sd);
+        raw = load_s6(k + 1, do_update);
       }
       double* zb = sm + (b ? v2::wSX : v2::wSG);       // z (24)
       double* lb = sm + (b ? v2::wqx : v2::wQX);       // lam (24)
@@ -960,7 +962,6 @@ struct SrbdSolver {
           nm_ = amax_nan(nm_, rm);
         }
       }
-      cur = nxt;
     }
     const double flag = warp_sum((ng_ != ng_ || nb_ != nb_ || nd_ != nd_ || nm_ != nm_) ? 1.0 : 0.0);
     res[0] = warp_max(ng_ == ng_ ? ng_ : 0.0);
