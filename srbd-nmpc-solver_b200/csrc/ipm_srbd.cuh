@@ -986,6 +986,7 @@ struct SrbdSolver {
     const srbd_ipm_args& a = p.a;
     // ---- d_ocp_qp_init_var (cold start): z = 0, pi = 0, t = max(thr0, -lo), lam = mu0/t (masked rows 0) ------
     int nmask = 0;
+#pragma unroll 4
     for (int k = 0; k <= N; ++k) {
       if (lane < 24) ws(k, v2::oZ)[lane] = 0.0;
       if (k < N) {
@@ -1060,20 +1061,35 @@ struct SrbdSolver {
     else if (alpha <= a.alpha_min) status = 2;
     else if (nan) status = 3;
     else status = 0;
-    // ---- outputs ---------------------------------------------------------------------------------------------
-    for (int k = 0; k <= N; ++k) {
-      const int nu = k < N ? 12 : 0;
-      if (lane < 12) {
-        if (k == 0) p.sol_x[((size_t)q * (N + 1)) * 12 + lane] = p.x0[(size_t)q * 12 + lane];
-        else {
-          p.sol_x[((size_t)q * (N + 1) + k) * 12 + lane] = ws(k, v2::oZ)[nu + lane];
-          p.sol_pi[((size_t)q * (N + 1) + k) * 12 + lane] = ws(k - 1, v2::oPI)[lane];
+    // ---- outputs (four stages per trip: the loads of a trip are issued before its stores) ----------------------------
+    {
+      const int l12 = lane < 12 ? lane : 0, lc = lane < 24 ? lane : 0;
+      for (int k0 = 0; k0 <= N; k0 += 4) {
+        double vx[4], vp[4], vu[4], vl[4], vt[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = k0 + j <= N ? k0 + j : N, nu = k < N ? 12 : 0, kk_ = k < N ? k : N - 1;
+          vx[j] = k == 0 ? __ldg(p.x0 + (size_t)q * 12 + l12) : __ldcg(ws(k, v2::oZ) + nu + l12);
+          vp[j] = __ldcg(ws(k > 0 ? k - 1 : 0, v2::oPI) + l12);
+          vu[j] = __ldcg(ws(kk_, v2::oZ) + l12);
+          vl[j] = __ldcg(ws(kk_, v2::oLAM) + lc);
+          vt[j] = __ldcg(ws(kk_, v2::oT) + lc);
         }
-        if (k < N) p.sol_u[((size_t)q * N + k) * 12 + lane] = ws(k, v2::oZ)[lane];
-      }
-      if (k < N && lane < 24) {
-        p.sol_lam[(size_t)q * N * 48 + k * 48 + lane] = ws(k, v2::oLAM)[lane];
-        p.sol_t[(size_t)q * N * 48 + k * 48 + lane] = ws(k, v2::oT)[lane];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = k0 + j;
+          if (k <= N) {
+            if (lane < 12) {
+              p.sol_x[((size_t)q * (N + 1) + k) * 12 + lane] = vx[j];
+              if (k > 0) p.sol_pi[((size_t)q * (N + 1) + k) * 12 + lane] = vp[j];
+              if (k < N) p.sol_u[((size_t)q * N + k) * 12 + lane] = vu[j];
+            }
+            if (k < N && lane < 24) {
+              p.sol_lam[(size_t)q * N * 48 + k * 48 + lane] = vl[j];
+              p.sol_t[(size_t)q * N * 48 + k * 48 + lane] = vt[j];
+            }
+          }
+        }
       }
     }
     if (lane == 0) {
