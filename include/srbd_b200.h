@@ -267,6 +267,14 @@ int srbd_sqp_iterate(srbd_ctx* ctx, int mode, int do_line_search);
 int srbd_solve_host(srbd_ctx* ctx, int mode, const double* x, const double* u, const double* xref,
                     const double* x0, const uint8_t* contact, double* sol_x, double* sol_u,
                     int* iter, int* status);
+/* The same, asynchronously: enqueues the H2D copies, the kernels and the D2H copies on the context's stream and
+ * returns; srbd_wait() blocks until they are done.  Host buffers must be pinned and stay untouched until then.  Two
+ * contexts driven alternately overlap the copies of one batch with the kernels of the other (streaming use: the
+ * reference calls NMPCSolver::solveQpProblems once per control step, NMPC_solver.cpp:316-330). */
+int srbd_solve_host_async(srbd_ctx* ctx, int mode, const double* x, const double* u, const double* xref,
+                          const double* x0, const uint8_t* contact, double* sol_x, double* sol_u,
+                          int* iter, int* status);
+int srbd_wait(srbd_ctx* ctx);
 
 /* ---- measurement helpers ----------------------------------------------------------------------*/
 /* DFMA-saturating microbenchmark: returns achieved FP64 FLOP/s on the context's device. */

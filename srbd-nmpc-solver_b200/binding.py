@@ -217,6 +217,16 @@ class Context:
                                          capi.dptr(x0), capi.u8ptr(contact), capi.dptr(sol_x),
                                          capi.dptr(sol_u), capi.iptr(it), capi.iptr(status)))
 
+    def solve_host_async(self, mode, x, u, xref, x0, contact, sol_x, sol_u, it, status):
+        """End-to-end call on caller-owned (ideally pinned) host buffers; nothing is allocated here."""
+        self._ck(self._L.srbd_solve_host_async(self._h, int(mode), capi.dptr(x), capi.dptr(u), capi.dptr(xref),
+                                         capi.dptr(x0), capi.u8ptr(contact), capi.dptr(sol_x),
+                                         capi.dptr(sol_u), capi.iptr(it), capi.iptr(status)))
+
+
+    def wait(self):
+        self._ck(self._L.srbd_wait(self._h))
+
     def fp64_peak(self):
         v = C.c_double()
         self._ck(self._L.srbd_fp64_peak(self._h, C.byref(v)))

@@ -123,7 +123,7 @@ _EXPORTS = [
     "srbd_upload_traj", "srbd_download_traj", "srbd_linearize", "srbd_assemble",
     "srbd_download_linearization", "srbd_download_qp", "srbd_qp_upload", "srbd_qp_solve",
     "srbd_download_solution", "srbd_download_stats", "srbd_batch_stats_get", "srbd_line_search",
-    "srbd_download_sqp_state", "srbd_reset_sqp_state", "srbd_sqp_iterate", "srbd_solve_host",
+    "srbd_download_sqp_state", "srbd_reset_sqp_state", "srbd_sqp_iterate", "srbd_solve_host", "srbd_solve_host_async", "srbd_wait",
     "srbd_fp64_peak",
 ]
 
@@ -178,6 +178,9 @@ def lib():
     L.srbd_sqp_iterate.argtypes = [vp, C.c_int, C.c_int]
     L.srbd_solve_host.argtypes = [vp, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p, c_u8_p,
                                   c_double_p, c_double_p, c_int_p, c_int_p]
+    L.srbd_solve_host_async.argtypes = [vp, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p, c_u8_p,
+                                  c_double_p, c_double_p, c_int_p, c_int_p]
+    L.srbd_wait.argtypes = [vp]
     L.srbd_fp64_peak.argtypes = [vp, c_double_p]
     for n in _EXPORTS:
         getattr(L, n)  # every symbol include/srbd_b200.h declares must be exported

@@ -719,6 +719,26 @@ int srbd_sqp_iterate(srbd_ctx* ctx, int mode, int do_line_search) {
   return SRBD_OK;
 }
 
+int srbd_solve_host_async(srbd_ctx* ctx, int mode, const double* x, const double* u, const double* xref,
+                          const double* x0, const uint8_t* contact, double* sol_x, double* sol_u, int* iter,
+                          int* status) {
+  if (int rc = srbd_upload_traj(ctx, x, u, xref, x0, contact)) return rc;
+  if (int rc = srbd_sqp_iterate(ctx, mode, 0)) return rc;
+  const size_t B = ctx->B, S = ctx->L.N + 1, N = ctx->L.N, D = sizeof(double);
+  if (sol_x) CU(cudaMemcpyAsync(sol_x, ctx->d_sol_x, B * S * 12 * D, cudaMemcpyDeviceToHost, ctx->stream));
+  if (sol_u) CU(cudaMemcpyAsync(sol_u, ctx->d_sol_u, B * N * 12 * D, cudaMemcpyDeviceToHost, ctx->stream));
+  if (iter) CU(cudaMemcpyAsync(iter, ctx->d_iter, B * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  if (status) CU(cudaMemcpyAsync(status, ctx->d_status, B * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  return SRBD_OK;
+}
+
+int srbd_wait(srbd_ctx* ctx) {
+  if (!ctx) return SRBD_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SRBD_OK;
+}
+
 int srbd_solve_host(srbd_ctx* ctx, int mode, const double* x, const double* u, const double* xref, const double* x0,
                     const uint8_t* contact, double* sol_x, double* sol_u, int* iter, int* status) {
   if (int rc = srbd_upload_traj(ctx, x, u, xref, x0, contact)) return rc;

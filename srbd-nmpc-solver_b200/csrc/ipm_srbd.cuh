@@ -8,7 +8,7 @@
 //                                       lower-triangle products W_g of each row's 6-vector precomputed per CTA;
 //   * only the lower side of the rows is active (ug masked), no box constraints, cold start.
 // Mapping: 4 independent warps per CTA, one QP per warp, persistent grid + atomic work counter.
-// S1, the Riccati factorization sweep, runs on the FP64 tensor cores (mma.sync m8n8k4 f64, "DMMA"): one
+// The solve runs on the FP64 tensor cores (mma.sync m8n8k4 f64, "DMMA"): one
 // instruction is 256 FMAs, i.e. 8 warp-wide DFMAs plus their shared-memory operand fetches in ONE issue slot
 // (scripts/microbench/fp64_pipes.cu: DMMA and DFMA share the FP64 pipe on B200, 36.9 vs 35.8 TFLOP/s, so the
 // gain is issue slots, not peak).  The stage matrix lives in the registers as 8x4 FRAGMENTS
@@ -17,17 +17,21 @@
 // when the B operand's rows are permuted by pi(r) = (r>>1) + 4(r&1), the two halves of the accumulator tile:
 //     D(8x8) = A(8x4) . B(4x8)^T-rows-permuted  ->  c0 = F[I][2J], c1 = F[I][2J+1].
 // So AL = G P, M = H + AL G^T and the trailing updates of the blocked (4-column BLASFEO-style panels) Cholesky
-// chain without any register shuffles: 18 + 18 + 15 DMMA per stage.  The 4-column panels themselves are solved
+// chain without any register shuffles: 18 + 18 + 12 DMMA per stage.  The 4-column panels themselves are solved
 // row-per-lane through a [37][4] shared-memory panel (every lane factors the 4x4 diagonal block redundantly, then
-// substitutes its own row); 12 appended identity rows turn the same substitution into L^-T (what the vector sweeps
-// need), and the gradient ("+1 row" of potrf_l_mn) rides along as row 24.
-// The vector sweeps (S2/S5 forward rollout fused with dlam/dt and the step length, S4 vector-only backward with
-// the centering correction on the fly, S6 variable update fused with the residuals) are FP64 FMA loops with
-// row-per-lane registers and broadcast operands from shared memory.
+// substitutes its own row); four appended identity rows per panel turn the same substitution into L_pp^-T, the
+// diagonal blocks of the blocked triangular solves of the vector sweeps (substitution, not an explicit 12x12
+// inverse: the residual of the Newton step decides convergence at tol 1e-8).
+// The gradient recursion (the "+1 row" of potrf_l_mn) and the vector sweeps (S2/S5 forward rollout fused with
+// dlam/dt, the step length and the mu_aff sums; S4 vector-only backward with the centering correction on the fly;
+// S6 variable update fused with the residuals) run in VECTOR-FRAGMENT form: a 12-vector is three registers valid
+// in lanes 0..3 = row 0 of an A operand, y = A x is 2 x 3 DMMA with A as pi-permuted B fragments, and the
+// accumulator pair of output tile I is k-tiles 2I, 2I+1 of y: chained products stay in registers; only the 24
+// constraint rows are handled row-per-lane (one shared-memory round trip per stage).
 // Memory: every sweep is SOFTWARE PIPELINED: while stage k is computed, the tiles of the next stage (BAbt record,
 // P / factor panels, the R block of RSQrq) stream into the other half of a shared-memory double buffer with
-// cp.async, and the next stage's per-row vectors are prefetched into registers, so HBM/L2 latency overlaps the
-// FP64 work.
+// cp.async, and the next stage's per-row vectors are prefetched into registers (raw loads only: arithmetic on a
+// prefetched value would wait for it at the prefetch point), so HBM/L2 latency overlaps the FP64 work.
 #pragma once
 #include <cuda_runtime.h>
 
