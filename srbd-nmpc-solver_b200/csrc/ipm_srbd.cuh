@@ -361,24 +361,20 @@ struct SrbdSolver {
         for (int kt = 0; kt < 3; ++kt) {
           dmma(c0[0], c0[1], tk[kt], GPF[0][kt], c0[0], c0[1]);
           dmma(c1[0], c1[1], tk[kt], GPF[1][kt], c1[0], c1[1]);
-          if (xr) dmma(c2[0], c2[1], tk[kt], GPF[2][kt], c2[0], c2[1]);
+          dmma(c2[0], c2[1], tk[kt], GPF[2][kt], c2[0], c2[1]);
         }
       }
       // ---- AL = G P_{k+1}: fragments ALF[I][0..2] (columns 0..3, 4..7, 8..11) -------------------------------------
       double ALF[3][3];
 #pragma unroll
       for (int I = 0; I < 3; ++I) {
-        if (I < 2 || xr) {
-          double a0 = 0.0, a1 = 0.0, e0 = 0.0, e1 = 0.0;
+        double a0 = 0.0, a1 = 0.0, e0 = 0.0, e1 = 0.0;
 #pragma unroll
-          for (int kt = 0; kt < 3; ++kt) {
-            dmma(a0, a1, GF[I][kt], PPF[0][kt], a0, a1);
-            dmma(e0, e1, GF[I][kt], PPF[1][kt], e0, e1);
-          }
-          ALF[I][0] = a0; ALF[I][1] = a1; ALF[I][2] = e0;
-        } else {
-          ALF[I][0] = 0.0; ALF[I][1] = 0.0; ALF[I][2] = 0.0;
+        for (int kt = 0; kt < 3; ++kt) {
+          dmma(a0, a1, GF[I][kt], PPF[0][kt], a0, a1);
+          dmma(e0, e1, GF[I][kt], PPF[1][kt], e0, e1);
         }
+        ALF[I][0] = a0; ALF[I][1] = a1; ALF[I][2] = e0;
       }
       // ---- M = (H + D^T Gamma D) + AL G^T + reg I: lower 8x8 tiles, MF[I][2J], MF[I][2J+1] ------------------------
       double MF[3][6];
@@ -387,10 +383,8 @@ struct SrbdSolver {
 #pragma unroll
         for (int J = 0; J <= I; ++J) {
           double a0 = 0.0, a1 = 0.0;
-          if (I < 2 || xr) {
 #pragma unroll
-            for (int kt = 0; kt < 3; ++kt) dmma(a0, a1, ALF[I][kt], GPF[J][kt], a0, a1);
-          }
+          for (int kt = 0; kt < 3; ++kt) dmma(a0, a1, ALF[I][kt], GPF[J][kt], a0, a1);
           MF[I][2 * J] = a0; MF[I][2 * J + 1] = a1;
         }
       __syncwarp();  // wS visible
@@ -459,31 +453,29 @@ struct SrbdSolver {
         // row 0, B = permuted fragment of the panel)
         const double nlv = -pan[96 + t];
         double dum;
+        // (no branch on the stage type: at stage 0 the rows 12..23 are zero and the extra DMMAs produce zeros; the
+        // updates that feed the NEXT panel come first, the rest trails behind the next panel's substitution)
         if (pp == 0) {
           const double nA0 = -pan[prA0], nA1 = -pan[prA1], nA2 = -pan[prA2];
           const double B0 = pan[prB0], B1 = pan[prB1], B2 = pan[prB2];
           dmma(dum, MF[0][1], nA0, B0, MF[0][0], MF[0][1]);
           dmma(dum, MF[1][1], nA1, B0, MF[1][0], MF[1][1]);
-          dmma(MF[1][2], MF[1][3], nA1, B1, MF[1][2], MF[1][3]);
+          dmma(dum, MF[2][1], nA2, B0, MF[2][0], MF[2][1]);
           dmma(dum, c0[1], nlv, B0, c0[0], c0[1]);
+          dmma(MF[1][2], MF[1][3], nA1, B1, MF[1][2], MF[1][3]);
+          dmma(MF[2][2], MF[2][3], nA2, B1, MF[2][2], MF[2][3]);
           dmma(c1[0], c1[1], nlv, B1, c1[0], c1[1]);
-          if (xr) {
-            dmma(dum, MF[2][1], nA2, B0, MF[2][0], MF[2][1]);
-            dmma(MF[2][2], MF[2][3], nA2, B1, MF[2][2], MF[2][3]);
-            dmma(MF[2][4], MF[2][5], nA2, B2, MF[2][4], MF[2][5]);
-            dmma(c2[0], c2[1], nlv, B2, c2[0], c2[1]);
-          }
+          dmma(MF[2][4], MF[2][5], nA2, B2, MF[2][4], MF[2][5]);
+          dmma(c2[0], c2[1], nlv, B2, c2[0], c2[1]);
         } else if (pp == 1) {
           const double nA1 = -pan[prA1], nA2 = -pan[prA2];
           const double B1 = pan[prB1], B2 = pan[prB2];
           dmma(MF[1][2], MF[1][3], nA1, B1, MF[1][2], MF[1][3]);
+          dmma(MF[2][2], MF[2][3], nA2, B1, MF[2][2], MF[2][3]);
           dmma(c1[0], c1[1], nlv, B1, c1[0], c1[1]);
-          if (xr) {
-            dmma(MF[2][2], MF[2][3], nA2, B1, MF[2][2], MF[2][3]);
-            dmma(MF[2][4], MF[2][5], nA2, B2, MF[2][4], MF[2][5]);
-            dmma(c2[0], c2[1], nlv, B2, c2[0], c2[1]);
-          }
-        } else if (xr) {
+          dmma(MF[2][4], MF[2][5], nA2, B2, MF[2][4], MF[2][5]);
+          dmma(c2[0], c2[1], nlv, B2, c2[0], c2[1]);
+        } else {
           const double nA1 = -pan[prA1], nA2 = -pan[prA2];
           const double B1 = pan[prB1], B2 = pan[prB2];
           dmma(dum, MF[1][3], nA1, B1, MF[1][2], MF[1][3]);
@@ -607,7 +599,7 @@ struct SrbdSolver {
       for (int kt = 0; kt < 3; ++kt) {
         dmma(c0[0], c0[1], tk[kt], sG[oG + 16 * kt], c0[0], c0[1]);
         dmma(c1[0], c1[1], tk[kt], sG[oG + 2 * v2::kGP + 16 * kt], c1[0], c1[1]);
-        if (k > 0) dmma(c2[0], c2[1], tk[kt], sG[oG + 4 * v2::kGP + 16 * kt], c2[0], c2[1]);
+        dmma(c2[0], c2[1], tk[kt], sG[oG + 4 * v2::kGP + 16 * kt], c2[0], c2[1]);
       }
       // ---- lv = L^-1 g~_u: blocked forward substitution (4x4 diagonal blocks by their inverses L_pp^-1, which the
       // factorization left in the E rows; same operation order as trsv up to the blocks) ----------------------------------
@@ -698,7 +690,7 @@ struct SrbdSolver {
       // ---- x+ = G^T [u; x] + rb: the x part first (it does not wait for u);  t = Ls^T x + lv ----------------------------
       double cx0[2] = {cur.rb[0], cur.rb[1]}, cx1[2] = {cur.rb[2], 0.0};
       double t0[2] = {sF[oLV], sF[oLV + v2::kPanF]}, t1[2] = {sF[oLV + 2 * v2::kPanF], 0.0};
-      if (k > 0) {
+      {  // (stage 0: x = 0 and the rows 12.. of its records are finite, so no branch on the stage type)
 #pragma unroll
         for (int kt = 0; kt < 3; ++kt) {
           dmma(t0[0], t0[1], xk[kt], sF[oLT + 16 * kt], t0[0], t0[1]);
@@ -915,7 +907,7 @@ struct SrbdSolver {
         for (int kt = 0; kt < 3; ++kt) {  // + G pi
           dmma(c0[0], c0[1], pk_[kt], sG[gB + 16 * kt], c0[0], c0[1]);
           dmma(c1[0], c1[1], pk_[kt], sG[gB + 2 * v2::kGP + 16 * kt], c1[0], c1[1]);
-          if (k > 0) dmma(c2[0], c2[1], pk_[kt], sG[gB + 4 * v2::kGP + 16 * kt], c2[0], c2[1]);
+          dmma(c2[0], c2[1], pk_[kt], sG[gB + 4 * v2::kGP + 16 * kt], c2[0], c2[1]);
         }
         if (k > 0) { c1[1] -= pp[0]; c2[0] -= pp[1]; c2[1] -= pp[2]; }
 #pragma unroll
@@ -928,10 +920,8 @@ struct SrbdSolver {
         double b0[2] = {sG[pbr], sG[pbr + 16]}, b1[2] = {sG[pbr + 32], 0.0};
 #pragma unroll
         for (int kt = 0; kt < 6; ++kt) {
-          if (kt < 3 || k > 0) {
-            dmma(b0[0], b0[1], zk[kt], sG[oGT + v2::kGP * kt], b0[0], b0[1]);
-            dmma(b1[0], b1[1], zk[kt], sG[oGT + 32 + v2::kGP * kt], b1[0], b1[1]);
-          }
+          dmma(b0[0], b0[1], zk[kt], sG[oGT + v2::kGP * kt], b0[0], b0[1]);  // stage 0: z[12..23] = 0
+          dmma(b1[0], b1[1], zk[kt], sG[oGT + 32 + v2::kGP * kt], b1[0], b1[1]);
         }
         b0[0] -= pb[12 + t]; b0[1] -= pb[16 + t]; b1[0] -= pb[20 + t];
         if (r == 0) {
