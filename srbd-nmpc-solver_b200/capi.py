@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsrbd_b200.so")
+# SRBD_LIB: A/B experiments with another build of the same library (development knob)
+LIB_PATH = os.environ.get("SRBD_LIB") or os.path.join(HERE, "libsrbd_b200.so")
 
 SRBD_NX, SRBD_NU, SRBD_NG, SRBD_STAT_M, SRBD_HIST_BINS = 12, 12, 24, 18, 64
 SRBD_BARRIER_SOFT, SRBD_HARD_INEQ = 0, 1

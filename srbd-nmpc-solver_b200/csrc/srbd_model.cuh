@@ -216,55 +216,63 @@ constexpr int kLinCompact = 40;  // 18 (drdot/d[r,l]) + 3 (F sum) + 6 (d0,d1) + 
 constexpr int kLinThreads = 128;
 constexpr int kRaw0Stride = 144 + 144 + 12 + 144 + 144 + 12;  // A0,B0,b0,S0,Q0,q0
 
-// element (i,j) of BAbt = [B^T; A^T; b^T] of an interior stage from the compact record
-__device__ __forceinline__ double babt_elem(const double* c, int i, int j, double dt, double minv, bool stage0) {
-  // c[0..18): jfx rows 0-2 x cols 0-5 (row-major 3x6); c[18..21): Fsum; c[21..24): d0; c[24..27): d1; c[27..39): b
+// Element (i,j) of the dense record BAbt = [B^T; A^T; b^T] as ONE term of the compact record c:
+//     element = fma(mul, c[src], add)
+// c[0..18): jfx rows 0-2 x cols 0-5 (row-major 3x6); c[18..21): F sum; c[21..24): d0; c[24..27): d1; c[27..39): b;
+// c[39] = 0 (the source of the constant elements, mul = 0).  336 elements, 48 of them depend on the stage.
+struct BabtTerm { int src; double mul, add; };
+__host__ __device__ __forceinline__ BabtTerm babt_term(int i, int j, double dt, double minv, bool stage0) {
+  BabtTerm t{39, 0.0, 0.0};
   if (i < 12) {  // B^T[i][j] = dt * jfu[j][i]
     const int row = j, col = i;  // jfu(row, col)
-    double v = 0.0;
     if (row >= 3 && row < 6) {
       const int a = row - 3;
       if (col < 3 || (col >= 6 && col < 9)) {  // skew(d) block: skew(d)(a, b)
-        const double* d = col < 3 ? c + 21 : c + 24;
         const int b = col < 3 ? col : col - 6;
         if (a != b) {
           const int k3 = 3 - a - b;  // the remaining index
-          const double sgn = ((b - a + 3) % 3 == 1) ? -1.0 : 1.0;  // skew(a,a+1) = -v[k]
-          v = sgn * d[k3];
+          t.src = (col < 3 ? 21 : 24) + k3;
+          t.mul = ((b - a + 3) % 3 == 1) ? -dt : dt;  // skew(a,a+1) = -v[k]
         }
       } else {  // identity blocks at cols 3-5 and 9-11
         const int b = col < 6 ? col - 3 : col - 9;
-        v = (a == b) ? 1.0 : 0.0;
+        t.add = (a == b) ? dt : 0.0;
       }
     } else if (row >= 9) {
       const int a = row - 9;
-      if (col < 3) v = (a == col) ? minv : 0.0;
-      else if (col >= 6 && col < 9) v = (a == col - 6) ? minv : 0.0;
+      if (col < 3) t.add = (a == col) ? dt * minv : 0.0;
+      else if (col >= 6 && col < 9) t.add = (a == col - 6) ? dt * minv : 0.0;
     }
-    return 0.0 + dt * v;
+    return t;
   }
-  if (stage0) return i == 12 ? c[27 + j] : 0.0;  // nx[0] := 0: stage 0 is [B^T (12 rows); b^T] only
+  if (stage0) {  // nx[0] := 0: stage 0 is [B^T (12 rows); b^T] only
+    if (i == 12) { t.src = 27 + j; t.mul = 1.0; t.add = -0.0; }
+    return t;
+  }
   if (i < 24) {  // A^T[c][j] = A[j][c] = delta + dt * jfx[j][c]
     const int row = j, col = i - 12;
-    double v = 0.0;
+    t.add = row == col ? 1.0 : 0.0;
     if (row < 3) {
-      if (col < 6) v = c[row * 6 + col];
+      if (col < 6) { t.src = row * 6 + col; t.mul = dt; }
     } else if (row < 6) {
       if (col >= 6 && col < 9) {
         const int a = row - 3, b = col - 6;
         if (a != b) {
-          const int k3 = 3 - a - b;
-          const double sgn = ((b - a + 3) % 3 == 1) ? -1.0 : 1.0;
-          v = sgn * c[18 + k3];
+          t.src = 18 + (3 - a - b);
+          t.mul = ((b - a + 3) % 3 == 1) ? -dt : dt;
         }
       }
     } else if (row < 9) {
-      if (col >= 9) v = (row - 6 == col - 9) ? 1.0 : 0.0;
+      if (col >= 9 && row - 6 == col - 9) t.add = dt;
     }
-    return (row == col ? 1.0 : 0.0) + dt * v;
+    return t;
   }
-  if (i == 24) return c[27 + j];
-  return 0.0;
+  if (i == 24) { t.src = 27 + j; t.mul = 1.0; t.add = -0.0; }  // (c + -0.0 = c for every c, -0.0 included)
+  return t;
+}
+__host__ __device__ __forceinline__ double babt_elem(const double* c, int i, int j, double dt, double minv, bool stage0) {
+  const BabtTerm t = babt_term(i, j, dt, minv, stage0);
+  return fma(t.mul, c[t.src], t.add);
 }
 
 __global__ void __launch_bounds__(kLinThreads) linearize_kernel(const LinParams p, const ModelDev* __restrict__ md) {
@@ -368,22 +376,41 @@ __global__ void __launch_bounds__(kLinThreads) linearize_kernel(const LinParams 
 #pragma unroll
       for (int i = 0; i < 12; ++i) c[27 + i] = -f[i];
     }
+    c[39] = 0.0;
   }
   __syncthreads();
-  // expand: each warp writes its 32 records, coalesced over the contiguous dense records
+  // expand: each warp writes its 32 records, coalesced over the contiguous dense records.  The per-lane terms of an
+  // interior record (11 elements per lane) are resolved once, so an element costs one shared-memory load, one FMA
+  // and one store; stage-0 records (1 in N) take the generic path.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const double dt = sm.dt, minv = 1.0 / sm.mass;
-  constexpr int kRec = 28 * 12;
-  for (int r = 0; r < 32; ++r) {
-    const long long it = item0 + warp * 32 + r;
+  constexpr int kRec = 28 * 12, kSlots = (kRec + 31) / 32;
+  int tsrc[kSlots];
+  double tmul[kSlots], tadd[kSlots];
+#pragma unroll
+  for (int sl = 0; sl < kSlots; ++sl) {
+    const int e = lane + 32 * sl, pnl = e / 48, rem = e - pnl * 48;
+    const BabtTerm t = babt_term(4 * pnl + (rem & 3), rem >> 2, dt, minv, false);
+    tsrc[sl] = t.src; tmul[sl] = t.mul; tadd[sl] = t.add;
+  }
+  const long long it0 = item0 + warp * 32;
+  int k = (int)(it0 % p.N);
+  for (int r = 0; r < 32; ++r, k = (k + 1 == p.N ? 0 : k + 1)) {
+    const long long it = it0 + r;
     if (it >= total) break;
-    const bool stage0 = (it % p.N) == 0;
     const double* c = sc[warp * 32 + r];
     double* dst = p.babt + (size_t)it * kRec;
-    for (int e = lane; e < kRec; e += 32) {
-      const int pnl = e / 48, rem = e - pnl * 48;
-      const int j = rem >> 2, i = 4 * pnl + (rem & 3);
-      dst[e] = babt_elem(c, i, j, dt, minv, stage0);
+    if (k != 0) {
+#pragma unroll
+      for (int sl = 0; sl < kSlots; ++sl) {
+        const int e = lane + 32 * sl;
+        if (e < kRec) dst[e] = fma(tmul[sl], c[tsrc[sl]], tadd[sl]);
+      }
+    } else {
+      for (int e = lane; e < kRec; e += 32) {
+        const int pnl = e / 48, rem = e - pnl * 48;
+        dst[e] = babt_elem(c, 4 * pnl + (rem & 3), rem >> 2, dt, minv, true);
+      }
     }
   }
 }
@@ -420,6 +447,42 @@ __device__ __forceinline__ void barrier_fn(double v, double mu, double theta, do
 __device__ __forceinline__ bool row_soft_in_hard_mode(int g) {
   const int r = g % 12;
   return r == 10 || r == 11;  // the +-x^T tau pair has no strict interior (NMPC_solver.cpp:301 keeps 20 rows)
+}
+
+// R-block element (i, j) of RSQrq: R delta_ij + sum_g Ac[g][i] ddb_g Ac[g][j] (NMPC_solver.cpp:308), summed in the
+// order g = 0..23.  Ac is two 12x6 blocks (fill_Ac / SRBD_model.cpp:244), so only the 12 rows of the common leg can
+// contribute, and in HARD_INEQ mode only its two relaxed rows have ddb != 0 (g_lo = 10, g_cnt = 2): the skipped terms
+// are exact zeros, so the sum is bit-identical to the full one.
+__device__ __forceinline__ double rblock_elem(const double* sAc, const double* c, int i, int j, double R, int g_lo,
+                                              int g_cnt) {
+  double s = 0.0;
+  if (i / 6 == j / 6) {
+    const int g0 = 12 * (i / 6) + g_lo;
+    for (int g = g0; g < g0 + g_cnt; ++g) s += (sAc[g * 12 + i] * c[g]) * sAc[g * 12 + j];
+  }
+  return (i == j ? R : 0.0) + s;
+}
+// One RSQrq record (28 x 24 panel-major: 7 panels of 96 doubles, 3 per lane and panel).  TYPE 0: first stage
+// (nu = 12, nx = 0), 1: interior, 2: last stage (nu = 0, nx = 12): with the panel and the stage type known at compile
+// time most elements fold to a stored zero.
+template <int TYPE>
+__device__ __forceinline__ void write_rsq(double* dst, const double* c, const double* sAc, const double* sQ,
+                                          const double* sQf, double R, int lane, int g_lo, int g_cnt) {
+  constexpr int nu = TYPE == 2 ? 0 : 12, nx = TYPE == 0 ? 0 : 12, n = nu + nx;
+#pragma unroll
+  for (int pnl = 0; pnl < 7; ++pnl)
+#pragma unroll
+    for (int sl = 0; sl < 3; ++sl) {
+      const int e = lane + 32 * sl, j = e >> 2, i = 4 * pnl + (e & 3);
+      double v = 0.0;
+      if (i < n && j < n) {
+        if (i < nu && j < nu) v = rblock_elem(sAc, c, i, j, R, g_lo, g_cnt);
+        else if (i >= nu && j >= nu && i == j) v = TYPE == 2 ? sQf[i - nu] : sQ[i - nu];
+      } else if (i == n && j < n) {
+        v = j < nu ? c[24 + j] : c[36 + (j - nu)];
+      }
+      dst[96 * pnl + e] = v;
+    }
 }
 
 __global__ void __launch_bounds__(kAsmThreads) assemble_kernel(const AsmParams p, const ModelDev* __restrict__ md) {
@@ -492,41 +555,31 @@ __global__ void __launch_bounds__(kAsmThreads) assemble_kernel(const AsmParams p
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int rI = 0; rI < 32; ++rI) {
-    const long long it = item0 + warp * 32 + rI;
+  const int g_lo = p.mode == SRBD_HARD_INEQ ? 10 : 0, g_cnt = p.mode == SRBD_HARD_INEQ ? 2 : 12;
+  const long long it0 = item0 + warp * 32;
+  int k = (int)(it0 % S);
+  for (int rI = 0; rI < 32; ++rI, k = (k == p.N ? 0 : k + 1)) {
+    const long long it = it0 + rI;
     if (it >= total) break;
-    const int k = (int)(it % S);
     const double* c = sc[warp * 32 + rI];
-    const int nu = k < p.N ? 12 : 0, nx = k > 0 ? 12 : 0, n = nu + nx;
+    const int nu = k < p.N ? 12 : 0;
     // RSQrq: 28 x 24 panel-major
     double* dst = p.rsq + (size_t)it * (28 * 24);
-    for (int e = lane; e < 28 * 24; e += 32) {
-      const int pnl = e / 96, rem = e - pnl * 96;
-      const int j = rem >> 2, i = 4 * pnl + (rem & 3);
-      double v = 0.0;
-      if (i < n && j < n) {
-        if (i < nu && j < nu) {  // R + Ac^T diag(ddb) Ac  (:308)
-          double s = 0.0;
-          for (int g = 0; g < 24; ++g) s += (sAc[g * 12 + i] * c[g]) * sAc[g * 12 + j];
-          v = (i == j ? sR : 0.0) + s;
-        } else if (i >= nu && j >= nu) {
-          if (i == j) v = (k < p.N) ? sQ[i - nu] : sQf[i - nu];
-        }
-      } else if (i == n && j < n) {
-        v = j < nu ? c[24 + j] : c[36 + (j - nu)];
-      }
-      dst[e] = v;
-    }
+    if (k == 0) write_rsq<0>(dst, c, sAc, sQ, sQf, sR, lane, g_lo, g_cnt);
+    else if (k < p.N) write_rsq<1>(dst, c, sAc, sQ, sQf, sR, lane, g_lo, g_cnt);
+    else write_rsq<2>(dst, c, sAc, sQ, sQf, sR, lane, g_lo, g_cnt);
     // DCt (n x 24): D^T = Ac^T in the u rows, C = 0; d = [lg | 0 | 0(-ug) | 0], masks
     double* dd = p.dct + (size_t)it * (24 * 24);
     double* dv = p.d + (size_t)it * 48;
     double* dk = p.dmask + (size_t)it * 48;
     if (k < p.N) {
-      for (int e = lane; e < 24 * 24; e += 32) {
-        const int pnl = e / 96, rem = e - pnl * 96;
-        const int g = rem >> 2, i = 4 * pnl + (rem & 3);
-        dd[e] = (i < nu) ? sAc[g * 12 + i] : 0.0;
-      }
+#pragma unroll
+      for (int pnl = 0; pnl < 6; ++pnl)
+#pragma unroll
+        for (int sl = 0; sl < 3; ++sl) {
+          const int e = lane + 32 * sl, g = e >> 2, i = 4 * pnl + (e & 3);
+          dd[96 * pnl + e] = (i < nu) ? sAc[g * 12 + i] : 0.0;
+        }
       for (int e = lane; e < 48; e += 32) {
         const bool lower = e < 24;
         const int g = lower ? e : e - 24;
