@@ -546,7 +546,7 @@ static int solve_srbd_variant(srbd_ctx* ctx) {
   if (!ctx->d_ws2) {
     CU(cudaFuncSetAttribute(ipm_srbd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes));
     int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ipm_srbd_kernel, 128, v2::kSmemBytes));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ipm_srbd_kernel, 32 * v2::kWarps, v2::kSmemBytes));
     if (occ < 1) return fail(ctx, SRBD_ERR_CUDA, "ipm_srbd_kernel does not fit on this device");
     if (const char* cap = std::getenv("SRBD_K3_CTAS_PER_SM")) {  // tuning knob: fewer resident QPs = higher L2 hit rate
       const int c = std::atoi(cap);
@@ -570,7 +570,7 @@ static int solve_srbd_variant(srbd_ctx* ctx) {
   p.iter = ctx->d_iter; p.status = ctx->d_status; p.res_max = ctx->d_resmax; p.bstats = ctx->d_bstats;
   CU(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
   CU(cudaMemsetAsync(ctx->d_bstats, 0, sizeof(srbd_batch_stats), ctx->stream));
-  ipm_srbd_kernel<<<ctx->grid2, 128, v2::kSmemBytes, ctx->stream>>>(p);
+  ipm_srbd_kernel<<<ctx->grid2, 32 * v2::kWarps, v2::kSmemBytes, ctx->stream>>>(p);
   ctx->launches++;
   CU(cudaGetLastError());
   ctx->solved = true;

@@ -60,7 +60,14 @@ struct SrbdIpmParams {
 };
 
 namespace v2 {
-constexpr int kWarps = 4;
+#ifndef SRBD_K3_WARPS
+#define SRBD_K3_WARPS 6       // warps (= QPs in flight) per CTA
+#endif
+#ifndef SRBD_K3_MIN_CTAS
+#define SRBD_K3_MIN_CTAS 2    // resident CTAs per SM the register allocation is bounded for
+#endif
+constexpr int kWarps = SRBD_K3_WARPS;
+constexpr int kMinCtas = SRBD_K3_MIN_CTAS;
 // per-stage workspace block (doubles)
 constexpr int oZ = 0, oDZ = 24, oRG = 48, oLAM = 72, oT = 96, oDLAM = 120, oDT = 144, oRD = 168, oRM = 192, oRMB = 216,
               oPI = 240, oDPI = 252, oRB = 264, oPV = 276, oLV = 288, oP = 300, oFT = 444, oPRB = 750, kStage = 762;
@@ -74,7 +81,7 @@ constexpr int kW2 = 22;            // row stride of W (21 lower-triangle product
 constexpr int sAC = 0;             // [24][12] constraint Jacobian, row-major
 constexpr int sW = sAC + 288;      // [24][22]
 constexpr int sQ = sW + 24 * kW2;  // diag(Q) (12), R (1), pad
-constexpr int kCtaShared = sQ + 16;    // 832 doubles = 52 x 128 B
+constexpr int kCtaShared = sQ + 32;    // 848 doubles = 53 x 128 B (sQ + 16 .. : one work-counter int per warp)
 // every tile starts on a 128-byte line (16 doubles): a 512-byte cp.async instruction then writes 4 wavefronts, not 5
 constexpr int kGT = 384;           // one BAbt tile: 7 x 54 = 378 -> 384
 constexpr int kFT = 464;           // [P 144 | factor panels 3 x 102 = 306] = 450 -> 464
@@ -1095,10 +1102,16 @@ struct SrbdSolver {
   }
 };
 
-__global__ void __launch_bounds__(128, 3) ipm_srbd_kernel(const SrbdIpmParams p) {
+#ifdef SRBD_K3_MAXREG
+#define SRBD_K3_BOUNDS __maxnreg__(SRBD_K3_MAXREG)
+#else
+#define SRBD_K3_BOUNDS __launch_bounds__(32 * v2::kWarps, v2::kMinCtas)
+#endif
+__global__ void SRBD_K3_BOUNDS ipm_srbd_kernel(const SrbdIpmParams p) {
   extern __shared__ __align__(128) double2 smem2[];  // no static shared memory: the tiles start on 128-byte lines
   double* smem = reinterpret_cast<double*>(smem2);
-  int* s_next = reinterpret_cast<int*>(smem + v2::sQ + 14);  // 4 ints in the pad behind diag(Q), R
+  int* s_next = reinterpret_cast<int*>(smem + v2::sQ + 16);  // one int per warp behind diag(Q), R
+  static_assert(v2::kWarps <= 32, "work-counter slots");
   // CTA-shared constants: Ac and, per constraint row g, the 21 lower-triangle products of its 6-vector
   for (int i = threadIdx.x; i < 288; i += blockDim.x) smem[v2::sAC + i] = p.model->Ac[i];
   if (threadIdx.x < 12) smem[v2::sQ + threadIdx.x] = p.model->m.Q[threadIdx.x];
