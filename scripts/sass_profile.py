@@ -92,7 +92,7 @@ def main():
     for (key, inner), c in by_line.items():
         outer[key].update(c)
     print("%6s %10s %7s %7s %6s  ops / stalls" % ("line", "instr/unit", "instr%", "samp%", "lanes"))
-    for key, c in sorted(outer.items(), key=lambda kv: -kv[1]["samples"])[:70]:
+    for key, c in sorted(outer.items(), key=lambda kv: -kv[1]["samples"])[:int(os.environ.get("SASS_TOP", "70"))]:
         ops = sorted(((k[3:], v) for k, v in c.items() if k.startswith("op_")), key=lambda kv: -kv[1])[:4]
         st = sorted(((k[6:], v) for k, v in c.items() if k.startswith("stall_")), key=lambda kv: -kv[1])[:3]
         print("%6d %10.0f %6.2f%% %6.2f%% %6.1f  %s | %s" % (

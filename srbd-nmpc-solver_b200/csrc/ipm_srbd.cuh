@@ -66,6 +66,26 @@ namespace v2 {
 #ifndef SRBD_K3_MIN_CTAS
 #define SRBD_K3_MIN_CTAS 2    // resident CTAs per SM the register allocation is bounded for
 #endif
+// stage loops unrolled by two: the loop-carried copies of the register-prefetched vectors (cur = nxt, 22-32 moves
+// per stage) and the buffer selects disappear
+#ifndef SRBD_K3_UNROLL_FAC
+#define SRBD_K3_UNROLL_FAC 0
+#endif
+#ifndef SRBD_K3_UNROLL_BWD
+#define SRBD_K3_UNROLL_BWD 0
+#endif
+#ifndef SRBD_K3_UNROLL_FWD
+#define SRBD_K3_UNROLL_FWD 0
+#endif
+#ifndef SRBD_K3_UNROLL_RES
+#define SRBD_K3_UNROLL_RES 0
+#endif
+#ifndef SRBD_K3_QBASE
+#define SRBD_K3_QBASE 1
+#endif
+#ifndef SRBD_K3_WBASE
+#define SRBD_K3_WBASE 0
+#endif
 constexpr int kWarps = SRBD_K3_WARPS;
 constexpr int kMinCtas = SRBD_K3_MIN_CTAS;
 // per-stage workspace block (doubles)
@@ -140,6 +160,9 @@ struct SrbdSolver {
   const double* sR;   // current R tile
   // fragment coordinates of this lane (see the header comment)
   int fr, ft, fpi;
+#if SRBD_K3_QBASE
+  int rbS, rbD;       // prefetch_Rblk: this lane's source / destination offset of the first copy
+#endif
   int offS[5];        // index into the 42 D^T Gamma D sums of this lane's element of the u-block fragments, or -1
 
   __device__ SrbdSolver(const SrbdIpmParams& p_, double* cta, double* warp_sm, int warp_global)
@@ -151,6 +174,20 @@ struct SrbdSolver {
     sm = warp_sm;
     sG = sm; sF = sm + v2::wF0; sR = sm + v2::wR0;
     fr = lane >> 2; ft = lane & 3; fpi = (fr >> 1) + 4 * (fr & 1);
+#if SRBD_K3_WBASE
+    Wc = W + (lane < 24 ? lane : 0);
+    Wf = W + ft;
+    asm volatile("" : "+l"(Wc), "+l"(Wf));
+#endif
+#if SRBD_K3_QBASE
+    {
+      const int pnl = lane < 8 ? 0 : (lane < 24 ? 1 : 2);
+      const int o = lane - (pnl == 0 ? 0 : (pnl == 1 ? 8 : 24));
+      rbS = pnl * 96 + 2 * o;
+      rbD = (pnl == 0 ? 0 : (pnl == 1 ? 16 : 48)) + 2 * o;
+      asm volatile("" : "+r"(rbS), "+r"(rbD));
+    }
+#endif
     // u-block fragments in the order (I,p) = (0,0) (0,1) (1,0) (1,1) (1,2)
 #pragma unroll
     for (int f = 0; f < 5; ++f) {
@@ -165,16 +202,48 @@ struct SrbdSolver {
     }
   }
   __device__ __forceinline__ double* ws(int k, int off) const { return W + (size_t)k * v2::kStage + off; }
-  __device__ __forceinline__ const double* gBAbt(int k) const { return p.babt + ((size_t)q * N + k) * 336; }
+#if SRBD_K3_WBASE
+  double *Wc, *Wf;    // W + min(lane, 23)-style index lc / W + (lane & 3): opaque per-lane bases of the vector loads
+  __device__ __forceinline__ double* wsc(int k, int off) const { return Wc + k * v2::kStage + off; }
+  __device__ __forceinline__ double* wsf(int k, int off) const { return Wf + k * v2::kStage + off; }
+#else
+  __device__ __forceinline__ double* wsc(int k, int off) const { return ws(k, off) + (lane < 24 ? lane : 0); }
+  __device__ __forceinline__ double* wsf(int k, int off) const { return ws(k, off) + ft; }
+#endif
+  // per-QP, per-lane base pointers of the packed QP data (set once per solve; kept opaque so that the compiler
+  // holds / reloads them instead of re-deriving them from (q, N, lane) with 64-bit multiplies at every stage)
+#if SRBD_K3_QBASE
+  const double *qG, *qR, *qD, *qM;
+  __device__ __forceinline__ void set_qp(int qp) {
+    q = qp;
+    const int lc = lane < 24 ? lane : 0;
+    qG = p.babt + (size_t)q * N * 336 + 2 * lane;
+    qR = p.rsq + (size_t)q * (N + 1) * 672;
+    qD = p.d + (size_t)q * (N + 1) * 48 + lc;
+    qM = p.dmask + (size_t)q * (N + 1) * 48 + lc;
+    asm volatile("" : "+l"(qG), "+l"(qR), "+l"(qD), "+l"(qM));
+  }
+  __device__ __forceinline__ const double* gBAbtL(int k) const { return qG + k * 336; }   // + 2 * lane
+  __device__ __forceinline__ const double* gRSQ(int k) const { return qR + k * 672; }
+  __device__ __forceinline__ const double* gDL(int k) const { return qD + k * 48; }       // + min(lane, 23)-ish (lc)
+  __device__ __forceinline__ const double* gMaskL(int k) const { return qM + k * 48; }    // + lc
+#else
+  __device__ __forceinline__ void set_qp(int qp) { q = qp; }
+  __device__ __forceinline__ const double* gBAbtL(int k) const { return p.babt + ((size_t)q * N + k) * 336 + 2 * lane; }
   __device__ __forceinline__ const double* gRSQ(int k) const { return p.rsq + ((size_t)q * (N + 1) + k) * 672; }
-  __device__ __forceinline__ const double* gD(int k) const { return p.d + ((size_t)q * (N + 1) + k) * 48; }
-  __device__ __forceinline__ const double* gMask(int k) const { return p.dmask + ((size_t)q * (N + 1) + k) * 48; }
+  __device__ __forceinline__ const double* gDL(int k) const {
+    return p.d + ((size_t)q * (N + 1) + k) * 48 + (lane < 24 ? lane : 0);
+  }
+  __device__ __forceinline__ const double* gMaskL(int k) const {
+    return p.dmask + ((size_t)q * (N + 1) + k) * 48 + (lane < 24 ? lane : 0);
+  }
+#endif
 
   // ---- asynchronous tile prefetch (cp.async, no registers) -------------------------------------------
   // BAbt record (panels of 4 rows x 12 = 48 doubles) -> padded panels; np = 6: rows 0..23, 7: + the b row.
   // One 24-lane instruction per panel: every address is base + immediate.
   __device__ __forceinline__ void prefetch_G(int k, int b, int np = 6) {
-    const double* src = gBAbt(k) + 2 * lane;
+    const double* src = gBAbtL(k);
     double* dst = sm + (b ? v2::wG1 : v2::wG0) + 2 * lane;
     if (lane < 24) {
 #pragma unroll
@@ -201,9 +270,13 @@ struct SrbdSolver {
   __device__ __forceinline__ void prefetch_Rblk(int k, int b) {
     const double* src = gRSQ(k);
     double* dst = sm + (b ? v2::wR1 : v2::wR0);
+#if SRBD_K3_QBASE
+    cp_async16(dst + rbD, src + rbS);
+#else
     const int pnl = lane < 8 ? 0 : (lane < 24 ? 1 : 2);
     const int o = lane - (pnl == 0 ? 0 : (pnl == 1 ? 8 : 24));
     cp_async16(dst + (pnl == 0 ? 0 : (pnl == 1 ? 16 : 48)) + 2 * o, src + pnl * 96 + 2 * o);
+#endif
     if (lane < 16) cp_async16(dst + 48 + 2 * (lane + 8), src + 192 + 2 * (lane + 8));
   }
   // R block of RSQrq and the gradient row n = [r; q] (24 scattered doubles: row n of the panel-major record)
@@ -228,12 +301,12 @@ struct SrbdSolver {
   __device__ __forceinline__ S1v load_s1(int k) const {
     const int lc = lane < 24 ? lane : 0;
     S1v v;
-    v.mk = __ldg(gMask(k) + lc); v.lam = __ldcg(ws(k, v2::oLAM) + lc); v.t = __ldcg(ws(k, v2::oT) + lc);
-    v.rm = __ldcg(ws(k, v2::oRM) + lc); v.rd = __ldcg(ws(k, v2::oRD) + lc);
+    v.mk = __ldg(gMaskL(k)); v.lam = __ldcg(wsc(k, v2::oLAM)); v.t = __ldcg(wsc(k, v2::oT));
+    v.rm = __ldcg(wsc(k, v2::oRM)); v.rd = __ldcg(wsc(k, v2::oRD));
 #pragma unroll
-    for (int j = 0; j < 6; ++j) v.rg[j] = __ldcg(ws(k, v2::oRG) + 4 * j + ft);
+    for (int j = 0; j < 6; ++j) v.rg[j] = __ldcg(wsf(k, v2::oRG) + 4 * j);
 #pragma unroll
-    for (int j = 0; j < 3; ++j) v.rb[j] = __ldcg(ws(k, v2::oRB) + 4 * j + ft);
+    for (int j = 0; j < 3; ++j) v.rb[j] = __ldcg(wsf(k, v2::oRB) + 4 * j);
     return v;
   }
   // 1/sqrt(x) of a positive pivot: MUFU.RSQ64H seed (rel. error < 2^-20) + one third-order step
@@ -286,14 +359,17 @@ struct SrbdSolver {
         }
       }
 #pragma unroll
-      for (int kt = 0; kt < 3; ++kt) pk[kt] = __ldcg(ws(N, v2::oRG) + 4 * kt + t);
+      for (int kt = 0; kt < 3; ++kt) pk[kt] = __ldcg(wsf(N, v2::oRG) + 4 * kt);
       __syncwarp();
       for (int e = lane; e < 144; e += 32) ws(N - 1, v2::oP)[e] = sP[e];  // P_k lives in block k-1 (next to FT_{k-1})
       if (r == 0) {
 #pragma unroll
-        for (int kt = 0; kt < 3; ++kt) ws(N, v2::oPV)[4 * kt + t] = pk[kt];
+        for (int kt = 0; kt < 3; ++kt) wsf(N, v2::oPV)[4 * kt] = pk[kt];
       }
     }
+#if SRBD_K3_UNROLL_FAC
+#pragma unroll 2
+#endif
     for (int k = N - 1; k >= 0; --k) {
       const int b = (N - 1 - k) & 1;
       const bool xr = k > 0;                 // the stage has x rows (rows 12..23)
@@ -355,7 +431,7 @@ struct SrbdSolver {
           dmma(d1[0], d1[1], cur.rb[kt], PPF[1][kt], d1[0], d1[1]);
         }
         if (r == 0) {  // P_{k+1} rb is the same for every KKT solve of this iteration
-          ws(k, v2::oPRB)[t] = d0[0]; ws(k, v2::oPRB)[4 + t] = d0[1]; ws(k, v2::oPRB)[8 + t] = d1[0];
+          wsf(k, v2::oPRB)[0] = d0[0]; wsf(k, v2::oPRB)[4] = d0[1]; wsf(k, v2::oPRB)[8] = d1[0];
         }
         const double tk[3] = {d0[0] + pk[0], d0[1] + pk[1], d1[0] + pk[2]};
 #pragma unroll
@@ -502,7 +578,7 @@ struct SrbdSolver {
         if (4 + t <= r) { sP[(4 + r) * 12 + 8 + t] = MF[2][5]; sP[(8 + t) * 12 + 4 + r] = MF[2][5]; }
         pk[0] = c1[1]; pk[1] = c2[0]; pk[2] = c2[1];   // p_k = g~_x after the three panels
         if (r == 0) {
-          ws(k, v2::oPV)[t] = pk[0]; ws(k, v2::oPV)[4 + t] = pk[1]; ws(k, v2::oPV)[8 + t] = pk[2];
+          wsf(k, v2::oPV)[0] = pk[0]; wsf(k, v2::oPV)[4] = pk[1]; wsf(k, v2::oPV)[8] = pk[2];
         }
         __syncwarp();
         for (int e = lane; e < 72; e += 32)
@@ -540,13 +616,13 @@ struct SrbdSolver {
   __device__ __forceinline__ S4v load_s4(int k) const {
     const int lc = lane < 24 ? lane : 0;
     S4v v;
-    v.mk = __ldg(gMask(k) + lc); v.rmb = __ldcg(ws(k, v2::oRMB) + lc); v.dt = __ldcg(ws(k, v2::oDT) + lc);
-    v.dlam = __ldcg(ws(k, v2::oDLAM) + lc); v.lam = __ldcg(ws(k, v2::oLAM) + lc); v.t = __ldcg(ws(k, v2::oT) + lc);
-    v.rd = __ldcg(ws(k, v2::oRD) + lc);
+    v.mk = __ldg(gMaskL(k)); v.rmb = __ldcg(wsc(k, v2::oRMB)); v.dt = __ldcg(wsc(k, v2::oDT));
+    v.dlam = __ldcg(wsc(k, v2::oDLAM)); v.lam = __ldcg(wsc(k, v2::oLAM)); v.t = __ldcg(wsc(k, v2::oT));
+    v.rd = __ldcg(wsc(k, v2::oRD));
 #pragma unroll
-    for (int j = 0; j < 6; ++j) v.rg[j] = __ldcg(ws(k, v2::oRG) + 4 * j + ft);
+    for (int j = 0; j < 6; ++j) v.rg[j] = __ldcg(wsf(k, v2::oRG) + 4 * j);
 #pragma unroll
-    for (int j = 0; j < 3; ++j) v.prb[j] = __ldcg(ws(k, v2::oPRB) + 4 * j + ft);
+    for (int j = 0; j < 3; ++j) v.prb[j] = __ldcg(wsf(k, v2::oPRB) + 4 * j);
     return v;
   }
   __device__ __forceinline__ void sweep_backvec(int mode, double sm_) {
@@ -558,14 +634,17 @@ struct SrbdSolver {
     const int oDt = t * 12 + pi;                                      // Ac[4kt+t][8I+pi]     : + 8 I + 48 kt
     double pk[3];
 #pragma unroll
-    for (int kt = 0; kt < 3; ++kt) pk[kt] = __ldcg(ws(N, v2::oRG) + 4 * kt + t);
+    for (int kt = 0; kt < 3; ++kt) pk[kt] = __ldcg(wsf(N, v2::oRG) + 4 * kt);
     if (r == 0) {
 #pragma unroll
-      for (int kt = 0; kt < 3; ++kt) ws(N, v2::oPV)[4 * kt + t] = pk[kt];
+      for (int kt = 0; kt < 3; ++kt) wsf(N, v2::oPV)[4 * kt] = pk[kt];
     }
     prefetch_G(N - 1, 0);
     prefetch_F(N - 1, 0, false);
     S4v cur = load_s4(N - 1);
+#if SRBD_K3_UNROLL_BWD
+#pragma unroll 2
+#endif
     for (int k = N - 1; k >= 0; --k) {
       const int b = (N - 1 - k) & 1;
       cp_async_wait_all();
@@ -585,7 +664,7 @@ struct SrbdSolver {
         rm = (rm - sm_) * cur.mk;
         const double ti = 1.0 / cur.t;
         if (lane < 24) {
-          ws(k, v2::oRM)[lane] = rm;
+          wsc(k, v2::oRM)[0] = rm;
           gbuf[lane] = (ti * (rm - cur.lam * cur.rd)) * cur.mk;
         }
       }
@@ -636,7 +715,7 @@ struct SrbdSolver {
         }
         pk[0] = p0[0]; pk[1] = p0[1]; pk[2] = p1[0];
         if (r == 0) {
-          ws(k, v2::oPV)[t] = pk[0]; ws(k, v2::oPV)[4 + t] = pk[1]; ws(k, v2::oPV)[8 + t] = pk[2];
+          wsf(k, v2::oPV)[0] = pk[0]; wsf(k, v2::oPV)[4] = pk[1]; wsf(k, v2::oPV)[8] = pk[2];
         }
       }
       cur = nxt;
@@ -654,12 +733,12 @@ struct SrbdSolver {
   __device__ __forceinline__ S2v load_s2(int k) const {
     const int lc = lane < 24 ? lane : 0;
     S2v v;
-    v.mk = __ldg(gMask(k) + lc); v.t = __ldcg(ws(k, v2::oT) + lc); v.lam = __ldcg(ws(k, v2::oLAM) + lc);
-    v.rd = __ldcg(ws(k, v2::oRD) + lc); v.rm = __ldcg(ws(k, v2::oRM) + lc);
+    v.mk = __ldg(gMaskL(k)); v.t = __ldcg(wsc(k, v2::oT)); v.lam = __ldcg(wsc(k, v2::oLAM));
+    v.rd = __ldcg(wsc(k, v2::oRD)); v.rm = __ldcg(wsc(k, v2::oRM));
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      v.rb[j] = __ldcg(ws(k, v2::oRB) + 4 * j + ft);
-      v.pv[j] = __ldcg(ws(k + 1, v2::oPV) + 4 * j + ft);
+      v.rb[j] = __ldcg(wsf(k, v2::oRB) + 4 * j);
+      v.pv[j] = __ldcg(wsf(k + 1, v2::oPV) + 4 * j);
     }
     return v;
   }
@@ -682,6 +761,9 @@ struct SrbdSolver {
     prefetch_G(0, 0);
     prefetch_F(0, 0, fin);
     S2v cur = load_s2(0);
+#if SRBD_K3_UNROLL_FWD
+#pragma unroll 2
+#endif
     for (int k = 0; k < N; ++k) {
       const int b = k & 1;
       cp_async_wait_all();
@@ -730,8 +812,8 @@ struct SrbdSolver {
       if (fin && r == 0) {
 #pragma unroll
         for (int kt = 0; kt < 3; ++kt) {
-          ws(k, v2::oDZ)[4 * kt + t] = uk[kt];
-          if (k > 0) ws(k, v2::oDZ)[12 + 4 * kt + t] = xk[kt];
+          wsf(k, v2::oDZ)[4 * kt] = uk[kt];
+          if (k > 0) wsf(k, v2::oDZ)[12 + 4 * kt] = xk[kt];
         }
       }
       xk[0] = cx0[0]; xk[1] = cx0[1]; xk[2] = cx1[0];
@@ -744,7 +826,7 @@ struct SrbdSolver {
           dmma(d1[0], d1[1], xk[kt], sF[oPP + 96 + 4 * kt], d1[0], d1[1]);
         }
         if (r == 0) {
-          ws(k, v2::oDPI)[t] = d0[0]; ws(k, v2::oDPI)[4 + t] = d0[1]; ws(k, v2::oDPI)[8 + t] = d1[0];
+          wsf(k, v2::oDPI)[0] = d0[0]; wsf(k, v2::oDPI)[4] = d0[1]; wsf(k, v2::oDPI)[8] = d1[0];
         }
       }
       __syncwarp();
@@ -758,8 +840,8 @@ struct SrbdSolver {
         const double num = cur.mk != 0.0 ? -(cur.lam * dt + cur.rm) : 1.0;
         const double dl = (num / cur.t) * cur.mk;
         if (lane < 24) {
-          ws(k, v2::oDT)[lane] = dt;
-          ws(k, v2::oDLAM)[lane] = dl;
+          wsc(k, v2::oDT)[0] = dt;
+          wsc(k, v2::oDLAM)[0] = dl;
           s0 += cur.lam * cur.t;
           s1 += cur.lam * dt + cur.t * dl;
           s2 += dl * dt;
@@ -772,7 +854,7 @@ struct SrbdSolver {
     }
     if (fin && r == 0) {  // x_N
 #pragma unroll
-      for (int kt = 0; kt < 3; ++kt) ws(N, v2::oDZ)[4 * kt + t] = xk[kt];
+      for (int kt = 0; kt < 3; ++kt) wsf(N, v2::oDZ)[4 * kt] = xk[kt];
     }
     ap = warp_min(np_ / dp_);
     ad = warp_min(nd_ / dd_);
@@ -796,21 +878,21 @@ struct SrbdSolver {
   __device__ __forceinline__ S6raw load_s6(int k, bool do_update) const {
     const int lc = lane < 24 ? lane : 0, l12 = lane < 12 ? lane : 0;
     S6raw v;
-    v.z = __ldcg(ws(k, v2::oZ) + lc);
+    v.z = __ldcg(wsc(k, v2::oZ));
     v.pi = 0.0; v.lam = 0.0; v.t = 1.0; v.xn = 0.0; v.lo = 0.0; v.mk = 0.0;
     v.dz = 0.0; v.dpi = 0.0; v.dlam = 0.0; v.dt = 0.0; v.dxn = 0.0;
     const int xo = (k + 1 < N ? 12 : 0);
     if (k < N) {
-      v.pi = __ldcg(ws(k, v2::oPI) + l12); v.lam = __ldcg(ws(k, v2::oLAM) + lc); v.t = __ldcg(ws(k, v2::oT) + lc);
-      v.xn = __ldcg(ws(k + 1, v2::oZ) + xo + l12); v.lo = __ldg(gD(k) + lc); v.mk = __ldg(gMask(k) + lc);
+      v.pi = __ldcg(wsc(k, v2::oPI)); v.lam = __ldcg(wsc(k, v2::oLAM)); v.t = __ldcg(wsc(k, v2::oT));
+      v.xn = __ldcg(wsc(k + 1, v2::oZ) + xo); v.lo = __ldg(gDL(k)); v.mk = __ldg(gMaskL(k));
     }
     if (do_update) {
-      v.dz = __ldcg(ws(k, v2::oDZ) + lc);
+      v.dz = __ldcg(wsc(k, v2::oDZ));
       if (k < N) {
-        v.dpi = __ldcg(ws(k, v2::oDPI) + l12);
-        v.dxn = __ldcg(ws(k + 1, v2::oDZ) + xo + l12);
-        v.dt = __ldcg(ws(k, v2::oDT) + lc);
-        v.dlam = __ldcg(ws(k, v2::oDLAM) + lc);
+        v.dpi = __ldcg(wsc(k, v2::oDPI));
+        v.dxn = __ldcg(wsc(k + 1, v2::oDZ) + xo);
+        v.dt = __ldcg(wsc(k, v2::oDT));
+        v.dlam = __ldcg(wsc(k, v2::oDLAM));
       }
     }
     return v;
@@ -858,6 +940,9 @@ struct SrbdSolver {
     prefetch_R(0, 0);
     S6raw raw = load_s6(0, do_update);
     double pp[3] = {0.0, 0.0, 0.0};  // updated pi_{k-1}, fragment form
+#if SRBD_K3_UNROLL_RES
+#pragma unroll 2
+#endif
     for (int k = 0; k <= N; ++k) {
       const int b = k & 1;
       const int nu = k < N ? 12 : 0, nx = k > 0 ? 12 : 0, n = nu + nx;
@@ -879,10 +964,10 @@ struct SrbdSolver {
         if (lane < 24) lb[lane] = cur.lam;
       }
       if (do_update) {
-        if (lane < n) ws(k, v2::oZ)[lane] = cur.z;
+        if (lane < n) wsc(k, v2::oZ)[0] = cur.z;
         if (k < N) {
-          if (lane < 12) ws(k, v2::oPI)[lane] = cur.pi;
-          if (lane < 24) { ws(k, v2::oT)[lane] = cur.t; ws(k, v2::oLAM)[lane] = cur.lam; }
+          if (lane < 12) wsc(k, v2::oPI)[0] = cur.pi;
+          if (lane < 24) { wsc(k, v2::oT)[0] = cur.t; wsc(k, v2::oLAM)[0] = cur.lam; }
         }
       }
       __syncwarp();
@@ -932,7 +1017,7 @@ struct SrbdSolver {
         }
         b0[0] -= pb[12 + t]; b0[1] -= pb[16 + t]; b1[0] -= pb[20 + t];
         if (r == 0) {
-          ws(k, v2::oRB)[t] = b0[0]; ws(k, v2::oRB)[4 + t] = b0[1]; ws(k, v2::oRB)[8 + t] = b1[0];
+          wsf(k, v2::oRB)[0] = b0[0]; wsf(k, v2::oRB)[4] = b0[1]; wsf(k, v2::oRB)[8] = b1[0];
         }
         nb_ = amax_nan(amax_nan(amax_nan(nb_, b0[0]), b0[1]), b1[0]);
         pp[0] = pk_[0]; pp[1] = pk_[1]; pp[2] = pk_[2];
@@ -940,9 +1025,9 @@ struct SrbdSolver {
         c0[0] -= pp[0]; c0[1] -= pp[1]; c1[0] -= pp[2];  // stage N: the x rows are rows 0..11
       }
       if (r == 0) {
-        ws(k, v2::oRG)[t] = c0[0]; ws(k, v2::oRG)[4 + t] = c0[1]; ws(k, v2::oRG)[8 + t] = c1[0];
+        wsf(k, v2::oRG)[0] = c0[0]; wsf(k, v2::oRG)[4] = c0[1]; wsf(k, v2::oRG)[8] = c1[0];
         if (n == 24) {
-          ws(k, v2::oRG)[12 + t] = c1[1]; ws(k, v2::oRG)[16 + t] = c2[0]; ws(k, v2::oRG)[20 + t] = c2[1];
+          wsf(k, v2::oRG)[12] = c1[1]; wsf(k, v2::oRG)[16] = c2[0]; wsf(k, v2::oRG)[20] = c2[1];
         }
       }
       ng_ = amax_nan(amax_nan(amax_nan(ng_, c0[0]), c0[1]), c1[0]);
@@ -955,9 +1040,9 @@ struct SrbdSolver {
         const double rd = ((cur.lo - v) + cur.t) * cur.mk;
         const double rm = (cur.lam * cur.t) * cur.mk;
         if (lane < 24) {
-          ws(k, v2::oRD)[lane] = rd;
-          ws(k, v2::oRM)[lane] = rm;
-          ws(k, v2::oRMB)[lane] = rm;
+          wsc(k, v2::oRD)[0] = rd;
+          wsc(k, v2::oRM)[0] = rm;
+          wsc(k, v2::oRMB)[0] = rm;
           smu += rm;
           nd_ = amax_nan(nd_, rd);
           nm_ = amax_nan(nm_, rm);
@@ -983,21 +1068,21 @@ struct SrbdSolver {
   }
 
   __device__ void solve_one(int qp) {
-    q = qp;
+    set_qp(qp);
     const srbd_ipm_args& a = p.a;
     // ---- d_ocp_qp_init_var (cold start): z = 0, pi = 0, t = max(thr0, -lo), lam = mu0/t (masked rows 0) ------
     int nmask = 0;
 #pragma unroll 4
     for (int k = 0; k <= N; ++k) {
-      if (lane < 24) ws(k, v2::oZ)[lane] = 0.0;
+      if (lane < 24) wsc(k, v2::oZ)[0] = 0.0;
       if (k < N) {
-        if (lane < 12) ws(k, v2::oPI)[lane] = 0.0;
+        if (lane < 12) wsc(k, v2::oPI)[0] = 0.0;
         if (lane < 24) {
-          const double lo = __ldg(gD(k) + lane), mk = __ldg(gMask(k) + lane);
+          const double lo = __ldg(gDL(k)), mk = __ldg(gMaskL(k));
           double tl = 0.0 - lo;
           tl = a.thr0 > tl ? a.thr0 : tl;
-          ws(k, v2::oT)[lane] = tl;
-          ws(k, v2::oLAM)[lane] = (a.mu0 / tl) * mk;
+          wsc(k, v2::oT)[0] = tl;
+          wsc(k, v2::oLAM)[0] = (a.mu0 / tl) * mk;
           nmask += (mk != 0.0);
           // the masked upper side never moves: t_u = max(thr0, up - v) with up = 0, v = 0; lam_u = 0
           const double tu = a.thr0 > 0.0 ? a.thr0 : 0.0;
@@ -1073,8 +1158,8 @@ struct SrbdSolver {
           vx[j] = k == 0 ? __ldg(p.x0 + (size_t)q * 12 + l12) : __ldcg(ws(k, v2::oZ) + nu + l12);
           vp[j] = __ldcg(ws(k > 0 ? k - 1 : 0, v2::oPI) + l12);
           vu[j] = __ldcg(ws(kk_, v2::oZ) + l12);
-          vl[j] = __ldcg(ws(kk_, v2::oLAM) + lc);
-          vt[j] = __ldcg(ws(kk_, v2::oT) + lc);
+          vl[j] = __ldcg(wsc(kk_, v2::oLAM));
+          vt[j] = __ldcg(wsc(kk_, v2::oT));
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {

@@ -409,3 +409,27 @@ def test_srbd_pipeline_other_horizons(pkg, orc, N, B):
     assert (st["status"] == ref["status"]).all()
     assert (st["iter"] == ref["iter"]).all(), (st["iter"], ref["iter"])
     check_iterates(sol, ref, ref_p, strict=(), bulk=0.75)  # conditioning grows with N: yardstick + bulk only
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,B", [(20, 1), (20, 5), (20, 13), (1, 7), (2, 6)])
+def test_srbd_ragged_batches_and_tiny_horizons(pkg, orc, N, B):
+    """Edge shapes of the throughput path: batches smaller than / not a multiple of the QPs one CTA holds
+    (SRBD_K3_WARPS = 6), a single QP, and the shortest horizons (N = 1: stage 0 is followed directly by the
+    terminal stage; N = 2: one interior stage).  Whole pipeline against the oracle's own linearize / assemble /
+    solve: equal iteration counts and statuses, primal iterates within 5e-9 (same bound as
+    test_srbd_pipeline_parity part 2), batch statistics consistent."""
+    w = pkg.workload.srbd_batch(B, N=N, contact_mode="gait", start=1000 + 17 * B + N)
+    with make_ctx(pkg, B, N) as ctx:
+        ctx.upload_traj(w["x"], w["u"], w["xref"], w["x0"], w["contact"])
+        ctx.sqp_iterate(1)
+        sol = ctx.download_solution(want=("x", "u", "pi", "lam", "t"))
+        st = ctx.download_stats()
+        bs = ctx.batch_stats()
+    ref = orc.pipeline(orc.model_params(N), orc.ipm_args(**SETTINGS), N, 1, w["x"], w["u"], w["xref"], w["x0"],
+                       w["contact"])
+    assert (st["status"] == ref["status"]).all(), (st["status"], ref["status"])
+    assert (st["iter"] == ref["iter"]).all(), (st["iter"], ref["iter"])
+    for k in ("x", "u", "t"):
+        assert relerr(sol[k], ref[k]).max() <= 5e-9, (k, relerr(sol[k], ref[k]).max())
+    assert bs["solves"] == B and bs["iter_sum"] == int(st["iter"].sum())
