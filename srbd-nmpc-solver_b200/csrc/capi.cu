@@ -540,7 +540,7 @@ int srbd_qp_upload(srbd_ctx* ctx, const srbd_qp_host* qp) {
   return SRBD_OK;
 }
 
-// K3 for QPs assembled by K2 in HARD_INEQ mode: the SRBD throughput variant (same algorithm as the generic kernel)
+// K3 for QPs assembled by K2: the SRBD throughput variant (same algorithm as the generic kernel)
 static int solve_srbd_variant(srbd_ctx* ctx) {
   const QpLayout& L = ctx->L;
   if (!ctx->d_ws2) {
@@ -594,7 +594,9 @@ int srbd_qp_solve(srbd_ctx* ctx) {
     for (int g = 0; g < 24; ++g)
       for (int j = 0; j < 12; ++j)
         if (Ac[g * 12 + j] != 0.0 && (j / 6) != (g / 12)) blocks = false;
-    if (!generic && blocks && ctx->is_srbd && ctx->assembled_mode == SRBD_HARD_INEQ && !ctx->args.warm_start &&
+    // (both assemble modes: BARRIER_SOFT masks every row, which the variant solves as the single unconstrained
+    // Riccati pass)
+    if (!generic && blocks && ctx->is_srbd && ctx->assembled_mode >= 0 && !ctx->args.warm_start &&
         ctx->args.ric_alg == 0 &&
         !ctx->export_ric && !ctx->export_stat)
       return solve_srbd_variant(ctx);

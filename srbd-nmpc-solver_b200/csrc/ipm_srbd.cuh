@@ -7,7 +7,11 @@
 //     contact)                       -> Ac lives in shared memory; D^T Gamma D = sum_g Gamma_g W_g with the 21
 //                                       lower-triangle products W_g of each row's 6-vector precomputed per CTA;
 //   * only the lower side of the rows is active (ug masked), no box constraints, cold start.
-// Mapping: 4 independent warps per CTA, one QP per warp, persistent grid + atomic work counter.
+// Mapping: independent warps, one QP per warp, persistent grid + atomic work counter; 6 warps per CTA and 2 CTAs per
+// SM (SRBD_K3_WARPS x SRBD_K3_MIN_CTAS).  The register file allows 3 warps per SM sub-partition at 168 registers
+// or 4 at 128 (nothing in between: 16384 registers per sub-partition), and the 4 x 128 build spills too much
+// (445k vs 545k solves/s); among the 12-warp shapes the ones whose shared memory fits the 196 KB carve-out
+// (6 x 2, 12 x 1) leave a 60 KB L1 instead of 28 KB and run 3-4 % faster than 4 x 3.
 // The solve runs on the FP64 tensor cores (mma.sync m8n8k4 f64, "DMMA"): one
 // instruction is 256 FMAs, i.e. 8 warp-wide DFMAs plus their shared-memory operand fetches in ONE issue slot
 // (scripts/microbench/fp64_pipes.cu: DMMA and DFMA share the FP64 pipe on B200, 36.9 vs 35.8 TFLOP/s, so the
@@ -603,12 +607,11 @@ struct SrbdSolver {
   // Vector sweeps in FRAGMENT FORM (scripts/proto_dmma_vec.py is the lane-level emulation of these bodies).
   // A length-12 vector is three registers ("k-tiles") valid in lanes 0..3: lane t of k-tile kt holds v[4 kt + t],
   // i.e. row 0 of a DMMA A operand (the other rows replicate it).  y = A x is 2 x 3 DMMA with the rows of A as
-  // pi-permuted B fragments, gathered STRAIGHT FROM GLOBAL MEMORY (every 8-byte gather fills whole 32-byte
-  // sectors of the panel-major records; no shared-memory staging, no cp.async) into registers that are refilled
-  // with the next stage's fragment right after their last use (one-stage-ahead prefetch at zero extra
-  // registers).  The accumulator pair (c0, c1) of output tile I is k-tiles 2I, 2I+1 of y, so a whole stage of the
-  // recursion (three to five chained gemvs) runs in registers; the only shared-memory round trip per stage is
-  // between the fragment form and the row-per-lane form of the 24 constraint rows.
+  // pi-permuted B fragments read from the cp.async-staged shared-memory tiles (fragments gathered straight from
+  // global memory into registers were slower: DESIGN.md section 5).  The accumulator pair (c0, c1) of output tile I
+  // is k-tiles 2I, 2I+1 of y, so a whole stage of the recursion (three to five chained gemvs) runs in registers;
+  // the only shared-memory round trip per stage is between the fragment form and the row-per-lane form of the 24
+  // constraint rows.
   // ------------------------------------------------------------------------------------------------
   // S4: vector-only backward sweep (gradient recursion with the stored factors).  mode 1: centering
   // correction, mode 2: centering only; sm_ = sigma*mu (clamped by the caller)
@@ -1091,7 +1094,13 @@ struct SrbdSolver {
         }
       }
     }
-    const int nc_mask = warp_sum_i(nmask);
+    const int nc_all = warp_sum_i(nmask);
+    // No active row at all (BARRIER_SOFT assembly masks every row): d_ocp_qp_fact_solve_kkt_unconstr, ONE Riccati
+    // factorization and solve on the QP itself, iter = 0 (oracle/ocp_qp_ipm.c:668).  It runs through the same call
+    // sites as an IPM iteration: at z = 0, pi = 0 the residuals are (g, b) themselves, Gamma = gamma = 0, the full
+    // step lands on the solution and the second residual pass evaluates it.
+    const bool unc = nc_all == 0;
+    const int nc_mask = unc ? 1 : nc_all;
     __syncwarp();
     double res[4], mu;
     double alpha = 1.0, sp_ = 0.0, sd_ = 0.0;
@@ -1099,8 +1108,9 @@ struct SrbdSolver {
     for (;; ++kk) {
       // residuals of the current iterate (kk > 0: the variable update of the previous iteration is fused in)
       residuals(res, mu, nc_mask, kk > 0, sp_, sd_);
-      if (!(kk < a.iter_max && alpha > a.alpha_min &&
-            (res[0] > a.tol_stat || res[1] > a.tol_eq || res[2] > a.tol_ineq || res[3] > a.tol_comp)))
+      if (unc ? kk > 0
+              : !(kk < a.iter_max && alpha > a.alpha_min &&
+                  (res[0] > a.tol_stat || res[1] > a.tol_eq || res[2] > a.tol_ineq || res[3] > a.tol_comp)))
         break;
       sweep_factor();
       // KKT solves of this iteration (one call site per sweep: the sweeps are inlined once).  phase 0: affine /
@@ -1111,8 +1121,8 @@ struct SrbdSolver {
         double sigma = 0.0, mua = 0.0, smv = 0.0;
         for (;;) {
           if (phase > 0) sweep_backvec(phase, smv);
-          sweep_forward(a.pred_corr != 1 || phase > 0, ap, ad);
-          if (a.pred_corr != 1) break;
+          sweep_forward(a.pred_corr != 1 || phase > 0 || unc, ap, ad);
+          if (a.pred_corr != 1 || unc) break;
           if (phase == 0) {
             mua = mu_aff(fmin(ap, ad), nc_mask);
             const double tmp = mua / mu;
@@ -1143,7 +1153,8 @@ struct SrbdSolver {
     }
     int status;
     const bool nan = (res[0] != res[0]) || (mu != mu);
-    if (kk == a.iter_max) status = 1;
+    if (unc) { kk = 0; status = nan ? 3 : 0; }
+    else if (kk == a.iter_max) status = 1;
     else if (alpha <= a.alpha_min) status = 2;
     else if (nan) status = 3;
     else status = 0;
@@ -1160,6 +1171,7 @@ struct SrbdSolver {
           vu[j] = __ldcg(ws(kk_, v2::oZ) + l12);
           vl[j] = __ldcg(wsc(kk_, v2::oLAM));
           vt[j] = __ldcg(wsc(kk_, v2::oT));
+          if (unc) { vl[j] = 0.0; vt[j] = 0.0; }  // the unconstrained solve reports lam = t = 0 on the masked rows
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -1173,6 +1185,7 @@ struct SrbdSolver {
             if (k < N && lane < 24) {
               p.sol_lam[(size_t)q * N * 48 + k * 48 + lane] = vl[j];
               p.sol_t[(size_t)q * N * 48 + k * 48 + lane] = vt[j];
+              if (unc) p.sol_t[(size_t)q * N * 48 + k * 48 + 24 + lane] = 0.0;
             }
           }
         }

@@ -139,21 +139,29 @@ def test_srbd_pipeline_parity(pkg, orc, mode, contact):
     assert bs["iter_hist"][:32] == list(np.bincount(st["iter"], minlength=32)[:32])
 
 
-def test_soft_mode_is_single_riccati_pass(pkg, orc):
+@pytest.mark.parametrize("generic", ["0", "1"])
+def test_soft_mode_is_single_riccati_pass(pkg, orc, monkeypatch, generic):
     """The reference's own workload: constraints folded into R,r => nb=ng active rows = 0 => iter == 0
-    (hpipm-cpp/test/ocp_qp_ipm_solver.cpp:56)."""
+    (hpipm-cpp/test/ocp_qp_ipm_solver.cpp:56).  Both K3 kernels take the unconstrained single-pass path
+    (generic = "0": the SRBD tensor-core variant, "1": the generic kernel); lam = t = 0 on the masked rows and
+    the residuals of the returned point are at rounding level, like the oracle's."""
+    monkeypatch.setenv("SRBD_K3_GENERIC", generic)
     B, N = 64, 20
     w = perturbed_workload(pkg, B, N, "stance")
     with make_ctx(pkg, B, N) as ctx:
         ctx.upload_traj(w["x"], w["u"], w["xref"], w["x0"], w["contact"])
         ctx.sqp_iterate(0)
-        sol = ctx.download_solution(want=("x", "u", "pi"))
+        sol = ctx.download_solution(want=("x", "u", "pi", "lam", "t"))
         st = ctx.download_stats()
     ref = orc.pipeline(orc.model_params(N), orc.ipm_args(**SETTINGS), N, 0, w["x"], w["u"], w["xref"], w["x0"], w["contact"])
     assert (st["iter"] == 0).all() and (st["status"] == 0).all()
+    assert (ref["iter"] == 0).all() and (ref["status"] == 0).all()
     for k in ("x", "u"):
         assert relerr(sol[k], ref[k]).max() <= TOL
     assert relerr(sol["pi"][:, 1:], ref["pi"][:, 1:]).max() <= TOL
+    assert (sol["lam"] == 0).all() and (sol["t"] == 0).all()  # oracle/ocp_qp_ipm.c:670-675
+    # stationarity / dynamics residuals of the returned point (|g| ~ 1e2..1e3 here), inequality / complementarity: none
+    assert (st["res_max"][:, :2] <= 1e-7).all() and (st["res_max"][:, 2:] == 0).all()
 
 
 def test_reference_sqp_loop_on_gpu(pkg, orc):
