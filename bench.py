@@ -319,7 +319,10 @@ def main():
             tj = json.load(open(tpath))
             traffic, traffic_src = tj["dram_bytes_per_qp"] * B, tj["source"]
             pipes_ncu = tj.get("pipes_ncu")
-        roofline = {"bound": "fp64", "kernel": "ipm_srbd_kernel (K3)", "achieved": achieved, "peak": peak,
+        # "tensor": K3 runs on the FP64 tensor cores (DMMA); their peak IS the FP64 pipe's (DMMA and DFMA share one
+        # datapath on B200: scripts/microbench/fp64_pipes.cu), measured live -- not the bf16 figure of MEASURED_PEAKS.json
+        roofline = {"bound": "tensor", "pipe": "fp64 (DMMA m8n8k4 + DFMA, one shared datapath)",
+                    "kernel": "ipm_srbd_kernel (K3)", "achieved": achieved, "peak": peak,
                     "unit": "TFLOP/s", "frac": achieved / peak if peak > 0 else None, "traffic": traffic,
                     "traffic_source": traffic_src, "pipes_ncu": pipes_ncu,
                     "peak_source": "measured live: DFMA-saturating microbenchmark srbd_fp64_peak() (MEASURED_PEAKS.json "
@@ -331,7 +334,7 @@ def main():
         hbm_peak = json.load(open(peaks_path))["hbm_gbs"] if os.path.exists(peaks_path) else 6650.0
         # HBM view of K1/K2 (write-bound kernels): dense packed records written per step
         k1_bytes = B * HORIZON * (336 + 12) * 8 + B * (HORIZON * 2 + 1) * 12 * 8
-        k2_bytes = B * (HORIZON + 1) * (672 + 96) * 8 + B * HORIZON * 576 * 8
+        k2_bytes = B * (HORIZON + 1) * (672 + 96 + 192) * 8 + B * HORIZON * 576 * 8  # RSQrq, d, dmask, stage record; DCt
         roofline["k1_hbm_frac"] = k1_bytes / (roofline["k1_ms"] * 1e-3) / 1e9 / hbm_peak
         roofline["k2_hbm_frac"] = k2_bytes / (roofline["k2_ms"] * 1e-3) / 1e9 / hbm_peak
         roofline["hbm_peak_gbs"] = hbm_peak

@@ -56,6 +56,6 @@ with torch.cuda.stream(st):
             ts.append(e0.elapsed_time(e1))
         res[nm] = float(np.median(ts))
 gb1 = B * N * (336 + 12) * 8 / 1e9
-gb2 = B * (N + 1) * (672 + 576 + 96) * 8 / 1e9
+gb2 = B * (N + 1) * (672 + 576 + 96 + 192) * 8 / 1e9  # RSQrq, DCt, d, dmask, compact stage record
 print("B=%d  K1 %.3f ms (%.0f GB/s written)  K2 %.3f ms (%.0f GB/s written)  lib=%s" % (
     B, res["K1"], gb1 / res["K1"] * 1e3, res["K2"], gb2 / res["K2"] * 1e3, os.environ.get("SRBD_LIB", "in-tree")))

@@ -28,6 +28,7 @@ struct srbd_ctx {
   ModelDev* d_model = nullptr;
   // NMPC level
   double *d_x = nullptr, *d_u = nullptr, *d_xref = nullptr, *d_x0abs = nullptr, *d_defect = nullptr;
+  double* d_srec = nullptr;  // [B][N+1][kSrec] compact stage records (K2 -> SRBD K3 variant)
   uint8_t* d_contact = nullptr;
   bool have_contact = false;
   double* d_alpha = nullptr; int* d_conv = nullptr; double* d_merit = nullptr;
@@ -193,6 +194,7 @@ int srbd_ctx_create(int device, int batch, const srbd_qp_dims* dims, void* strea
     A(dalloc(&ctx->d_x, B * S * 12)); A(dalloc(&ctx->d_u, B * N * 12)); A(dalloc(&ctx->d_xref, B * S * 12));
     A(dalloc(&ctx->d_x0abs, B * 12)); A(dalloc(&ctx->d_defect, B * N * 12)); A(dalloc(&ctx->d_contact, B * N * 2));
     A(dalloc(&ctx->d_alpha, B)); A(dalloc(&ctx->d_conv, B)); A(dalloc(&ctx->d_merit, B * 3));
+    A(dalloc(&ctx->d_srec, B * S * kSrec));
   }
   A(dalloc(&ctx->d_babt, B * N * L.babt_stride)); A(dalloc(&ctx->d_rsq, B * S * L.rsq_stride));
   A(dalloc(&ctx->d_dct, B * S * L.dct_stride)); A(dalloc(&ctx->d_d, B * S * L.d_stride));
@@ -238,7 +240,7 @@ int srbd_ctx_destroy(srbd_ctx* ctx) {
                   ctx->d_dmask, ctx->d_raw0, ctx->d_x0, ctx->d_xinit, ctx->d_uinit, ctx->d_sol_x, ctx->d_sol_u,
                   ctx->d_sol_pi, ctx->d_sol_lam, ctx->d_sol_t, ctx->d_P, ctx->d_p, ctx->d_K, ctx->d_k,
                   ctx->d_stat, ctx->d_iter, ctx->d_status, ctx->d_counter, ctx->d_resmax, ctx->d_bstats, ctx->d_ws,
-                  ctx->d_ws2};
+                  ctx->d_ws2, ctx->d_srec};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (void* p : ctx->raw_dev)
@@ -379,7 +381,8 @@ int srbd_assemble(srbd_ctx* ctx, int mode) {
   AsmParams p{};
   p.B = ctx->B; p.N = ctx->L.N; p.mode = mode;
   p.x = ctx->d_x; p.u = ctx->d_u; p.xref = ctx->d_xref; p.contact = ctx->have_contact ? ctx->d_contact : nullptr;
-  p.rsq = ctx->d_rsq; p.dct = ctx->d_dct; p.d = ctx->d_d; p.dmask = ctx->d_dmask; p.raw0 = ctx->d_raw0; p.fcon = nullptr;
+  p.rsq = ctx->d_rsq; p.srec = ctx->d_srec; p.dct = ctx->d_dct; p.d = ctx->d_d; p.dmask = ctx->d_dmask; p.raw0 = ctx->d_raw0;
+  p.fcon = nullptr;
   const long long total = (long long)p.B * (p.N + 1);
   const int grid = (int)((total + kAsmThreads - 1) / kAsmThreads);
   assemble_kernel<<<grid, kAsmThreads, 0, ctx->stream>>>(p, ctx->d_model);
@@ -564,7 +567,7 @@ static int solve_srbd_variant(srbd_ctx* ctx) {
   }
   SrbdIpmParams p{};
   p.B = ctx->B; p.N = L.N; p.a = ctx->args;
-  p.babt = ctx->d_babt; p.rsq = ctx->d_rsq; p.d = ctx->d_d; p.dmask = ctx->d_dmask; p.x0 = ctx->d_x0;
+  p.babt = ctx->d_babt; p.srec = ctx->d_srec; p.x0 = ctx->d_x0;
   p.model = ctx->d_model; p.ws = ctx->d_ws2; p.ws_size = (L.N + 1) * v2::kStage; p.counter = ctx->d_counter;
   p.sol_x = ctx->d_sol_x; p.sol_u = ctx->d_sol_u; p.sol_pi = ctx->d_sol_pi; p.sol_lam = ctx->d_sol_lam; p.sol_t = ctx->d_sol_t;
   p.iter = ctx->d_iter; p.status = ctx->d_status; p.res_max = ctx->d_resmax; p.bstats = ctx->d_bstats;

@@ -48,9 +48,7 @@ struct SrbdIpmParams {
   int B, N;
   srbd_ipm_args a;
   const double* babt;   // [B][N][336]
-  const double* rsq;    // [B][N+1][672]
-  const double* d;      // [B][N+1][48]   (lower part used)
-  const double* dmask;  // [B][N+1][48]
+  const double* srec;   // [B][N+1][kSrec] compact stage records of K2 (srbd_model.cuh: R tile, gradient row, lg, masks)
   const double* x0;     // [B][12]
   const ModelDev* model;
   double* ws;           // [gridDim.x*4][ws_size]
@@ -164,9 +162,6 @@ struct SrbdSolver {
   const double* sR;   // current R tile
   // fragment coordinates of this lane (see the header comment)
   int fr, ft, fpi;
-#if SRBD_K3_QBASE
-  int rbS, rbD;       // prefetch_Rblk: this lane's source / destination offset of the first copy
-#endif
   int offS[5];        // index into the 42 D^T Gamma D sums of this lane's element of the u-block fragments, or -1
 
   __device__ SrbdSolver(const SrbdIpmParams& p_, double* cta, double* warp_sm, int warp_global)
@@ -182,15 +177,6 @@ struct SrbdSolver {
     Wc = W + (lane < 24 ? lane : 0);
     Wf = W + ft;
     asm volatile("" : "+l"(Wc), "+l"(Wf));
-#endif
-#if SRBD_K3_QBASE
-    {
-      const int pnl = lane < 8 ? 0 : (lane < 24 ? 1 : 2);
-      const int o = lane - (pnl == 0 ? 0 : (pnl == 1 ? 8 : 24));
-      rbS = pnl * 96 + 2 * o;
-      rbD = (pnl == 0 ? 0 : (pnl == 1 ? 16 : 48)) + 2 * o;
-      asm volatile("" : "+r"(rbS), "+r"(rbD));
-    }
 #endif
     // u-block fragments in the order (I,p) = (0,0) (0,1) (1,0) (1,1) (1,2)
 #pragma unroll
@@ -217,31 +203,25 @@ struct SrbdSolver {
   // per-QP, per-lane base pointers of the packed QP data (set once per solve; kept opaque so that the compiler
   // holds / reloads them instead of re-deriving them from (q, N, lane) with 64-bit multiplies at every stage)
 #if SRBD_K3_QBASE
-  const double *qG, *qR, *qD, *qM;
+  const double *qG, *qT;
   __device__ __forceinline__ void set_qp(int qp) {
     q = qp;
-    const int lc = lane < 24 ? lane : 0;
     qG = p.babt + (size_t)q * N * 336 + 2 * lane;
-    qR = p.rsq + (size_t)q * (N + 1) * 672;
-    qD = p.d + (size_t)q * (N + 1) * 48 + lc;
-    qM = p.dmask + (size_t)q * (N + 1) * 48 + lc;
-    asm volatile("" : "+l"(qG), "+l"(qR), "+l"(qD), "+l"(qM));
+    qT = p.srec + (size_t)q * (N + 1) * kSrec + 2 * lane;
+    asm volatile("" : "+l"(qG), "+l"(qT));
   }
   __device__ __forceinline__ const double* gBAbtL(int k) const { return qG + k * 336; }   // + 2 * lane
-  __device__ __forceinline__ const double* gRSQ(int k) const { return qR + k * 672; }
-  __device__ __forceinline__ const double* gDL(int k) const { return qD + k * 48; }       // + min(lane, 23)-ish (lc)
-  __device__ __forceinline__ const double* gMaskL(int k) const { return qM + k * 48; }    // + lc
+  __device__ __forceinline__ const double* gRecL(int k) const { return qT + k * kSrec; }  // + 2 * lane
 #else
   __device__ __forceinline__ void set_qp(int qp) { q = qp; }
   __device__ __forceinline__ const double* gBAbtL(int k) const { return p.babt + ((size_t)q * N + k) * 336 + 2 * lane; }
-  __device__ __forceinline__ const double* gRSQ(int k) const { return p.rsq + ((size_t)q * (N + 1) + k) * 672; }
-  __device__ __forceinline__ const double* gDL(int k) const {
-    return p.d + ((size_t)q * (N + 1) + k) * 48 + (lane < 24 ? lane : 0);
-  }
-  __device__ __forceinline__ const double* gMaskL(int k) const {
-    return p.dmask + ((size_t)q * (N + 1) + k) * 48 + (lane < 24 ? lane : 0);
+  __device__ __forceinline__ const double* gRecL(int k) const {
+    return p.srec + ((size_t)q * (N + 1) + k) * kSrec + 2 * lane;
   }
 #endif
+  // lg / mask of row min(lane, 23)-ish (lanes >= 24 read row 0) from the stage record
+  __device__ __forceinline__ const double* gDL(int k) const { return gRecL(k) + 144 - (lane < 24 ? lane : 2 * lane); }
+  __device__ __forceinline__ const double* gMaskL(int k) const { return gDL(k) + 24; }
 
   // ---- asynchronous tile prefetch (cp.async, no registers) -------------------------------------------
   // BAbt record (panels of 4 rows x 12 = 48 doubles) -> padded panels; np = 6: rows 0..23, 7: + the b row.
@@ -269,25 +249,22 @@ struct SrbdSolver {
     for (int i = 0; i < 4; ++i) cp_async16(dst + 144 + 64 * i, src + 144 + 64 * i);
     if (lane < 25) cp_async16(dst + 144 + 256, src + 144 + 256);
   }
-  // R block of RSQrq only (rows 0..11, lower: prefixes of panels 0..2 = 8 + 16 + 24 16-byte chunks).  R_k is NOT a
-  // constant: the rows that stay a relaxed barrier in HARD_INEQ mode add Ac^T diag(b'') Ac (NMPC_solver.cpp:308)
+  // R tile of stage k (the lower 12 x 12 block of rows 0..11 of RSQrq as panel prefixes, 96 doubles): the head of the
+  // compact stage record, a linear copy.  R_k is NOT a constant: the rows that stay a relaxed barrier in HARD_INEQ
+  // mode add Ac^T diag(b'') Ac (NMPC_solver.cpp:308)
   __device__ __forceinline__ void prefetch_Rblk(int k, int b) {
-    const double* src = gRSQ(k);
-    double* dst = sm + (b ? v2::wR1 : v2::wR0);
-#if SRBD_K3_QBASE
-    cp_async16(dst + rbD, src + rbS);
-#else
-    const int pnl = lane < 8 ? 0 : (lane < 24 ? 1 : 2);
-    const int o = lane - (pnl == 0 ? 0 : (pnl == 1 ? 8 : 24));
-    cp_async16(dst + (pnl == 0 ? 0 : (pnl == 1 ? 16 : 48)) + 2 * o, src + pnl * 96 + 2 * o);
-#endif
-    if (lane < 16) cp_async16(dst + 48 + 2 * (lane + 8), src + 192 + 2 * (lane + 8));
+    const double* src = gRecL(k);
+    double* dst = sm + (b ? v2::wR1 : v2::wR0) + 2 * lane;
+    cp_async16(dst, src);
+    if (lane < 16) cp_async16(dst + 64, src + 64);
   }
-  // R block of RSQrq and the gradient row n = [r; q] (24 scattered doubles: row n of the panel-major record)
+  // ... and with the gradient row n = [r; q] (record offsets 108..131)
   __device__ __forceinline__ void prefetch_R(int k, int b) {
-    prefetch_Rblk(k, b);
-    const int n = (k < N ? 12 : 0) + (k > 0 ? 12 : 0);
-    if (lane < n) cp_async8(sm + (b ? v2::wR1 : v2::wR0) + 108 + lane, gRSQ(k) + (n >> 2) * 96 + 4 * lane + (n & 3));
+    const double* src = gRecL(k);
+    double* dst = sm + (b ? v2::wR1 : v2::wR0) + 2 * lane;
+    cp_async16(dst, src);
+    cp_async16(dst + 64, src + 64);
+    if (lane < 2) cp_async16(dst + 128, src + 128);
   }
   __device__ __forceinline__ void set_bufs(int b) {
     sG = sm + (b ? v2::wG1 : v2::wG0);
@@ -303,7 +280,6 @@ struct SrbdSolver {
   // matrix update); Q = diag(Q) is a model constant for k < N (NMPC_solver.cpp:305), R_k is read from RSQrq.
   struct S1v { double mk, lam, t, rm, rd, rg[6], rb[3]; };
   __device__ __forceinline__ S1v load_s1(int k) const {
-    const int lc = lane < 24 ? lane : 0;
     S1v v;
     v.mk = __ldg(gMaskL(k)); v.lam = __ldcg(wsc(k, v2::oLAM)); v.t = __ldcg(wsc(k, v2::oT));
     v.rm = __ldcg(wsc(k, v2::oRM)); v.rd = __ldcg(wsc(k, v2::oRD));
@@ -350,12 +326,12 @@ struct SrbdSolver {
     // ---- stage N: P_N = Q_N + reg I, p_N = rg_N ------------------------------------------------------
     double pk[3];
     {
-      const double* rs = gRSQ(N);
+      const double* rs = gRecL(N) - 2 * lane;  // Q_N: the R tile of the last stage record
       if (lane < 12) {
 #pragma unroll
         for (int c = 0; c < 12; ++c) {
           if (c <= lane) {
-            double v = __ldg(rs + pm_index(lane, c, 24));
+            double v = __ldg(rs + ((lane >> 2) == 0 ? 0 : ((lane >> 2) == 1 ? 16 : 48)) + 4 * c + (lane & 3));
             if (c == lane) v += reg;
             sP[lane * 12 + c] = v;
             sP[c * 12 + lane] = v;
@@ -617,7 +593,6 @@ struct SrbdSolver {
   // correction, mode 2: centering only; sm_ = sigma*mu (clamped by the caller)
   struct S4v { double mk, rmb, dt, dlam, lam, t, rd, rg[6], prb[3]; };
   __device__ __forceinline__ S4v load_s4(int k) const {
-    const int lc = lane < 24 ? lane : 0;
     S4v v;
     v.mk = __ldg(gMaskL(k)); v.rmb = __ldcg(wsc(k, v2::oRMB)); v.dt = __ldcg(wsc(k, v2::oDT));
     v.dlam = __ldcg(wsc(k, v2::oDLAM)); v.lam = __ldcg(wsc(k, v2::oLAM)); v.t = __ldcg(wsc(k, v2::oT));
@@ -734,7 +709,6 @@ struct SrbdSolver {
   double mu_s0, mu_s1, mu_s2;  // sum lam t, sum (lam dt + t dlam), sum dlam dt of the last forward sweep
   struct S2v { double mk, t, lam, rd, rm, rb[3], pv[3]; };
   __device__ __forceinline__ S2v load_s2(int k) const {
-    const int lc = lane < 24 ? lane : 0;
     S2v v;
     v.mk = __ldg(gMaskL(k)); v.t = __ldcg(wsc(k, v2::oT)); v.lam = __ldcg(wsc(k, v2::oLAM));
     v.rd = __ldcg(wsc(k, v2::oRD)); v.rm = __ldcg(wsc(k, v2::oRM));
@@ -879,7 +853,6 @@ struct SrbdSolver {
   // the prefetch point) ...
   struct S6raw { double z, pi, lam, t, xn, lo, mk, dz, dpi, dlam, dt, dxn; };
   __device__ __forceinline__ S6raw load_s6(int k, bool do_update) const {
-    const int lc = lane < 24 ? lane : 0, l12 = lane < 12 ? lane : 0;
     S6raw v;
     v.z = __ldcg(wsc(k, v2::oZ));
     v.pi = 0.0; v.lam = 0.0; v.t = 1.0; v.xn = 0.0; v.lo = 0.0; v.mk = 0.0;
@@ -1160,7 +1133,7 @@ struct SrbdSolver {
     else status = 0;
     // ---- outputs (four stages per trip: the loads of a trip are issued before its stores) ----------------------------
     {
-      const int l12 = lane < 12 ? lane : 0, lc = lane < 24 ? lane : 0;
+      const int l12 = lane < 12 ? lane : 0;
       for (int k0 = 0; k0 <= N; k0 += 4) {
         double vx[4], vp[4], vu[4], vl[4], vt[4];
 #pragma unroll

@@ -425,6 +425,7 @@ struct AsmParams {
   const double* xref;   // [B][N+1][12]
   const uint8_t* contact;  // [B][N][2] or null
   double* rsq;    // [B][N+1][28*24]
+  double* srec;   // [B][N+1][kSrec] compact stage records for the SRBD K3 variant
   double* dct;    // [B][N+1][24*24]
   double* d;      // [B][N+1][48]
   double* dmask;  // [B][N+1][48]
@@ -466,23 +467,43 @@ __device__ __forceinline__ double rblock_elem(const double* sAc, const double* c
 // (nu = 12, nx = 0), 1: interior, 2: last stage (nu = 0, nx = 12): with the panel and the stage type known at compile
 // time most elements fold to a stored zero.
 template <int TYPE>
-__device__ __forceinline__ void write_rsq(double* dst, const double* c, const double* sAc, const double* sQ,
-                                          const double* sQf, double R, int lane, int g_lo, int g_cnt) {
+__device__ __forceinline__ double rsq_elem(int i, int j, const double* c, const double* sAc, const double* sQ,
+                                           const double* sQf, double R, int g_lo, int g_cnt) {
   constexpr int nu = TYPE == 2 ? 0 : 12, nx = TYPE == 0 ? 0 : 12, n = nu + nx;
+  double v = 0.0;
+  if (i < n && j < n) {
+    if (i < nu && j < nu) v = rblock_elem(sAc, c, i, j, R, g_lo, g_cnt);
+    else if (i >= nu && j >= nu && i == j) v = TYPE == 2 ? sQf[i - nu] : sQ[i - nu];
+  } else if (i == n && j < n) {
+    v = j < nu ? c[24 + j] : c[36 + (j - nu)];
+  }
+  return v;
+}
+// Compact stage record for the SRBD K3 variant (ipm_srbd.cuh), kSrec doubles on 128-byte lines:
+//   [0, 96)    the lower 12 x 12 block of rows 0..11 of RSQrq (R_k, or Q_N at the last stage) as the prefixes of its
+//              three row panels: panel p (rows 4p..4p+3) holds columns 0..4p+3, element (i, j) at 4 j + (i & 3)
+//   [108, 132) the gradient row n of RSQrq ([r; q], r only at stage 0, q_N at the last stage)
+//   [144, 168) lg (lower bounds of the 24 rows), [168, 192) their masks
+// i.e. exactly the shared-memory R tile of the kernel followed by the two per-row vectors every sweep loads: one
+// linear cp.async stream and one base pointer instead of panel-prefix / strided-row gathers from three arrays.
+constexpr int kSrec = 192;
+template <int TYPE>
+__device__ __forceinline__ void write_rsq(double* dst, double* srec, const double* c, const double* sAc,
+                                          const double* sQ, const double* sQf, double R, int lane, int g_lo,
+                                          int g_cnt) {
+  constexpr int n = (TYPE == 2 ? 0 : 12) + (TYPE == 0 ? 0 : 12);
 #pragma unroll
   for (int pnl = 0; pnl < 7; ++pnl)
 #pragma unroll
     for (int sl = 0; sl < 3; ++sl) {
       const int e = lane + 32 * sl, j = e >> 2, i = 4 * pnl + (e & 3);
-      double v = 0.0;
-      if (i < n && j < n) {
-        if (i < nu && j < nu) v = rblock_elem(sAc, c, i, j, R, g_lo, g_cnt);
-        else if (i >= nu && j >= nu && i == j) v = TYPE == 2 ? sQf[i - nu] : sQ[i - nu];
-      } else if (i == n && j < n) {
-        v = j < nu ? c[24 + j] : c[36 + (j - nu)];
-      }
+      const double v = rsq_elem<TYPE>(i, j, c, sAc, sQ, sQf, R, g_lo, g_cnt);
       dst[96 * pnl + e] = v;
+      // the R-tile prefix of panels 0..2: columns j <= 4 pnl + 3
+      if (pnl < 3 && j < 4 * pnl + 4) srec[(pnl == 0 ? 0 : (pnl == 1 ? 16 : 48)) + e] = v;
     }
+  if (lane < 24) srec[108 + lane] = lane < n ? rsq_elem<TYPE>(n, lane, c, sAc, sQ, sQf, R, g_lo, g_cnt) : 0.0;
+  if (lane < 12) { srec[96 + lane] = 0.0; srec[132 + lane] = 0.0; }
 }
 
 __global__ void __launch_bounds__(kAsmThreads) assemble_kernel(const AsmParams p, const ModelDev* __restrict__ md) {
@@ -565,9 +586,10 @@ __global__ void __launch_bounds__(kAsmThreads) assemble_kernel(const AsmParams p
     const int nu = k < p.N ? 12 : 0;
     // RSQrq: 28 x 24 panel-major
     double* dst = p.rsq + (size_t)it * (28 * 24);
-    if (k == 0) write_rsq<0>(dst, c, sAc, sQ, sQf, sR, lane, g_lo, g_cnt);
-    else if (k < p.N) write_rsq<1>(dst, c, sAc, sQ, sQf, sR, lane, g_lo, g_cnt);
-    else write_rsq<2>(dst, c, sAc, sQ, sQf, sR, lane, g_lo, g_cnt);
+    double* sr = p.srec + (size_t)it * kSrec;
+    if (k == 0) write_rsq<0>(dst, sr, c, sAc, sQ, sQf, sR, lane, g_lo, g_cnt);
+    else if (k < p.N) write_rsq<1>(dst, sr, c, sAc, sQ, sQf, sR, lane, g_lo, g_cnt);
+    else write_rsq<2>(dst, sr, c, sAc, sQ, sQf, sR, lane, g_lo, g_cnt);
     // DCt (n x 24): D^T = Ac^T in the u rows, C = 0; d = [lg | 0 | 0(-ug) | 0], masks
     double* dd = p.dct + (size_t)it * (24 * 24);
     double* dv = p.d + (size_t)it * 48;
@@ -584,11 +606,14 @@ __global__ void __launch_bounds__(kAsmThreads) assemble_kernel(const AsmParams p
         const bool lower = e < 24;
         const int g = lower ? e : e - 24;
         const bool hard = (p.mode == SRBD_HARD_INEQ) && !row_soft_in_hard_mode(g);
-        dv[e] = (lower && p.mode == SRBD_HARD_INEQ) ? c[48 + g] : 0.0;
-        dk[e] = (lower && hard) ? 1.0 : 0.0;
+        const double dvv = (lower && p.mode == SRBD_HARD_INEQ) ? c[48 + g] : 0.0;
+        const double dkk = (lower && hard) ? 1.0 : 0.0;
+        dv[e] = dvv;
+        dk[e] = dkk;
+        if (lower) { sr[144 + g] = dvv; sr[168 + g] = dkk; }
       }
     } else {
-      for (int e = lane; e < 48; e += 32) { dv[e] = 0.0; dk[e] = 0.0; }
+      for (int e = lane; e < 48; e += 32) { dv[e] = 0.0; dk[e] = 0.0; sr[144 + e] = 0.0; }
     }
   }
 }
