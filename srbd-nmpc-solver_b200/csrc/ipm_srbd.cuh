@@ -82,6 +82,9 @@ namespace v2 {
 #ifndef SRBD_K3_UNROLL_RES
 #define SRBD_K3_UNROLL_RES 0
 #endif
+#ifndef SRBD_K3_L2PF
+#define SRBD_K3_L2PF 15   // bit 0: vectors, 1: P / factor panels, 2: BAbt record, 3: stage record
+#endif
 #ifndef SRBD_K3_QBASE
 #define SRBD_K3_QBASE 1
 #endif
@@ -138,6 +141,12 @@ __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc)
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
   const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc));
+}
+// L2 prefetch of one 128-byte line per lane (no destination register): issued TWO stages ahead of the sweeps, so that
+// the register prefetches and cp.async copies of the next stage (issued one stage ahead) find their lines in L2
+// instead of waiting for HBM at the top of the following stage (11 % of the stall samples of v13 were exactly that)
+__device__ __forceinline__ void l2_prefetch(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p));
 }
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
@@ -266,6 +275,19 @@ struct SrbdSolver {
     cp_async16(dst + 64, src + 64);
     if (lane < 2) cp_async16(dst + 128, src + 128);
   }
+  // Lines of stage k that a sweep will read: the vector part of the workspace block (doubles 0..299), optionally
+  // P_{k+1} (300..443) and the factor panels / P rb (444..761), the BAbt record and the compact stage record.
+  // Every lane takes one line per instruction (the blocks are not line aligned: one spare line each).
+  __device__ __forceinline__ void prefetch_L2(int k, bool with_P, bool with_F, bool with_rec) const {
+#if SRBD_K3_L2PF
+    const double* w = ws(k, 0) + 16 * lane;
+    if ((SRBD_K3_L2PF & 1) && lane < 20) l2_prefetch(w);                       // vectors: 2400 B = 19 (+1) lines
+    if ((SRBD_K3_L2PF & 2) && with_P && lane < 10) l2_prefetch(w + 304);       // P: 1152 B
+    if ((SRBD_K3_L2PF & 2) && with_F && lane < 21) l2_prefetch(w + 448);       // panels + P rb: 2544 B = 20 (+1) lines
+    if ((SRBD_K3_L2PF & 4) && lane < 22) l2_prefetch(gBAbtL(k) + 14 * lane);   // BAbt: 2688 B = 21 (+1) lines
+    if ((SRBD_K3_L2PF & 8) && with_rec && lane < 12) l2_prefetch(gRecL(k) + 14 * lane);  // stage record: 12 lines
+#endif
+  }
   __device__ __forceinline__ void set_bufs(int b) {
     sG = sm + (b ? v2::wG1 : v2::wG0);
     sF = sm + (b ? v2::wF1 : v2::wF0);
@@ -361,6 +383,7 @@ struct SrbdSolver {
         prefetch_G(k - 1, b ^ 1);
         prefetch_Rblk(k - 1, b ^ 1);
         nxt = load_s1(k - 1);
+        if (k > 1) prefetch_L2(k - 2, false, false, true);
       }
       double* gbuf = sm + (b ? v2::wqx : v2::wQX);
       double* Gbuf = sm + (b ? v2::wSG : v2::wSX);
@@ -633,6 +656,7 @@ struct SrbdSolver {
         prefetch_G(k - 1, b ^ 1);
         prefetch_F(k - 1, b ^ 1, false);
         nxt = load_s4(k - 1);
+        if (k > 1) prefetch_L2(k - 2, false, true, false);
       }
       double* gbuf = sm + (b ? v2::wqx : v2::wQX);
       // ---- row-per-lane: res_m of this solve and gamma ------------------------------------------------------------
@@ -751,6 +775,7 @@ struct SrbdSolver {
         prefetch_G(k + 1, b ^ 1);
         prefetch_F(k + 1, b ^ 1, fin);
         nxt = load_s2(k + 1);
+        if (k + 2 < N) prefetch_L2(k + 2, fin, true, false);
       }
       double* ubuf = sm + (b ? v2::wSX : v2::wSG);
       // ---- x+ = G^T [u; x] + rb: the x part first (it does not wait for u);  t = Ls^T x + lv ----------------------------
@@ -930,6 +955,7 @@ struct SrbdSolver {
         if (k + 1 < N) prefetch_G(k + 1, b ^ 1, 7);
         prefetch_R(k + 1, b ^ 1);
         raw = load_s6(k + 1, do_update);
+        if (k + 2 < N) prefetch_L2(k + 2, false, false, true);
       }
       double* zb = sm + (b ? v2::wSX : v2::wSG);       // z (24)
       double* lb = sm + (b ? v2::wqx : v2::wQX);       // lam (24)
@@ -1069,8 +1095,8 @@ struct SrbdSolver {
     }
     const int nc_all = warp_sum_i(nmask);
     // No active row at all (BARRIER_SOFT assembly masks every row): d_ocp_qp_fact_solve_kkt_unconstr, ONE Riccati
-    // factorization and solve on the QP itself, iter = 0 (oracle/ocp_qp_ipm.c:668).  It runs through the same call
-    // sites as an IPM iteration: at z = 0, pi = 0 the residuals are (g, b) themselves, Gamma = gamma = 0, the full
+    // factorization and solve on the QP itself, iter = 0 (hpipm_d_ocp_qp_kkt.h:54; the reference's own test expects
+    // iter == 0, hpipm-cpp/test/ocp_qp_ipm_solver.cpp:56).  It runs through the same call sites as an IPM iteration: at z = 0, pi = 0 the residuals are (g, b) themselves, Gamma = gamma = 0, the full
     // step lands on the solution and the second residual pass evaluates it.
     const bool unc = nc_all == 0;
     const int nc_mask = unc ? 1 : nc_all;
