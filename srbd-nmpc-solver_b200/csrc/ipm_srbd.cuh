@@ -83,7 +83,7 @@ namespace v2 {
 #define SRBD_K3_UNROLL_RES 0
 #endif
 #ifndef SRBD_K3_L2PF
-#define SRBD_K3_L2PF 15   // bit 0: vectors, 1: P / factor panels, 2: BAbt record, 3: stage record
+#define SRBD_K3_L2PF 0    // off (measured slower); bit 0: vectors, 1: P / factor panels, 2: BAbt record, 3: stage record
 #endif
 #ifndef SRBD_K3_QBASE
 #define SRBD_K3_QBASE 1
@@ -142,9 +142,10 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) 
   const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc));
 }
-// L2 prefetch of one 128-byte line per lane (no destination register): issued TWO stages ahead of the sweeps, so that
-// the register prefetches and cp.async copies of the next stage (issued one stage ahead) find their lines in L2
-// instead of waiting for HBM at the top of the following stage (11 % of the stall samples of v13 were exactly that)
+// L2 prefetch of one 128-byte line per lane (no destination register), two stages ahead of the sweeps, meant to let the
+// register prefetches and cp.async copies of the next stage find their lines in L2 (11 % of the stall samples of v13 are
+// the loop-top wait for them).  EXPERIMENT, off by default: with 1776 QPs in flight the working set is twice the L2,
+// and the deeper prefetch evicts more than it saves (519-551 k against 567 k solves/s)
 __device__ __forceinline__ void l2_prefetch(const void* p) {
   asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p));
 }
