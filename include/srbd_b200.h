@@ -207,7 +207,9 @@ typedef enum srbd_buf {
   SRBD_BUF_D = 16,
   SRBD_BUF_DMASK = 17,
   SRBD_BUF_DEFECT = 18,  /* [B][N][12] shooting defect f (SRBD_model.cpp:189-197) */
-  SRBD_BUF_COUNT = 19
+  SRBD_BUF_STAGE_REC = 19, /* [B][N+1][192] compact stage records written by srbd_assemble next to the dense ones:
+                              [R tile 96 | pad 12 | gradient row 24 | pad 12 | lg 24 | lg mask 24], see DESIGN.md section 3 */
+  SRBD_BUF_COUNT = 20
 } srbd_buf;
 
 /* ---- defaults ------------------------------------------------------------------------------ */

@@ -37,7 +37,7 @@ dump = {}
 for mode, name in ((C.SRBD_HARD_INEQ, "hard"), (C.SRBD_BARRIER_SOFT, "soft")):
     ctx.linearize(); ctx.assemble(mode); ctx.sync()
     # buffer ids of include/srbd_b200.h (SRBD_BUF_BABT .. SRBD_BUF_DEFECT)
-    for buf, bn in ((13, "babt"), (14, "rsq"), (15, "dct"), (16, "d"), (17, "dmask"), (18, "defect")):
+    for buf, bn in ((13, "babt"), (14, "rsq"), (15, "dct"), (16, "d"), (17, "dmask"), (18, "defect"), (19, "stage_rec")):
         n = 512  # QPs kept in the dump
         t = ctx.device_tensor(buf)
         dump[name + "_" + bn] = t.reshape(B, -1)[:n].cpu().numpy().copy()

@@ -319,6 +319,7 @@ int srbd_ctx_device_ptr(srbd_ctx* ctx, int buf, void** ptr, size_t* bytes) {
     case SRBD_BUF_D: p = ctx->d_d; n = B * S * L.d_stride * D; break;
     case SRBD_BUF_DMASK: p = ctx->d_dmask; n = B * S * L.d_stride * D; break;
     case SRBD_BUF_DEFECT: p = ctx->d_defect; n = B * N * 12 * D; break;
+    case SRBD_BUF_STAGE_REC: p = ctx->d_srec; n = ctx->d_srec ? B * S * kSrec * D : 0; break;
     default: return fail(ctx, SRBD_ERR_ARG, "unknown buffer id");
   }
   if (!p) return fail(ctx, SRBD_ERR_STATE, "buffer not allocated for these dimensions");

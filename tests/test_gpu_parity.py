@@ -441,3 +441,35 @@ def test_srbd_ragged_batches_and_tiny_horizons(pkg, orc, N, B):
     for k in ("x", "u", "t"):
         assert relerr(sol[k], ref[k]).max() <= 5e-9, (k, relerr(sol[k], ref[k]).max())
     assert bs["solves"] == B and bs["iter_sum"] == int(st["iter"].sum())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1])
+def test_stage_record_repeats_the_dense_records(pkg, mode):
+    """K2's compact stage record (what the SRBD K3 variant reads: include/srbd_b200.h SRBD_BUF_STAGE_REC) must be a
+    bit-exact excerpt of the dense panel-major records the generic kernel and the getters use: the lower 12 x 12
+    block of rows 0..11 of RSQrq as panel prefixes, its gradient row n, and lg / lg_mask — at the first, the
+    interior and the last stage, in both assemble modes."""
+    B, N = 96, 20
+    w = perturbed_workload(pkg, B, N, "gait")
+    with make_ctx(pkg, B, N) as ctx:
+        ctx.upload_traj(w["x"], w["u"], w["xref"], w["x0"], w["contact"])
+        ctx.linearize(); ctx.assemble(mode); ctx.sync()
+        rec = ctx.device_tensor(19).reshape(B, N + 1, 192).cpu().numpy()
+        rsq = ctx.device_tensor(14).reshape(B, N + 1, 28 * 24).cpu().numpy()
+        d = ctx.device_tensor(16).reshape(B, N + 1, 48).cpu().numpy()
+        dm = ctx.device_tensor(17).reshape(B, N + 1, 48).cpu().numpy()
+    pm = lambda i, j: (i // 4) * 96 + 4 * j + (i % 4)      # panel-major index in the 28 x 24 record (cn = 24)
+    base = (0, 16, 48)
+    for i in range(12):
+        for j in range(4 * (i // 4) + 4):                    # panel prefix: columns 0 .. 4 (i / 4) + 3
+            assert np.array_equal(rec[:, :, base[i // 4] + 4 * j + (i % 4)], rsq[:, :, pm(i, j)]), (i, j)
+    for k in range(N + 1):
+        n = (12 if k < N else 0) + (12 if k > 0 else 0)
+        for j in range(n):
+            assert np.array_equal(rec[:, k, 108 + j], rsq[:, k, pm(n, j)]), (k, j)
+    assert np.array_equal(rec[:, :, 144:168], d[:, :, :24]) and np.array_equal(rec[:, :N, 168:192], dm[:, :N, :24])
+    if mode == 1:
+        assert (rec[:, :N, 168:192].sum(axis=2) == 20).all()   # 20 hard rows per stage (NMPC_solver.cpp:301)
+    else:
+        assert (rec[:, :, 168:192] == 0).all()
