@@ -160,6 +160,34 @@ def emit_json(line):
         os.write(_JSON_FD, data)
 
 
+def latency_leg(pkg, reps=300):
+    """The second half of BASELINE.json's metric ("... ; p50 solve latency"), config 5: ONE SRBD QP, N=50, all stance,
+    HARD_INEQ, solved host memory -> host memory through srbd_solve_host (K1 + K2 + K3 + copies), 10 warm-ups, then
+    `reps` back-to-back calls timed on the host clock (the call is synchronous)."""
+    from srbd_nmpc_solver_b200.binding import make_dims
+    N = 50
+    w = pkg.workload.srbd_batch(1, N=N, contact_mode="stance")
+    c = pkg.Context(1, make_dims(N=N))
+    c.set_model(pkg.default_model_params(N))
+    c.set_ipm_args(pkg.default_ipm_args(**dict(SETTINGS, tol_stat=1e-6)))
+    sx, su = np.zeros((1, N + 1, 12)), np.zeros((1, N, 12))
+    it, stt = np.zeros(1, dtype=np.int32), np.zeros(1, dtype=np.int32)
+    mode = pkg.capi.SRBD_HARD_INEQ
+    for _ in range(10):
+        c.solve_host(mode, w["x"], w["u"], w["xref"], w["x0"], w["contact"], sx, su, it, stt)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        c.solve_host(mode, w["x"], w["u"], w["xref"], w["x0"], w["contact"], sx, su, it, stt)
+        ts.append(time.perf_counter() - t0)
+    c.close()
+    ts = np.array(ts) * 1e6
+    return {"p50_us": float(np.percentile(ts, 50)), "p99_us": float(np.percentile(ts, 99)), "calls": reps,
+            "ipm_iterations": int(it[0]), "status": int(stt[0]),
+            "workload": "BASELINE config 5: one SRBD QP, N=50, all stance, HARD_INEQ, tol 1e-8 (tol_stat 1e-6), "
+                        "host->host through srbd_solve_host on rank 0"}
+
+
 def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
@@ -171,6 +199,7 @@ def main():
     ap.add_argument("--contact", default="gait", choices=["gait", "stance"])
     ap.add_argument("--cpu-sample", type=int, default=8192, help="QPs per step of the CPU baseline / reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true", help="skip the single-instance latency leg (BASELINE config 5)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -346,6 +375,7 @@ def main():
                             "sample": f"first {args.cpu_sample} QPs of rank 0's shard, one pass ({dt:.1f} s), OpenMP over QPs; "
                                       "CPU oracle port (reference HPIPM/BLASFEO/Eigen not buildable offline)",
                             "iteration_counts_equal_gpu": same}
+        latency = None if args.no_latency else latency_leg(pkg)
         it = st["iter"]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -353,14 +383,14 @@ def main():
                 "config": {"workload": "BASELINE config 3: 65536 SRBD QPs per GPU, N=20, randomized contact schedules, "
                                        "hard friction-cone/force-box rows (HARD_INEQ), full IPM to tol 1e-8, ric_alg=0",
                            "qps_per_gpu": B, "global_batch": world * B, "horizon": HORIZON, "contact": args.contact,
-                           "l2": "inputs larger than L2 (packed QP data 18.5 GB per step, trajectories 0.4 GB)",
+                           "l2": "inputs larger than L2 (packed QP data 20.6 GB per step, trajectories 0.4 GB)",
                            "parallelism": f"dp{world} (independent QPs, no data-path collective)"},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms_max, "steps": 2 * args.e2e_steps,
                         "how": "two contexts / CUDA streams take the steps alternately (srbd_solve_host_async + srbd_wait): "
                                "copies of one step overlap the kernels of the other"},
-                "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "latency": latency,
                 "ipm": {"iter_mean": float(it.mean()), "iter_min": int(it.min()), "iter_max": int(it.max()),
                         "status_counts_all_ranks": stats_all["status_count"], "solves_all_ranks": stats_all["solves"],
                         "iter_sum_all_ranks": stats_all["iter_sum"], "res_max_all_ranks": stats_all["res_max"]}}

@@ -134,6 +134,24 @@ static_assert(kWarpShared % 16 == 0 && kCtaShared % 16 == 0, "tiles must start o
 constexpr int kSmemBytes = (kCtaShared + kWarps * kWarpShared) * 8;
 }  // namespace v2
 
+// load of a workspace double (private to the warp, re-read once per sweep: no reuse in L1).  SRBD_K3_WSLD selects the
+// cache operator for A/B runs: 0 = ld.global.cg (L2 only), 1 = L1::no_allocate, 2 = default (.ca), 3 = .cs (streaming)
+#ifndef SRBD_K3_WSLD
+#define SRBD_K3_WSLD 0
+#endif
+__device__ __forceinline__ double ws_ld(const double* p) {
+#if SRBD_K3_WSLD == 0
+  return __ldcg(p);
+#elif SRBD_K3_WSLD == 1
+  double v;
+  asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];\n" : "=d"(v) : "l"(p));
+  return v;
+#elif SRBD_K3_WSLD == 2
+  return *reinterpret_cast<const volatile double*>(p);
+#else
+  return __ldcs(p);
+#endif
+}
 __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
   const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
@@ -304,12 +322,12 @@ struct SrbdSolver {
   struct S1v { double mk, lam, t, rm, rd, rg[6], rb[3]; };
   __device__ __forceinline__ S1v load_s1(int k) const {
     S1v v;
-    v.mk = __ldg(gMaskL(k)); v.lam = __ldcg(wsc(k, v2::oLAM)); v.t = __ldcg(wsc(k, v2::oT));
-    v.rm = __ldcg(wsc(k, v2::oRM)); v.rd = __ldcg(wsc(k, v2::oRD));
+    v.mk = __ldg(gMaskL(k)); v.lam = ws_ld(wsc(k, v2::oLAM)); v.t = ws_ld(wsc(k, v2::oT));
+    v.rm = ws_ld(wsc(k, v2::oRM)); v.rd = ws_ld(wsc(k, v2::oRD));
 #pragma unroll
-    for (int j = 0; j < 6; ++j) v.rg[j] = __ldcg(wsf(k, v2::oRG) + 4 * j);
+    for (int j = 0; j < 6; ++j) v.rg[j] = ws_ld(wsf(k, v2::oRG) + 4 * j);
 #pragma unroll
-    for (int j = 0; j < 3; ++j) v.rb[j] = __ldcg(wsf(k, v2::oRB) + 4 * j);
+    for (int j = 0; j < 3; ++j) v.rb[j] = ws_ld(wsf(k, v2::oRB) + 4 * j);
     return v;
   }
   // 1/sqrt(x) of a positive pivot: MUFU.RSQ64H seed (rel. error < 2^-20) + one third-order step
@@ -362,7 +380,7 @@ struct SrbdSolver {
         }
       }
 #pragma unroll
-      for (int kt = 0; kt < 3; ++kt) pk[kt] = __ldcg(wsf(N, v2::oRG) + 4 * kt);
+      for (int kt = 0; kt < 3; ++kt) pk[kt] = ws_ld(wsf(N, v2::oRG) + 4 * kt);
       __syncwarp();
       for (int e = lane; e < 144; e += 32) ws(N - 1, v2::oP)[e] = sP[e];  // P_k lives in block k-1 (next to FT_{k-1})
       if (r == 0) {
@@ -618,13 +636,13 @@ struct SrbdSolver {
   struct S4v { double mk, rmb, dt, dlam, lam, t, rd, rg[6], prb[3]; };
   __device__ __forceinline__ S4v load_s4(int k) const {
     S4v v;
-    v.mk = __ldg(gMaskL(k)); v.rmb = __ldcg(wsc(k, v2::oRMB)); v.dt = __ldcg(wsc(k, v2::oDT));
-    v.dlam = __ldcg(wsc(k, v2::oDLAM)); v.lam = __ldcg(wsc(k, v2::oLAM)); v.t = __ldcg(wsc(k, v2::oT));
-    v.rd = __ldcg(wsc(k, v2::oRD));
+    v.mk = __ldg(gMaskL(k)); v.rmb = ws_ld(wsc(k, v2::oRMB)); v.dt = ws_ld(wsc(k, v2::oDT));
+    v.dlam = ws_ld(wsc(k, v2::oDLAM)); v.lam = ws_ld(wsc(k, v2::oLAM)); v.t = ws_ld(wsc(k, v2::oT));
+    v.rd = ws_ld(wsc(k, v2::oRD));
 #pragma unroll
-    for (int j = 0; j < 6; ++j) v.rg[j] = __ldcg(wsf(k, v2::oRG) + 4 * j);
+    for (int j = 0; j < 6; ++j) v.rg[j] = ws_ld(wsf(k, v2::oRG) + 4 * j);
 #pragma unroll
-    for (int j = 0; j < 3; ++j) v.prb[j] = __ldcg(wsf(k, v2::oPRB) + 4 * j);
+    for (int j = 0; j < 3; ++j) v.prb[j] = ws_ld(wsf(k, v2::oPRB) + 4 * j);
     return v;
   }
   __device__ __forceinline__ void sweep_backvec(int mode, double sm_) {
@@ -636,7 +654,7 @@ struct SrbdSolver {
     const int oDt = t * 12 + pi;                                      // Ac[4kt+t][8I+pi]     : + 8 I + 48 kt
     double pk[3];
 #pragma unroll
-    for (int kt = 0; kt < 3; ++kt) pk[kt] = __ldcg(wsf(N, v2::oRG) + 4 * kt);
+    for (int kt = 0; kt < 3; ++kt) pk[kt] = ws_ld(wsf(N, v2::oRG) + 4 * kt);
     if (r == 0) {
 #pragma unroll
       for (int kt = 0; kt < 3; ++kt) wsf(N, v2::oPV)[4 * kt] = pk[kt];
@@ -735,12 +753,12 @@ struct SrbdSolver {
   struct S2v { double mk, t, lam, rd, rm, rb[3], pv[3]; };
   __device__ __forceinline__ S2v load_s2(int k) const {
     S2v v;
-    v.mk = __ldg(gMaskL(k)); v.t = __ldcg(wsc(k, v2::oT)); v.lam = __ldcg(wsc(k, v2::oLAM));
-    v.rd = __ldcg(wsc(k, v2::oRD)); v.rm = __ldcg(wsc(k, v2::oRM));
+    v.mk = __ldg(gMaskL(k)); v.t = ws_ld(wsc(k, v2::oT)); v.lam = ws_ld(wsc(k, v2::oLAM));
+    v.rd = ws_ld(wsc(k, v2::oRD)); v.rm = ws_ld(wsc(k, v2::oRM));
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      v.rb[j] = __ldcg(wsf(k, v2::oRB) + 4 * j);
-      v.pv[j] = __ldcg(wsf(k + 1, v2::oPV) + 4 * j);
+      v.rb[j] = ws_ld(wsf(k, v2::oRB) + 4 * j);
+      v.pv[j] = ws_ld(wsf(k + 1, v2::oPV) + 4 * j);
     }
     return v;
   }
@@ -880,21 +898,21 @@ struct SrbdSolver {
   struct S6raw { double z, pi, lam, t, xn, lo, mk, dz, dpi, dlam, dt, dxn; };
   __device__ __forceinline__ S6raw load_s6(int k, bool do_update) const {
     S6raw v;
-    v.z = __ldcg(wsc(k, v2::oZ));
+    v.z = ws_ld(wsc(k, v2::oZ));
     v.pi = 0.0; v.lam = 0.0; v.t = 1.0; v.xn = 0.0; v.lo = 0.0; v.mk = 0.0;
     v.dz = 0.0; v.dpi = 0.0; v.dlam = 0.0; v.dt = 0.0; v.dxn = 0.0;
     const int xo = (k + 1 < N ? 12 : 0);
     if (k < N) {
-      v.pi = __ldcg(wsc(k, v2::oPI)); v.lam = __ldcg(wsc(k, v2::oLAM)); v.t = __ldcg(wsc(k, v2::oT));
-      v.xn = __ldcg(wsc(k + 1, v2::oZ) + xo); v.lo = __ldg(gDL(k)); v.mk = __ldg(gMaskL(k));
+      v.pi = ws_ld(wsc(k, v2::oPI)); v.lam = ws_ld(wsc(k, v2::oLAM)); v.t = ws_ld(wsc(k, v2::oT));
+      v.xn = ws_ld(wsc(k + 1, v2::oZ) + xo); v.lo = __ldg(gDL(k)); v.mk = __ldg(gMaskL(k));
     }
     if (do_update) {
-      v.dz = __ldcg(wsc(k, v2::oDZ));
+      v.dz = ws_ld(wsc(k, v2::oDZ));
       if (k < N) {
-        v.dpi = __ldcg(wsc(k, v2::oDPI));
-        v.dxn = __ldcg(wsc(k + 1, v2::oDZ) + xo);
-        v.dt = __ldcg(wsc(k, v2::oDT));
-        v.dlam = __ldcg(wsc(k, v2::oDLAM));
+        v.dpi = ws_ld(wsc(k, v2::oDPI));
+        v.dxn = ws_ld(wsc(k + 1, v2::oDZ) + xo);
+        v.dt = ws_ld(wsc(k, v2::oDT));
+        v.dlam = ws_ld(wsc(k, v2::oDLAM));
       }
     }
     return v;
@@ -1166,11 +1184,11 @@ struct SrbdSolver {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int k = k0 + j <= N ? k0 + j : N, nu = k < N ? 12 : 0, kk_ = k < N ? k : N - 1;
-          vx[j] = k == 0 ? __ldg(p.x0 + (size_t)q * 12 + l12) : __ldcg(ws(k, v2::oZ) + nu + l12);
-          vp[j] = __ldcg(ws(k > 0 ? k - 1 : 0, v2::oPI) + l12);
-          vu[j] = __ldcg(ws(kk_, v2::oZ) + l12);
-          vl[j] = __ldcg(wsc(kk_, v2::oLAM));
-          vt[j] = __ldcg(wsc(kk_, v2::oT));
+          vx[j] = k == 0 ? __ldg(p.x0 + (size_t)q * 12 + l12) : ws_ld(ws(k, v2::oZ) + nu + l12);
+          vp[j] = ws_ld(ws(k > 0 ? k - 1 : 0, v2::oPI) + l12);
+          vu[j] = ws_ld(ws(kk_, v2::oZ) + l12);
+          vl[j] = ws_ld(wsc(kk_, v2::oLAM));
+          vt[j] = ws_ld(wsc(kk_, v2::oT));
           if (unc) { vl[j] = 0.0; vt[j] = 0.0; }  // the unconstrained solve reports lam = t = 0 on the masked rows
         }
 #pragma unroll
