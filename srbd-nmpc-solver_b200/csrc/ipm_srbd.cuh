@@ -68,8 +68,9 @@ namespace v2 {
 #ifndef SRBD_K3_MIN_CTAS
 #define SRBD_K3_MIN_CTAS 2    // resident CTAs per SM the register allocation is bounded for
 #endif
+// ---- compile-time knobs of the A/B experiments (defaults = what measured fastest) ------------
 // stage loops unrolled by two: the loop-carried copies of the register-prefetched vectors (cur = nxt, 22-32 moves
-// per stage) and the buffer selects disappear
+// per stage) and the buffer selects disappear, but every unrolled sweep costs 5 % (instruction cache): off
 #ifndef SRBD_K3_UNROLL_FAC
 #define SRBD_K3_UNROLL_FAC 0
 #endif
@@ -85,6 +86,8 @@ namespace v2 {
 #ifndef SRBD_K3_L2PF
 #define SRBD_K3_L2PF 0    // off (measured slower); bit 0: vectors, 1: P / factor panels, 2: BAbt record, 3: stage record
 #endif
+// QBASE: per-QP base pointers of the packed QP data held opaque (+1 %).  WBASE: the per-lane workspace bases as well
+// (fewer address instructions, but 116 B of spills: -3 %)
 #ifndef SRBD_K3_QBASE
 #define SRBD_K3_QBASE 1
 #endif
@@ -135,7 +138,8 @@ constexpr int kSmemBytes = (kCtaShared + kWarps * kWarpShared) * 8;
 }  // namespace v2
 
 // load of a workspace double (private to the warp, re-read once per sweep: no reuse in L1).  SRBD_K3_WSLD selects the
-// cache operator for A/B runs: 0 = ld.global.cg (L2 only), 1 = L1::no_allocate, 2 = default (.ca), 3 = .cs (streaming)
+// cache operator for A/B runs: 0 = ld.global.cg (L2 only), 1 = L1::no_allocate, 2 = default (.ca), 3 = .cs (streaming):
+// 574 / 567 / 578 / 574 k solves/s, i.e. no measurable effect
 #ifndef SRBD_K3_WSLD
 #define SRBD_K3_WSLD 0
 #endif
