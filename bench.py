@@ -104,7 +104,14 @@ def cpu_reference_run(pkg, batch, threads=0, seed_start=0, contact="gait"):
     from oracle import oracle as orc
     w = pkg.workload.srbd_batch(batch, N=HORIZON, contact_mode=contact, start=seed_start)
     m, a = orc.model_params(HORIZON), orc.ipm_args(**SETTINGS)
-    nthr = orc.num_threads() if threads <= 0 else threads
+    # all the host threads this process may use: torchrun exports OMP_NUM_THREADS=1 to its workers, which would make
+    # the reported CPU baseline a single-core number at N > 1
+    if threads <= 0:
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            threads = os.cpu_count() or 1
+    nthr = threads
     t0 = time.perf_counter()
     out = orc.pipeline(m, a, HORIZON, pkg.capi.SRBD_HARD_INEQ, w["x"], w["u"], w["xref"], w["x0"], w["contact"],
                        threads=nthr, duals=False)
