@@ -275,7 +275,10 @@ __host__ __device__ __forceinline__ double babt_elem(const double* c, int i, int
   return fma(t.mul, c[t.src], t.add);
 }
 
-__global__ void __launch_bounds__(kLinThreads) linearize_kernel(const LinParams p, const ModelDev* __restrict__ md) {
+#ifndef SRBD_K1_MIN_CTAS
+#define SRBD_K1_MIN_CTAS 1   // resident CTAs per SM the register allocation of K1 is bounded for (A/B knob)
+#endif
+__global__ void __launch_bounds__(kLinThreads, SRBD_K1_MIN_CTAS) linearize_kernel(const LinParams p, const ModelDev* __restrict__ md) {
   __shared__ double sc[kLinThreads][kLinCompact + 1];
   __shared__ srbd_model_params sm;
   {
