@@ -14,6 +14,7 @@ from oracle import oracle as orc
 from srbd_nmpc_solver_b200.binding import make_dims
 shards = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 per = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
+contact = sys.argv[3] if len(sys.argv) > 3 else "gait"   # "gait": config 3, "stance": config 2
 N = 20
 S = dict(iter_max=30, alpha_min=1e-8, mu0=1e2, tol_stat=1e-8, tol_eq=1e-8, tol_ineq=1e-8, tol_comp=1e-8,
          reg_prim=1e-12, warm_start=0, pred_corr=1, ric_alg=0, split_step=1)
@@ -25,7 +26,7 @@ def rel(a, b):
     return np.linalg.norm(a - b, axis=1) / np.maximum(np.linalg.norm(b, axis=1), 1e-300)
 
 
-out = dict(config="BASELINE config 3, N=20, gait, HARD_INEQ, tol 1e-8", shards=[])
+out = dict(config="BASELINE config %s, N=20, %s, HARD_INEQ, tol 1e-8" % ("3" if contact == "gait" else "2", contact), shards=[])
 ctx = pkg.Context(per)
 ctx.set_model(pkg.default_model_params(N)); ctx.set_ipm_args(pkg.default_ipm_args(**S))
 tot = dict(qps=0, iter_mismatch=0, status_mismatch=0, gpu_not_converged=0, cpu_not_converged=0)
@@ -33,7 +34,7 @@ worst = dict(x=0.0, u=0.0, t=0.0)
 worst_id = dict(x=0.0, u=0.0, t=0.0)
 for s in range(shards):
     start = 1_000_000 + s * per          # QP indices outside every other test's / bench's range
-    w = pkg.workload.srbd_batch(per, N=N, contact_mode="gait", start=start)
+    w = pkg.workload.srbd_batch(per, N=N, contact_mode=contact, start=start)
     ctx.upload_traj(w["x"], w["u"], w["xref"], w["x0"], w["contact"])
     ctx.sqp_iterate(HARD)
     sol = ctx.download_solution(want=("x", "u", "t"))

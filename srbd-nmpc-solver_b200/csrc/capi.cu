@@ -49,6 +49,7 @@ struct srbd_ctx {
   srbd_batch_stats* d_bstats = nullptr;
   double* d_ws = nullptr;
   double* d_ws2 = nullptr;   // workspace of the SRBD throughput variant of K3 (ipm_srbd.cuh)
+  int* d_retry = nullptr;    // [B + 1]: rescue list of the variant (QPs that did not converge) and, at [B], its length
   int grid2 = 0;
   int assembled_mode = -1;   // >= 0: the packed QP came from srbd_assemble (K2) in that mode
   int grid = 0, stat_rows = 0;
@@ -240,7 +241,7 @@ int srbd_ctx_destroy(srbd_ctx* ctx) {
                   ctx->d_dmask, ctx->d_raw0, ctx->d_x0, ctx->d_xinit, ctx->d_uinit, ctx->d_sol_x, ctx->d_sol_u,
                   ctx->d_sol_pi, ctx->d_sol_lam, ctx->d_sol_t, ctx->d_P, ctx->d_p, ctx->d_K, ctx->d_k,
                   ctx->d_stat, ctx->d_iter, ctx->d_status, ctx->d_counter, ctx->d_resmax, ctx->d_bstats, ctx->d_ws,
-                  ctx->d_ws2, ctx->d_srec};
+                  ctx->d_ws2, ctx->d_srec, ctx->d_retry};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (void* p : ctx->raw_dev)
@@ -544,6 +545,40 @@ int srbd_qp_upload(srbd_ctx* ctx, const srbd_qp_host* qp) {
   return SRBD_OK;
 }
 
+// K3, generic kernel (any hpipm::OcpQp data).  qlist / qcount (device): solve only those QPs and keep the batch
+// statistics accumulated so far (the rescue pass of the SRBD variant); null: the whole batch.
+static int launch_generic(srbd_ctx* ctx, const int* qlist, const int* qcount) {
+  const QpLayout& L = ctx->L;
+  const size_t B = ctx->B, S = L.N + 1, N = L.N;
+  if (ctx->export_ric && !ctx->d_P) {
+    CU(dalloc(&ctx->d_P, B * S * L.nx * L.nx)); CU(dalloc(&ctx->d_p, B * S * L.nx));
+    CU(dalloc(&ctx->d_K, B * N * L.nu * L.nx)); CU(dalloc(&ctx->d_k, B * N * L.nu));
+  }
+  if (ctx->export_stat && !ctx->d_stat) CU(dalloc(&ctx->d_stat, B * (size_t)ctx->stat_rows * SRBD_STAT_M));
+  IpmParams p{};
+  p.L = L; p.a = ctx->args; p.B = ctx->B;
+  p.babt = ctx->d_babt; p.rsq = ctx->d_rsq; p.dct = ctx->d_dct; p.d = ctx->d_d; p.dmask = ctx->d_dmask;
+  p.x_init = ctx->have_init ? ctx->d_xinit : nullptr;
+  p.u_init = ctx->have_init ? ctx->d_uinit : nullptr;
+  p.x0 = ctx->d_x0; p.raw0 = ctx->d_raw0; p.ws = ctx->d_ws; p.counter = ctx->d_counter;
+  p.sol_x = ctx->d_sol_x; p.sol_u = ctx->d_sol_u; p.sol_pi = ctx->d_sol_pi; p.sol_lam = ctx->d_sol_lam; p.sol_t = ctx->d_sol_t;
+  if (ctx->export_ric) { p.ric_P = ctx->d_P; p.ric_p = ctx->d_p; p.ric_K = ctx->d_K; p.ric_k = ctx->d_k; }
+  p.iter = ctx->d_iter; p.status = ctx->d_status; p.res_max = ctx->d_resmax;
+  p.stat = ctx->export_stat ? ctx->d_stat : nullptr;
+  p.stat_rows = ctx->stat_rows;
+  p.bstats = ctx->d_bstats;
+  CU(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
+  if (!qlist) CU(cudaMemsetAsync(ctx->d_bstats, 0, sizeof(srbd_batch_stats), ctx->stream));
+  p.qlist = qlist; p.qcount = qcount;
+  KernelChoice kc = pick_kernel(L);
+  const int grid = qlist ? (ctx->grid < ctx->sm_count ? ctx->grid : ctx->sm_count) : ctx->grid;  // a rescue list is short
+  kc.fn<<<grid, 32, 0, ctx->stream>>>(p);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  ctx->solved = true;
+  return SRBD_OK;
+}
+
 // K3 for QPs assembled by K2: the SRBD throughput variant (same algorithm as the generic kernel)
 static int solve_srbd_variant(srbd_ctx* ctx) {
   const QpLayout& L = ctx->L;
@@ -565,19 +600,30 @@ static int solve_srbd_variant(srbd_ctx* ctx) {
     if (g > need) g = need;
     ctx->grid2 = (int)g;
     CU(dalloc(&ctx->d_ws2, (size_t)ctx->grid2 * v2::kWarps * (size_t)(L.N + 1) * v2::kStage));
+    CU(dalloc(&ctx->d_retry, (size_t)ctx->B + 1));
   }
+  // Rescue pass: a QP on which the variant does not reach status 0 (about 1 in 1e5 sits on the rounding floor of the
+  // blocked triangular solves) is solved again by the generic kernel, whose row-by-row
+  // substitution is as accurate as the reference's trsv.  SRBD_K3_NO_RESCUE=1 switches it off (diagnosis).
+  const char* nr = std::getenv("SRBD_K3_NO_RESCUE");
+  const bool rescue = !(nr && nr[0] == '1');
   SrbdIpmParams p{};
   p.B = ctx->B; p.N = L.N; p.a = ctx->args;
   p.babt = ctx->d_babt; p.srec = ctx->d_srec; p.x0 = ctx->d_x0;
   p.model = ctx->d_model; p.ws = ctx->d_ws2; p.ws_size = (L.N + 1) * v2::kStage; p.counter = ctx->d_counter;
   p.sol_x = ctx->d_sol_x; p.sol_u = ctx->d_sol_u; p.sol_pi = ctx->d_sol_pi; p.sol_lam = ctx->d_sol_lam; p.sol_t = ctx->d_sol_t;
   p.iter = ctx->d_iter; p.status = ctx->d_status; p.res_max = ctx->d_resmax; p.bstats = ctx->d_bstats;
+  if (rescue) {
+    p.retry_list = ctx->d_retry; p.retry_count = ctx->d_retry + ctx->B;
+    CU(cudaMemsetAsync(ctx->d_retry + ctx->B, 0, sizeof(int), ctx->stream));
+  }
   CU(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
   CU(cudaMemsetAsync(ctx->d_bstats, 0, sizeof(srbd_batch_stats), ctx->stream));
   ipm_srbd_kernel<<<ctx->grid2, 32 * v2::kWarps, v2::kSmemBytes, ctx->stream>>>(p);
   ctx->launches++;
   CU(cudaGetLastError());
   ctx->solved = true;
+  if (rescue) return launch_generic(ctx, ctx->d_retry, ctx->d_retry + ctx->B);
   return SRBD_OK;
 }
 
@@ -605,33 +651,7 @@ int srbd_qp_solve(srbd_ctx* ctx) {
         !ctx->export_ric && !ctx->export_stat)
       return solve_srbd_variant(ctx);
   }
-  const QpLayout& L = ctx->L;
-  const size_t B = ctx->B, S = L.N + 1, N = L.N;
-  if (ctx->export_ric && !ctx->d_P) {
-    CU(dalloc(&ctx->d_P, B * S * L.nx * L.nx)); CU(dalloc(&ctx->d_p, B * S * L.nx));
-    CU(dalloc(&ctx->d_K, B * N * L.nu * L.nx)); CU(dalloc(&ctx->d_k, B * N * L.nu));
-  }
-  if (ctx->export_stat && !ctx->d_stat) CU(dalloc(&ctx->d_stat, B * (size_t)ctx->stat_rows * SRBD_STAT_M));
-  IpmParams p{};
-  p.L = L; p.a = ctx->args; p.B = ctx->B;
-  p.babt = ctx->d_babt; p.rsq = ctx->d_rsq; p.dct = ctx->d_dct; p.d = ctx->d_d; p.dmask = ctx->d_dmask;
-  p.x_init = ctx->have_init ? ctx->d_xinit : nullptr;
-  p.u_init = ctx->have_init ? ctx->d_uinit : nullptr;
-  p.x0 = ctx->d_x0; p.raw0 = ctx->d_raw0; p.ws = ctx->d_ws; p.counter = ctx->d_counter;
-  p.sol_x = ctx->d_sol_x; p.sol_u = ctx->d_sol_u; p.sol_pi = ctx->d_sol_pi; p.sol_lam = ctx->d_sol_lam; p.sol_t = ctx->d_sol_t;
-  if (ctx->export_ric) { p.ric_P = ctx->d_P; p.ric_p = ctx->d_p; p.ric_K = ctx->d_K; p.ric_k = ctx->d_k; }
-  p.iter = ctx->d_iter; p.status = ctx->d_status; p.res_max = ctx->d_resmax;
-  p.stat = ctx->export_stat ? ctx->d_stat : nullptr;
-  p.stat_rows = ctx->stat_rows;
-  p.bstats = ctx->d_bstats;
-  CU(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
-  CU(cudaMemsetAsync(ctx->d_bstats, 0, sizeof(srbd_batch_stats), ctx->stream));
-  KernelChoice kc = pick_kernel(L);
-  kc.fn<<<ctx->grid, 32, 0, ctx->stream>>>(p);
-  ctx->launches++;
-  CU(cudaGetLastError());
-  ctx->solved = true;
-  return SRBD_OK;
+  return launch_generic(ctx, nullptr, nullptr);
 }
 
 int srbd_download_solution(srbd_ctx* ctx, const srbd_sol_host* sol) {

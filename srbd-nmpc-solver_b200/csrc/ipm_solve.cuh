@@ -43,6 +43,9 @@ struct IpmParams {
   double* stat;  // [B][stat_rows][18] or null
   int stat_rows;
   srbd_batch_stats* bstats;
+  // optional work list: solve only the QPs qlist[0 .. *qcount) (the rescue pass behind the SRBD variant, capi.cu)
+  const int* qlist;
+  const int* qcount;
 };
 
 // compile-time dimension policy (loops unroll, index math folds) ...
@@ -1048,17 +1051,20 @@ __global__ void __launch_bounds__(32) ipm_solve_kernel(const IpmParams p) {
   __shared__ double smem[Solver<D>::kSmemDoubles];
   __shared__ int sidx[3 * kMaxNB];
   __shared__ int s_next;
+  if (p.qlist && *p.qcount == 0) return;  // empty rescue list (the usual case): nothing to set up
   Solver<D> S(p, smem, sidx);
   // per-CTA partial batch statistics (fused epilogue; one set of atomics per CTA at the end)
   long long it_sum = 0, solves = 0;
   int st_cnt[5] = {0, 0, 0, 0, 0};
   double rmax[4] = {0.0, 0.0, 0.0, 0.0};
+  const int n_work = p.qlist ? *p.qcount : p.B;
   for (;;) {
     if (threadIdx.x == 0) s_next = atomicAdd(p.counter, 1);
     __syncwarp();
-    const int qp = s_next;
+    const int idx = s_next;
     __syncwarp();
-    if (qp >= p.B) break;
+    if (idx >= n_work) break;
+    const int qp = p.qlist ? p.qlist[idx] : idx;
     S.solve_one(qp);
     if (threadIdx.x == 0) {
       const int it = p.iter[qp], st = p.status[qp];

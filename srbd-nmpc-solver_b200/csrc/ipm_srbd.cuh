@@ -59,6 +59,10 @@ struct SrbdIpmParams {
   int* status;
   double* res_max;
   srbd_batch_stats* bstats;
+  // rescue list (or null): QPs that end with status != 0 are appended here instead of being counted; capi.cu then
+  // runs the generic kernel (row-by-row substitution, no block inverses) on exactly those
+  int* retry_list;
+  int* retry_count;
 };
 
 namespace v2 {
@@ -1263,11 +1267,15 @@ __global__ void SRBD_K3_BOUNDS ipm_srbd_kernel(const SrbdIpmParams p) {
     S.solve_one(qp);
     if (lane == 0) {
       const int it = p.iter[qp], st = p.status[qp];
-      it_sum += it;
-      solves += 1;
-      st_cnt[st < 0 || st > 4 ? 4 : st] += 1;
-      atomicAdd((unsigned long long*)&p.bstats->iter_hist[it < SRBD_HIST_BINS ? it : SRBD_HIST_BINS - 1], 1ull);
-      for (int i = 0; i < 4; ++i) rmax[i] = fmax(rmax[i], p.res_max[4 * (size_t)qp + i]);
+      if (st != 0 && p.retry_list) {
+        p.retry_list[atomicAdd(p.retry_count, 1)] = qp;   // counted by the rescue pass
+      } else {
+        it_sum += it;
+        solves += 1;
+        st_cnt[st < 0 || st > 4 ? 4 : st] += 1;
+        atomicAdd((unsigned long long*)&p.bstats->iter_hist[it < SRBD_HIST_BINS ? it : SRBD_HIST_BINS - 1], 1ull);
+        for (int i = 0; i < 4; ++i) rmax[i] = fmax(rmax[i], p.res_max[4 * (size_t)qp + i]);
+      }
     }
   }
   if (lane == 0 && solves > 0) {

@@ -473,3 +473,35 @@ def test_stage_record_repeats_the_dense_records(pkg, mode):
         assert (rec[:, :N, 168:192].sum(axis=2) == 20).all()   # 20 hard rows per stage (NMPC_solver.cpp:301)
     else:
         assert (rec[:, :, 168:192] == 0).all()
+
+
+@pytest.mark.gpu
+def test_rescue_pass_matches_the_generic_kernel(pkg, orc, monkeypatch):
+    """QP 1007927 of the all-stance workload sits on the rounding floor of the SRBD variant's blocked triangular
+    solves (found by scripts/parity_sweep.py: the variant alone runs to iter_max with res_stat 8e-5, the generic kernel
+    and the oracle converge in 12 iterations).  With the rescue pass (default) the batch reports the generic kernel's
+    result for it — the oracle's iteration count and status — and the batch statistics count every QP exactly once."""
+    from srbd_nmpc_solver_b200.binding import make_dims
+    B, N, first = 64, 20, 1007927 - 20
+    w = pkg.workload.srbd_batch(B, N=N, contact_mode="stance", start=first)
+    res = {}
+    for rescue in ("1", "0"):
+        monkeypatch.setenv("SRBD_K3_NO_RESCUE", rescue)
+        with make_ctx(pkg, B, N) as ctx:
+            ctx.upload_traj(w["x"], w["u"], w["xref"], w["x0"], w["contact"])
+            ctx.sqp_iterate(1)
+            res[rescue] = (ctx.download_solution(want=("x", "u")), ctx.download_stats(), ctx.batch_stats())
+            if rescue == "0":
+                lin, qp = ctx.download_linearization(), ctx.download_qp()
+    arrays = dict(A=lin["A"], Bm=lin["Bm"], b=lin["b"], Q=qp["Q"], S=qp["S"], R=qp["R"], q=qp["q"], r=qp["r"],
+                  D=qp["D"], lg=qp["lg"], ug=np.zeros_like(qp["lg"]), lg_mask=qp["lg_mask"],
+                  ug_mask=np.zeros_like(qp["lg"]), x0=w["x0"] - w["x"][:, 0])
+    ref = orc.qp_solve(make_dims(N=N), orc.ipm_args(**SETTINGS), arrays, B, want=("x", "u"))
+    (_, st_raw, _), (sol, st, bs) = res["1"], res["0"]
+    assert st_raw["status"][20] == 1 and st_raw["iter"][20] == 30       # the variant alone: iter_max
+    assert (st["status"] == 0).all() and (ref["status"] == 0).all()
+    assert (st["iter"] == ref["iter"]).all(), (st["iter"], ref["iter"])
+    assert relerr(sol["x"], ref["x"]).max() <= 5e-9
+    others = np.arange(B) != 20
+    assert (st["iter"][others] == st_raw["iter"][others]).all()         # nothing else changed
+    assert bs["solves"] == B and bs["iter_sum"] == int(st["iter"].sum()) and bs["status_count"][0] == B
