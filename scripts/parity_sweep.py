@@ -63,6 +63,10 @@ for s in range(shards):
                frac_below_1e9={k: float((v <= 1e-9).mean()) for k, v in e.items()}, cpu_seconds=dt,
                identical=dict(iter_mismatch=int((st["iter"] != rid["iter"]).sum()),
                               status_mismatch=int((st["status"] != rid["status"]).sum()),
+                              cpu_status_counts=np.bincount(rid["status"], minlength=5).tolist(),
+                              status_pairs=[dict(qp=int(start + i), gpu=int(st["status"][i]), cpu=int(rid["status"][i]),
+                                                 gpu_iter=int(st["iter"][i]), cpu_iter=int(rid["iter"][i]))
+                                            for i in np.flatnonzero(st["status"] != rid["status"])],
                               mismatches=[dict(qp=int(start + i), gpu_iter=int(st["iter"][i]), cpu_iter=int(rid["iter"][i]),
                                                gpu_res_max=[float(v) for v in st["res_max"][i]],
                                                cpu_res_max=[float(v) for v in rid["res_max"][i]])
