@@ -602,9 +602,11 @@ static int solve_srbd_variant(srbd_ctx* ctx) {
     CU(dalloc(&ctx->d_ws2, (size_t)ctx->grid2 * v2::kWarps * (size_t)(L.N + 1) * v2::kStage));
     CU(dalloc(&ctx->d_retry, (size_t)ctx->B + 1));
   }
-  // Rescue pass: a QP on which the variant does not reach status 0 (about 1 in 1e5 sits on the rounding floor of the
-  // blocked triangular solves) is solved again by the generic kernel, whose row-by-row
-  // substitution is as accurate as the reference's trsv.  SRBD_K3_NO_RESCUE=1 switches it off (diagnosis).
+  // Rescue pass: a QP on which the variant runs to iter_max (about 1 in 1e5 sits on the rounding floor of the blocked
+  // triangular solves) is solved again by the generic kernel, whose row-by-row substitution is as
+  // accurate as the reference's trsv.  Only iter_max: the min-step / NaN endings seen on the long-horizon workload
+  // (config 4, N = 100) end the same way in the generic kernel, at 50 ms per one-warp solve.  SRBD_K3_NO_RESCUE=1
+  // switches the pass off (diagnosis).
   const char* nr = std::getenv("SRBD_K3_NO_RESCUE");
   const bool rescue = !(nr && nr[0] == '1');
   SrbdIpmParams p{};

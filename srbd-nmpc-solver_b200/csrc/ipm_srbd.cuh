@@ -59,8 +59,8 @@ struct SrbdIpmParams {
   int* status;
   double* res_max;
   srbd_batch_stats* bstats;
-  // rescue list (or null): QPs that end with status != 0 are appended here instead of being counted; capi.cu then
-  // runs the generic kernel (row-by-row substitution, no block inverses) on exactly those
+  // rescue list (or null): QPs that run to iter_max are appended here instead of being counted; capi.cu then runs
+  // the generic kernel (row-by-row substitution, no block inverses) on exactly those
   int* retry_list;
   int* retry_count;
 };
@@ -1267,7 +1267,7 @@ __global__ void SRBD_K3_BOUNDS ipm_srbd_kernel(const SrbdIpmParams p) {
     S.solve_one(qp);
     if (lane == 0) {
       const int it = p.iter[qp], st = p.status[qp];
-      if (st != 0 && p.retry_list) {
+      if (st == 1 && p.retry_list) {  // iter_max only: see capi.cu, solve_srbd_variant
         p.retry_list[atomicAdd(p.retry_count, 1)] = qp;   // counted by the rescue pass
       } else {
         it_sum += it;
