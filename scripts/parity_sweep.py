@@ -15,9 +15,11 @@ from srbd_nmpc_solver_b200.binding import make_dims
 shards = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 per = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
 contact = sys.argv[3] if len(sys.argv) > 3 else "gait"   # "gait": config 3, "stance": config 2
-N = 20
+N = int(sys.argv[4]) if len(sys.argv) > 4 else 20
 S = dict(iter_max=30, alpha_min=1e-8, mu0=1e2, tol_stat=1e-8, tol_eq=1e-8, tol_ineq=1e-8, tol_comp=1e-8,
          reg_prim=1e-12, warm_start=0, pred_corr=1, ric_alg=0, split_step=1)
+if N > 20:   # the long-horizon settings of BASELINE configs 4 / 5 (tests/test_gpu_parity.py::test_srbd_pipeline_other_horizons)
+    S.update(iter_max=50, tol_stat=1e-6)
 HARD = pkg.capi.SRBD_HARD_INEQ
 
 
@@ -26,8 +28,8 @@ def rel(a, b):
     return np.linalg.norm(a - b, axis=1) / np.maximum(np.linalg.norm(b, axis=1), 1e-300)
 
 
-out = dict(config="BASELINE config %s, N=20, %s, HARD_INEQ, tol 1e-8" % ("3" if contact == "gait" else "2", contact), shards=[])
-ctx = pkg.Context(per)
+out = dict(config="BASELINE config %s generator, N=%d, %s, HARD_INEQ, settings %s" % ("3" if contact == "gait" else "2", N, contact, S), shards=[])
+ctx = pkg.Context(per, make_dims(N=N))
 ctx.set_model(pkg.default_model_params(N)); ctx.set_ipm_args(pkg.default_ipm_args(**S))
 tot = dict(qps=0, iter_mismatch=0, status_mismatch=0, gpu_not_converged=0, cpu_not_converged=0)
 worst = dict(x=0.0, u=0.0, t=0.0)
