@@ -366,9 +366,16 @@ static void compute_res(W* w) {
   w->obj = obj;
 }
 
+/* Division by a Cholesky pivot in the triangular solves.  BLASFEO's potrf stores the INVERSE diagonal next to the
+ * factor (0 for a non-positive pivot) and its trsv / trsm kernels multiply by it (blasfeo_common.h: dA / use_dA), so a
+ * failed pivot zeroes the component instead of producing inf / nan; for a positive pivot this is the plain division
+ * (bit-identical to what the golden vectors pin).  At tol 1e-8 this matters for ~1 QP in 1e4..1e5: with mu ~ 1e-11 a
+ * pivot of the barrier-augmented Hessian can cancel to <= 0 in the last iteration (profiles/r1_v14_parity_sweep_*). */
+static inline double pdiv(double s, double d) { return d > 0.0 ? s / d : 0.0; }
+
 /* dense lower Cholesky of the leading nc columns of an (m x m, ld) symmetric matrix held in its lower
- * triangle, applied right-looking to all m rows (BLASFEO potrf_l_mn semantics).  Returns 0 on a
- * non-positive pivot (the pivot is then replaced by 0 like BLASFEO does, giving inf/nan downstream). */
+ * triangle, applied right-looking to all m rows (BLASFEO potrf_l_mn semantics).  A non-positive pivot is replaced
+ * by 0 and its column is scaled by 0, like BLASFEO does. */
 static void potrf_l_mn(int m, int nc, double* A, int ld) {
   for (int j = 0; j < nc; ++j) {
     double dj = A[j + ld * j];
@@ -525,7 +532,7 @@ static void kkt_solve(W* w, const srbd_ipm_args* a, int fact, int with_constr, c
       for (int i = 0; i < nuk; ++i) {
         double s = gt[i];
         for (int j = 0; j < i; ++j) s -= Lr[i + nu * j] * lv[j];
-        lv[i] = s / Lr[i + nu * i];
+        lv[i] = pdiv(s, Lr[i + nu * i]);
       }
       for (int i = 0; i < nxk; ++i) {
         double s = gt[nuk + i];
@@ -550,7 +557,7 @@ static void kkt_solve(W* w, const srbd_ipm_args* a, int fact, int with_constr, c
     for (int i = nuk - 1; i >= 0; --i) { /* u = -Lr^-T t */
       double s = t[i];
       for (int j = i + 1; j < nuk; ++j) s -= Lr[j + nu * i] * t[j];
-      t[i] = s / Lr[i + nu * i];
+      t[i] = pdiv(s, Lr[i + nu * i]);
     }
     for (int i = 0; i < nuk; ++i) z[i] = -t[i];
     if (k < N) {
@@ -830,7 +837,7 @@ static void write_outputs(W* w, const srbd_qp_dims* d, const srbd_ipm_args* a, c
       for (int i = nu - 1; i >= 0; --i) {
         double s = Ls[c + nx * i];
         for (int j = i + 1; j < nu; ++j) s -= Lr[j + nu * i] * Kbuf[j + nu * c];
-        Kbuf[i + nu * c] = s / Lr[i + nu * i];
+        Kbuf[i + nu * c] = pdiv(s, Lr[i + nu * i]);
       }
       for (int i = 0; i < nu; ++i) Kbuf[i + nu * c] = -Kbuf[i + nu * c];
     }
@@ -844,7 +851,7 @@ static void write_outputs(W* w, const srbd_qp_dims* d, const srbd_ipm_args* a, c
         for (int i = nu - 1; i >= 0; --i) {
           double s = lv[i];
           for (int j = i + 1; j < nu; ++j) s -= Lr[j + nu * i] * t[j];
-          t[i] = s / Lr[i + nu * i];
+          t[i] = pdiv(s, Lr[i + nu * i]);
         }
         for (int i = 0; i < nu; ++i) kk[i] = -t[i];
       } else { /* absolute form by the identity u = K x + k */
@@ -922,12 +929,12 @@ static void write_outputs(W* w, const srbd_qp_dims* d, const srbd_ipm_args* a, c
       for (int i = 0; i < nu; ++i) {
         double s = H0[i + nu * c];
         for (int j = 0; j < i; ++j) s -= Lr0[i + nu * j] * y[j];
-        y[i] = s / Lr0[i + nu * i];
+        y[i] = pdiv(s, Lr0[i + nu * i]);
       }
       for (int i = nu - 1; i >= 0; --i) {
         double s = y[i];
         for (int j = i + 1; j < nu; ++j) s -= Lr0[j + nu * i] * y[j];
-        y[i] = s / Lr0[i + nu * i];
+        y[i] = pdiv(s, Lr0[i + nu * i]);
       }
       for (int i = 0; i < nu; ++i) GH[i + nu * c] = y[i];
     }

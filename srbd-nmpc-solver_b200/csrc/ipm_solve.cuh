@@ -102,6 +102,10 @@ __device__ __forceinline__ int warp_sum_i(int v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
   return v;
 }
+// Division by a Cholesky pivot in the triangular solves: BLASFEO's trsv multiplies by the inverse diagonal that potrf
+// stored, which is 0 for a non-positive pivot (blasfeo_common.h: dA / use_dA) -- the component becomes 0 instead of
+// inf / nan.  For a positive pivot: the plain division.
+__device__ __forceinline__ double pivot_div(double s, double d) { return d > 0.0 ? s / d : 0.0; }
 // NaN-propagating inf-norm accumulate (fmax would swallow NaNs)
 __device__ __forceinline__ double amax_nan(double acc, double v) {
   const double a = fabs(v);
@@ -442,7 +446,7 @@ struct Solver {
           if (lane == i) {
             double acc = sg[i];
             for (int j = 0; j < i; ++j) acc -= sLi[i * LDI + j] * st[j];
-            acc = acc / sLi[i * LDI + i];
+            acc = pivot_div(acc, sLi[i * LDI + i]);
             st[i] = acc;
             wlv(k)[i] = acc;
           }
@@ -483,7 +487,7 @@ struct Solver {
         if (lane == i) {
           double acc = st[i];
           for (int j = i + 1; j < nu; ++j) acc -= sLi[j * LDI + i] * st[j];
-          st[i] = acc / sLi[i * LDI + i];
+          st[i] = pivot_div(acc, sLi[i * LDI + i]);
         }
         __syncwarp();
       }
