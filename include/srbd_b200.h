@@ -242,7 +242,7 @@ int srbd_upload_traj(srbd_ctx* ctx, const double* x, const double* u, const doub
                      const double* x0, const uint8_t* contact);
 int srbd_download_traj(srbd_ctx* ctx, double* x, double* u);
 int srbd_linearize(srbd_ctx* ctx);           /* K1: A,B,b,defect for every (QP, stage) */
-int srbd_assemble(srbd_ctx* ctx, int mode);  /* K2: packed RSQrq / DCt / d / masks */
+int srbd_assemble(srbd_ctx* ctx, int mode);  /* K2: packed RSQrq / DCt / d / masks + the compact stage records */
 int srbd_download_linearization(srbd_ctx* ctx, double* A, double* Bm, double* b, double* defect);
 /* unpack the packed stage records back to column-major hpipm-cpp fields (tests / facades) */
 int srbd_download_qp(srbd_ctx* ctx, double* Q, double* S, double* R, double* q, double* r,
@@ -250,7 +250,11 @@ int srbd_download_qp(srbd_ctx* ctx, double* Q, double* S, double* R, double* q, 
 
 /* ---- QP level (any dims up to the compiled maxima) ------------------------------------------- */
 int srbd_qp_upload(srbd_ctx* ctx, const srbd_qp_host* qp); /* H2D + pack (d_ocp_qp_set_all analog) */
-int srbd_qp_solve(srbd_ctx* ctx);                          /* K3: the whole IPM, one launch */
+/* K3: the whole IPM solve of every QP of the batch (d_ocp_qp_ipm_solve, hpipm_d_ocp_qp_ipm.h:238), asynchronous on
+ * the context's stream.  QPs assembled by srbd_assemble() go through the tensor-core variant (one launch) followed by
+ * the rescue launch of the generic kernel for the QPs that ran to iter_max (usually none);
+ * everything else (srbd_qp_upload data, warm start, Riccati / statistics exports) through the generic kernel. */
+int srbd_qp_solve(srbd_ctx* ctx);
 int srbd_download_solution(srbd_ctx* ctx, const srbd_sol_host* sol);
 int srbd_download_stats(srbd_ctx* ctx, const srbd_stats_host* st);
 int srbd_batch_stats_get(srbd_ctx* ctx, srbd_batch_stats* out);
