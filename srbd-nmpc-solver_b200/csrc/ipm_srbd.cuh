@@ -87,6 +87,9 @@ namespace v2 {
 #ifndef SRBD_K3_UNROLL_RES
 #define SRBD_K3_UNROLL_RES 0
 #endif
+#ifndef SRBD_K3_DUMMY_DMMA
+#define SRBD_K3_DUMMY_DMMA 0   // experiment only
+#endif
 #ifndef SRBD_K3_L2PF
 #define SRBD_K3_L2PF 0    // off (measured slower); bit 0: vectors, 1: P / factor panels, 2: BAbt record, 3: stage record
 #endif
@@ -716,6 +719,18 @@ struct SrbdSolver {
         dmma(c1[0], c1[1], tk[kt], sG[oG + 2 * v2::kGP + 16 * kt], c1[0], c1[1]);
         dmma(c2[0], c2[1], tk[kt], sG[oG + 4 * v2::kGP + 16 * kt], c2[0], c2[1]);
       }
+#if SRBD_K3_DUMMY_DMMA
+      {  // EXPERIMENT: marginal cost of one more gemv-form DMMA group (9 DMMA on operands that are already loaded)
+        double z0[2] = {0.0, 0.0}, z1[2] = {0.0, 0.0}, z2[2] = {0.0, 0.0};
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {
+          dmma(z0[0], z0[1], tk[kt], sG[oG + 16 * kt], z0[0], z0[1]);
+          dmma(z1[0], z1[1], tk[kt], sG[oG + 2 * v2::kGP + 16 * kt], z1[0], z1[1]);
+          dmma(z2[0], z2[1], tk[kt], sG[oG + 4 * v2::kGP + 16 * kt], z2[0], z2[1]);
+        }
+        if (z0[0] + z1[1] + z2[0] == 123.456789) ws(k, v2::oLV)[0] = z0[1] + z1[0] + z2[1];
+      }
+#endif
       // ---- lv = L^-1 g~_u: blocked forward substitution (4x4 diagonal blocks by their inverses L_pp^-1, which the
       // factorization left in the E rows; same operation order as trsv up to the blocks) ----------------------------------
       double lv0, lv1, lv2, junk;
