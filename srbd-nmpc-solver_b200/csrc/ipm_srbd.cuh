@@ -87,6 +87,10 @@ namespace v2 {
 #ifndef SRBD_K3_UNROLL_RES
 #define SRBD_K3_UNROLL_RES 0
 #endif
+// two half-used output tiles that multiply the same vector share one DMMA (bit-identical results)
+#ifndef SRBD_K3_MERGE_HALVES
+#define SRBD_K3_MERGE_HALVES 1
+#endif
 #ifndef SRBD_K3_DUMMY_DMMA
 #define SRBD_K3_DUMMY_DMMA 0   // experiment only
 #endif
@@ -738,8 +742,13 @@ struct SrbdSolver {
         const int P1 = v2::kPanF, P2 = 2 * v2::kPanF;
         double g1, g2;
         dmma(lv0, junk, c0[0], sF[bA], 0.0, 0.0);                       // lv0 = X0 g0
+#if SRBD_K3_MERGE_HALVES
+        // (one DMMA for both products of -lv0: the lanes of the first accumulator half supply L10, the others L20)
+        dmma(g1, g2, -lv0, sF[bB + 16 + (pi < 4 ? 0 : 16)], c0[1], c1[0]);   // g1 - L10 lv0 | g2 - L20 lv0
+#else
         dmma(g1, junk, -lv0, sF[bB + 16], c0[1], 0.0);                  // g1 - L10 lv0
         dmma(g2, junk, -lv0, sF[bB + 32], c1[0], 0.0);                  // g2 - L20 lv0
+#endif
         dmma(lv1, junk, g1, sF[bA + P1 + 16], 0.0, 0.0);                // lv1 = X1 (.)
         dmma(g2, junk, -lv1, sF[bB + P1 + 32], g2, 0.0);                // ... - L21 lv1
         dmma(lv2, junk, g2, sF[bA + P2 + 32], 0.0, 0.0);                // lv2 = X2 (.)
@@ -825,12 +834,26 @@ struct SrbdSolver {
       double t0[2] = {sF[oLV], sF[oLV + v2::kPanF]}, t1[2] = {sF[oLV + 2 * v2::kPanF], 0.0};
       {  // (stage 0: x = 0 and the rows 12.. of its records are finite, so no branch on the stage type)
 #pragma unroll
+#if SRBD_K3_MERGE_HALVES
+        // rows 8..11 of t and of x+ use half an output tile each and multiply the same x: ONE DMMA whose first-half
+        // lanes (pi < 4) supply Ls^T and whose second-half lanes supply G^T (same per-element arithmetic, 3 DMMA less)
+        const int om = pi < 4 ? (b ? v2::wF1 : v2::wF0) + oLT + 2 * v2::kPanF
+                              : (b ? v2::wG1 : v2::wG0) + oGT + 16 + 3 * v2::kGP;
+        const int os = pi < 4 ? 16 : v2::kGP;
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {
+          dmma(t0[0], t0[1], xk[kt], sF[oLT + 16 * kt], t0[0], t0[1]);
+          dmma(cx0[0], cx0[1], xk[kt], sG[oGT + v2::kGP * (3 + kt)], cx0[0], cx0[1]);
+          dmma(t1[0], cx1[0], xk[kt], sm[om + os * kt], t1[0], cx1[0]);
+        }
+#else
         for (int kt = 0; kt < 3; ++kt) {
           dmma(t0[0], t0[1], xk[kt], sF[oLT + 16 * kt], t0[0], t0[1]);
           dmma(t1[0], t1[1], xk[kt], sF[oLT + 2 * v2::kPanF + 16 * kt], t1[0], t1[1]);
           dmma(cx0[0], cx0[1], xk[kt], sG[oGT + v2::kGP * (3 + kt)], cx0[0], cx0[1]);
           dmma(cx1[0], cx1[1], xk[kt], sG[oGT + 32 + v2::kGP * (3 + kt)], cx1[0], cx1[1]);
         }
+#endif
       }
       // ---- u = -L^-T t: blocked back substitution (diagonal blocks by L_pp^-T) ---------------------------------------
       double uk[3];
@@ -838,8 +861,12 @@ struct SrbdSolver {
         const int P1 = v2::kPanF, P2 = 2 * v2::kPanF;
         double w0, w1, junk;
         dmma(uk[2], junk, -t1[0], sF[bB + P2 + 32], 0.0, 0.0);           // u2 = X2^T (-t2)
+#if SRBD_K3_MERGE_HALVES
+        dmma(w1, w0, -uk[2], sF[bA + 32 + (pi < 4 ? P1 : 0)], -t0[1], -t0[0]);   // -t1 - L21^T u2 | -t0 - L20^T u2
+#else
         dmma(w1, junk, -uk[2], sF[bA + P1 + 32], -t0[1], 0.0);           // -t1 - L21^T u2
         dmma(w0, junk, -uk[2], sF[bA + 32], -t0[0], 0.0);                // -t0 - L20^T u2
+#endif
         dmma(uk[1], junk, w1, sF[bB + P1 + 16], 0.0, 0.0);               // u1 = X1^T (.)
         dmma(w0, junk, -uk[1], sF[bA + 16], w0, 0.0);                    // ... - L10^T u1
         dmma(uk[0], junk, w0, sF[bB], 0.0, 0.0);                         // u0 = X0^T (.)
@@ -1023,11 +1050,24 @@ struct SrbdSolver {
       if (n < 24) { c1[1] = 0.0; c2[0] = 0.0; c2[1] = 0.0; }
       // dense lower block of rows 0..11 (R_k, or Q_N at stage N)
 #pragma unroll
+#if SRBD_K3_MERGE_HALVES
+      // rows 8..11 of H z (first accumulator half) and rows 8..11 of G^T z (res_b, second half) multiply the same z:
+      // one DMMA per k-tile for both (at stage N the second half is unused)
+      const int pbr = (k > 0 ? 6 : 3) * v2::kGP + 4 * t;  // the b row of BAbt: row n
+      double b0[2] = {sG[pbr], sG[pbr + 16]}, b1[2] = {sG[pbr + 32], 0.0};
+#pragma unroll
+      for (int kt = 0; kt < 3; ++kt) {
+        dmma(c0[0], c0[1], zk[kt], sR[oRs[0][kt]], c0[0], c0[1]);
+        const double r1 = sR[oRs[1][kt]], g1 = sG[oGT + 16 + v2::kGP * kt];
+        dmma(c1[0], b1[0], zk[kt], pi < 4 ? r1 : g1, c1[0], b1[0]);
+      }
+#else
       for (int kt = 0; kt < 3; ++kt) {
         dmma(c0[0], c0[1], zk[kt], sR[oRs[0][kt]], c0[0], c0[1]);
         const double r1 = sR[oRs[1][kt]];
         dmma(c1[0], c1[1], zk[kt], pi < 4 ? r1 : 0.0, c1[0], c1[1]);
       }
+#endif
       if (k < N) {
         if (k > 0) {  // diag(Q) on the x rows 12..23
           c1[1] = fma(cQ[t], zk[3], c1[1]);
@@ -1052,6 +1092,13 @@ struct SrbdSolver {
           if (kt >= 3) dmma(c1[0], c1[1], nl[kt], cAc[oDt + 48 * kt + 8], c1[0], c1[1]);
         }
         // res_b
+#if SRBD_K3_MERGE_HALVES
+#pragma unroll
+        for (int kt = 0; kt < 6; ++kt) {
+          dmma(b0[0], b0[1], zk[kt], sG[oGT + v2::kGP * kt], b0[0], b0[1]);  // stage 0: z[12..23] = 0
+          if (kt >= 3) dmma(b1[0], b1[1], zk[kt], sG[oGT + 32 + v2::kGP * kt], b1[0], b1[1]);
+        }
+#else
         const int pbr = (k > 0 ? 6 : 3) * v2::kGP + 4 * t;  // the b row of BAbt: row n
         double b0[2] = {sG[pbr], sG[pbr + 16]}, b1[2] = {sG[pbr + 32], 0.0};
 #pragma unroll
@@ -1059,6 +1106,7 @@ struct SrbdSolver {
           dmma(b0[0], b0[1], zk[kt], sG[oGT + v2::kGP * kt], b0[0], b0[1]);  // stage 0: z[12..23] = 0
           dmma(b1[0], b1[1], zk[kt], sG[oGT + 32 + v2::kGP * kt], b1[0], b1[1]);
         }
+#endif
         b0[0] -= pb[12 + t]; b0[1] -= pb[16 + t]; b1[0] -= pb[20 + t];
         if (r == 0) {
           wsf(k, v2::oRB)[0] = b0[0]; wsf(k, v2::oRB)[4] = b0[1]; wsf(k, v2::oRB)[8] = b1[0];
