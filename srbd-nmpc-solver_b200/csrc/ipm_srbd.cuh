@@ -474,8 +474,15 @@ struct SrbdSolver {
 #pragma unroll
         for (int kt = 0; kt < 6; ++kt) {
           const double gam = gbuf[4 * kt + t];
+#if SRBD_K3_MERGE_HALVES
+          // the rows of leg 1 (kt >= 3) only reach columns 6..11 = the second half of tile 0 and the first half of
+          // tile 1: one DMMA whose first-half lanes supply Ac[.][8 + pi] and whose second-half lanes Ac[.][pi]
+          if (kt < 3) dmma(c0[0], c0[1], gam, cAc[oDt + 48 * kt], c0[0], c0[1]);
+          else dmma(c1[0], c0[1], gam, cAc[oDt + 48 * kt + (pi < 4 ? 8 : 0)], c1[0], c0[1]);
+#else
           dmma(c0[0], c0[1], gam, cAc[oDt + 48 * kt], c0[0], c0[1]);
           if (kt >= 3) dmma(c1[0], c1[1], gam, cAc[oDt + 48 * kt + 8], c1[0], c1[1]);
+#endif
         }
 #pragma unroll
         for (int kt = 0; kt < 3; ++kt) {
@@ -714,8 +721,15 @@ struct SrbdSolver {
 #pragma unroll
       for (int kt = 0; kt < 6; ++kt) {
         const double gam = gbuf[4 * kt + t];
+#if SRBD_K3_MERGE_HALVES
+        // the rows of leg 1 (kt >= 3) only reach columns 6..11 = the second half of tile 0 and the first half of
+        // tile 1: one DMMA whose first-half lanes supply Ac[.][8 + pi] and whose second-half lanes Ac[.][pi]
+        if (kt < 3) dmma(c0[0], c0[1], gam, cAc[oDt + 48 * kt], c0[0], c0[1]);
+        else dmma(c1[0], c0[1], gam, cAc[oDt + 48 * kt + (pi < 4 ? 8 : 0)], c1[0], c0[1]);
+#else
         dmma(c0[0], c0[1], gam, cAc[oDt + 48 * kt], c0[0], c0[1]);
         if (kt >= 3) dmma(c1[0], c1[1], gam, cAc[oDt + 48 * kt + 8], c1[0], c1[1]);
+#endif
       }
 #pragma unroll
       for (int kt = 0; kt < 3; ++kt) {
@@ -1088,8 +1102,15 @@ struct SrbdSolver {
         if (k > 0) { c1[1] -= pp[0]; c2[0] -= pp[1]; c2[1] -= pp[2]; }
 #pragma unroll
         for (int kt = 0; kt < 6; ++kt) {  // J^T (lam_u - lam_l) = -D^T lam
+#if SRBD_K3_MERGE_HALVES
+          // the rows of leg 1 (kt >= 3) only reach columns 6..11 = the second half of tile 0 and the first half of
+          // tile 1: one DMMA whose first-half lanes supply Ac[.][8 + pi] and whose second-half lanes Ac[.][pi]
+          if (kt < 3) dmma(c0[0], c0[1], nl[kt], cAc[oDt + 48 * kt], c0[0], c0[1]);
+          else dmma(c1[0], c0[1], nl[kt], cAc[oDt + 48 * kt + (pi < 4 ? 8 : 0)], c1[0], c0[1]);
+#else
           dmma(c0[0], c0[1], nl[kt], cAc[oDt + 48 * kt], c0[0], c0[1]);
           if (kt >= 3) dmma(c1[0], c1[1], nl[kt], cAc[oDt + 48 * kt + 8], c1[0], c1[1]);
+#endif
         }
         // res_b
 #if SRBD_K3_MERGE_HALVES
