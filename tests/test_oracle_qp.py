@@ -194,3 +194,20 @@ def test_status_max_iter(pkg, orc):
     dims_d, arrays = pkg.workload.random_qp(1, N=8, nx=4, nu=2, nbu=2, seed=3)
     out = orc.qp_solve(_dims(pkg, dims_d), orc.ipm_args(iter_max=2), arrays, 1)
     assert out["status"][0] == 1 and out["iter"][0] == 2
+
+
+def test_failed_pivot_zeroes_the_component(pkg, orc):
+    """BLASFEO's potrf stores the inverse diagonal (0 for a non-positive pivot) and its trsv multiplies by it
+    (blasfeo_common.h:71,76), so a failed pivot zeroes a component of the triangular solve instead of producing inf / nan.
+    QP 1000454 of the all-stance N=50 workload hits such a pivot in its last iteration (mu ~ 2e-11): with a division by the
+    zeroed pivot the oracle ended in NaN (status 3); with the inverse-diagonal semantics it converges in the 12 iterations
+    the GPU takes (scripts/diag_qp.py 1000454 stance 50, profiles/r1_v14_parity_sweep_n50_stance.json)."""
+    N = 50
+    settings = dict(iter_max=50, alpha_min=1e-8, mu0=1e2, tol_stat=1e-6, tol_eq=1e-8, tol_ineq=1e-8, tol_comp=1e-8,
+                    reg_prim=1e-12, warm_start=0, pred_corr=1, ric_alg=0, split_step=1)
+    w = pkg.workload.srbd_batch(1, N=N, contact_mode="stance", start=1000454)
+    ref = orc.pipeline(orc.model_params(N), orc.ipm_args(**settings), N, pkg.capi.SRBD_HARD_INEQ, w["x"], w["u"],
+                       w["xref"], w["x0"], w["contact"])
+    assert ref["status"][0] == 0 and ref["iter"][0] == 12
+    assert np.isfinite(ref["x"]).all() and np.isfinite(ref["u"]).all()
+    assert ref["res_max"][0, 0] <= 1e-6 and (ref["res_max"][0, 1:] <= 1e-8).all()
