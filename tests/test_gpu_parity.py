@@ -505,3 +505,24 @@ def test_rescue_pass_matches_the_generic_kernel(pkg, orc, monkeypatch):
     others = np.arange(B) != 20
     assert (st["iter"][others] == st_raw["iter"][others]).all()         # nothing else changed
     assert bs["solves"] == B and bs["iter_sum"] == int(st["iter"].sum()) and bs["status_count"][0] == B
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("generic", ["0", "1"])
+def test_failed_pivot_zeroes_the_component_on_gpu(pkg, orc, monkeypatch, generic):
+    """Both K3 kernels on the QP of tests/test_oracle_qp.py::test_failed_pivot_zeroes_the_component (all stance, N=50): a
+    non-positive pivot in the last iteration must zero the component (BLASFEO's inverse diagonal), not produce NaN —
+    12 iterations, status 0, like the oracle."""
+    monkeypatch.setenv("SRBD_K3_GENERIC", generic)
+    N = 50
+    settings = dict(SETTINGS, iter_max=50, tol_stat=1e-6)
+    w = pkg.workload.srbd_batch(1, N=N, contact_mode="stance", start=1000454)
+    with make_ctx(pkg, 1, N, settings=settings) as ctx:
+        ctx.upload_traj(w["x"], w["u"], w["xref"], w["x0"], w["contact"])
+        ctx.sqp_iterate(1)
+        sol = ctx.download_solution(want=("x", "u"))
+        st = ctx.download_stats()
+    ref = orc.pipeline(orc.model_params(N), orc.ipm_args(**settings), N, 1, w["x"], w["u"], w["xref"], w["x0"], w["contact"])
+    assert st["status"][0] == 0 and ref["status"][0] == 0
+    assert st["iter"][0] == ref["iter"][0] == 12
+    assert np.isfinite(sol["x"]).all() and relerr(sol["x"], ref["x"]).max() <= 1e-6
