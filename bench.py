@@ -48,6 +48,16 @@ def stage_flops(N, nx=12, nu=12, ng=24):
     return f_it, f_res
 
 
+def bench_config(world, B, contact):
+    """The `config` object of the JSON line, shared by the B200 arm and the --impl reference arm (same workload)."""
+    return {"workload": "BASELINE config 3: 65536 SRBD QPs per GPU, N=20, randomized contact schedules, "
+                        "hard friction-cone/force-box rows (HARD_INEQ), full IPM to tol_stat=tol_eq=tol_ineq=tol_comp=1e-8, "
+                        "ric_alg=0",
+            "qps_per_gpu": B, "global_batch": world * B, "horizon": HORIZON, "contact": contact,
+            "l2": "inputs larger than L2 (packed QP data per step >> 126 MB, trajectories 0.4 GB)",
+            "parallelism": f"dp{world} (independent QPs, no data-path collective)"}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -83,12 +93,16 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for r in self.rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except Exception:
                 continue
+            try:
+                pw.append(float(r[3]))
+            except Exception:
+                pass
             for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
                               ("sw_power_cap", 8)):
                 if len(r) > col and r[col].lower().startswith("active"):
@@ -96,7 +110,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "sm_mhz_min": float(min(sm)), "power_w": float(np.median(pw)) if pw else None}
 
 
 def cpu_reference_run(pkg, batch, threads=0, seed_start=0, contact="gait"):
@@ -119,6 +133,20 @@ def cpu_reference_run(pkg, batch, threads=0, seed_start=0, contact="gait"):
     return batch / dt, nthr, out, dt
 
 
+def cpu_baseline_record(value, cores, sample, **extra):
+    """cpu_baseline object: the oracle PORT (plain-C restatement with naive loops), not the reference's HPIPM/BLASFEO
+    (not buildable offline: no Eigen / yaml-cpp / HPIPM / BLASFEO sources).  BLASFEO's hand-written AVX2 / AVX-512
+    micro-kernels are several times faster than these triple loops on the same cores: read the GPU/CPU ratio with that
+    in mind (the roofline fraction, not this ratio, measures kernel quality)."""
+    rec = {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+           "solves_per_s_per_core": value / max(cores, 1),
+           "build": "gcc -O3 -mavx2 -mfma -fopenmp (oracle/Makefile), plain triple loops, one QP per OpenMP task",
+           "note": "CPU oracle port; the reference's HPIPM/BLASFEO/Eigen cannot be built offline and would be several "
+                   "times faster per core (hand-written BLASFEO micro-kernels)"}
+    rec.update(extra)
+    return rec
+
+
 def run_reference(args, pkg, rank, world):
     """--impl reference: the reference's CPU implementation of the path.  The reference itself cannot be built
     offline (Eigen / yaml-cpp / HPIPM / BLASFEO absent), so this is the oracle port (kind = "port")."""
@@ -136,11 +164,10 @@ def run_reference(args, pkg, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "BASELINE config 3: SRBD QPs N=20, randomized contact schedules, HARD_INEQ, IPM tol 1e-8",
-                       "qps_per_step": sample, "horizon": HORIZON},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{sample} QPs per step x {args.steps} steps, OpenMP over QPs, all host threads; "
-                                       "CPU oracle port (reference HPIPM/BLASFEO/Eigen not buildable offline)"},
+            # the SAME workload as the B200 arm (config 3); each timed step is a bounded sample of it (cpu_baseline.sample)
+            "config": bench_config(world, args.batch, args.contact),
+            "cpu_baseline": cpu_baseline_record(val, cores, f"{sample} consecutive QPs of that workload per step x "
+                                                f"{args.steps} steps (a different slice each step), OpenMP over QPs"),
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit_json(line)
 
@@ -191,8 +218,8 @@ def latency_leg(pkg, reps=300):
     ts = np.array(ts) * 1e6
     return {"p50_us": float(np.percentile(ts, 50)), "p99_us": float(np.percentile(ts, 99)), "calls": reps,
             "ipm_iterations": int(it[0]), "status": int(stt[0]),
-            "workload": "BASELINE config 5: one SRBD QP, N=50, all stance, HARD_INEQ, tol 1e-8 (tol_stat 1e-6), "
-                        "host->host through srbd_solve_host on rank 0"}
+            "workload": "BASELINE config 5: one SRBD QP, N=50, all stance, HARD_INEQ, tol_stat=1e-6, "
+                        "tol_eq=tol_ineq=tol_comp=1e-8, host->host through srbd_solve_host on rank 0"}
 
 
 def main():
@@ -222,8 +249,8 @@ def main():
         run_reference(args, pkg, rank, world)
         return
 
-    # NCCL prints its version banner on STDOUT when NCCL_DEBUG is VERSION/INFO: stdout carries exactly one JSON line
-    os.environ["NCCL_DEBUG"] = os.environ.get("SRBD_NCCL_DEBUG", "WARN")
+    # NCCL_DEBUG is left as the caller set it: whatever NCCL prints on stdout goes to stderr (claim_stdout above), so
+    # the driver can count ranks in the NCCL log and stdout still carries exactly one JSON line
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -238,26 +265,15 @@ def main():
     ctx = pkg.Context(B, device=local_rank)
     ctx.set_model(pkg.default_model_params(HORIZON))
     ctx.set_ipm_args(pkg.default_ipm_args(**SETTINGS))
+    # Roofline denominator FIRST, on a cool board: a short DMMA burst (srbd_fp64_peak).  Measured after the sustained
+    # loop the same probe reads 30-35 TFLOP/s (1000 W cap), which made round 1's `frac` move between runs.
+    fp64_peak = ctx.fp64_peak() / 1e12
     ctx.upload_traj(w["x"], w["u"], w["xref"], w["x0"], w["contact"])
     ctx.sync()
-    stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
     mode = pkg.capi.SRBD_HARD_INEQ
 
     def ev():
         return torch.cuda.Event(enable_timing=True)
-
-    def step(evs=None):
-        if evs:
-            evs[0].record(stream)
-        ctx.linearize()
-        if evs:
-            evs[1].record(stream)
-        ctx.assemble(mode)
-        if evs:
-            evs[2].record(stream)
-        ctx.qp_solve()
-        if evs:
-            evs[3].record(stream)
 
     def barrier():
         torch.cuda.synchronize()
@@ -265,25 +281,72 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    ctx.sync()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    barrier()
-    l0 = ctx.launch_count
-    all_evs = [[ev() for _ in range(4)] for _ in range(args.steps)]
-    for s in range(args.steps):
-        step(all_evs[s])
-    barrier()
-    launches = ctx.launch_count - l0
-    clocks = sampler.stop() if rank == 0 else None
-    total_ms = all_evs[0][0].elapsed_time(all_evs[-1][3])
-    k_ms = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(3)] for e in all_evs])  # K1, K2, K3 per step
+    def timed_steps(c, steps, warmup):
+        """W untimed + K timed steps (K1 -> K2 -> K3) of context c with device-resident inputs; CUDA events on the
+        context's stream.  Returns (ms over the K steps on this rank, per-step [K1, K2, K3] ms, launches)."""
+        stream = torch.cuda.ExternalStream(c.stream, device=local_rank)
+
+        def step(evs=None):
+            if evs:
+                evs[0].record(stream)
+            c.linearize()
+            if evs:
+                evs[1].record(stream)
+            c.assemble(mode)
+            if evs:
+                evs[2].record(stream)
+            c.qp_solve()
+            if evs:
+                evs[3].record(stream)
+        for _ in range(warmup):
+            step()
+        c.sync()
+        barrier()
+        l0 = c.launch_count
+        evs = [[ev() for _ in range(4)] for _ in range(steps)]
+        for s_ in range(steps):
+            step(evs[s_])
+        barrier()
+        return (evs[0][0].elapsed_time(evs[-1][3]),
+                np.array([[e[i].elapsed_time(e[i + 1]) for i in range(3)] for e in evs]), c.launch_count - l0)
+
+    sampler = ClockSampler(local_rank)   # every rank samples ITS GPU during the timed region
+    sampler.start()
+    total_ms, k_ms, launches = timed_steps(ctx, args.steps, args.warmup)
+    clocks_rank = sampler.stop()
+    clocks = clocks_rank if rank == 0 else None
     total_ms_max = pkg.sharding.max_over_ranks(total_ms)  # device time, max over ranks
     ms_per_step = total_ms_max / args.steps
     value = world * B / (ms_per_step * 1e-3)
+    # per-rank record: names the limiter when the max-over-ranks time is not rank 0's
+    mine = {"rank": rank, "ms_per_step": total_ms / args.steps, "k3_ms": float(k_ms[:, 2].mean()),
+            "sm_mhz": clocks_rank.get("sm_mhz"), "sm_mhz_min": clocks_rank.get("sm_mhz_min"),
+            "power_w": clocks_rank.get("power_w"), "reasons": clocks_rank.get("reasons")}
+    if world > 1:
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
+    else:
+        per_rank = [mine]
+    rank_ms = np.array([r["ms_per_step"] for r in per_rank])
+
+    # strong scaling of BASELINE config 3 AS WRITTEN ("batch 65536 ... sharded over 1/2/4/8"): 65536 QPs in total,
+    # 65536 / N per GPU (rank r owns QPs [r B/N, (r+1) B/N) of the same generator)
+    strong = None
+    if world > 1:
+        Bs = B // world
+        ws_ = pkg.workload.srbd_batch(Bs, N=HORIZON, contact_mode=args.contact, start=rank * Bs)
+        cs = pkg.Context(Bs, device=local_rank)
+        cs.set_model(pkg.default_model_params(HORIZON))
+        cs.set_ipm_args(pkg.default_ipm_args(**SETTINGS))
+        cs.upload_traj(ws_["x"], ws_["u"], ws_["xref"], ws_["x0"], ws_["contact"])
+        cs.sync()
+        s_ms, _, _ = timed_steps(cs, args.steps, args.warmup)
+        s_ms_max = pkg.sharding.max_over_ranks(s_ms) / args.steps
+        strong = {"scaling": "strong", "global_batch": Bs * world, "qps_per_gpu": Bs, "ms_per_step": s_ms_max,
+                  "value": Bs * world / (s_ms_max * 1e-3), "unit": UNIT,
+                  "note": "value(N) / value(1 GPU, 65536 QPs) / N is the strong-scaling efficiency; a 65536 / N shard is "
+                          "65536 / N / 1776 resident-QP waves of the persistent K3 grid (tail effects grow with N)"}
+        cs.close()
 
     # per-rank statistics block (fused epilogue of K3), gathered over NCCL
     bs = ctx.batch_stats()
@@ -348,7 +411,7 @@ def main():
         flops_launch = float(st["iter"].sum()) * f_it + B * f_res
         k3_ms = float(k_ms[:, 2].mean())
         achieved = flops_launch / (k3_ms * 1e-3) / 1e12
-        peak = ctx.fp64_peak() / 1e12
+        peak = fp64_peak
         traffic, traffic_src, pipes_ncu = None, None, None
         tpath = os.path.join(ROOT, "profiles", "k3_traffic.json")
         if os.path.exists(tpath):  # dram bytes of K3 from the committed `ncu --set full` capture, scaled per QP
@@ -361,8 +424,8 @@ def main():
                     "kernel": "ipm_srbd_kernel (K3)", "achieved": achieved, "peak": peak,
                     "unit": "TFLOP/s", "frac": achieved / peak if peak > 0 else None, "traffic": traffic,
                     "traffic_source": traffic_src, "pipes_ncu": pipes_ncu,
-                    "peak_source": "measured live: DFMA-saturating microbenchmark srbd_fp64_peak() (MEASURED_PEAKS.json "
-                                   "carries no FP64 figure)",
+                    "peak_source": "measured live BEFORE the timed loop: DMMA-saturating burst srbd_fp64_peak() "
+                                   "(MEASURED_PEAKS.json carries no FP64 figure; DMMA and DFMA share the pipe)",
                     "flops_per_launch": flops_launch, "kernel_ms": k3_ms,
                     "kernel_share_of_step": k3_ms / float(k_ms.sum(1).mean()),
                     "k1_ms": float(k_ms[:, 0].mean()), "k2_ms": float(k_ms[:, 1].mean())}
@@ -374,25 +437,26 @@ def main():
         roofline["k1_hbm_frac"] = k1_bytes / (roofline["k1_ms"] * 1e-3) / 1e9 / hbm_peak
         roofline["k2_hbm_frac"] = k2_bytes / (roofline["k2_ms"] * 1e-3) / 1e9 / hbm_peak
         roofline["hbm_peak_gbs"] = hbm_peak
+        # HBM view of K3: its measured DRAM traffic (ncu capture above) over its live kernel time
+        if traffic:
+            roofline["k3_hbm_gbs"] = traffic / (k3_ms * 1e-3) / 1e9
+            roofline["k3_hbm_frac"] = roofline["k3_hbm_gbs"] / hbm_peak
         cpu_baseline = None
         if not args.no_cpu_baseline:
             v, cores, out, dt = cpu_reference_run(pkg, args.cpu_sample)
             same = bool(np.array_equal(out["iter"], st["iter"][:args.cpu_sample])) if args.cpu_sample <= B else None
-            cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                            "sample": f"first {args.cpu_sample} QPs of rank 0's shard, one pass ({dt:.1f} s), OpenMP over QPs; "
-                                      "CPU oracle port (reference HPIPM/BLASFEO/Eigen not buildable offline)",
-                            "iteration_counts_equal_gpu": same}
+            cpu_baseline = cpu_baseline_record(v, cores, f"first {args.cpu_sample} QPs of rank 0's shard, one pass "
+                                               f"({dt:.1f} s), OpenMP over QPs", iteration_counts_equal_gpu=same)
         latency = None if args.no_latency else latency_leg(pkg)
         it = st["iter"]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "BASELINE config 3: 65536 SRBD QPs per GPU, N=20, randomized contact schedules, "
-                                       "hard friction-cone/force-box rows (HARD_INEQ), full IPM to tol 1e-8, ric_alg=0",
-                           "qps_per_gpu": B, "global_batch": world * B, "horizon": HORIZON, "contact": args.contact,
-                           "l2": "inputs larger than L2 (packed QP data 20.6 GB per step, trajectories 0.4 GB)",
-                           "parallelism": f"dp{world} (independent QPs, no data-path collective)"},
+                "config": bench_config(world, B, args.contact),
                 "clocks": clocks, "gpu_launches": int(launches),
+                "per_rank_ms": {"min": float(rank_ms.min()), "median": float(np.median(rank_ms)),
+                                "max": float(rank_ms.max()), "ranks": per_rank},
+                "strong": strong,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms_max, "steps": 2 * args.e2e_steps,
                         "how": "two contexts / CUDA streams take the steps alternately (srbd_solve_host_async + srbd_wait): "

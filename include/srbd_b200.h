@@ -214,8 +214,8 @@ typedef enum srbd_buf {
 
 /* ---- defaults ------------------------------------------------------------------------------ */
 void srbd_model_params_default(srbd_model_params* p, int horizon);
-/* mode: 0 SpeedAbs, 1 Speed, 2 Balance, 3 Robust (hpipm-cpp HpipmMode); hidden defaults follow
- * HPIPM SPEED; fields of OcpQpIpmSolverSettings get that struct's defaults. */
+/* The fields of OcpQpIpmSolverSettings get that struct's defaults (ocp_qp_ipm_solver_settings.hpp:26-86), the hidden
+ * constants those of HPIPM's SPEED mode (d_ocp_qp_ipm_arg_set_default(SPEED)). */
 void srbd_ipm_args_default(srbd_ipm_args* a);
 size_t srbd_qp_nct(const srbd_qp_dims* d); /* length of lam / t per QP */
 
@@ -255,6 +255,8 @@ int srbd_qp_upload(srbd_ctx* ctx, const srbd_qp_host* qp); /* H2D + pack (d_ocp_
  * the rescue launch of the generic kernel for the QPs that ran to iter_max (usually none);
  * everything else (srbd_qp_upload data, warm start, Riccati / statistics exports) through the generic kernel. */
 int srbd_qp_solve(srbd_ctx* ctx);
+/* P, p, K, k (and a meaningful pi[0]) exist only when the LAST solve ran with srbd_set_outputs(ctx, 1, ..): otherwise
+ * asking for them returns SRBD_ERR_STATE (never the exports of an earlier solve). */
 int srbd_download_solution(srbd_ctx* ctx, const srbd_sol_host* sol);
 int srbd_download_stats(srbd_ctx* ctx, const srbd_stats_host* st);
 int srbd_batch_stats_get(srbd_ctx* ctx, srbd_batch_stats* out);
@@ -283,7 +285,8 @@ int srbd_solve_host_async(srbd_ctx* ctx, int mode, const double* x, const double
 int srbd_wait(srbd_ctx* ctx);
 
 /* ---- measurement helpers ----------------------------------------------------------------------*/
-/* DFMA-saturating microbenchmark: returns achieved FP64 FLOP/s on the context's device. */
+/* FP64-pipe-saturating microbenchmark (DMMA m8n8k4 chains; DMMA and DFMA share one datapath on B200): returns the
+ * achieved FP64 FLOP/s on the context's device.  A short burst: call it BEFORE a sustained run (power cap). */
 int srbd_fp64_peak(srbd_ctx* ctx, double* flops_per_s);
 
 #ifdef __cplusplus

@@ -31,27 +31,52 @@
 
 #include "srbd_oracle.h"
 
+/* Arithmetic type of the restatement.  The default build (double) is THE oracle; the same source compiled with
+ * -DORC_REAL=__float128 -DORC_QUAD (oracle/Makefile: _build/libsrbd_oracle_quad.so, entry points suffixed _q) is the
+ * higher-precision ARBITER: identical algorithm, constants, operation order and status logic, rounding ~1e-34, inputs
+ * and outputs still double.  Where the GPU and the double oracle differ (iterates beyond 1e-9, iteration count, status)
+ * the arbiter says what the algorithm does in (nearly) exact arithmetic and which side is closer to it. */
+#ifdef ORC_QUAD
+#include <quadmath.h>
+typedef __float128 real;
+#define R_SQRT sqrtq
+#define R_FABS fabsq
+#define R_ISNAN isnanq
+#define ORC_NAME(f) f##_q
+#else
+typedef double real;
+#define R_SQRT sqrt
+#define R_FABS fabs
+#define R_ISNAN isnan
+#define ORC_NAME(f) f
+#endif
+static inline void cpy_out(double* dst, const real* src, size_t n) { for (size_t i = 0; i < n; ++i) dst[i] = (double)src[i]; }
+static inline void cpy_in(real* dst, const double* src, size_t n) { for (size_t i = 0; i < n; ++i) dst[i] = (real)src[i]; }
+
+#ifdef ORC_QUAD
+#define orc_qp_nct orc_qp_nct_q
+#endif
 size_t orc_qp_nct(const srbd_qp_dims* d);
 
 typedef struct {
   int N, nx, nu, nm, ncm, ngm; /* nm = nu+nx (ld of every n-row matrix), ncm = max constraints/side */
   int *nuk, *nxk, *nbk, *ngk;  /* per stage (after the x0 embedding) */
   /* QP data per stage */
-  double *H, *g, *G, *bb, *DCt, *lo, *up, *ml, *mu;
+  real *H, *g, *G, *bb, *DCt, *lo, *up, *ml, *mu;
   int* idxb;
   /* iterate */
-  double *z, *pi, *ll, *lu, *tl, *tu;
+  real *z, *pi, *ll, *lu, *tl, *tu;
   /* step */
-  double *dz, *dpi, *dll, *dlu, *dtl, *dtu;
+  real *dz, *dpi, *dll, *dlu, *dtl, *dtu;
   /* residuals */
-  double *rg, *rb, *rdl, *rdu, *rml, *rmu, *rml_bkp, *rmu_bkp;
+  real *rg, *rb, *rdl, *rdu, *rml, *rmu, *rml_bkp, *rmu_bkp;
   /* Gamma / gamma */
-  double *Gl, *Gu, *gl, *gu;
+  real *Gl, *Gu, *gl, *gu;
   /* Riccati factors */
-  double *Lr, *Ls, *lv, *P, *p, *Lfull, *Pb;
+  real *Lr, *Ls, *lv, *P, *p, *Lfull, *Pb;
   /* scratch */
-  double *M, *AL, *gt, *tmp;
-  double res_max[4], mu_res, obj;
+  real *M, *AL, *gt, *tmp;
+  real res_max[4], mu_res, obj;
   int nc_mask;
 } W;
 
@@ -66,7 +91,7 @@ typedef struct {
 #define PK(w, k) ((w)->P + (size_t)(k) * (w)->nx * (w)->nx)
 #define LFK(w, k) ((w)->Lfull + (size_t)(k) * (w)->nm * (w)->nm)
 
-static double* dalloc(size_t n) { return (double*)calloc(n ? n : 1, sizeof(double)); }
+static real* dalloc(size_t n) { return (real*)calloc(n ? n : 1, sizeof(real)); }
 
 static W* w_create(const srbd_qp_dims* d) {
   W* w = (W*)calloc(1, sizeof(W));
@@ -124,9 +149,9 @@ static void embed_qp(W* w, const srbd_qp_dims* d, const srbd_qp_host* qp, int wh
   const double* x0 = qp->x0 + q * nx;
   for (int k = 0; k <= N; ++k) {
     const int nuk = w->nuk[k], nxk = w->nxk[k];
-    double* H = HK(w, k);
-    double* g = VN(w, g, k);
-    memset(H, 0, sizeof(double) * nm * nm);
+    real* H = HK(w, k);
+    real* g = VN(w, g, k);
+    memset(H, 0, sizeof(real) * nm * nm);
     if (k < N) {
       const double* R = qp->R + (q * N + k) * nu * nu;
       const double* r = qp->r + (q * N + k) * nu;
@@ -137,7 +162,7 @@ static void embed_qp(W* w, const srbd_qp_dims* d, const srbd_qp_host* qp, int wh
       if (k == 0) { /* r0 = S0 x0 + r0 */
         if (S)
           for (int i = 0; i < nu; ++i) {
-            double s = 0.0;
+            real s = 0.0;
             for (int j = 0; j < nx; ++j) s += S[i + nu * j] * x0[j];
             g[i] = s + r[i];
           }
@@ -160,8 +185,8 @@ static void embed_qp(W* w, const srbd_qp_dims* d, const srbd_qp_host* qp, int wh
       const double* A = qp->A + (q * N + k) * nx * nx;
       const double* B = qp->Bm + (q * N + k) * nx * nu;
       const double* b = qp->b + (q * N + k) * nx;
-      double* G = GK(w, k);
-      double* bb = VX(w, bb, k);
+      real* G = GK(w, k);
+      real* bb = VX(w, bb, k);
       for (int j = 0; j < nx; ++j) {
         for (int i = 0; i < nu; ++i) G[i + nm * j] = B[j + nx * i];
         if (k > 0)
@@ -170,15 +195,15 @@ static void embed_qp(W* w, const srbd_qp_dims* d, const srbd_qp_host* qp, int wh
       for (int j = 0; j < nx; ++j) bb[j] = b[j];
       if (k == 0) /* b0 = A0 x0 + b0 */
         for (int i = 0; i < nx; ++i) {
-          double s = 0.0;
+          real s = 0.0;
           for (int j = 0; j < nx; ++j) s += A[i + nx * j] * x0[j];
           bb[i] = s + b[i];
         }
     }
     /* constraints: [box-u, box-x, general] */
     int* idxb = w->idxb + (size_t)k * w->ncm;
-    double* lo = VC(w, lo, k); double* up = VC(w, up, k);
-    double* ml = VC(w, ml, k); double* mu = VC(w, mu, k);
+    real* lo = VC(w, lo, k); real* up = VC(w, up, k);
+    real* ml = VC(w, ml, k); real* mu = VC(w, mu, k);
     int c = 0;
     if (k < N)
       for (int j = 0; j < d->nbu; ++j, ++c) {
@@ -197,8 +222,8 @@ static void embed_qp(W* w, const srbd_qp_dims* d, const srbd_qp_host* qp, int wh
         mu[c] = qp->ubx_mask ? qp->ubx_mask[o] : 1.0;
       }
     const int ngk = w->ngk[k];
-    double* DCt = DK(w, k);
-    memset(DCt, 0, sizeof(double) * nm * w->ngm);
+    real* DCt = DK(w, k);
+    memset(DCt, 0, sizeof(real) * nm * w->ngm);
     for (int j = 0; j < ngk; ++j, ++c) {
       if (k < N) {
         size_t o = (q * N + k) * d->ng + j;
@@ -233,40 +258,40 @@ static void embed_qp(W* w, const srbd_qp_dims* d, const srbd_qp_host* qp, int wh
 }
 
 /* J z for one stage: v[0..nb) box, v[nb..nb+ng) general */
-static void apply_J(const W* w, int k, const double* z, double* v) {
+static void apply_J(const W* w, int k, const real* z, real* v) {
   const int n = w->nuk[k] + w->nxk[k], nb = w->nbk[k], ng = w->ngk[k], nm = w->nm;
   const int* idxb = w->idxb + (size_t)k * w->ncm;
-  const double* DCt = DK(w, k);
+  const real* DCt = DK(w, k);
   for (int j = 0; j < nb; ++j) v[j] = z[idxb[j]];
   for (int j = 0; j < ng; ++j) {
-    double s = 0.0;
+    real s = 0.0;
     for (int i = 0; i < n; ++i) s += DCt[i + nm * j] * z[i];
     v[nb + j] = s;
   }
 }
 
 /* out += J^T v */
-static void apply_Jt_add(const W* w, int k, const double* v, double* out) {
+static void apply_Jt_add(const W* w, int k, const real* v, real* out) {
   const int n = w->nuk[k] + w->nxk[k], nb = w->nbk[k], ng = w->ngk[k], nm = w->nm;
   const int* idxb = w->idxb + (size_t)k * w->ncm;
-  const double* DCt = DK(w, k);
+  const real* DCt = DK(w, k);
   for (int j = 0; j < nb; ++j) out[idxb[j]] += v[j];
   for (int j = 0; j < ng; ++j) {
-    const double vj = v[nb + j];
+    const real vj = v[nb + j];
     for (int i = 0; i < n; ++i) out[i] += DCt[i + nm * j] * vj;
   }
 }
 
 /* d_ocp_qp_init_var (hpipm_d_ocp_qp_ipm.h:232), SURVEY.md Appendix C "INIT" */
 static void init_var(W* w, const srbd_ipm_args* a) {
-  const double thr0 = a->thr0, mu0 = a->mu0;
+  const real thr0 = a->thr0, mu0 = a->mu0;
   for (int k = 0; k <= w->N; ++k) {
     const int nb = w->nbk[k], ng = w->ngk[k];
-    double* z = VN(w, z, k);
+    real* z = VN(w, z, k);
     const int* idxb = w->idxb + (size_t)k * w->ncm;
-    double *lo = VC(w, lo, k), *up = VC(w, up, k), *tl = VC(w, tl, k), *tu = VC(w, tu, k);
-    double *ll = VC(w, ll, k), *lu = VC(w, lu, k), *ml = VC(w, ml, k), *mu = VC(w, mu, k);
-    if (k < w->N) memset(VX(w, pi, k), 0, sizeof(double) * w->nx);
+    real *lo = VC(w, lo, k), *up = VC(w, up, k), *tl = VC(w, tl, k), *tu = VC(w, tu, k);
+    real *ll = VC(w, ll, k), *lu = VC(w, lu, k), *ml = VC(w, ml, k), *mu = VC(w, mu, k);
+    if (k < w->N) memset(VX(w, pi, k), 0, sizeof(real) * w->nx);
     for (int j = 0; j < nb; ++j) {
       const int i = idxb[j];
       tl[j] = -lo[j] + z[i];
@@ -284,7 +309,7 @@ static void init_var(W* w, const srbd_ipm_args* a) {
         z[i] = up[j] - thr0;
       }
     }
-    double* v = w->tmp;
+    real* v = w->tmp;
     apply_J(w, k, z, v);
     for (int j = nb; j < nb + ng; ++j) {
       tl[j] = v[j] - lo[j];
@@ -302,16 +327,16 @@ static void init_var(W* w, const srbd_ipm_args* a) {
 /* d_ocp_qp_res_compute + _compute_inf_norm (hpipm_d_ocp_qp_res.h:90,94), Appendix C "RESIDUALS" */
 static void compute_res(W* w) {
   const int nm = w->nm;
-  double n_g = 0.0, n_b = 0.0, n_d = 0.0, n_m = 0.0, summ = 0.0, obj = 0.0;
+  real n_g = 0.0, n_b = 0.0, n_d = 0.0, n_m = 0.0, summ = 0.0, obj = 0.0;
   for (int k = 0; k <= w->N; ++k) {
     const int nuk = w->nuk[k], nxk = w->nxk[k], n = nuk + nxk, nb = w->nbk[k], ng = w->ngk[k], nc = nb + ng;
-    const double* H = HK(w, k);
-    const double* g = VN(w, g, k);
-    const double* z = VN(w, z, k);
-    double* rg = VN(w, rg, k);
-    double quad = 0.0, lin = 0.0;
+    const real* H = HK(w, k);
+    const real* g = VN(w, g, k);
+    const real* z = VN(w, z, k);
+    real* rg = VN(w, rg, k);
+    real quad = 0.0, lin = 0.0;
     for (int i = 0; i < n; ++i) { /* symv with the lower triangle */
-      double s = 0.0;
+      real s = 0.0;
       for (int j = 0; j < n; ++j) s += (i >= j ? H[i + nm * j] : H[j + nm * i]) * z[j];
       quad += z[i] * s;
       lin += g[i] * z[i];
@@ -319,30 +344,30 @@ static void compute_res(W* w) {
     }
     obj += 0.5 * quad + lin;
     if (k < w->N) {
-      const double* G = GK(w, k);
-      const double* pi = VX(w, pi, k);
-      const double* zn = VN(w, z, k + 1);
-      double* rb = VX(w, rb, k);
+      const real* G = GK(w, k);
+      const real* pi = VX(w, pi, k);
+      const real* zn = VN(w, z, k + 1);
+      real* rb = VX(w, rb, k);
       for (int i = 0; i < n; ++i) {
-        double s = 0.0;
+        real s = 0.0;
         for (int j = 0; j < w->nx; ++j) s += G[i + nm * j] * pi[j];
         rg[i] += s;
       }
       for (int j = 0; j < w->nx; ++j) {
-        double s = 0.0;
+        real s = 0.0;
         for (int i = 0; i < n; ++i) s += G[i + nm * j] * z[i];
         rb[j] = (s + VX(w, bb, k)[j]) - zn[w->nuk[k + 1] + j];
-        if (fabs(rb[j]) > n_b) n_b = fabs(rb[j]);
+        if (R_FABS(rb[j]) > n_b) n_b = R_FABS(rb[j]);
       }
     }
     if (k > 0) {
-      const double* pim = VX(w, pi, k - 1);
+      const real* pim = VX(w, pi, k - 1);
       for (int i = 0; i < nxk; ++i) rg[nuk + i] -= pim[i];
     }
-    double *ll = VC(w, ll, k), *lu = VC(w, lu, k), *tl = VC(w, tl, k), *tu = VC(w, tu, k);
-    double *ml = VC(w, ml, k), *mu = VC(w, mu, k), *lo = VC(w, lo, k), *up = VC(w, up, k);
-    double *rdl = VC(w, rdl, k), *rdu = VC(w, rdu, k), *rml = VC(w, rml, k), *rmu = VC(w, rmu, k);
-    double* v = w->tmp;
+    real *ll = VC(w, ll, k), *lu = VC(w, lu, k), *tl = VC(w, tl, k), *tu = VC(w, tu, k);
+    real *ml = VC(w, ml, k), *mu = VC(w, mu, k), *lo = VC(w, lo, k), *up = VC(w, up, k);
+    real *rdl = VC(w, rdl, k), *rdu = VC(w, rdu, k), *rml = VC(w, rml, k), *rmu = VC(w, rmu, k);
+    real* v = w->tmp;
     for (int j = 0; j < nc; ++j) v[j] = lu[j] - ll[j];
     apply_Jt_add(w, k, v, rg);
     apply_J(w, k, z, v);
@@ -353,16 +378,16 @@ static void compute_res(W* w) {
       rmu[j] = (lu[j] * tu[j]) * mu[j];
       summ += rml[j];
       summ += rmu[j];
-      if (fabs(rdl[j]) > n_d) n_d = fabs(rdl[j]);
-      if (fabs(rdu[j]) > n_d) n_d = fabs(rdu[j]);
-      if (fabs(rml[j]) > n_m) n_m = fabs(rml[j]);
-      if (fabs(rmu[j]) > n_m) n_m = fabs(rmu[j]);
+      if (R_FABS(rdl[j]) > n_d) n_d = R_FABS(rdl[j]);
+      if (R_FABS(rdu[j]) > n_d) n_d = R_FABS(rdu[j]);
+      if (R_FABS(rml[j]) > n_m) n_m = R_FABS(rml[j]);
+      if (R_FABS(rmu[j]) > n_m) n_m = R_FABS(rmu[j]);
     }
     for (int i = 0; i < n; ++i)
-      if (fabs(rg[i]) > n_g) n_g = fabs(rg[i]);
+      if (R_FABS(rg[i]) > n_g) n_g = R_FABS(rg[i]);
   }
   w->res_max[0] = n_g; w->res_max[1] = n_b; w->res_max[2] = n_d; w->res_max[3] = n_m;
-  w->mu_res = w->nc_mask > 0 ? summ / (double)w->nc_mask : 0.0;
+  w->mu_res = w->nc_mask > 0 ? summ / (real)w->nc_mask : 0.0;
   w->obj = obj;
 }
 
@@ -371,18 +396,18 @@ static void compute_res(W* w) {
  * failed pivot zeroes the component instead of producing inf / nan; for a positive pivot this is the plain division
  * (bit-identical to what the golden vectors pin).  At tol 1e-8 this matters for ~1 QP in 1e4..1e5: with mu ~ 1e-11 a
  * pivot of the barrier-augmented Hessian can cancel to <= 0 in the last iteration (profiles/r1_v14_parity_sweep_*). */
-static inline double pdiv(double s, double d) { return d > 0.0 ? s / d : 0.0; }
+static inline real pdiv(real s, real d) { return d > 0.0 ? s / d : 0.0; }
 
 /* dense lower Cholesky of the leading nc columns of an (m x m, ld) symmetric matrix held in its lower
  * triangle, applied right-looking to all m rows (BLASFEO potrf_l_mn semantics).  A non-positive pivot is replaced
  * by 0 and its column is scaled by 0, like BLASFEO does. */
-static void potrf_l_mn(int m, int nc, double* A, int ld) {
+static void potrf_l_mn(int m, int nc, real* A, int ld) {
   for (int j = 0; j < nc; ++j) {
-    double dj = A[j + ld * j];
+    real dj = A[j + ld * j];
     for (int k = 0; k < j; ++k) dj -= A[j + ld * k] * A[j + ld * k];
-    double inv;
+    real inv;
     if (dj > 0.0) {
-      dj = sqrt(dj);
+      dj = R_SQRT(dj);
       inv = 1.0 / dj;
     } else {
       dj = 0.0;
@@ -390,7 +415,7 @@ static void potrf_l_mn(int m, int nc, double* A, int ld) {
     }
     A[j + ld * j] = dj;
     for (int i = j + 1; i < m; ++i) {
-      double s = A[i + ld * j];
+      real s = A[i + ld * j];
       for (int k = 0; k < j; ++k) s -= A[i + ld * k] * A[j + ld * k];
       A[i + ld * j] = s * inv;
     }
@@ -402,27 +427,27 @@ static void potrf_l_mn(int m, int nc, double* A, int ld) {
  * the (step) QP; Gamma/gamma from w->Gl.. when with_constr.  fact=1 factorizes (and stores Lr, Ls, P);
  * fact=0 reuses the factors (vector part only).  Results: oz (N+1 stages of [u;x]), opi.
  */
-static void kkt_solve(W* w, const srbd_ipm_args* a, int fact, int with_constr, const double* rhs_g,
-                      const double* rhs_b, double* oz, double* opi) {
+static void kkt_solve(W* w, const srbd_ipm_args* a, int fact, int with_constr, const real* rhs_g,
+                      const real* rhs_b, real* oz, real* opi) {
   const int nm = w->nm, nx = w->nx, nu = w->nu, N = w->N;
-  double* M = w->M;
-  double* AL = w->AL;
-  double* gt = w->gt;
+  real* M = w->M;
+  real* AL = w->AL;
+  real* gt = w->gt;
   for (int k = N; k >= 0; --k) {
     const int nuk = w->nuk[k], nxk = w->nxk[k], n = nuk + nxk, nb = w->nbk[k], ng = w->ngk[k], nc = nb + ng;
     const int* idxb = w->idxb + (size_t)k * w->ncm;
-    const double* DCt = DK(w, k);
-    const double* G = GK(w, k);
+    const real* DCt = DK(w, k);
+    const real* G = GK(w, k);
     if (fact) {
-      const double* H = HK(w, k);
+      const real* H = HK(w, k);
       for (int j = 0; j < n; ++j)
         for (int i = 0; i < n; ++i) M[i + nm * j] = (i >= j) ? H[i + nm * j] : H[j + nm * i];
       if (with_constr) {
-        const double *Gl = VC(w, Gl, k), *Gu = VC(w, Gu, k);
+        const real *Gl = VC(w, Gl, k), *Gu = VC(w, Gu, k);
         for (int j = 0; j < nb; ++j) M[idxb[j] + nm * idxb[j]] += Gl[j] + Gu[j];
         for (int c = 0; c < n; ++c)
           for (int i = c; i < n; ++i) {
-            double s = 0.0;
+            real s = 0.0;
             for (int j = 0; j < ng; ++j) s += (DCt[i + nm * j] * (Gl[nb + j] + Gu[nb + j])) * DCt[c + nm * j];
             M[i + nm * c] += s;
             if (i != c) M[c + nm * i] = M[i + nm * c];
@@ -430,32 +455,32 @@ static void kkt_solve(W* w, const srbd_ipm_args* a, int fact, int with_constr, c
       }
       if (k < N) {
         if (a->ric_alg == 0) { /* classical: AL = G P_{k+1}; M += AL G^T */
-          const double* Pn = PK(w, k + 1);
+          const real* Pn = PK(w, k + 1);
           for (int j = 0; j < nx; ++j)
             for (int i = 0; i < n; ++i) {
-              double s = 0.0;
+              real s = 0.0;
               for (int l = 0; l < nx; ++l) s += G[i + nm * l] * Pn[l + nx * j];
               AL[i + nm * j] = s;
             }
           for (int c = 0; c < n; ++c)
             for (int i = c; i < n; ++i) {
-              double s = 0.0;
+              real s = 0.0;
               for (int l = 0; l < nx; ++l) s += AL[i + nm * l] * G[c + nm * l];
               M[i + nm * c] += s;
               if (i != c) M[c + nm * i] = M[i + nm * c];
             }
         } else { /* square root: AL = G Lxx_{k+1}; M += AL AL^T */
-          const double* Ln = LFK(w, k + 1);
+          const real* Ln = LFK(w, k + 1);
           const int off = w->nuk[k + 1];
           for (int j = 0; j < nx; ++j)
             for (int i = 0; i < n; ++i) {
-              double s = 0.0;
+              real s = 0.0;
               for (int l = j; l < nx; ++l) s += G[i + nm * l] * Ln[(off + l) + nm * (off + j)];
               AL[i + nm * j] = s;
             }
           for (int c = 0; c < n; ++c)
             for (int i = c; i < n; ++i) {
-              double s = 0.0;
+              real s = 0.0;
               for (int l = 0; l < nx; ++l) s += AL[i + nm * l] * AL[c + nm * l];
               M[i + nm * c] += s;
               if (i != c) M[c + nm * i] = M[i + nm * c];
@@ -465,26 +490,26 @@ static void kkt_solve(W* w, const srbd_ipm_args* a, int fact, int with_constr, c
       for (int i = 0; i < n; ++i) M[i + nm * i] += a->reg_prim;
       if (a->ric_alg == 0) {
         potrf_l_mn(n, nuk, M, nm); /* Lr (nu x nu), Ls (nx x nu) */
-        double* Lr = LRK(w, k);
-        double* Ls = LSK(w, k);
-        double* P = PK(w, k);
+        real* Lr = LRK(w, k);
+        real* Ls = LSK(w, k);
+        real* P = PK(w, k);
         for (int j = 0; j < nuk; ++j) {
           for (int i = 0; i < nuk; ++i) Lr[i + nu * j] = i >= j ? M[i + nm * j] : 0.0;
           for (int i = 0; i < nxk; ++i) Ls[i + nx * j] = M[(nuk + i) + nm * j];
         }
         for (int c = 0; c < nxk; ++c) /* P = M_xx - Ls Ls^T, symmetrized from the lower triangle */
           for (int i = c; i < nxk; ++i) {
-            double s = M[(nuk + i) + nm * (nuk + c)];
+            real s = M[(nuk + i) + nm * (nuk + c)];
             for (int l = 0; l < nuk; ++l) s -= Ls[i + nx * l] * Ls[c + nx * l];
             P[i + nx * c] = s;
             P[c + nx * i] = s;
           }
       } else {
         potrf_l_mn(n, n, M, nm);
-        double* Lf = LFK(w, k);
-        double* Lr = LRK(w, k);
-        double* Ls = LSK(w, k);
-        double* P = PK(w, k);
+        real* Lf = LFK(w, k);
+        real* Lr = LRK(w, k);
+        real* Ls = LSK(w, k);
+        real* P = PK(w, k);
         for (int j = 0; j < n; ++j)
           for (int i = 0; i < n; ++i) Lf[i + nm * j] = i >= j ? M[i + nm * j] : 0.0;
         for (int j = 0; j < nuk; ++j) {
@@ -493,7 +518,7 @@ static void kkt_solve(W* w, const srbd_ipm_args* a, int fact, int with_constr, c
         }
         for (int c = 0; c < nxk; ++c) /* P = Lxx Lxx^T */
           for (int i = c; i < nxk; ++i) {
-            double s = 0.0;
+            real s = 0.0;
             for (int l = 0; l <= c; ++l) s += Lf[(nuk + i) + nm * (nuk + l)] * Lf[(nuk + c) + nm * (nuk + l)];
             P[i + nx * c] = s;
             P[c + nx * i] = s;
@@ -503,39 +528,39 @@ static void kkt_solve(W* w, const srbd_ipm_args* a, int fact, int with_constr, c
     /* gradient */
     for (int i = 0; i < n; ++i) gt[i] = rhs_g[(size_t)k * nm + i];
     if (with_constr) {
-      double* v = w->tmp;
-      const double *gl = VC(w, gl, k), *gu = VC(w, gu, k);
+      real* v = w->tmp;
+      const real *gl = VC(w, gl, k), *gu = VC(w, gu, k);
       for (int j = 0; j < nc; ++j) v[j] = gl[j] - gu[j];
       apply_Jt_add(w, k, v, gt);
     }
     if (k < N) {
-      const double* Pn = PK(w, k + 1);
-      const double* pn = VX(w, p, k + 1);
-      const double* rb = rhs_b + (size_t)k * nx;
-      double* t = w->tmp;
+      const real* Pn = PK(w, k + 1);
+      const real* pn = VX(w, p, k + 1);
+      const real* rb = rhs_b + (size_t)k * nx;
+      real* t = w->tmp;
       for (int i = 0; i < nx; ++i) {
-        double s = 0.0;
+        real s = 0.0;
         for (int j = 0; j < nx; ++j) s += Pn[i + nx * j] * rb[j];
         t[i] = s + pn[i];
       }
       for (int i = 0; i < n; ++i) {
-        double s = 0.0;
+        real s = 0.0;
         for (int j = 0; j < nx; ++j) s += G[i + nm * j] * t[j];
         gt[i] += s;
       }
     }
     { /* lv = Lr^-1 g_u ; p = g_x - Ls lv */
-      const double* Lr = LRK(w, k);
-      const double* Ls = LSK(w, k);
-      double* lv = VN(w, lv, k);
-      double* p = VX(w, p, k);
+      const real* Lr = LRK(w, k);
+      const real* Ls = LSK(w, k);
+      real* lv = VN(w, lv, k);
+      real* p = VX(w, p, k);
       for (int i = 0; i < nuk; ++i) {
-        double s = gt[i];
+        real s = gt[i];
         for (int j = 0; j < i; ++j) s -= Lr[i + nu * j] * lv[j];
         lv[i] = pdiv(s, Lr[i + nu * i]);
       }
       for (int i = 0; i < nxk; ++i) {
-        double s = gt[nuk + i];
+        real s = gt[nuk + i];
         for (int j = 0; j < nuk; ++j) s -= Ls[i + nx * j] * lv[j];
         p[i] = s;
       }
@@ -544,37 +569,37 @@ static void kkt_solve(W* w, const srbd_ipm_args* a, int fact, int with_constr, c
   /* forward rollout */
   for (int k = 0; k <= N; ++k) {
     const int nuk = w->nuk[k], nxk = w->nxk[k], n = nuk + nxk;
-    const double* Lr = LRK(w, k);
-    const double* Ls = LSK(w, k);
-    const double* lv = VN(w, lv, k);
-    double* z = oz + (size_t)k * nm;
-    double* t = w->tmp;
+    const real* Lr = LRK(w, k);
+    const real* Ls = LSK(w, k);
+    const real* lv = VN(w, lv, k);
+    real* z = oz + (size_t)k * nm;
+    real* t = w->tmp;
     for (int i = 0; i < nuk; ++i) { /* t = Ls^T x + lv */
-      double s = 0.0;
+      real s = 0.0;
       for (int j = 0; j < nxk; ++j) s += Ls[j + nx * i] * z[nuk + j];
       t[i] = s + lv[i];
     }
     for (int i = nuk - 1; i >= 0; --i) { /* u = -Lr^-T t */
-      double s = t[i];
+      real s = t[i];
       for (int j = i + 1; j < nuk; ++j) s -= Lr[j + nu * i] * t[j];
       t[i] = pdiv(s, Lr[i + nu * i]);
     }
     for (int i = 0; i < nuk; ++i) z[i] = -t[i];
     if (k < N) {
-      const double* G = GK(w, k);
-      const double* rb = rhs_b + (size_t)k * nx;
-      double* zn = oz + (size_t)(k + 1) * nm;
+      const real* G = GK(w, k);
+      const real* rb = rhs_b + (size_t)k * nx;
+      real* zn = oz + (size_t)(k + 1) * nm;
       const int off = w->nuk[k + 1];
       for (int j = 0; j < nx; ++j) {
-        double s = 0.0;
+        real s = 0.0;
         for (int i = 0; i < n; ++i) s += G[i + nm * j] * z[i];
         zn[off + j] = s + rb[j];
       }
-      const double* Pn = PK(w, k + 1);
-      const double* pn = VX(w, p, k + 1);
-      double* pi = opi + (size_t)k * nx;
+      const real* Pn = PK(w, k + 1);
+      const real* pn = VX(w, p, k + 1);
+      real* pi = opi + (size_t)k * nx;
       for (int i = 0; i < nx; ++i) {
-        double s = 0.0;
+        real s = 0.0;
         for (int j = 0; j < nx; ++j) s += Pn[i + nx * j] * zn[off + j];
         pi[i] = s + pn[i];
       }
@@ -586,10 +611,10 @@ static void kkt_solve(W* w, const srbd_ipm_args* a, int fact, int with_constr, c
 static void compute_Gamma_gamma(W* w, int with_Gamma) {
   for (int k = 0; k <= w->N; ++k) {
     const int nc = w->nbk[k] + w->ngk[k];
-    double *ll = VC(w, ll, k), *lu = VC(w, lu, k), *tl = VC(w, tl, k), *tu = VC(w, tu, k);
-    double *ml = VC(w, ml, k), *mu = VC(w, mu, k);
+    real *ll = VC(w, ll, k), *lu = VC(w, lu, k), *tl = VC(w, tl, k), *tu = VC(w, tu, k);
+    real *ml = VC(w, ml, k), *mu = VC(w, mu, k);
     for (int j = 0; j < nc; ++j) {
-      const double til = 1.0 / tl[j], tiu = 1.0 / tu[j];
+      const real til = 1.0 / tl[j], tiu = 1.0 / tu[j];
       if (with_Gamma) {
         VC(w, Gl, k)[j] = (til * ll[j]) * ml[j];
         VC(w, Gu, k)[j] = (tiu * lu[j]) * mu[j];
@@ -604,12 +629,12 @@ static void compute_Gamma_gamma(W* w, int with_Gamma) {
 static void compute_dlam_dt(W* w) {
   for (int k = 0; k <= w->N; ++k) {
     const int nc = w->nbk[k] + w->ngk[k];
-    double* v = w->tmp;
+    real* v = w->tmp;
     apply_J(w, k, VN(w, dz, k), v);
     for (int j = 0; j < nc; ++j) {
-      const double ml = VC(w, ml, k)[j], mu = VC(w, mu, k)[j];
-      const double dtl = (v[j] - VC(w, rdl, k)[j]) * ml;
-      const double dtu = (-v[j] - VC(w, rdu, k)[j]) * mu;
+      const real ml = VC(w, ml, k)[j], mu = VC(w, mu, k)[j];
+      const real dtl = (v[j] - VC(w, rdl, k)[j]) * ml;
+      const real dtu = (-v[j] - VC(w, rdu, k)[j]) * mu;
       VC(w, dtl, k)[j] = dtl;
       VC(w, dtu, k)[j] = dtu;
       VC(w, dll, k)[j] = (-(VC(w, ll, k)[j] * dtl + VC(w, rml, k)[j]) / VC(w, tl, k)[j]) * ml;
@@ -619,37 +644,37 @@ static void compute_dlam_dt(W* w) {
 }
 
 /* d_compute_alpha_qp: exact min over the ratios (order independent) */
-static void step_length(const W* w, double* ap, double* ad) {
-  double alpha_p = 1.0, alpha_d = 1.0;
+static void step_length(const W* w, real* ap, real* ad) {
+  real alpha_p = 1.0, alpha_d = 1.0;
   for (int k = 0; k <= w->N; ++k) {
     const int nc = w->nbk[k] + w->ngk[k];
     for (int j = 0; j < nc; ++j) {
-      const double dtl = VC(w, dtl, k)[j], dtu = VC(w, dtu, k)[j], dll = VC(w, dll, k)[j], dlu = VC(w, dlu, k)[j];
-      if (dtl < 0.0) { double r = -VC(w, tl, k)[j] / dtl; if (r < alpha_p) alpha_p = r; }
-      if (dtu < 0.0) { double r = -VC(w, tu, k)[j] / dtu; if (r < alpha_p) alpha_p = r; }
-      if (dll < 0.0) { double r = -VC(w, ll, k)[j] / dll; if (r < alpha_d) alpha_d = r; }
-      if (dlu < 0.0) { double r = -VC(w, lu, k)[j] / dlu; if (r < alpha_d) alpha_d = r; }
+      const real dtl = VC(w, dtl, k)[j], dtu = VC(w, dtu, k)[j], dll = VC(w, dll, k)[j], dlu = VC(w, dlu, k)[j];
+      if (dtl < 0.0) { real r = -VC(w, tl, k)[j] / dtl; if (r < alpha_p) alpha_p = r; }
+      if (dtu < 0.0) { real r = -VC(w, tu, k)[j] / dtu; if (r < alpha_p) alpha_p = r; }
+      if (dll < 0.0) { real r = -VC(w, ll, k)[j] / dll; if (r < alpha_d) alpha_d = r; }
+      if (dlu < 0.0) { real r = -VC(w, lu, k)[j] / dlu; if (r < alpha_d) alpha_d = r; }
     }
   }
   *ap = alpha_p; *ad = alpha_d;
 }
 
 /* d_compute_mu_aff_qp: sum (lam + alpha dlam)(t + alpha dt) / nc_mask, stage by stage, lower then upper */
-static double mu_aff(const W* w, double alpha) {
-  double s = 0.0;
+static real mu_aff(const W* w, real alpha) {
+  real s = 0.0;
   for (int k = 0; k <= w->N; ++k) {
     const int nc = w->nbk[k] + w->ngk[k];
-    double sk = 0.0;
+    real sk = 0.0;
     for (int j = 0; j < nc; ++j) {
       sk += (VC(w, ll, k)[j] + alpha * VC(w, dll, k)[j]) * (VC(w, tl, k)[j] + alpha * VC(w, dtl, k)[j]);
       sk += (VC(w, lu, k)[j] + alpha * VC(w, dlu, k)[j]) * (VC(w, tu, k)[j] + alpha * VC(w, dtu, k)[j]);
     }
     s += sk;
   }
-  return s / (double)w->nc_mask;
+  return s / (real)w->nc_mask;
 }
 
-static double shorten(const srbd_ipm_args* a, double alpha) {
+static real shorten(const srbd_ipm_args* a, real alpha) {
   if (alpha < 1.0) {
     if (a->alpha_shorten == 0) return alpha * 0.995;
     return alpha * ((1.0 - alpha) * 0.99 + alpha * 0.9999999);
@@ -661,10 +686,10 @@ static int any_nan(const W* w) {
   for (int k = 0; k <= w->N; ++k) {
     const int n = w->nuk[k] + w->nxk[k];
     for (int i = 0; i < n; ++i)
-      if (isnan(VN(w, z, k)[i])) return 1;
+      if (R_ISNAN(VN(w, z, k)[i])) return 1;
   }
-  return isnan(w->mu_res) || isnan(w->res_max[0]) || isnan(w->res_max[1]) || isnan(w->res_max[2]) ||
-         isnan(w->res_max[3]);
+  return R_ISNAN(w->mu_res) || R_ISNAN(w->res_max[0]) || R_ISNAN(w->res_max[1]) || R_ISNAN(w->res_max[2]) ||
+         R_ISNAN(w->res_max[3]);
 }
 
 /* d_ocp_qp_ipm_solve (hpipm_d_ocp_qp_ipm.h:238), SURVEY.md Appendix C "MAIN".  Returns status. */
@@ -690,36 +715,36 @@ static int ipm_solve(W* w, const srbd_ipm_args* a, int* iter_out, double* stat, 
   }
   init_var(w, a);
   compute_res(w);
-  double mu = w->mu_res;
+  real mu = w->mu_res;
   if (stat && stat_rows > 0) {
     stat[5] = mu;
     for (int i = 0; i < 4; ++i) stat[6 + i] = w->res_max[i];
     stat[10] = w->obj;
   }
-  double alpha = 1.0;
+  real alpha = 1.0;
   int kk = 0;
   for (; kk < a->iter_max && alpha > a->alpha_min &&
          (w->res_max[0] > a->tol_stat || w->res_max[1] > a->tol_eq || w->res_max[2] > a->tol_ineq ||
           w->res_max[3] > a->tol_comp);
        ++kk) {
     double* row = (stat && kk + 1 < stat_rows) ? stat + SRBD_STAT_M * (kk + 1) : NULL;
-    memcpy(w->rml_bkp, w->rml, sizeof(double) * S * w->ncm);
-    memcpy(w->rmu_bkp, w->rmu, sizeof(double) * S * w->ncm);
+    memcpy(w->rml_bkp, w->rml, sizeof(real) * S * w->ncm);
+    memcpy(w->rmu_bkp, w->rmu, sizeof(real) * S * w->ncm);
     /* affine (predictor) step */
     compute_Gamma_gamma(w, 1);
     kkt_solve(w, a, 1, 1, w->rg, w->rb, w->dz, w->dpi);
     compute_dlam_dt(w);
-    double ap, ad;
+    real ap, ad;
     step_length(w, &ap, &ad);
-    double alpha_aff = ap < ad ? ap : ad;
+    real alpha_aff = ap < ad ? ap : ad;
     if (row) row[0] = alpha_aff;
     if (a->pred_corr == 1) {
-      const double mua = mu_aff(w, alpha_aff);
-      const double tmp = mua / mu;
-      const double sigma = tmp * tmp * tmp;
+      const real mua = mu_aff(w, alpha_aff);
+      const real tmp = mua / mu;
+      const real sigma = tmp * tmp * tmp;
       if (row) { row[1] = mua; row[2] = sigma; }
       /* centering-correction: res_m = res_m_bkp + dt*dlam - max(sigma*mu, tau_min), masked */
-      double sm = sigma * mu;
+      real sm = sigma * mu;
       sm = sm > a->tau_min ? sm : a->tau_min;
       for (int k = 0; k <= N; ++k) {
         const int nc = w->nbk[k] + w->ngk[k];
@@ -733,10 +758,10 @@ static int ipm_solve(W* w, const srbd_ipm_args* a, int* iter_out, double* stat, 
       compute_dlam_dt(w);
       step_length(w, &ap, &ad);
       if (a->cond_pred_corr == 1) {
-        const double al = ap < ad ? ap : ad;
-        const double muc = mu_aff(w, al);
+        const real al = ap < ad ? ap : ad;
+        const real muc = mu_aff(w, al);
         if (muc > a->cond_factor * mua) { /* centering direction only */
-          const double sm2 = sigma * mu;
+          const real sm2 = sigma * mu;
           for (int k = 0; k <= N; ++k) {
             const int nc = w->nbk[k] + w->ngk[k];
             for (int j = 0; j < nc; ++j) {
@@ -752,12 +777,12 @@ static int ipm_solve(W* w, const srbd_ipm_args* a, int* iter_out, double* stat, 
       }
     }
     if (!a->split_step) {
-      const double al = ap < ad ? ap : ad;
+      const real al = ap < ad ? ap : ad;
       ap = al; ad = al;
     }
     alpha = ap < ad ? ap : ad;
     if (row) { row[3] = ap; row[4] = ad; }
-    const double sp = shorten(a, ap), sd = shorten(a, ad);
+    const real sp = shorten(a, ap), sd = shorten(a, ad);
     /* d_update_var_qp: kkt_solve returned the minimizer of the step QP (gradient res_g~, offset res_b),
      * which IS the Newton direction; (z,t) move with alpha_prim, (pi,lam) with alpha_dual. */
     for (int k = 0; k <= N; ++k) {
@@ -766,7 +791,7 @@ static int ipm_solve(W* w, const srbd_ipm_args* a, int* iter_out, double* stat, 
       if (k < N)
         for (int i = 0; i < w->nx; ++i) VX(w, pi, k)[i] += sd * VX(w, dpi, k)[i];
       for (int j = 0; j < nc; ++j) {
-        const double ml = VC(w, ml, k)[j], mu_ = VC(w, mu, k)[j];
+        const real ml = VC(w, ml, k)[j], mu_ = VC(w, mu, k)[j];
         VC(w, tl, k)[j] += sp * VC(w, dtl, k)[j];
         VC(w, tu, k)[j] += sp * VC(w, dtu, k)[j];
         VC(w, ll, k)[j] += sd * VC(w, dll, k)[j];
@@ -809,54 +834,54 @@ static void write_outputs(W* w, const srbd_qp_dims* d, const srbd_ipm_args* a, c
   if (sol->x) {
     double* X = sol->x + q * (N + 1) * nx;
     memcpy(X, x0, sizeof(double) * nx);
-    for (int k = 1; k <= N; ++k) memcpy(X + (size_t)k * nx, VN(w, z, k) + w->nuk[k], sizeof(double) * nx);
+    for (int k = 1; k <= N; ++k) cpy_out(X + (size_t)k * nx, VN(w, z, k) + w->nuk[k], nx);
   }
   if (sol->u)
-    for (int k = 0; k < N; ++k) memcpy(sol->u + (q * N + k) * nu, VN(w, z, k), sizeof(double) * nu);
+    for (int k = 0; k < N; ++k) cpy_out(sol->u + (q * N + k) * nu, VN(w, z, k), nu);
   if (sol->lam || sol->t) {
     size_t nct = orc_qp_nct(d), o = 0;
     for (int k = 0; k <= N; ++k) {
       const int nc = w->nbk[k] + w->ngk[k];
       if (sol->lam) {
-        memcpy(sol->lam + q * nct + o, VC(w, ll, k), sizeof(double) * nc);
-        memcpy(sol->lam + q * nct + o + nc, VC(w, lu, k), sizeof(double) * nc);
+        cpy_out(sol->lam + q * nct + o, VC(w, ll, k), nc);
+        cpy_out(sol->lam + q * nct + o + nc, VC(w, lu, k), nc);
       }
       if (sol->t) {
-        memcpy(sol->t + q * nct + o, VC(w, tl, k), sizeof(double) * nc);
-        memcpy(sol->t + q * nct + o + nc, VC(w, tu, k), sizeof(double) * nc);
+        cpy_out(sol->t + q * nct + o, VC(w, tl, k), nc);
+        cpy_out(sol->t + q * nct + o + nc, VC(w, tu, k), nc);
       }
       o += 2 * (size_t)nc;
     }
   }
   /* K_k = -Lr^-T Ls^T for k>=1 */
-  double* Kbuf = dalloc((size_t)nu * nx + 1);
+  real* Kbuf = dalloc((size_t)nu * nx + 1);
   for (int k = 1; k < N; ++k) {
-    const double* Lr = LRK(w, k);
-    const double* Ls = LSK(w, k);
+    const real* Lr = LRK(w, k);
+    const real* Ls = LSK(w, k);
     for (int c = 0; c < nx; ++c) { /* column c of K: solve Lr^T y = Ls(c,:)^T */
       for (int i = nu - 1; i >= 0; --i) {
-        double s = Ls[c + nx * i];
+        real s = Ls[c + nx * i];
         for (int j = i + 1; j < nu; ++j) s -= Lr[j + nu * i] * Kbuf[j + nu * c];
         Kbuf[i + nu * c] = pdiv(s, Lr[i + nu * i]);
       }
       for (int i = 0; i < nu; ++i) Kbuf[i + nu * c] = -Kbuf[i + nu * c];
     }
-    if (sol->K) memcpy(sol->K + (q * N + k) * nu * nx, Kbuf, sizeof(double) * nu * nx);
+    if (sol->K) cpy_out(sol->K + (q * N + k) * nu * nx, Kbuf, nu * nx);
     if (sol->k) {
       double* kk = sol->k + (q * N + k) * nu;
-      const double* z = VN(w, z, k);
+      const real* z = VN(w, z, k);
       if (unconstrained) { /* true Riccati feed-forward: -Lr^-T lv */
-        const double* lv = VN(w, lv, k);
-        double t[64];
+        const real* lv = VN(w, lv, k);
+        real t[64];
         for (int i = nu - 1; i >= 0; --i) {
-          double s = lv[i];
+          real s = lv[i];
           for (int j = i + 1; j < nu; ++j) s -= Lr[j + nu * i] * t[j];
           t[i] = pdiv(s, Lr[i + nu * i]);
         }
         for (int i = 0; i < nu; ++i) kk[i] = -t[i];
       } else { /* absolute form by the identity u = K x + k */
         for (int i = 0; i < nu; ++i) {
-          double s = 0.0;
+          real s = 0.0;
           for (int j = 0; j < nx; ++j) s += Kbuf[i + nu * j] * z[nu + j];
           kk[i] = z[i] - s;
         }
@@ -864,17 +889,17 @@ static void write_outputs(W* w, const srbd_qp_dims* d, const srbd_ipm_args* a, c
     }
   }
   for (int k = 1; k <= N; ++k) {
-    if (sol->pi) memcpy(sol->pi + (q * (N + 1) + k) * nx, VX(w, pi, k - 1), sizeof(double) * nx);
-    if (sol->P) memcpy(sol->P + (q * (N + 1) + k) * nx * nx, PK(w, k), sizeof(double) * nx * nx);
+    if (sol->pi) cpy_out(sol->pi + (q * (N + 1) + k) * nx, VX(w, pi, k - 1), nx);
+    if (sol->P) cpy_out(sol->P + (q * (N + 1) + k) * nx * nx, PK(w, k), nx * nx);
     if (sol->p) {
       double* pp = sol->p + (q * (N + 1) + k) * nx;
       if (unconstrained) {
-        memcpy(pp, VX(w, p, k), sizeof(double) * nx);
+        cpy_out(pp, VX(w, p, k), nx);
       } else { /* pi_k = P_k x_k + p_k */
-        const double* P = PK(w, k);
-        const double* xk = VN(w, z, k) + w->nuk[k];
+        const real* P = PK(w, k);
+        const real* xk = VN(w, z, k) + w->nuk[k];
         for (int i = 0; i < nx; ++i) {
-          double s = 0.0;
+          real s = 0.0;
           for (int j = 0; j < nx; ++j) s += P[i + nx * j] * xk[j];
           pp[i] = VX(w, pi, k - 1)[i] - s;
         }
@@ -883,94 +908,94 @@ static void write_outputs(W* w, const srbd_qp_dims* d, const srbd_ipm_args* a, c
   }
   /* stage 0 (ocp_qp_ipm_solver.cpp:349-373) */
   {
-    const double* Lr0 = LRK(w, 0);
+    const real* Lr0 = LRK(w, 0);
     const double* A0 = qp->A + (q * N) * nx * nx;
     const double* B0 = qp->Bm + (q * N) * nx * nu;
     const double* b0 = qp->b + (q * N) * nx; /* the ORIGINAL b (:369) */
     const double* S0 = qp->S ? qp->S + (q * N) * nu * nx : NULL;
     const double* Q0 = qp->Q + (q * (N + 1)) * nx * nx;
     const double* q0 = qp->q + (q * (N + 1)) * nx;
-    const double* P1 = PK(w, 1);
+    const real* P1 = PK(w, 1);
     /* p1 in the convention exported above */
-    double* p1 = dalloc(nx);
-    if (unconstrained) memcpy(p1, VX(w, p, 1), sizeof(double) * nx);
+    real* p1 = dalloc(nx);
+    if (unconstrained) memcpy(p1, VX(w, p, 1), sizeof(real) * nx);
     else {
-      const double* x1 = VN(w, z, 1) + w->nuk[1];
+      const real* x1 = VN(w, z, 1) + w->nuk[1];
       for (int i = 0; i < nx; ++i) {
-        double s = 0.0;
+        real s = 0.0;
         for (int j = 0; j < nx; ++j) s += P1[i + nx * j] * x1[j];
         p1[i] = VX(w, pi, 0)[i] - s;
       }
     }
-    double* BtP = dalloc((size_t)nu * nx + 1);  /* B0^T P1 */
-    double* AtP = dalloc((size_t)nx * nx + 1);  /* A0^T P1 */
-    double* H0 = dalloc((size_t)nu * nx + 1);
-    double* GH = dalloc((size_t)nu * nx + 1);   /* G0^-1 H0 */
+    real* BtP = dalloc((size_t)nu * nx + 1);  /* B0^T P1 */
+    real* AtP = dalloc((size_t)nx * nx + 1);  /* A0^T P1 */
+    real* H0 = dalloc((size_t)nu * nx + 1);
+    real* GH = dalloc((size_t)nu * nx + 1);   /* G0^-1 H0 */
     for (int j = 0; j < nx; ++j)
       for (int i = 0; i < nu; ++i) {
-        double s = 0.0;
+        real s = 0.0;
         for (int l = 0; l < nx; ++l) s += B0[l + nx * i] * P1[l + nx * j];
         BtP[i + nu * j] = s;
       }
     for (int j = 0; j < nx; ++j)
       for (int i = 0; i < nx; ++i) {
-        double s = 0.0;
+        real s = 0.0;
         for (int l = 0; l < nx; ++l) s += A0[l + nx * i] * P1[l + nx * j];
         AtP[i + nx * j] = s;
       }
     for (int j = 0; j < nx; ++j)
       for (int i = 0; i < nu; ++i) {
-        double s = 0.0;
+        real s = 0.0;
         for (int l = 0; l < nx; ++l) s += BtP[i + nu * l] * A0[l + nx * j];
         H0[i + nu * j] = (S0 ? S0[i + nu * j] : 0.0) + s;
       }
     for (int c = 0; c < nx; ++c) { /* GH(:,c) = (Lr0 Lr0^T)^-1 H0(:,c) */
-      double y[64];
+      real y[64];
       for (int i = 0; i < nu; ++i) {
-        double s = H0[i + nu * c];
+        real s = H0[i + nu * c];
         for (int j = 0; j < i; ++j) s -= Lr0[i + nu * j] * y[j];
         y[i] = pdiv(s, Lr0[i + nu * i]);
       }
       for (int i = nu - 1; i >= 0; --i) {
-        double s = y[i];
+        real s = y[i];
         for (int j = i + 1; j < nu; ++j) s -= Lr0[j + nu * i] * y[j];
         y[i] = pdiv(s, Lr0[i + nu * i]);
       }
       for (int i = 0; i < nu; ++i) GH[i + nu * c] = y[i];
     }
-    double* K0 = dalloc((size_t)nu * nx + 1);
-    double* k0 = dalloc(nu + 1);
+    real* K0 = dalloc((size_t)nu * nx + 1);
+    real* k0 = dalloc(nu + 1);
     for (int i = 0; i < nu * nx; ++i) K0[i] = -GH[i];
-    const double* u0 = VN(w, z, 0);
+    const real* u0 = VN(w, z, 0);
     for (int i = 0; i < nu; ++i) {
-      double s = 0.0;
+      real s = 0.0;
       for (int j = 0; j < nx; ++j) s += K0[i + nu * j] * x0[j];
       k0[i] = u0[i] - s;
     }
-    if (sol->K) memcpy(sol->K + (q * N) * nu * nx, K0, sizeof(double) * nu * nx);
-    if (sol->k) memcpy(sol->k + (q * N) * nu, k0, sizeof(double) * nu);
-    double* P0 = dalloc((size_t)nx * nx + 1);
-    double* p0 = dalloc(nx + 1);
+    if (sol->K) cpy_out(sol->K + (q * N) * nu * nx, K0, nu * nx);
+    if (sol->k) cpy_out(sol->k + (q * N) * nu, k0, nu);
+    real* P0 = dalloc((size_t)nx * nx + 1);
+    real* p0 = dalloc(nx + 1);
     for (int j = 0; j < nx; ++j)
       for (int i = 0; i < nx; ++i) {
-        double s1 = 0.0, s2 = 0.0;
+        real s1 = 0.0, s2 = 0.0;
         for (int l = 0; l < nu; ++l) s1 += H0[l + nu * i] * GH[l + nu * j];
         for (int l = 0; l < nx; ++l) s2 += AtP[i + nx * l] * A0[l + nx * j];
         P0[i + nx * j] = (Q0[i + nx * j] - s1) + s2;
       }
     for (int i = 0; i < nx; ++i) {
-      double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      real s1 = 0.0, s2 = 0.0, s3 = 0.0;
       for (int l = 0; l < nx; ++l) s1 += A0[l + nx * i] * p1[l];
       for (int l = 0; l < nx; ++l) s2 += AtP[i + nx * l] * b0[l];
       for (int l = 0; l < nu; ++l) s3 += H0[l + nu * i] * k0[l];
       p0[i] = ((q0[i] + s1) + s2) + s3;
     }
-    if (sol->P) memcpy(sol->P + (q * (N + 1)) * nx * nx, P0, sizeof(double) * nx * nx);
-    if (sol->p) memcpy(sol->p + (q * (N + 1)) * nx, p0, sizeof(double) * nx);
+    if (sol->P) cpy_out(sol->P + (q * (N + 1)) * nx * nx, P0, nx * nx);
+    if (sol->p) cpy_out(sol->p + (q * (N + 1)) * nx, p0, nx);
     if (sol->pi) {
       double* pi0 = sol->pi + (q * (N + 1)) * nx;
       for (int i = 0; i < nx; ++i) {
-        double s = 0.0;
+        real s = 0.0;
         for (int j = 0; j < nx; ++j) s += P0[i + nx * j] * x0[j];
         pi0[i] = p0[i] + s;
       }
@@ -991,7 +1016,7 @@ size_t orc_qp_nct(const srbd_qp_dims* d) {
   return n;
 }
 
-int orc_qp_solve_one(const srbd_qp_dims* d, const srbd_ipm_args* a, const srbd_qp_host* qp,
+int ORC_NAME(orc_qp_solve_one)(const srbd_qp_dims* d, const srbd_ipm_args* a, const srbd_qp_host* qp,
                      const srbd_sol_host* sol, const srbd_stats_host* st, int stat_rows, int which) {
   W* w = w_create(d);
   embed_qp(w, d, qp, which);
@@ -1000,9 +1025,9 @@ int orc_qp_solve_one(const srbd_qp_dims* d, const srbd_ipm_args* a, const srbd_q
   /* primal warm start (ocp_qp_ipm_solver.cpp:328-333): x[i+1], u[i] */
   if (a->warm_start && qp->x_init && qp->u_init) {
     for (int k = 0; k <= N; ++k) {
-      double* z = VN(w, z, k);
-      if (k < N) memcpy(z, qp->u_init + (q * N + k) * nu, sizeof(double) * nu);
-      if (k > 0) memcpy(z + w->nuk[k], qp->x_init + (q * (N + 1) + k) * nx, sizeof(double) * nx);
+      real* z = VN(w, z, k);
+      if (k < N) cpy_in(z, qp->u_init + (q * N + k) * nu, nu);
+      if (k > 0) cpy_in(z + w->nuk[k], qp->x_init + (q * (N + 1) + k) * nx, nx);
     }
   }
   int iter = 0;
@@ -1013,12 +1038,13 @@ int orc_qp_solve_one(const srbd_qp_dims* d, const srbd_ipm_args* a, const srbd_q
   if (st) {
     if (st->iter) st->iter[q] = iter;
     if (st->status) st->status[q] = status;
-    if (st->res_max) memcpy(st->res_max + 4 * q, w->res_max, sizeof(double) * 4);
+    if (st->res_max) cpy_out(st->res_max + 4 * q, w->res_max, 4);
   }
   w_free(w);
   return status;
 }
 
+#ifndef ORC_QUAD
 int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
@@ -1026,19 +1052,21 @@ int orc_num_threads(void) {
   return 1;
 #endif
 }
+#endif
 
-int orc_qp_solve_batch(const srbd_qp_dims* d, const srbd_ipm_args* a, const srbd_qp_host* qp,
+int ORC_NAME(orc_qp_solve_batch)(const srbd_qp_dims* d, const srbd_ipm_args* a, const srbd_qp_host* qp,
                        const srbd_sol_host* sol, const srbd_stats_host* st, int stat_rows, int batch,
                        int threads) {
 #ifdef _OPENMP
   if (threads <= 0) threads = omp_get_max_threads();
 #pragma omp parallel for schedule(dynamic, 4) num_threads(threads)
 #endif
-  for (int i = 0; i < batch; ++i) orc_qp_solve_one(d, a, qp, sol, st, stat_rows, i);
+  for (int i = 0; i < batch; ++i) ORC_NAME(orc_qp_solve_one)(d, a, qp, sol, st, stat_rows, i);
   (void)threads;
   return 0;
 }
 
+#ifndef ORC_QUAD
 void orc_ipm_args_default(srbd_ipm_args* a) {
   memset(a, 0, sizeof(*a));
   /* OcpQpIpmSolverSettings defaults (ocp_qp_ipm_solver_settings.hpp:26-86) */
@@ -1049,3 +1077,4 @@ void orc_ipm_args_default(srbd_ipm_args* a) {
   a->cond_pred_corr = 1; a->cond_factor = 2.0; a->thr0 = 0.1;
   a->lam_min = a->t_min = a->tau_min = 1e-16; a->t_lam_min = 2; a->alpha_shorten = 1;
 }
+#endif

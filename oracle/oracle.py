@@ -21,17 +21,33 @@ _pkg = srbd_pkg.load()
 capi = _pkg.capi
 
 LIB_PATH = os.path.join(HERE, "_build", "libsrbd_oracle.so")
+QUAD_PATH = os.path.join(HERE, "_build", "libsrbd_oracle_quad.so")
 _lib = None
+_qlib = None
 
 
 def build(force=False):
     srcs = [os.path.join(HERE, f) for f in ("srbd_model.c", "ocp_qp_ipm.c", "pipeline.c", "srbd_oracle.h")]
     srcs.append(os.path.join(ROOT, "include", "srbd_b200.h"))
-    if (not force and os.path.exists(LIB_PATH)
-            and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs if os.path.exists(s))):
+    if (not force and all(os.path.exists(p) and all(os.path.getmtime(p) >= os.path.getmtime(s) for s in srcs
+                                                      if os.path.exists(s)) for p in (LIB_PATH, QUAD_PATH))):
         return LIB_PATH
-    subprocess.check_call(["make", "-C", HERE, "-B"], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", HERE, "-B", "all"], stdout=subprocess.DEVNULL)
     return LIB_PATH
+
+
+def quad_lib():
+    """The higher-precision ARBITER: ocp_qp_ipm.c compiled with __float128 arithmetic (same algorithm, constants,
+    operation order; inputs / outputs double)."""
+    global _qlib
+    if _qlib is None:
+        if not os.path.exists(QUAD_PATH):
+            build(force=True)
+        L = C.CDLL(QUAD_PATH)
+        L.orc_qp_solve_batch_q.argtypes = [C.POINTER(capi.QpDims), C.POINTER(capi.IpmArgs), C.POINTER(capi.QpHost),
+                                           C.POINTER(capi.SolHost), C.POINTER(capi.StatsHost), C.c_int, C.c_int, C.c_int]
+        _qlib = L
+    return _qlib
 
 
 def lib():
@@ -60,6 +76,7 @@ def lib():
     L.orc_barrier.restype = None
     L.orc_assemble_batch.argtypes = [MP, C.c_int, C.c_int, C.c_int, dp, dp, dp, u8] + [dp] * 13 + [C.c_int]
     L.orc_line_search.argtypes = [MP, C.c_int, dp, dp, dp, u8, dp, dp, dp, dp]
+    L.orc_line_search_mode.argtypes = [MP, C.c_int, C.c_int, dp, dp, dp, u8, dp, dp, dp, dp]
     L.orc_qp_solve_batch.argtypes = [QD, IA, C.POINTER(capi.QpHost), C.POINTER(capi.SolHost),
                                      C.POINTER(capi.StatsHost), C.c_int, C.c_int, C.c_int]
     L.orc_pipeline_batch.argtypes = [MP, IA, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, u8, dp, dp, dp,
@@ -148,20 +165,22 @@ def assemble(m, N, mode, x, u, xref, contact=None, threads=0):
     return o
 
 
-def line_search(m, N, x, u, xref, dx, du, alpha, contact=None):
+def line_search(m, N, x, u, xref, dx, du, alpha, contact=None, mode=0):
     """One QP.  Returns (x_new, u_new, alpha_new, converged, merit[3])."""
     x, u = _f(x).copy(), _f(u).copy()
     al = np.array([alpha], dtype=np.float64)
     merit = np.zeros(3)
     ct = None if contact is None else np.ascontiguousarray(contact, dtype=np.uint8)
-    conv = lib().orc_line_search(C.byref(m), N, capi.dptr(x), capi.dptr(u), capi.dptr(_f(xref)),
+    conv = lib().orc_line_search_mode(C.byref(m), N, mode, capi.dptr(x), capi.dptr(u), capi.dptr(_f(xref)),
                                  capi.u8ptr(ct), capi.dptr(_f(dx)), capi.dptr(_f(du)), capi.dptr(al),
                                  capi.dptr(merit))
     return x, u, float(al[0]), int(conv), merit
 
 
-def qp_solve(dims, args, arrays, batch, stat_rows=0, threads=0, want=("x", "u", "pi", "lam", "t", "P", "p", "K", "k")):
-    """arrays: dict of hpipm-cpp OcpQp fields batched [B][stage][...] (column-major blocks)."""
+def qp_solve(dims, args, arrays, batch, stat_rows=0, threads=0, want=("x", "u", "pi", "lam", "t", "P", "p", "K", "k"),
+             quad=False):
+    """arrays: dict of hpipm-cpp OcpQp fields batched [B][stage][...] (column-major blocks).
+    quad=True: the __float128 arbiter build of the same source (about 50x slower; inputs / outputs double)."""
     qp, keep = capi.make_qp_host(arrays)
     N, nx, nu = dims.N, dims.nx, dims.nu
     nct = capi.qp_nct(dims)
@@ -180,8 +199,8 @@ def qp_solve(dims, args, arrays, batch, stat_rows=0, threads=0, want=("x", "u", 
     if stat_rows > 0:
         out["stat"] = np.zeros((batch, stat_rows, capi.SRBD_STAT_M))
         st.stat = capi.dptr(out["stat"])
-    lib().orc_qp_solve_batch(C.byref(dims), C.byref(args), C.byref(qp), C.byref(sol), C.byref(st),
-                             stat_rows, batch, threads)
+    fn = quad_lib().orc_qp_solve_batch_q if quad else lib().orc_qp_solve_batch
+    fn(C.byref(dims), C.byref(args), C.byref(qp), C.byref(sol), C.byref(st), stat_rows, batch, threads)
     del keep
     return out
 

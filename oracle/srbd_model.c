@@ -358,7 +358,7 @@ void orc_assemble(const srbd_model_params* m, int N, int mode, const double* x, 
 }
 
 /* cost of one stage as the line search evaluates it (NMPC_solver.cpp:166-187, 213-231) */
-static void stage_merit(const srbd_model_params* m, int N, int k, const double* x, const double* u,
+static void stage_merit(const srbd_model_params* m, int N, int mode, int k, const double* x, const double* u,
                         const double* xref, const uint8_t* contact, double* phi, double* theta,
                         double* Jx, double* Ju) {
   const double* xk = x + 12 * k;
@@ -389,6 +389,10 @@ static void stage_merit(const srbd_model_params* m, int N, int k, const double* 
   double bsum = 0.0, db[24];
   for (int g = 0; g < 24; ++g) {
     double bv;
+    db[g] = 0.0;
+    /* HARD_INEQ extension: the hard rows are constraints of the QP, not cost terms (only the rows the assembly keeps
+     * as a relaxed barrier enter the merit function); mode 0 = the reference, all 24 rows */
+    if (mode == SRBD_HARD_INEQ && !row_is_soft_in_hard_mode(g)) continue;
     orc_barrier(fc[g], m->mu_b, m->theta_b, &bv, &db[g], NULL);
     bsum += bv;
   }
@@ -409,6 +413,12 @@ static void stage_merit(const srbd_model_params* m, int N, int k, const double* 
 int orc_line_search(const srbd_model_params* m, int N, double* x, double* u, const double* xref,
                     const uint8_t* contact, const double* dx, const double* du, double* alpha,
                     double* merit) {
+  return orc_line_search_mode(m, N, SRBD_BARRIER_SOFT, x, u, xref, contact, dx, du, alpha, merit);
+}
+
+int orc_line_search_mode(const srbd_model_params* m, int N, int mode, double* x, double* u, const double* xref,
+                         const uint8_t* contact, const double* dx, const double* du, double* alpha,
+                         double* merit) {
   const double theta_max = 1e-6, theta_min = 5e-10, eta = 1e-4, byta_phi = 1e-6, byta_theta = 1e-6,
                byta_alpha = 0.5, alpha_min = 1e-4; /* NMPC_solver.h:97-103 */
   double theta = 0.0, phi = 0.0, dphi = 0.0;
@@ -416,7 +426,7 @@ int orc_line_search(const srbd_model_params* m, int N, double* x, double* u, con
   double* Ju = (double*)malloc(sizeof(double) * 12 * (N > 0 ? N : 1));
   double* xa = (double*)malloc(sizeof(double) * 12 * (N + 1));
   double* ua = (double*)malloc(sizeof(double) * 12 * (N > 0 ? N : 1));
-  for (int k = 0; k <= N; ++k) stage_merit(m, N, k, x, u, xref, contact, &phi, &theta, Jx + 12 * k, k < N ? Ju + 12 * k : NULL);
+  for (int k = 0; k <= N; ++k) stage_merit(m, N, mode, k, x, u, xref, contact, &phi, &theta, Jx + 12 * k, k < N ? Ju + 12 * k : NULL);
   for (int k = 0; k <= N; ++k) { /* :191-198 */
     double s = 0.0;
     for (int i = 0; i < 12; ++i) s += dx[12 * k + i] * Jx[12 * k + i];
@@ -431,7 +441,7 @@ int orc_line_search(const srbd_model_params* m, int N, double* x, double* u, con
     double theta_a = 0.0, phi_a = 0.0;
     for (int i = 0; i < 12 * (N + 1); ++i) xa[i] = x[i] + *alpha * dx[i];
     for (int i = 0; i < 12 * N; ++i) ua[i] = u[i] + *alpha * du[i];
-    for (int k = 0; k <= N; ++k) stage_merit(m, N, k, xa, ua, xref, contact, &phi_a, &theta_a, NULL, NULL);
+    for (int k = 0; k <= N; ++k) stage_merit(m, N, mode, k, xa, ua, xref, contact, &phi_a, &theta_a, NULL, NULL);
     int accept = 0;
     if (theta_a > theta_max) {
       if (theta_a < (1.0 - byta_theta) * theta) accept = 1;

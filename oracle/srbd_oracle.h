@@ -68,6 +68,11 @@ void orc_assemble(const srbd_model_params* m, int N, int mode, const double* x, 
 int orc_line_search(const srbd_model_params* m, int N, double* x, double* u, const double* xref,
                     const uint8_t* contact, const double* dx, const double* du, double* alpha,
                     double* merit);
+/* The same for a step that came from a QP assembled in `mode`: in SRBD_HARD_INEQ (the extension of
+ * NMPC_solver.cpp:300-304) only the rows the assembly keeps as a relaxed barrier enter phi / dphi. */
+int orc_line_search_mode(const srbd_model_params* m, int N, int mode, double* x, double* u,
+                         const double* xref, const uint8_t* contact, const double* dx, const double* du,
+                         double* alpha, double* merit);
 
 /* ---- OCP-QP IPM (hpipm::OcpQpIpmSolver::solve semantics) --------------------------------------------- */
 /* Solves ONE QP (index `which` of the batch views in qp / sol / st).  Returns the HpipmStatus. */

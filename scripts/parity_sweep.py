@@ -46,6 +46,43 @@ for s in range(shards):
                   D=qp["D"], lg=qp["lg"], ug=np.zeros_like(qp["lg"]), lg_mask=qp["lg_mask"],
                   ug_mask=np.zeros_like(qp["lg"]), x0=w["x0"] - w["x"][:, 0])
     rid = orc.qp_solve(make_dims(N=N), orc.ipm_args(**S), arrays, per, want=("x", "u", "t"))
+    # ---- the higher-precision ARBITER (the same algorithm in __float128, oracle/Makefile ORC_QUAD) on every QP where
+    # the GPU and the double oracle disagree on identical inputs: iteration count / status, or x / u / t beyond 1e-9
+    # (at most ARB_MAX per shard, the worst first).  It says which side is closer to the exact-arithmetic iterates.
+    ARB_MAX = int(os.environ.get("SRBD_ARBITER_MAX", "384"))
+    tl_ = rid["t"].reshape(per, N, 48)[:, :, :24]; gl_ = sol["t"].reshape(per, N, 48)[:, :, :24]
+    e_all = np.maximum.reduce([rel(sol["x"], rid["x"]), rel(sol["u"], rid["u"]), rel(gl_, tl_)])
+    e_all = np.where(np.isfinite(e_all), e_all, np.inf)
+    flag = (st["iter"] != rid["iter"]) | (st["status"] != rid["status"]) | (e_all > 1e-9)
+    cand = np.flatnonzero(flag)
+    cand = cand[np.argsort(-(e_all[cand] + 1e3 * ((st["iter"] != rid["iter"]) | (st["status"] != rid["status"]))[cand]))][:ARB_MAX]
+    arb = dict(flagged=int(flag.sum()), examined=int(len(cand)))
+    if len(cand):
+        sub = {k: np.ascontiguousarray(v[cand]) for k, v in arrays.items()}
+        t0 = time.perf_counter()
+        rq = orc.qp_solve(make_dims(N=N), orc.ipm_args(**S), sub, len(cand), want=("x", "u", "t"), quad=True)
+        arb["seconds"] = time.perf_counter() - t0
+        tq = rq["t"].reshape(len(cand), N, 48)[:, :, :24]
+        eg = dict(x=rel(sol["x"][cand], rq["x"]), u=rel(sol["u"][cand], rq["u"]), t=rel(gl_[cand], tq))
+        eo = dict(x=rel(rid["x"][cand], rq["x"]), u=rel(rid["u"][cand], rq["u"]), t=rel(tl_[cand], tq))
+        conv = (rq["status"] == 0) & (st["status"][cand] == 0) & (rid["status"][cand] == 0)
+        arb.update(
+            arbiter_status_counts=np.bincount(rq["status"], minlength=5).tolist(),
+            gpu_iter_equals_arbiter=int((st["iter"][cand] == rq["iter"]).sum()),
+            oracle_iter_equals_arbiter=int((rid["iter"][cand] == rq["iter"]).sum()),
+            gpu_status_equals_arbiter=int((st["status"][cand] == rq["status"]).sum()),
+            oracle_status_equals_arbiter=int((rid["status"][cand] == rq["status"]).sum()),
+            all_three_converged=int(conv.sum()),
+            gpu_closer={k: int((eg[k][conv] <= eo[k][conv]).sum()) for k in eg},
+            gpu_vs_arbiter_max={k: float(eg[k][conv].max()) if conv.any() else None for k in eg},
+            oracle_vs_arbiter_max={k: float(eo[k][conv].max()) if conv.any() else None for k in eo},
+            gpu_vs_arbiter_median={k: float(np.median(eg[k][conv])) if conv.any() else None for k in eg},
+            oracle_vs_arbiter_median={k: float(np.median(eo[k][conv])) if conv.any() else None for k in eo},
+            disagreements=[dict(qp=int(start + i), gpu=[int(st["status"][i]), int(st["iter"][i])],
+                                oracle=[int(rid["status"][i]), int(rid["iter"][i])],
+                                arbiter=[int(rq["status"][j]), int(rq["iter"][j])])
+                           for j, i in enumerate(cand)
+                           if st["iter"][i] != rid["iter"][i] or st["status"][i] != rid["status"][i]][:64])
     del lin, qp, arrays
     tl = rid["t"].reshape(per, N, 48)[:, :, :24]   # lower side (the upper side is masked)
     gl = sol["t"].reshape(per, N, 48)[:, :, :24]
@@ -63,6 +100,7 @@ for s in range(shards):
                relerr_max={k: float(v.max()) for k, v in e.items()},
                relerr_p999={k: float(np.quantile(v, 0.999)) for k, v in e.items()},
                frac_below_1e9={k: float((v <= 1e-9).mean()) for k, v in e.items()}, cpu_seconds=dt,
+               arbiter=arb,
                identical=dict(iter_mismatch=int((st["iter"] != rid["iter"]).sum()),
                               status_mismatch=int((st["status"] != rid["status"]).sum()),
                               cpu_status_counts=np.bincount(rid["status"], minlength=5).tolist(),

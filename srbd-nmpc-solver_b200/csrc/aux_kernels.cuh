@@ -158,6 +158,8 @@ __global__ void __launch_bounds__(128) pack_kernel(const PackParams p) {
 // ---------------------------------------------------------------------------------------------------
 struct LsParams {
   int B, N;
+  int mode;              // assemble mode of the QP that produced the step: in SRBD_HARD_INEQ only the rows K2 kept as a
+                         // relaxed barrier (row_soft_in_hard_mode) enter the merit function and its gradient
   double* x;             // [B][N+1][12] in/out
   double* u;             // [B][N][12]   in/out
   const double* xref;
@@ -225,6 +227,8 @@ __device__ __forceinline__ void stage_merit(const srbd_model_params& m, const do
 #pragma unroll
   for (int i = 0; i < 12; ++i) Ju[i] = 0.0;
   for (int g = 0; g < 24; ++g) {
+    // hard rows are constraints of the QP, not cost terms: phi / dphi must describe the cost the QP step minimized
+    if (p.mode == SRBD_HARD_INEQ && !row_soft_in_hard_mode(g)) continue;
     double v = 0.0;
 #pragma unroll
     for (int j = 0; j < 12; ++j) v += Ac[g * 12 + j] * u[j];
@@ -314,17 +318,26 @@ __global__ void __launch_bounds__(128) line_search_kernel(const LsParams p, cons
 }
 
 // ---------------------------------------------------------------------------------------------------
-// FP64 FMA peak probe (the roofline denominator MEASURED_PEAKS.json does not carry):
-// 8 independent DFMA chains per thread, enough resident warps to saturate the FP64 pipe.
+// FP64 peak probe (the roofline denominator MEASURED_PEAKS.json does not carry): 8 independent
+// DMMA m8n8k4 chains per warp (256 FMAs per instruction), 32 resident warps per SM.  DMMA and DFMA share ONE FP64
+// datapath on B200 (scripts/microbench/fp64_pipes.cu: 36.9 vs 35.8 TFLOP/s); the DMMA form saturates it with fewer
+// issue slots, so it is the stabler figure.  Run as a short burst BEFORE the timed loop (bench.py): after seconds of
+// sustained load the board sits on its 1000 W cap and the same probe reads 30-35.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double seed) {
-  double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
-  const double m = 1.0000001, c = 1e-9;
-  for (int i = 0; i < iters; ++i) {
-    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
-    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  double c0[8], c1[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { c0[i] = seed + i; c1[i] = i; }
+  const double a = 1.0000001, b = 0.5;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                   : "+d"(c0[i]), "+d"(c1[i]) : "d"(a), "d"(b));
   }
-  const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c0[i] + c1[i];
   if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 

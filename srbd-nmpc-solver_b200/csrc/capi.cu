@@ -54,6 +54,7 @@ struct srbd_ctx {
   int assembled_mode = -1;   // >= 0: the packed QP came from srbd_assemble (K2) in that mode
   int grid = 0, stat_rows = 0;
   bool export_ric = false, export_stat = false;
+  bool ric_valid = false, stat_valid = false;  // the LAST solve wrote the Riccati exports (+ pi[0]) / the statistics table
   long long launches = 0;
   std::string err;
   int sm_count = 0;
@@ -576,6 +577,7 @@ static int launch_generic(srbd_ctx* ctx, const int* qlist, const int* qcount) {
   ctx->launches++;
   CU(cudaGetLastError());
   ctx->solved = true;
+  if (!qlist) { ctx->ric_valid = ctx->export_ric; ctx->stat_valid = ctx->export_stat; }
   return SRBD_OK;
 }
 
@@ -625,6 +627,8 @@ static int solve_srbd_variant(srbd_ctx* ctx) {
   ctx->launches++;
   CU(cudaGetLastError());
   ctx->solved = true;
+  ctx->ric_valid = false;   // the variant exports neither P, p, K, k nor pi[0] nor the statistics table
+  ctx->stat_valid = false;
   if (rescue) return launch_generic(ctx, ctx->d_retry, ctx->d_retry + ctx->B);
   return SRBD_OK;
 }
@@ -665,8 +669,9 @@ int srbd_download_solution(srbd_ctx* ctx, const srbd_sol_host* sol) {
   auto dl = [&](double* dst, const double* src, size_t n) -> cudaError_t {
     return dst ? cudaMemcpyAsync(dst, src, n * D, cudaMemcpyDeviceToHost, ctx->stream) : cudaSuccess;
   };
-  if ((sol->P || sol->p || sol->K || sol->k) && !ctx->d_P)
-    return fail(ctx, SRBD_ERR_STATE, "Riccati outputs were not exported: call srbd_set_outputs(ctx, 1, ..) before the solve");
+  if ((sol->P || sol->p || sol->K || sol->k) && !(ctx->d_P && ctx->ric_valid))
+    return fail(ctx, SRBD_ERR_STATE, "Riccati outputs were not exported by the last solve: call srbd_set_outputs(ctx, 1, ..) "
+                                     "before srbd_qp_solve (pi[0] is only produced together with them)");
   CU(dl(sol->x, ctx->d_sol_x, B * S * L.nx)); CU(dl(sol->u, ctx->d_sol_u, B * N * L.nu));
   CU(dl(sol->pi, ctx->d_sol_pi, B * S * L.nx));
   CU(dl(sol->lam, ctx->d_sol_lam, B * (size_t)L.nct)); CU(dl(sol->t, ctx->d_sol_t, B * (size_t)L.nct));
@@ -685,7 +690,8 @@ int srbd_download_stats(srbd_ctx* ctx, const srbd_stats_host* st) {
   if (st->status) CU(cudaMemcpyAsync(st->status, ctx->d_status, B * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   if (st->res_max) CU(cudaMemcpyAsync(st->res_max, ctx->d_resmax, B * 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   if (st->stat) {
-    if (!ctx->d_stat) return fail(ctx, SRBD_ERR_STATE, "statistics table was not exported: srbd_set_outputs(ctx, .., 1)");
+    if (!ctx->d_stat || !ctx->stat_valid)
+      return fail(ctx, SRBD_ERR_STATE, "statistics table was not exported by the last solve: srbd_set_outputs(ctx, .., 1)");
     CU(cudaMemcpyAsync(st->stat, ctx->d_stat, B * (size_t)ctx->stat_rows * SRBD_STAT_M * sizeof(double),
                        cudaMemcpyDeviceToHost, ctx->stream));
   }
@@ -709,6 +715,7 @@ int srbd_line_search(srbd_ctx* ctx) {
   CU(cudaSetDevice(ctx->device));
   LsParams p{};
   p.B = ctx->B; p.N = ctx->L.N;
+  p.mode = ctx->assembled_mode == SRBD_HARD_INEQ ? SRBD_HARD_INEQ : SRBD_BARRIER_SOFT;
   p.x = ctx->d_x; p.u = ctx->d_u; p.xref = ctx->d_xref; p.contact = ctx->have_contact ? ctx->d_contact : nullptr;
   p.dx = ctx->d_sol_x; p.du = ctx->d_sol_u; p.alpha = ctx->d_alpha; p.converged = ctx->d_conv; p.merit = ctx->d_merit;
   line_search_kernel<<<(ctx->B + 3) / 4, 128, 0, ctx->stream>>>(p, ctx->d_model);
@@ -783,7 +790,7 @@ int srbd_solve_host(srbd_ctx* ctx, int mode, const double* x, const double* u, c
 int srbd_fp64_peak(srbd_ctx* ctx, double* flops_per_s) {
   if (!ctx || !flops_per_s) return SRBD_ERR_ARG;
   CU(cudaSetDevice(ctx->device));
-  const int blocks = ctx->sm_count * 8, threads = 256, iters = 20000;
+  const int blocks = ctx->sm_count * 4, threads = 256, iters = 4096;  // 32 warps per SM, ~3 ms per launch
   double* d_out = nullptr;
   CU(dalloc(&d_out, (size_t)blocks * threads));
   cudaEvent_t e0, e1;
@@ -798,7 +805,7 @@ int srbd_fp64_peak(srbd_ctx* ctx, double* flops_per_s) {
     CU(cudaEventSynchronize(e1));
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, e0, e1));
-    const double fl = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3);
+    const double fl = 2.0 * 256.0 * 8.0 * (double)iters * blocks * (threads / 32) / (ms * 1e-3);  // 8 DMMA x 256 FMA per warp and trip
     if (rep > 0 && fl > best) best = fl;
   }
   cudaEventDestroy(e0);

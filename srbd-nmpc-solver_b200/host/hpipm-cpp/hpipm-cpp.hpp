@@ -298,10 +298,10 @@ class OcpQpIpmSolver {
       }
     }
     // flatten into the batch-contiguous column-major layout of srbd_qp_host
-    auto cat = [&](size_t per, auto getter, size_t stages) {
+    auto cat = [&](size_t per, auto getter, size_t stages, size_t first = 0) {
       std::vector<double> v(static_cast<size_t>(B) * stages * per, 0.0);
       for (int b = 0; b < B; ++b)
-        for (size_t i = 0; i < stages; ++i) {
+        for (size_t i = first; i < stages; ++i) {
           const double* src = getter((*qps[b])[i]);
           if (src && per) std::memcpy(v.data() + (static_cast<size_t>(b) * stages + i) * per, src, per * sizeof(double));
         }
@@ -315,8 +315,9 @@ class OcpQpIpmSolver {
     auto R = cat(nu * nu, [](const OcpQp& q) { return q.R.data(); }, N);
     auto qv = cat(nx, [](const OcpQp& q) { return q.q.data(); }, N + 1);
     auto rv = cat(nu, [](const OcpQp& q) { return q.r.data(); }, N);
-    auto lbx = cat(nbx, [&](const OcpQp& q) { return q.lbx.size() ? q.lbx.data() : nullptr; }, N + 1);
-    auto ubx = cat(nbx, [&](const OcpQp& q) { return q.ubx.size() ? q.ubx.data() : nullptr; }, N + 1);
+    // (stage 0 is skipped: nbx[0] := 0 in the solver, and uniformDims() lets nbx[0] differ from nbx)
+    auto lbx = cat(nbx, [&](const OcpQp& q) { return q.lbx.size() ? q.lbx.data() : nullptr; }, N + 1, 1);
+    auto ubx = cat(nbx, [&](const OcpQp& q) { return q.ubx.size() ? q.ubx.data() : nullptr; }, N + 1, 1);
     auto lbu = cat(nbu, [](const OcpQp& q) { return q.lbu.data(); }, N);
     auto ubu = cat(nbu, [](const OcpQp& q) { return q.ubu.data(); }, N);
     auto C = cat(ng * nx, [&](const OcpQp& q) { return q.C.size() ? q.C.data() : nullptr; }, N);
@@ -359,7 +360,19 @@ class OcpQpIpmSolver {
           if (i < N) std::memcpy(uin.data() + (b * N + i) * nu, (*sols[b])[i].u.data(), nu * sizeof(double));
         }
     }
-    const OcpQp& first = (*qps[0])[N > 1 ? 1 : 0];
+    // The C-ABI takes ONE index set for idxbx (stages 1..N) and one for idxbu (stages 0..N-1), shared by the batch;
+    // the reference passes them per stage (ocp_qp_ipm_solver.cpp:263-272).  Differing sets would silently put the
+    // bounds on the wrong variables: refuse them.
+    for (int b = 0; b < B; ++b)
+      for (size_t i = 0; i <= N; ++i) {
+        const OcpQp& s = (*qps[b])[i];
+        if (i >= 1 && nbx && s.idxbx != (*qps[0])[N].idxbx)
+          throw std::runtime_error("ocp_qp[" + std::to_string(i) + "].idxbx differs between stages / batch entries: the "
+                                   "B200 path needs one idxbx for stages 1..N");
+        if (i < N && nbu && s.idxbu != (*qps[0])[0].idxbu)
+          throw std::runtime_error("ocp_qp[" + std::to_string(i) + "].idxbu differs between stages / batch entries: the "
+                                   "B200 path needs one idxbu for stages 0..N-1");
+      }
     srbd_qp_host h{};
     h.A = A.data(); h.Bm = Bm.data(); h.b = bv.data(); h.Q = Q.data(); h.S = S.data(); h.R = R.data(); h.q = qv.data(); h.r = rv.data();
     h.idxbx = nbx ? (*qps[0])[N].idxbx.data() : nullptr; h.lbx = lbx.data(); h.ubx = ubx.data(); h.lbx_mask = lbxm.data(); h.ubx_mask = ubxm.data();
@@ -368,7 +381,6 @@ class OcpQpIpmSolver {
     h.CN = CN.data(); h.lgN = lgN.data(); h.ugN = ugN.data(); h.lgN_mask = lgNm.data(); h.ugN_mask = ugNm.data();
     h.x0 = x0v.data();
     if (solver_settings_.warm_start) { h.x_init = xin.data(); h.u_init = uin.data(); }
-    (void)first;
 
     srbd_ipm_args a;
     srbd_ipm_args_default(&a);
