@@ -341,8 +341,9 @@ __global__ void __launch_bounds__(kLinThreads, SRBD_K1_MIN_CTAS) linearize_kerne
         dx0[i] = p.x0[(size_t)q * 12 + i] - x[i];
         p.dx0[(size_t)q * 12 + i] = dx0[i];
       }
-      double* raw = p.raw0 + (size_t)q * kRaw0Stride;
       const double minv = 1.0 / sm.mass;
+      if (p.raw0) {
+      double* raw = p.raw0 + (size_t)q * kRaw0Stride;
       // raw column-major A0 = I + dt jfx, B0 = dt jfu, b0 (the stage-0 reconstruction of the facade needs them)
       for (int e = 0; e < 288; ++e) raw[e] = 0.0;
       double* A0 = raw;
@@ -372,6 +373,18 @@ __global__ void __launch_bounds__(kLinThreads, SRBD_K1_MIN_CTAS) linearize_kerne
         for (int j = 0; j < 12; ++j) s += A0[i + 12 * j] * dx0[j];
         b0[i] = s + (-f[i]);
         raw[288 + i] = -f[i];
+      }
+      } else {
+        // throughput path (no raw stage-0 blocks: they only serve the Riccati exports / getters): the same A0 entries,
+        // element (i, j) = the term of row 12 + j, column i of the dense record, summed in the same order
+        c[39] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+          double s = 0.0;
+#pragma unroll
+          for (int j = 0; j < 12; ++j) s += babt_elem(c, 12 + j, i, dt, minv, false) * dx0[j];
+          b0[i] = s + (-f[i]);
+        }
       }
 #pragma unroll
       for (int i = 0; i < 12; ++i) c[27 + i] = b0[i];
@@ -434,6 +447,9 @@ struct AsmParams {
   double* dmask;  // [B][N+1][48]
   double* raw0;   // S0, Q0, q0 part
   double* fcon;   // [B][N][24] constraint values (diagnostics, NMPC_solver.cpp:289) or null
+  // optional work list: assemble only the QPs qlist[0 .. *qcount) (dense records for the rescue list of K3, capi.cu)
+  const int* qlist;
+  const int* qcount;
 };
 
 constexpr int kAsmThreads = 64;
@@ -490,25 +506,31 @@ __device__ __forceinline__ double rsq_elem(int i, int j, const double* c, const 
 // i.e. exactly the shared-memory R tile of the kernel followed by the two per-row vectors every sweep loads: one
 // linear cp.async stream and one base pointer instead of panel-prefix / strided-row gathers from three arrays.
 constexpr int kSrec = 192;
-template <int TYPE>
+// DENSE: also the full 28 x 24 record (generic kernel, getters, rescue pass); the throughput path writes the compact
+// record only (K3's SRBD variant reads nothing else: 192 instead of 1536 doubles per stage)
+template <int TYPE, bool DENSE>
 __device__ __forceinline__ void write_rsq(double* dst, double* srec, const double* c, const double* sAc,
                                           const double* sQ, const double* sQf, double R, int lane, int g_lo,
                                           int g_cnt) {
   constexpr int n = (TYPE == 2 ? 0 : 12) + (TYPE == 0 ? 0 : 12);
 #pragma unroll
-  for (int pnl = 0; pnl < 7; ++pnl)
+  for (int pnl = 0; pnl < (DENSE ? 7 : 3); ++pnl)
 #pragma unroll
     for (int sl = 0; sl < 3; ++sl) {
       const int e = lane + 32 * sl, j = e >> 2, i = 4 * pnl + (e & 3);
-      const double v = rsq_elem<TYPE>(i, j, c, sAc, sQ, sQf, R, g_lo, g_cnt);
-      dst[96 * pnl + e] = v;
-      // the R-tile prefix of panels 0..2: columns j <= 4 pnl + 3
-      if (pnl < 3 && j < 4 * pnl + 4) srec[(pnl == 0 ? 0 : (pnl == 1 ? 16 : 48)) + e] = v;
+      const bool in_tile = pnl < 3 && j < 4 * pnl + 4;   // the R-tile prefix of panels 0..2: columns j <= 4 pnl + 3
+      if (!DENSE && 32 * sl >= 16 * (pnl + 1)) continue; // (compile time: no lane of this slot is inside the prefix)
+      if (DENSE || in_tile) {
+        const double v = rsq_elem<TYPE>(i, j, c, sAc, sQ, sQf, R, g_lo, g_cnt);
+        if (DENSE) dst[96 * pnl + e] = v;
+        if (in_tile) srec[(pnl == 0 ? 0 : (pnl == 1 ? 16 : 48)) + e] = v;
+      }
     }
   if (lane < 24) srec[108 + lane] = lane < n ? rsq_elem<TYPE>(n, lane, c, sAc, sQ, sQf, R, g_lo, g_cnt) : 0.0;
   if (lane < 12) { srec[96 + lane] = 0.0; srec[132 + lane] = 0.0; }
 }
 
+template <bool DENSE>
 __global__ void __launch_bounds__(kAsmThreads) assemble_kernel(const AsmParams p, const ModelDev* __restrict__ md) {
   // compact per item: [0..24) ddb (barrier curvature per row, 0 for hard rows), [24..36) r, [36..48) q,
   // [48..72) lg = -f, stage kind in sk[]
@@ -521,11 +543,15 @@ __global__ void __launch_bounds__(kAsmThreads) assemble_kernel(const AsmParams p
   if (threadIdx.x == 0) sR = md->m.R;
   __syncthreads();
   const int S = p.N + 1;
-  const long long total = (long long)p.B * S;
-  const long long item0 = (long long)blockIdx.x * kAsmThreads;
+  // items are (QP, stage) pairs; with a work list the QP index is qlist[item / S] (the list is short: one grid-stride
+  // trip per 64 * gridDim.x items)
+  const long long total = (long long)(p.qlist ? *p.qcount : p.B) * S;
+  for (long long item0 = (long long)blockIdx.x * kAsmThreads; item0 < total; item0 += (long long)gridDim.x * kAsmThreads) {
   const long long item = item0 + threadIdx.x;
+  __syncthreads();  // (second trip: everyone is done reading sc)
   if (item < total) {
-    const int q = (int)(item / S), k = (int)(item % S);
+    const int qi = (int)(item / S), k = (int)(item % S);
+    const int q = p.qlist ? p.qlist[qi] : qi;
     double* c = sc[threadIdx.x];
     const double* xk = p.x + ((size_t)q * S + k) * 12;
     const double* xr = p.xref + ((size_t)q * S + k) * 12;
@@ -564,7 +590,7 @@ __global__ void __launch_bounds__(kAsmThreads) assemble_kernel(const AsmParams p
         c[24 + i] = sR * u[i] + r[i];                // r = R u + Ac^T db (NMPC_solver.cpp:309)
         c[36 + i] = sQ[i] * (xk[i] - xr[i]);         // q = Q (x - xref)  (:306)
       }
-      if (k == 0) {
+      if (DENSE && k == 0) {
         double* raw = p.raw0 + (size_t)q * kRaw0Stride;
         for (int e = 0; e < 144; ++e) {
           raw[300 + e] = 0.0;                              // S0
@@ -583,42 +609,49 @@ __global__ void __launch_bounds__(kAsmThreads) assemble_kernel(const AsmParams p
   const long long it0 = item0 + warp * 32;
   int k = (int)(it0 % S);
   for (int rI = 0; rI < 32; ++rI, k = (k == p.N ? 0 : k + 1)) {
-    const long long it = it0 + rI;
-    if (it >= total) break;
+    const long long it_ = it0 + rI;
+    if (it_ >= total) break;
+    // record index in the [B][N+1] arrays (with a work list: the listed QP's own records)
+    const long long it = p.qlist ? (long long)p.qlist[it_ / S] * S + k : it_;
     const double* c = sc[warp * 32 + rI];
     const int nu = k < p.N ? 12 : 0;
     // RSQrq: 28 x 24 panel-major
-    double* dst = p.rsq + (size_t)it * (28 * 24);
+    double* dst = DENSE ? p.rsq + (size_t)it * (28 * 24) : nullptr;
     double* sr = p.srec + (size_t)it * kSrec;
-    if (k == 0) write_rsq<0>(dst, sr, c, sAc, sQ, sQf, sR, lane, g_lo, g_cnt);
-    else if (k < p.N) write_rsq<1>(dst, sr, c, sAc, sQ, sQf, sR, lane, g_lo, g_cnt);
-    else write_rsq<2>(dst, sr, c, sAc, sQ, sQf, sR, lane, g_lo, g_cnt);
+    if (k == 0) write_rsq<0, DENSE>(dst, sr, c, sAc, sQ, sQf, sR, lane, g_lo, g_cnt);
+    else if (k < p.N) write_rsq<1, DENSE>(dst, sr, c, sAc, sQ, sQf, sR, lane, g_lo, g_cnt);
+    else write_rsq<2, DENSE>(dst, sr, c, sAc, sQ, sQf, sR, lane, g_lo, g_cnt);
     // DCt (n x 24): D^T = Ac^T in the u rows, C = 0; d = [lg | 0 | 0(-ug) | 0], masks
-    double* dd = p.dct + (size_t)it * (24 * 24);
-    double* dv = p.d + (size_t)it * 48;
-    double* dk = p.dmask + (size_t)it * 48;
+    double* dd = DENSE ? p.dct + (size_t)it * (24 * 24) : nullptr;
+    double* dv = DENSE ? p.d + (size_t)it * 48 : nullptr;
+    double* dk = DENSE ? p.dmask + (size_t)it * 48 : nullptr;
     if (k < p.N) {
+      if (DENSE) {
 #pragma unroll
-      for (int pnl = 0; pnl < 6; ++pnl)
+        for (int pnl = 0; pnl < 6; ++pnl)
 #pragma unroll
-        for (int sl = 0; sl < 3; ++sl) {
-          const int e = lane + 32 * sl, g = e >> 2, i = 4 * pnl + (e & 3);
-          dd[96 * pnl + e] = (i < nu) ? sAc[g * 12 + i] : 0.0;
-        }
+          for (int sl = 0; sl < 3; ++sl) {
+            const int e = lane + 32 * sl, g = e >> 2, i = 4 * pnl + (e & 3);
+            dd[96 * pnl + e] = (i < nu) ? sAc[g * 12 + i] : 0.0;
+          }
+      }
       for (int e = lane; e < 48; e += 32) {
         const bool lower = e < 24;
         const int g = lower ? e : e - 24;
         const bool hard = (p.mode == SRBD_HARD_INEQ) && !row_soft_in_hard_mode(g);
         const double dvv = (lower && p.mode == SRBD_HARD_INEQ) ? c[48 + g] : 0.0;
         const double dkk = (lower && hard) ? 1.0 : 0.0;
-        dv[e] = dvv;
-        dk[e] = dkk;
+        if (DENSE) { dv[e] = dvv; dk[e] = dkk; }
         if (lower) { sr[144 + g] = dvv; sr[168 + g] = dkk; }
       }
     } else {
-      for (int e = lane; e < 48; e += 32) { dv[e] = 0.0; dk[e] = 0.0; sr[144 + e] = 0.0; }
+      for (int e = lane; e < 48; e += 32) {
+        if (DENSE) { dv[e] = 0.0; dk[e] = 0.0; }
+        sr[144 + e] = 0.0;
+      }
     }
   }
+  }  // grid-stride trip
 }
 
 }  // namespace srbd

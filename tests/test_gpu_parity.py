@@ -34,7 +34,7 @@ def _dump_report():
 
 
 def check_iterates(sol, ref, ref_p, ref_q=None, fields=("x", "u", "pi", "lam", "t"), tol=TOL, strict=("x", "pi", "t"),
-                   bulk=0.85, label=None):
+                   bulk=0.85, label=None, floor=None):
     """GPU iterates vs the oracle's, PER QP (north_star: relative error <= 1e-9 on primal and dual iterates).
 
     e[i]    = normwise relative error GPU vs oracle of QP i
@@ -54,6 +54,8 @@ def check_iterates(sol, ref, ref_p, ref_q=None, fields=("x", "u", "pi", "lam", "
             q = q[:, 1:] if q is not None else None
         e, sens = relerr(a, b), relerr(c, b)
         yard = np.maximum(tol, 10 * sens)
+        if floor is not None:   # per-QP floor of a derived quantity (see the caller)
+            yard = np.maximum(yard, floor)
         rec = {"n": int(len(e)), "max": float(e.max()), "frac_le_tol": float((e <= tol).mean()),
                "sens_max": float(sens.max())}
         if q is not None:
@@ -163,7 +165,12 @@ def test_srbd_pipeline_parity(pkg, orc, mode, contact):
 
     def jt(o):
         return {"jt": np.einsum("bkgj,bkg->bkj", D, o["lam"].reshape(B, N, 48)[:, :, :24])}
-    check_iterates(jt(sol), jt(ref), jt(ref_p), jt(ref_q), fields=("jt",), strict=(), label="pipeline_%s_B%d" % (contact, B))
+    # J^T lam is what the stationarity residual determines: two points that both satisfy |res_stat| <= tol may differ in
+    # it by the sum of their residuals, i.e. relatively by (res_gpu + res_oracle) / |J^T lam| -- the per-QP floor
+    jn = np.maximum(np.linalg.norm(jt(ref)["jt"].reshape(B, -1), axis=1), 1e-300)
+    floor = (st["res_max"][:, 0] + ref["res_max"][:, 0]) * np.sqrt(N * 12.0) / jn
+    check_iterates(jt(sol), jt(ref), jt(ref_p), jt(ref_q), fields=("jt",), strict=(), label="pipeline_%s_B%d" % (contact, B),
+                   floor=floor)
     # final residual norms are rounding-level quantities: both sides must be below tol, and agree in magnitude
     assert (st["res_max"] <= 1e-8).all() and (ref["res_max"] <= 1e-8).all()
     # complementarity gap max(lam*t): products of iterates that agree to ~1e-9 relative, evaluated on the row where
