@@ -16,6 +16,11 @@ ts = []
 for _ in range(reps):
     t0 = time.perf_counter(); ctx.qp_solve(); ctx.sync(); ts.append(time.perf_counter() - t0)
 st = ctx.download_stats()
+if os.environ.get("SRBD_PROF"):   # a -DSRBD_K3_PROFILE=1 build: per-sweep clock64 sums of the last solve
+    h = ctx.batch_stats()["iter_hist"][48:53]
+    tot = float(sum(h))
+    print("per-sweep cycles per QP: residual %.0f  factor %.0f  backvec %.0f  forward(pred) %.0f  forward(fin) %.0f  | shares %s" % (
+        *[v / B for v in h], " ".join("%.1f%%" % (100 * v / tot) for v in h)))
 t = min(ts)
 print("ok B=%d iters=%.3f allconv=%s  K3 %.2f ms  -> %.0f solves/s (generic=%s)" % (
     B, st["iter"].mean(), (st["status"] == 0).all(), 1e3 * t, B / t, os.environ.get("SRBD_K3_GENERIC", "0")))

@@ -54,7 +54,12 @@ struct srbd_ctx {
   int assembled_mode = -1;   // >= 0: the packed QP came from srbd_assemble (K2) in that mode
   int grid = 0, stat_rows = 0;
   bool export_ric = false, export_stat = false;
-  bool ric_valid = false, stat_valid = false;  // the LAST solve wrote the Riccati exports (+ pi[0]) / the statistics table
+  bool ric_valid = false, stat_valid = false;
+  // K1 / K2 write the dense records (RSQrq, DCt, d, dmask, raw stage-0 blocks) only when something will read them: the
+  // generic kernel, the getters, the rescue pass.  The throughput path (SRBD variant of K3) reads BAbt and the compact
+  // stage records only; the dense ones are then materialised lazily from the unchanged trajectory (ensure_dense).
+  bool dense_valid = false, raw0_valid = false;
+  long long traj_version = 0, asm_traj_version = -1;  // the LAST solve wrote the Riccati exports (+ pi[0]) / the statistics table
   long long launches = 0;
   std::string err;
   int sm_count = 0;
@@ -120,6 +125,23 @@ KernelChoice pick_kernel(const QpLayout& L) {
 }
 
 int raw0_stride(const QpLayout& L) { return 2 * L.nx * L.nx + 2 * L.nx * L.nu + 2 * L.nx; }
+
+// Will srbd_qp_solve take the SRBD tensor-core variant for a QP assembled by K2 under the current settings?
+bool variant_eligible(const srbd_ctx* ctx) {
+  const char* force = std::getenv("SRBD_K3_GENERIC");
+  if (force && force[0] == '1') return false;
+  // the variant relies on Ac being two 12x6 blocks (SRBD_model.cpp:244: Ac.block<12,6>(12*leg, 6*leg))
+  double Ac[288];
+  fill_Ac(ctx->model, Ac);
+  for (int g = 0; g < 24; ++g)
+    for (int j = 0; j < 12; ++j)
+      if (Ac[g * 12 + j] != 0.0 && (j / 6) != (g / 12)) return false;
+  return ctx->is_srbd && !ctx->args.warm_start && ctx->args.ric_alg == 0 && !ctx->export_ric && !ctx->export_stat;
+}
+bool want_dense(const srbd_ctx* ctx) {
+  const char* d = std::getenv("SRBD_K2_DENSE");   // diagnosis: always write the dense records
+  return (d && d[0] == '1') || !variant_eligible(ctx);
+}
 
 }  // namespace
 
@@ -295,6 +317,8 @@ int srbd_ctx_sync(srbd_ctx* ctx) {
   return SRBD_OK;
 }
 
+static int ensure_dense(srbd_ctx* ctx);
+
 int srbd_ctx_device_ptr(srbd_ctx* ctx, int buf, void** ptr, size_t* bytes) {
   if (!ctx || !ptr || !bytes) return SRBD_ERR_ARG;
   const QpLayout& L = ctx->L;
@@ -324,6 +348,13 @@ int srbd_ctx_device_ptr(srbd_ctx* ctx, int buf, void** ptr, size_t* bytes) {
     case SRBD_BUF_STAGE_REC: p = ctx->d_srec; n = ctx->d_srec ? B * S * kSrec * D : 0; break;
     default: return fail(ctx, SRBD_ERR_ARG, "unknown buffer id");
   }
+  if (buf == SRBD_BUF_RSQRQ || buf == SRBD_BUF_DCT || buf == SRBD_BUF_D || buf == SRBD_BUF_DMASK)
+    if (ctx->packed) {
+      const long long l0 = ctx->launches;
+      if (int rc = ensure_dense(ctx)) return rc;
+      // the caller reads the buffer on ITS stream: what was just launched on the context's stream must be done
+      if (ctx->launches != l0) CU(cudaStreamSynchronize(ctx->stream));
+    }
   if (!p) return fail(ctx, SRBD_ERR_STATE, "buffer not allocated for these dimensions");
   *ptr = p;
   *bytes = n;
@@ -349,6 +380,7 @@ int srbd_upload_traj(srbd_ctx* ctx, const double* x, const double* u, const doub
   CU(cudaMemcpyAsync(ctx->d_x0abs, x0, B * 12 * D, cudaMemcpyHostToDevice, ctx->stream));
   ctx->have_contact = contact != nullptr;
   if (contact) CU(cudaMemcpyAsync(ctx->d_contact, contact, B * N * 2, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->traj_version++;
   return SRBD_OK;
 }
 
@@ -362,16 +394,40 @@ int srbd_download_traj(srbd_ctx* ctx, double* x, double* u) {
   return SRBD_OK;
 }
 
-int srbd_linearize(srbd_ctx* ctx) {
-  if (int rc = require_srbd(ctx)) return rc;
+static int launch_linearize(srbd_ctx* ctx, bool raw0) {
   CU(cudaSetDevice(ctx->device));
   LinParams p{};
   p.B = ctx->B; p.N = ctx->L.N;
   p.x = ctx->d_x; p.u = ctx->d_u; p.x0 = ctx->d_x0abs;
-  p.babt = ctx->d_babt; p.defect = ctx->d_defect; p.raw0 = ctx->d_raw0; p.dx0 = ctx->d_x0;
+  p.babt = ctx->d_babt; p.defect = ctx->d_defect; p.raw0 = raw0 ? ctx->d_raw0 : nullptr; p.dx0 = ctx->d_x0;
   const long long total = (long long)p.B * p.N;
   const int grid = (int)((total + kLinThreads - 1) / kLinThreads);
   linearize_kernel<<<grid, kLinThreads, 0, ctx->stream>>>(p, ctx->d_model);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  ctx->raw0_valid = raw0;
+  return SRBD_OK;
+}
+
+int srbd_linearize(srbd_ctx* ctx) {
+  if (int rc = require_srbd(ctx)) return rc;
+  return launch_linearize(ctx, want_dense(ctx));
+}
+
+// K2.  dense: also RSQrq / DCt / d / dmask / raw stage-0 blocks; qlist / qcount (device): only those QPs
+static int launch_assemble(srbd_ctx* ctx, int mode, bool dense, const int* qlist, const int* qcount) {
+  CU(cudaSetDevice(ctx->device));
+  AsmParams p{};
+  p.B = ctx->B; p.N = ctx->L.N; p.mode = mode;
+  p.x = ctx->d_x; p.u = ctx->d_u; p.xref = ctx->d_xref; p.contact = ctx->have_contact ? ctx->d_contact : nullptr;
+  p.rsq = ctx->d_rsq; p.srec = ctx->d_srec; p.dct = ctx->d_dct; p.d = ctx->d_d; p.dmask = ctx->d_dmask; p.raw0 = ctx->d_raw0;
+  p.fcon = nullptr;
+  p.qlist = qlist; p.qcount = qcount;
+  const long long total = (long long)p.B * (p.N + 1);
+  int grid = (int)((total + kAsmThreads - 1) / kAsmThreads);
+  if (qlist && grid > 2 * ctx->sm_count) grid = 2 * ctx->sm_count;  // a rescue list is short (grid-stride loop inside)
+  if (dense) assemble_kernel<true><<<grid, kAsmThreads, 0, ctx->stream>>>(p, ctx->d_model);
+  else assemble_kernel<false><<<grid, kAsmThreads, 0, ctx->stream>>>(p, ctx->d_model);
   ctx->launches++;
   CU(cudaGetLastError());
   return SRBD_OK;
@@ -380,25 +436,41 @@ int srbd_linearize(srbd_ctx* ctx) {
 int srbd_assemble(srbd_ctx* ctx, int mode) {
   if (int rc = require_srbd(ctx)) return rc;
   if (mode != SRBD_BARRIER_SOFT && mode != SRBD_HARD_INEQ) return fail(ctx, SRBD_ERR_ARG, "bad assemble mode");
-  CU(cudaSetDevice(ctx->device));
-  AsmParams p{};
-  p.B = ctx->B; p.N = ctx->L.N; p.mode = mode;
-  p.x = ctx->d_x; p.u = ctx->d_u; p.xref = ctx->d_xref; p.contact = ctx->have_contact ? ctx->d_contact : nullptr;
-  p.rsq = ctx->d_rsq; p.srec = ctx->d_srec; p.dct = ctx->d_dct; p.d = ctx->d_d; p.dmask = ctx->d_dmask; p.raw0 = ctx->d_raw0;
-  p.fcon = nullptr;
-  const long long total = (long long)p.B * (p.N + 1);
-  const int grid = (int)((total + kAsmThreads - 1) / kAsmThreads);
-  assemble_kernel<<<grid, kAsmThreads, 0, ctx->stream>>>(p, ctx->d_model);
-  ctx->launches++;
-  CU(cudaGetLastError());
+  const bool dense = want_dense(ctx);
+  if (int rc = launch_assemble(ctx, mode, dense, nullptr, nullptr)) return rc;
   ctx->packed = true;
   ctx->have_init = false;
   ctx->assembled_mode = mode;
+  ctx->dense_valid = dense;
+  ctx->asm_traj_version = ctx->traj_version;
+  return SRBD_OK;
+}
+
+// The dense records of the assembled QP (and the raw stage-0 blocks), for whoever reads them after a compact-only
+// assembly: re-runs K1 / K2 on the trajectory the QP was assembled from.
+static int ensure_dense(srbd_ctx* ctx) {
+  if (ctx->assembled_mode < 0) return SRBD_OK;            // srbd_qp_upload data: pack_kernel always writes dense records
+  if (ctx->dense_valid && ctx->raw0_valid) return SRBD_OK;
+  if (ctx->asm_traj_version != ctx->traj_version)
+    return fail(ctx, SRBD_ERR_STATE, "the dense QP records were not written by srbd_assemble (throughput path) and the "
+                                     "trajectory has changed since (line search / upload): read them before, or set "
+                                     "SRBD_K2_DENSE=1");
+  if (!ctx->raw0_valid)
+    if (int rc = launch_linearize(ctx, true)) return rc;
+  if (!ctx->dense_valid) {
+    if (int rc = launch_assemble(ctx, ctx->assembled_mode, true, nullptr, nullptr)) return rc;
+    ctx->dense_valid = true;
+  }
   return SRBD_OK;
 }
 
 int srbd_download_linearization(srbd_ctx* ctx, double* A, double* Bm, double* b, double* defect) {
   if (int rc = require_srbd(ctx)) return rc;
+  if (!ctx->raw0_valid && (A || b)) {   // stage 0's A and un-embedded b come from the raw blocks
+    if (ctx->asm_traj_version != ctx->traj_version && ctx->assembled_mode >= 0)
+      return fail(ctx, SRBD_ERR_STATE, "raw stage-0 blocks were not written (throughput path) and the trajectory has changed");
+    if (int rc = launch_linearize(ctx, true)) return rc;
+  }
   const QpLayout& L = ctx->L;
   const size_t B = ctx->B, N = L.N;
   std::vector<double> h(B * N * L.babt_stride);
@@ -434,6 +506,7 @@ int srbd_download_qp(srbd_ctx* ctx, double* Q, double* S, double* R, double* q, 
                      double* lg_mask) {
   if (int rc = require_srbd(ctx)) return rc;
   if (!ctx->packed) return fail(ctx, SRBD_ERR_STATE, "assemble first");
+  if (int rc = ensure_dense(ctx)) return rc;
   const QpLayout& L = ctx->L;
   const size_t B = ctx->B, N = L.N, S1 = N + 1;
   std::vector<double> hr(B * S1 * L.rsq_stride), hd(B * S1 * L.dct_stride), hv(B * S1 * L.d_stride), hm(B * S1 * L.d_stride);
@@ -629,7 +702,12 @@ static int solve_srbd_variant(srbd_ctx* ctx) {
   ctx->solved = true;
   ctx->ric_valid = false;   // the variant exports neither P, p, K, k nor pi[0] nor the statistics table
   ctx->stat_valid = false;
-  if (rescue) return launch_generic(ctx, ctx->d_retry, ctx->d_retry + ctx->B);
+  if (rescue) {
+    // the generic kernel reads the dense records: write them for the listed QPs only (an empty kernel otherwise)
+    if (!ctx->dense_valid)
+      if (int rc = launch_assemble(ctx, ctx->assembled_mode, true, ctx->d_retry, ctx->d_retry + ctx->B)) return rc;
+    return launch_generic(ctx, ctx->d_retry, ctx->d_retry + ctx->B);
+  }
   return SRBD_OK;
 }
 
@@ -640,23 +718,10 @@ int srbd_qp_solve(srbd_ctx* ctx) {
     return fail(ctx, SRBD_ERR_ARG, "warm_start=1 needs x_init/u_init (qp_sol[i].x / .u must be pre-sized, "
                                    "hpipm-cpp/src/ocp_qp_ipm_solver.cpp:190-207)");
   CU(cudaSetDevice(ctx->device));
-  {
-    const char* force = std::getenv("SRBD_K3_GENERIC");
-    const bool generic = force && force[0] == '1';
-    // the variant relies on Ac being two 12x6 blocks (SRBD_model.cpp:244: Ac.block<12,6>(12*leg, 6*leg))
-    double Ac[288];
-    fill_Ac(ctx->model, Ac);
-    bool blocks = true;
-    for (int g = 0; g < 24; ++g)
-      for (int j = 0; j < 12; ++j)
-        if (Ac[g * 12 + j] != 0.0 && (j / 6) != (g / 12)) blocks = false;
-    // (both assemble modes: BARRIER_SOFT masks every row, which the variant solves as the single unconstrained
-    // Riccati pass)
-    if (!generic && blocks && ctx->is_srbd && ctx->assembled_mode >= 0 && !ctx->args.warm_start &&
-        ctx->args.ric_alg == 0 &&
-        !ctx->export_ric && !ctx->export_stat)
-      return solve_srbd_variant(ctx);
-  }
+  // QPs assembled by K2 (both modes: BARRIER_SOFT masks every row, which the variant solves as the single unconstrained
+  // Riccati pass) take the SRBD tensor-core variant unless a setting needs the generic kernel
+  if (ctx->assembled_mode >= 0 && variant_eligible(ctx)) return solve_srbd_variant(ctx);
+  if (int rc = ensure_dense(ctx)) return rc;
   return launch_generic(ctx, nullptr, nullptr);
 }
 
@@ -721,6 +786,7 @@ int srbd_line_search(srbd_ctx* ctx) {
   line_search_kernel<<<(ctx->B + 3) / 4, 128, 0, ctx->stream>>>(p, ctx->d_model);
   ctx->launches++;
   CU(cudaGetLastError());
+  ctx->traj_version++;   // the trajectory moved: the assembled QP no longer belongs to it
   return SRBD_OK;
 }
 

@@ -105,6 +105,24 @@ namespace v2 {
 #ifndef SRBD_K3_WBASE
 #define SRBD_K3_WBASE 0
 #endif
+// Tile prefetch engine PER SWEEP (bit mask: 1 factorization S1, 2 backward vector sweep S4, 4 forward sweep S2,
+// 8 residual sweep S6).  Bit set: TMA bulk copies (cp.async.bulk.shared.global, completion on a per-warp mbarrier pair)
+// issued by ONE lane, one instruction per contiguous block (the BAbt record, the [P | factor panels] tile, the R tile),
+// nothing through the LSU.  Bit clear: Ampere-style per-lane 16-byte cp.async (LDGSTS), the round-1 engine.
+// Measured (16384 QPs burst / 65536 QPs sustained, profiles/r2_k3_tile_engine_ab.txt): every sweep on bulk copies (nine
+// per stage with the padded BAbt tile) 483 k / 496 k solves/s against 588 k / 546 k for cp.async; three per stage (unpadded
+// tile) 549 k / 548 k; S1 + S6 only 554 k / 530 k; S1 only 568 k / 534 k; S6 only 575 k / 540 k against 580 k / 545 k
+// without any.  A bulk copy has a longer latency than the per-lane copies and the prefetch distance is one stage (the
+// shared memory is full), which the short vector sweeps S2 / S4 (2.6-3.0 k cycles per stage) and the factorization cannot
+// hide; the residual sweep has no recursion to wait for and takes them at no measurable cost.  Default: S6 only.
+#ifndef SRBD_K3_TMA
+#define SRBD_K3_TMA 8
+#endif
+// panel stride of the BAbt tile in shared memory.  48 = the record as it lies in HBM (one bulk copy); 54 (= 2 mod 4) makes
+// the row-permuted B fragments bank-conflict free but measures no faster (580 k vs 576 k burst, 545 k vs 538 k sustained)
+#ifndef SRBD_K3_GP
+#define SRBD_K3_GP 48
+#endif
 constexpr int kWarps = SRBD_K3_WARPS;
 constexpr int kMinCtas = SRBD_K3_MIN_CTAS;
 // per-stage workspace block (doubles)
@@ -114,8 +132,7 @@ constexpr int oZ = 0, oDZ = 24, oRG = 48, oLAM = 72, oT = 96, oDLAM = 120, oDT =
 constexpr int kPanF = 102;         // panel stride in the factor tile: rows 0..24 (100) + 2 (bank-conflict-free fragments)
 constexpr int kPan = 148;          // the full panel during the factorization: + rows 25..36 = rows 0..11 of L
 // shared memory (doubles)
-constexpr int kGP = 54;            // padded panel stride of the BAbt tile (4 rows x 12 cols + 6): = 2 mod 4, so that the
-                                   // row-permuted B fragments (rows pi and pi+4 in one half-warp) are bank-conflict free
+constexpr int kGP = SRBD_K3_GP;    // panel stride of the BAbt tile (4 rows x 12 cols [+ 6 padding])
 constexpr int kW2 = 22;            // row stride of W (21 lower-triangle products of a constraint row's 6-vector)
 constexpr int sAC = 0;             // [24][12] constraint Jacobian, row-major
 constexpr int sW = sAC + 288;      // [24][22]
@@ -143,6 +160,7 @@ constexpr int wT = wXN + 12;       // 12 t / lv
 constexpr int wPV = wT + 12;       // 12 p_{k+1}
 constexpr int wDI = wPV + 12;      // 12 (spare)
 constexpr int wLAM = wDI + 12;     // 24 lam (residual sweep)
+constexpr int wBAR = wLAM + 24;    // 2 mbarriers (TMA tile engine) in the padding
 constexpr int kWarpShared = wLAM + 24 + 8;   // multiple of 16
 static_assert(kWarpShared % 16 == 0 && kCtaShared % 16 == 0, "tiles must start on 128-byte lines");
 constexpr int kSmemBytes = (kCtaShared + kWarps * kWarpShared) * 8;
@@ -185,6 +203,36 @@ __device__ __forceinline__ void l2_prefetch(const void* p) {
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
+
+// ---- TMA bulk copies + mbarrier (sm_90+; SASS: UBLKCP / SYNCS) -------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.expect_tx.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "SRBD_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra SRBD_MBAR_DONE;\n"
+      "bra SRBD_MBAR_WAIT;\n"
+      "SRBD_MBAR_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (16-byte aligned, size a multiple of 16), completes `bytes` transactions on `bar`
+__device__ __forceinline__ void bulk_g2s(double* smem_dst, const double* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// generic-proxy accesses of this thread (and, after a __syncwarp, of its warp) before async-proxy writes of the same memory
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 // D(8x8) = A(8x4) * B(4x8) + C on the FP64 tensor cores; fragment layout in the header comment
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b, double c0, double c1) {
@@ -245,69 +293,153 @@ struct SrbdSolver {
 #endif
   // per-QP, per-lane base pointers of the packed QP data (set once per solve; kept opaque so that the compiler
   // holds / reloads them instead of re-deriving them from (q, N, lane) with 64-bit multiplies at every stage)
+  static constexpr int kLaneOff = 2;   // every lane copies its own 16-byte chunk (lane 0's pointer is the record base)
 #if SRBD_K3_QBASE
   const double *qG, *qT;
   __device__ __forceinline__ void set_qp(int qp) {
     q = qp;
-    qG = p.babt + (size_t)q * N * 336 + 2 * lane;
-    qT = p.srec + (size_t)q * (N + 1) * kSrec + 2 * lane;
+    qG = p.babt + (size_t)q * N * 336 + kLaneOff * lane;
+    qT = p.srec + (size_t)q * (N + 1) * kSrec + kLaneOff * lane;
     asm volatile("" : "+l"(qG), "+l"(qT));
   }
   __device__ __forceinline__ const double* gBAbtL(int k) const { return qG + k * 336; }   // + 2 * lane
   __device__ __forceinline__ const double* gRecL(int k) const { return qT + k * kSrec; }  // + 2 * lane
 #else
   __device__ __forceinline__ void set_qp(int qp) { q = qp; }
-  __device__ __forceinline__ const double* gBAbtL(int k) const { return p.babt + ((size_t)q * N + k) * 336 + 2 * lane; }
+  __device__ __forceinline__ const double* gBAbtL(int k) const { return p.babt + ((size_t)q * N + k) * 336 + kLaneOff * lane; }
   __device__ __forceinline__ const double* gRecL(int k) const {
-    return p.srec + ((size_t)q * (N + 1) + k) * kSrec + 2 * lane;
+    return p.srec + ((size_t)q * (N + 1) + k) * kSrec + kLaneOff * lane;
   }
 #endif
   // lg / mask of row min(lane, 23)-ish (lanes >= 24 read row 0) from the stage record
-  __device__ __forceinline__ const double* gDL(int k) const { return gRecL(k) + 144 - (lane < 24 ? lane : 2 * lane); }
+  __device__ __forceinline__ const double* gDL(int k) const {
+    return gRecL(k) + 144 + (lane < 24 ? lane : 0) - kLaneOff * lane;
+  }
   __device__ __forceinline__ const double* gMaskL(int k) const { return gDL(k) + 24; }
 
   // ---- asynchronous tile prefetch (cp.async, no registers) -------------------------------------------
   // BAbt record (panels of 4 rows x 12 = 48 doubles) -> padded panels; np = 6: rows 0..23, 7: + the b row.
   // One 24-lane instruction per panel: every address is base + immediate.
+  // per-warp mbarrier pair (one per tile buffer) in the padding of the warp's shared block; tph: bit b = the phase
+  // parity the next wait on barrier b expects
+  unsigned tph;
+  __device__ __forceinline__ unsigned long long* bar(int b) const {
+    return reinterpret_cast<unsigned long long*>(sm + v2::wBAR) + b;
+  }
+  __device__ __forceinline__ void tiles_init() {
+    tph = 0;
+    if (SRBD_K3_TMA) {
+      if (lane == 0) {
+        mbar_init(bar(0), 1);
+        mbar_init(bar(1), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        fence_proxy_async();
+      }
+      __syncwarp();
+    }
+  }
+  // Stage k's tiles have landed in buffer b.  TMA: lane 0 issued every expect_tx / copy of this phase before (program
+  // order), its arrival closes the phase's arrival count; the phase completes when the bytes are in.
+  template <bool TMA>
+  __device__ __forceinline__ void tiles_wait(int b) {
+    if (TMA) {
+      if (lane == 0) mbar_arrive(bar(b));
+      mbar_wait(bar(b), (tph >> b) & 1u);
+      tph ^= 1u << b;
+    } else {
+      cp_async_wait_all();
+    }
+  }
+  // TMA: before the first copy into a buffer the warp has read / written with ordinary shared-memory instructions (call
+  // after the __syncwarp that ends those accesses)
+  template <bool TMA>
+  __device__ __forceinline__ void tiles_begin() const {
+    if (TMA && lane == 0) fence_proxy_async();
+  }
+  // BAbt record (panels of 4 rows x 12 = 48 doubles) -> panels of stride kGP; np = 6: rows 0..23, 7: + the b row.
+  template <bool TMA>
   __device__ __forceinline__ void prefetch_G(int k, int b, int np = 6) {
-    const double* src = gBAbtL(k);
-    double* dst = sm + (b ? v2::wG1 : v2::wG0) + 2 * lane;
-    if (lane < 24) {
+    const double* src = gBAbtL(k);   // + 2 * lane
+    double* dst = sm + (b ? v2::wG1 : v2::wG0);
+    if (TMA) {
+      if (lane == 0) {
+        mbar_expect_tx(bar(b), np * 384);
+        if (v2::kGP == 48) {
+          bulk_g2s(dst, src, np * 384, bar(b));
+        } else {
+#pragma unroll
+          for (int pnl = 0; pnl < 7; ++pnl)
+            if (pnl < np) bulk_g2s(dst + pnl * v2::kGP, src + pnl * 48, 384, bar(b));
+        }
+      }
+    } else if (lane < 24) {   // one 24-lane instruction per panel: every address is base + immediate
 #pragma unroll
       for (int pnl = 0; pnl < 7; ++pnl)
-        if (pnl < np) cp_async16(dst + pnl * v2::kGP, src + pnl * 48);
+        if (pnl < np) cp_async16(dst + 2 * lane + pnl * v2::kGP, src + pnl * 48);
     }
   }
   // [P_{k+1} (144) |] factor panels of stage k (3 x 102): contiguous in the workspace (P_{k+1} lives in block k)
+  template <bool TMA>
   __device__ __forceinline__ void prefetch_F(int k, int b, bool with_P) {
-    double* dst = sm + (b ? v2::wF1 : v2::wF0) + 2 * lane;
-    const double* src = ws(k, v2::oP) + 2 * lane;
-    if (with_P) {
+    double* dst = sm + (b ? v2::wF1 : v2::wF0);
+    const double* src = ws(k, v2::oP);
+    if (TMA) {
+      if (lane == 0) {
+        if (with_P) {
+          mbar_expect_tx(bar(b), 450 * 8);
+          bulk_g2s(dst, src, 450 * 8, bar(b));
+        } else {
+          mbar_expect_tx(bar(b), 306 * 8);
+          bulk_g2s(dst + 144, src + 144, 306 * 8, bar(b));
+        }
+      }
+    } else {
+      dst += 2 * lane; src += 2 * lane;
+      if (with_P) {
 #pragma unroll
-      for (int i = 0; i < 2; ++i) cp_async16(dst + 64 * i, src + 64 * i);
-      if (lane < 8) cp_async16(dst + 128, src + 128);
+        for (int i = 0; i < 2; ++i) cp_async16(dst + 64 * i, src + 64 * i);
+        if (lane < 8) cp_async16(dst + 128, src + 128);
+      }
+      // chunks 72 .. 224
+#pragma unroll
+      for (int i = 0; i < 4; ++i) cp_async16(dst + 144 + 64 * i, src + 144 + 64 * i);
+      if (lane < 25) cp_async16(dst + 144 + 256, src + 144 + 256);
     }
-    // chunks 72 .. 224
-#pragma unroll
-    for (int i = 0; i < 4; ++i) cp_async16(dst + 144 + 64 * i, src + 144 + 64 * i);
-    if (lane < 25) cp_async16(dst + 144 + 256, src + 144 + 256);
   }
   // R tile of stage k (the lower 12 x 12 block of rows 0..11 of RSQrq as panel prefixes, 96 doubles): the head of the
   // compact stage record, a linear copy.  R_k is NOT a constant: the rows that stay a relaxed barrier in HARD_INEQ
   // mode add Ac^T diag(b'') Ac (NMPC_solver.cpp:308)
+  template <bool TMA>
   __device__ __forceinline__ void prefetch_Rblk(int k, int b) {
-    const double* src = gRecL(k);
-    double* dst = sm + (b ? v2::wR1 : v2::wR0) + 2 * lane;
-    cp_async16(dst, src);
-    if (lane < 16) cp_async16(dst + 64, src + 64);
+    const double* src = gRecL(k);    // + 2 * lane
+    double* dst = sm + (b ? v2::wR1 : v2::wR0);
+    if (TMA) {
+      if (lane == 0) {
+        mbar_expect_tx(bar(b), 96 * 8);
+        bulk_g2s(dst, src, 96 * 8, bar(b));
+      }
+    } else {
+      dst += 2 * lane;
+      cp_async16(dst, src);
+      if (lane < 16) cp_async16(dst + 64, src + 64);
+    }
   }
   // ... and with the gradient row n = [r; q] (record offsets 108..131)
+  template <bool TMA>
   __device__ __forceinline__ void prefetch_R(int k, int b) {
     const double* src = gRecL(k);
-    double* dst = sm + (b ? v2::wR1 : v2::wR0) + 2 * lane;
-    cp_async16(dst, src);
-    cp_async16(dst + 64, src + 64);
-    if (lane < 2) cp_async16(dst + 128, src + 128);
+    double* dst = sm + (b ? v2::wR1 : v2::wR0);
+    if (TMA) {
+      if (lane == 0) {
+        mbar_expect_tx(bar(b), 132 * 8);
+        bulk_g2s(dst, src, 132 * 8, bar(b));
+      }
+    } else {
+      dst += 2 * lane;
+      cp_async16(dst, src);
+      cp_async16(dst + 64, src + 64);
+      if (lane < 2) cp_async16(dst + 128, src + 128);
+    }
   }
   // Lines of stage k that a sweep will read: the vector part of the workspace block (doubles 0..299), optionally
   // P_{k+1} (300..443) and the factor panels / P rb (444..761), the BAbt record and the compact stage record.
@@ -358,6 +490,7 @@ struct SrbdSolver {
     return x > 0.0 ? y : 0.0;
   }
   __device__ void sweep_factor() {
+    constexpr bool kT1 = (SRBD_K3_TMA & 1) != 0;
     const double reg = p.a.reg_prim;
     double* sP = sm + v2::wP;
     double* sPan = sm + v2::wPAN;
@@ -376,13 +509,14 @@ struct SrbdSolver {
     const int rel1 = 48 + (r & 3) + 4 * t;                   // rows 8..11 (r < 4)
     const double qd3 = dg1 ? cQ[t] : 0.0, qd4 = dg0 ? cQ[4 + t] : 0.0, qd5 = dg1 ? cQ[8 + t] : 0.0;  // diag(Q)
     // start streaming stage N-1 while stage N is handled
-    prefetch_G(N - 1, 0);
-    prefetch_Rblk(N - 1, 0);
+    tiles_begin<kT1>();
+    prefetch_G<kT1>(N - 1, 0);
+    prefetch_Rblk<kT1>(N - 1, 0);
     S1v cur = load_s1(N - 1);
     // ---- stage N: P_N = Q_N + reg I, p_N = rg_N ------------------------------------------------------
     double pk[3];
     {
-      const double* rs = gRecL(N) - 2 * lane;  // Q_N: the R tile of the last stage record
+      const double* rs = gRecL(N) - kLaneOff * lane;  // Q_N: the R tile of the last stage record
       if (lane < 12) {
 #pragma unroll
         for (int c = 0; c < 12; ++c) {
@@ -409,13 +543,14 @@ struct SrbdSolver {
     for (int k = N - 1; k >= 0; --k) {
       const int b = (N - 1 - k) & 1;
       const bool xr = k > 0;                 // the stage has x rows (rows 12..23)
-      cp_async_wait_all();
+      tiles_wait<kT1>(b);
       __syncwarp();  // stage k's tiles have landed; every lane is done with the other buffers
       set_bufs(b);
       S1v nxt = cur;
       if (k > 0) {
-        prefetch_G(k - 1, b ^ 1);
-        prefetch_Rblk(k - 1, b ^ 1);
+        tiles_begin<kT1>();
+        prefetch_G<kT1>(k - 1, b ^ 1);
+        prefetch_Rblk<kT1>(k - 1, b ^ 1);
         nxt = load_s1(k - 1);
         if (k > 1) prefetch_L2(k - 2, false, false, true);
       }
@@ -668,6 +803,7 @@ struct SrbdSolver {
     return v;
   }
   __device__ __forceinline__ void sweep_backvec(int mode, double sm_) {
+    constexpr bool kT4 = (SRBD_K3_TMA & 2) != 0;
     const int r = fr, t = ft, pi = fpi;
     const int oG = (pi >> 2) * v2::kGP + 4 * t + (pi & 3);            // G[8I+pi][4kt+t]      : + 2 kGP I + 16 kt
     // 4x4 blocks of the factor panels as B fragments: row index t / column pi, and row pi / column t
@@ -681,21 +817,23 @@ struct SrbdSolver {
 #pragma unroll
       for (int kt = 0; kt < 3; ++kt) wsf(N, v2::oPV)[4 * kt] = pk[kt];
     }
-    prefetch_G(N - 1, 0);
-    prefetch_F(N - 1, 0, false);
+    tiles_begin<kT4>();
+    prefetch_G<kT4>(N - 1, 0);
+    prefetch_F<kT4>(N - 1, 0, false);
     S4v cur = load_s4(N - 1);
 #if SRBD_K3_UNROLL_BWD
 #pragma unroll 2
 #endif
     for (int k = N - 1; k >= 0; --k) {
       const int b = (N - 1 - k) & 1;
-      cp_async_wait_all();
+      tiles_wait<kT4>(b);
       __syncwarp();  // stage k's tiles have landed; every lane is done with the other buffers
       set_bufs(b);
       S4v nxt = cur;
       if (k > 0) {
-        prefetch_G(k - 1, b ^ 1);
-        prefetch_F(k - 1, b ^ 1, false);
+        tiles_begin<kT4>();
+        prefetch_G<kT4>(k - 1, b ^ 1);
+        prefetch_F<kT4>(k - 1, b ^ 1, false);
         nxt = load_s4(k - 1);
         if (k > 1) prefetch_L2(k - 2, false, true, false);
       }
@@ -809,6 +947,7 @@ struct SrbdSolver {
     return v;
   }
   __device__ __forceinline__ void sweep_forward(bool fin, double& ap, double& ad) {
+    constexpr bool kT2 = (SRBD_K3_TMA & 4) != 0;
     const int r = fr, t = ft, pi = fpi;
     const int oLT = 144 + (pi >> 2) * v2::kPanF + 48 + 4 * t + (pi & 3);  // Ls[4kt+t][8I+pi]   : + 2 kPanF I + 16 kt
     // 4x4 blocks of the factor panels as B fragments: row index t / column pi, and row pi / column t
@@ -824,21 +963,23 @@ struct SrbdSolver {
     double np_ = 1.0, dp_ = 1.0, nd_ = 1.0, dd_ = 1.0;  // step lengths as fractions num/den (no division per row)
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
     double xk[3] = {0.0, 0.0, 0.0};
-    prefetch_G(0, 0);
-    prefetch_F(0, 0, fin);
+    tiles_begin<kT2>();
+    prefetch_G<kT2>(0, 0);
+    prefetch_F<kT2>(0, 0, fin);
     S2v cur = load_s2(0);
 #if SRBD_K3_UNROLL_FWD
 #pragma unroll 2
 #endif
     for (int k = 0; k < N; ++k) {
       const int b = k & 1;
-      cp_async_wait_all();
+      tiles_wait<kT2>(b);
       __syncwarp();
       set_bufs(b);
       S2v nxt = cur;
       if (k + 1 < N) {
-        prefetch_G(k + 1, b ^ 1);
-        prefetch_F(k + 1, b ^ 1, fin);
+        tiles_begin<kT2>();
+        prefetch_G<kT2>(k + 1, b ^ 1);
+        prefetch_F<kT2>(k + 1, b ^ 1, fin);
         nxt = load_s2(k + 1);
         if (k + 2 < N) prefetch_L2(k + 2, fin, true, false);
       }
@@ -999,6 +1140,7 @@ struct SrbdSolver {
     return v;
   }
   __device__ void residuals(double res[4], double& mu, int nc_mask, bool do_update, double sp, double sd) {
+    constexpr bool kT6 = (SRBD_K3_TMA & 8) != 0;
     const int r = fr, t = ft, pi = fpi;
     const int gB = (pi >> 2) * v2::kGP + 4 * t + (pi & 3);   // G[8I+pi][4kt+t]   : + 2 kGP I + 16 kt
     const int oGT = 4 * pi + t;                              // G[4kt+t][8I+pi]   : + 32 I + kGP kt
@@ -1020,8 +1162,9 @@ struct SrbdSolver {
 #pragma unroll
     for (int j = 0; j < 6; ++j) acr[j] = cAc[lc * 12 + j0 + j];
     double ng_ = 0.0, nb_ = 0.0, nd_ = 0.0, nm_ = 0.0, smu = 0.0;
-    prefetch_G(0, 0, 7);
-    prefetch_R(0, 0);
+    tiles_begin<kT6>();
+    prefetch_G<kT6>(0, 0, 7);
+    prefetch_R<kT6>(0, 0);
     S6raw raw = load_s6(0, do_update);
     double pp[3] = {0.0, 0.0, 0.0};  // updated pi_{k-1}, fragment form
 #if SRBD_K3_UNROLL_RES
@@ -1030,13 +1173,14 @@ struct SrbdSolver {
     for (int k = 0; k <= N; ++k) {
       const int b = k & 1;
       const int nu = k < N ? 12 : 0, nx = k > 0 ? 12 : 0, n = nu + nx;
-      cp_async_wait_all();
+      tiles_wait<kT6>(b);
       __syncwarp();
       set_bufs(b);
       const S6v cur = updated(raw, do_update, sp, sd);
       if (k < N) {
-        if (k + 1 < N) prefetch_G(k + 1, b ^ 1, 7);
-        prefetch_R(k + 1, b ^ 1);
+        tiles_begin<kT6>();
+        if (k + 1 < N) prefetch_G<kT6>(k + 1, b ^ 1, 7);
+        prefetch_R<kT6>(k + 1, b ^ 1);
         raw = load_s6(k + 1, do_update);
         if (k + 2 < N) prefetch_L2(k + 2, false, false, true);
       }
@@ -1180,6 +1324,15 @@ struct SrbdSolver {
     return alpha;
   }
 
+#ifndef SRBD_K3_PROFILE
+#define SRBD_K3_PROFILE 0   // development: per-sweep clock64 sums in bins 48..52 of the iteration histogram
+#endif
+#if SRBD_K3_PROFILE
+  long long prof[5] = {0, 0, 0, 0, 0};
+#define SRBD_PROF(i, call) do { const long long t0_ = clock64(); call; prof[i] += clock64() - t0_; } while (0)
+#else
+#define SRBD_PROF(i, call) call
+#endif
   __device__ void solve_one(int qp) {
     set_qp(qp);
     const srbd_ipm_args& a = p.a;
@@ -1217,12 +1370,12 @@ struct SrbdSolver {
     int kk = 0;
     for (;; ++kk) {
       // residuals of the current iterate (kk > 0: the variable update of the previous iteration is fused in)
-      residuals(res, mu, nc_mask, kk > 0, sp_, sd_);
+      SRBD_PROF(0, residuals(res, mu, nc_mask, kk > 0, sp_, sd_));
       if (unc ? kk > 0
               : !(kk < a.iter_max && alpha > a.alpha_min &&
                   (res[0] > a.tol_stat || res[1] > a.tol_eq || res[2] > a.tol_ineq || res[3] > a.tol_comp)))
         break;
-      sweep_factor();
+      SRBD_PROF(1, sweep_factor());
       // KKT solves of this iteration (one call site per sweep: the sweeps are inlined once).  phase 0: affine /
       // only solve (its backward part was done by the factorization sweep), 1: corrector, 2: conditional centering
       double ap, ad;
@@ -1230,8 +1383,16 @@ struct SrbdSolver {
         int phase = 0;
         double sigma = 0.0, mua = 0.0, smv = 0.0;
         for (;;) {
-          if (phase > 0) sweep_backvec(phase, smv);
+          if (phase > 0) SRBD_PROF(2, sweep_backvec(phase, smv));
+#if SRBD_K3_PROFILE
+          {
+            const long long t0_ = clock64();
+            sweep_forward(a.pred_corr != 1 || phase > 0 || unc, ap, ad);
+            prof[phase > 0 ? 4 : 3] += clock64() - t0_;
+          }
+#else
           sweep_forward(a.pred_corr != 1 || phase > 0 || unc, ap, ad);
+#endif
           if (a.pred_corr != 1 || unc) break;
           if (phase == 0) {
             mua = mu_aff(fmin(ap, ad), nc_mask);
@@ -1339,6 +1500,7 @@ __global__ void SRBD_K3_BOUNDS ipm_srbd_kernel(const SrbdIpmParams p) {
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   SrbdSolver S(p, smem, smem + v2::kCtaShared + warp * v2::kWarpShared, blockIdx.x * v2::kWarps + warp);
+  S.tiles_init();
   long long it_sum = 0, solves = 0;
   int st_cnt[5] = {0, 0, 0, 0, 0};
   double rmax[4] = {0.0, 0.0, 0.0, 0.0};
@@ -1362,6 +1524,10 @@ __global__ void SRBD_K3_BOUNDS ipm_srbd_kernel(const SrbdIpmParams p) {
       }
     }
   }
+#if SRBD_K3_PROFILE
+  if (lane == 0)
+    for (int i = 0; i < 5; ++i) atomicAdd((unsigned long long*)&p.bstats->iter_hist[48 + i], (unsigned long long)S.prof[i]);
+#endif
   if (lane == 0 && solves > 0) {
     atomicAdd((unsigned long long*)&p.bstats->solves, (unsigned long long)solves);
     atomicAdd((unsigned long long*)&p.bstats->iter_sum, (unsigned long long)it_sum);
