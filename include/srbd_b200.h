@@ -261,6 +261,19 @@ int srbd_download_solution(srbd_ctx* ctx, const srbd_sol_host* sol);
 int srbd_download_stats(srbd_ctx* ctx, const srbd_stats_host* st);
 int srbd_batch_stats_get(srbd_ctx* ctx, srbd_batch_stats* out);
 
+/* ---- closed-loop batched MPC --------------------------------------------------------------------*/
+/* The MPC loop of the reference's example and test (hpipm-cpp/examples/example_mpc.cpp:99-119,
+ * hpipm-cpp/test/ocp_qp_ipm_solver.cpp:298-314) for B robots at once, on the device: for t = 0 .. steps-1
+ *     x0 := x(t);  solve the QP uploaded by srbd_qp_upload (only x0 changes: b0 <- A0 x0 + b0, r0 <- S0 x0 + r0 are
+ *     re-embedded);  x(t+1) := A x(t) + B u0 + b.
+ * With warm_start = 1 step 0 starts from the uploaded x_init / u_init and every later step from the previous solution,
+ * exactly like passing `solution` back into OcpQpIpmSolver::solve.  No host round trip between the steps.
+ * A, Bm, b: the plant, column-major [nx*nx], [nx*nu], [nx], one per robot ([B][...]) or shared (plant_shared = 1).
+ * x_start [B][nx].  Outputs (any may be NULL): x_traj [steps+1][B][nx], u_traj [steps][B][nu], iter / status
+ * [steps][B].  After the call srbd_download_solution returns the solution of the LAST step. */
+int srbd_mpc_run(srbd_ctx* ctx, const double* A, const double* Bm, const double* b, int plant_shared,
+                 const double* x_start, int steps, double* x_traj, double* u_traj, int* iter, int* status);
+
 /* ---- SQP level --------------------------------------------------------------------------------*/
 /* K4: filter line search on the device: updates the trajectory in place, per-QP alpha carried in
  * the context (NMPC_solver.h:104), writes converged[B] (NMPC_solver.cpp:267).  merit: [B][3] =

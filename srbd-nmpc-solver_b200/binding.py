@@ -227,6 +227,23 @@ class Context:
     def wait(self):
         self._ck(self._L.srbd_wait(self._h))
 
+    def mpc_run(self, A, Bm, b, x_start, steps):
+        """Closed-loop batched MPC on the device (srbd_mpc_run): A, Bm, b = the plant, row-major numpy matrices, shared
+        ([nx,nx], [nx,nu], [nx]) or one per robot ([B,nx,nx], ...).  Returns x_traj [steps+1,B,nx], u_traj [steps,B,nu],
+        iter / status [steps,B]."""
+        nx, nu, B = self.dims.nx, self.dims.nu, self.batch
+        A, Bm, b = (np.asarray(v, dtype=np.float64) for v in (A, Bm, b))
+        shared = A.ndim == 2
+        Ac = np.ascontiguousarray(np.swapaxes(A, -1, -2))    # column-major blocks
+        Bc = np.ascontiguousarray(np.swapaxes(Bm, -1, -2))
+        bc = np.ascontiguousarray(b)
+        xs = np.ascontiguousarray(x_start, dtype=np.float64).reshape(B, nx)
+        xt, ut = np.zeros((steps + 1, B, nx)), np.zeros((steps, B, nu))
+        it, st = np.zeros((steps, B), dtype=np.int32), np.zeros((steps, B), dtype=np.int32)
+        self._ck(self._L.srbd_mpc_run(self._h, capi.dptr(Ac), capi.dptr(Bc), capi.dptr(bc), 1 if shared else 0,
+                                      capi.dptr(xs), int(steps), capi.dptr(xt), capi.dptr(ut), capi.iptr(it), capi.iptr(st)))
+        return xt, ut, it, st
+
     def fp64_peak(self):
         v = C.c_double()
         self._ck(self._L.srbd_fp64_peak(self._h, C.byref(v)))

@@ -125,7 +125,7 @@ _EXPORTS = [
     "srbd_download_linearization", "srbd_download_qp", "srbd_qp_upload", "srbd_qp_solve",
     "srbd_download_solution", "srbd_download_stats", "srbd_batch_stats_get", "srbd_line_search",
     "srbd_download_sqp_state", "srbd_reset_sqp_state", "srbd_sqp_iterate", "srbd_solve_host", "srbd_solve_host_async", "srbd_wait",
-    "srbd_fp64_peak",
+    "srbd_fp64_peak", "srbd_mpc_run",
 ]
 
 _lib = None
@@ -183,6 +183,8 @@ def lib():
                                   c_double_p, c_double_p, c_int_p, c_int_p]
     L.srbd_wait.argtypes = [vp]
     L.srbd_fp64_peak.argtypes = [vp, c_double_p]
+    L.srbd_mpc_run.argtypes = [vp, c_double_p, c_double_p, c_double_p, C.c_int, c_double_p, C.c_int, c_double_p,
+                               c_double_p, c_int_p, c_int_p]
     for n in _EXPORTS:
         getattr(L, n)  # every symbol include/srbd_b200.h declares must be exported
     _lib = L

@@ -20,6 +20,7 @@ struct PackParams {
   srbd_qp_host qp;  // DEVICE pointers (same shapes as the host view)
   double *babt, *rsq, *dct, *d, *dmask, *raw0;
   int raw0_stride;
+  double* r0raw;  // [B][nu] the un-embedded r0 (the closed-loop driver re-embeds x0 every step) or null
 };
 
 __global__ void __launch_bounds__(128) pack_kernel(const PackParams p) {
@@ -148,7 +149,81 @@ __global__ void __launch_bounds__(128) pack_kernel(const PackParams p) {
       raw[oS + e] = p.qp.S ? p.qp.S[q0N * nu * nx + e] : 0.0;
     }
     for (int e = lane; e < nx; e += 32) { raw[ob + e] = p.qp.b[q0N * nx + e]; raw[oq + e] = p.qp.q[q0S * nx + e]; }
+    if (p.r0raw)
+      for (int e = lane; e < nu; e += 32) p.r0raw[(size_t)q * nu + e] = p.qp.r[q0N * nu + e];
   }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Closed-loop batched MPC (hpipm-cpp/examples/example_mpc.cpp:99-119, test/ocp_qp_ipm_solver.cpp:298-314): the QP data
+// stay on the device, every step only the initial state changes.  mpc_embed_kernel redoes the x0 embedding of stage 0
+// for the current plant state (same arithmetic as pack_kernel: b0 <- A0 x0 + b0, r0 <- S0 x0 + r0), mpc_plant_kernel
+// applies u0 to the plant, x <- A x + B u0 + b, and records the closed-loop trajectory.  One thread per robot.
+// ---------------------------------------------------------------------------------------------------
+struct MpcParams {
+  QpLayout L;
+  int B, t;
+  const double* raw0; int raw0_stride;
+  const double* r0raw;
+  double* xcur;            // [B][nx] plant state
+  double* x0;              // [B][nx] initial state of the QP
+  double *babt, *rsq;
+  const double *A, *Bm, *b;  // plant: [B or 1][nx*nx], [nx*nu], [nx] column-major
+  int plant_shared;
+  const double* sol_u;     // [B][N][nu]
+  const int *iter, *status;
+  double *x_traj, *u_traj; // [steps+1][B][nx], [steps][B][nu]
+  int *iter_traj, *status_traj;
+};
+
+__global__ void __launch_bounds__(128) mpc_embed_kernel(const MpcParams p) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= p.B) return;
+  const QpLayout& L = p.L;
+  const int nx = L.nx, nu = L.nu;
+  const double* raw = p.raw0 + (size_t)q * p.raw0_stride;
+  const double *A0 = raw, *b0 = raw + nx * nx + nx * nu, *S0 = b0 + nx;
+  const double* x0 = p.xcur + (size_t)q * nx;
+  double* ba = p.babt + (size_t)q * L.N * L.babt_stride;
+  double* rs = p.rsq + (size_t)q * (L.N + 1) * L.rsq_stride;
+  for (int j = 0; j < nx; ++j) {
+    double s = 0.0;
+    for (int l = 0; l < nx; ++l) s += A0[j + nx * l] * x0[l];
+    ba[pm_index(nu, j, L.babt_cn)] = s + b0[j];
+    p.x0[(size_t)q * nx + j] = x0[j];
+    if (p.t == 0) p.x_traj[(size_t)q * nx + j] = x0[j];
+  }
+  for (int j = 0; j < nu; ++j) {
+    double s = 0.0;
+    for (int l = 0; l < nx; ++l) s += S0[j + nu * l] * x0[l];
+    rs[pm_index(nu, j, L.rsq_cn)] = s + p.r0raw[(size_t)q * nu + j];
+  }
+}
+
+__global__ void __launch_bounds__(128) mpc_plant_kernel(const MpcParams p) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= p.B) return;
+  const QpLayout& L = p.L;
+  const int nx = L.nx, nu = L.nu;
+  const size_t po = p.plant_shared ? 0 : (size_t)q;
+  const double *A = p.A + po * nx * nx, *Bm = p.Bm + po * nx * nu, *b = p.b + po * nx;
+  const double* u0 = p.sol_u + (size_t)q * L.N * nu;
+  double* x = p.xcur + (size_t)q * nx;
+  double xn[kMaxNX];
+  for (int i = 0; i < nx; ++i) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int l = 0; l < nx; ++l) s1 += A[i + nx * l] * x[l];
+    for (int l = 0; l < nu; ++l) s2 += Bm[i + nx * l] * u0[l];
+    xn[i] = (s1 + s2) + b[i];
+  }
+  const size_t B = p.B;
+  for (int i = 0; i < nx; ++i) {
+    x[i] = xn[i];
+    p.x_traj[((size_t)(p.t + 1) * B + q) * nx + i] = xn[i];
+  }
+  for (int i = 0; i < nu; ++i) p.u_traj[((size_t)p.t * B + q) * nu + i] = u0[i];
+  p.iter_traj[(size_t)p.t * B + q] = p.iter[q];
+  p.status_traj[(size_t)p.t * B + q] = p.status[q];
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -35,6 +35,12 @@ struct srbd_ctx {
   // packed QP
   double *d_babt = nullptr, *d_rsq = nullptr, *d_dct = nullptr, *d_d = nullptr, *d_dmask = nullptr, *d_raw0 = nullptr;
   double* d_x0 = nullptr;  // [B][nx] QP-level initial state (delta form on the NMPC path)
+  double* d_r0raw = nullptr;  // [B][nu] un-embedded r0 of uploaded QPs (closed-loop driver)
+  // closed-loop MPC driver (lazy)
+  double *d_mpc_x = nullptr, *d_mpc_u = nullptr, *d_mpc_xcur = nullptr, *d_plantA = nullptr, *d_plantB = nullptr, *d_plantb = nullptr;
+  int *d_mpc_iter = nullptr, *d_mpc_status = nullptr;
+  int mpc_steps_alloc = 0, plant_alloc = 0;
+  bool warm_from_solution = false;  // the next solve takes the previous solution (on the device) as the primal warm start
   double *d_xinit = nullptr, *d_uinit = nullptr;
   bool have_init = false, packed = false, solved = false;
   // raw QP-level staging (lazy)
@@ -224,6 +230,7 @@ int srbd_ctx_create(int device, int batch, const srbd_qp_dims* dims, void* strea
   A(dalloc(&ctx->d_dct, B * S * L.dct_stride)); A(dalloc(&ctx->d_d, B * S * L.d_stride));
   A(dalloc(&ctx->d_dmask, B * S * L.d_stride)); A(dalloc(&ctx->d_raw0, B * raw0_stride(L)));
   A(dalloc(&ctx->d_x0, B * L.nx)); A(dalloc(&ctx->d_xinit, B * S * L.nx)); A(dalloc(&ctx->d_uinit, B * N * L.nu));
+  A(dalloc(&ctx->d_r0raw, B * L.nu));
   A(dalloc(&ctx->d_sol_x, B * S * L.nx)); A(dalloc(&ctx->d_sol_u, B * N * L.nu)); A(dalloc(&ctx->d_sol_pi, B * S * L.nx));
   A(dalloc(&ctx->d_sol_lam, B * (size_t)L.nct)); A(dalloc(&ctx->d_sol_t, B * (size_t)L.nct));
   A(dalloc(&ctx->d_iter, B)); A(dalloc(&ctx->d_status, B)); A(dalloc(&ctx->d_resmax, B * 4));
@@ -264,7 +271,8 @@ int srbd_ctx_destroy(srbd_ctx* ctx) {
                   ctx->d_dmask, ctx->d_raw0, ctx->d_x0, ctx->d_xinit, ctx->d_uinit, ctx->d_sol_x, ctx->d_sol_u,
                   ctx->d_sol_pi, ctx->d_sol_lam, ctx->d_sol_t, ctx->d_P, ctx->d_p, ctx->d_K, ctx->d_k,
                   ctx->d_stat, ctx->d_iter, ctx->d_status, ctx->d_counter, ctx->d_resmax, ctx->d_bstats, ctx->d_ws,
-                  ctx->d_ws2, ctx->d_srec, ctx->d_retry};
+                  ctx->d_ws2, ctx->d_srec, ctx->d_retry, ctx->d_r0raw, ctx->d_mpc_x, ctx->d_mpc_u, ctx->d_mpc_xcur,
+                  ctx->d_plantA, ctx->d_plantB, ctx->d_plantb, ctx->d_mpc_iter, ctx->d_mpc_status};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (void* p : ctx->raw_dev)
@@ -609,7 +617,7 @@ int srbd_qp_upload(srbd_ctx* ctx, const srbd_qp_host* qp) {
   PackParams p{};
   p.L = L; p.B = ctx->B; p.qp = dq;
   p.babt = ctx->d_babt; p.rsq = ctx->d_rsq; p.dct = ctx->d_dct; p.d = ctx->d_d; p.dmask = ctx->d_dmask;
-  p.raw0 = ctx->d_raw0; p.raw0_stride = raw0_stride(L);
+  p.raw0 = ctx->d_raw0; p.raw0_stride = raw0_stride(L); p.r0raw = ctx->d_r0raw;
   const long long total = (long long)ctx->B * (L.N + 1);
   pack_kernel<<<(int)((total + 3) / 4), 128, 0, ctx->stream>>>(p);
   ctx->launches++;
@@ -634,6 +642,10 @@ static int launch_generic(srbd_ctx* ctx, const int* qlist, const int* qcount) {
   p.babt = ctx->d_babt; p.rsq = ctx->d_rsq; p.dct = ctx->d_dct; p.d = ctx->d_d; p.dmask = ctx->d_dmask;
   p.x_init = ctx->have_init ? ctx->d_xinit : nullptr;
   p.u_init = ctx->have_init ? ctx->d_uinit : nullptr;
+  if (ctx->warm_from_solution) {  // every QP reads its guess before it writes its solution: in place
+    p.x_init = ctx->d_sol_x;
+    p.u_init = ctx->d_sol_u;
+  }
   p.x0 = ctx->d_x0; p.raw0 = ctx->d_raw0; p.ws = ctx->d_ws; p.counter = ctx->d_counter;
   p.sol_x = ctx->d_sol_x; p.sol_u = ctx->d_sol_u; p.sol_pi = ctx->d_sol_pi; p.sol_lam = ctx->d_sol_lam; p.sol_t = ctx->d_sol_t;
   if (ctx->export_ric) { p.ric_P = ctx->d_P; p.ric_p = ctx->d_p; p.ric_K = ctx->d_K; p.ric_k = ctx->d_k; }
@@ -769,6 +781,70 @@ int srbd_batch_stats_get(srbd_ctx* ctx, srbd_batch_stats* out) {
   if (!ctx->solved) return fail(ctx, SRBD_ERR_STATE, "solve first");
   CU(cudaSetDevice(ctx->device));
   CU(cudaMemcpyAsync(out, ctx->d_bstats, sizeof(*out), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SRBD_OK;
+}
+
+// ---- closed-loop batched MPC -----------------------------------------------------------------------
+int srbd_mpc_run(srbd_ctx* ctx, const double* A, const double* Bm, const double* b, int plant_shared, const double* x_start,
+                 int steps, double* x_traj, double* u_traj, int* iter, int* status) {
+  if (!ctx || !A || !Bm || !b || !x_start || steps < 1) return SRBD_ERR_ARG;
+  if (!ctx->packed || ctx->assembled_mode >= 0)
+    return fail(ctx, SRBD_ERR_STATE, "srbd_mpc_run needs QP data from srbd_qp_upload (the QP stays fixed, x0 changes per step)");
+  if (ctx->args.warm_start && !ctx->have_init)
+    return fail(ctx, SRBD_ERR_ARG, "warm_start=1 needs x_init/u_init for the first step");
+  CU(cudaSetDevice(ctx->device));
+  const QpLayout& L = ctx->L;
+  const size_t B = ctx->B, nx = L.nx, nu = L.nu, D = sizeof(double);
+  const size_t np = plant_shared ? 1 : B;
+  if (steps > ctx->mpc_steps_alloc) {
+    for (void* q : {(void*)ctx->d_mpc_x, (void*)ctx->d_mpc_u, (void*)ctx->d_mpc_iter, (void*)ctx->d_mpc_status})
+      if (q) cudaFree(q);
+    ctx->d_mpc_x = ctx->d_mpc_u = nullptr; ctx->d_mpc_iter = ctx->d_mpc_status = nullptr;
+    CU(dalloc(&ctx->d_mpc_x, (size_t)(steps + 1) * B * nx)); CU(dalloc(&ctx->d_mpc_u, (size_t)steps * B * nu));
+    CU(dalloc(&ctx->d_mpc_iter, (size_t)steps * B)); CU(dalloc(&ctx->d_mpc_status, (size_t)steps * B));
+    ctx->mpc_steps_alloc = steps;
+  }
+  if (!ctx->d_mpc_xcur) CU(dalloc(&ctx->d_mpc_xcur, B * nx));
+  if ((int)np > ctx->plant_alloc) {
+    for (void* q : {(void*)ctx->d_plantA, (void*)ctx->d_plantB, (void*)ctx->d_plantb})
+      if (q) cudaFree(q);
+    ctx->d_plantA = ctx->d_plantB = ctx->d_plantb = nullptr;
+    CU(dalloc(&ctx->d_plantA, np * nx * nx)); CU(dalloc(&ctx->d_plantB, np * nx * nu)); CU(dalloc(&ctx->d_plantb, np * nx));
+    ctx->plant_alloc = (int)np;
+  }
+  CU(cudaMemcpyAsync(ctx->d_plantA, A, np * nx * nx * D, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_plantB, Bm, np * nx * nu * D, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_plantb, b, np * nx * D, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_mpc_xcur, x_start, B * nx * D, cudaMemcpyHostToDevice, ctx->stream));
+  MpcParams p{};
+  p.L = L; p.B = ctx->B;
+  p.raw0 = ctx->d_raw0; p.raw0_stride = raw0_stride(L); p.r0raw = ctx->d_r0raw;
+  p.xcur = ctx->d_mpc_xcur; p.x0 = ctx->d_x0; p.babt = ctx->d_babt; p.rsq = ctx->d_rsq;
+  p.A = ctx->d_plantA; p.Bm = ctx->d_plantB; p.b = ctx->d_plantb; p.plant_shared = plant_shared ? 1 : 0;
+  p.sol_u = ctx->d_sol_u; p.iter = ctx->d_iter; p.status = ctx->d_status;
+  p.x_traj = ctx->d_mpc_x; p.u_traj = ctx->d_mpc_u; p.iter_traj = ctx->d_mpc_iter; p.status_traj = ctx->d_mpc_status;
+  const int grid = (ctx->B + 127) / 128;
+  int rc = SRBD_OK;
+  for (int t = 0; t < steps && rc == SRBD_OK; ++t) {
+    p.t = t;
+    mpc_embed_kernel<<<grid, 128, 0, ctx->stream>>>(p);
+    ctx->launches++;
+    // step 0 starts from the uploaded guess, later steps from the previous solution (the reference passes `solution`
+    // back in, examples/example_mpc.cpp:114)
+    ctx->warm_from_solution = ctx->args.warm_start && t > 0;
+    rc = srbd_qp_solve(ctx);
+    ctx->warm_from_solution = false;
+    if (rc != SRBD_OK) break;
+    mpc_plant_kernel<<<grid, 128, 0, ctx->stream>>>(p);
+    ctx->launches++;
+  }
+  if (rc != SRBD_OK) return rc;
+  CU(cudaGetLastError());
+  if (x_traj) CU(cudaMemcpyAsync(x_traj, ctx->d_mpc_x, (size_t)(steps + 1) * B * nx * D, cudaMemcpyDeviceToHost, ctx->stream));
+  if (u_traj) CU(cudaMemcpyAsync(u_traj, ctx->d_mpc_u, (size_t)steps * B * nu * D, cudaMemcpyDeviceToHost, ctx->stream));
+  if (iter) CU(cudaMemcpyAsync(iter, ctx->d_mpc_iter, (size_t)steps * B * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  if (status) CU(cudaMemcpyAsync(status, ctx->d_mpc_status, (size_t)steps * B * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return SRBD_OK;
 }
