@@ -249,7 +249,12 @@ int srbd_download_qp(srbd_ctx* ctx, double* Q, double* S, double* R, double* q, 
                      double* D, double* lg, double* lg_mask);
 
 /* ---- QP level (any dims up to the compiled maxima) ------------------------------------------- */
-int srbd_qp_upload(srbd_ctx* ctx, const srbd_qp_host* qp); /* H2D + pack (d_ocp_qp_set_all analog) */
+/* H2D + pack (d_ocp_qp_set_all analog).  Host fields that lie in one contiguous range (a staging arena) travel in a single
+ * copy.  With the SRBD dimensions (nx = nu = 12, ng = 24, no boxes) the batch is also checked ON THE DEVICE for the
+ * structure srbd_assemble produces (S = 0, C = 0, one constant diagonal Q for stages 1..N-1, one constant D made of two
+ * 12 x 6 blocks, ug masked); srbd_qp_solve then routes it to the tensor-core variant of K3 when the settings allow
+ * (cold start, ric_alg = 0, no Riccati / statistics exports) -- the reference's own boundary reaches the fast kernel. */
+int srbd_qp_upload(srbd_ctx* ctx, const srbd_qp_host* qp);
 /* K3: the whole IPM solve of every QP of the batch (d_ocp_qp_ipm_solve, hpipm_d_ocp_qp_ipm.h:238), asynchronous on
  * the context's stream.  QPs assembled by srbd_assemble() go through the tensor-core variant (one launch) followed by
  * the rescue launch of the generic kernel for the QPs that ran to iter_max (usually none);
@@ -259,6 +264,16 @@ int srbd_qp_solve(srbd_ctx* ctx);
  * asking for them returns SRBD_ERR_STATE (never the exports of an earlier solve). */
 int srbd_download_solution(srbd_ctx* ctx, const srbd_sol_host* sol);
 int srbd_download_stats(srbd_ctx* ctx, const srbd_stats_host* st);
+/* The same outputs in ONE device-to-host copy: x, u, pi, res_max, iter, status (and lam, t with with_duals = 1) live in one
+ * device arena; srbd_out_layout returns their offsets IN DOUBLES inside it (order: x, u, pi, res_max [B][4], iter int32
+ * [B], status int32 [B], lam, t) and its total length; srbd_download_packed copies the arena (up to `status` without
+ * the duals) into a host buffer of that layout -- pinned (srbd_host_alloc) for an asynchronous copy -- and waits. */
+int srbd_out_layout(const srbd_ctx* ctx, size_t offs[8], size_t* total_doubles);
+int srbd_download_packed(srbd_ctx* ctx, double* arena, int with_duals);
+/* pinned (page-locked) host memory for staging buffers that outlive a solve (the facades own one arena per solver:
+ * the reference's wrappers own their workspaces the same way, detail/d_ocp_qp_ipm_ws_wrapper.cpp:141-155) */
+int srbd_host_alloc(size_t bytes, void** ptr);
+int srbd_host_free(void* ptr);
 int srbd_batch_stats_get(srbd_ctx* ctx, srbd_batch_stats* out);
 
 /* ---- closed-loop batched MPC --------------------------------------------------------------------*/

@@ -125,7 +125,7 @@ _EXPORTS = [
     "srbd_download_linearization", "srbd_download_qp", "srbd_qp_upload", "srbd_qp_solve",
     "srbd_download_solution", "srbd_download_stats", "srbd_batch_stats_get", "srbd_line_search",
     "srbd_download_sqp_state", "srbd_reset_sqp_state", "srbd_sqp_iterate", "srbd_solve_host", "srbd_solve_host_async", "srbd_wait",
-    "srbd_fp64_peak", "srbd_mpc_run",
+    "srbd_fp64_peak", "srbd_mpc_run", "srbd_out_layout", "srbd_download_packed", "srbd_host_alloc", "srbd_host_free",
 ]
 
 _lib = None
@@ -183,6 +183,10 @@ def lib():
                                   c_double_p, c_double_p, c_int_p, c_int_p]
     L.srbd_wait.argtypes = [vp]
     L.srbd_fp64_peak.argtypes = [vp, c_double_p]
+    L.srbd_out_layout.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    L.srbd_download_packed.argtypes = [vp, c_double_p, C.c_int]
+    L.srbd_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.srbd_host_free.argtypes = [vp]
     L.srbd_mpc_run.argtypes = [vp, c_double_p, c_double_p, c_double_p, C.c_int, c_double_p, C.c_int, c_double_p,
                                c_double_p, c_int_p, c_int_p]
     for n in _EXPORTS:

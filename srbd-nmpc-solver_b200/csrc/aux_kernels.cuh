@@ -155,6 +155,80 @@ __global__ void __launch_bounds__(128) pack_kernel(const PackParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Structure detection for QP-level uploads with the SRBD dimensions (nx = nu = 12, 24 general rows, no boxes): does the
+// batch have the structure K2 guarantees and the tensor-core variant of K3 relies on (ipm_srbd.cuh)?
+//   S = 0, C = 0 (stages >= 1; C0 is dropped anyway), Q_k = one constant diagonal matrix for 1 <= k < N, D_k = one
+//   constant matrix made of two 12 x 6 blocks, the upper side of every row masked (ug_mask = 0).
+// R_k, Q_N (symmetric, lower triangle used), r, q, lg, lg_mask, A, B, b are free.  One warp per (QP, stage): any violation
+// raises *bad; the same warp writes the compact stage record (srbd_model.cuh: R tile, gradient row, lg, lg mask) the
+// variant reads, and item (0, 0) fills the model block (Ac = D, diag(Q)).  No host round trip: both K3 kernels are
+// launched, each gated on *bad (capi.cu).
+// ---------------------------------------------------------------------------------------------------
+struct DetectParams {
+  int B, N;
+  srbd_qp_host qp;   // DEVICE pointers
+  double* srec;      // [B][N+1][kSrec]
+  ModelDev* model;
+  int* bad;
+};
+
+__global__ void __launch_bounds__(128) detect_srbd_kernel(const DetectParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long it = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int S = p.N + 1, N = p.N;
+  if (it >= (long long)p.B * S) return;
+  const int q = (int)(it / S), k = (int)(it % S);
+  const size_t qN = (size_t)q * N + k, qS = (size_t)q * S + k;
+  bool bad = false;
+  if (k < N) {
+    if (p.qp.S)
+      for (int e = lane; e < 144; e += 32) bad |= p.qp.S[qN * 144 + e] != 0.0;
+    if (p.qp.C && k > 0)
+      for (int e = lane; e < 288; e += 32) bad |= p.qp.C[qN * 288 + e] != 0.0;
+    const double* D = p.qp.D + qN * 288;   // column-major 24 x 12: D(g, j) at g + 24 j
+    for (int e = lane; e < 288; e += 32) {
+      const int g = e % 24, j = e / 24;
+      const double v = D[e];
+      bad |= v != p.qp.D[e];                               // constant over stages and QPs
+      bad |= v != 0.0 && (j / 6) != (g / 12);              // two 12 x 6 blocks
+    }
+    if (!p.qp.ug_mask) bad = true;                         // no mask array = every row active on both sides
+    else if (lane < 24) bad |= p.qp.ug_mask[qN * 24 + lane] != 0.0;
+  }
+  if (k > 0 && k < N) {
+    const double* Q = p.qp.Q + qS * 144;
+    const double* Qr = p.qp.Q + 144;                       // QP 0, stage 1
+    for (int e = lane; e < 144; e += 32) {
+      const int i = e % 12, j = e / 12;
+      bad |= (i == j) ? (Q[e] != Qr[e]) : (Q[e] != 0.0);
+    }
+  }
+  if (__any_sync(0xffffffffu, bad) && lane == 0) atomicExch(p.bad, 1);
+  // ---- compact stage record ------------------------------------------------------------------------------------------
+  double* sr = p.srec + qS * kSrec;
+  const double* H = k < N ? p.qp.R + qN * 144 : p.qp.Q + qS * 144;   // lower 12 x 12 block of rows 0..11
+  for (int e = lane; e < 96; e += 32) {
+    const int pnl = e < 16 ? 0 : (e < 48 ? 1 : 2), off = e - (pnl == 0 ? 0 : (pnl == 1 ? 16 : 48));
+    const int j = off >> 2, i = 4 * pnl + (off & 3);
+    sr[e] = H[i + 12 * j];
+  }
+  if (lane < 12) { sr[96 + lane] = 0.0; sr[132 + lane] = 0.0; }
+  if (lane < 24) {
+    double g = 0.0;
+    if (k < N) g = lane < 12 ? p.qp.r[qN * 12 + lane] : (k > 0 ? p.qp.q[qS * 12 + lane - 12] : 0.0);
+    else g = lane < 12 ? p.qp.q[qS * 12 + lane] : 0.0;
+    sr[108 + lane] = g;
+    sr[144 + lane] = k < N ? p.qp.lg[qN * 24 + lane] : 0.0;
+    sr[168 + lane] = k < N ? (p.qp.lg_mask ? (p.qp.lg_mask[qN * 24 + lane] != 0.0 ? 1.0 : 0.0) : 1.0) : 0.0;
+  }
+  if (it == 0) {
+    for (int e = lane; e < 288; e += 32) p.model->Ac[(e % 24) * 12 + e / 24] = p.qp.D[e];
+    if (lane < 12) p.model->m.Q[lane] = N > 1 ? p.qp.Q[144 + 13 * lane] : 0.0;
+    if (lane == 0) p.model->m.R = 0.0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Closed-loop batched MPC (hpipm-cpp/examples/example_mpc.cpp:99-119, test/ocp_qp_ipm_solver.cpp:298-314): the QP data
 // stay on the device, every step only the initial state changes.  mpc_embed_kernel redoes the x0 embedding of stage 0
 // for the current plant state (same arithmetic as pack_kernel: b0 <- A0 x0 + b0, r0 <- S0 x0 + r0), mpc_plant_kernel

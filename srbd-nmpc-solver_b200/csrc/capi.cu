@@ -41,6 +41,19 @@ struct srbd_ctx {
   int *d_mpc_iter = nullptr, *d_mpc_status = nullptr;
   int mpc_steps_alloc = 0, plant_alloc = 0;
   bool warm_from_solution = false;  // the next solve takes the previous solution (on the device) as the primal warm start
+  // outputs live in ONE device arena [x | u | pi | res_max | iter | status | lam | t] (srbd_out_layout): a caller with a
+  // host arena of the same layout fetches them with a single D2H copy (srbd_download_packed)
+  double* d_out = nullptr;
+  size_t out_off[8] = {0, 0, 0, 0, 0, 0, 0, 0}, out_total = 0;
+  // QP-level uploads whose host fields lie in one contiguous (pinned) range take ONE H2D copy into this arena
+  char* d_in = nullptr;
+  size_t in_bytes = 0;
+  // uploaded QPs with the structure K2 guarantees (S = 0, C = 0, constant diagonal Q, one constant block D, upper side
+  // masked) may take the tensor-core variant: detected on the device at upload
+  ModelDev* d_model_qp = nullptr;
+  int* d_flag = nullptr;
+  int* h_flag = nullptr;     // pinned
+  bool upload_variant_ok = false;
   double *d_xinit = nullptr, *d_uinit = nullptr;
   bool have_init = false, packed = false, solved = false;
   // raw QP-level staging (lazy)
@@ -132,17 +145,23 @@ KernelChoice pick_kernel(const QpLayout& L) {
 
 int raw0_stride(const QpLayout& L) { return 2 * L.nx * L.nx + 2 * L.nx * L.nu + 2 * L.nx; }
 
-// Will srbd_qp_solve take the SRBD tensor-core variant for a QP assembled by K2 under the current settings?
-bool variant_eligible(const srbd_ctx* ctx) {
+// Do the dimensions and settings allow the SRBD tensor-core variant of K3 (cold start, classical Riccati, no Riccati /
+// statistics exports)?
+bool settings_allow_variant(const srbd_ctx* ctx) {
   const char* force = std::getenv("SRBD_K3_GENERIC");
   if (force && force[0] == '1') return false;
+  return ctx->is_srbd && !ctx->args.warm_start && ctx->args.ric_alg == 0 && !ctx->export_ric && !ctx->export_stat;
+}
+// Will srbd_qp_solve take the variant for a QP assembled by K2 under the current settings?
+bool variant_eligible(const srbd_ctx* ctx) {
+  if (!settings_allow_variant(ctx)) return false;
   // the variant relies on Ac being two 12x6 blocks (SRBD_model.cpp:244: Ac.block<12,6>(12*leg, 6*leg))
   double Ac[288];
   fill_Ac(ctx->model, Ac);
   for (int g = 0; g < 24; ++g)
     for (int j = 0; j < 12; ++j)
       if (Ac[g * 12 + j] != 0.0 && (j / 6) != (g / 12)) return false;
-  return ctx->is_srbd && !ctx->args.warm_start && ctx->args.ric_alg == 0 && !ctx->export_ric && !ctx->export_stat;
+  return true;
 }
 bool want_dense(const srbd_ctx* ctx) {
   const char* d = std::getenv("SRBD_K2_DENSE");   // diagnosis: always write the dense records
@@ -231,10 +250,25 @@ int srbd_ctx_create(int device, int batch, const srbd_qp_dims* dims, void* strea
   A(dalloc(&ctx->d_dmask, B * S * L.d_stride)); A(dalloc(&ctx->d_raw0, B * raw0_stride(L)));
   A(dalloc(&ctx->d_x0, B * L.nx)); A(dalloc(&ctx->d_xinit, B * S * L.nx)); A(dalloc(&ctx->d_uinit, B * N * L.nu));
   A(dalloc(&ctx->d_r0raw, B * L.nu));
-  A(dalloc(&ctx->d_sol_x, B * S * L.nx)); A(dalloc(&ctx->d_sol_u, B * N * L.nu)); A(dalloc(&ctx->d_sol_pi, B * S * L.nx));
-  A(dalloc(&ctx->d_sol_lam, B * (size_t)L.nct)); A(dalloc(&ctx->d_sol_t, B * (size_t)L.nct));
-  A(dalloc(&ctx->d_iter, B)); A(dalloc(&ctx->d_status, B)); A(dalloc(&ctx->d_resmax, B * 4));
+  {
+    // output arena (offsets in doubles, every block on a 256-byte boundary)
+    const size_t sizes[8] = {B * S * L.nx, B * N * L.nu, B * S * L.nx, B * 4, (B + 1) / 2, (B + 1) / 2,
+                             B * (size_t)L.nct, B * (size_t)L.nct};
+    size_t o = 0;
+    for (int i = 0; i < 8; ++i) { ctx->out_off[i] = o; o += (sizes[i] + 31) & ~(size_t)31; }
+    ctx->out_total = o;
+    A(dalloc(&ctx->d_out, o));
+    if (ok) {
+      ctx->d_sol_x = ctx->d_out + ctx->out_off[0]; ctx->d_sol_u = ctx->d_out + ctx->out_off[1];
+      ctx->d_sol_pi = ctx->d_out + ctx->out_off[2]; ctx->d_resmax = ctx->d_out + ctx->out_off[3];
+      ctx->d_iter = reinterpret_cast<int*>(ctx->d_out + ctx->out_off[4]);
+      ctx->d_status = reinterpret_cast<int*>(ctx->d_out + ctx->out_off[5]);
+      ctx->d_sol_lam = ctx->d_out + ctx->out_off[6]; ctx->d_sol_t = ctx->d_out + ctx->out_off[7];
+    }
+  }
   A(dalloc(&ctx->d_counter, 1)); A(dalloc(&ctx->d_bstats, 1));
+  A(dalloc(&ctx->d_model_qp, 1)); A(dalloc(&ctx->d_flag, 1));
+  ok = ok && cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_flag), sizeof(int), cudaHostAllocDefault) == cudaSuccess;
   if (!ok) return bail(SRBD_ERR_CUDA);
   // persistent grid: every resident warp gets a private workspace
   KernelChoice kc = pick_kernel(L);
@@ -268,15 +302,16 @@ int srbd_ctx_destroy(srbd_ctx* ctx) {
   cudaSetDevice(ctx->device);
   void* ptrs[] = {ctx->d_model, ctx->d_x, ctx->d_u, ctx->d_xref, ctx->d_x0abs, ctx->d_defect, ctx->d_contact,
                   ctx->d_alpha, ctx->d_conv, ctx->d_merit, ctx->d_babt, ctx->d_rsq, ctx->d_dct, ctx->d_d,
-                  ctx->d_dmask, ctx->d_raw0, ctx->d_x0, ctx->d_xinit, ctx->d_uinit, ctx->d_sol_x, ctx->d_sol_u,
-                  ctx->d_sol_pi, ctx->d_sol_lam, ctx->d_sol_t, ctx->d_P, ctx->d_p, ctx->d_K, ctx->d_k,
-                  ctx->d_stat, ctx->d_iter, ctx->d_status, ctx->d_counter, ctx->d_resmax, ctx->d_bstats, ctx->d_ws,
+                  ctx->d_dmask, ctx->d_raw0, ctx->d_x0, ctx->d_xinit, ctx->d_uinit, ctx->d_out, ctx->d_in, ctx->d_model_qp,
+                  ctx->d_flag, ctx->d_P, ctx->d_p, ctx->d_K, ctx->d_k,
+                  ctx->d_stat, ctx->d_counter, ctx->d_bstats, ctx->d_ws,
                   ctx->d_ws2, ctx->d_srec, ctx->d_retry, ctx->d_r0raw, ctx->d_mpc_x, ctx->d_mpc_u, ctx->d_mpc_xcur,
                   ctx->d_plantA, ctx->d_plantB, ctx->d_plantb, ctx->d_mpc_iter, ctx->d_mpc_status};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (void* p : ctx->raw_dev)
     if (p) cudaFree(p);
+  if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return SRBD_OK;
@@ -593,25 +628,57 @@ int srbd_qp_upload(srbd_ctx* ctx, const srbd_qp_host* qp) {
       {&srbd_qp_host::lgN_mask, B * L.ngN}, {&srbd_qp_host::ugN_mask, B * L.ngN},
       {&srbd_qp_host::x0, B * nx}};
   const int nf = sizeof(fields) / sizeof(fields[0]);
-  if (!ctx->raw_alloc) {
-    ctx->raw_dev.assign(nf, nullptr);
-    for (int i = 0; i < nf; ++i)
-      if (fields[i].n) CU(cudaMalloc(&ctx->raw_dev[i], fields[i].n * sizeof(double)));
-    ctx->raw_alloc = true;
-  }
+  // Host fields that lie in ONE contiguous range (the facades flatten into a pinned arena) travel in a single H2D copy
+  const char *lo = nullptr, *hi = nullptr;
+  size_t sum = 0;
+  auto span = [&](const double* ptr, size_t n) {
+    if (!ptr || !n) return;
+    const char* a = reinterpret_cast<const char*>(ptr);
+    if (!lo || a < lo) lo = a;
+    if (!hi || a + n * sizeof(double) > hi) hi = a + n * sizeof(double);
+    sum += n * sizeof(double);
+  };
+  for (int i = 0; i < nf; ++i) span(qp->*(fields[i].m), fields[i].n);
+  span(qp->x_init, qp->x_init && qp->u_init ? B * S * nx : 0);
+  span(qp->u_init, qp->x_init && qp->u_init ? B * N * nu : 0);
+  const bool contiguous = lo && (size_t)(hi - lo) <= sum + 64 * (size_t)(nf + 2);
   srbd_qp_host dq{};
-  for (int i = 0; i < nf; ++i) {
-    const double* src = qp->*(fields[i].m);
-    if (src && fields[i].n) {
-      CU(cudaMemcpyAsync(ctx->raw_dev[i], src, fields[i].n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-      dq.*(fields[i].m) = (const double*)ctx->raw_dev[i];
+  auto dev_of = [&](const double* src) { return reinterpret_cast<const double*>(ctx->d_in + (reinterpret_cast<const char*>(src) - lo)); };
+  if (contiguous) {
+    const size_t bytes = (size_t)(hi - lo);
+    if (bytes > ctx->in_bytes) {
+      if (ctx->d_in) cudaFree(ctx->d_in);
+      ctx->d_in = nullptr; ctx->in_bytes = 0;
+      CU(cudaMalloc(reinterpret_cast<void**>(&ctx->d_in), bytes));
+      ctx->in_bytes = bytes;
     }
+    CU(cudaMemcpyAsync(ctx->d_in, lo, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    for (int i = 0; i < nf; ++i) {
+      const double* src = qp->*(fields[i].m);
+      if (src && fields[i].n) dq.*(fields[i].m) = dev_of(src);
+    }
+    CU(cudaMemcpyAsync(ctx->d_x0, dev_of(qp->x0), B * nx * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  } else {
+    if (!ctx->raw_alloc) {
+      ctx->raw_dev.assign(nf, nullptr);
+      for (int i = 0; i < nf; ++i)
+        if (fields[i].n) CU(cudaMalloc(&ctx->raw_dev[i], fields[i].n * sizeof(double)));
+      ctx->raw_alloc = true;
+    }
+    for (int i = 0; i < nf; ++i) {
+      const double* src = qp->*(fields[i].m);
+      if (src && fields[i].n) {
+        CU(cudaMemcpyAsync(ctx->raw_dev[i], src, fields[i].n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        dq.*(fields[i].m) = (const double*)ctx->raw_dev[i];
+      }
+    }
+    CU(cudaMemcpyAsync(ctx->d_x0, qp->x0, B * nx * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   }
-  CU(cudaMemcpyAsync(ctx->d_x0, qp->x0, B * nx * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   ctx->have_init = false;
   if (qp->x_init && qp->u_init) {
-    CU(cudaMemcpyAsync(ctx->d_xinit, qp->x_init, B * S * nx * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->d_uinit, qp->u_init, B * N * nu * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const cudaMemcpyKind kd = contiguous ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    CU(cudaMemcpyAsync(ctx->d_xinit, contiguous ? dev_of(qp->x_init) : qp->x_init, B * S * nx * sizeof(double), kd, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_uinit, contiguous ? dev_of(qp->u_init) : qp->u_init, B * N * nu * sizeof(double), kd, ctx->stream));
     ctx->have_init = true;
   }
   PackParams p{};
@@ -624,12 +691,23 @@ int srbd_qp_upload(srbd_ctx* ctx, const srbd_qp_host* qp) {
   CU(cudaGetLastError());
   ctx->packed = true;
   ctx->assembled_mode = -1;
+  ctx->upload_variant_ok = false;
+  if (ctx->is_srbd) {  // SRBD dimensions: does the data have K2's structure?  (decided on the device, aux_kernels.cuh)
+    DetectParams dp{};
+    dp.B = ctx->B; dp.N = L.N; dp.qp = dq; dp.srec = ctx->d_srec; dp.model = ctx->d_model_qp; dp.bad = ctx->d_flag;
+    CU(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+    detect_srbd_kernel<<<(int)((total + 3) / 4), 128, 0, ctx->stream>>>(dp);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    ctx->upload_variant_ok = true;
+  }
   return SRBD_OK;
 }
 
 // K3, generic kernel (any hpipm::OcpQp data).  qlist / qcount (device): solve only those QPs and keep the batch
 // statistics accumulated so far (the rescue pass of the SRBD variant); null: the whole batch.
-static int launch_generic(srbd_ctx* ctx, const int* qlist, const int* qcount) {
+static int launch_generic(srbd_ctx* ctx, const int* qlist, const int* qcount, const int* gate = nullptr, int gate_value = 0,
+                          bool keep_stats = false) {
   const QpLayout& L = ctx->L;
   const size_t B = ctx->B, S = L.N + 1, N = L.N;
   if (ctx->export_ric && !ctx->d_P) {
@@ -654,8 +732,9 @@ static int launch_generic(srbd_ctx* ctx, const int* qlist, const int* qcount) {
   p.stat_rows = ctx->stat_rows;
   p.bstats = ctx->d_bstats;
   CU(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
-  if (!qlist) CU(cudaMemsetAsync(ctx->d_bstats, 0, sizeof(srbd_batch_stats), ctx->stream));
+  if (!qlist && !keep_stats) CU(cudaMemsetAsync(ctx->d_bstats, 0, sizeof(srbd_batch_stats), ctx->stream));
   p.qlist = qlist; p.qcount = qcount;
+  p.gate = gate; p.gate_value = gate_value;
   KernelChoice kc = pick_kernel(L);
   const int grid = qlist ? (ctx->grid < ctx->sm_count ? ctx->grid : ctx->sm_count) : ctx->grid;  // a rescue list is short
   kc.fn<<<grid, 32, 0, ctx->stream>>>(p);
@@ -667,7 +746,7 @@ static int launch_generic(srbd_ctx* ctx, const int* qlist, const int* qcount) {
 }
 
 // K3 for QPs assembled by K2: the SRBD throughput variant (same algorithm as the generic kernel)
-static int solve_srbd_variant(srbd_ctx* ctx) {
+static int solve_srbd_variant(srbd_ctx* ctx, const ModelDev* model, const int* gate = nullptr) {
   const QpLayout& L = ctx->L;
   if (!ctx->d_ws2) {
     CU(cudaFuncSetAttribute(ipm_srbd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes));
@@ -699,7 +778,8 @@ static int solve_srbd_variant(srbd_ctx* ctx) {
   SrbdIpmParams p{};
   p.B = ctx->B; p.N = L.N; p.a = ctx->args;
   p.babt = ctx->d_babt; p.srec = ctx->d_srec; p.x0 = ctx->d_x0;
-  p.model = ctx->d_model; p.ws = ctx->d_ws2; p.ws_size = (L.N + 1) * v2::kStage; p.counter = ctx->d_counter;
+  p.model = model; p.ws = ctx->d_ws2;
+  p.gate = gate; p.gate_value = 0; p.ws_size = (L.N + 1) * v2::kStage; p.counter = ctx->d_counter;
   p.sol_x = ctx->d_sol_x; p.sol_u = ctx->d_sol_u; p.sol_pi = ctx->d_sol_pi; p.sol_lam = ctx->d_sol_lam; p.sol_t = ctx->d_sol_t;
   p.iter = ctx->d_iter; p.status = ctx->d_status; p.res_max = ctx->d_resmax; p.bstats = ctx->d_bstats;
   if (rescue) {
@@ -716,7 +796,7 @@ static int solve_srbd_variant(srbd_ctx* ctx) {
   ctx->stat_valid = false;
   if (rescue) {
     // the generic kernel reads the dense records: write them for the listed QPs only (an empty kernel otherwise)
-    if (!ctx->dense_valid)
+    if (ctx->assembled_mode >= 0 && !ctx->dense_valid)
       if (int rc = launch_assemble(ctx, ctx->assembled_mode, true, ctx->d_retry, ctx->d_retry + ctx->B)) return rc;
     return launch_generic(ctx, ctx->d_retry, ctx->d_retry + ctx->B);
   }
@@ -732,7 +812,14 @@ int srbd_qp_solve(srbd_ctx* ctx) {
   CU(cudaSetDevice(ctx->device));
   // QPs assembled by K2 (both modes: BARRIER_SOFT masks every row, which the variant solves as the single unconstrained
   // Riccati pass) take the SRBD tensor-core variant unless a setting needs the generic kernel
-  if (ctx->assembled_mode >= 0 && variant_eligible(ctx)) return solve_srbd_variant(ctx);
+  if (ctx->assembled_mode >= 0 && variant_eligible(ctx)) return solve_srbd_variant(ctx, ctx->d_model);
+  if (ctx->assembled_mode < 0 && ctx->upload_variant_ok && settings_allow_variant(ctx)) {
+    // Uploaded QP with the SRBD dimensions: detect_srbd_kernel left *d_flag = 0 if it has K2's structure.  Both kernels
+    // are launched, each gated on the flag (no host round trip): the variant (+ its rescue launch) runs if 0, the
+    // generic kernel if 1.
+    if (int rc = solve_srbd_variant(ctx, ctx->d_model_qp, ctx->d_flag)) return rc;
+    return launch_generic(ctx, nullptr, nullptr, ctx->d_flag, 1, true);
+  }
   if (int rc = ensure_dense(ctx)) return rc;
   return launch_generic(ctx, nullptr, nullptr);
 }
@@ -755,6 +842,34 @@ int srbd_download_solution(srbd_ctx* ctx, const srbd_sol_host* sol) {
   CU(dl(sol->P, ctx->d_P, B * S * L.nx * L.nx)); CU(dl(sol->p, ctx->d_p, B * S * L.nx));
   CU(dl(sol->K, ctx->d_K, B * N * L.nu * L.nx)); CU(dl(sol->k, ctx->d_k, B * N * L.nu));
   CU(cudaStreamSynchronize(ctx->stream));
+  return SRBD_OK;
+}
+
+int srbd_out_layout(const srbd_ctx* ctx, size_t offs[8], size_t* total_doubles) {
+  if (!ctx || !offs || !total_doubles) return SRBD_ERR_ARG;
+  for (int i = 0; i < 8; ++i) offs[i] = ctx->out_off[i];
+  *total_doubles = ctx->out_total;
+  return SRBD_OK;
+}
+
+int srbd_download_packed(srbd_ctx* ctx, double* arena, int with_duals) {
+  if (!ctx || !arena) return SRBD_ERR_ARG;
+  if (!ctx->solved) return fail(ctx, SRBD_ERR_STATE, "solve first");
+  CU(cudaSetDevice(ctx->device));
+  const size_t n = with_duals ? ctx->out_total : ctx->out_off[6];
+  CU(cudaMemcpyAsync(arena, ctx->d_out, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SRBD_OK;
+}
+
+int srbd_host_alloc(size_t bytes, void** ptr) {
+  if (!ptr) return SRBD_ERR_ARG;
+  *ptr = nullptr;
+  return cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? SRBD_OK : SRBD_ERR_CUDA;
+}
+
+int srbd_host_free(void* ptr) {
+  if (ptr && cudaFreeHost(ptr) != cudaSuccess) return SRBD_ERR_CUDA;
   return SRBD_OK;
 }
 

@@ -46,6 +46,9 @@ struct IpmParams {
   // optional work list: solve only the QPs qlist[0 .. *qcount) (the rescue pass behind the SRBD variant, capi.cu)
   const int* qlist;
   const int* qcount;
+  // device-side dispatch (QP-level uploads, capi.cu): run only if *gate == gate_value
+  const int* gate;
+  int gate_value;
 };
 
 // compile-time dimension policy (loops unroll, index math folds) ...
@@ -1055,6 +1058,7 @@ __global__ void __launch_bounds__(32) ipm_solve_kernel(const IpmParams p) {
   __shared__ double smem[Solver<D>::kSmemDoubles];
   __shared__ int sidx[3 * kMaxNB];
   __shared__ int s_next;
+  if (p.gate && *p.gate != p.gate_value) return;
   if (p.qlist && *p.qcount == 0) return;  // empty rescue list (the usual case): nothing to set up
   Solver<D> S(p, smem, sidx);
   // per-CTA partial batch statistics (fused epilogue; one set of atomics per CTA at the end)

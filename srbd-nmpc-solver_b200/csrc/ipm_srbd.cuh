@@ -63,6 +63,9 @@ struct SrbdIpmParams {
   // the generic kernel (row-by-row substitution, no block inverses) on exactly those
   int* retry_list;
   int* retry_count;
+  // device-side dispatch (QP-level uploads, capi.cu): run only if *gate == gate_value
+  const int* gate;
+  int gate_value;
 };
 
 namespace v2 {
@@ -1478,6 +1481,7 @@ struct SrbdSolver {
 #endif
 __global__ void SRBD_K3_BOUNDS ipm_srbd_kernel(const SrbdIpmParams p) {
   extern __shared__ __align__(128) double2 smem2[];  // no static shared memory: the tiles start on 128-byte lines
+  if (p.gate && *p.gate != p.gate_value) return;
   double* smem = reinterpret_cast<double*>(smem2);
   int* s_next = reinterpret_cast<int*>(smem + v2::sQ + 16);  // one int per warp behind diag(Q), R
   static_assert(v2::kWarps <= 32, "work-counter slots");

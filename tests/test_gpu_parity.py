@@ -671,3 +671,57 @@ def test_closed_loop_batched_mpc_on_device(pkg, orc, golden_quadcopter):
         oa["x_init"], oa["u_init"] = o["x"].copy(), o["u"].copy()
         x = x @ A.T + o["u"][:, 0] @ Bm.T
     assert iters_equal >= 0.97 * B * steps, (iters_equal, B * steps)
+
+
+@pytest.mark.gpu
+def test_uploaded_srbd_qps_reach_the_tensor_core_kernel(pkg, orc):
+    """The reference's own boundary (hpipm::OcpQpIpmSolver::solve -> srbd_qp_upload / srbd_qp_solve) must reach the fast
+    kernel: a batch with the SRBD dimensions is checked on the device for the structure K2 guarantees
+    (detect_srbd_kernel) and routed to the tensor-core variant when the settings allow.  (1) K2's own QPs, downloaded and
+    uploaded again as plain hpipm-cpp fields, give BIT-IDENTICAL iterates to the NMPC-level path (same kernel, same
+    data); (2) with Riccati exports requested, or (3) with one S entry made non-zero, the generic kernel runs instead
+    and the result matches the oracle."""
+    from srbd_nmpc_solver_b200.binding import make_dims
+    B, N = 96, 20
+    w = pkg.workload.srbd_batch(B, N=N, contact_mode="gait", start=300)
+    with make_ctx(pkg, B, N) as ctx:
+        ctx.upload_traj(w["x"], w["u"], w["xref"], w["x0"], w["contact"])
+        ctx.sqp_iterate(1)
+        sol_k2 = ctx.download_solution(want=("x", "u", "pi", "lam", "t"))
+        st_k2 = ctx.download_stats()
+        lin, qp = ctx.download_linearization(), ctx.download_qp()
+    arrays = dict(A=lin["A"], Bm=lin["Bm"], b=lin["b"], Q=qp["Q"], S=qp["S"], R=qp["R"], q=qp["q"], r=qp["r"],
+                  D=qp["D"], lg=qp["lg"], ug=np.zeros_like(qp["lg"]), lg_mask=qp["lg_mask"],
+                  ug_mask=np.zeros_like(qp["lg"]), x0=w["x0"] - w["x"][:, 0])
+    with make_ctx(pkg, B, N) as ctx:
+        ctx.qp_upload(arrays)
+        ctx.qp_solve()
+        sol = ctx.download_solution(want=("x", "u", "pi", "lam", "t"))
+        st = ctx.download_stats()
+        bs = ctx.batch_stats()
+        assert (st["iter"] == st_k2["iter"]).all() and (st["status"] == st_k2["status"]).all()
+        for k in ("x", "u", "lam", "t"):
+            assert np.array_equal(sol[k], sol_k2[k]), k            # same kernel on the same data
+        assert np.array_equal(sol["pi"][:, 1:], sol_k2["pi"][:, 1:])
+        assert bs["solves"] == B and bs["iter_sum"] == int(st["iter"].sum())
+        # (2) exports requested: the generic kernel (and P, p, K, k come back)
+        ctx.set_outputs(export_ric=True, export_stat=False)
+        ctx.qp_solve()
+        sol_g = ctx.download_solution()
+        st_g = ctx.download_stats()
+        assert (st_g["iter"] == st["iter"]).all() and not np.array_equal(sol_g["x"], sol["x"])
+        assert relerr(sol_g["x"], sol["x"]).max() <= TOL and np.isfinite(sol_g["P"]).all()
+        ctx.set_outputs(export_ric=False, export_stat=False)
+        # (3) structure broken: S != 0 in one stage of one QP
+        arrays2 = dict(arrays, S=arrays["S"].copy())
+        arrays2["S"][5, 3, 7] = 1e-3
+        ctx.qp_upload(arrays2)
+        ctx.qp_solve()
+        sol2 = ctx.download_solution(want=("x", "u"))
+        st2 = ctx.download_stats()
+        bs2 = ctx.batch_stats()
+    ref2 = orc.qp_solve(make_dims(N=N), orc.ipm_args(**SETTINGS), arrays2, B, want=("x", "u"))
+    assert (st2["iter"] == ref2["iter"]).all() and (st2["status"] == ref2["status"]).all()
+    assert relerr(sol2["x"], ref2["x"]).max() <= TOL
+    assert bs2["solves"] == B and bs2["iter_sum"] == int(st2["iter"].sum())
+    assert not np.array_equal(sol2["x"][5], sol["x"][5])
