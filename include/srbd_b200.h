@@ -97,6 +97,13 @@ typedef struct srbd_ipm_args {
   double lam_min, t_min, tau_min; /* 1e-16 */
   int t_lam_min;           /* 2: clip lam,t after the update */
   int alpha_shorten;       /* 0: alpha*=0.995 ; 1: alpha*=((1-alpha)*0.99+alpha*0.9999999) */
+  /* iterative refinement of the Newton steps (hpipm_d_ocp_qp_ipm.h:74-75; 0 / 0 in SPEED, 0 / 2 in BALANCE, 0 / 4 in
+   * ROBUST mode): after the predictor (itref_pred_max) / corrector (itref_corr_max) solve, the residual of the LINEAR
+   * KKT system is computed, and while it is neither below itref_abs x the exit tolerance nor below itref_rel x the
+   * current nonlinear residual (component-wise: stat, eq, ineq, comp) the system is solved again for it with the same
+   * factorization and the correction added to the step. */
+  int itref_pred_max, itref_corr_max;
+  double itref_abs, itref_rel; /* 1.0, 1e-3 */
 } srbd_ipm_args;
 
 /* Uniform OCP-QP dimensions (stage 0 has its state eliminated by the x0 embedding, stage N has
@@ -217,6 +224,13 @@ void srbd_model_params_default(srbd_model_params* p, int horizon);
 /* The fields of OcpQpIpmSolverSettings get that struct's defaults (ocp_qp_ipm_solver_settings.hpp:26-86), the hidden
  * constants those of HPIPM's SPEED mode (d_ocp_qp_ipm_arg_set_default(SPEED)). */
 void srbd_ipm_args_default(srbd_ipm_args* a);
+/* The hidden constants of d_ocp_qp_ipm_arg_set_default(mode) (hpipm-cpp/src/ocp_qp_ipm_solver.cpp:103; mode = hpipm-cpp's
+ * HpipmMode: 0 SpeedAbs, 1 Speed, 2 Balance, 3 Robust) that this implementation honours: cond_pred_corr (0 in SpeedAbs),
+ * itref_pred_max / itref_corr_max (0 / 2 in Balance, 0 / 4 in Robust).  NOT implemented: the absolute-form iteration of
+ * SpeedAbs (abs_form = 1: the delta form runs instead) and the LQ re-factorization of Balance / Robust (lq_fact = 1 / 2).
+ * Returns SRBD_ERR_ARG for an unknown mode.  The public fields (iter_max, tolerances, ...) are left alone: hpipm-cpp
+ * overrides them from OcpQpIpmSolverSettings right after (:104-116). */
+int srbd_ipm_args_set_mode(srbd_ipm_args* a, int mode);
 size_t srbd_qp_nct(const srbd_qp_dims* d); /* length of lam / t per QP */
 
 /* ---- context ------------------------------------------------------------------------------- */

@@ -72,6 +72,9 @@ typedef struct {
   real *rg, *rb, *rdl, *rdu, *rml, *rmu, *rml_bkp, *rmu_bkp;
   /* Gamma / gamma */
   real *Gl, *Gu, *gl, *gu;
+  /* iterative refinement: residual of the linear system (rhs of the correction solve) and the correction */
+  real *lg_, *lb_, *ldl, *ldu, *lml, *lmu, *cz, *cpi;
+  real lin_max[4];
   /* Riccati factors */
   real *Lr, *Ls, *lv, *P, *p, *Lfull, *Pb;
   /* scratch */
@@ -123,6 +126,8 @@ static W* w_create(const srbd_qp_dims* d) {
   w->rdl = dalloc(S * nc); w->rdu = dalloc(S * nc); w->rml = dalloc(S * nc); w->rmu = dalloc(S * nc);
   w->rml_bkp = dalloc(S * nc); w->rmu_bkp = dalloc(S * nc);
   w->Gl = dalloc(S * nc); w->Gu = dalloc(S * nc); w->gl = dalloc(S * nc); w->gu = dalloc(S * nc);
+  w->lg_ = dalloc(S * nm); w->lb_ = dalloc(S * nx); w->ldl = dalloc(S * nc); w->ldu = dalloc(S * nc);
+  w->lml = dalloc(S * nc); w->lmu = dalloc(S * nc); w->cz = dalloc(S * nm); w->cpi = dalloc(S * nx);
   w->Lr = dalloc(S * nu * nu); w->Ls = dalloc(S * nx * nu); w->lv = dalloc(S * nm);
   w->P = dalloc(S * nx * nx); w->p = dalloc(S * nx); w->Lfull = dalloc(S * nm * nm); w->Pb = dalloc(S * nx);
   w->M = dalloc(nm * nm); w->AL = dalloc(nm * nx); w->gt = dalloc(nm); w->tmp = dalloc(nm + nx + nc);
@@ -137,6 +142,7 @@ static void w_free(W* w) {
   free(w->rb); free(w->rdl); free(w->rdu); free(w->rml); free(w->rmu); free(w->rml_bkp); free(w->rmu_bkp);
   free(w->Gl); free(w->Gu); free(w->gl); free(w->gu); free(w->Lr); free(w->Ls); free(w->lv); free(w->P);
   free(w->p); free(w->Lfull); free(w->Pb); free(w->M); free(w->AL); free(w->gt); free(w->tmp);
+  free(w->lg_); free(w->lb_); free(w->ldl); free(w->ldu); free(w->lml); free(w->lmu); free(w->cz); free(w->cpi);
   free(w);
 }
 
@@ -625,6 +631,114 @@ static void compute_Gamma_gamma(W* w, int with_Gamma) {
   }
 }
 
+/* Residual of the LINEAR KKT system at the step (dz, dpi, dlam, dt) -- d_ocp_qp_res_compute_lin (hpipm_d_ocp_qp_res.h)
+ * with qp_step's right-hand sides (rg, rb, rd, rm of the solve being refined):
+ *   lin_g = H dz + rg + G dpi - [0; dpi_{k-1}] + J^T (dlam_u - dlam_l)      lin_b = G^T dz + rb - dx_{k+1}
+ *   lin_d_l = (-J dz + dt_l) + rd_l,  lin_d_u = (J dz + dt_u) + rd_u           lin_m = lam dt + t dlam + rm
+ * and its inf-norms (stat, eq, ineq, comp) in w->lin_max. */
+static void compute_res_lin(W* w) {
+  const int nm = w->nm;
+  real n_g = 0.0, n_b = 0.0, n_d = 0.0, n_m = 0.0;
+  for (int k = 0; k <= w->N; ++k) {
+    const int nuk = w->nuk[k], nxk = w->nxk[k], n = nuk + nxk, nb = w->nbk[k], ng = w->ngk[k], nc = nb + ng;
+    const real* H = HK(w, k);
+    const real* dz = VN(w, dz, k);
+    real* lg = VN(w, lg_, k);
+    for (int i = 0; i < n; ++i) {
+      real s = 0.0;
+      for (int j = 0; j < n; ++j) s += (i >= j ? H[i + nm * j] : H[j + nm * i]) * dz[j];
+      lg[i] = s + VN(w, rg, k)[i];
+    }
+    if (k < w->N) {
+      const real* G = GK(w, k);
+      const real* dpi = VX(w, dpi, k);
+      const real* dzn = VN(w, dz, k + 1);
+      real* lb = VX(w, lb_, k);
+      for (int i = 0; i < n; ++i) {
+        real s = 0.0;
+        for (int j = 0; j < w->nx; ++j) s += G[i + nm * j] * dpi[j];
+        lg[i] += s;
+      }
+      for (int j = 0; j < w->nx; ++j) {
+        real s = 0.0;
+        for (int i = 0; i < n; ++i) s += G[i + nm * j] * dz[i];
+        lb[j] = (s + VX(w, rb, k)[j]) - dzn[w->nuk[k + 1] + j];
+        if (R_FABS(lb[j]) > n_b) n_b = R_FABS(lb[j]);
+      }
+    }
+    if (k > 0) {
+      const real* dpim = VX(w, dpi, k - 1);
+      for (int i = 0; i < nxk; ++i) lg[nuk + i] -= dpim[i];
+    }
+    real* v = w->tmp;
+    for (int j = 0; j < nc; ++j) v[j] = VC(w, dlu, k)[j] - VC(w, dll, k)[j];
+    apply_Jt_add(w, k, v, lg);
+    apply_J(w, k, dz, v);
+    for (int j = 0; j < nc; ++j) {
+      const real ml = VC(w, ml, k)[j], mu = VC(w, mu, k)[j];
+      const real ldl = ((-v[j] + VC(w, dtl, k)[j]) + VC(w, rdl, k)[j]) * ml;
+      const real ldu = ((v[j] + VC(w, dtu, k)[j]) + VC(w, rdu, k)[j]) * mu;
+      const real lml = ((VC(w, ll, k)[j] * VC(w, dtl, k)[j] + VC(w, tl, k)[j] * VC(w, dll, k)[j]) + VC(w, rml, k)[j]) * ml;
+      const real lmu = ((VC(w, lu, k)[j] * VC(w, dtu, k)[j] + VC(w, tu, k)[j] * VC(w, dlu, k)[j]) + VC(w, rmu, k)[j]) * mu;
+      VC(w, ldl, k)[j] = ldl; VC(w, ldu, k)[j] = ldu; VC(w, lml, k)[j] = lml; VC(w, lmu, k)[j] = lmu;
+      if (R_FABS(ldl) > n_d) n_d = R_FABS(ldl);
+      if (R_FABS(ldu) > n_d) n_d = R_FABS(ldu);
+      if (R_FABS(lml) > n_m) n_m = R_FABS(lml);
+      if (R_FABS(lmu) > n_m) n_m = R_FABS(lmu);
+    }
+    for (int i = 0; i < n; ++i)
+      if (R_FABS(lg[i]) > n_g) n_g = R_FABS(lg[i]);
+  }
+  w->lin_max[0] = n_g; w->lin_max[1] = n_b; w->lin_max[2] = n_d; w->lin_max[3] = n_m;
+}
+
+/* Iterative refinement of the current step (hpipm_d_ocp_qp_ipm.h:74-75 itref_pred_max / itref_corr_max): up to `max_it`
+ * times: linear residual; stop when every component is below itref_abs * its exit tolerance or itref_rel * the current
+ * nonlinear residual; else solve the KKT system for it with the stored factorization (d_ocp_qp_solve_kkt_step on
+ * qp_itref) and add the correction to (dz, dpi, dlam, dt).  Returns the number of refinement solves. */
+static void kkt_solve(W* w, const srbd_ipm_args* a, int fact, int with_constr, const real* rhs_g,
+                      const real* rhs_b, real* oz, real* opi);
+static int refine_step(W* w, const srbd_ipm_args* a, int max_it) {
+  const int N = w->N;
+  const double tol[4] = {a->tol_stat, a->tol_eq, a->tol_ineq, a->tol_comp};
+  int done = 0;
+  for (int it = 0; it < max_it; ++it) {
+    compute_res_lin(w);
+    int ok = 1;
+    for (int i = 0; i < 4; ++i)
+      ok = ok && (w->lin_max[i] < a->itref_abs * tol[i] || w->lin_max[i] < a->itref_rel * w->res_max[i]);
+    if (ok) break;
+    /* gamma of the correction solve from (lin_m, lin_d); Gamma unchanged */
+    for (int k = 0; k <= N; ++k) {
+      const int nc = w->nbk[k] + w->ngk[k];
+      for (int j = 0; j < nc; ++j) {
+        const real til = 1.0 / VC(w, tl, k)[j], tiu = 1.0 / VC(w, tu, k)[j];
+        VC(w, gl, k)[j] = (til * (VC(w, lml, k)[j] - VC(w, ll, k)[j] * VC(w, ldl, k)[j])) * VC(w, ml, k)[j];
+        VC(w, gu, k)[j] = (tiu * (VC(w, lmu, k)[j] - VC(w, lu, k)[j] * VC(w, ldu, k)[j])) * VC(w, mu, k)[j];
+      }
+    }
+    kkt_solve(w, a, 0, 1, w->lg_, w->lb_, w->cz, w->cpi);
+    for (int k = 0; k <= N; ++k) {
+      const int n = w->nuk[k] + w->nxk[k], nc = w->nbk[k] + w->ngk[k];
+      real* v = w->tmp;
+      apply_J(w, k, VN(w, cz, k), v);
+      for (int j = 0; j < nc; ++j) {
+        const real ml = VC(w, ml, k)[j], mu = VC(w, mu, k)[j];
+        const real ctl = (v[j] - VC(w, ldl, k)[j]) * ml;
+        const real ctu = (-v[j] - VC(w, ldu, k)[j]) * mu;
+        const real cll = (-(VC(w, ll, k)[j] * ctl + VC(w, lml, k)[j]) / VC(w, tl, k)[j]) * ml;
+        const real clu = (-(VC(w, lu, k)[j] * ctu + VC(w, lmu, k)[j]) / VC(w, tu, k)[j]) * mu;
+        VC(w, dtl, k)[j] += ctl; VC(w, dtu, k)[j] += ctu; VC(w, dll, k)[j] += cll; VC(w, dlu, k)[j] += clu;
+      }
+      for (int i = 0; i < n; ++i) VN(w, dz, k)[i] += VN(w, cz, k)[i];
+      if (k < N)
+        for (int i = 0; i < w->nx; ++i) VX(w, dpi, k)[i] += VX(w, cpi, k)[i];
+    }
+    ++done;
+  }
+  return done;
+}
+
 /* dt = +-J dz - res_d ; dlam = -(lam*dt + res_m)/t   (d_compute_lam_t_qp) */
 static void compute_dlam_dt(W* w) {
   for (int k = 0; k <= w->N; ++k) {
@@ -734,6 +848,10 @@ static int ipm_solve(W* w, const srbd_ipm_args* a, int* iter_out, double* stat, 
     compute_Gamma_gamma(w, 1);
     kkt_solve(w, a, 1, 1, w->rg, w->rb, w->dz, w->dpi);
     compute_dlam_dt(w);
+    if (a->itref_pred_max > 0) {
+      const int nref = refine_step(w, a, a->itref_pred_max);
+      if (row) row[12] = nref;
+    }
     real ap, ad;
     step_length(w, &ap, &ad);
     real alpha_aff = ap < ad ? ap : ad;
@@ -756,6 +874,13 @@ static int ipm_solve(W* w, const srbd_ipm_args* a, int* iter_out, double* stat, 
       compute_Gamma_gamma(w, 0);
       kkt_solve(w, a, 0, 1, w->rg, w->rb, w->dz, w->dpi);
       compute_dlam_dt(w);
+      if (a->itref_corr_max > 0) {
+        const int nref = refine_step(w, a, a->itref_corr_max);
+        if (row) {
+          row[13] = nref;
+          for (int i = 0; i < 4; ++i) row[14 + i] = (double)w->lin_max[i];
+        }
+      }
       step_length(w, &ap, &ad);
       if (a->cond_pred_corr == 1) {
         const real al = ap < ad ? ap : ad;
@@ -1076,5 +1201,6 @@ void orc_ipm_args_default(srbd_ipm_args* a) {
   /* hidden HPIPM SPEED-mode defaults */
   a->cond_pred_corr = 1; a->cond_factor = 2.0; a->thr0 = 0.1;
   a->lam_min = a->t_min = a->tau_min = 1e-16; a->t_lam_min = 2; a->alpha_shorten = 1;
+  a->itref_pred_max = 0; a->itref_corr_max = 0; a->itref_abs = 1.0; a->itref_rel = 1e-3;
 }
 #endif

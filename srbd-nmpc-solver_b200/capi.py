@@ -36,7 +36,9 @@ class IpmArgs(C.Structure):
                 ("pred_corr", C.c_int), ("ric_alg", C.c_int), ("split_step", C.c_int),
                 ("cond_pred_corr", C.c_int), ("cond_factor", C.c_double), ("thr0", C.c_double),
                 ("lam_min", C.c_double), ("t_min", C.c_double), ("tau_min", C.c_double),
-                ("t_lam_min", C.c_int), ("alpha_shorten", C.c_int)]
+                ("t_lam_min", C.c_int), ("alpha_shorten", C.c_int),
+                ("itref_pred_max", C.c_int), ("itref_corr_max", C.c_int), ("itref_abs", C.c_double),
+                ("itref_rel", C.c_double)]
 
 
 class QpDims(C.Structure):
@@ -117,7 +119,7 @@ def make_qp_host(arrays):
 
 
 _EXPORTS = [
-    "srbd_model_params_default", "srbd_ipm_args_default", "srbd_qp_nct", "srbd_ctx_create",
+    "srbd_model_params_default", "srbd_ipm_args_default", "srbd_ipm_args_set_mode", "srbd_qp_nct", "srbd_ctx_create",
     "srbd_ctx_destroy", "srbd_last_error", "srbd_set_model", "srbd_set_ipm_args", "srbd_set_outputs",
     "srbd_ctx_stat_rows",
     "srbd_ctx_stream", "srbd_ctx_device_ptr", "srbd_ctx_sync", "srbd_ctx_launch_count",
@@ -146,6 +148,7 @@ def lib():
     L.srbd_model_params_default.restype = None
     L.srbd_ipm_args_default.argtypes = [C.POINTER(IpmArgs)]
     L.srbd_ipm_args_default.restype = None
+    L.srbd_ipm_args_set_mode.argtypes = [C.POINTER(IpmArgs), C.c_int]
     L.srbd_qp_nct.argtypes = [C.POINTER(QpDims)]
     L.srbd_qp_nct.restype = C.c_size_t
     L.srbd_ctx_create.argtypes = [C.c_int, C.c_int, C.POINTER(QpDims), vp, C.POINTER(vp)]

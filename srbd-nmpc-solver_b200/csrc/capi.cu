@@ -150,7 +150,8 @@ int raw0_stride(const QpLayout& L) { return 2 * L.nx * L.nx + 2 * L.nx * L.nu + 
 bool settings_allow_variant(const srbd_ctx* ctx) {
   const char* force = std::getenv("SRBD_K3_GENERIC");
   if (force && force[0] == '1') return false;
-  return ctx->is_srbd && !ctx->args.warm_start && ctx->args.ric_alg == 0 && !ctx->export_ric && !ctx->export_stat;
+  return ctx->is_srbd && !ctx->args.warm_start && ctx->args.ric_alg == 0 && !ctx->export_ric && !ctx->export_stat &&
+         ctx->args.itref_pred_max == 0 && ctx->args.itref_corr_max == 0;   // (the variant has no iterative refinement)
 }
 // Will srbd_qp_solve take the variant for a QP assembled by K2 under the current settings?
 bool variant_eligible(const srbd_ctx* ctx) {
@@ -199,6 +200,15 @@ void srbd_ipm_args_default(srbd_ipm_args* a) {
   a->reg_prim = 1e-12; a->warm_start = 0; a->pred_corr = 1; a->ric_alg = 1; a->split_step = 0;
   a->cond_pred_corr = 1; a->cond_factor = 2.0; a->thr0 = 0.1;  // HPIPM SPEED-mode hidden defaults
   a->lam_min = a->t_min = a->tau_min = 1e-16; a->t_lam_min = 2; a->alpha_shorten = 1;
+  a->itref_pred_max = 0; a->itref_corr_max = 0; a->itref_abs = 1.0; a->itref_rel = 1e-3;
+}
+
+int srbd_ipm_args_set_mode(srbd_ipm_args* a, int mode) {
+  if (!a || mode < 0 || mode > 3) return SRBD_ERR_ARG;
+  a->cond_pred_corr = mode == 0 ? 0 : 1;
+  a->itref_pred_max = 0;
+  a->itref_corr_max = mode == 2 ? 2 : (mode == 3 ? 4 : 0);
+  return SRBD_OK;
 }
 
 size_t srbd_qp_nct(const srbd_qp_dims* d) {
@@ -333,6 +343,8 @@ int srbd_set_ipm_args(srbd_ctx* ctx, const srbd_ipm_args* a) {
   if (!ctx || !a) return SRBD_ERR_ARG;
   if (a->iter_max < 0 || a->iter_max > 1000) return fail(ctx, SRBD_ERR_ARG, "iter_max out of range");
   if (a->ric_alg != 0 && a->ric_alg != 1) return fail(ctx, SRBD_ERR_ARG, "ric_alg must be 0 (classical) or 1 (square root)");
+  if (a->itref_pred_max < 0 || a->itref_corr_max < 0 || a->itref_pred_max > 16 || a->itref_corr_max > 16)
+    return fail(ctx, SRBD_ERR_ARG, "itref_pred_max / itref_corr_max out of range");
   ctx->args = *a;
   const int rows = a->iter_max + 2;
   if (rows != ctx->stat_rows) {

@@ -138,9 +138,13 @@ struct Solver {
   double* W;
   double *sM, *sB, *sP, *sLi, *sQx, *sqx, *sg, *st, *sx, *sxn, *sdinv, *spn, *sLx;
   int* sIdx;
+  // which workspace vectors the KKT solve reads as its right-hand sides (the step solves: the residuals; the
+  // refinement solves: the residual of the linear system)
+  struct Rhs { int rg, rb, rdl, rdu, rml, rmu; } rhs;
 
   __device__ Solver(const IpmParams& p_, double* smem, int* sidx)
       : p(p_), L(p_.L), dm(p_.L), lane(threadIdx.x & 31), q(0), N(p_.L.N) {
+    rhs = Rhs{L.ws_rg, L.ws_rb, L.ws_rdl, L.ws_rdu, L.ws_rml, L.ws_rmu};
     W = p.ws + (size_t)blockIdx.x * L.ws_size;
     sM = smem;
     sB = sM + (D::kNM + 1) * LD;
@@ -256,8 +260,8 @@ struct Solver {
       const double ll = wC(L.ws_ll, s.k)[j], lu = wC(L.ws_lu, s.k)[j];
       const double til = 1.0 / wC(L.ws_tl, s.k)[j], tiu = 1.0 / wC(L.ws_tu, s.k)[j];
       const double Gl = (til * ll) * ml, Gu = (tiu * lu) * mu;
-      const double gl = (til * (wC(L.ws_rml, s.k)[j] - ll * wC(L.ws_rdl, s.k)[j])) * ml;
-      const double gu = (tiu * (wC(L.ws_rmu, s.k)[j] - lu * wC(L.ws_rdu, s.k)[j])) * mu;
+      const double gl = (til * (wC(rhs.rml, s.k)[j] - ll * wC(rhs.rdl, s.k)[j])) * ml;
+      const double gu = (tiu * (wC(rhs.rmu, s.k)[j] - lu * wC(rhs.rdu, s.k)[j])) * mu;
       sQx[j] = Gl + Gu;
       sqx[j] = gl - gu;
     }
@@ -279,14 +283,14 @@ struct Solver {
       const double* dct = gDCt(k);
       // ---- rhs gradient row --------------------------------------------------------------------
       if (lane < n) {
-        double g = absolute ? __ldg(rsq + pm_index(n, lane, rsq_cn())) : wN(L.ws_rg, k)[lane];
+        double g = absolute ? __ldg(rsq + pm_index(n, lane, rsq_cn())) : wN(rhs.rg, k)[lane];
         if (constr) g += Jtv_row(s, dct, sqx, lane);
         sg[lane] = g;
       }
       // rb / b row of this stage into sxn, t = P_{k+1} rb + p_{k+1} into st[0..nxn)
       if (k < N) {
         if (lane < nxn)
-          sxn[lane] = absolute ? __ldg(gBAbt(k) + pm_index(n, lane, babt_cn())) : wX(L.ws_rb, k)[lane];
+          sxn[lane] = absolute ? __ldg(gBAbt(k) + pm_index(n, lane, babt_cn())) : wX(rhs.rb, k)[lane];
         if (!fact) {  // P_{k+1}, p_{k+1} from the workspace (fact keeps them in sP from the previous stage)
           const double* Pn = wP(k + 1);
           for (int e = lane; e < nxn * nxn; e += 32) sP[(e / nxn) * LDP + (e % nxn)] = Pn[e];
@@ -506,7 +510,7 @@ struct Solver {
         if (lane < nxn) {
           double acc = 0.0;
           for (int i = 0; i < n; ++i) acc += __ldg(ba + pm_index(i, lane, babt_cn())) * sx[i];
-          const double rb = absolute ? __ldg(ba + pm_index(n, lane, babt_cn())) : wX(L.ws_rb, k)[lane];
+          const double rb = absolute ? __ldg(ba + pm_index(n, lane, babt_cn())) : wX(rhs.rb, k)[lane];
           acc += rb;
           sxn[lane] = acc;
           zn[s.nun + lane] = acc;
@@ -703,6 +707,23 @@ struct Solver {
     ad = warp_min(a_d);
   }
 
+  // d_compute_alpha_qp on the stored step (after a refinement changed it)
+  __device__ void step_lengths(double& ap, double& ad) {
+    double a_p = 1.0, a_d = 1.0;
+    for (int k = 0; k <= N; ++k) {
+      const St s = stage(k);
+      for (int j = lane; j < s.nc; j += 32) {
+        const double dtl = wC(L.ws_dtl, k)[j], dtu = wC(L.ws_dtu, k)[j], dll = wC(L.ws_dll, k)[j], dlu = wC(L.ws_dlu, k)[j];
+        if (dtl < 0.0) a_p = fmin(a_p, -wC(L.ws_tl, k)[j] / dtl);
+        if (dtu < 0.0) a_p = fmin(a_p, -wC(L.ws_tu, k)[j] / dtu);
+        if (dll < 0.0) a_d = fmin(a_d, -wC(L.ws_ll, k)[j] / dll);
+        if (dlu < 0.0) a_d = fmin(a_d, -wC(L.ws_lu, k)[j] / dlu);
+      }
+    }
+    ap = warp_min(a_p);
+    ad = warp_min(a_d);
+  }
+
   // d_compute_mu_aff_qp
   __device__ double mu_aff(double alpha, int nc_mask) {
     double sm = 0.0;
@@ -714,6 +735,114 @@ struct Solver {
       }
     }
     return warp_sum(sm) / (double)nc_mask;
+  }
+
+  // ------------------------------------------------------------------------------------------------
+  // Iterative refinement (hpipm_d_ocp_qp_ipm.h:74-75 itref_pred_max / itref_corr_max; BALANCE / ROBUST modes).
+  // residuals_lin: d_ocp_qp_res_compute_lin -- the residual of the LINEAR KKT system at the current step
+  //   lin_g = H dz + rg + G dpi - [0; dpi_{k-1}] + J^T (dlam_u - dlam_l)     lin_b = G^T dz + rb - dx_{k+1}
+  //   lin_d_l = (-J dz + dt_l) + rd_l,  lin_d_u = (J dz + dt_u) + rd_u          lin_m = lam dt + t dlam + rm
+  // (rg, rb, rd, rm = the right-hand sides of the solve being refined) and its inf-norms.
+  // ------------------------------------------------------------------------------------------------
+  __device__ void residuals_lin(double lin[4]) {
+    double ng_ = 0.0, nb_ = 0.0, nd_ = 0.0, nm_ = 0.0;
+    const int nc_m = ncm();
+    for (int k = 0; k <= N; ++k) {
+      const St s = stage(k);
+      const int n = s.n, nu = s.nu;
+      const double* dz = wN(L.ws_dz, k);
+      const double* rsq = gRSQ(k);
+      const double* dct = gDCt(k);
+      const double* mk = gMask(k);
+      if (lane < n) sx[lane] = dz[lane];
+      for (int j = lane; j < s.nc; j += 32) sqx[j] = wC(L.ws_dlu, k)[j] - wC(L.ws_dll, k)[j];
+      if (k < N && lane < dm.nx()) sxn[lane] = wX(L.ws_dpi, k)[lane];
+      __syncwarp();
+      if (lane < n) {
+        const int cn = rsq_cn();
+        double acc = 0.0;
+        for (int j = 0; j < n; ++j) {
+          const int a = lane >= j ? lane : j, b = lane >= j ? j : lane;
+          acc += __ldg(rsq + pm_index(a, b, cn)) * sx[j];
+        }
+        double r = acc + wN(L.ws_rg, k)[lane];
+        if (k < N) {
+          const double* ba = gBAbt(k);
+          double a2 = 0.0;
+          for (int j = 0; j < s.nxn; ++j) a2 += __ldg(ba + pm_index(lane, j, babt_cn())) * sxn[j];
+          r += a2;
+        }
+        if (k > 0 && lane >= nu) r -= wX(L.ws_dpi, k - 1)[lane - nu];
+        r += Jtv_row(s, dct, sqx, lane);
+        wN(L.ws_lg, k)[lane] = r;
+        ng_ = amax_nan(ng_, r);
+      }
+      if (k < N && lane < s.nxn) {
+        const double* ba = gBAbt(k);
+        double acc = 0.0;
+        for (int i = 0; i < n; ++i) acc += __ldg(ba + pm_index(i, lane, babt_cn())) * sx[i];
+        const double r = (acc + wX(L.ws_rb, k)[lane]) - wN(L.ws_dz, k + 1)[s.nun + lane];
+        wX(L.ws_lb, k)[lane] = r;
+        nb_ = amax_nan(nb_, r);
+      }
+      for (int j = lane; j < s.nc; j += 32) {
+        const double v = Jz_row(s, dct, sx, j);
+        const double ml = __ldg(mk + j), mu_ = __ldg(mk + nc_m + j);
+        const double dtl = wC(L.ws_dtl, k)[j], dtu = wC(L.ws_dtu, k)[j];
+        const double ldl = ((-v + dtl) + wC(L.ws_rdl, k)[j]) * ml;
+        const double ldu = ((v + dtu) + wC(L.ws_rdu, k)[j]) * mu_;
+        const double lml = ((wC(L.ws_ll, k)[j] * dtl + wC(L.ws_tl, k)[j] * wC(L.ws_dll, k)[j]) + wC(L.ws_rml, k)[j]) * ml;
+        const double lmu = ((wC(L.ws_lu, k)[j] * dtu + wC(L.ws_tu, k)[j] * wC(L.ws_dlu, k)[j]) + wC(L.ws_rmu, k)[j]) * mu_;
+        wC(L.ws_ldl, k)[j] = ldl; wC(L.ws_ldu, k)[j] = ldu; wC(L.ws_lml, k)[j] = lml; wC(L.ws_lmu, k)[j] = lmu;
+        nd_ = amax_nan(amax_nan(nd_, ldl), ldu);
+        nm_ = amax_nan(amax_nan(nm_, lml), lmu);
+      }
+      __syncwarp();
+    }
+    lin[0] = warp_max(ng_ == ng_ ? ng_ : 0.0);
+    lin[1] = warp_max(nb_ == nb_ ? nb_ : 0.0);
+    lin[2] = warp_max(nd_ == nd_ ? nd_ : 0.0);
+    lin[3] = warp_max(nm_ == nm_ ? nm_ : 0.0);
+    const double flag = warp_sum((ng_ != ng_ || nb_ != nb_ || nd_ != nd_ || nm_ != nm_) ? 1.0 : 0.0);
+    if (flag > 0.0) lin[0] = lin[0] + __longlong_as_double(0x7ff8000000000000LL);
+  }
+  // the refinement loop; returns the number of correction solves, lin[] = the last linear residual norms
+  __device__ int refine(int max_it, const double res[4], double lin[4]) {
+    const srbd_ipm_args& a = p.a;
+    const double tol[4] = {a.tol_stat, a.tol_eq, a.tol_ineq, a.tol_comp};
+    const int nc_m = ncm();
+    int done = 0;
+    for (int it = 0; it < max_it; ++it) {
+      residuals_lin(lin);
+      bool ok = true;
+      for (int i = 0; i < 4; ++i) ok = ok && (lin[i] < a.itref_abs * tol[i] || lin[i] < a.itref_rel * res[i]);
+      if (ok) break;
+      rhs = Rhs{L.ws_lg, L.ws_lb, L.ws_ldl, L.ws_ldu, L.ws_lml, L.ws_lmu};
+      backward(false, true, false);
+      forward(L.ws_cz, L.ws_cpi, false);
+      rhs = Rhs{L.ws_rg, L.ws_rb, L.ws_rdl, L.ws_rdu, L.ws_rml, L.ws_rmu};
+      for (int k = 0; k <= N; ++k) {
+        const St s = stage(k);
+        const double* cz = wN(L.ws_cz, k);
+        const double* mk = gMask(k);
+        if (lane < s.n) sx[lane] = cz[lane];
+        __syncwarp();
+        for (int j = lane; j < s.nc; j += 32) {
+          const double v = Jz_row(s, gDCt(k), sx, j);
+          const double ml = __ldg(mk + j), mu_ = __ldg(mk + nc_m + j);
+          const double ctl = (v - wC(L.ws_ldl, k)[j]) * ml;
+          const double ctu = (-v - wC(L.ws_ldu, k)[j]) * mu_;
+          const double cll = (-(wC(L.ws_ll, k)[j] * ctl + wC(L.ws_lml, k)[j]) / wC(L.ws_tl, k)[j]) * ml;
+          const double clu = (-(wC(L.ws_lu, k)[j] * ctu + wC(L.ws_lmu, k)[j]) / wC(L.ws_tu, k)[j]) * mu_;
+          wC(L.ws_dtl, k)[j] += ctl; wC(L.ws_dtu, k)[j] += ctu; wC(L.ws_dll, k)[j] += cll; wC(L.ws_dlu, k)[j] += clu;
+        }
+        if (lane < s.n) wN(L.ws_dz, k)[lane] += cz[lane];
+        if (k < N && lane < dm.nx()) wX(L.ws_dpi, k)[lane] += wX(L.ws_cpi, k)[lane];
+        __syncwarp();
+      }
+      ++done;
+    }
+    return done;
   }
 
   // backup res_m (BACKUP_RES_M)
@@ -1001,6 +1130,12 @@ struct Solver {
         forward(L.ws_dz, L.ws_dpi, false);
         double ap, ad;
         dlam_dt_alpha(ap, ad);
+        double itr[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // itref_pred, itref_corr, lin_res_{stat,eq,ineq,comp}
+        if (a.itref_pred_max > 0) {
+          double lin[4];
+          itr[0] = refine(a.itref_pred_max, res, lin);
+          step_lengths(ap, ad);
+        }
         const double alpha_aff = fmin(ap, ad);
         double row[5] = {alpha_aff, 0.0, 0.0, 0.0, 0.0};
         if (a.pred_corr == 1) {
@@ -1014,6 +1149,10 @@ struct Solver {
           backward(false, true, false);
           forward(L.ws_dz, L.ws_dpi, false);
           dlam_dt_alpha(ap, ad);
+          if (a.itref_corr_max > 0) {
+            itr[1] = refine(a.itref_corr_max, res, itr + 2);
+            step_lengths(ap, ad);
+          }
           if (a.cond_pred_corr == 1) {
             const double muc = mu_aff(fmin(ap, ad), nc_mask);
             if (muc > a.cond_factor * mua) {
@@ -1033,6 +1172,7 @@ struct Solver {
         update(shorten(ap), shorten(ad));
         residuals(res, mu, obj, nc_mask);
         stat_row(kk + 1, 0, row, 5);
+        stat_row(kk + 1, 12, itr, 6);
         stat_row(kk + 1, 5, &mu, 1);
         stat_row(kk + 1, 6, res, 4);
         stat_row(kk + 1, 10, &obj, 1);

@@ -48,6 +48,8 @@ struct QpLayout {
   int ws_dz, ws_dpi, ws_dll, ws_dlu, ws_dtl, ws_dtu;
   int ws_rg, ws_rb, ws_rdl, ws_rdu, ws_rml, ws_rmu, ws_rmlb, ws_rmub;
   int ws_Li, ws_Ls, ws_lv, ws_P, ws_p, ws_Lr;
+  // iterative refinement (ipm_solve.cuh: refine): residual of the linear system and the correction
+  int ws_lg, ws_lb, ws_ldl, ws_ldu, ws_lml, ws_lmu, ws_cz, ws_cpi;
   int ws_size;
 };
 
@@ -94,6 +96,8 @@ inline int make_layout(const srbd_qp_dims& d, const int* idxbx, const int* idxbu
   L.ws_rmlb = take(L.ncm); L.ws_rmub = take(L.ncm);
   L.ws_Li = take(L.nu * L.nu); L.ws_Ls = take(L.nx * L.nu); L.ws_lv = take(L.nu);
   L.ws_P = take(L.nx * L.nx); L.ws_p = take(L.nx); L.ws_Lr = take(L.nu * L.nu);
+  L.ws_lg = take(L.nm); L.ws_lb = take(L.nx); L.ws_ldl = take(L.ncm); L.ws_ldu = take(L.ncm);
+  L.ws_lml = take(L.ncm); L.ws_lmu = take(L.ncm); L.ws_cz = take(L.nm); L.ws_cpi = take(L.nx);
   L.ws_size = (o + 15) & ~15;
   *out = L;
   return 0;

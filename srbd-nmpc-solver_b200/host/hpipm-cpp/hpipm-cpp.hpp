@@ -12,6 +12,7 @@
 #include <iomanip>
 #include <iostream>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -180,6 +181,61 @@ inline std::string to_string(const HpipmStatus& s) {
 }
 inline std::ostream& operator<<(std::ostream& os, const HpipmStatus& s) { return os << to_string(s); }
 
+namespace detail {
+// Process-wide pool of B200 contexts (device buffers, stream, pinned staging arena), keyed by (device, batch, dims).
+// The reference constructs a NEW OcpQpIpmSolver in every SQP iteration (NMPC_solver.cpp:319) and its wrappers malloc
+// their workspaces each time (detail/d_ocp_qp_ipm_ws_wrapper.cpp:141-155); here a solver object borrows a context from
+// the pool and gives it back in its destructor, so nothing is allocated after the first solver of a shape.
+struct PooledContext {
+  srbd_ctx* ctx = nullptr;
+  int device = 0, batch = 0;
+  srbd_qp_dims dims{};
+  double* arena = nullptr;      // pinned host staging: [QP fields ... | outputs]
+  size_t arena_doubles = 0;
+};
+class ContextPool {
+ public:
+  static ContextPool& instance() { static ContextPool* p = new ContextPool(); return *p; }  // never destroyed: CUDA may be gone at exit
+  PooledContext acquire(int device, int batch, const srbd_qp_dims& d) {
+    {
+      std::lock_guard<std::mutex> lock(m_);
+      for (size_t i = 0; i < free_.size(); ++i)
+        if (free_[i].device == device && free_[i].batch == batch && std::memcmp(&free_[i].dims, &d, sizeof(d)) == 0) {
+          PooledContext e = free_[i];
+          free_.erase(free_.begin() + static_cast<long>(i));
+          return e;
+        }
+    }
+    PooledContext e;
+    e.device = device; e.batch = batch; e.dims = d;
+    const int rc = srbd_ctx_create(device, batch, &d, nullptr, &e.ctx);
+    if (rc != 0) throw std::runtime_error("srbd_ctx_create failed (" + std::to_string(rc) + "): no usable CUDA device or "
+                                          "dimensions beyond the compiled maxima");
+    ++created_;
+    return e;
+  }
+  void release(PooledContext e) {
+    if (!e.ctx) return;
+    std::lock_guard<std::mutex> lock(m_);
+    free_.push_back(e);
+  }
+  void clear() {  // explicit teardown (tests, long-running hosts that change shapes)
+    std::lock_guard<std::mutex> lock(m_);
+    for (auto& e : free_) { if (e.arena) srbd_host_free(e.arena); srbd_ctx_destroy(e.ctx); }
+    free_.clear();
+  }
+  long created() const { return created_; }
+ private:
+  std::mutex m_;
+  std::vector<PooledContext> free_;
+  long created_ = 0;
+};
+}  // namespace detail
+
+// number of device contexts created so far (tests: a solver per SQP iteration must not create more than one)
+inline long contextsCreated() { return detail::ContextPool::instance().created(); }
+inline void releaseCachedContexts() { detail::ContextPool::instance().clear(); }
+
 class OcpQpIpmSolver {
  public:
   OcpQpIpmSolver(const std::vector<OcpQp>& ocp_qp, const OcpQpIpmSolverSettings& s = OcpQpIpmSolverSettings()) {
@@ -195,16 +251,21 @@ class OcpQpIpmSolver {
     if (this != &o) {
       release();
       solver_settings_ = o.solver_settings_; solver_statistics_ = o.solver_statistics_; dim_ = o.dim_;
-      ctx_ = o.ctx_; ctx_dims_ = o.ctx_dims_; ctx_batch_ = o.ctx_batch_; device_ = o.device_;
-      o.ctx_ = nullptr;
+      pc_ = o.pc_; device_ = o.device_; want_ric_ = o.want_ric_; want_stat_ = o.want_stat_;
+      o.pc_ = detail::PooledContext();
     }
     return *this;
   }
 
   void setSolverSettings(const OcpQpIpmSolverSettings& s) { solver_settings_ = s; }
   void setDevice(int device) { device_ = device; }
+  // NEW.  Which optional outputs solve() produces.  Default (true, true) = the reference: P, p, K, k of every stage and
+  // the per-iteration statistics table.  (false, false) fills x, u, pi[1..N] only (pi[0] is reconstructed from the Riccati
+  // data, ocp_qp_ipm_solver.cpp:349-373) and lets QPs with the structure NMPCSolver::prepareQpStructures produces take the
+  // tensor-core kernel (include/srbd_b200.h: srbd_qp_upload) -- what NMPCSolver::solveQpProblems needs (:322-329).
+  void setOutputs(bool riccati, bool statistics) { want_ric_ = riccati; want_stat_ = statistics; }
 
-  // sizes the (grow-only) device workspace like the reference's wrappers do (detail/d_ocp_qp_ipm_ws_wrapper.cpp:141-155)
+  // sizes the (grow-only, pooled) device workspace like the reference's wrappers do (detail/d_ocp_qp_ipm_ws_wrapper.cpp:141-155)
   void resize(const std::vector<OcpQp>& ocp_qp) {
     dim_.resize(ocp_qp);
     ensureContext(1);
@@ -215,11 +276,12 @@ class OcpQpIpmSolver {
     std::vector<std::vector<OcpQpSolution>*> sols{&qp_sol};
     std::vector<const Eigen::VectorXd*> x0s{&x0};
     std::vector<HpipmStatus> st;
-    solveImpl(x0s, qps, sols, st, /*collect_stats=*/true);
+    solveImpl(x0s, qps, sols, st, nullptr);
     return st[0];
   }
 
-  // NEW: B independent QPs of identical dimensions in one launch; statistics are those of the last QP
+  // NEW: B independent QPs of identical dimensions in one launch.  getSolverStatistics() describes the LAST QP of the
+  // batch; getBatchIterations() / getBatchMaxResiduals() hold iter and the four max residuals of every QP.
   std::vector<HpipmStatus> solveBatch(const std::vector<Eigen::VectorXd>& x0, std::vector<std::vector<OcpQp>>& ocp_qp,
                                       std::vector<std::vector<OcpQpSolution>>& qp_sol) {
     if (x0.size() != ocp_qp.size()) throw std::runtime_error("x0.size() must be " + std::to_string(ocp_qp.size()));
@@ -229,28 +291,63 @@ class OcpQpIpmSolver {
     std::vector<const Eigen::VectorXd*> x0s;
     for (size_t i = 0; i < ocp_qp.size(); ++i) { qps.push_back(&ocp_qp[i]); sols.push_back(&qp_sol[i]); x0s.push_back(&x0[i]); }
     std::vector<HpipmStatus> st;
-    solveImpl(x0s, qps, sols, st, true);
+    solveImpl(x0s, qps, sols, st, nullptr);
     return st;
+  }
+
+  // NEW: the closed MPC loop of examples/example_mpc.cpp:99-119 / test/ocp_qp_ipm_solver.cpp:298-314 for B robots, on the
+  // device (srbd_mpc_run): for t < sim_steps: x0 := x(t); solve(x0, qp, solution) with `solution` passed back in as the
+  // warm start; x(t+1) := A x(t) + B u0 + b.  x0[i] is robot i's initial state, qp_sol[i] its initial guess (when
+  // warm_start = 1) and, on return, the solution of its LAST step.  x_traj[t][i] (t <= sim_steps) / u_traj[t][i] are the
+  // closed-loop states and applied inputs; the returned status matrix is [sim_steps][B].
+  struct ClosedLoopResult {
+    std::vector<std::vector<Eigen::VectorXd>> x_traj, u_traj;
+    std::vector<std::vector<HpipmStatus>> status;
+    std::vector<std::vector<int>> iter;
+  };
+  ClosedLoopResult solveClosedLoop(const std::vector<Eigen::VectorXd>& x0, std::vector<std::vector<OcpQp>>& ocp_qp,
+                                   std::vector<std::vector<OcpQpSolution>>& qp_sol, const Eigen::MatrixXd& A,
+                                   const Eigen::MatrixXd& B, const Eigen::VectorXd& b, int sim_steps) {
+    if (x0.size() != ocp_qp.size()) throw std::runtime_error("x0.size() must be " + std::to_string(ocp_qp.size()));
+    if (qp_sol.size() != ocp_qp.size()) qp_sol.resize(ocp_qp.size());
+    if (sim_steps < 1) throw std::runtime_error("sim_steps must be positive");
+    std::vector<const std::vector<OcpQp>*> qps;
+    std::vector<std::vector<OcpQpSolution>*> sols;
+    std::vector<const Eigen::VectorXd*> x0s;
+    for (size_t i = 0; i < ocp_qp.size(); ++i) { qps.push_back(&ocp_qp[i]); sols.push_back(&qp_sol[i]); x0s.push_back(&x0[i]); }
+    ClosedLoop cl{&A, &B, &b, sim_steps, ClosedLoopResult()};
+    std::vector<HpipmStatus> st;
+    solveImpl(x0s, qps, sols, st, &cl);
+    return cl.out;
   }
 
   const OcpQpIpmSolverSettings& getIpmSolverSettings() const { return solver_settings_; }
   const OcpQpIpmSolverStatistics& getSolverStatistics() const { return solver_statistics_; }
+  const std::vector<int>& getBatchIterations() const { return batch_iter_; }
+  const std::vector<double>& getBatchMaxResiduals() const { return batch_res_; }  // [B][4]: stat, eq, ineq, comp
 
  private:
+  struct ClosedLoop {
+    const Eigen::MatrixXd *A, *B;
+    const Eigen::VectorXd* b;
+    int steps;
+    ClosedLoopResult out;
+  };
   OcpQpIpmSolverSettings solver_settings_;
   OcpQpIpmSolverStatistics solver_statistics_;
   OcpQpDim dim_;
-  srbd_ctx* ctx_ = nullptr;
-  srbd_qp_dims ctx_dims_{};
-  int ctx_batch_ = 0;
+  detail::PooledContext pc_;
   int device_ = 0;
+  bool want_ric_ = true, want_stat_ = true;
+  std::vector<int> batch_iter_;
+  std::vector<double> batch_res_;
 
   void release() {
-    if (ctx_) srbd_ctx_destroy(ctx_);
-    ctx_ = nullptr;
+    detail::ContextPool::instance().release(pc_);
+    pc_ = detail::PooledContext();
   }
   void check(int rc, const char* what) const {
-    if (rc != 0) throw std::runtime_error(std::string(what) + " failed (" + std::to_string(rc) + "): " + srbd_last_error(ctx_));
+    if (rc != 0) throw std::runtime_error(std::string(what) + " failed (" + std::to_string(rc) + "): " + srbd_last_error(pc_.ctx));
   }
   srbd_qp_dims uniformDims() const {
     // the GPU path takes uniform stage dimensions (every reference workload and test has them)
@@ -268,97 +365,43 @@ class OcpQpIpmSolver {
   }
   void ensureContext(int batch) {
     const srbd_qp_dims d = uniformDims();
-    if (ctx_ && std::memcmp(&d, &ctx_dims_, sizeof(d)) == 0 && batch == ctx_batch_) return;
+    if (pc_.ctx && std::memcmp(&d, &pc_.dims, sizeof(d)) == 0 && batch == pc_.batch) return;
     release();
-    const int rc = srbd_ctx_create(device_, batch, &d, nullptr, &ctx_);
-    if (rc != 0) throw std::runtime_error("srbd_ctx_create failed (" + std::to_string(rc) + "): no usable CUDA device or "
-                                          "dimensions beyond the compiled maxima");
-    ctx_dims_ = d;
-    ctx_batch_ = batch;
+    pc_ = detail::ContextPool::instance().acquire(device_, batch, d);
+  }
+  double* arena(size_t doubles) {  // pinned, grow-only, owned by the pooled context
+    if (doubles > pc_.arena_doubles) {
+      if (pc_.arena) srbd_host_free(pc_.arena);
+      pc_.arena = nullptr; pc_.arena_doubles = 0;
+      void* p = nullptr;
+      if (srbd_host_alloc(doubles * sizeof(double), &p) != 0) throw std::runtime_error("srbd_host_alloc failed");
+      pc_.arena = static_cast<double*>(p);
+      pc_.arena_doubles = doubles;
+    }
+    return pc_.arena;
   }
 
   void solveImpl(const std::vector<const Eigen::VectorXd*>& x0s, const std::vector<const std::vector<OcpQp>*>& qps,
-                 const std::vector<std::vector<OcpQpSolution>*>& sols, std::vector<HpipmStatus>& status, bool collect_stats) {
+                 const std::vector<std::vector<OcpQpSolution>*>& sols, std::vector<HpipmStatus>& status, ClosedLoop* loop) {
     solver_settings_.checkSettings();
     const int B = static_cast<int>(qps.size());
     dim_.resize(*qps[0]);  // resize(ocp_qp) on every call like the reference (ocp_qp_ipm_solver.cpp:185)
     for (int b = 1; b < B; ++b) { OcpQpDim chk(*qps[b]); (void)chk; }
     ensureContext(B);
-    const srbd_qp_dims d = ctx_dims_;
-    const size_t N = d.N, nx = d.nx, nu = d.nu, nbx = d.nbx, nbu = d.nbu, ng = d.ng, ngN = d.ngN;
+    srbd_ctx* ctx = pc_.ctx;
+    const srbd_qp_dims d = pc_.dims;
+    const size_t N = d.N, nx = d.nx, nu = d.nu, nbx = d.nbx, nbu = d.nbu, ng = d.ng, ngN = d.ngN, Bz = static_cast<size_t>(B);
+    const bool warm = solver_settings_.warm_start != 0;
     // warm start needs pre-sized solutions (ocp_qp_ipm_solver.cpp:189-208)
     for (int b = 0; b < B; ++b) {
       auto& s = *sols[b];
       if (s.size() != N + 1) s.resize(N + 1);
-      for (size_t i = 0; i <= N; ++i) {
-        if (solver_settings_.warm_start) {
+      if (warm)
+        for (size_t i = 0; i <= N; ++i) {
           if (static_cast<size_t>(s[i].x.size()) != nx) throw std::runtime_error("qp_sol[" + std::to_string(i) + "].x.size() must be " + std::to_string(nx));
           if (i < N && static_cast<size_t>(s[i].u.size()) != nu) throw std::runtime_error("qp_sol[" + std::to_string(i) + "].u.size() must be " + std::to_string(nu));
         }
-      }
-    }
-    // flatten into the batch-contiguous column-major layout of srbd_qp_host
-    auto cat = [&](size_t per, auto getter, size_t stages, size_t first = 0) {
-      std::vector<double> v(static_cast<size_t>(B) * stages * per, 0.0);
-      for (int b = 0; b < B; ++b)
-        for (size_t i = first; i < stages; ++i) {
-          const double* src = getter((*qps[b])[i]);
-          if (src && per) std::memcpy(v.data() + (static_cast<size_t>(b) * stages + i) * per, src, per * sizeof(double));
-        }
-      return v;
-    };
-    auto A = cat(nx * nx, [](const OcpQp& q) { return q.A.data(); }, N);
-    auto Bm = cat(nx * nu, [](const OcpQp& q) { return q.B.data(); }, N);
-    auto bv = cat(nx, [](const OcpQp& q) { return q.b.data(); }, N);
-    auto Q = cat(nx * nx, [](const OcpQp& q) { return q.Q.data(); }, N + 1);
-    auto S = cat(nu * nx, [](const OcpQp& q) { return q.S.data(); }, N);
-    auto R = cat(nu * nu, [](const OcpQp& q) { return q.R.data(); }, N);
-    auto qv = cat(nx, [](const OcpQp& q) { return q.q.data(); }, N + 1);
-    auto rv = cat(nu, [](const OcpQp& q) { return q.r.data(); }, N);
-    // (stage 0 is skipped: nbx[0] := 0 in the solver, and uniformDims() lets nbx[0] differ from nbx)
-    auto lbx = cat(nbx, [&](const OcpQp& q) { return q.lbx.size() ? q.lbx.data() : nullptr; }, N + 1, 1);
-    auto ubx = cat(nbx, [&](const OcpQp& q) { return q.ubx.size() ? q.ubx.data() : nullptr; }, N + 1, 1);
-    auto lbu = cat(nbu, [](const OcpQp& q) { return q.lbu.data(); }, N);
-    auto ubu = cat(nbu, [](const OcpQp& q) { return q.ubu.data(); }, N);
-    auto C = cat(ng * nx, [&](const OcpQp& q) { return q.C.size() ? q.C.data() : nullptr; }, N);
-    auto D = cat(ng * nu, [](const OcpQp& q) { return q.D.data(); }, N);
-    auto lg = cat(ng, [](const OcpQp& q) { return q.lg.data(); }, N);
-    auto ug = cat(ng, [](const OcpQp& q) { return q.ug.data(); }, N);
-    // masks apply only when their size matches (ocp_qp_ipm_solver.cpp:292-321); default is "all ones"
-    auto mask = [&](size_t per, auto vec, size_t stages, size_t first) {
-      std::vector<double> v(static_cast<size_t>(B) * stages * per, 1.0);
-      for (int b = 0; b < B; ++b)
-        for (size_t i = first; i < stages; ++i) {
-          const Eigen::VectorXd& m = vec((*qps[b])[i]);
-          if (per && static_cast<size_t>(m.size()) == per)
-            std::memcpy(v.data() + (static_cast<size_t>(b) * stages + i) * per, m.data(), per * sizeof(double));
-        }
-      return v;
-    };
-    auto lbxm = mask(nbx, [](const OcpQp& q) -> const Eigen::VectorXd& { return q.lbx_mask; }, N + 1, 1);
-    auto ubxm = mask(nbx, [](const OcpQp& q) -> const Eigen::VectorXd& { return q.ubx_mask; }, N + 1, 1);
-    auto lbum = mask(nbu, [](const OcpQp& q) -> const Eigen::VectorXd& { return q.lbu_mask; }, N, 0);
-    auto ubum = mask(nbu, [](const OcpQp& q) -> const Eigen::VectorXd& { return q.ubu_mask; }, N, 0);
-    auto lgm = mask(ng, [](const OcpQp& q) -> const Eigen::VectorXd& { return q.lg_mask; }, N, 0);
-    auto ugm = mask(ng, [](const OcpQp& q) -> const Eigen::VectorXd& { return q.ug_mask; }, N, 0);
-    std::vector<double> CN(B * ngN * nx), lgN(B * ngN), ugN(B * ngN), lgNm(B * ngN, 1.0), ugNm(B * ngN, 1.0), x0v(B * nx);
-    std::vector<double> xin(B * (N + 1) * nx, 0.0), uin(B * N * nu, 0.0);
-    for (int b = 0; b < B; ++b) {
-      const OcpQp& qN = (*qps[b])[N];
-      if (ngN) {
-        std::memcpy(CN.data() + b * ngN * nx, qN.C.data(), ngN * nx * sizeof(double));
-        std::memcpy(lgN.data() + b * ngN, qN.lg.data(), ngN * sizeof(double));
-        std::memcpy(ugN.data() + b * ngN, qN.ug.data(), ngN * sizeof(double));
-        if (static_cast<size_t>(qN.lg_mask.size()) == ngN) std::memcpy(lgNm.data() + b * ngN, qN.lg_mask.data(), ngN * sizeof(double));
-        if (static_cast<size_t>(qN.ug_mask.size()) == ngN) std::memcpy(ugNm.data() + b * ngN, qN.ug_mask.data(), ngN * sizeof(double));
-      }
       if (static_cast<size_t>(x0s[b]->size()) != nx) throw std::runtime_error("x0.size() must be " + std::to_string(nx));
-      std::memcpy(x0v.data() + b * nx, x0s[b]->data(), nx * sizeof(double));
-      if (solver_settings_.warm_start)
-        for (size_t i = 0; i <= N; ++i) {
-          std::memcpy(xin.data() + (b * (N + 1) + i) * nx, (*sols[b])[i].x.data(), nx * sizeof(double));
-          if (i < N) std::memcpy(uin.data() + (b * N + i) * nu, (*sols[b])[i].u.data(), nu * sizeof(double));
-        }
     }
     // The C-ABI takes ONE index set for idxbx (stages 1..N) and one for idxbu (stages 0..N-1), shared by the batch;
     // the reference passes them per stage (ocp_qp_ipm_solver.cpp:263-272).  Differing sets would silently put the
@@ -373,66 +416,178 @@ class OcpQpIpmSolver {
           throw std::runtime_error("ocp_qp[" + std::to_string(i) + "].idxbu differs between stages / batch entries: the "
                                    "B200 path needs one idxbu for stages 0..N-1");
       }
+    // ---- staging arena: every QP field batch-contiguous and column-major (srbd_qp_host), one after the other, then the
+    // outputs in the device's own layout: ONE H2D copy up, ONE D2H copy down -------------------------------------------
+    size_t out_off[8], out_total = 0;
+    check(srbd_out_layout(ctx, out_off, &out_total), "srbd_out_layout");
+    const size_t in_sizes[30] = {Bz * N * nx * nx, Bz * N * nx * nu, Bz * N * nx, Bz * (N + 1) * nx * nx, Bz * N * nu * nx,
+                                 Bz * N * nu * nu, Bz * (N + 1) * nx, Bz * N * nu,
+                                 Bz * (N + 1) * nbx, Bz * (N + 1) * nbx, Bz * (N + 1) * nbx, Bz * (N + 1) * nbx,
+                                 Bz * N * nbu, Bz * N * nbu, Bz * N * nbu, Bz * N * nbu,
+                                 Bz * N * ng * nx, Bz * N * ng * nu, Bz * N * ng, Bz * N * ng, Bz * N * ng, Bz * N * ng,
+                                 Bz * ngN * nx, Bz * ngN, Bz * ngN, Bz * ngN, Bz * ngN, Bz * nx,
+                                 warm ? Bz * (N + 1) * nx : 0, warm ? Bz * N * nu : 0};
+    size_t in_off[31];
+    in_off[0] = 0;
+    for (int i = 0; i < 30; ++i) in_off[i + 1] = in_off[i] + in_sizes[i];
+    const size_t in_total = in_off[30];
+    double* ar = arena(in_total + out_total);
+    double* out = ar + in_total;
+    enum { fA, fB, fb, fQ, fS, fR, fq, fr, flbx, fubx, flbxm, fubxm, flbu, fubu, flbum, fubum, fC, fD, flg, fug, flgm, fugm,
+           fCN, flgN, fugN, flgNm, fugNm, fx0, fxin, fuin };
+    auto put = [&](int f, size_t b, size_t stages, size_t i, size_t per, const double* src) {
+      if (per) std::memcpy(ar + in_off[f] + (b * stages + i) * per, src, per * sizeof(double));
+    };
+    auto fill = [&](int f, size_t b, size_t stages, size_t i, size_t per, double v) {
+      double* dst = ar + in_off[f] + (b * stages + i) * per;
+      for (size_t e = 0; e < per; ++e) dst[e] = v;
+    };
+    // masks apply only when their size matches (ocp_qp_ipm_solver.cpp:292-321); default is "all ones"
+    auto mask = [&](int f, size_t b, size_t stages, size_t i, size_t per, const Eigen::VectorXd& m) {
+      if (static_cast<size_t>(m.size()) == per) put(f, b, stages, i, per, m.data());
+      else fill(f, b, stages, i, per, 1.0);
+    };
+    for (size_t b = 0; b < Bz; ++b) {
+      const std::vector<OcpQp>& qp = *qps[b];
+      for (size_t i = 0; i <= N; ++i) {
+        const OcpQp& s = qp[i];
+        put(fQ, b, N + 1, i, nx * nx, s.Q.data());
+        put(fq, b, N + 1, i, nx, s.q.data());
+        // (stage 0 is skipped: nbx[0] := 0 in the solver, and uniformDims() lets nbx[0] differ from nbx)
+        if (i >= 1) {
+          put(flbx, b, N + 1, i, nbx, s.lbx.data()); put(fubx, b, N + 1, i, nbx, s.ubx.data());
+          mask(flbxm, b, N + 1, i, nbx, s.lbx_mask); mask(fubxm, b, N + 1, i, nbx, s.ubx_mask);
+        } else {
+          fill(flbx, b, N + 1, i, nbx, 0.0); fill(fubx, b, N + 1, i, nbx, 0.0);
+          fill(flbxm, b, N + 1, i, nbx, 1.0); fill(fubxm, b, N + 1, i, nbx, 1.0);
+        }
+        if (i == N) break;
+        put(fA, b, N, i, nx * nx, s.A.data()); put(fB, b, N, i, nx * nu, s.B.data()); put(fb, b, N, i, nx, s.b.data());
+        put(fS, b, N, i, nu * nx, s.S.data()); put(fR, b, N, i, nu * nu, s.R.data()); put(fr, b, N, i, nu, s.r.data());
+        put(flbu, b, N, i, nbu, s.lbu.data()); put(fubu, b, N, i, nbu, s.ubu.data());
+        mask(flbum, b, N, i, nbu, s.lbu_mask); mask(fubum, b, N, i, nbu, s.ubu_mask);
+        if (ng) {
+          if (s.C.size()) put(fC, b, N, i, ng * nx, s.C.data()); else fill(fC, b, N, i, ng * nx, 0.0);
+          put(fD, b, N, i, ng * nu, s.D.data());
+          put(flg, b, N, i, ng, s.lg.data()); put(fug, b, N, i, ng, s.ug.data());
+          mask(flgm, b, N, i, ng, s.lg_mask); mask(fugm, b, N, i, ng, s.ug_mask);
+        }
+      }
+      const OcpQp& qN = qp[N];
+      if (ngN) {
+        put(fCN, b, 1, 0, ngN * nx, qN.C.data()); put(flgN, b, 1, 0, ngN, qN.lg.data()); put(fugN, b, 1, 0, ngN, qN.ug.data());
+        mask(flgNm, b, 1, 0, ngN, qN.lg_mask); mask(fugNm, b, 1, 0, ngN, qN.ug_mask);
+      }
+      put(fx0, b, 1, 0, nx, x0s[b]->data());
+      if (warm)
+        for (size_t i = 0; i <= N; ++i) {
+          put(fxin, b, N + 1, i, nx, (*sols[b])[i].x.data());
+          if (i < N) put(fuin, b, N, i, nu, (*sols[b])[i].u.data());
+        }
+    }
+    auto at = [&](int f) -> const double* { return in_sizes[f] ? ar + in_off[f] : nullptr; };
     srbd_qp_host h{};
-    h.A = A.data(); h.Bm = Bm.data(); h.b = bv.data(); h.Q = Q.data(); h.S = S.data(); h.R = R.data(); h.q = qv.data(); h.r = rv.data();
-    h.idxbx = nbx ? (*qps[0])[N].idxbx.data() : nullptr; h.lbx = lbx.data(); h.ubx = ubx.data(); h.lbx_mask = lbxm.data(); h.ubx_mask = ubxm.data();
-    h.idxbu = nbu ? (*qps[0])[0].idxbu.data() : nullptr; h.lbu = lbu.data(); h.ubu = ubu.data(); h.lbu_mask = lbum.data(); h.ubu_mask = ubum.data();
-    h.C = C.data(); h.D = D.data(); h.lg = lg.data(); h.ug = ug.data(); h.lg_mask = lgm.data(); h.ug_mask = ugm.data();
-    h.CN = CN.data(); h.lgN = lgN.data(); h.ugN = ugN.data(); h.lgN_mask = lgNm.data(); h.ugN_mask = ugNm.data();
-    h.x0 = x0v.data();
-    if (solver_settings_.warm_start) { h.x_init = xin.data(); h.u_init = uin.data(); }
+    h.A = at(fA); h.Bm = at(fB); h.b = at(fb); h.Q = at(fQ); h.S = at(fS); h.R = at(fR); h.q = at(fq); h.r = at(fr);
+    h.idxbx = nbx ? (*qps[0])[N].idxbx.data() : nullptr; h.lbx = at(flbx); h.ubx = at(fubx); h.lbx_mask = at(flbxm); h.ubx_mask = at(fubxm);
+    h.idxbu = nbu ? (*qps[0])[0].idxbu.data() : nullptr; h.lbu = at(flbu); h.ubu = at(fubu); h.lbu_mask = at(flbum); h.ubu_mask = at(fubum);
+    h.C = at(fC); h.D = at(fD); h.lg = at(flg); h.ug = at(fug); h.lg_mask = at(flgm); h.ug_mask = at(fugm);
+    h.CN = at(fCN); h.lgN = at(flgN); h.ugN = at(fugN); h.lgN_mask = at(flgNm); h.ugN_mask = at(fugNm);
+    h.x0 = at(fx0);
+    if (warm) { h.x_init = at(fxin); h.u_init = at(fuin); }
 
     srbd_ipm_args a;
     srbd_ipm_args_default(&a);
+    srbd_ipm_args_set_mode(&a, static_cast<int>(solver_settings_.mode));  // d_ocp_qp_ipm_arg_set_default(mode), :103
     a.iter_max = solver_settings_.iter_max; a.alpha_min = solver_settings_.alpha_min; a.mu0 = solver_settings_.mu0;
     a.tol_stat = solver_settings_.tol_stat; a.tol_eq = solver_settings_.tol_eq; a.tol_ineq = solver_settings_.tol_ineq;
     a.tol_comp = solver_settings_.tol_comp; a.reg_prim = solver_settings_.reg_prim; a.warm_start = solver_settings_.warm_start;
     a.pred_corr = solver_settings_.pred_corr; a.ric_alg = solver_settings_.ric_alg; a.split_step = solver_settings_.split_step;
-    check(srbd_set_ipm_args(ctx_, &a), "srbd_set_ipm_args");
-    check(srbd_set_outputs(ctx_, 1, collect_stats ? 1 : 0), "srbd_set_outputs");
-    check(srbd_qp_upload(ctx_, &h), "srbd_qp_upload");
-    check(srbd_qp_solve(ctx_), "srbd_qp_solve");
-
-    std::vector<double> x(B * (N + 1) * nx), u(B * N * nu), pi(B * (N + 1) * nx), P(B * (N + 1) * nx * nx), p(B * (N + 1) * nx),
-        K(B * N * nu * nx), k(B * N * nu);
-    srbd_sol_host so{};
-    so.x = x.data(); so.u = u.data(); so.pi = pi.data(); so.P = P.data(); so.p = p.data(); so.K = K.data(); so.k = k.data();
-    check(srbd_download_solution(ctx_, &so), "srbd_download_solution");
-    const int rows = srbd_ctx_stat_rows(ctx_);
-    std::vector<int> it(B), st(B);
-    std::vector<double> rm(B * 4), tab(static_cast<size_t>(B) * rows * SRBD_STAT_M);
-    srbd_stats_host sh{};
-    sh.iter = it.data(); sh.status = st.data(); sh.res_max = rm.data(); sh.stat = collect_stats ? tab.data() : nullptr;
-    check(srbd_download_stats(ctx_, &sh), "srbd_download_stats");
-
+    check(srbd_set_ipm_args(ctx, &a), "srbd_set_ipm_args");
+    const bool ric = want_ric_, stat = want_stat_ && !loop;
+    check(srbd_set_outputs(ctx, ric ? 1 : 0, stat ? 1 : 0), "srbd_set_outputs");
+    check(srbd_qp_upload(ctx, &h), "srbd_qp_upload");
+    if (loop) {
+      const int steps = loop->steps;
+      if (static_cast<size_t>(loop->A->rows()) != nx || static_cast<size_t>(loop->A->cols()) != nx ||
+          static_cast<size_t>(loop->B->rows()) != nx || static_cast<size_t>(loop->B->cols()) != nu ||
+          static_cast<size_t>(loop->b->size()) != nx)
+        throw std::runtime_error("solveClosedLoop: the plant must be A (nx x nx), B (nx x nu), b (nx)");
+      std::vector<double> xs(Bz * nx), xt((steps + 1) * Bz * nx), ut(steps * Bz * nu);
+      std::vector<int> it(steps * Bz), st(steps * Bz);
+      for (size_t b = 0; b < Bz; ++b) std::memcpy(xs.data() + b * nx, x0s[b]->data(), nx * sizeof(double));
+      check(srbd_mpc_run(ctx, loop->A->data(), loop->B->data(), loop->b->data(), 1, xs.data(), steps, xt.data(), ut.data(),
+                         it.data(), st.data()), "srbd_mpc_run");
+      auto& o = loop->out;
+      o.x_traj.assign(steps + 1, std::vector<Eigen::VectorXd>(Bz, Eigen::VectorXd(static_cast<int>(nx))));
+      o.u_traj.assign(steps, std::vector<Eigen::VectorXd>(Bz, Eigen::VectorXd(static_cast<int>(nu))));
+      o.status.assign(steps, std::vector<HpipmStatus>(Bz));
+      o.iter.assign(steps, std::vector<int>(Bz));
+      for (int t = 0; t <= steps; ++t)
+        for (size_t b = 0; b < Bz; ++b) {
+          std::memcpy(o.x_traj[t][b].data(), xt.data() + (t * Bz + b) * nx, nx * sizeof(double));
+          if (t == steps) continue;
+          std::memcpy(o.u_traj[t][b].data(), ut.data() + (t * Bz + b) * nu, nu * sizeof(double));
+          const int sv = st[t * Bz + b];
+          o.status[t][b] = (sv >= 0 && sv <= 3) ? static_cast<HpipmStatus>(sv) : HpipmStatus::UnknownFailure;
+          o.iter[t][b] = it[t * Bz + b];
+        }
+    } else {
+      check(srbd_qp_solve(ctx), "srbd_qp_solve");
+    }
+    check(srbd_download_packed(ctx, out, 0), "srbd_download_packed");
+    const double *x = out + out_off[0], *u = out + out_off[1], *pi = out + out_off[2], *rm = out + out_off[3];
+    const int* it = reinterpret_cast<const int*>(out + out_off[4]);
+    const int* st = reinterpret_cast<const int*>(out + out_off[5]);
+    std::vector<double> P, p, K, k, tab;
+    if (ric) {
+      P.resize(Bz * (N + 1) * nx * nx); p.resize(Bz * (N + 1) * nx); K.resize(Bz * N * nu * nx); k.resize(Bz * N * nu);
+      srbd_sol_host so{};
+      so.P = P.data(); so.p = p.data(); so.K = K.data(); so.k = k.data();
+      check(srbd_download_solution(ctx, &so), "srbd_download_solution");
+    }
+    const int rows = srbd_ctx_stat_rows(ctx);
+    if (stat) {
+      tab.resize(Bz * rows * SRBD_STAT_M);
+      srbd_stats_host sh{};
+      sh.stat = tab.data();
+      check(srbd_download_stats(ctx, &sh), "srbd_download_stats");
+    }
     status.resize(B);
-    for (int b = 0; b < B; ++b) {
+    batch_iter_.assign(it, it + B);
+    batch_res_.assign(rm, rm + 4 * Bz);
+    for (size_t b = 0; b < Bz; ++b) {
       auto& s = *sols[b];
       for (size_t i = 0; i <= N; ++i) {
-        s[i].x.resize(nx); s[i].pi.resize(nx); s[i].P.resize(nx, nx); s[i].p.resize(nx);
-        std::memcpy(s[i].x.data(), x.data() + (b * (N + 1) + i) * nx, nx * sizeof(double));
-        std::memcpy(s[i].pi.data(), pi.data() + (b * (N + 1) + i) * nx, nx * sizeof(double));
-        std::memcpy(s[i].P.data(), P.data() + (b * (N + 1) + i) * nx * nx, nx * nx * sizeof(double));
-        std::memcpy(s[i].p.data(), p.data() + (b * (N + 1) + i) * nx, nx * sizeof(double));
+        s[i].x.resize(nx); s[i].pi.resize(nx);
+        std::memcpy(s[i].x.data(), x + (b * (N + 1) + i) * nx, nx * sizeof(double));
+        std::memcpy(s[i].pi.data(), pi + (b * (N + 1) + i) * nx, nx * sizeof(double));
+        if (ric) {
+          s[i].P.resize(nx, nx); s[i].p.resize(nx);
+          std::memcpy(s[i].P.data(), P.data() + (b * (N + 1) + i) * nx * nx, nx * nx * sizeof(double));
+          std::memcpy(s[i].p.data(), p.data() + (b * (N + 1) + i) * nx, nx * sizeof(double));
+        }
         if (i < N) {
-          s[i].u.resize(nu); s[i].K.resize(nu, nx); s[i].k.resize(nu);
-          std::memcpy(s[i].u.data(), u.data() + (b * N + i) * nu, nu * sizeof(double));
-          std::memcpy(s[i].K.data(), K.data() + (b * N + i) * nu * nx, nu * nx * sizeof(double));
-          std::memcpy(s[i].k.data(), k.data() + (b * N + i) * nu, nu * sizeof(double));
+          s[i].u.resize(nu);
+          std::memcpy(s[i].u.data(), u + (b * N + i) * nu, nu * sizeof(double));
+          if (ric) {
+            s[i].K.resize(nu, nx); s[i].k.resize(nu);
+            std::memcpy(s[i].K.data(), K.data() + (b * N + i) * nu * nx, nu * nx * sizeof(double));
+            std::memcpy(s[i].k.data(), k.data() + (b * N + i) * nu, nu * sizeof(double));
+          }
         }
       }
       status[b] = (st[b] >= 0 && st[b] <= 3) ? static_cast<HpipmStatus>(st[b]) : HpipmStatus::UnknownFailure;
     }
     // statistics of the (last) QP: iter, 4 max residuals, rows 0..iter+1 of the 18-column table (:376-403)
-    const int b = B - 1;
-    solver_statistics_.iter = it[b];
-    solver_statistics_.max_res_stat = rm[4 * b + 0]; solver_statistics_.max_res_eq = rm[4 * b + 1];
-    solver_statistics_.max_res_ineq = rm[4 * b + 2]; solver_statistics_.max_res_comp = rm[4 * b + 3];
+    const size_t bl = Bz - 1;
+    solver_statistics_.iter = it[bl];
+    solver_statistics_.max_res_stat = rm[4 * bl + 0]; solver_statistics_.max_res_eq = rm[4 * bl + 1];
+    solver_statistics_.max_res_ineq = rm[4 * bl + 2]; solver_statistics_.max_res_comp = rm[4 * bl + 3];
     solver_statistics_.clear();
-    if (collect_stats) {
+    if (stat) {
       auto cols = solver_statistics_.columns();
-      for (int i = 0; i <= it[b] + 1 && i < rows; ++i)
-        for (int c = 0; c < SRBD_STAT_M; ++c) cols[c]->push_back(tab[(static_cast<size_t>(b) * rows + i) * SRBD_STAT_M + c]);
+      for (int i = 0; i <= it[bl] + 1 && i < rows; ++i)
+        for (int c = 0; c < SRBD_STAT_M; ++c) cols[c]->push_back(tab[(bl * rows + i) * SRBD_STAT_M + c]);
     }
   }
 };

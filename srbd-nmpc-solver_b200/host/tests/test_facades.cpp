@@ -148,8 +148,8 @@ static void test_constrained() {
   std::printf("constrained: done (%d iterations)\n", solver.getSolverStatistics().iter);
 }
 
-static void test_compare_results(const std::string& golden) {
-  const int N = 10;
+// the quadcopter MPC problem of hpipm-cpp/test/ocp_qp_ipm_solver.cpp:170-283 (= examples/example_mpc.cpp:16-96)
+static std::vector<hpipm::OcpQp> quadcopterQp(int N) {
   std::vector<hpipm::OcpQp> qp(N + 1);
   const double Ad[12][12] = {
       {1., 0., 0., 0., 0., 0., 0.1, 0., 0., 0., 0., 0.}, {0., 1., 0., 0., 0., 0., 0., 0.1, 0., 0., 0., 0.},
@@ -185,6 +185,14 @@ static void test_compare_results(const std::string& golden) {
       qp[i].lbu.fill(9.6 - u0); qp[i].ubu.fill(13.0 - u0);
     }
   }
+  return qp;
+}
+
+static void test_compare_results(const std::string& golden) {
+  const int N = 10;
+  std::vector<hpipm::OcpQp> qp = quadcopterQp(N);
+  const MatrixXd A = qp[0].A, B = qp[0].B;
+  const double u0 = 10.5916;
   hpipm::OcpQpIpmSolverSettings s;
   s.mode = hpipm::HpipmMode::Balance; s.iter_max = 30; s.alpha_min = 1e-8; s.mu0 = 1e2;
   s.tol_stat = s.tol_eq = s.tol_ineq = s.tol_comp = 1e-10;
@@ -208,6 +216,107 @@ static void test_compare_results(const std::string& golden) {
     x = xn;
   }
   std::printf("compareResults: done\n");
+}
+
+// NEW (extensions of the facade): the closed loop of compareResults on the device for several robots, and the pooled
+// contexts behind "a new solver object per SQP iteration" (NMPC_solver.cpp:319)
+static void test_closed_loop_and_pool(const std::string& golden) {
+  const int N = 10, B = 3, steps = 15;
+  std::vector<hpipm::OcpQp> qp1 = quadcopterQp(N);
+  MatrixXd A = qp1[0].A, Bm = qp1[0].B;
+  hpipm::OcpQpIpmSolverSettings s;
+  s.mode = hpipm::HpipmMode::Balance; s.iter_max = 30; s.alpha_min = 1e-8; s.mu0 = 1e2;
+  s.tol_stat = s.tol_eq = s.tol_ineq = s.tol_comp = 1e-10;
+  s.reg_prim = 1e-12; s.warm_start = 1; s.pred_corr = 1; s.ric_alg = 0; s.split_step = 1;
+  const double u0 = 10.5916;
+  std::vector<std::vector<hpipm::OcpQp>> qps(B, qp1);
+  std::vector<std::vector<hpipm::OcpQpSolution>> sols(B, std::vector<hpipm::OcpQpSolution>(N + 1));
+  std::vector<VectorXd> x0(B, VectorXd(12));
+  x0[1](0) = 0.2; x0[1](2) = -0.1; x0[2](1) = -0.3; x0[2](8) = 0.1;
+  for (int b = 0; b < B; ++b)
+    for (int i = 0; i <= N; ++i) { sols[b][i].x = x0[b]; if (i < N) { sols[b][i].u = VectorXd(4); sols[b][i].u.fill(u0); } }
+  auto sols_loop = sols;
+  hpipm::OcpQpIpmSolver solver(s);
+  solver.setOutputs(false, false);
+  const auto res = solver.solveClosedLoop(x0, qps, sols, A, Bm, VectorXd(12), steps);
+  CHECK((int)res.x_traj.size() == steps + 1 && (int)res.u_traj.size() == steps);
+  // robot 0 against the golden vectors: x(t) and u0(t) within 1e-9 |sol_t| (the criterion of :310 restricted to them)
+  std::ifstream in(golden);
+  CHECK(in.good());
+  for (int t = 0; t < steps; ++t) {
+    std::vector<double> gold(172);
+    for (double& v : gold) in >> v;
+    double nrm = 0, ex = 0, eu = 0;
+    for (double v : gold) nrm += v * v;
+    for (int k = 0; k < 12; ++k) ex += (res.x_traj[t][0](k) - gold[k]) * (res.x_traj[t][0](k) - gold[k]);
+    for (int k = 0; k < 4; ++k) eu += (res.u_traj[t][0](k) - gold[132 + k]) * (res.u_traj[t][0](k) - gold[132 + k]);
+    CHECK(std::sqrt(ex) <= 1e-9 * std::sqrt(nrm) && std::sqrt(eu) <= 1e-9 * std::sqrt(nrm));
+    for (int b = 0; b < B; ++b) CHECK(res.status[t][b] == hpipm::HpipmStatus::Success);
+  }
+  // every robot against the host-driven loop (one solve() per step and robot, a NEW solver object each time)
+  const long created0 = hpipm::contextsCreated();
+  for (int b = 0; b < B; ++b) {
+    VectorXd x = x0[b];
+    for (int t = 0; t < steps; ++t) {
+      hpipm::OcpQpIpmSolver per_step(qps[b], s);   // what NMPCSolver::solveQpProblems does (NMPC_solver.cpp:319)
+      CHECK(per_step.solve(x, qps[b], sols_loop[b]) == hpipm::HpipmStatus::Success);
+      CHECK(approxV(res.x_traj[t][b], x, 1e-8) || t == 0);
+      CHECK(approxV(res.u_traj[t][b], sols_loop[b][0].u, 1e-7));
+      VectorXd xn(12);
+      for (int i = 0; i < 12; ++i) { double sacc = 0; for (int j = 0; j < 12; ++j) sacc += A(i, j) * x(j); for (int j = 0; j < 4; ++j) sacc += Bm(i, j) * sols_loop[b][0].u(j); xn(i) = sacc; }
+      x = xn;
+    }
+  }
+  // 45 solver objects of one shape: at most one new device context (the pool hands the same one out again)
+  CHECK(hpipm::contextsCreated() - created0 <= 1);
+  std::printf("closed loop + context pool: done (%ld contexts created for %d solver objects)\n",
+              hpipm::contextsCreated() - created0, B * steps);
+}
+
+// NEW: QPs with the structure NMPCSolver::prepareQpStructures produces reach the tensor-core kernel through the
+// reference's own boundary when the optional outputs are switched off; same iterates as the default path within 1e-9
+static void test_srbd_structured_qp_fast_path() {
+  const int N = 20, nx = 12, nu = 12, ng = 24;
+  std::vector<hpipm::OcpQp> qp(N + 1);
+  MatrixXd D(ng, nu);
+  for (int leg = 0; leg < 2; ++leg) {
+    const int r0 = 12 * leg, c0 = 6 * leg;
+    D(r0 + 0, c0 + 0) = -1; D(r0 + 0, c0 + 2) = 0.5; D(r0 + 1, c0 + 1) = -1; D(r0 + 1, c0 + 2) = 0.5;
+    D(r0 + 2, c0 + 0) = 1; D(r0 + 2, c0 + 2) = 0.5; D(r0 + 3, c0 + 1) = 1; D(r0 + 3, c0 + 2) = 0.5;
+    D(r0 + 4, c0 + 2) = -1; D(r0 + 5, c0 + 2) = 1;
+    for (int k = 6; k < 12; ++k) { D(r0 + k, c0 + 2) = 0.05; D(r0 + k, c0 + 3 + (k % 3)) = (k % 2) ? 1.0 : -1.0; }
+  }
+  for (int i = 0; i <= N; ++i) {
+    qp[i].Q = MatrixXd(nx, nx); for (int k = 0; k < nx; ++k) qp[i].Q(k, k) = i < N ? (k == 11 ? 10.0 : 0.0) : 20.0 * (1 + k);
+    qp[i].q = RndV(nx);
+    if (i == N) break;
+    qp[i].A = MatrixXd::Identity(nx, nx); for (int k = 0; k < 6; ++k) qp[i].A(k, 6 + k) = 0.015;
+    qp[i].B = Rnd(nx, nu); for (int r = 0; r < nx; ++r) for (int c = 0; c < nu; ++c) qp[i].B(r, c) *= 0.02;
+    qp[i].b = RndV(nx); for (int k = 0; k < nx; ++k) qp[i].b(k) *= 0.01;
+    qp[i].R = MatrixXd(nu, nu); for (int k = 0; k < nu; ++k) qp[i].R(k, k) = 1e-2;
+    qp[i].S = MatrixXd(nu, nx); qp[i].r = RndV(nu);
+    qp[i].C = MatrixXd(ng, nx); qp[i].D = D;
+    qp[i].lg = VectorXd(ng); for (int k = 0; k < ng; ++k) qp[i].lg(k) = -1.0 - 0.1 * k;
+    qp[i].ug = VectorXd(ng); qp[i].ug_mask = VectorXd(ng);   // upper side masked (zeros)
+    qp[i].lg_mask = VectorXd(ng); qp[i].lg_mask.fill(1.0); qp[i].lg_mask(10) = 0.0; qp[i].lg_mask(23) = 0.0;
+  }
+  const VectorXd x0 = RndV(nx);
+  hpipm::OcpQpIpmSolverSettings s;
+  s.ric_alg = 0; s.iter_max = 40; s.split_step = 1;
+  std::vector<hpipm::OcpQpSolution> full(N + 1), fast(N + 1);
+  hpipm::OcpQpIpmSolver a(qp, s), b(qp, s);
+  CHECK(a.solve(x0, qp, full) == hpipm::HpipmStatus::Success);   // default outputs: generic kernel, P / K / statistics
+  b.setOutputs(false, false);
+  CHECK(b.solve(x0, qp, fast) == hpipm::HpipmStatus::Success);   // tensor-core kernel
+  CHECK(a.getSolverStatistics().iter == b.getSolverStatistics().iter && b.getSolverStatistics().iter > 3);
+  CHECK(full[1].P.rows() == nx && fast[1].P.rows() == 0);
+  bool differ = false;
+  for (int i = 0; i <= N; ++i) {
+    CHECK(approxV(full[i].x, fast[i].x, 1e-9));
+    if (i < N) { CHECK(approxV(full[i].u, fast[i].u, 1e-8)); for (int k = 0; k < nu; ++k) differ = differ || full[i].u(k) != fast[i].u(k); }
+  }
+  CHECK(differ);   // (two different kernels: equal to rounding, not bit for bit)
+  std::printf("SRBD-structured QP through the facade: done (%d iterations on both kernels)\n", b.getSolverStatistics().iter);
 }
 
 static void test_errors() {
@@ -270,6 +379,8 @@ int main(int argc, char** argv) {
     test_unconstrained();
     test_constrained();
     test_compare_results(golden);
+    test_closed_loop_and_pool(golden);
+    test_srbd_structured_qp_fast_path();
     test_srbd_model();
     test_nmpc_solver();
   } catch (const std::exception& e) {

@@ -725,3 +725,61 @@ def test_uploaded_srbd_qps_reach_the_tensor_core_kernel(pkg, orc):
     assert relerr(sol2["x"], ref2["x"]).max() <= TOL
     assert bs2["solves"] == B and bs2["iter_sum"] == int(st2["iter"].sum())
     assert not np.array_equal(sol2["x"][5], sol["x"][5])
+
+
+@pytest.mark.gpu
+def test_iterative_refinement_matches_the_oracle(pkg, orc):
+    """itref_pred_max / itref_corr_max (hpipm_d_ocp_qp_ipm.h:74-75; 0 / 2 in BALANCE, 0 / 4 in ROBUST mode): the generic
+    kernel against the oracle on random constrained QPs -- iteration counts, iterates, and the itref_pred / itref_corr /
+    lin_res_* columns of the statistics table -- and on the four N = 50 all-stance QPs of the round-2 sweep that sit on the
+    rounding floor (e.g. QP 1003144: the double oracle ends min-step after 20 iterations without refinement, the
+    __float128 arbiter converges in 14).  With itref_corr_max = 2 the GPU must end every one of them like the oracle on
+    identical inputs or, where the two differ, like the arbiter (same status, same iteration count).  Whether refinement
+    CURES such a QP depends on the last bits of its data and of the arithmetic (on the oracle's own assembly of these four
+    the oracle converges on all; on the GPU-assembled data the GPU does and the oracle ends two of them min-step): the
+    floor is the double-precision evaluation of the residuals, not the linear solve; the outcome is recorded."""
+    from srbd_nmpc_solver_b200.binding import make_dims
+    B = 16
+    dims_d, arrays = pkg.workload.random_qp(B, N=12, seed=11, a_scale=0.4, nx=5, nu=3, ng=2, nbx=2, nbu=3)
+    dims = make_dims(**dims_d)
+    # (thresholds at 0: every refinement step runs -- on these well-conditioned QPs the default thresholds never ask for one)
+    settings = dict(SETTINGS, iter_max=40, tol_stat=1e-6, itref_pred_max=1, itref_corr_max=2, itref_abs=0.0, itref_rel=0.0)
+    with make_ctx(pkg, B, dims=dims, settings=settings) as ctx:
+        ctx.set_outputs(export_ric=False, export_stat=True)
+        ctx.qp_upload(arrays)
+        ctx.qp_solve()
+        sol = ctx.download_solution(want=("x", "u", "pi", "lam", "t"))
+        st = ctx.download_stats(with_table=True)
+    ref = orc.qp_solve(dims, orc.ipm_args(**settings), arrays, B, stat_rows=42, want=("x", "u", "pi", "lam", "t"))
+    ref_p = orc.qp_solve(dims, orc.ipm_args(**settings), perturb_1ulp(arrays), B, want=("x", "u", "pi", "lam", "t"))
+    ref_q = orc.qp_solve(dims, orc.ipm_args(**settings), arrays, B, want=("x", "u", "pi", "lam", "t"), quad=True)
+    assert (st["status"] == 0).all() and (st["iter"] == ref["iter"]).all()
+    check_iterates(sol, ref, ref_p, ref_q, strict=("x", "u"), label="itref_random")
+    assert ref["stat"][:, :, 12:14].sum() > 0                     # the refinement really ran
+    assert np.array_equal(st["stat"][:, :, 12:14], ref["stat"][:, :, 12:14])
+    # the N = 50 knife-edge QPs through the whole pipeline
+    N, idx = 50, [1003144, 1000673, 1002803, 1000454]
+    ws = [pkg.workload.srbd_batch(1, N=N, contact_mode="stance", start=i) for i in idx]
+    w = {k: np.concatenate([x[k] for x in ws]) for k in ws[0]}
+    s50 = dict(SETTINGS, iter_max=50, tol_stat=1e-6, itref_corr_max=2)
+    with make_ctx(pkg, len(idx), N, settings=s50) as ctx:
+        ctx.upload_traj(w["x"], w["u"], w["xref"], w["x0"], w["contact"])
+        ctx.sqp_iterate(1)
+        st = ctx.download_stats()
+        lin, qp = ctx.download_linearization(), ctx.download_qp()
+    arrays = dict(A=lin["A"], Bm=lin["Bm"], b=lin["b"], Q=qp["Q"], S=qp["S"], R=qp["R"], q=qp["q"], r=qp["r"],
+                  D=qp["D"], lg=qp["lg"], ug=np.zeros_like(qp["lg"]), lg_mask=qp["lg_mask"],
+                  ug_mask=np.zeros_like(qp["lg"]), x0=w["x0"] - w["x"][:, 0])
+    o = orc.qp_solve(make_dims(N=N), orc.ipm_args(**s50), arrays, len(idx), want=("x", "u"))
+    q = orc.qp_solve(make_dims(N=N), orc.ipm_args(**dict(s50, itref_corr_max=0)), arrays, len(idx), want=("x", "u"), quad=True)
+    assert (q["status"] == 0).all()
+    # knife-edge QPs: where GPU and double oracle end differently, the arbiter decides (the GPU must agree with one of them)
+    like_o = (st["status"] == o["status"]) & (st["iter"] == o["iter"])
+    like_q = (st["status"] == q["status"]) & (st["iter"] == q["iter"])
+    assert (like_o | like_q).all(), (st["status"], st["iter"], o["status"], o["iter"], q["iter"])
+    o0 = orc.qp_solve(make_dims(N=N), orc.ipm_args(**dict(s50, itref_corr_max=0)), arrays, len(idx), want=("x", "u"))
+    REPORT["itref_n50_knife_edge"] = {"qps": idx, "arbiter_iter": q["iter"].tolist(),
+                                      "no_refinement": [o0["status"].tolist(), o0["iter"].tolist()],
+                                      "itref_corr_2_oracle": [o["status"].tolist(), o["iter"].tolist()],
+                                      "itref_corr_2_gpu": [st["status"].tolist(), st["iter"].tolist()]}
+    _dump_report()
