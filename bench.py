@@ -196,30 +196,48 @@ def emit_json(line):
 
 def latency_leg(pkg, reps=300):
     """The second half of BASELINE.json's metric ("... ; p50 solve latency"), config 5: ONE SRBD QP, N=50, all stance,
-    HARD_INEQ, solved host memory -> host memory through srbd_solve_host (K1 + K2 + K3 + copies), 10 warm-ups, then
-    `reps` back-to-back calls timed on the host clock (the call is synchronous)."""
+    HARD_INEQ, all four tolerances 1e-8, solved host memory -> host memory, 10 warm-ups, then `reps` back-to-back calls
+    timed on the host clock (the calls are synchronous).  Two forms of the same pipeline (K1 + K2 + K3 + copies):
+    srbd_solve_host_graph (pinned staging in the context, ONE CUDA graph launch per call) and the plain srbd_solve_host
+    (five copies up, five launches, four copies down)."""
     from srbd_nmpc_solver_b200.binding import make_dims
     N = 50
     w = pkg.workload.srbd_batch(1, N=N, contact_mode="stance")
     c = pkg.Context(1, make_dims(N=N))
     c.set_model(pkg.default_model_params(N))
-    c.set_ipm_args(pkg.default_ipm_args(**dict(SETTINGS, tol_stat=1e-6)))
+    c.set_ipm_args(pkg.default_ipm_args(**dict(SETTINGS, iter_max=50)))
     sx, su = np.zeros((1, N + 1, 12)), np.zeros((1, N, 12))
     it, stt = np.zeros(1, dtype=np.int32), np.zeros(1, dtype=np.int32)
     mode = pkg.capi.SRBD_HARD_INEQ
-    for _ in range(10):
-        c.solve_host(mode, w["x"], w["u"], w["xref"], w["x0"], w["contact"], sx, su, it, stt)
-    ts = []
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        c.solve_host(mode, w["x"], w["u"], w["xref"], w["x0"], w["contact"], sx, su, it, stt)
-        ts.append(time.perf_counter() - t0)
+    out = {}
+    for name, fn in (("graph", c.solve_host_graph), ("plain", c.solve_host)):
+        for _ in range(10):
+            fn(mode, w["x"], w["u"], w["xref"], w["x0"], w["contact"], sx, su, it, stt)
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn(mode, w["x"], w["u"], w["xref"], w["x0"], w["contact"], sx, su, it, stt)
+            ts.append(time.perf_counter() - t0)
+        ts = np.array(ts) * 1e6
+        out[name] = (float(np.percentile(ts, 50)), float(np.percentile(ts, 99)), sx.copy())
     c.close()
-    ts = np.array(ts) * 1e6
-    return {"p50_us": float(np.percentile(ts, 50)), "p99_us": float(np.percentile(ts, 99)), "calls": reps,
+    assert np.array_equal(out["graph"][2], out["plain"][2]), "graph replay and plain call disagree"
+    # the CPU oracle on the same problem, one core (the reference calls HPIPM once per control step, NMPC_solver.cpp:316-330)
+    from oracle import oracle as orc
+    m, a = orc.model_params(N), orc.ipm_args(**dict(SETTINGS, iter_max=50))
+    tc = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        o = orc.pipeline(m, a, N, mode, w["x"], w["u"], w["xref"], w["x0"], w["contact"], threads=1, duals=False)
+        tc.append(time.perf_counter() - t0)
+    return {"p50_us": out["graph"][0], "p99_us": out["graph"][1], "calls": reps,
+            "p50_us_plain_call": out["plain"][0], "p99_us_plain_call": out["plain"][1],
+            "cpu_oracle_port_1core_us": float(np.median(tc) * 1e6), "cpu_iterations": int(o["iter"][0]),
             "ipm_iterations": int(it[0]), "status": int(stt[0]),
-            "workload": "BASELINE config 5: one SRBD QP, N=50, all stance, HARD_INEQ, tol_stat=1e-6, "
-                        "tol_eq=tol_ineq=tol_comp=1e-8, host->host through srbd_solve_host on rank 0"}
+            "workload": "BASELINE config 5: one SRBD QP, N=50, all stance, HARD_INEQ, tol_stat=tol_eq=tol_ineq=tol_comp=1e-8, "
+                        "host->host through srbd_solve_host_graph on rank 0",
+            "note": "one QP = one warp: the solve is a serial Riccati chain (51 stages x 12 iterations x 5 sweeps); the "
+                    "GPU path is a throughput design (DESIGN.md section 5, latency)"}
 
 
 def main():

@@ -325,6 +325,13 @@ int srbd_solve_host_async(srbd_ctx* ctx, int mode, const double* x, const double
                           const double* x0, const uint8_t* contact, double* sol_x, double* sol_u,
                           int* iter, int* status);
 int srbd_wait(srbd_ctx* ctx);
+/* The low-latency form of srbd_solve_host (BASELINE config 5: one problem per call, the reference's call site
+ * NMPCSolver::solveQpProblems, NMPC_solver.cpp:316-330): the inputs are staged in pinned memory owned by the context and
+ * the whole pipeline -- H2D copies, K1, K2, K3 (+ its rescue launches), D2H copies -- is replayed as ONE CUDA graph
+ * launch (captured on the first call for a given mode).  Any host buffers; synchronous. */
+int srbd_solve_host_graph(srbd_ctx* ctx, int mode, const double* x, const double* u, const double* xref,
+                          const double* x0, const uint8_t* contact, double* sol_x, double* sol_u,
+                          int* iter, int* status);
 
 /* ---- measurement helpers ----------------------------------------------------------------------*/
 /* FP64-pipe-saturating microbenchmark (DMMA m8n8k4 chains; DMMA and DFMA share one datapath on B200): returns the

@@ -69,39 +69,55 @@ out["config2_b1024_stance"] = dict(gpu_solves_per_s=B / float(np.median(ts)), gp
 c.close()
 
 # ---- config 4: B=4096, N=100, full SQP (K1+K2+K3+K4, <= 15 iterations) ---------------------------------------------
+# Two start distributions: spread = 1.0 is the config-3 generator taken literally (CoM up to 0.28 m beside the feet: over a
+# 1.5 s horizon no admissible wrench holds the body, the SQP linearisation is meaningless after a few stages) and
+# spread = 0.25 a physically sensible one (workload.srbd_batch).  Two step-length policies: "carried" = the reference
+# (alpha_ is a member that is never reset, NMPC_solver.h:104: once halved it stays halved) and "reset" = alpha := 1 at
+# every SQP iteration (srbd_reset_sqp_state).
 B, N = 4096, 100
 S4 = dict(S8, iter_max=50, tol_stat=1e-6)
-w = pkg.workload.srbd_batch(B, N=N, contact_mode="gait")
-c = ctx_for(B, N, S4)
-c.upload_traj(w["x"], w["u"], w["xref"], w["x0"], w["contact"]); c.sqp_iterate(HARD); c.sync()
-c.reset_sqp_state(); c.upload_traj(w["x"], w["u"], w["xref"], w["x0"], w["contact"])
-t0 = time.perf_counter(); hist = np.zeros(64, dtype=np.int64); nconv = []; qp_solves = 0; statuses = np.zeros(5, dtype=np.int64)
-for it in range(15):
-    c.sqp_iterate(HARD, do_line_search=True)
-    bs = c.batch_stats(); hist += np.array(bs["iter_hist"]); statuses += np.array(bs["status_count"]); qp_solves += B
-    conv = c.download_sqp_state()[1]; nconv.append(int(conv.sum()))
-c.sync(); tt = time.perf_counter() - t0
-out["config4_b4096_n100_full_sqp"] = dict(sqp_iterations=15, seconds=tt, qp_solves_per_s=qp_solves / tt, nmpc_solves_per_s=B / tt,
-    converged_per_sqp_iteration=nconv, ipm_status_counts=statuses.tolist(),
-    ipm_iteration_histogram={str(i): int(v) for i, v in enumerate(hist) if v}, settings=S4,
-    note="every SQP iteration = K1+K2+K3+K4 on the device; host reads back 4096 convergence flags + stats per iteration")
-c.close()
+out["config4_b4096_n100_full_sqp"] = {}
+for spread in (1.0, 0.25):
+    for policy in ("carried", "reset"):
+        w = pkg.workload.srbd_batch(B, N=N, contact_mode="gait", spread=spread)
+        c = ctx_for(B, N, S4)
+        c.upload_traj(w["x"], w["u"], w["xref"], w["x0"], w["contact"]); c.sqp_iterate(HARD); c.sync()
+        c.reset_sqp_state(); c.upload_traj(w["x"], w["u"], w["xref"], w["x0"], w["contact"])
+        t0 = time.perf_counter(); hist = np.zeros(64, dtype=np.int64); nconv = []; qp_solves = 0; statuses = np.zeros(5, dtype=np.int64)
+        ever = np.zeros(B, dtype=bool)
+        for it in range(15):
+            if policy == "reset":
+                c.reset_sqp_state()
+            c.sqp_iterate(HARD, do_line_search=True)
+            bs = c.batch_stats(); hist += np.array(bs["iter_hist"]); statuses += np.array(bs["status_count"]); qp_solves += B
+            conv = c.download_sqp_state()[1]; ever |= conv.astype(bool); nconv.append(int(conv.sum()))
+        c.sync(); tt = time.perf_counter() - t0
+        out["config4_b4096_n100_full_sqp"]["spread_%g_alpha_%s" % (spread, policy)] = dict(
+            sqp_iterations=15, seconds=tt, qp_solves_per_s=qp_solves / tt, nmpc_solves_per_s=B / tt,
+            converged_flag_per_sqp_iteration=nconv, problems_converged_at_some_iteration=int(ever.sum()),
+            ipm_status_counts=statuses.tolist(),
+            ipm_iteration_histogram={str(i): int(v) for i, v in enumerate(hist) if v}, settings=S4,
+            note="every SQP iteration = K1+K2+K3+K4 on the device; host reads back 4096 convergence flags + stats per iteration")
+        c.close()
 
 # ---- config 5: one QP, N=50, latency host->host ------------------------------------------------------------------------
 N = 50
+S5 = dict(S8, iter_max=50)
 w = pkg.workload.srbd_batch(1, N=N, contact_mode="stance")
-c = ctx_for(1, N, dict(S8, tol_stat=1e-6))
+c = ctx_for(1, N, S5)
 sx, su = np.zeros((1, N + 1, 12)), np.zeros((1, N, 12)); it = np.zeros(1, dtype=np.int32); stt = np.zeros(1, dtype=np.int32)
-for _ in range(10): c.solve_host(HARD, w["x"], w["u"], w["xref"], w["x0"], w["contact"], sx, su, it, stt)
+for _ in range(10): c.solve_host_graph(HARD, w["x"], w["u"], w["xref"], w["x0"], w["contact"], sx, su, it, stt)
 ts = []
 for _ in range(1000):
-    t0 = time.perf_counter(); c.solve_host(HARD, w["x"], w["u"], w["xref"], w["x0"], w["contact"], sx, su, it, stt); ts.append(time.perf_counter() - t0)
+    t0 = time.perf_counter(); c.solve_host_graph(HARD, w["x"], w["u"], w["xref"], w["x0"], w["contact"], sx, su, it, stt); ts.append(time.perf_counter() - t0)
 tcs = []
 for _ in range(30):
-    t0 = time.perf_counter(); o = orc.pipeline(orc.model_params(N), orc.ipm_args(**dict(S8, tol_stat=1e-6)), N, HARD, w["x"], w["u"], w["xref"], w["x0"], w["contact"], threads=1, duals=False); tcs.append(time.perf_counter() - t0)
+    t0 = time.perf_counter(); o = orc.pipeline(orc.model_params(N), orc.ipm_args(**S5), N, HARD, w["x"], w["u"], w["xref"], w["x0"], w["contact"], threads=1, duals=False); tcs.append(time.perf_counter() - t0)
 ts, tcs = np.array(ts) * 1e6, np.array(tcs) * 1e6
 out["config5_single_qp_n50_latency"] = dict(gpu_p50_us=float(np.percentile(ts, 50)), gpu_p99_us=float(np.percentile(ts, 99)), ipm_iterations=int(it[0]), status=int(stt[0]),
     cpu_oracle_1core_p50_us=float(np.percentile(tcs, 50)), cpu_oracle_1core_p99_us=float(np.percentile(tcs, 99)), oracle_iterations=int(o["iter"][0]),
-    note="K1+K2+K3 for one QP on one warp incl. H2D/D2H; the sequential Riccati chain leaves the GPU no parallelism here")
+    settings=S5,
+    note="K1+K2+K3 for one QP on one warp incl. H2D/D2H through srbd_solve_host_graph (one CUDA graph launch per call); "
+         "the sequential Riccati chain leaves the GPU no parallelism here")
 c.close()
 print(json.dumps(out))

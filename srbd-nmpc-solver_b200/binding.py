@@ -217,6 +217,12 @@ class Context:
                                          capi.dptr(x0), capi.u8ptr(contact), capi.dptr(sol_x),
                                          capi.dptr(sol_u), capi.iptr(it), capi.iptr(status)))
 
+    def solve_host_graph(self, mode, x, u, xref, x0, contact, sol_x, sol_u, it, status):
+        """The low-latency form: pinned staging inside the context, the whole pipeline replayed as one CUDA graph."""
+        self._ck(self._L.srbd_solve_host_graph(self._h, int(mode), capi.dptr(x), capi.dptr(u), capi.dptr(xref),
+                                               capi.dptr(x0), capi.u8ptr(contact), capi.dptr(sol_x),
+                                               capi.dptr(sol_u), capi.iptr(it), capi.iptr(status)))
+
     def solve_host_async(self, mode, x, u, xref, x0, contact, sol_x, sol_u, it, status):
         """End-to-end call on caller-owned (ideally pinned) host buffers; nothing is allocated here."""
         self._ck(self._L.srbd_solve_host_async(self._h, int(mode), capi.dptr(x), capi.dptr(u), capi.dptr(xref),

@@ -54,6 +54,11 @@ struct srbd_ctx {
   int* d_flag = nullptr;
   int* h_flag = nullptr;     // pinned
   bool upload_variant_ok = false;
+  // low-latency host -> host path (srbd_solve_host_graph): the whole pipeline as ONE CUDA graph launch over pinned staging
+  cudaGraphExec_t graph_exec = nullptr;
+  int graph_mode = -1, graph_contact = -1;
+  long long graph_launches = 0;
+  char* h_stage = nullptr;   // pinned: [x | u | xref | x0 | sol_x | sol_u | iter | status | contact]
   double *d_xinit = nullptr, *d_uinit = nullptr;
   bool have_init = false, packed = false, solved = false;
   // raw QP-level staging (lazy)
@@ -322,6 +327,8 @@ int srbd_ctx_destroy(srbd_ctx* ctx) {
   for (void* p : ctx->raw_dev)
     if (p) cudaFree(p);
   if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
+  if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return SRBD_OK;
@@ -761,9 +768,10 @@ static int launch_generic(srbd_ctx* ctx, const int* qlist, const int* qcount, co
 static int solve_srbd_variant(srbd_ctx* ctx, const ModelDev* model, const int* gate = nullptr) {
   const QpLayout& L = ctx->L;
   if (!ctx->d_ws2) {
-    CU(cudaFuncSetAttribute(ipm_srbd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes));
+    CU(cudaFuncSetAttribute(ipm_srbd_kernel<SRBD_K3_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes));
+    CU(cudaFuncSetAttribute(ipm_srbd_kernel<SRBD_K3_TMA_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes));
     int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ipm_srbd_kernel, 32 * v2::kWarps, v2::kSmemBytes));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ipm_srbd_kernel<SRBD_K3_TMA>, 32 * v2::kWarps, v2::kSmemBytes));
     if (occ < 1) return fail(ctx, SRBD_ERR_CUDA, "ipm_srbd_kernel does not fit on this device");
     if (const char* cap = std::getenv("SRBD_K3_CTAS_PER_SM")) {  // tuning knob: fewer resident QPs = higher L2 hit rate
       const int c = std::atoi(cap);
@@ -800,7 +808,9 @@ static int solve_srbd_variant(srbd_ctx* ctx, const ModelDev* model, const int* g
   }
   CU(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
   CU(cudaMemsetAsync(ctx->d_bstats, 0, sizeof(srbd_batch_stats), ctx->stream));
-  ipm_srbd_kernel<<<ctx->grid2, 32 * v2::kWarps, v2::kSmemBytes, ctx->stream>>>(p);
+  // batches of fewer QPs than SMs have nothing to hide a bulk copy's latency behind: the cp.async-only instantiation
+  if (ctx->B < ctx->sm_count) ipm_srbd_kernel<SRBD_K3_TMA_SMALL><<<ctx->grid2, 32 * v2::kWarps, v2::kSmemBytes, ctx->stream>>>(p);
+  else ipm_srbd_kernel<SRBD_K3_TMA><<<ctx->grid2, 32 * v2::kWarps, v2::kSmemBytes, ctx->stream>>>(p);
   ctx->launches++;
   CU(cudaGetLastError());
   ctx->solved = true;
@@ -1053,6 +1063,53 @@ int srbd_solve_host(srbd_ctx* ctx, int mode, const double* x, const double* u, c
   if (iter) CU(cudaMemcpyAsync(iter, ctx->d_iter, B * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   if (status) CU(cudaMemcpyAsync(status, ctx->d_status, B * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  return SRBD_OK;
+}
+
+int srbd_solve_host_graph(srbd_ctx* ctx, int mode, const double* x, const double* u, const double* xref, const double* x0,
+                          const uint8_t* contact, double* sol_x, double* sol_u, int* iter, int* status) {
+  if (int rc = require_srbd(ctx)) return rc;
+  if (!x || !u || !xref || !x0) return fail(ctx, SRBD_ERR_ARG, "null trajectory pointer");
+  CU(cudaSetDevice(ctx->device));
+  const size_t B = ctx->B, S = ctx->L.N + 1, N = ctx->L.N, D = sizeof(double);
+  const size_t nX = B * S * 12, nU = B * N * 12, n0 = B * 12;
+  // staging layout (doubles first, then the two int arrays, then the contact bytes)
+  const size_t oX = 0, oU = oX + nX, oR = oU + nU, o0 = oR + nX, oSX = o0 + n0, oSU = oSX + nX, oI = oSU + nU;
+  const size_t bytes = oI * D + 2 * B * sizeof(int) + B * N * 2;
+  if (!ctx->h_stage) CU(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_stage), bytes, cudaHostAllocDefault));
+  double* hd = reinterpret_cast<double*>(ctx->h_stage);
+  int* hi = reinterpret_cast<int*>(ctx->h_stage + oI * D);
+  uint8_t* hc = reinterpret_cast<uint8_t*>(hi + 2 * B);
+  std::memcpy(hd + oX, x, nX * D); std::memcpy(hd + oU, u, nU * D); std::memcpy(hd + oR, xref, nX * D);
+  std::memcpy(hd + o0, x0, n0 * D);
+  if (contact) std::memcpy(hc, contact, B * N * 2);
+  const int has_contact = contact ? 1 : 0;
+  if (!ctx->graph_exec || ctx->graph_mode != mode || ctx->graph_contact != has_contact) {
+    if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+    // one eager pass first: lazy allocations and function attributes must not happen inside a capture
+    if (int rc = srbd_solve_host(ctx, mode, hd + oX, hd + oU, hd + oR, hd + o0, contact ? hc : nullptr, hd + oSX, hd + oSU, hi, hi + B))
+      return rc;
+    const long long l0 = ctx->launches;
+    CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = srbd_solve_host_async(ctx, mode, hd + oX, hd + oU, hd + oR, hd + o0, contact ? hc : nullptr, hd + oSX, hd + oSU, hi, hi + B);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+    if (rc != SRBD_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) return fail(ctx, SRBD_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+    const cudaError_t ie = cudaGraphInstantiate(&ctx->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) return fail(ctx, SRBD_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie));
+    ctx->graph_launches = ctx->launches - l0;
+    ctx->launches = l0;   // (the capture enqueued nothing)
+    ctx->graph_mode = mode; ctx->graph_contact = has_contact;
+  }
+  CU(cudaGraphLaunch(ctx->graph_exec, ctx->stream));
+  ctx->launches += ctx->graph_launches;
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (sol_x) std::memcpy(sol_x, hd + oSX, nX * D);
+  if (sol_u) std::memcpy(sol_u, hd + oSU, nU * D);
+  if (iter) std::memcpy(iter, hi, B * sizeof(int));
+  if (status) std::memcpy(status, hi + B, B * sizeof(int));
   return SRBD_OK;
 }
 

@@ -117,9 +117,15 @@ namespace v2 {
 // tile) 549 k / 548 k; S1 + S6 only 554 k / 530 k; S1 only 568 k / 534 k; S6 only 575 k / 540 k against 580 k / 545 k
 // without any.  A bulk copy has a longer latency than the per-lane copies and the prefetch distance is one stage (the
 // shared memory is full), which the short vector sweeps S2 / S4 (2.6-3.0 k cycles per stage) and the factorization cannot
-// hide; the residual sweep has no recursion to wait for and takes them at no measurable cost.  Default: S6 only.
+// hide; the residual sweep has no recursion to wait for and takes them at no measurable cost when the GPU is full.  A
+// single QP alone (BASELINE config 5) has nothing to overlap the longer latency with: 3.75 ms against 3.59 ms per N = 50
+// solve.  Hence two instantiations: SRBD_K3_TMA (default: S6) for batches that fill the machine, SRBD_K3_TMA_SMALL
+// (default: none) for batches of fewer QPs than SMs (capi.cu picks).
 #ifndef SRBD_K3_TMA
 #define SRBD_K3_TMA 8
+#endif
+#ifndef SRBD_K3_TMA_SMALL
+#define SRBD_K3_TMA_SMALL 0
 #endif
 // panel stride of the BAbt tile in shared memory.  48 = the record as it lies in HBM (one bulk copy); 54 (= 2 mod 4) makes
 // the row-permuted B fragments bank-conflict free but measures no faster (580 k vs 576 k burst, 545 k vs 538 k sustained)
@@ -243,6 +249,8 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b,
       : "=d"(d0), "=d"(d1)
       : "d"(a), "d"(b), "d"(c0), "d"(c1));
 }
+// kTma: the tile-engine mask of this instantiation (SRBD_K3_TMA above)
+template <int kTma>
 struct SrbdSolver {
   const SrbdIpmParams& p;
   int lane, q, N;
@@ -331,7 +339,7 @@ struct SrbdSolver {
   }
   __device__ __forceinline__ void tiles_init() {
     tph = 0;
-    if (SRBD_K3_TMA) {
+    if (kTma) {
       if (lane == 0) {
         mbar_init(bar(0), 1);
         mbar_init(bar(1), 1);
@@ -493,7 +501,7 @@ struct SrbdSolver {
     return x > 0.0 ? y : 0.0;
   }
   __device__ void sweep_factor() {
-    constexpr bool kT1 = (SRBD_K3_TMA & 1) != 0;
+    constexpr bool kT1 = (kTma & 1) != 0;
     const double reg = p.a.reg_prim;
     double* sP = sm + v2::wP;
     double* sPan = sm + v2::wPAN;
@@ -806,7 +814,7 @@ struct SrbdSolver {
     return v;
   }
   __device__ __forceinline__ void sweep_backvec(int mode, double sm_) {
-    constexpr bool kT4 = (SRBD_K3_TMA & 2) != 0;
+    constexpr bool kT4 = (kTma & 2) != 0;
     const int r = fr, t = ft, pi = fpi;
     const int oG = (pi >> 2) * v2::kGP + 4 * t + (pi & 3);            // G[8I+pi][4kt+t]      : + 2 kGP I + 16 kt
     // 4x4 blocks of the factor panels as B fragments: row index t / column pi, and row pi / column t
@@ -950,7 +958,7 @@ struct SrbdSolver {
     return v;
   }
   __device__ __forceinline__ void sweep_forward(bool fin, double& ap, double& ad) {
-    constexpr bool kT2 = (SRBD_K3_TMA & 4) != 0;
+    constexpr bool kT2 = (kTma & 4) != 0;
     const int r = fr, t = ft, pi = fpi;
     const int oLT = 144 + (pi >> 2) * v2::kPanF + 48 + 4 * t + (pi & 3);  // Ls[4kt+t][8I+pi]   : + 2 kPanF I + 16 kt
     // 4x4 blocks of the factor panels as B fragments: row index t / column pi, and row pi / column t
@@ -1143,7 +1151,7 @@ struct SrbdSolver {
     return v;
   }
   __device__ void residuals(double res[4], double& mu, int nc_mask, bool do_update, double sp, double sd) {
-    constexpr bool kT6 = (SRBD_K3_TMA & 8) != 0;
+    constexpr bool kT6 = (kTma & 8) != 0;
     const int r = fr, t = ft, pi = fpi;
     const int gB = (pi >> 2) * v2::kGP + 4 * t + (pi & 3);   // G[8I+pi][4kt+t]   : + 2 kGP I + 16 kt
     const int oGT = 4 * pi + t;                              // G[4kt+t][8I+pi]   : + 32 I + kGP kt
@@ -1479,6 +1487,7 @@ struct SrbdSolver {
 #else
 #define SRBD_K3_BOUNDS __launch_bounds__(32 * v2::kWarps, v2::kMinCtas)
 #endif
+template <int kTma>
 __global__ void SRBD_K3_BOUNDS ipm_srbd_kernel(const SrbdIpmParams p) {
   extern __shared__ __align__(128) double2 smem2[];  // no static shared memory: the tiles start on 128-byte lines
   if (p.gate && *p.gate != p.gate_value) return;
@@ -1503,7 +1512,7 @@ __global__ void SRBD_K3_BOUNDS ipm_srbd_kernel(const SrbdIpmParams p) {
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  SrbdSolver S(p, smem, smem + v2::kCtaShared + warp * v2::kWarpShared, blockIdx.x * v2::kWarps + warp);
+  SrbdSolver<kTma> S(p, smem, smem + v2::kCtaShared + warp * v2::kWarpShared, blockIdx.x * v2::kWarps + warp);
   S.tiles_init();
   long long it_sum = 0, solves = 0;
   int st_cnt[5] = {0, 0, 0, 0, 0};

@@ -783,3 +783,27 @@ def test_iterative_refinement_matches_the_oracle(pkg, orc):
                                       "itref_corr_2_oracle": [o["status"].tolist(), o["iter"].tolist()],
                                       "itref_corr_2_gpu": [st["status"].tolist(), st["iter"].tolist()]}
     _dump_report()
+
+
+@pytest.mark.gpu
+def test_low_latency_graph_path_config5(pkg, orc):
+    """BASELINE config 5 (one SRBD QP, N = 50, all stance, HARD_INEQ, ALL FOUR tolerances 1e-8) through the low-latency
+    entry point srbd_solve_host_graph (pinned staging + one CUDA graph launch per call): same iteration count and status
+    as the oracle, primal iterates within the pipeline tolerance, bit-identical to the plain call, and replayable with
+    new inputs (the graph is independent of the caller's buffers)."""
+    from srbd_nmpc_solver_b200.binding import make_dims
+    N = 50
+    settings = dict(SETTINGS, iter_max=50)
+    sx, su = np.zeros((1, N + 1, 12)), np.zeros((1, N, 12))
+    it, stt = np.zeros(1, dtype=np.int32), np.zeros(1, dtype=np.int32)
+    with make_ctx(pkg, 1, N, settings=settings) as ctx:
+        for start in (0, 3, 0):
+            w = pkg.workload.srbd_batch(1, N=N, contact_mode="stance", start=start)
+            ctx.solve_host_graph(1, w["x"], w["u"], w["xref"], w["x0"], w["contact"], sx, su, it, stt)
+            gx, gu, git = sx.copy(), su.copy(), int(it[0])
+            ctx.solve_host(1, w["x"], w["u"], w["xref"], w["x0"], w["contact"], sx, su, it, stt)
+            assert np.array_equal(gx, sx) and np.array_equal(gu, su) and git == int(it[0])
+            ref = orc.pipeline(orc.model_params(N), orc.ipm_args(**settings), N, 1, w["x"], w["u"], w["xref"], w["x0"],
+                               w["contact"])
+            assert stt[0] == 0 and ref["status"][0] == 0 and git == int(ref["iter"][0]), (start, git, ref["iter"])
+            assert relerr(gx, ref["x"]).max() <= 5e-9 and relerr(gu, ref["u"]).max() <= 5e-8
