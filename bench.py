@@ -240,6 +240,23 @@ def latency_leg(pkg, reps=300):
                     "GPU path is a throughput design (DESIGN.md section 5, latency)"}
 
 
+def facade_leg(batch, device):
+    """The reference's OWN boundary as the measured path: hpipm::OcpQpIpmSolver::solveBatch on host std::vector<OcpQp>
+    (srbd-nmpc-solver_b200/host/tests/bench_facade.cpp, built by __graft_entry__.build()).  The QP-level interface moves
+    228 KB per N=20 QP (every A, B, Q, S, R, C, D) against 6 KB for the NMPC-level calls, so a 65536-QP batch would be
+    15 GB of host data: measured at `batch` QPs and reported per second."""
+    exe = os.path.join(ROOT, "srbd-nmpc-solver_b200", "host", "tests", "bench_facade")
+    if not os.path.exists(exe):
+        return {"unavailable": "bench_facade not built (python -c 'import __graft_entry__ as g; g.build()')"}
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[device]
+               if os.environ.get("CUDA_VISIBLE_DEVICES") else str(device))
+    try:
+        r = subprocess.run([exe, str(batch), "3"], capture_output=True, text=True, timeout=600, env=env)
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:  # the headline line must not depend on this leg
+        return {"unavailable": repr(e)[:200]}
+
+
 def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
@@ -252,6 +269,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=8192, help="QPs per step of the CPU baseline / reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true", help="skip the single-instance latency leg (BASELINE config 5)")
+    ap.add_argument("--no-facade", action="store_true", help="skip the hpipm-cpp facade leg (host/tests/bench_facade)")
+    ap.add_argument("--facade-batch", type=int, default=4096)
     ap.add_argument("--e2e-steps", type=int, default=3)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -466,6 +485,7 @@ def main():
             cpu_baseline = cpu_baseline_record(v, cores, f"first {args.cpu_sample} QPs of rank 0's shard, one pass "
                                                f"({dt:.1f} s), OpenMP over QPs", iteration_counts_equal_gpu=same)
         latency = None if args.no_latency else latency_leg(pkg)
+        facade = None if args.no_facade else facade_leg(args.facade_batch, local_rank)
         it = st["iter"]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -479,7 +499,7 @@ def main():
                         "ms_per_step": e2e_ms_max, "steps": 2 * args.e2e_steps,
                         "how": "two contexts / CUDA streams take the steps alternately (srbd_solve_host_async + srbd_wait): "
                                "copies of one step overlap the kernels of the other"},
-                "roofline": roofline, "cpu_baseline": cpu_baseline, "latency": latency,
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "latency": latency, "facade_e2e": facade,
                 "ipm": {"iter_mean": float(it.mean()), "iter_min": int(it.min()), "iter_max": int(it.max()),
                         "status_counts_all_ranks": stats_all["status_count"], "solves_all_ranks": stats_all["solves"],
                         "iter_sum_all_ranks": stats_all["iter_sum"], "res_max_all_ranks": stats_all["res_max"]}}

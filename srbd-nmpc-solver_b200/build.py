@@ -36,6 +36,7 @@ def build(force=False, verbose=False):
 
 
 HOST_TEST = os.path.join(HERE, "host", "tests", "test_facades")
+HOST_BENCH = os.path.join(HERE, "host", "tests", "bench_facade")
 
 
 def build_host_tests(force=False):
@@ -44,17 +45,27 @@ def build_host_tests(force=False):
     deps = [src] + [os.path.join(HERE, "host", f) for f in ("NMPC_solver.hpp", "SRBD_model.hpp", "eigen_shim.hpp",
                                                              os.path.join("hpipm-cpp", "hpipm-cpp.hpp"))]
     if (not force and os.path.exists(HOST_TEST) and
-            all(os.path.getmtime(HOST_TEST) >= os.path.getmtime(d) for d in deps + [OUT])):
+            os.path.exists(HOST_BENCH) and
+            all(min(os.path.getmtime(HOST_TEST), os.path.getmtime(HOST_BENCH)) >= os.path.getmtime(d)
+                for d in deps + [OUT, os.path.join(HERE, "host", "tests", "bench_facade.cpp")])):
         return HOST_TEST
     gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     cmd = [gxx, "-std=c++17", "-O2", "-Wall", "-Wextra", src, "-o", HOST_TEST, "-L" + HERE, "-lsrbd_b200",
-           "-Wl,-rpath," + HERE, "-Wl,-rpath,$ORIGIN/../.."]
+           "-Wl,-rpath," + HERE, "-Wl,-rpath,$ORIGIN/../..", "-pthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("g++ failed for the host facade test")
     if r.stderr.strip():
         sys.stderr.write(r.stderr)
+    # the facade benchmark (bench.py: `facade_e2e`)
+    bsrc = os.path.join(HERE, "host", "tests", "bench_facade.cpp")
+    cmd = [gxx, "-std=c++17", "-O2", "-Wall", "-Wextra", bsrc, "-o", HOST_BENCH, "-L" + HERE, "-lsrbd_b200",
+           "-Wl,-rpath," + HERE, "-Wl,-rpath,$ORIGIN/../..", "-pthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed for the facade benchmark")
     return HOST_TEST
 
 

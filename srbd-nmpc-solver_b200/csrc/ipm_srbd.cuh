@@ -801,10 +801,10 @@ struct SrbdSolver {
   // ------------------------------------------------------------------------------------------------
   // S4: vector-only backward sweep (gradient recursion with the stored factors).  mode 1: centering
   // correction, mode 2: centering only; sm_ = sigma*mu (clamped by the caller)
-  struct S4v { double mk, rmb, dt, dlam, lam, t, rd, rg[6], prb[3]; };
+  struct S4v { double mk, dt, dlam, lam, t, rd, rg[6], prb[3]; };
   __device__ __forceinline__ S4v load_s4(int k) const {
     S4v v;
-    v.mk = __ldg(gMaskL(k)); v.rmb = ws_ld(wsc(k, v2::oRMB)); v.dt = ws_ld(wsc(k, v2::oDT));
+    v.mk = __ldg(gMaskL(k)); v.dt = ws_ld(wsc(k, v2::oDT));
     v.dlam = ws_ld(wsc(k, v2::oDLAM)); v.lam = ws_ld(wsc(k, v2::oLAM)); v.t = ws_ld(wsc(k, v2::oT));
     v.rd = ws_ld(wsc(k, v2::oRD));
 #pragma unroll
@@ -851,7 +851,9 @@ struct SrbdSolver {
       double* gbuf = sm + (b ? v2::wqx : v2::wQX);
       // ---- row-per-lane: res_m of this solve and gamma ------------------------------------------------------------
       {
-        double rm = cur.rmb;
+        // res_m of the iterate (BACKUP_RES_M) = lam * t on the active rows: recomputed from the iterate the residual sweep
+        // stored (bit-identical to what it put into res_m) instead of a stored copy
+        double rm = (cur.lam * cur.t) * cur.mk;
         if (mode == 1) rm += cur.dt * cur.dlam;
         rm = (rm - sm_) * cur.mk;
         const double ti = 1.0 / cur.t;
@@ -1310,7 +1312,6 @@ struct SrbdSolver {
         if (lane < 24) {
           wsc(k, v2::oRD)[0] = rd;
           wsc(k, v2::oRM)[0] = rm;
-          wsc(k, v2::oRMB)[0] = rm;
           smu += rm;
           nd_ = amax_nan(nd_, rd);
           nm_ = amax_nan(nm_, rm);

@@ -15,6 +15,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../../include/srbd_b200.h"
@@ -230,6 +231,22 @@ class ContextPool {
   std::vector<PooledContext> free_;
   long created_ = 0;
 };
+// Flattening B x (N+1) Eigen objects into the staging arena (and scattering the solutions back) is plain memory
+// traffic: 228 KB per N = 20 SRBD QP.  Large batches split it over a few host threads.
+template <class F>
+inline void parallelFor(size_t n, size_t grain, F&& fn) {
+  size_t nt = std::thread::hardware_concurrency();
+  if (nt > 16) nt = 16;
+  if (nt * grain > n) nt = n / grain;
+  if (nt < 2) { fn(size_t(0), n); return; }
+  std::vector<std::thread> th;
+  const size_t chunk = (n + nt - 1) / nt;
+  for (size_t t = 0; t < nt; ++t) {
+    const size_t lo = t * chunk, hi = lo + chunk < n ? lo + chunk : n;
+    if (lo < hi) th.emplace_back([&fn, lo, hi] { fn(lo, hi); });
+  }
+  for (auto& t : th) t.join();
+}
 }  // namespace detail
 
 // number of device contexts created so far (tests: a solver per SQP iteration must not create more than one)
@@ -447,7 +464,8 @@ class OcpQpIpmSolver {
       if (static_cast<size_t>(m.size()) == per) put(f, b, stages, i, per, m.data());
       else fill(f, b, stages, i, per, 1.0);
     };
-    for (size_t b = 0; b < Bz; ++b) {
+    detail::parallelFor(Bz, 64, [&](size_t b_lo, size_t b_hi) {
+    for (size_t b = b_lo; b < b_hi; ++b) {
       const std::vector<OcpQp>& qp = *qps[b];
       for (size_t i = 0; i <= N; ++i) {
         const OcpQp& s = qp[i];
@@ -485,6 +503,7 @@ class OcpQpIpmSolver {
           if (i < N) put(fuin, b, N, i, nu, (*sols[b])[i].u.data());
         }
     }
+    });
     auto at = [&](int f) -> const double* { return in_sizes[f] ? ar + in_off[f] : nullptr; };
     srbd_qp_host h{};
     h.A = at(fA); h.Bm = at(fB); h.b = at(fb); h.Q = at(fQ); h.S = at(fS); h.R = at(fR); h.q = at(fq); h.r = at(fr);
@@ -555,7 +574,8 @@ class OcpQpIpmSolver {
     status.resize(B);
     batch_iter_.assign(it, it + B);
     batch_res_.assign(rm, rm + 4 * Bz);
-    for (size_t b = 0; b < Bz; ++b) {
+    detail::parallelFor(Bz, 64, [&](size_t b_lo, size_t b_hi) {
+    for (size_t b = b_lo; b < b_hi; ++b) {
       auto& s = *sols[b];
       for (size_t i = 0; i <= N; ++i) {
         s[i].x.resize(nx); s[i].pi.resize(nx);
@@ -578,6 +598,7 @@ class OcpQpIpmSolver {
       }
       status[b] = (st[b] >= 0 && st[b] <= 3) ? static_cast<HpipmStatus>(st[b]) : HpipmStatus::UnknownFailure;
     }
+    });
     // statistics of the (last) QP: iter, 4 max residuals, rows 0..iter+1 of the 18-column table (:376-403)
     const size_t bl = Bz - 1;
     solver_statistics_.iter = it[bl];
