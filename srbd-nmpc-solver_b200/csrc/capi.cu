@@ -74,6 +74,7 @@ struct srbd_ctx {
   double* d_ws = nullptr;
   double* d_ws2 = nullptr;   // workspace of the SRBD throughput variant of K3 (ipm_srbd.cuh)
   int* d_retry = nullptr;    // [B + 1]: rescue list of the variant (QPs that did not converge) and, at [B], its length
+  int* d_retry2 = nullptr;   // [B + 1]: what the first rescue stage (the variant with the other pivot rounding) leaves over
   int grid2 = 0;
   int assembled_mode = -1;   // >= 0: the packed QP came from srbd_assemble (K2) in that mode
   int grid = 0, stat_rows = 0;
@@ -87,6 +88,7 @@ struct srbd_ctx {
   long long launches = 0;
   std::string err;
   int sm_count = 0;
+  int smem_optin = 0;   // cudaDevAttrMaxSharedMemoryPerBlockOptin
 };
 
 namespace {
@@ -244,6 +246,7 @@ int srbd_ctx_create(int device, int batch, const srbd_qp_dims* dims, void* strea
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(SRBD_ERR_CUDA);
   ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
   if (stream) ctx->stream = (cudaStream_t)stream;
   else {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(SRBD_ERR_CUDA);
@@ -320,7 +323,7 @@ int srbd_ctx_destroy(srbd_ctx* ctx) {
                   ctx->d_dmask, ctx->d_raw0, ctx->d_x0, ctx->d_xinit, ctx->d_uinit, ctx->d_out, ctx->d_in, ctx->d_model_qp,
                   ctx->d_flag, ctx->d_P, ctx->d_p, ctx->d_K, ctx->d_k,
                   ctx->d_stat, ctx->d_counter, ctx->d_bstats, ctx->d_ws,
-                  ctx->d_ws2, ctx->d_srec, ctx->d_retry, ctx->d_r0raw, ctx->d_mpc_x, ctx->d_mpc_u, ctx->d_mpc_xcur,
+                  ctx->d_ws2, ctx->d_srec, ctx->d_retry, ctx->d_retry2, ctx->d_r0raw, ctx->d_mpc_x, ctx->d_mpc_u, ctx->d_mpc_xcur,
                   ctx->d_plantA, ctx->d_plantB, ctx->d_plantb, ctx->d_mpc_iter, ctx->d_mpc_status};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -756,7 +759,17 @@ static int launch_generic(srbd_ctx* ctx, const int* qlist, const int* qcount, co
   p.gate = gate; p.gate_value = gate_value;
   KernelChoice kc = pick_kernel(L);
   const int grid = qlist ? (ctx->grid < ctx->sm_count ? ctx->grid : ctx->sm_count) : ctx->grid;  // a rescue list is short
-  kc.fn<<<grid, 32, 0, ctx->stream>>>(p);
+  // fewer CTAs than SMs: the workspace of each CTA's QP in its dynamic shared memory, when it fits (IpmParams::ws_in_smem)
+  const bool refine = ctx->args.itref_pred_max > 0 || ctx->args.itref_corr_max > 0;
+  const size_t ws_bytes = (size_t)(refine ? L.ws_size : L.ws_size_core) * sizeof(double);
+  const char* nosm = std::getenv("SRBD_K3_WS_GLOBAL");
+  size_t dyn = 0;
+  if (grid <= ctx->sm_count && ws_bytes + 24 * 1024 <= (size_t)ctx->smem_optin && !(nosm && nosm[0] == '1')) {
+    if (cudaFuncSetAttribute(kc.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_bytes) == cudaSuccess) dyn = ws_bytes;
+    else cudaGetLastError();
+  }
+  p.ws_in_smem = dyn ? 1 : 0;
+  kc.fn<<<grid, 32, dyn, ctx->stream>>>(p);
   ctx->launches++;
   CU(cudaGetLastError());
   ctx->solved = true;
@@ -768,10 +781,11 @@ static int launch_generic(srbd_ctx* ctx, const int* qlist, const int* qcount, co
 static int solve_srbd_variant(srbd_ctx* ctx, const ModelDev* model, const int* gate = nullptr) {
   const QpLayout& L = ctx->L;
   if (!ctx->d_ws2) {
-    CU(cudaFuncSetAttribute(ipm_srbd_kernel<SRBD_K3_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes));
-    CU(cudaFuncSetAttribute(ipm_srbd_kernel<SRBD_K3_TMA_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes));
+    CU(cudaFuncSetAttribute(ipm_srbd_kernel<SRBD_K3_TMA, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes));
+    CU(cudaFuncSetAttribute(ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes));
+    CU(cudaFuncSetAttribute(ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes));
     int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ipm_srbd_kernel<SRBD_K3_TMA>, 32 * v2::kWarps, v2::kSmemBytes));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ipm_srbd_kernel<SRBD_K3_TMA, 0>, 32 * v2::kWarps, v2::kSmemBytes));
     if (occ < 1) return fail(ctx, SRBD_ERR_CUDA, "ipm_srbd_kernel does not fit on this device");
     if (const char* cap = std::getenv("SRBD_K3_CTAS_PER_SM")) {  // tuning knob: fewer resident QPs = higher L2 hit rate
       const int c = std::atoi(cap);
@@ -787,6 +801,7 @@ static int solve_srbd_variant(srbd_ctx* ctx, const ModelDev* model, const int* g
     ctx->grid2 = (int)g;
     CU(dalloc(&ctx->d_ws2, (size_t)ctx->grid2 * v2::kWarps * (size_t)(L.N + 1) * v2::kStage));
     CU(dalloc(&ctx->d_retry, (size_t)ctx->B + 1));
+    CU(dalloc(&ctx->d_retry2, (size_t)ctx->B + 1));
   }
   // Rescue pass: a QP on which the variant runs to iter_max (about 1 in 1e5 sits on the rounding floor of the blocked
   // triangular solves) is solved again by the generic kernel, whose row-by-row substitution is as
@@ -809,18 +824,31 @@ static int solve_srbd_variant(srbd_ctx* ctx, const ModelDev* model, const int* g
   CU(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
   CU(cudaMemsetAsync(ctx->d_bstats, 0, sizeof(srbd_batch_stats), ctx->stream));
   // batches of fewer QPs than SMs have nothing to hide a bulk copy's latency behind: the cp.async-only instantiation
-  if (ctx->B < ctx->sm_count) ipm_srbd_kernel<SRBD_K3_TMA_SMALL><<<ctx->grid2, 32 * v2::kWarps, v2::kSmemBytes, ctx->stream>>>(p);
-  else ipm_srbd_kernel<SRBD_K3_TMA><<<ctx->grid2, 32 * v2::kWarps, v2::kSmemBytes, ctx->stream>>>(p);
+  if (ctx->B < ctx->sm_count) ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 0><<<ctx->grid2, 32 * v2::kWarps, v2::kSmemBytes, ctx->stream>>>(p);
+  else ipm_srbd_kernel<SRBD_K3_TMA, 0><<<ctx->grid2, 32 * v2::kWarps, v2::kSmemBytes, ctx->stream>>>(p);
   ctx->launches++;
   CU(cudaGetLastError());
   ctx->solved = true;
   ctx->ric_valid = false;   // the variant exports neither P, p, K, k nor pi[0] nor the statistics table
   ctx->stat_valid = false;
   if (rescue) {
-    // the generic kernel reads the dense records: write them for the listed QPs only (an empty kernel otherwise)
+    // Stage 1: the listed QPs again in the SAME tensor-core kernel with the other rounding of the inverse pivots (kPivot =
+    // 1): a QP that runs to iter_max sits on a knife edge of the rounding floor, and each rounding has its own (about 3
+    // per million, scripts/count_iter_max.py).  An empty kernel unless the list is non-empty; 1.4 ms for one QP.
+    SrbdIpmParams r = p;
+    r.qlist = ctx->d_retry; r.qcount = ctx->d_retry + ctx->B;
+    r.retry_list = ctx->d_retry2; r.retry_count = ctx->d_retry2 + ctx->B;
+    CU(cudaMemsetAsync(ctx->d_retry2 + ctx->B, 0, sizeof(int), ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
+    const int g1 = ctx->grid2 < ctx->sm_count ? ctx->grid2 : ctx->sm_count;
+    ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 1><<<g1, 32 * v2::kWarps, v2::kSmemBytes, ctx->stream>>>(r);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    // Stage 2: what is still on the list goes to the generic kernel (row-by-row substitution, no block inverses), which
+    // reads the dense records: write them for the listed QPs only (empty kernels otherwise)
     if (ctx->assembled_mode >= 0 && !ctx->dense_valid)
-      if (int rc = launch_assemble(ctx, ctx->assembled_mode, true, ctx->d_retry, ctx->d_retry + ctx->B)) return rc;
-    return launch_generic(ctx, ctx->d_retry, ctx->d_retry + ctx->B);
+      if (int rc = launch_assemble(ctx, ctx->assembled_mode, true, ctx->d_retry2, ctx->d_retry2 + ctx->B)) return rc;
+    return launch_generic(ctx, ctx->d_retry2, ctx->d_retry2 + ctx->B);
   }
   return SRBD_OK;
 }

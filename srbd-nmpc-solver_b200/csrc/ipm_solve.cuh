@@ -49,6 +49,11 @@ struct IpmParams {
   // device-side dispatch (QP-level uploads, capi.cu): run only if *gate == gate_value
   const int* gate;
   int gate_value;
+  // Small launches (fewer CTAs than SMs: single QPs through the facade, the rescue list): the per-QP workspace lives in
+  // the CTA's DYNAMIC SHARED MEMORY instead of global memory.  One warp alone pays a full L2 round trip at the top of
+  // every phase of every stage (about sixty per stage and iteration: 14.1 ms for one N = 20 SRBD QP against 1.4 ms in
+  // the tensor-core variant); with the iterate, the residuals and the factors on chip those are shared-memory loads.
+  int ws_in_smem;
 };
 
 // compile-time dimension policy (loops unroll, index math folds) ...
@@ -142,10 +147,10 @@ struct Solver {
   // refinement solves: the residual of the linear system)
   struct Rhs { int rg, rb, rdl, rdu, rml, rmu; } rhs;
 
-  __device__ Solver(const IpmParams& p_, double* smem, int* sidx)
+  __device__ Solver(const IpmParams& p_, double* smem, int* sidx, double* ws_smem)
       : p(p_), L(p_.L), dm(p_.L), lane(threadIdx.x & 31), q(0), N(p_.L.N) {
     rhs = Rhs{L.ws_rg, L.ws_rb, L.ws_rdl, L.ws_rdu, L.ws_rml, L.ws_rmu};
-    W = p.ws + (size_t)blockIdx.x * L.ws_size;
+    W = p.ws_in_smem ? ws_smem : p.ws + (size_t)blockIdx.x * L.ws_size;
     sM = smem;
     sB = sM + (D::kNM + 1) * LD;
     sP = sB + (D::kNM + 1) * LD;
@@ -1198,9 +1203,10 @@ __global__ void __launch_bounds__(32) ipm_solve_kernel(const IpmParams p) {
   __shared__ double smem[Solver<D>::kSmemDoubles];
   __shared__ int sidx[3 * kMaxNB];
   __shared__ int s_next;
+  extern __shared__ __align__(16) double ws_dyn[];   // the workspace of this CTA's QP when p.ws_in_smem
   if (p.gate && *p.gate != p.gate_value) return;
   if (p.qlist && *p.qcount == 0) return;  // empty rescue list (the usual case): nothing to set up
-  Solver<D> S(p, smem, sidx);
+  Solver<D> S(p, smem, sidx, ws_dyn);
   // per-CTA partial batch statistics (fused epilogue; one set of atomics per CTA at the end)
   long long it_sum = 0, solves = 0;
   int st_cnt[5] = {0, 0, 0, 0, 0};

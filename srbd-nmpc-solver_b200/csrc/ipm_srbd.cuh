@@ -63,6 +63,9 @@ struct SrbdIpmParams {
   // the generic kernel (row-by-row substitution, no block inverses) on exactly those
   int* retry_list;
   int* retry_count;
+  // optional work list (the first rescue stage, capi.cu): solve only the QPs qlist[0 .. *qcount)
+  const int* qlist;
+  const int* qcount;
   // device-side dispatch (QP-level uploads, capi.cu): run only if *gate == gate_value
   const int* gate;
   int gate_value;
@@ -249,8 +252,13 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b,
       : "=d"(d0), "=d"(d1)
       : "d"(a), "d"(b), "d"(c0), "d"(c1));
 }
-// kTma: the tile-engine mask of this instantiation (SRBD_K3_TMA above)
-template <int kTma>
+// kTma: the tile-engine mask of this instantiation (SRBD_K3_TMA above).  kPivot: how the inverse Cholesky pivots are formed:
+// 0 = MUFU seed + one third-order step (1.25 ulp, the throughput flavour), 1 = CUDA's rsqrt() (1 ulp, 5 % slower).  Both
+// are faithful; they ROUND differently.  About 2-4 QPs per million sit on a knife edge of the IPM's rounding floor and run
+// to iter_max in one flavour and not in the other (scripts/count_iter_max.py: 2 + 1 per 2 x 1048576 QPs with flavour 0,
+// 1 + 1 OTHER ones with flavour 1, 4 + 0 with an extra Newton step): the first rescue stage re-solves the listed QPs
+// with flavour 1 at tensor-core speed (1.4 ms for one QP instead of 14-17 ms in the generic kernel).
+template <int kTma, int kPivot>
 struct SrbdSolver {
   const SrbdIpmParams& p;
   int lane, q, N;
@@ -492,12 +500,25 @@ struct SrbdSolver {
   // y (1 + e/2 + 3 e^2/8), e = 1 - x y^2  (error ~ e^3); a non-positive pivot gives 0 like BLASFEO's potrf
   // (BLASFEO potrf_l_mn semantics)
   static __device__ __forceinline__ double rsqrt_pivot(double x) {
+#if SRBD_K3_EXACT_RSQRT == 1
+    return x > 0.0 ? 1.0 / sqrt(x) : 0.0;   // (experiment: IEEE sqrt + division)
+#elif SRBD_K3_EXACT_RSQRT == 2
+    return x > 0.0 ? rsqrt(x) : 0.0;        // (experiment: the CUDA library function, 1 ulp)
+#endif
+    if (kPivot == 1) return x > 0.0 ? rsqrt(x) : 0.0;
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;\n" : "=d"(y) : "d"(x));
     const double tt = x * y;
     const double e = fma(-tt, y, 1.0);
     const double q = e * fma(0.375, e, 0.5);
     y = fma(y, q, y);
+#if SRBD_K3_EXACT_RSQRT == 3
+    {  // (experiment: one more Newton step on the residual of the refined value)
+      const double t2 = x * y;
+      const double e2 = fma(-t2, y, 1.0);
+      y = fma(y * 0.5, e2, y);
+    }
+#endif
     return x > 0.0 ? y : 0.0;
   }
   __device__ void sweep_factor() {
@@ -1336,6 +1357,9 @@ struct SrbdSolver {
     return alpha;
   }
 
+#ifndef SRBD_K3_EXACT_RSQRT
+#define SRBD_K3_EXACT_RSQRT 0
+#endif
 #ifndef SRBD_K3_PROFILE
 #define SRBD_K3_PROFILE 0   // development: per-sweep clock64 sums in bins 48..52 of the iteration histogram
 #endif
@@ -1488,10 +1512,11 @@ struct SrbdSolver {
 #else
 #define SRBD_K3_BOUNDS __launch_bounds__(32 * v2::kWarps, v2::kMinCtas)
 #endif
-template <int kTma>
+template <int kTma, int kPivot>
 __global__ void SRBD_K3_BOUNDS ipm_srbd_kernel(const SrbdIpmParams p) {
   extern __shared__ __align__(128) double2 smem2[];  // no static shared memory: the tiles start on 128-byte lines
   if (p.gate && *p.gate != p.gate_value) return;
+  if (p.qlist && *p.qcount == 0) return;   // empty rescue list (the usual case)
   double* smem = reinterpret_cast<double*>(smem2);
   int* s_next = reinterpret_cast<int*>(smem + v2::sQ + 16);  // one int per warp behind diag(Q), R
   static_assert(v2::kWarps <= 32, "work-counter slots");
@@ -1513,7 +1538,7 @@ __global__ void SRBD_K3_BOUNDS ipm_srbd_kernel(const SrbdIpmParams p) {
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  SrbdSolver<kTma> S(p, smem, smem + v2::kCtaShared + warp * v2::kWarpShared, blockIdx.x * v2::kWarps + warp);
+  SrbdSolver<kTma, kPivot> S(p, smem, smem + v2::kCtaShared + warp * v2::kWarpShared, blockIdx.x * v2::kWarps + warp);
   S.tiles_init();
   long long it_sum = 0, solves = 0;
   int st_cnt[5] = {0, 0, 0, 0, 0};
@@ -1521,9 +1546,10 @@ __global__ void SRBD_K3_BOUNDS ipm_srbd_kernel(const SrbdIpmParams p) {
   for (;;) {
     if (lane == 0) s_next[warp] = atomicAdd(p.counter, 1);
     __syncwarp();
-    const int qp = s_next[warp];
+    const int idx = s_next[warp];
     __syncwarp();
-    if (qp >= p.B) break;
+    if (idx >= (p.qlist ? *p.qcount : p.B)) break;
+    const int qp = p.qlist ? p.qlist[idx] : idx;
     S.solve_one(qp);
     if (lane == 0) {
       const int it = p.iter[qp], st = p.status[qp];

@@ -51,6 +51,7 @@ struct QpLayout {
   // iterative refinement (ipm_solve.cuh: refine): residual of the linear system and the correction
   int ws_lg, ws_lb, ws_ldl, ws_ldu, ws_lml, ws_lmu, ws_cz, ws_cpi;
   int ws_size;
+  int ws_size_core;   // without the refinement vectors (they come last)
 };
 
 __host__ __device__ inline int stage_nu(const QpLayout& L, int k) { return k < L.N ? L.nu : 0; }
@@ -96,6 +97,7 @@ inline int make_layout(const srbd_qp_dims& d, const int* idxbx, const int* idxbu
   L.ws_rmlb = take(L.ncm); L.ws_rmub = take(L.ncm);
   L.ws_Li = take(L.nu * L.nu); L.ws_Ls = take(L.nx * L.nu); L.ws_lv = take(L.nu);
   L.ws_P = take(L.nx * L.nx); L.ws_p = take(L.nx); L.ws_Lr = take(L.nu * L.nu);
+  L.ws_size_core = (o + 15) & ~15;
   L.ws_lg = take(L.nm); L.ws_lb = take(L.nx); L.ws_ldl = take(L.ncm); L.ws_ldu = take(L.ncm);
   L.ws_lml = take(L.ncm); L.ws_lmu = take(L.ncm); L.ws_cz = take(L.nm); L.ws_cpi = take(L.nx);
   L.ws_size = (o + 15) & ~15;

@@ -533,10 +533,14 @@ def test_stage_record_repeats_the_dense_records(pkg, mode):
 
 @pytest.mark.gpu
 def test_rescue_pass_matches_the_generic_kernel(pkg, orc, monkeypatch):
-    """QP 1007927 of the all-stance workload sits on the rounding floor of the SRBD variant's blocked triangular
-    solves (found by scripts/parity_sweep.py: the variant alone runs to iter_max with res_stat 8e-5, the generic kernel
-    and the oracle converge in 12 iterations).  With the rescue pass (default) the batch reports the generic kernel's
-    result for it — the oracle's iteration count and status — and the batch statistics count every QP exactly once."""
+    """QP 1007927 of the all-stance workload sits on a knife edge of the IPM's rounding floor (found by
+    scripts/parity_sweep.py: the SRBD variant alone runs to iter_max with res_stat 8e-5, the generic kernel, the oracle and
+    the arbiter converge in 12 iterations).  Every rounding of the arithmetic has its own such QPs, about 3 per million
+    (scripts/count_iter_max.py).  The rescue (default) re-solves the QPs on the device-side list, stage 1 in the same
+    tensor-core kernel with the other rounding of the inverse pivots (1.4 ms), stage 2 -- what is still unsolved -- in the
+    generic kernel: the batch reports a CONVERGED solve for it, within the parity tolerance of the oracle's solution, with
+    the oracle's iteration count up to the one iteration by which two roundings may differ on such a QP, and the batch
+    statistics count every QP exactly once.  Nothing else changes."""
     from srbd_nmpc_solver_b200.binding import make_dims
     B, N, first = 64, 20, 1007927 - 20
     w = pkg.workload.srbd_batch(B, N=N, contact_mode="stance", start=first)
@@ -556,9 +560,10 @@ def test_rescue_pass_matches_the_generic_kernel(pkg, orc, monkeypatch):
     (_, st_raw, _), (sol, st, bs) = res["1"], res["0"]
     assert st_raw["status"][20] == 1 and st_raw["iter"][20] == 30       # the variant alone: iter_max
     assert (st["status"] == 0).all() and (ref["status"] == 0).all()
-    assert (st["iter"] == ref["iter"]).all(), (st["iter"], ref["iter"])
-    assert relerr(sol["x"], ref["x"]).max() <= 5e-9
     others = np.arange(B) != 20
+    assert (st["iter"][others] == ref["iter"][others]).all(), (st["iter"], ref["iter"])
+    assert abs(int(st["iter"][20]) - int(ref["iter"][20])) <= 1, (st["iter"][20], ref["iter"][20])
+    assert relerr(sol["x"], ref["x"]).max() <= 5e-9
     assert (st["iter"][others] == st_raw["iter"][others]).all()         # nothing else changed
     assert bs["solves"] == B and bs["iter_sum"] == int(st["iter"].sum()) and bs["status_count"][0] == B
 
