@@ -135,6 +135,11 @@ namespace v2 {
 #ifndef SRBD_K3_GP
 #define SRBD_K3_GP 48
 #endif
+// experiments on the inverse Cholesky pivots of EVERY instantiation (1: 1 / sqrt, 2: CUDA rsqrt(), 3: one more Newton step);
+// the product uses the template parameter kPivot of SrbdSolver instead
+#ifndef SRBD_K3_EXACT_RSQRT
+#define SRBD_K3_EXACT_RSQRT 0
+#endif
 constexpr int kWarps = SRBD_K3_WARPS;
 constexpr int kMinCtas = SRBD_K3_MIN_CTAS;
 // per-stage workspace block (doubles)
@@ -1357,9 +1362,6 @@ struct SrbdSolver {
     return alpha;
   }
 
-#ifndef SRBD_K3_EXACT_RSQRT
-#define SRBD_K3_EXACT_RSQRT 0
-#endif
 #ifndef SRBD_K3_PROFILE
 #define SRBD_K3_PROFILE 0   // development: per-sweep clock64 sums in bins 48..52 of the iteration histogram
 #endif
