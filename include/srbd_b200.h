@@ -312,6 +312,15 @@ int srbd_download_sqp_state(srbd_ctx* ctx, double* alpha, int* converged, double
 int srbd_reset_sqp_state(srbd_ctx* ctx);
 /* linearize + assemble + solve (+ line search if do_line_search) with device-resident inputs */
 int srbd_sqp_iterate(srbd_ctx* ctx, int mode, int do_line_search);
+/* The outer SQP loop of NMPCSolver::controlLoop (NMPC_solver.cpp:367-375) ON THE DEVICE: up to max_iter iterations of
+ * K1 + K2 + K3 + K4 enqueued without a host round trip.  Per problem the loop ends at its first "nmpc solve success"
+ * (:372-374): a converged problem is frozen (K3 skips it, K4 leaves its trajectory alone), and once every problem of the
+ * batch has converged the remaining launches return at once (a device-side counter gates them).  Resets the converged
+ * flags, NOT the carried step length alpha (NMPC_solver.h:104; srbd_reset_sqp_state does).  Asynchronous; read the
+ * outcome with srbd_download_sqp_state (converged flags, merit of the last iteration of each problem) and
+ * srbd_download_sqp_iters (SQP iterations each problem took), the trajectories with srbd_download_traj. */
+int srbd_sqp_solve(srbd_ctx* ctx, int mode, int max_iter);
+int srbd_download_sqp_iters(srbd_ctx* ctx, int* iters);
 
 /* ---- end to end (host buffers in, host buffers out; the `e2e` leg of bench.py) ----------------*/
 int srbd_solve_host(srbd_ctx* ctx, int mode, const double* x, const double* u, const double* xref,

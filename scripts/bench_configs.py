@@ -100,6 +100,21 @@ for spread in (1.0, 0.25):
             note="every SQP iteration = K1+K2+K3+K4 on the device; host reads back 4096 convergence flags + stats per iteration")
         c.close()
 
+# the same workload (spread 0.25) through the DEVICE-side loop (srbd_sqp_solve): no read-back per iteration, converged
+# problems are frozen (K3 skips them), the remaining launches return at once when every problem has converged
+w = pkg.workload.srbd_batch(B, N=N, contact_mode="gait", spread=0.25)
+c = ctx_for(B, N, S4)
+c.upload_traj(w["x"], w["u"], w["xref"], w["x0"], w["contact"]); c.sqp_solve(HARD, 15); c.sync()
+c.reset_sqp_state(); c.upload_traj(w["x"], w["u"], w["xref"], w["x0"], w["contact"]); c.sync()
+t0 = time.perf_counter(); sqp_it = c.sqp_solve(HARD, 15); tt = time.perf_counter() - t0
+conv = c.download_sqp_state()[1]
+out["config4_b4096_n100_full_sqp"]["spread_0.25_device_loop"] = dict(
+    seconds=tt, nmpc_solves_per_s=B / tt, qp_solves=int(sqp_it.sum()), qp_solves_per_s=float(sqp_it.sum()) / tt,
+    problems_converged=int((conv != 0).sum()), sqp_iterations_mean=float(sqp_it.mean()),
+    sqp_iteration_histogram={str(i): int(v) for i, v in enumerate(np.bincount(sqp_it, minlength=16)) if v},
+    note="srbd_sqp_solve: one call, one read-back; a problem leaves the loop at its first 'nmpc solve success' like the reference")
+c.close()
+
 # ---- config 5: one QP, N=50, latency host->host ------------------------------------------------------------------------
 N = 50
 S5 = dict(S8, iter_max=50)

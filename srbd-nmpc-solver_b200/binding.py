@@ -211,6 +211,13 @@ class Context:
     def sqp_iterate(self, mode, do_line_search=False):
         self._ck(self._L.srbd_sqp_iterate(self._h, int(mode), int(bool(do_line_search))))
 
+    def sqp_solve(self, mode, max_iter):
+        """The outer SQP loop on the device (srbd_sqp_solve); returns the SQP iterations each problem took."""
+        self._ck(self._L.srbd_sqp_solve(self._h, int(mode), int(max_iter)))
+        it = np.zeros(self.batch, dtype=np.int32)
+        self._ck(self._L.srbd_download_sqp_iters(self._h, capi.iptr(it)))
+        return it
+
     def solve_host(self, mode, x, u, xref, x0, contact, sol_x, sol_u, it, status):
         """End-to-end call on caller-owned (ideally pinned) host buffers; nothing is allocated here."""
         self._ck(self._L.srbd_solve_host(self._h, int(mode), capi.dptr(x), capi.dptr(u), capi.dptr(xref),

@@ -126,7 +126,7 @@ _EXPORTS = [
     "srbd_upload_traj", "srbd_download_traj", "srbd_linearize", "srbd_assemble",
     "srbd_download_linearization", "srbd_download_qp", "srbd_qp_upload", "srbd_qp_solve",
     "srbd_download_solution", "srbd_download_stats", "srbd_batch_stats_get", "srbd_line_search",
-    "srbd_download_sqp_state", "srbd_reset_sqp_state", "srbd_sqp_iterate", "srbd_solve_host", "srbd_solve_host_async", "srbd_wait", "srbd_solve_host_graph",
+    "srbd_download_sqp_state", "srbd_reset_sqp_state", "srbd_sqp_iterate", "srbd_sqp_solve", "srbd_download_sqp_iters", "srbd_solve_host", "srbd_solve_host_async", "srbd_wait", "srbd_solve_host_graph",
     "srbd_fp64_peak", "srbd_mpc_run", "srbd_out_layout", "srbd_download_packed", "srbd_host_alloc", "srbd_host_free",
 ]
 
@@ -180,6 +180,8 @@ def lib():
     L.srbd_download_sqp_state.argtypes = [vp, c_double_p, c_int_p, c_double_p]
     L.srbd_reset_sqp_state.argtypes = [vp]
     L.srbd_sqp_iterate.argtypes = [vp, C.c_int, C.c_int]
+    L.srbd_sqp_solve.argtypes = [vp, C.c_int, C.c_int]
+    L.srbd_download_sqp_iters.argtypes = [vp, c_int_p]
     L.srbd_solve_host.argtypes = [vp, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p, c_u8_p,
                                   c_double_p, c_double_p, c_int_p, c_int_p]
     L.srbd_solve_host_async.argtypes = [vp, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p, c_u8_p,

@@ -318,6 +318,13 @@ struct LsParams {
   double* alpha;         // [B]
   int* converged;        // [B]
   double* merit;         // [B][3] phi, dphi, theta
+  // device-side SQP loop (srbd_sqp_solve): a QP whose converged flag is already set is left alone (the reference leaves its
+  // loop at the first "nmpc solve success", NMPC_solver.cpp:372-374); the others bump their iteration count and, if still
+  // not converged, the counter that gates the next iteration's kernels
+  int freeze;
+  const int* run_gate;
+  int* active_next;
+  int* sqp_iter;         // [B]
 };
 
 // phi / theta (and optionally the cost gradient dotted with the step) of one stage at (x + a dx, u + a du)
@@ -425,6 +432,8 @@ __global__ void __launch_bounds__(128) line_search_kernel(const LsParams p, cons
   const int lane = threadIdx.x & 31;
   const int q = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (q >= p.B) return;
+  if (p.run_gate && *p.run_gate == 0) return;
+  if (p.freeze && p.converged[q]) return;
   const int N = p.N;
   const double theta_max = 1e-6, theta_min = 5e-10, eta = 1e-4, byta_phi = 1e-6, byta_theta = 1e-6,
                byta_alpha = 0.5, alpha_min = 1e-4;  // NMPC_solver.h:97-103
@@ -459,7 +468,10 @@ __global__ void __launch_bounds__(128) line_search_kernel(const LsParams p, cons
   }
   if (lane == 0) {
     p.alpha[q] = alpha;
-    p.converged[q] = (dphi > -1e-3 && theta < 1e-6) ? 1 : 0;  // NMPC_solver.cpp:267
+    const int conv = (dphi > -1e-3 && theta < 1e-6) ? 1 : 0;  // NMPC_solver.cpp:267
+    p.converged[q] = conv;
+    if (p.sqp_iter) p.sqp_iter[q] += 1;
+    if (p.active_next && !conv) atomicAdd(p.active_next, 1);
     p.merit[3 * (size_t)q + 0] = phi;
     p.merit[3 * (size_t)q + 1] = dphi;
     p.merit[3 * (size_t)q + 2] = theta;

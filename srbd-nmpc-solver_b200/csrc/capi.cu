@@ -54,6 +54,13 @@ struct srbd_ctx {
   int* d_flag = nullptr;
   int* h_flag = nullptr;     // pinned
   bool upload_variant_ok = false;
+  // device-side SQP loop (srbd_sqp_solve): per-iteration counters of the QPs still iterating (gate of the next iteration's
+  // kernels), per-QP iteration counts; sqp_loop: the launches below run gated / frozen
+  int* d_active = nullptr;
+  int* d_sqp_iter = nullptr;
+  int active_alloc = 0;
+  bool sqp_loop = false;
+  const int* cur_gate = nullptr;
   // low-latency host -> host path (srbd_solve_host_graph): the whole pipeline as ONE CUDA graph launch over pinned staging
   cudaGraphExec_t graph_exec = nullptr;
   int graph_mode = -1, graph_contact = -1;
@@ -323,7 +330,7 @@ int srbd_ctx_destroy(srbd_ctx* ctx) {
                   ctx->d_dmask, ctx->d_raw0, ctx->d_x0, ctx->d_xinit, ctx->d_uinit, ctx->d_out, ctx->d_in, ctx->d_model_qp,
                   ctx->d_flag, ctx->d_P, ctx->d_p, ctx->d_K, ctx->d_k,
                   ctx->d_stat, ctx->d_counter, ctx->d_bstats, ctx->d_ws,
-                  ctx->d_ws2, ctx->d_srec, ctx->d_retry, ctx->d_retry2, ctx->d_r0raw, ctx->d_mpc_x, ctx->d_mpc_u, ctx->d_mpc_xcur,
+                  ctx->d_ws2, ctx->d_srec, ctx->d_retry, ctx->d_retry2, ctx->d_active, ctx->d_sqp_iter, ctx->d_r0raw, ctx->d_mpc_x, ctx->d_mpc_u, ctx->d_mpc_xcur,
                   ctx->d_plantA, ctx->d_plantB, ctx->d_plantb, ctx->d_mpc_iter, ctx->d_mpc_status};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -465,6 +472,7 @@ static int launch_linearize(srbd_ctx* ctx, bool raw0) {
   p.B = ctx->B; p.N = ctx->L.N;
   p.x = ctx->d_x; p.u = ctx->d_u; p.x0 = ctx->d_x0abs;
   p.babt = ctx->d_babt; p.defect = ctx->d_defect; p.raw0 = raw0 ? ctx->d_raw0 : nullptr; p.dx0 = ctx->d_x0;
+  p.run_gate = ctx->cur_gate;
   const long long total = (long long)p.B * p.N;
   const int grid = (int)((total + kLinThreads - 1) / kLinThreads);
   linearize_kernel<<<grid, kLinThreads, 0, ctx->stream>>>(p, ctx->d_model);
@@ -488,6 +496,7 @@ static int launch_assemble(srbd_ctx* ctx, int mode, bool dense, const int* qlist
   p.rsq = ctx->d_rsq; p.srec = ctx->d_srec; p.dct = ctx->d_dct; p.d = ctx->d_d; p.dmask = ctx->d_dmask; p.raw0 = ctx->d_raw0;
   p.fcon = nullptr;
   p.qlist = qlist; p.qcount = qcount;
+  p.run_gate = ctx->cur_gate;
   const long long total = (long long)p.B * (p.N + 1);
   int grid = (int)((total + kAsmThreads - 1) / kAsmThreads);
   if (qlist && grid > 2 * ctx->sm_count) grid = 2 * ctx->sm_count;  // a rescue list is short (grid-stride loop inside)
@@ -757,6 +766,7 @@ static int launch_generic(srbd_ctx* ctx, const int* qlist, const int* qcount, co
   if (!qlist && !keep_stats) CU(cudaMemsetAsync(ctx->d_bstats, 0, sizeof(srbd_batch_stats), ctx->stream));
   p.qlist = qlist; p.qcount = qcount;
   p.gate = gate; p.gate_value = gate_value;
+  p.run_gate = ctx->cur_gate; p.frozen = ctx->sqp_loop ? ctx->d_conv : nullptr;
   KernelChoice kc = pick_kernel(L);
   const int grid = qlist ? (ctx->grid < ctx->sm_count ? ctx->grid : ctx->sm_count) : ctx->grid;  // a rescue list is short
   // fewer CTAs than SMs: the workspace of each CTA's QP in its dynamic shared memory, when it fits (IpmParams::ws_in_smem)
@@ -814,7 +824,8 @@ static int solve_srbd_variant(srbd_ctx* ctx, const ModelDev* model, const int* g
   p.B = ctx->B; p.N = L.N; p.a = ctx->args;
   p.babt = ctx->d_babt; p.srec = ctx->d_srec; p.x0 = ctx->d_x0;
   p.model = model; p.ws = ctx->d_ws2;
-  p.gate = gate; p.gate_value = 0; p.ws_size = (L.N + 1) * v2::kStage; p.counter = ctx->d_counter;
+  p.gate = gate; p.gate_value = 0;
+  p.run_gate = ctx->cur_gate; p.frozen = ctx->sqp_loop ? ctx->d_conv : nullptr; p.ws_size = (L.N + 1) * v2::kStage; p.counter = ctx->d_counter;
   p.sol_x = ctx->d_sol_x; p.sol_u = ctx->d_sol_u; p.sol_pi = ctx->d_sol_pi; p.sol_lam = ctx->d_sol_lam; p.sol_t = ctx->d_sol_t;
   p.iter = ctx->d_iter; p.status = ctx->d_status; p.res_max = ctx->d_resmax; p.bstats = ctx->d_bstats;
   if (rescue) {
@@ -1024,6 +1035,10 @@ int srbd_line_search(srbd_ctx* ctx) {
   p.mode = ctx->assembled_mode == SRBD_HARD_INEQ ? SRBD_HARD_INEQ : SRBD_BARRIER_SOFT;
   p.x = ctx->d_x; p.u = ctx->d_u; p.xref = ctx->d_xref; p.contact = ctx->have_contact ? ctx->d_contact : nullptr;
   p.dx = ctx->d_sol_x; p.du = ctx->d_sol_u; p.alpha = ctx->d_alpha; p.converged = ctx->d_conv; p.merit = ctx->d_merit;
+  if (ctx->sqp_loop) {
+    p.freeze = 1; p.run_gate = ctx->cur_gate; p.sqp_iter = ctx->d_sqp_iter;
+    p.active_next = ctx->cur_gate ? const_cast<int*>(ctx->cur_gate) + 1 : ctx->d_active + 1;
+  }
   line_search_kernel<<<(ctx->B + 3) / 4, 128, 0, ctx->stream>>>(p, ctx->d_model);
   ctx->launches++;
   CU(cudaGetLastError());
@@ -1058,6 +1073,44 @@ int srbd_sqp_iterate(srbd_ctx* ctx, int mode, int do_line_search) {
   if (int rc = srbd_qp_solve(ctx)) return rc;
   if (do_line_search)
     if (int rc = srbd_line_search(ctx)) return rc;
+  return SRBD_OK;
+}
+
+int srbd_sqp_solve(srbd_ctx* ctx, int mode, int max_iter) {
+  if (int rc = require_srbd(ctx)) return rc;
+  if (max_iter < 1 || max_iter > 1000) return fail(ctx, SRBD_ERR_ARG, "max_iter out of range");
+  CU(cudaSetDevice(ctx->device));
+  if (max_iter + 2 > ctx->active_alloc) {
+    if (ctx->d_active) cudaFree(ctx->d_active);
+    ctx->d_active = nullptr;
+    CU(dalloc(&ctx->d_active, (size_t)max_iter + 2));
+    ctx->active_alloc = max_iter + 2;
+  }
+  if (!ctx->d_sqp_iter) CU(dalloc(&ctx->d_sqp_iter, (size_t)ctx->B));
+  CU(cudaMemsetAsync(ctx->d_active, 0, (size_t)(max_iter + 2) * sizeof(int), ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_sqp_iter, 0, (size_t)ctx->B * sizeof(int), ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_conv, 0, (size_t)ctx->B * sizeof(int), ctx->stream));
+  // Iteration i runs gated on d_active[i] (the number of QPs iteration i-1 left unconverged; iteration 0 is not gated) and
+  // its line search counts into d_active[i+1]: once every QP has converged the remaining launches return at once.  No
+  // host round trip between the iterations; one read-back (srbd_download_sqp_state / srbd_download_sqp_iters) at the end.
+  int rc = SRBD_OK;
+  ctx->sqp_loop = true;
+  for (int i = 0; i < max_iter && rc == SRBD_OK; ++i) {
+    ctx->cur_gate = i == 0 ? nullptr : ctx->d_active + i;
+    rc = srbd_sqp_iterate(ctx, mode, 1);
+  }
+  ctx->sqp_loop = false;
+  ctx->cur_gate = nullptr;
+  return rc;
+}
+
+int srbd_download_sqp_iters(srbd_ctx* ctx, int* iters) {
+  if (int rc = require_srbd(ctx)) return rc;
+  if (!iters) return SRBD_ERR_ARG;
+  if (!ctx->d_sqp_iter) return fail(ctx, SRBD_ERR_STATE, "srbd_sqp_solve first");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(iters, ctx->d_sqp_iter, (size_t)ctx->B * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
   return SRBD_OK;
 }
 

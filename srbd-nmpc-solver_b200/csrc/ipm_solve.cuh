@@ -54,6 +54,9 @@ struct IpmParams {
   // every phase of every stage (about sixty per stage and iteration: 14.1 ms for one N = 20 SRBD QP against 1.4 ms in
   // the tensor-core variant); with the iterate, the residuals and the factors on chip those are shared-memory loads.
   int ws_in_smem;
+  // device-side SQP loop (srbd_sqp_solve): return at once if *run_gate == 0; skip QPs whose frozen[] flag is set
+  const int* run_gate;
+  const int* frozen;
 };
 
 // compile-time dimension policy (loops unroll, index math folds) ...
@@ -1205,6 +1208,7 @@ __global__ void __launch_bounds__(32) ipm_solve_kernel(const IpmParams p) {
   __shared__ int s_next;
   extern __shared__ __align__(16) double ws_dyn[];   // the workspace of this CTA's QP when p.ws_in_smem
   if (p.gate && *p.gate != p.gate_value) return;
+  if (p.run_gate && *p.run_gate == 0) return;
   if (p.qlist && *p.qcount == 0) return;  // empty rescue list (the usual case): nothing to set up
   Solver<D> S(p, smem, sidx, ws_dyn);
   // per-CTA partial batch statistics (fused epilogue; one set of atomics per CTA at the end)
@@ -1219,6 +1223,7 @@ __global__ void __launch_bounds__(32) ipm_solve_kernel(const IpmParams p) {
     __syncwarp();
     if (idx >= n_work) break;
     const int qp = p.qlist ? p.qlist[idx] : idx;
+    if (p.frozen && p.frozen[qp]) continue;
     S.solve_one(qp);
     if (threadIdx.x == 0) {
       const int it = p.iter[qp], st = p.status[qp];

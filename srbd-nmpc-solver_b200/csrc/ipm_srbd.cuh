@@ -69,6 +69,10 @@ struct SrbdIpmParams {
   // device-side dispatch (QP-level uploads, capi.cu): run only if *gate == gate_value
   const int* gate;
   int gate_value;
+  // device-side SQP loop (srbd_sqp_solve): return at once if *run_gate == 0; skip QPs whose frozen[] flag is set (their NMPC
+  // problem has converged: the reference leaves its SQP loop then, NMPC_solver.cpp:372-374)
+  const int* run_gate;
+  const int* frozen;
 };
 
 namespace v2 {
@@ -1518,6 +1522,7 @@ template <int kTma, int kPivot>
 __global__ void SRBD_K3_BOUNDS ipm_srbd_kernel(const SrbdIpmParams p) {
   extern __shared__ __align__(128) double2 smem2[];  // no static shared memory: the tiles start on 128-byte lines
   if (p.gate && *p.gate != p.gate_value) return;
+  if (p.run_gate && *p.run_gate == 0) return;
   if (p.qlist && *p.qcount == 0) return;   // empty rescue list (the usual case)
   double* smem = reinterpret_cast<double*>(smem2);
   int* s_next = reinterpret_cast<int*>(smem + v2::sQ + 16);  // one int per warp behind diag(Q), R
@@ -1552,6 +1557,7 @@ __global__ void SRBD_K3_BOUNDS ipm_srbd_kernel(const SrbdIpmParams p) {
     __syncwarp();
     if (idx >= (p.qlist ? *p.qcount : p.B)) break;
     const int qp = p.qlist ? p.qlist[idx] : idx;
+    if (p.frozen && p.frozen[qp]) continue;
     S.solve_one(qp);
     if (lane == 0) {
       const int it = p.iter[qp], st = p.status[qp];

@@ -210,6 +210,7 @@ struct LinParams {
   double* defect;      // [B][N][12]
   double* raw0;        // [B][raw0 stride]: A0, B0, b0 (column-major), rest written by K2
   double* dx0;         // [B][12]
+  const int* run_gate; // device-side SQP loop (srbd_sqp_solve): return at once if *run_gate == 0 (every QP converged)
 };
 
 constexpr int kLinCompact = 40;  // 18 (drdot/d[r,l]) + 3 (F sum) + 6 (d0,d1) + 12 (b) + pad
@@ -281,6 +282,7 @@ __host__ __device__ __forceinline__ double babt_elem(const double* c, int i, int
 __global__ void __launch_bounds__(kLinThreads, SRBD_K1_MIN_CTAS) linearize_kernel(const LinParams p, const ModelDev* __restrict__ md) {
   __shared__ double sc[kLinThreads][kLinCompact + 1];
   __shared__ srbd_model_params sm;
+  if (p.run_gate && *p.run_gate == 0) return;
   {
     const int nw = sizeof(srbd_model_params) / sizeof(double);
     const double* src = reinterpret_cast<const double*>(&md->m);
@@ -450,6 +452,7 @@ struct AsmParams {
   // optional work list: assemble only the QPs qlist[0 .. *qcount) (dense records for the rescue list of K3, capi.cu)
   const int* qlist;
   const int* qcount;
+  const int* run_gate; // device-side SQP loop: return at once if *run_gate == 0
 };
 
 constexpr int kAsmThreads = 64;
@@ -538,6 +541,7 @@ __global__ void __launch_bounds__(kAsmThreads) assemble_kernel(const AsmParams p
   __shared__ double sAc[24 * 12];
   __shared__ double sQ[12], sQf[12];
   __shared__ double sR;
+  if (p.run_gate && *p.run_gate == 0) return;
   for (int i = threadIdx.x; i < 288; i += blockDim.x) sAc[i] = md->Ac[i];
   if (threadIdx.x < 12) { sQ[threadIdx.x] = md->m.Q[threadIdx.x]; sQf[threadIdx.x] = md->m.Qf[threadIdx.x]; }
   if (threadIdx.x == 0) sR = md->m.R;

@@ -28,6 +28,7 @@ struct NMPCConfig {  // config/mpc_option.yaml:1-18
   int batch = 1;          // new: independent problems solved together
   int assemble_mode = SRBD_BARRIER_SOFT;  // the reference's formulation (constraints as relaxed barriers)
   int device = 0;
+  bool device_sqp_loop = true;  // new: the outer SQP loop runs on the device (false: host-driven, one read-back per iteration)
 };
 
 class NMPCSolver {
@@ -63,10 +64,22 @@ class NMPCSolver {
       setupReference();
       last_sqp_iters_ = 0;
       check(srbd_upload_traj(ctx_, x_nmpc_.data(), u_nmpc_.data(), x_ref_.data(), x0_.data(), nullptr), "srbd_upload_traj");
-      for (int i = 0; i < cfg_.sqp_max_loop; ++i) {
-        prepareQpStructures();
-        solveQpProblems();
-        if (checkConvergence()) break;
+      if (cfg_.device_sqp_loop) {
+        // the whole SQP loop (:367-375) on the device: no host round trip between the iterations, every problem leaves
+        // the loop at its own first "nmpc solve success" (srbd_sqp_solve)
+        check(srbd_sqp_solve(ctx_, cfg_.assemble_mode, cfg_.sqp_max_loop), "srbd_sqp_solve");
+        std::vector<int> it(B_), conv(B_);
+        check(srbd_download_sqp_iters(ctx_, it.data()), "srbd_download_sqp_iters");
+        check(srbd_download_sqp_state(ctx_, nullptr, conv.data(), nullptr), "srbd_download_sqp_state");
+        bool all = true;
+        for (int b = 0; b < B_; ++b) { if (it[b] > last_sqp_iters_) last_sqp_iters_ = it[b]; all = all && conv[b]; }
+        if (all) std::cout << "nmpc solve success!" << std::endl;
+      } else {
+        for (int i = 0; i < cfg_.sqp_max_loop; ++i) {
+          prepareQpStructures();
+          solveQpProblems();
+          if (checkConvergence()) break;
+        }
       }
       check(srbd_download_traj(ctx_, x_nmpc_.data(), u_nmpc_.data()), "srbd_download_traj");
     }

@@ -812,3 +812,43 @@ def test_low_latency_graph_path_config5(pkg, orc):
                                w["contact"])
             assert stt[0] == 0 and ref["status"][0] == 0 and git == int(ref["iter"][0]), (start, git, ref["iter"])
             assert relerr(gx, ref["x"]).max() <= 5e-9 and relerr(gu, ref["u"]).max() <= 5e-8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,B,mode,spread", [(20, 48, 0, 0.25), (100, 32, 1, 0.25)])
+def test_device_side_sqp_loop(pkg, N, B, mode, spread):
+    """srbd_sqp_solve: the outer SQP loop of NMPCSolver::controlLoop (NMPC_solver.cpp:367-375) on the device, without a host
+    round trip per iteration.  Against the host-driven loop (srbd_sqp_iterate + convergence read-back) on the same problems:
+    every problem must leave the loop at the SAME iteration (its first "nmpc solve success") with a BIT-IDENTICAL
+    trajectory (same kernels, same inputs: K3's result for a QP does not depend on which other QPs are still active), and
+    problems that never converge must end where 15 host-driven iterations end."""
+    iters = 15
+    settings = dict(SETTINGS, iter_max=50, tol_stat=1e-6) if N > 20 else dict(SETTINGS, tol_stat=1e-4, tol_eq=1e-4, tol_ineq=1e-4, tol_comp=1e-4)
+    w = pkg.workload.srbd_batch(B, N=N, contact_mode="gait" if mode else "stance", spread=spread, start=9000)
+    first = np.full(B, -1)
+    snap_x, snap_u = np.zeros((B, N + 1, 12)), np.zeros((B, N, 12))
+    with make_ctx(pkg, B, N, settings=settings) as ctx:
+        ctx.upload_traj(w["x"], w["u"], w["xref"], w["x0"], w["contact"])
+        for it in range(iters):            # host-driven reference loop; converged problems keep their snapshot
+            ctx.sqp_iterate(mode, do_line_search=True)
+            conv = ctx.download_sqp_state()[1]
+            gx, gu = ctx.download_traj()
+            new = (conv != 0) & (first < 0)
+            snap_x[new], snap_u[new] = gx[new], gu[new]
+            first[new] = it + 1
+        never = first < 0
+        snap_x[never], snap_u[never] = gx[never], gu[never]
+    with make_ctx(pkg, B, N, settings=settings) as ctx:
+        ctx.upload_traj(w["x"], w["u"], w["xref"], w["x0"], w["contact"])
+        l0 = ctx.launch_count
+        sqp_it = ctx.sqp_solve(mode, iters)
+        conv = ctx.download_sqp_state()[1]
+        dx, du = ctx.download_traj()
+    assert ((conv != 0) == (first > 0)).all()
+    assert (sqp_it[first > 0] == first[first > 0]).all(), (sqp_it, first)
+    assert (sqp_it[never] == iters).all()
+    assert (first > 0).sum() >= B // 4, first            # the workload does converge for a good part of the batch
+    # A frozen problem keeps the trajectory of its converging iteration; in the host-driven loop alpha of a converged problem
+    # keeps being used, so only problems are comparable up to their own convergence -- which is what the snapshots hold.
+    # Problems that never converge interact with nothing and must match after 15 iterations as well.
+    assert np.array_equal(dx, snap_x) and np.array_equal(du, snap_u)
