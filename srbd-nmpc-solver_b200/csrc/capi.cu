@@ -500,8 +500,13 @@ static int launch_assemble(srbd_ctx* ctx, int mode, bool dense, const int* qlist
   const long long total = (long long)p.B * (p.N + 1);
   int grid = (int)((total + kAsmThreads - 1) / kAsmThreads);
   if (qlist && grid > 2 * ctx->sm_count) grid = 2 * ctx->sm_count;  // a rescue list is short (grid-stride loop inside)
-  if (dense) assemble_kernel<true><<<grid, kAsmThreads, 0, ctx->stream>>>(p, ctx->d_model);
-  else assemble_kernel<false><<<grid, kAsmThreads, 0, ctx->stream>>>(p, ctx->d_model);
+  if (mode == SRBD_HARD_INEQ) {
+    if (dense) assemble_kernel<true, SRBD_HARD_INEQ><<<grid, kAsmThreads, 0, ctx->stream>>>(p, ctx->d_model);
+    else assemble_kernel<false, SRBD_HARD_INEQ><<<grid, kAsmThreads, 0, ctx->stream>>>(p, ctx->d_model);
+  } else {
+    if (dense) assemble_kernel<true, SRBD_BARRIER_SOFT><<<grid, kAsmThreads, 0, ctx->stream>>>(p, ctx->d_model);
+    else assemble_kernel<false, SRBD_BARRIER_SOFT><<<grid, kAsmThreads, 0, ctx->stream>>>(p, ctx->d_model);
+  }
   ctx->launches++;
   CU(cudaGetLastError());
   return SRBD_OK;

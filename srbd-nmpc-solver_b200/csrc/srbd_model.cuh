@@ -478,13 +478,47 @@ __device__ __forceinline__ bool row_soft_in_hard_mode(int g) {
 // are exact zeros, so the sum is bit-identical to the full one.
 __device__ __forceinline__ double rblock_elem(const double* sAc, const double* c, int i, int j, double R, int g_lo,
                                               int g_cnt) {
+  // (explicit roundings: the hoisted form of the throughput path below must give the same bits)
   double s = 0.0;
   if (i / 6 == j / 6) {
     const int g0 = 12 * (i / 6) + g_lo;
-    for (int g = g0; g < g0 + g_cnt; ++g) s += (sAc[g * 12 + i] * c[g]) * sAc[g * 12 + j];
+    for (int g = g0; g < g0 + g_cnt; ++g) s = __fma_rn(__dmul_rn(sAc[g * 12 + i], c[g]), sAc[g * 12 + j], s);
   }
-  return (i == j ? R : 0.0) + s;
+  return __dadd_rn(i == j ? R : 0.0, s);
 }
+// The R tile of the compact stage record in HARD_INEQ mode with everything that does not depend on the stage hoisted out
+// of the per-item loop: a lane owns up to four elements (i, j) of the tile (panel prefixes 16 + 32 + 48); only the two
+// relaxed rows g0 = 12 leg + 10, g0 + 1 of the common leg contribute, R_ij = R delta_ij + (a_i0 c_g0) a_j0 + (a_i1 c_g1) a_j1
+// -- the same operations in the same order as rblock_elem.
+struct RTileHard {
+  double ai0[4], aj0[4], ai1[4], aj1[4], rd[4];
+  int g0[4], off[4];
+  bool valid[4];
+  __device__ __forceinline__ void init(const double* sAc, double R, int lane) {
+#pragma unroll
+    for (int sidx = 0; sidx < 4; ++sidx) {
+      const int pnl = sidx < 3 ? sidx : 2, sl = sidx < 3 ? 0 : 1;
+      const int e = lane + 32 * sl, j = e >> 2, i = 4 * pnl + (e & 3);
+      valid[sidx] = j < 4 * pnl + 4;
+      off[sidx] = (pnl == 0 ? 0 : (pnl == 1 ? 16 : 48)) + e;
+      const bool same = valid[sidx] && (i / 6 == j / 6);
+      const int g = same ? 12 * (i / 6) + 10 : 10;
+      g0[sidx] = g;
+      ai0[sidx] = same ? sAc[g * 12 + i] : 0.0; aj0[sidx] = same ? sAc[g * 12 + j] : 0.0;
+      ai1[sidx] = same ? sAc[(g + 1) * 12 + i] : 0.0; aj1[sidx] = same ? sAc[(g + 1) * 12 + j] : 0.0;
+      rd[sidx] = (valid[sidx] && i == j) ? R : 0.0;
+    }
+  }
+  __device__ __forceinline__ void write(double* srec, const double* c) const {
+#pragma unroll
+    for (int sidx = 0; sidx < 4; ++sidx)
+      if (valid[sidx]) {
+        double t = __fma_rn(__dmul_rn(ai0[sidx], c[g0[sidx]]), aj0[sidx], 0.0);
+        t = __fma_rn(__dmul_rn(ai1[sidx], c[g0[sidx] + 1]), aj1[sidx], t);
+        srec[off[sidx]] = __dadd_rn(rd[sidx], t);
+      }
+  }
+};
 // One RSQrq record (28 x 24 panel-major: 7 panels of 96 doubles, 3 per lane and panel).  TYPE 0: first stage
 // (nu = 12, nx = 0), 1: interior, 2: last stage (nu = 0, nx = 12): with the panel and the stage type known at compile
 // time most elements fold to a stored zero.
@@ -533,7 +567,9 @@ __device__ __forceinline__ void write_rsq(double* dst, double* srec, const doubl
   if (lane < 12) { srec[96 + lane] = 0.0; srec[132 + lane] = 0.0; }
 }
 
-template <bool DENSE>
+// MODE: the assemble mode as a template parameter (p.mode must equal it): the throughput instantiation <false, HARD_INEQ>
+// skips the barrier of the hard rows and writes the R tile from hoisted coefficients
+template <bool DENSE, int MODE>
 __global__ void __launch_bounds__(kAsmThreads) assemble_kernel(const AsmParams p, const ModelDev* __restrict__ md) {
   // compact per item: [0..24) ddb (barrier curvature per row, 0 for hard rows), [24..36) r, [36..48) q,
   // [48..72) lg = -f, stage kind in sk[]
@@ -581,13 +617,15 @@ __global__ void __launch_bounds__(kAsmThreads) assemble_kernel(const AsmParams p
         }
         const double f = s + bc;
         if (p.fcon) p.fcon[((size_t)q * p.N + k) * 24 + g] = f;
-        double db, ddb;
-        barrier_fn(f, m.mu_b, m.theta_b, &db, &ddb);
-        if (p.mode == SRBD_HARD_INEQ && !row_soft_in_hard_mode(g)) { db = 0.0; ddb = 0.0; }
+        double db = 0.0, ddb = 0.0;
+        const bool hard_row = MODE == SRBD_HARD_INEQ && !row_soft_in_hard_mode(g);
+        if (!hard_row) barrier_fn(f, m.mu_b, m.theta_b, &db, &ddb);
         c[g] = ddb;
         c[48 + g] = -f;
+        if (!hard_row) {   // (a hard row adds exact zeros)
 #pragma unroll
-        for (int j = 0; j < 12; ++j) r[j] += sAc[g * 12 + j] * db;
+          for (int j = 0; j < 12; ++j) r[j] += sAc[g * 12 + j] * db;
+        }
       }
 #pragma unroll
       for (int i = 0; i < 12; ++i) {
@@ -609,7 +647,10 @@ __global__ void __launch_bounds__(kAsmThreads) assemble_kernel(const AsmParams p
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g_lo = p.mode == SRBD_HARD_INEQ ? 10 : 0, g_cnt = p.mode == SRBD_HARD_INEQ ? 2 : 12;
+  constexpr int g_lo = MODE == SRBD_HARD_INEQ ? 10 : 0, g_cnt = MODE == SRBD_HARD_INEQ ? 2 : 12;
+  constexpr bool kFast = !DENSE && MODE == SRBD_HARD_INEQ;
+  RTileHard rt;
+  if (kFast) rt.init(sAc, sR, lane);
   const long long it0 = item0 + warp * 32;
   int k = (int)(it0 % S);
   for (int rI = 0; rI < 32; ++rI, k = (k == p.N ? 0 : k + 1)) {
@@ -622,7 +663,12 @@ __global__ void __launch_bounds__(kAsmThreads) assemble_kernel(const AsmParams p
     // RSQrq: 28 x 24 panel-major
     double* dst = DENSE ? p.rsq + (size_t)it * (28 * 24) : nullptr;
     double* sr = p.srec + (size_t)it * kSrec;
-    if (k == 0) write_rsq<0, DENSE>(dst, sr, c, sAc, sQ, sQf, sR, lane, g_lo, g_cnt);
+    if (kFast && k < p.N) {
+      rt.write(sr, c);
+      const int n = k == 0 ? 12 : 24;
+      if (lane < 24) sr[108 + lane] = lane < n ? (lane < 12 ? c[24 + lane] : c[36 + (lane - 12)]) : 0.0;
+      if (lane < 12) { sr[96 + lane] = 0.0; sr[132 + lane] = 0.0; }
+    } else if (k == 0) write_rsq<0, DENSE>(dst, sr, c, sAc, sQ, sQf, sR, lane, g_lo, g_cnt);
     else if (k < p.N) write_rsq<1, DENSE>(dst, sr, c, sAc, sQ, sQf, sR, lane, g_lo, g_cnt);
     else write_rsq<2, DENSE>(dst, sr, c, sAc, sQ, sQf, sR, lane, g_lo, g_cnt);
     // DCt (n x 24): D^T = Ac^T in the u rows, C = 0; d = [lg | 0 | 0(-ug) | 0], masks
@@ -642,8 +688,8 @@ __global__ void __launch_bounds__(kAsmThreads) assemble_kernel(const AsmParams p
       for (int e = lane; e < 48; e += 32) {
         const bool lower = e < 24;
         const int g = lower ? e : e - 24;
-        const bool hard = (p.mode == SRBD_HARD_INEQ) && !row_soft_in_hard_mode(g);
-        const double dvv = (lower && p.mode == SRBD_HARD_INEQ) ? c[48 + g] : 0.0;
+        const bool hard = (MODE == SRBD_HARD_INEQ) && !row_soft_in_hard_mode(g);
+        const double dvv = (lower && MODE == SRBD_HARD_INEQ) ? c[48 + g] : 0.0;
         const double dkk = (lower && hard) ? 1.0 : 0.0;
         if (DENSE) { dv[e] = dvv; dk[e] = dkk; }
         if (lower) { sr[144 + g] = dvv; sr[168 + g] = dkk; }
