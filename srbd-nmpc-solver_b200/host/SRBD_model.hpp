@@ -57,7 +57,7 @@ class SRBDModel {
   }
   // SRBD_model.cpp:237-260 -> K2 (rows of the hard-inequality assembly: D = Ac, lg = -(Ac u + b))
   void GetConstrain(const Vec& u, Mat& Ac, Mat& f) {
-    Vec x(12);
+    Vec x = Vec::Zero(12);   // (the constraint rows do not depend on the state; zero-initialised for real Eigen too)
     stage(x, x, u);
     check(srbd_linearize(ctx_), "srbd_linearize");
     check(srbd_assemble(ctx_, SRBD_HARD_INEQ), "srbd_assemble");
