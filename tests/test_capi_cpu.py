@@ -73,3 +73,28 @@ def test_workload_is_shard_invariant(pkg):
         assert np.array_equal(full[k], np.concatenate([a[k], b[k]]))
     assert full["contact"].sum(axis=2).min() >= 1
     assert np.linalg.norm(full["x0"][:, :3], axis=1).min() >= 1e-2 - 1e-15
+
+
+def test_ipm_args_set_mode(pkg, lib):
+    """srbd_ipm_args_set_mode: the hidden constants of d_ocp_qp_ipm_arg_set_default(mode) this implementation honours
+    (hpipm-cpp's HpipmMode: 0 SpeedAbs, 1 Speed, 2 Balance, 3 Robust); the public fields are left alone."""
+    want = {0: (0, 0, 0), 1: (1, 0, 0), 2: (1, 0, 2), 3: (1, 0, 4)}
+    for mode, (cpc, ip, ic) in want.items():
+        a = pkg.default_ipm_args(iter_max=77, tol_stat=3e-5)
+        assert lib.srbd_ipm_args_set_mode(C.byref(a), mode) == 0
+        assert (a.cond_pred_corr, a.itref_pred_max, a.itref_corr_max) == (cpc, ip, ic)
+        assert a.iter_max == 77 and a.tol_stat == 3e-5 and a.itref_abs == 1.0 and a.itref_rel == 1e-3
+    a = pkg.default_ipm_args()
+    assert lib.srbd_ipm_args_set_mode(C.byref(a), 7) != 0
+
+
+def test_workload_spread(pkg):
+    """spread pulls the start states towards the reference's upright pose; spread = 1 is the config-2/3 generator itself."""
+    a = pkg.workload.srbd_batch(16, N=5, contact_mode="gait")
+    b = pkg.workload.srbd_batch(16, N=5, contact_mode="gait", spread=1.0)
+    c = pkg.workload.srbd_batch(16, N=5, contact_mode="gait", spread=0.25)
+    for k in a:
+        assert np.array_equal(a[k], b[k])
+    up = np.zeros(12); up[8] = 1.0
+    assert np.allclose(c["x0"] - up, 0.25 * (a["x0"] - up)) and np.array_equal(c["contact"], a["contact"])
+    assert np.allclose(c["xref"][:, 0, [2, 6, 7]], 0.25 * a["xref"][:, 0, [2, 6, 7]])

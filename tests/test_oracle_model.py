@@ -213,3 +213,28 @@ def test_reference_sqp_loop(pkg, orc):
     assert alphas[:6] == [1.0] * 6 and alphas[6:] == [0.5] * 5
     u0_expected = [54.37, 48.28, 100.32, 4.46, 24.94, 5.55, 63.53, 59.05, 122.50, 4.46, 25.97, 6.28]
     assert np.allclose(u[0], u0_expected, atol=0.02)
+
+
+def test_line_search_merit_by_assemble_mode(pkg, orc):
+    """orc_line_search_mode: in SRBD_HARD_INEQ only the rows the assembly keeps as a relaxed barrier (+-x^T tau of each
+    contact) enter phi / dphi -- the hard rows are constraints of the QP, not cost terms; mode 0 is the reference
+    (NMPC_solver.cpp:166-187: all 24 rows).  The constraint violation theta does not depend on the mode."""
+    N = 6
+    w = pkg.workload.srbd_batch(1, N=N, contact_mode="gait", spread=0.25)
+    m = orc.model_params(N)
+    rng = np.random.default_rng(2)
+    dx, du = 1e-3 * rng.standard_normal((N + 1, 12)), 1e-2 * rng.standard_normal((N, 12))
+    outs = [orc.line_search(m, N, w["x"][0], w["u"][0], w["xref"][0], dx, du, 1.0, contact=w["contact"][0], mode=md)
+            for md in (0, 1)]
+    (_, _, _, _, m0), (_, _, _, _, m1) = outs
+    assert m0[2] == m1[2] and m0[2] > 0.0                   # theta
+    assert m0[0] != m1[0] and m0[1] != m1[1]                # phi, dphi
+    # the difference of phi is the barrier of the 20 hard rows: -mu_b log(v) for v > theta_b etc.: recompute it
+    diff = 0.0
+    for k in range(N):
+        Ac, f = orc.constraint(m, w["u"][0, k], stance=w["contact"][0, k])
+        for g in range(24):
+            if g % 12 in (10, 11):
+                continue
+            diff += orc.barrier(float(f[g]), m.mu_b, m.theta_b)[0]
+    assert abs((m0[0] - m1[0]) - diff) <= 1e-9 * max(1.0, abs(diff))
