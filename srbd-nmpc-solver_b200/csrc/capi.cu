@@ -795,10 +795,17 @@ static int launch_generic(srbd_ctx* ctx, const int* qlist, const int* qcount, co
 // K3 for QPs assembled by K2: the SRBD throughput variant (same algorithm as the generic kernel)
 static int solve_srbd_variant(srbd_ctx* ctx, const ModelDev* model, const int* gate = nullptr) {
   const QpLayout& L = ctx->L;
+  constexpr int kTeamSmem = v2::kSmemBytes + kTeamShared * 8;
+  // LATENCY mode: with fewer QPs than SMs every QP gets a whole CTA (the team instantiation: the residual sweep split over
+  // the warps, bit-identical results).  SRBD_K3_TEAM=0: one warp per QP as in the throughput mode.
+  const char* te = std::getenv("SRBD_K3_TEAM");
+  const bool team = ctx->B < ctx->sm_count && !(te && te[0] == '0');
   if (!ctx->d_ws2) {
     CU(cudaFuncSetAttribute(ipm_srbd_kernel<SRBD_K3_TMA, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes));
     CU(cudaFuncSetAttribute(ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes));
     CU(cudaFuncSetAttribute(ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes));
+    CU(cudaFuncSetAttribute(ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 0, v2::kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTeamSmem));
+    CU(cudaFuncSetAttribute(ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 1, v2::kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTeamSmem));
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ipm_srbd_kernel<SRBD_K3_TMA, 0>, 32 * v2::kWarps, v2::kSmemBytes));
     if (occ < 1) return fail(ctx, SRBD_ERR_CUDA, "ipm_srbd_kernel does not fit on this device");
@@ -840,7 +847,8 @@ static int solve_srbd_variant(srbd_ctx* ctx, const ModelDev* model, const int* g
   CU(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
   CU(cudaMemsetAsync(ctx->d_bstats, 0, sizeof(srbd_batch_stats), ctx->stream));
   // batches of fewer QPs than SMs have nothing to hide a bulk copy's latency behind: the cp.async-only instantiation
-  if (ctx->B < ctx->sm_count) ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 0><<<ctx->grid2, 32 * v2::kWarps, v2::kSmemBytes, ctx->stream>>>(p);
+  if (team) ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 0, v2::kWarps><<<ctx->B, 32 * v2::kWarps, kTeamSmem, ctx->stream>>>(p);
+  else if (ctx->B < ctx->sm_count) ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 0><<<ctx->grid2, 32 * v2::kWarps, v2::kSmemBytes, ctx->stream>>>(p);
   else ipm_srbd_kernel<SRBD_K3_TMA, 0><<<ctx->grid2, 32 * v2::kWarps, v2::kSmemBytes, ctx->stream>>>(p);
   ctx->launches++;
   CU(cudaGetLastError());
@@ -857,7 +865,8 @@ static int solve_srbd_variant(srbd_ctx* ctx, const ModelDev* model, const int* g
     CU(cudaMemsetAsync(ctx->d_retry2 + ctx->B, 0, sizeof(int), ctx->stream));
     CU(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
     const int g1 = ctx->grid2 < ctx->sm_count ? ctx->grid2 : ctx->sm_count;
-    ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 1><<<g1, 32 * v2::kWarps, v2::kSmemBytes, ctx->stream>>>(r);
+    if (team) ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 1, v2::kWarps><<<ctx->B, 32 * v2::kWarps, kTeamSmem, ctx->stream>>>(r);
+    else ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 1><<<g1, 32 * v2::kWarps, v2::kSmemBytes, ctx->stream>>>(r);
     ctx->launches++;
     CU(cudaGetLastError());
     // Stage 2: what is still on the list goes to the generic kernel (row-by-row substitution, no block inverses), which

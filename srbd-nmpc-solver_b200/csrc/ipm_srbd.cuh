@@ -267,7 +267,10 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b,
 // to iter_max in one flavour and not in the other (scripts/count_iter_max.py: 2 + 1 per 2 x 1048576 QPs with flavour 0,
 // 1 + 1 OTHER ones with flavour 1, 4 + 0 with an extra Newton step): the first rescue stage re-solves the listed QPs
 // with flavour 1 at tensor-core speed (1.4 ms for one QP instead of 14-17 ms in the generic kernel).
-template <int kTma, int kPivot>
+// kTeam: 0 = one warp per QP (throughput); n > 0 = LATENCY mode, the n warps of the CTA work on ONE QP: the residual sweep
+// (no recursion: a fifth of a solve) is split over them by stage, the four Riccati recursions stay on warp 0.  Results are
+// bit-identical to kTeam = 0 (same operations per element; the duality measure is summed in the original order).
+template <int kTma, int kPivot, int kTeam>
 struct SrbdSolver {
   const SrbdIpmParams& p;
   int lane, q, N;
@@ -279,6 +282,8 @@ struct SrbdSolver {
   const double* sG;   // current BAbt tile
   const double* sF;   // current factor tile
   const double* sR;   // current R tile
+  int wid;            // warp of the CTA (team mode: 0 = leader)
+  double* cred;       // CTA-shared scratch of the team: [kTeam][6] partial norms | broadcast slots
   // fragment coordinates of this lane (see the header comment)
   int fr, ft, fpi;
   int offS[5];        // index into the 42 D^T Gamma D sums of this lane's element of the u-block fragments, or -1
@@ -290,6 +295,8 @@ struct SrbdSolver {
     cW = cta + v2::sW;
     cQ = cta + v2::sQ;
     sm = warp_sm;
+    wid = threadIdx.x >> 5;
+    cred = cta + v2::kCtaShared;
     sG = sm; sF = sm + v2::wF0; sR = sm + v2::wR0;
     fr = lane >> 2; ft = lane & 3; fpi = (fr >> 1) + 4 * (fr & 1);
 #if SRBD_K3_WBASE
@@ -1183,6 +1190,85 @@ struct SrbdSolver {
     return v;
   }
   __device__ void residuals(double res[4], double& mu, int nc_mask, bool do_update, double sp, double sd) {
+    double acc[5];
+    residual_sweep(0, 1, do_update, sp, sd, acc);
+    const double ng_ = acc[0], nb_ = acc[1], nd_ = acc[2], nm_ = acc[3], smu = acc[4];
+    const double flag = warp_sum((ng_ != ng_ || nb_ != nb_ || nd_ != nd_ || nm_ != nm_) ? 1.0 : 0.0);
+    res[0] = warp_max(ng_ == ng_ ? ng_ : 0.0);
+    res[1] = warp_max(nb_ == nb_ ? nb_ : 0.0);
+    res[2] = warp_max(nd_ == nd_ ? nd_ : 0.0);
+    res[3] = warp_max(nm_ == nm_ ? nm_ : 0.0);
+    if (flag > 0.0) res[0] = res[0] + __longlong_as_double(0x7ff8000000000000LL);
+    mu = warp_sum(smu) / (double)nc_mask;
+    __syncwarp();
+  }
+  // Team mode: (A) every warp applies the variable update to its stages in place (same expressions as updated()), (B) after
+  // a CTA barrier every warp runs the residual sweep over its stages on the stored iterate, (C) the partial norms meet in
+  // shared memory, the leader re-sums res_m in stage order for mu.  Every warp returns the same res[] and mu.
+  __device__ void residuals_team(double res[4], double& mu, int nc_mask, bool do_update, double sp, double sd) {
+    if (do_update) {
+      for (int k = wid; k <= N; k += kTeam) {
+        const int n = (k < N ? 12 : 0) + (k > 0 ? 12 : 0);
+        if (lane < n) {
+          double z = ws_ld(wsc(k, v2::oZ));
+          z += sp * ws_ld(wsc(k, v2::oDZ));
+          wsc(k, v2::oZ)[0] = z;
+        }
+        if (k < N) {
+          if (lane < 12) {
+            double v = ws_ld(wsc(k, v2::oPI));
+            v += sd * ws_ld(wsc(k, v2::oDPI));
+            wsc(k, v2::oPI)[0] = v;
+          }
+          if (lane < 24) {
+            double tt = ws_ld(wsc(k, v2::oT)), ll = ws_ld(wsc(k, v2::oLAM));
+            const double mk = __ldg(gMaskL(k));
+            tt += sp * ws_ld(wsc(k, v2::oDT));
+            ll += sd * ws_ld(wsc(k, v2::oDLAM));
+            if (p.a.t_lam_min == 2 && mk != 0.0) {
+              tt = tt < p.a.t_min ? p.a.t_min : tt;
+              ll = ll < p.a.lam_min ? p.a.lam_min : ll;
+            }
+            wsc(k, v2::oT)[0] = tt; wsc(k, v2::oLAM)[0] = ll;
+          }
+        }
+      }
+      __threadfence_block();
+    }
+    __syncthreads();
+    double acc[5];
+    residual_sweep(wid, kTeam, false, 0.0, 0.0, acc);
+    const double ng_ = acc[0], nb_ = acc[1], nd_ = acc[2], nm_ = acc[3];
+    const double flag = warp_sum((ng_ != ng_ || nb_ != nb_ || nd_ != nd_ || nm_ != nm_) ? 1.0 : 0.0);
+    const double r0 = warp_max(ng_ == ng_ ? ng_ : 0.0), r1 = warp_max(nb_ == nb_ ? nb_ : 0.0);
+    const double r2 = warp_max(nd_ == nd_ ? nd_ : 0.0), r3 = warp_max(nm_ == nm_ ? nm_ : 0.0);
+    if (lane == 0) {
+      double* o = cred + 6 * wid;
+      o[0] = r0; o[1] = r1; o[2] = r2; o[3] = r3; o[4] = flag;
+    }
+    __threadfence_block();
+    __syncthreads();
+    double f = 0.0;
+    res[0] = res[1] = res[2] = res[3] = 0.0;
+    for (int w = 0; w < kTeam; ++w) {
+      const double* o = cred + 6 * w;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) res[i] = fmax(res[i], o[i]);
+      f += o[4];
+    }
+    if (f > 0.0) res[0] = res[0] + __longlong_as_double(0x7ff8000000000000LL);
+    // mu: the sum of res_m in the order of the one-warp sweep (per row over the stages, then across the rows)
+    double smu = 0.0;
+    if (wid == 0 && lane < 24) {
+#pragma unroll 8
+      for (int k = 0; k < N; ++k) smu += ws_ld(wsc(k, v2::oRM));
+    }
+    mu = warp_sum(smu) / (double)nc_mask;
+    __syncwarp();
+  }
+  // the residual sweep over the stages k0, k0 + kstep, ... <= N; acc: per-lane partial inf-norms (stat, eq, ineq, comp) and
+  // the per-lane sum of res_m
+  __device__ void residual_sweep(int k0, int kstep, bool do_update, double sp, double sd, double acc[5]) {
     constexpr bool kT6 = (kTma & 8) != 0;
     const int r = fr, t = ft, pi = fpi;
     const int gB = (pi >> 2) * v2::kGP + 4 * t + (pi & 3);   // G[8I+pi][4kt+t]   : + 2 kGP I + 16 kt
@@ -1205,27 +1291,34 @@ struct SrbdSolver {
 #pragma unroll
     for (int j = 0; j < 6; ++j) acr[j] = cAc[lc * 12 + j0 + j];
     double ng_ = 0.0, nb_ = 0.0, nd_ = 0.0, nm_ = 0.0, smu = 0.0;
+    acc[0] = acc[1] = acc[2] = acc[3] = acc[4] = 0.0;
+    if (k0 > N) return;
     tiles_begin<kT6>();
-    prefetch_G<kT6>(0, 0, 7);
-    prefetch_R<kT6>(0, 0);
-    S6raw raw = load_s6(0, do_update);
+    if (k0 < N) prefetch_G<kT6>(k0, 0, 7);
+    prefetch_R<kT6>(k0, 0);
+    S6raw raw = load_s6(k0, do_update);
     double pp[3] = {0.0, 0.0, 0.0};  // updated pi_{k-1}, fragment form
+    int b = 0;
 #if SRBD_K3_UNROLL_RES
 #pragma unroll 2
 #endif
-    for (int k = 0; k <= N; ++k) {
-      const int b = k & 1;
+    for (int k = k0; k <= N; k += kstep, b ^= 1) {
       const int nu = k < N ? 12 : 0, nx = k > 0 ? 12 : 0, n = nu + nx;
       tiles_wait<kT6>(b);
       __syncwarp();
       set_bufs(b);
       const S6v cur = updated(raw, do_update, sp, sd);
-      if (k < N) {
+      if (kTeam && k > 0) {   // (a strided sweep does not carry pi_{k-1} over from the previous trip)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) pp[j] = ws_ld(wsf(k - 1, v2::oPI) + 4 * j);
+      }
+      if (k + kstep <= N) {
+        const int kn = k + kstep;
         tiles_begin<kT6>();
-        if (k + 1 < N) prefetch_G<kT6>(k + 1, b ^ 1, 7);
-        prefetch_R<kT6>(k + 1, b ^ 1);
-        raw = load_s6(k + 1, do_update);
-        if (k + 2 < N) prefetch_L2(k + 2, false, false, true);
+        if (kn < N) prefetch_G<kT6>(kn, b ^ 1, 7);
+        prefetch_R<kT6>(kn, b ^ 1);
+        raw = load_s6(kn, do_update);
+        if (kn + 1 < N) prefetch_L2(kn + 1, false, false, true);
       }
       double* zb = sm + (b ? v2::wSX : v2::wSG);       // z (24)
       double* lb = sm + (b ? v2::wqx : v2::wQX);       // lam (24)
@@ -1348,13 +1441,7 @@ struct SrbdSolver {
         }
       }
     }
-    const double flag = warp_sum((ng_ != ng_ || nb_ != nb_ || nd_ != nd_ || nm_ != nm_) ? 1.0 : 0.0);
-    res[0] = warp_max(ng_ == ng_ ? ng_ : 0.0);
-    res[1] = warp_max(nb_ == nb_ ? nb_ : 0.0);
-    res[2] = warp_max(nd_ == nd_ ? nd_ : 0.0);
-    res[3] = warp_max(nm_ == nm_ ? nm_ : 0.0);
-    if (flag > 0.0) res[0] = res[0] + __longlong_as_double(0x7ff8000000000000LL);
-    mu = warp_sum(smu) / (double)nc_mask;
+    acc[0] = ng_; acc[1] = nb_; acc[2] = nd_; acc[3] = nm_; acc[4] = smu;
     __syncwarp();
   }
 
@@ -1380,8 +1467,9 @@ struct SrbdSolver {
     const srbd_ipm_args& a = p.a;
     // ---- d_ocp_qp_init_var (cold start): z = 0, pi = 0, t = max(thr0, -lo), lam = mu0/t (masked rows 0) ------
     int nmask = 0;
+    const bool lead = kTeam == 0 || wid == 0;   // team mode: warp 0 initialises, runs the recursions and writes the outputs
 #pragma unroll 4
-    for (int k = 0; k <= N; ++k) {
+    for (int k = lead ? 0 : N + 1; k <= N; ++k) {
       if (lane < 24) wsc(k, v2::oZ)[0] = 0.0;
       if (k < N) {
         if (lane < 12) wsc(k, v2::oPI)[0] = 0.0;
@@ -1399,7 +1487,13 @@ struct SrbdSolver {
         }
       }
     }
-    const int nc_all = warp_sum_i(nmask);
+    int nc_all = warp_sum_i(nmask);
+    if (kTeam) {
+      if (wid == 0 && lane == 0) cred[6 * kTeam + 3] = (double)nc_all;
+      __threadfence_block();
+      __syncthreads();
+      nc_all = (int)cred[6 * kTeam + 3];
+    }
     // No active row at all (BARRIER_SOFT assembly masks every row): d_ocp_qp_fact_solve_kkt_unconstr, ONE Riccati
     // factorization and solve on the QP itself, iter = 0 (hpipm_d_ocp_qp_kkt.h:54; the reference's own test expects
     // iter == 0, hpipm-cpp/test/ocp_qp_ipm_solver.cpp:56).  It runs through the same call sites as an IPM iteration: at z = 0, pi = 0 the residuals are (g, b) themselves, Gamma = gamma = 0, the full
@@ -1412,11 +1506,13 @@ struct SrbdSolver {
     int kk = 0;
     for (;; ++kk) {
       // residuals of the current iterate (kk > 0: the variable update of the previous iteration is fused in)
-      SRBD_PROF(0, residuals(res, mu, nc_mask, kk > 0, sp_, sd_));
+      if (kTeam) SRBD_PROF(0, residuals_team(res, mu, nc_mask, kk > 0, sp_, sd_));
+      else SRBD_PROF(0, residuals(res, mu, nc_mask, kk > 0, sp_, sd_));
       if (unc ? kk > 0
               : !(kk < a.iter_max && alpha > a.alpha_min &&
                   (res[0] > a.tol_stat || res[1] > a.tol_eq || res[2] > a.tol_ineq || res[3] > a.tol_comp)))
         break;
+      if (lead) {
       SRBD_PROF(1, sweep_factor());
       // KKT solves of this iteration (one call site per sweep: the sweeps are inlined once).  phase 0: affine /
       // only solve (its backward part was done by the factorization sweep), 1: corrector, 2: conditional centering
@@ -1463,7 +1559,15 @@ struct SrbdSolver {
       alpha = fmin(ap, ad);
       sp_ = shorten(ap);
       sd_ = shorten(ad);
+      }  // lead
+      if (kTeam) {   // the step lengths of the leader reach the team (the barrier also orders its dz, dpi, dt, dlam stores)
+        if (wid == 0 && lane == 0) { cred[6 * kTeam] = alpha; cred[6 * kTeam + 1] = sp_; cred[6 * kTeam + 2] = sd_; }
+        __threadfence_block();
+        __syncthreads();
+        alpha = cred[6 * kTeam]; sp_ = cred[6 * kTeam + 1]; sd_ = cred[6 * kTeam + 2];
+      }
     }
+    if (!lead) return;
     int status;
     const bool nan = (res[0] != res[0]) || (mu != mu);
     if (unc) { kk = 0; status = nan ? 3 : 0; }
@@ -1518,8 +1622,12 @@ struct SrbdSolver {
 #else
 #define SRBD_K3_BOUNDS __launch_bounds__(32 * v2::kWarps, v2::kMinCtas)
 #endif
-template <int kTma, int kPivot>
+// shared-memory doubles of the team's scratch (between the CTA constants and the warp blocks): [kTeam][6] + 4, whole lines
+constexpr int kTeamShared = 48;
+static_assert(6 * v2::kWarps + 4 <= kTeamShared, "team scratch");
+template <int kTma, int kPivot, int kTeam = 0>
 __global__ void SRBD_K3_BOUNDS ipm_srbd_kernel(const SrbdIpmParams p) {
+  static_assert(kTeam == 0 || kTeam == v2::kWarps, "a team is the whole CTA");
   extern __shared__ __align__(128) double2 smem2[];  // no static shared memory: the tiles start on 128-byte lines
   if (p.gate && *p.gate != p.gate_value) return;
   if (p.run_gate && *p.run_gate == 0) return;
@@ -1545,8 +1653,40 @@ __global__ void SRBD_K3_BOUNDS ipm_srbd_kernel(const SrbdIpmParams p) {
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  SrbdSolver<kTma, kPivot> S(p, smem, smem + v2::kCtaShared + warp * v2::kWarpShared, blockIdx.x * v2::kWarps + warp);
+  SrbdSolver<kTma, kPivot, kTeam> S(p, smem, smem + v2::kCtaShared + (kTeam ? kTeamShared : 0) + warp * v2::kWarpShared,
+                                    kTeam ? blockIdx.x : blockIdx.x * v2::kWarps + warp);
   S.tiles_init();
+  if (kTeam) {   // one QP per CTA at a time; the helpers see every solve_one call of their leader
+    for (;;) {
+      __syncthreads();   // (the previous QP's outputs are written, s_next[0] is free)
+      if (threadIdx.x == 0) s_next[0] = atomicAdd(p.counter, 1);
+      __syncthreads();
+      const int idx = s_next[0];
+      if (idx >= (p.qlist ? *p.qcount : p.B)) break;
+      const int qp = p.qlist ? p.qlist[idx] : idx;
+      if (p.frozen && p.frozen[qp]) continue;
+      S.solve_one(qp);
+      if (threadIdx.x == 0) {
+        const int it = p.iter[qp], st = p.status[qp];
+        if (st == 1 && p.retry_list) {
+          p.retry_list[atomicAdd(p.retry_count, 1)] = qp;
+        } else {
+          atomicAdd((unsigned long long*)&p.bstats->solves, 1ull);
+          atomicAdd((unsigned long long*)&p.bstats->iter_sum, (unsigned long long)it);
+          atomicAdd((unsigned long long*)&p.bstats->status_count[st < 0 || st > 4 ? 4 : st], 1ull);
+          atomicAdd((unsigned long long*)&p.bstats->iter_hist[it < SRBD_HIST_BINS ? it : SRBD_HIST_BINS - 1], 1ull);
+          for (int i = 0; i < 4; ++i)
+            atomicMax((unsigned long long*)&p.bstats->res_max[i],
+                      (unsigned long long)__double_as_longlong(p.res_max[4 * (size_t)qp + i]));
+        }
+      }
+    }
+#if SRBD_K3_PROFILE
+    if (threadIdx.x == 0)
+      for (int i = 0; i < 5; ++i) atomicAdd((unsigned long long*)&p.bstats->iter_hist[48 + i], (unsigned long long)S.prof[i]);
+#endif
+    return;
+  }
   long long it_sum = 0, solves = 0;
   int st_cnt[5] = {0, 0, 0, 0, 0};
   double rmax[4] = {0.0, 0.0, 0.0, 0.0};
