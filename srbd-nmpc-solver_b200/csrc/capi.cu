@@ -821,7 +821,7 @@ static int solve_srbd_variant(srbd_ctx* ctx, const ModelDev* model, const int* g
     const long long need = (ctx->B + v2::kWarps - 1) / v2::kWarps;
     if (g > need) g = need;
     ctx->grid2 = (int)g;
-    CU(dalloc(&ctx->d_ws2, (size_t)ctx->grid2 * v2::kWarps * (size_t)(L.N + 1) * v2::kStage));
+    CU(dalloc(&ctx->d_ws2, (size_t)ctx->grid2 * v2::kWarps * (size_t)(L.N + 1) * (v2::kStage + v2::kAlt)));
     CU(dalloc(&ctx->d_retry, (size_t)ctx->B + 1));
     CU(dalloc(&ctx->d_retry2, (size_t)ctx->B + 1));
   }
@@ -837,7 +837,7 @@ static int solve_srbd_variant(srbd_ctx* ctx, const ModelDev* model, const int* g
   p.babt = ctx->d_babt; p.srec = ctx->d_srec; p.x0 = ctx->d_x0;
   p.model = model; p.ws = ctx->d_ws2;
   p.gate = gate; p.gate_value = 0;
-  p.run_gate = ctx->cur_gate; p.frozen = ctx->sqp_loop ? ctx->d_conv : nullptr; p.ws_size = (L.N + 1) * v2::kStage; p.counter = ctx->d_counter;
+  p.run_gate = ctx->cur_gate; p.frozen = ctx->sqp_loop ? ctx->d_conv : nullptr; p.ws_size = (L.N + 1) * (v2::kStage + v2::kAlt); p.counter = ctx->d_counter;
   p.sol_x = ctx->d_sol_x; p.sol_u = ctx->d_sol_u; p.sol_pi = ctx->d_sol_pi; p.sol_lam = ctx->d_sol_lam; p.sol_t = ctx->d_sol_t;
   p.iter = ctx->d_iter; p.status = ctx->d_status; p.res_max = ctx->d_resmax; p.bstats = ctx->d_bstats;
   if (rescue) {

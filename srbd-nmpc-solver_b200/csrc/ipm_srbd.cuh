@@ -150,6 +150,10 @@ constexpr int kMinCtas = SRBD_K3_MIN_CTAS;
 constexpr int oZ = 0, oDZ = 24, oRG = 48, oLAM = 72, oT = 96, oDLAM = 120, oDT = 144, oRD = 168, oRM = 192, oRMB = 216,
               oPI = 240, oDPI = 252, oRB = 264, oPV = 276, oLV = 288, oP = 300, oFT = 444, oPRB = 750, kStage = 762;
 // factor tile of a stage: 3 column panels x [25 rows][4]: rows 0..11 = rows of L^-T (E rows), 12..23 = Ls, 24 = lv
+// team (latency) mode only: a second (z, pi) slot per stage BEHIND the N + 1 stage blocks (the stage blocks of the throughput
+// mode are untouched).  The team's residual sweep reads iterate slot s and writes the updated one to slot s ^ 1: a warp may
+// then read its neighbours' z_{k+1}, pi_{k-1} while they store theirs.
+constexpr int kAlt = 36;           // [z 24 | pi 12]
 constexpr int kPanF = 102;         // panel stride in the factor tile: rows 0..24 (100) + 2 (bank-conflict-free fragments)
 constexpr int kPan = 148;          // the full panel during the factorization: + rows 25..36 = rows 0..11 of L
 // shared memory (doubles)
@@ -283,6 +287,7 @@ struct SrbdSolver {
   const double* sF;   // current factor tile
   const double* sR;   // current R tile
   int wid;            // warp of the CTA (team mode: 0 = leader)
+  int zs;             // team mode: the slot holding the current (z, pi)
   double* cred;       // CTA-shared scratch of the team: [kTeam][6] partial norms | broadcast slots
   // fragment coordinates of this lane (see the header comment)
   int fr, ft, fpi;
@@ -296,6 +301,7 @@ struct SrbdSolver {
     cQ = cta + v2::sQ;
     sm = warp_sm;
     wid = threadIdx.x >> 5;
+    zs = 0;
     cred = cta + v2::kCtaShared;
     sG = sm; sF = sm + v2::wF0; sR = sm + v2::wR0;
     fr = lane >> 2; ft = lane & 3; fpi = (fr >> 1) + 4 * (fr & 1);
@@ -326,6 +332,16 @@ struct SrbdSolver {
   __device__ __forceinline__ double* wsc(int k, int off) const { return ws(k, off) + (lane < 24 ? lane : 0); }
   __device__ __forceinline__ double* wsf(int k, int off) const { return ws(k, off) + ft; }
 #endif
+  // (z, pi) of stage k in slot s (s is 0 outside the team mode): per-lane pointers like wsc / wsf
+  __device__ __forceinline__ double* zc(int k, int s) const {
+    return (kTeam && s) ? wsc(N + 1, 0) + k * v2::kAlt : wsc(k, v2::oZ);
+  }
+  __device__ __forceinline__ double* pic(int k, int s) const {
+    return (kTeam && s) ? wsc(N + 1, 0) + k * v2::kAlt + 24 : wsc(k, v2::oPI);
+  }
+  __device__ __forceinline__ double* pif(int k, int s) const {
+    return (kTeam && s) ? wsf(N + 1, 0) + k * v2::kAlt + 24 : wsf(k, v2::oPI);
+  }
   // per-QP, per-lane base pointers of the packed QP data (set once per solve; kept opaque so that the compiler
   // holds / reloads them instead of re-deriving them from (q, N, lane) with 64-bit multiplies at every stage)
   static constexpr int kLaneOff = 2;   // every lane copies its own 16-byte chunk (lane 0's pointer is the record base)
@@ -1150,16 +1166,25 @@ struct SrbdSolver {
   struct S6v { double z, pi, lam, t, xn, lo, mk; };
   // raw loads of a stage (issued one stage ahead: NO arithmetic on them here, or the warp would wait for the loads at
   // the prefetch point) ...
-  struct S6raw { double z, pi, lam, t, xn, lo, mk, dz, dpi, dlam, dt, dxn; };
+  struct S6raw { double z, pi, lam, t, xn, lo, mk, dz, dpi, dlam, dt, dxn, ppi[3], pdpi[3]; };
   __device__ __forceinline__ S6raw load_s6(int k, bool do_update) const {
     S6raw v;
-    v.z = ws_ld(wsc(k, v2::oZ));
+    v.z = ws_ld(zc(k, zs));
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { v.ppi[j] = 0.0; v.pdpi[j] = 0.0; }
+    if (kTeam && k > 0) {   // a strided sweep does not carry pi_{k-1} over from its previous trip
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        v.ppi[j] = ws_ld(pif(k - 1, zs) + 4 * j);
+        if (do_update) v.pdpi[j] = ws_ld(wsf(k - 1, v2::oDPI) + 4 * j);
+      }
+    }
     v.pi = 0.0; v.lam = 0.0; v.t = 1.0; v.xn = 0.0; v.lo = 0.0; v.mk = 0.0;
     v.dz = 0.0; v.dpi = 0.0; v.dlam = 0.0; v.dt = 0.0; v.dxn = 0.0;
     const int xo = (k + 1 < N ? 12 : 0);
     if (k < N) {
-      v.pi = ws_ld(wsc(k, v2::oPI)); v.lam = ws_ld(wsc(k, v2::oLAM)); v.t = ws_ld(wsc(k, v2::oT));
-      v.xn = ws_ld(wsc(k + 1, v2::oZ) + xo); v.lo = __ldg(gDL(k)); v.mk = __ldg(gMaskL(k));
+      v.pi = ws_ld(pic(k, zs)); v.lam = ws_ld(wsc(k, v2::oLAM)); v.t = ws_ld(wsc(k, v2::oT));
+      v.xn = ws_ld(zc(k + 1, zs) + xo); v.lo = __ldg(gDL(k)); v.mk = __ldg(gMaskL(k));
     }
     if (do_update) {
       v.dz = ws_ld(wsc(k, v2::oDZ));
@@ -1202,42 +1227,15 @@ struct SrbdSolver {
     mu = warp_sum(smu) / (double)nc_mask;
     __syncwarp();
   }
-  // Team mode: (A) every warp applies the variable update to its stages in place (same expressions as updated()), (B) after
-  // a CTA barrier every warp runs the residual sweep over its stages on the stored iterate, (C) the partial norms meet in
-  // shared memory, the leader re-sums res_m in stage order for mu.  Every warp returns the same res[] and mu.
+  // Team mode: every warp runs the residual sweep (with the fused variable update) over its stages k = wid, wid + kTeam, ...:
+  // it reads (z, pi) of its neighbours from slot zs and writes its own updated ones to slot zs ^ 1 (t, lam, the steps and
+  // the residuals are private to a stage).  The partial norms meet in shared memory; the leader re-sums res_m in stage order
+  // for mu (bit-identical to the one-warp sweep).  Every warp returns the same res[].
   __device__ void residuals_team(double res[4], double& mu, int nc_mask, bool do_update, double sp, double sd) {
-    if (do_update) {
-      for (int k = wid; k <= N; k += kTeam) {
-        const int n = (k < N ? 12 : 0) + (k > 0 ? 12 : 0);
-        if (lane < n) {
-          double z = ws_ld(wsc(k, v2::oZ));
-          z += sp * ws_ld(wsc(k, v2::oDZ));
-          wsc(k, v2::oZ)[0] = z;
-        }
-        if (k < N) {
-          if (lane < 12) {
-            double v = ws_ld(wsc(k, v2::oPI));
-            v += sd * ws_ld(wsc(k, v2::oDPI));
-            wsc(k, v2::oPI)[0] = v;
-          }
-          if (lane < 24) {
-            double tt = ws_ld(wsc(k, v2::oT)), ll = ws_ld(wsc(k, v2::oLAM));
-            const double mk = __ldg(gMaskL(k));
-            tt += sp * ws_ld(wsc(k, v2::oDT));
-            ll += sd * ws_ld(wsc(k, v2::oDLAM));
-            if (p.a.t_lam_min == 2 && mk != 0.0) {
-              tt = tt < p.a.t_min ? p.a.t_min : tt;
-              ll = ll < p.a.lam_min ? p.a.lam_min : ll;
-            }
-            wsc(k, v2::oT)[0] = tt; wsc(k, v2::oLAM)[0] = ll;
-          }
-        }
-      }
-      __threadfence_block();
-    }
-    __syncthreads();
     double acc[5];
-    residual_sweep(wid, kTeam, false, 0.0, 0.0, acc);
+    residual_sweep(wid, kTeam, do_update, sp, sd, acc);
+    if (do_update) zs ^= 1;
+
     const double ng_ = acc[0], nb_ = acc[1], nd_ = acc[2], nm_ = acc[3];
     const double flag = warp_sum((ng_ != ng_ || nb_ != nb_ || nd_ != nd_ || nm_ != nm_) ? 1.0 : 0.0);
     const double r0 = warp_max(ng_ == ng_ ? ng_ : 0.0), r1 = warp_max(nb_ == nb_ ? nb_ : 0.0);
@@ -1308,9 +1306,12 @@ struct SrbdSolver {
       __syncwarp();
       set_bufs(b);
       const S6v cur = updated(raw, do_update, sp, sd);
-      if (kTeam && k > 0) {   // (a strided sweep does not carry pi_{k-1} over from the previous trip)
+      if (kTeam) {   // pi_{k-1}, updated like the warp of stage k - 1 does (same expression as in updated())
 #pragma unroll
-        for (int j = 0; j < 3; ++j) pp[j] = ws_ld(wsf(k - 1, v2::oPI) + 4 * j);
+        for (int j = 0; j < 3; ++j) {
+          pp[j] = raw.ppi[j];
+          if (do_update) pp[j] += sd * raw.pdpi[j];
+        }
       }
       if (k + kstep <= N) {
         const int kn = k + kstep;
@@ -1329,9 +1330,9 @@ struct SrbdSolver {
         if (lane < 24) lb[lane] = cur.lam;
       }
       if (do_update) {
-        if (lane < n) wsc(k, v2::oZ)[0] = cur.z;
+        if (lane < n) zc(k, zs ^ 1)[0] = cur.z;
         if (k < N) {
-          if (lane < 12) wsc(k, v2::oPI)[0] = cur.pi;
+          if (lane < 12) pic(k, zs ^ 1)[0] = cur.pi;
           if (lane < 24) { wsc(k, v2::oT)[0] = cur.t; wsc(k, v2::oLAM)[0] = cur.lam; }
         }
       }
@@ -1467,6 +1468,7 @@ struct SrbdSolver {
     const srbd_ipm_args& a = p.a;
     // ---- d_ocp_qp_init_var (cold start): z = 0, pi = 0, t = max(thr0, -lo), lam = mu0/t (masked rows 0) ------
     int nmask = 0;
+    zs = 0;
     const bool lead = kTeam == 0 || wid == 0;   // team mode: warp 0 initialises, runs the recursions and writes the outputs
 #pragma unroll 4
     for (int k = lead ? 0 : N + 1; k <= N; ++k) {
@@ -1583,9 +1585,10 @@ struct SrbdSolver {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int k = k0 + j <= N ? k0 + j : N, nu = k < N ? 12 : 0, kk_ = k < N ? k : N - 1;
-          vx[j] = k == 0 ? __ldg(p.x0 + (size_t)q * 12 + l12) : ws_ld(ws(k, v2::oZ) + nu + l12);
-          vp[j] = ws_ld(ws(k > 0 ? k - 1 : 0, v2::oPI) + l12);
-          vu[j] = ws_ld(ws(kk_, v2::oZ) + l12);
+          const int l0 = lane < 24 ? lane : 0;   // (zc / pic are per-lane pointers: + min(lane, 23)-ish)
+          vx[j] = k == 0 ? __ldg(p.x0 + (size_t)q * 12 + l12) : ws_ld(zc(k, zs) - l0 + nu + l12);
+          vp[j] = ws_ld(pic(k > 0 ? k - 1 : 0, zs) - l0 + l12);
+          vu[j] = ws_ld(zc(kk_, zs) - l0 + l12);
           vl[j] = ws_ld(wsc(kk_, v2::oLAM));
           vt[j] = ws_ld(wsc(kk_, v2::oT));
           if (unc) { vl[j] = 0.0; vt[j] = 0.0; }  // the unconstrained solve reports lam = t = 0 on the masked rows
@@ -1620,7 +1623,7 @@ struct SrbdSolver {
 #ifdef SRBD_K3_MAXREG
 #define SRBD_K3_BOUNDS __maxnreg__(SRBD_K3_MAXREG)
 #else
-#define SRBD_K3_BOUNDS __launch_bounds__(32 * v2::kWarps, v2::kMinCtas)
+#define SRBD_K3_BOUNDS __launch_bounds__(32 * v2::kWarps, kTeam ? 1 : v2::kMinCtas)
 #endif
 // shared-memory doubles of the team's scratch (between the CTA constants and the warp blocks): [kTeam][6] + 4, whole lines
 constexpr int kTeamShared = 48;
