@@ -161,10 +161,13 @@ int raw0_stride(const QpLayout& L) { return 2 * L.nx * L.nx + 2 * L.nx * L.nu + 
 
 // Do the dimensions and settings allow the SRBD tensor-core variant of K3 (cold start, classical Riccati, no Riccati /
 // statistics exports)?
-bool settings_allow_variant(const srbd_ctx* ctx) {
+// exports_ok: the caller can hand the variant the raw stage-0 blocks its Riccati export needs (QP-level uploads: pack_kernel
+// always writes them; K2 writes S0, Q0, q0 only with the dense records)
+bool settings_allow_variant(const srbd_ctx* ctx, bool exports_ok = false) {
   const char* force = std::getenv("SRBD_K3_GENERIC");
   if (force && force[0] == '1') return false;
-  return ctx->is_srbd && !ctx->args.warm_start && ctx->args.ric_alg == 0 && !ctx->export_ric && !ctx->export_stat &&
+  if (!exports_ok && (ctx->export_ric || ctx->export_stat)) return false;
+  return ctx->is_srbd && !ctx->args.warm_start && ctx->args.ric_alg == 0 &&
          ctx->args.itref_pred_max == 0 && ctx->args.itref_corr_max == 0;   // (the variant has no iterative refinement)
 }
 // Will srbd_qp_solve take the variant for a QP assembled by K2 under the current settings?
@@ -806,6 +809,8 @@ static int solve_srbd_variant(srbd_ctx* ctx, const ModelDev* model, const int* g
     CU(cudaFuncSetAttribute(ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes));
     CU(cudaFuncSetAttribute(ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 0, v2::kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTeamSmem));
     CU(cudaFuncSetAttribute(ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 1, v2::kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTeamSmem));
+    CU(cudaFuncSetAttribute(ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes));
+    CU(cudaFuncSetAttribute(ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 0, v2::kWarps, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTeamSmem));
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ipm_srbd_kernel<SRBD_K3_TMA, 0>, 32 * v2::kWarps, v2::kSmemBytes));
     if (occ < 1) return fail(ctx, SRBD_ERR_CUDA, "ipm_srbd_kernel does not fit on this device");
@@ -844,17 +849,40 @@ static int solve_srbd_variant(srbd_ctx* ctx, const ModelDev* model, const int* g
     p.retry_list = ctx->d_retry; p.retry_count = ctx->d_retry + ctx->B;
     CU(cudaMemsetAsync(ctx->d_retry + ctx->B, 0, sizeof(int), ctx->stream));
   }
+  if (ctx->export_ric) {   // (QP-level uploads only: settings_allow_variant)
+    const size_t B = ctx->B, S = L.N + 1, N = L.N;
+    if (!ctx->d_P) {
+      CU(dalloc(&ctx->d_P, B * S * L.nx * L.nx)); CU(dalloc(&ctx->d_p, B * S * L.nx));
+      CU(dalloc(&ctx->d_K, B * N * L.nu * L.nx)); CU(dalloc(&ctx->d_k, B * N * L.nu));
+    }
+    p.ric_P = ctx->d_P; p.ric_p = ctx->d_p; p.ric_K = ctx->d_K; p.ric_k = ctx->d_k;
+    p.raw0 = ctx->d_raw0; p.raw0_stride = raw0_stride(L);
+  }
+  if (ctx->export_stat) {
+    if (!ctx->d_stat) CU(dalloc(&ctx->d_stat, (size_t)ctx->B * ctx->stat_rows * SRBD_STAT_M));
+    p.stat = ctx->d_stat; p.stat_rows = ctx->stat_rows;
+  }
   CU(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
   CU(cudaMemsetAsync(ctx->d_bstats, 0, sizeof(srbd_batch_stats), ctx->stream));
   // batches of fewer QPs than SMs have nothing to hide a bulk copy's latency behind: the cp.async-only instantiation
-  if (team) ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 0, v2::kWarps><<<ctx->B, 32 * v2::kWarps, kTeamSmem, ctx->stream>>>(p);
+  // with the facade's exports: the exporting instantiations (cp.async tile engine); their rescue list goes straight to the
+  // generic kernel, which exports too
+  const bool exports = ctx->export_ric || ctx->export_stat;
+  if (exports && team) ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 0, v2::kWarps, true><<<ctx->B, 32 * v2::kWarps, kTeamSmem, ctx->stream>>>(p);
+  else if (exports) ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 0, 0, true><<<ctx->grid2, 32 * v2::kWarps, v2::kSmemBytes, ctx->stream>>>(p);
+  else if (team) ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 0, v2::kWarps><<<ctx->B, 32 * v2::kWarps, kTeamSmem, ctx->stream>>>(p);
   else if (ctx->B < ctx->sm_count) ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 0><<<ctx->grid2, 32 * v2::kWarps, v2::kSmemBytes, ctx->stream>>>(p);
   else ipm_srbd_kernel<SRBD_K3_TMA, 0><<<ctx->grid2, 32 * v2::kWarps, v2::kSmemBytes, ctx->stream>>>(p);
   ctx->launches++;
   CU(cudaGetLastError());
   ctx->solved = true;
-  ctx->ric_valid = false;   // the variant exports neither P, p, K, k nor pi[0] nor the statistics table
-  ctx->stat_valid = false;
+  ctx->ric_valid = ctx->export_ric;   // (P, p, K, k, pi[0]: only on request; see settings_allow_variant)
+  ctx->stat_valid = ctx->export_stat;
+  if (rescue && exports) {
+    if (ctx->assembled_mode >= 0 && !ctx->dense_valid)
+      if (int rc = launch_assemble(ctx, ctx->assembled_mode, true, ctx->d_retry, ctx->d_retry + ctx->B)) return rc;
+    return launch_generic(ctx, ctx->d_retry, ctx->d_retry + ctx->B);
+  }
   if (rescue) {
     // Stage 1: the listed QPs again in the SAME tensor-core kernel with the other rounding of the inverse pivots (kPivot =
     // 1): a QP that runs to iter_max sits on a knife edge of the rounding floor, and each rounding has its own (about 3
@@ -888,7 +916,7 @@ int srbd_qp_solve(srbd_ctx* ctx) {
   // QPs assembled by K2 (both modes: BARRIER_SOFT masks every row, which the variant solves as the single unconstrained
   // Riccati pass) take the SRBD tensor-core variant unless a setting needs the generic kernel
   if (ctx->assembled_mode >= 0 && variant_eligible(ctx)) return solve_srbd_variant(ctx, ctx->d_model);
-  if (ctx->assembled_mode < 0 && ctx->upload_variant_ok && settings_allow_variant(ctx)) {
+  if (ctx->assembled_mode < 0 && ctx->upload_variant_ok && settings_allow_variant(ctx, true)) {
     // Uploaded QP with the SRBD dimensions: detect_srbd_kernel left *d_flag = 0 if it has K2's structure.  Both kernels
     // are launched, each gated on the flag (no host round trip): the variant (+ its rescue launch) runs if 0, the
     // generic kernel if 1.

@@ -73,6 +73,14 @@ struct SrbdIpmParams {
   // problem has converged: the reference leaves its SQP loop then, NMPC_solver.cpp:372-374)
   const int* run_gate;
   const int* frozen;
+  // optional exports (QP-level uploads through the hpipm-cpp facade, which fills them like the reference does,
+  // hpipm-cpp/src/ocp_qp_ipm_solver.cpp:337-387): the Riccati matrices of the last factorization, pi[0], and the
+  // per-iteration statistics table [B][stat_rows][18]
+  double *ric_P, *ric_p, *ric_K, *ric_k;   // null: none
+  const double* raw0;   // [B][raw0_stride] raw stage-0 blocks A0 | B0 | b0 | S0 | Q0 | q0 (column-major), for the stage-0 export
+  int raw0_stride;
+  double* stat;         // null: none
+  int stat_rows;
 };
 
 namespace v2 {
@@ -274,7 +282,9 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b,
 // kTeam: 0 = one warp per QP (throughput); n > 0 = LATENCY mode, the n warps of the CTA work on ONE QP: the residual sweep
 // (no recursion: a fifth of a solve) is split over them by stage, the four Riccati recursions stay on warp 0.  Results are
 // bit-identical to kTeam = 0 (same operations per element; the duality measure is summed in the original order).
-template <int kTma, int kPivot, int kTeam>
+// kExp: the instantiation that can write the facade's exports (Riccati matrices, pi[0], statistics table); the throughput
+// instantiations carry none of that code.
+template <int kTma, int kPivot, int kTeam, bool kExp>
 struct SrbdSolver {
   const SrbdIpmParams& p;
   int lane, q, N;
@@ -1214,9 +1224,10 @@ struct SrbdSolver {
     }
     return v;
   }
-  __device__ void residuals(double res[4], double& mu, int nc_mask, bool do_update, double sp, double sd) {
-    double acc[5];
+  __device__ void residuals(double res[4], double& mu, double& obj, int nc_mask, bool do_update, double sp, double sd) {
+    double acc[6];
     residual_sweep(0, 1, do_update, sp, sd, acc);
+    obj = (kExp && p.stat) ? warp_sum(acc[5]) : 0.0;
     const double ng_ = acc[0], nb_ = acc[1], nd_ = acc[2], nm_ = acc[3], smu = acc[4];
     const double flag = warp_sum((ng_ != ng_ || nb_ != nb_ || nd_ != nd_ || nm_ != nm_) ? 1.0 : 0.0);
     res[0] = warp_max(ng_ == ng_ ? ng_ : 0.0);
@@ -1231,8 +1242,8 @@ struct SrbdSolver {
   // it reads (z, pi) of its neighbours from slot zs and writes its own updated ones to slot zs ^ 1 (t, lam, the steps and
   // the residuals are private to a stage).  The partial norms meet in shared memory; the leader re-sums res_m in stage order
   // for mu (bit-identical to the one-warp sweep).  Every warp returns the same res[].
-  __device__ void residuals_team(double res[4], double& mu, int nc_mask, bool do_update, double sp, double sd) {
-    double acc[5];
+  __device__ void residuals_team(double res[4], double& mu, double& obj, int nc_mask, bool do_update, double sp, double sd) {
+    double acc[6];
     residual_sweep(wid, kTeam, do_update, sp, sd, acc);
     if (do_update) zs ^= 1;
 
@@ -1240,19 +1251,22 @@ struct SrbdSolver {
     const double flag = warp_sum((ng_ != ng_ || nb_ != nb_ || nd_ != nd_ || nm_ != nm_) ? 1.0 : 0.0);
     const double r0 = warp_max(ng_ == ng_ ? ng_ : 0.0), r1 = warp_max(nb_ == nb_ ? nb_ : 0.0);
     const double r2 = warp_max(nd_ == nd_ ? nd_ : 0.0), r3 = warp_max(nm_ == nm_ ? nm_ : 0.0);
+    const double ob = (kExp && p.stat) ? warp_sum(acc[5]) : 0.0;
     if (lane == 0) {
       double* o = cred + 6 * wid;
-      o[0] = r0; o[1] = r1; o[2] = r2; o[3] = r3; o[4] = flag;
+      o[0] = r0; o[1] = r1; o[2] = r2; o[3] = r3; o[4] = flag; o[5] = ob;
     }
     __threadfence_block();
     __syncthreads();
     double f = 0.0;
     res[0] = res[1] = res[2] = res[3] = 0.0;
+    obj = 0.0;
     for (int w = 0; w < kTeam; ++w) {
       const double* o = cred + 6 * w;
 #pragma unroll
       for (int i = 0; i < 4; ++i) res[i] = fmax(res[i], o[i]);
       f += o[4];
+      obj += o[5];
     }
     if (f > 0.0) res[0] = res[0] + __longlong_as_double(0x7ff8000000000000LL);
     // mu: the sum of res_m in the order of the one-warp sweep (per row over the stages, then across the rows)
@@ -1265,8 +1279,10 @@ struct SrbdSolver {
     __syncwarp();
   }
   // the residual sweep over the stages k0, k0 + kstep, ... <= N; acc: per-lane partial inf-norms (stat, eq, ineq, comp) and
-  // the per-lane sum of res_m
-  __device__ void residual_sweep(int k0, int kstep, bool do_update, double sp, double sd, double acc[5]) {
+  // the per-lane sum of res_m; with the statistics table also the per-lane part of the objective 1/2 z'Hz + g'z
+  __device__ void residual_sweep(int k0, int kstep, bool do_update, double sp, double sd, double acc[6]) {
+    const bool want_obj = kExp && p.stat != nullptr;
+    double ob = 0.0;
     constexpr bool kT6 = (kTma & 8) != 0;
     const int r = fr, t = ft, pi = fpi;
     const int gB = (pi >> 2) * v2::kGP + 4 * t + (pi & 3);   // G[8I+pi][4kt+t]   : + 2 kGP I + 16 kt
@@ -1289,7 +1305,7 @@ struct SrbdSolver {
 #pragma unroll
     for (int j = 0; j < 6; ++j) acr[j] = cAc[lc * 12 + j0 + j];
     double ng_ = 0.0, nb_ = 0.0, nd_ = 0.0, nm_ = 0.0, smu = 0.0;
-    acc[0] = acc[1] = acc[2] = acc[3] = acc[4] = 0.0;
+    acc[0] = acc[1] = acc[2] = acc[3] = acc[4] = acc[5] = 0.0;
     if (k0 > N) return;
     tiles_begin<kT6>();
     if (k0 < N) prefetch_G<kT6>(k0, 0, 7);
@@ -1363,6 +1379,13 @@ struct SrbdSolver {
         dmma(c1[0], c1[1], zk[kt], pi < 4 ? r1 : 0.0, c1[0], c1[1]);
       }
 #endif
+      if (want_obj) {   // rows 0..11: c = g + H z so far; rows 12..23 (0 < k < N): H = diag(Q)
+        double o = 0.5 * (zk[0] * (c0[0] + sR[108 + t]) + zk[1] * (c0[1] + sR[112 + t]) + zk[2] * (c1[0] + sR[116 + t]));
+        if (k > 0 && k < N)
+          o += zk[3] * fma(0.5 * cQ[t], zk[3], sR[120 + t]) + zk[4] * fma(0.5 * cQ[4 + t], zk[4], sR[124 + t]) +
+               zk[5] * fma(0.5 * cQ[8 + t], zk[5], sR[128 + t]);
+        if (r == 0) ob += o;
+      }
       if (k < N) {
         if (k > 0) {  // diag(Q) on the x rows 12..23
           c1[1] = fma(cQ[t], zk[3], c1[1]);
@@ -1442,8 +1465,197 @@ struct SrbdSolver {
         }
       }
     }
-    acc[0] = ng_; acc[1] = nb_; acc[2] = nd_; acc[3] = nm_; acc[4] = smu;
+    acc[0] = ng_; acc[1] = nb_; acc[2] = nd_; acc[3] = nm_; acc[4] = smu; acc[5] = ob;
     __syncwarp();
+  }
+
+  // ------------------------------------------------------------------------------------------------
+  // Exports of the hpipm-cpp facade (ocp_qp_ipm_solver.cpp:337-387), row-per-lane from the workspace of the LAST
+  // factorization, same formulas as the generic kernel's write_outputs (ipm_solve.cuh).  Not on the throughput path.
+  // ------------------------------------------------------------------------------------------------
+  __device__ __forceinline__ void stat_row(int row, int col0, const double* v, int n) const {
+    if (kExp && p.stat && row < p.stat_rows && lane == 0) {
+      double* rr = p.stat + ((size_t)q * p.stat_rows + row) * SRBD_STAT_M;
+      for (int i = 0; i < n; ++i) rr[col0 + i] = v[i];
+    }
+  }
+  // factor panels pn (3 x kPanF, layout of oFT): T_pp = L_pp^-T in rows 4pp..4pp+3 of panel pp, L[i][j] (i >= 4 (j/4) + 4) in
+  // row i of panel j / 4
+  static __device__ __forceinline__ double pnT(const double* pn, int pp, int a, int b) { return pn[pp * v2::kPanF + (4 * pp + a) * 4 + b]; }
+  static __device__ __forceinline__ double pnL(const double* pn, int i, int j) { return pn[(j >> 2) * v2::kPanF + i * 4 + (j & 3)]; }
+  // v <- L^-T v (blocked back substitution)
+  static __device__ void tri_bwd(const double* pn, double v[12]) {
+#pragma unroll
+    for (int pp = 2; pp >= 0; --pp) {
+      double b[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double a = v[4 * pp + j];
+        for (int i = 4 * pp + 4; i < 12; ++i) a -= pnL(pn, i, 4 * pp + j) * v[i];
+        b[j] = a;
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        double y = 0.0;
+#pragma unroll
+        for (int j = a; j < 4; ++j) y += pnT(pn, pp, a, j) * b[j];
+        v[4 * pp + a] = y;
+      }
+    }
+  }
+  // v <- L^-1 v (blocked forward substitution; L_pp^-1 = T_pp^T)
+  static __device__ void tri_fwd(const double* pn, double v[12]) {
+#pragma unroll
+    for (int pp = 0; pp < 3; ++pp) {
+      double b[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        double acc = v[4 * pp + a];
+        for (int j = 0; j < 4 * pp; ++j) acc -= pnL(pn, 4 * pp + a, j) * v[j];
+        b[a] = acc;
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        double y = 0.0;
+#pragma unroll
+        for (int j = 0; j <= a; ++j) y += pnT(pn, pp, j, a) * b[j];
+        v[4 * pp + a] = y;
+      }
+    }
+  }
+  __device__ __noinline__ void export_riccati(bool unc) {
+    double* sPn = sm;          // factor panels of the stage (306)
+    double* sPk = sm + 320;    // P_k (144)
+    double* sx_ = sm + 480;    // z_k (24)
+    double* sK = sm + 512;     // K_k, column-major (144)
+    const size_t qS = (size_t)q * (N + 1), qN = (size_t)q * N;
+    const int l0 = lane < 24 ? lane : 0;
+    for (int k = 1; k <= N; ++k) {
+      const int nu = k < N ? 12 : 0;
+      __syncwarp();
+      for (int e = lane; e < 144; e += 32) {
+        const double v = ws_ld(ws(k - 1, v2::oP) + e);
+        sPk[e] = v;
+        p.ric_P[(qS + k) * 144 + e] = v;   // symmetric: row-major == column-major
+      }
+      if (k < N)
+        for (int e = lane; e < 306; e += 32) sPn[e] = ws_ld(ws(k, v2::oFT) + e);
+      if (lane < 24) sx_[lane] = lane < nu + 12 ? ws_ld(zc(k, zs)) : 0.0;
+      __syncwarp();
+      if (lane < 12) {
+        double v;
+        if (unc) v = ws_ld(ws(k, v2::oPV) + lane);
+        else {   // p_k = pi_k - P_k x_k
+          double acc = 0.0;
+          for (int j = 0; j < 12; ++j) acc += sPk[lane * 12 + j] * sx_[nu + j];
+          v = ws_ld(pic(k - 1, zs) - l0 + lane) - acc;
+        }
+        p.ric_p[(qS + k) * 12 + lane] = v;
+      }
+      if (k < N) {
+        if (lane < 13) {   // lanes 0..11: column c = lane of K_k = -L^-T Ls^T; lane 12: -L^-T lv
+          double y[12];
+#pragma unroll
+          for (int j = 0; j < 12; ++j) y[j] = sPn[(j >> 2) * v2::kPanF + (lane < 12 ? 12 + lane : 24) * 4 + (j & 3)];
+          tri_bwd(sPn, y);
+          if (lane < 12) {
+#pragma unroll
+            for (int i = 0; i < 12; ++i) {
+              sK[i + 12 * lane] = -y[i];
+              p.ric_K[(qN + k) * 144 + i + 12 * lane] = -y[i];
+            }
+          } else if (unc) {
+#pragma unroll
+            for (int i = 0; i < 12; ++i) p.ric_k[(qN + k) * 12 + i] = -y[i];
+          }
+        }
+        __syncwarp();
+        if (!unc && lane < 12) {   // k_k = u_k - K_k x_k
+          double acc = 0.0;
+          for (int c = 0; c < 12; ++c) acc += sK[lane + 12 * c] * sx_[12 + c];
+          p.ric_k[(qN + k) * 12 + lane] = sx_[lane] - acc;
+        }
+      }
+    }
+    __syncwarp();
+    // ---- stage 0 (ocp_qp_ipm_solver.cpp:349-373) from the raw stage-0 blocks --------------------------------------------
+    {
+      const double* raw = p.raw0 + (size_t)q * p.raw0_stride;
+      const double *A0 = raw, *B0 = raw + 144, *b0 = raw + 288, *S0 = raw + 300, *Q0 = raw + 444, *q0 = raw + 588;
+      const double* x0 = p.x0 + (size_t)q * 12;
+      double* sP1 = sPk;            // P_1
+      double* H0 = sm + 672;        // [i * 12 + j], nu x nx
+      double* AtP = sm + 816;
+      double* GH = sm + 960;
+      double* BtP = sm + 1104;
+      double* sv = sm + 1248;       // k0 (12) | p1 (12)
+      for (int e = lane; e < 144; e += 32) sP1[e] = ws_ld(ws(0, v2::oP) + e);
+      for (int e = lane; e < 306; e += 32) sPn[e] = ws_ld(ws(0, v2::oFT) + e);
+      if (lane < 12) sx_[lane] = ws_ld(zc(0, zs));   // u_0
+      __syncwarp();
+      for (int e = lane; e < 144; e += 32) {
+        const int i = e / 12, j = e % 12;
+        double a1 = 0.0, a2 = 0.0;
+        for (int l = 0; l < 12; ++l) {
+          a1 += B0[l + 12 * i] * sP1[l * 12 + j];
+          a2 += A0[l + 12 * i] * sP1[l * 12 + j];
+        }
+        BtP[e] = a1; AtP[e] = a2;
+      }
+      __syncwarp();
+      for (int e = lane; e < 144; e += 32) {
+        const int i = e / 12, j = e % 12;
+        double acc = 0.0;
+        for (int l = 0; l < 12; ++l) acc += BtP[i * 12 + l] * A0[l + 12 * j];
+        H0[e] = S0[i + 12 * j] + acc;
+      }
+      __syncwarp();
+      if (lane < 12) {   // column c = lane of GH = L^-T L^-1 H0
+        double y[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) y[i] = H0[i * 12 + lane];
+        tri_fwd(sPn, y);
+        tri_bwd(sPn, y);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+          GH[i * 12 + lane] = y[i];
+          p.ric_K[qN * 144 + i + 12 * lane] = -y[i];
+        }
+      }
+      __syncwarp();
+      if (lane < 12) {
+        double acc = 0.0;
+        for (int j = 0; j < 12; ++j) acc += -GH[lane * 12 + j] * x0[j];
+        const double k0 = sx_[lane] - acc;
+        sv[lane] = k0;
+        p.ric_k[qN * 12 + lane] = k0;
+        sv[12 + lane] = p.ric_p[(qS + 1) * 12 + lane];   // (written by this lane above)
+      }
+      __syncwarp();
+      double* P0 = p.ric_P + qS * 144;
+      for (int e = lane; e < 144; e += 32) {
+        const int i = e % 12, j = e / 12;  // column-major output
+        double s1 = 0.0, s2 = 0.0;
+        for (int l = 0; l < 12; ++l) s1 += H0[l * 12 + i] * GH[l * 12 + j];
+        for (int l = 0; l < 12; ++l) s2 += AtP[i * 12 + l] * A0[l + 12 * j];
+        const double v = (Q0[i + 12 * j] - s1) + s2;
+        P0[e] = v;
+        sK[e] = v;
+      }
+      __syncwarp();
+      if (lane < 12) {
+        double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        for (int l = 0; l < 12; ++l) s1 += A0[l + 12 * lane] * sv[12 + l];
+        for (int l = 0; l < 12; ++l) s2 += AtP[lane * 12 + l] * b0[l];
+        for (int l = 0; l < 12; ++l) s3 += H0[l * 12 + lane] * sv[l];
+        const double p0 = ((q0[lane] + s1) + s2) + s3;
+        p.ric_p[qS * 12 + lane] = p0;
+        double acc = 0.0;
+        for (int j = 0; j < 12; ++j) acc += sK[lane + 12 * j] * x0[j];
+        p.sol_pi[qS * 12 + lane] = p0 + acc;
+      }
+      __syncwarp();
+    }
   }
 
   __device__ __forceinline__ double shorten(double alpha) const {
@@ -1503,13 +1715,23 @@ struct SrbdSolver {
     const bool unc = nc_all == 0;
     const int nc_mask = unc ? 1 : nc_all;
     __syncwarp();
-    double res[4], mu;
+    double res[4], mu, obj;
     double alpha = 1.0, sp_ = 0.0, sd_ = 0.0;
     int kk = 0;
+    if (kExp && p.stat && lead) {
+      double* st = p.stat + (size_t)q * p.stat_rows * SRBD_STAT_M;
+      for (int i = lane; i < p.stat_rows * SRBD_STAT_M; i += 32) st[i] = 0.0;
+      __syncwarp();
+    }
     for (;; ++kk) {
       // residuals of the current iterate (kk > 0: the variable update of the previous iteration is fused in)
-      if (kTeam) SRBD_PROF(0, residuals_team(res, mu, nc_mask, kk > 0, sp_, sd_));
-      else SRBD_PROF(0, residuals(res, mu, nc_mask, kk > 0, sp_, sd_));
+      if (kTeam) SRBD_PROF(0, residuals_team(res, mu, obj, nc_mask, kk > 0, sp_, sd_));
+      else SRBD_PROF(0, residuals(res, mu, obj, nc_mask, kk > 0, sp_, sd_));
+      if (kExp && p.stat && lead && (!unc || kk > 0)) {   // row kk: mu, the four residual norms, the objective of iterate kk
+        if (!unc) stat_row(kk, 5, &mu, 1);
+        stat_row(unc ? 0 : kk, 6, res, 4);
+        stat_row(unc ? 0 : kk, 10, &obj, 1);
+      }
       if (unc ? kk > 0
               : !(kk < a.iter_max && alpha > a.alpha_min &&
                   (res[0] > a.tol_stat || res[1] > a.tol_eq || res[2] > a.tol_ineq || res[3] > a.tol_comp)))
@@ -1533,6 +1755,7 @@ struct SrbdSolver {
 #else
           sweep_forward(a.pred_corr != 1 || phase > 0 || unc, ap, ad);
 #endif
+          if (phase == 0 && !unc) { const double aff = fmin(ap, ad); stat_row(kk + 1, 0, &aff, 1); }
           if (a.pred_corr != 1 || unc) break;
           if (phase == 0) {
             mua = mu_aff(fmin(ap, ad), nc_mask);
@@ -1540,6 +1763,7 @@ struct SrbdSolver {
             sigma = tmp * tmp * tmp;
             smv = sigma * mu;
             smv = smv > a.tau_min ? smv : a.tau_min;
+            { const double r2[2] = {mua, sigma}; stat_row(kk + 1, 1, r2, 2); }
             phase = 1;
             continue;
           }
@@ -1559,6 +1783,7 @@ struct SrbdSolver {
         ap = al; ad = al;
       }
       alpha = fmin(ap, ad);
+      if (!unc) { const double r2[2] = {ap, ad}; stat_row(kk + 1, 3, r2, 2); }
       sp_ = shorten(ap);
       sd_ = shorten(ad);
       }  // lead
@@ -1611,6 +1836,7 @@ struct SrbdSolver {
         }
       }
     }
+    if (kExp && p.ric_P) export_riccati(unc);
     if (lane == 0) {
       p.iter[q] = kk;
       p.status[q] = status;
@@ -1628,7 +1854,7 @@ struct SrbdSolver {
 // shared-memory doubles of the team's scratch (between the CTA constants and the warp blocks): [kTeam][6] + 4, whole lines
 constexpr int kTeamShared = 48;
 static_assert(6 * v2::kWarps + 4 <= kTeamShared, "team scratch");
-template <int kTma, int kPivot, int kTeam = 0>
+template <int kTma, int kPivot, int kTeam = 0, bool kExp = false>
 __global__ void SRBD_K3_BOUNDS ipm_srbd_kernel(const SrbdIpmParams p) {
   static_assert(kTeam == 0 || kTeam == v2::kWarps, "a team is the whole CTA");
   extern __shared__ __align__(128) double2 smem2[];  // no static shared memory: the tiles start on 128-byte lines
@@ -1656,7 +1882,7 @@ __global__ void SRBD_K3_BOUNDS ipm_srbd_kernel(const SrbdIpmParams p) {
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  SrbdSolver<kTma, kPivot, kTeam> S(p, smem, smem + v2::kCtaShared + (kTeam ? kTeamShared : 0) + warp * v2::kWarpShared,
+  SrbdSolver<kTma, kPivot, kTeam, kExp> S(p, smem, smem + v2::kCtaShared + (kTeam ? kTeamShared : 0) + warp * v2::kWarpShared,
                                     kTeam ? blockIdx.x : blockIdx.x * v2::kWarps + warp);
   S.tiles_init();
   if (kTeam) {   // one QP per CTA at a time; the helpers see every solve_one call of their leader

@@ -7,6 +7,7 @@
 // usage: test_facades <tests/golden/quadcopter_sol.txt>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <fstream>
 #include <functional>
 #include <sstream>
@@ -303,19 +304,38 @@ static void test_srbd_structured_qp_fast_path() {
   const VectorXd x0 = RndV(nx);
   hpipm::OcpQpIpmSolverSettings s;
   s.ric_alg = 0; s.iter_max = 40; s.split_step = 1;
-  std::vector<hpipm::OcpQpSolution> full(N + 1), fast(N + 1);
-  hpipm::OcpQpIpmSolver a(qp, s), b(qp, s);
-  CHECK(a.solve(x0, qp, full) == hpipm::HpipmStatus::Success);   // default outputs: generic kernel, P / K / statistics
+  std::vector<hpipm::OcpQpSolution> full(N + 1), fast(N + 1), gen(N + 1);
+  hpipm::OcpQpIpmSolver a(qp, s), b(qp, s), c(qp, s);
+  // default outputs (P, p, K, k, pi[0], statistics, like hpipm-cpp's solve()): the tensor-core kernel with its exports
+  CHECK(a.solve(x0, qp, full) == hpipm::HpipmStatus::Success);
   b.setOutputs(false, false);
-  CHECK(b.solve(x0, qp, fast) == hpipm::HpipmStatus::Success);   // tensor-core kernel
+  CHECK(b.solve(x0, qp, fast) == hpipm::HpipmStatus::Success);   // tensor-core kernel, x / u / pi only
+  setenv("SRBD_K3_GENERIC", "1", 1);
+  CHECK(c.solve(x0, qp, gen) == hpipm::HpipmStatus::Success);    // the generic kernel on the same request as `a`
+  unsetenv("SRBD_K3_GENERIC");
   CHECK(a.getSolverStatistics().iter == b.getSolverStatistics().iter && b.getSolverStatistics().iter > 3);
-  CHECK(full[1].P.rows() == nx && fast[1].P.rows() == 0);
-  bool differ = false;
+  CHECK(a.getSolverStatistics().iter == c.getSolverStatistics().iter);
+  CHECK(full[1].P.rows() == nx && fast[1].P.rows() == 0 && gen[1].P.rows() == nx);
+  bool differ = false, same = true;
   for (int i = 0; i <= N; ++i) {
-    CHECK(approxV(full[i].x, fast[i].x, 1e-9));
-    if (i < N) { CHECK(approxV(full[i].u, fast[i].u, 1e-8)); for (int k = 0; k < nu; ++k) differ = differ || full[i].u(k) != fast[i].u(k); }
+    CHECK(approxV(gen[i].x, fast[i].x, 1e-9));
+    CHECK(approxM(gen[i].P, full[i].P, 1e-6) && approxV(gen[i].p, full[i].p, 1e-6) && approxV(gen[i].pi, full[i].pi, 1e-6));
+    for (int k = 0; k < nx; ++k) same = same && full[i].x(k) == fast[i].x(k);
+    if (i < N) {
+      CHECK(approxV(gen[i].u, fast[i].u, 1e-8));
+      CHECK(approxM(gen[i].K, full[i].K, 1e-6) && approxV(gen[i].k, full[i].k, 1e-6));
+      for (int k = 0; k < nu; ++k) { differ = differ || gen[i].u(k) != fast[i].u(k); same = same && full[i].u(k) == fast[i].u(k); }
+    }
   }
   CHECK(differ);   // (two different kernels: equal to rounding, not bit for bit)
+  CHECK(same);     // (one kernel, with and without the exports: bit for bit)
+  {
+    const auto& sa = a.getSolverStatistics(); const auto& sc = c.getSolverStatistics();
+    CHECK(sa.alpha_prim.size() == sc.alpha_prim.size() && sa.obj.size() == sc.obj.size());
+    for (size_t i = 0; i < sa.alpha_prim.size() && i < sc.alpha_prim.size(); ++i)
+      CHECK(std::abs(sa.alpha_prim[i] - sc.alpha_prim[i]) <= 1e-6 && std::abs(sa.mu[i] - sc.mu[i]) <= 1e-6 * (1.0 + sc.mu[i]) &&
+            std::abs(sa.obj[i] - sc.obj[i]) <= 1e-8 * (1.0 + std::abs(sc.obj[i])));
+  }
   std::printf("SRBD-structured QP through the facade: done (%d iterations on both kernels)\n", b.getSolverStatistics().iter);
 }
 
