@@ -139,6 +139,10 @@ namespace v2 {
 #ifndef SRBD_K3_TMA
 #define SRBD_K3_TMA 8
 #endif
+// residual sweep fused into the factorization sweep (sweep_resfac), throughput instantiations only
+#ifndef SRBD_K3_FUSE
+#define SRBD_K3_FUSE 1
+#endif
 #ifndef SRBD_K3_TMA_SMALL
 #define SRBD_K3_TMA_SMALL 0
 #endif
@@ -1658,6 +1662,488 @@ struct SrbdSolver {
     }
   }
 
+
+  // ------------------------------------------------------------------------------------------------
+  // S6 + S1 FUSED (throughput instantiations): the residual sweep runs BACKWARD inside the factorization sweep.  The
+  // residuals of a stage (res_g, res_b, res_d, res_m) only need the iterate of the stage and of its two neighbours, and the
+  // factorization of stage k consumes exactly those residuals: one pass over the BAbt record, the R tile and the stage
+  // vectors instead of two (15 % less DRAM traffic per iteration, no second tile pipeline).  The convergence test needs the
+  // norms of ALL stages, i.e. the end of the sweep: the factorization of the last (converged) iterate is wasted, one in
+  // thirteen.  Element by element the same operations as residual_sweep + sweep_factor; the duality measure is re-summed
+  // from the stored res_m in forward stage order, so the results are bit-identical to the two separate sweeps.
+  // (Not for the exporting instantiation: hpipm's getters return the factorization the last STEP was computed with.)
+  // ------------------------------------------------------------------------------------------------
+  struct RFraw { double z, pi, lam, t, lo, mk, dz, dpi, dlam, dt, ppi[3], pdpi[3]; };
+  __device__ __forceinline__ RFraw load_rf(int k, bool do_update) const {
+    RFraw v;
+    v.z = ws_ld(wsc(k, v2::oZ));
+    v.pi = 0.0; v.lam = 0.0; v.t = 1.0; v.lo = 0.0; v.mk = 0.0;
+    v.dz = 0.0; v.dpi = 0.0; v.dlam = 0.0; v.dt = 0.0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { v.ppi[j] = 0.0; v.pdpi[j] = 0.0; }
+    if (k > 0) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) v.ppi[j] = ws_ld(wsf(k - 1, v2::oPI) + 4 * j);
+    }
+    if (k < N) {
+      v.pi = ws_ld(wsc(k, v2::oPI)); v.lam = ws_ld(wsc(k, v2::oLAM)); v.t = ws_ld(wsc(k, v2::oT));
+      v.lo = __ldg(gDL(k)); v.mk = __ldg(gMaskL(k));
+    }
+    if (do_update) {
+      v.dz = ws_ld(wsc(k, v2::oDZ));
+      if (k > 0) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) v.pdpi[j] = ws_ld(wsf(k - 1, v2::oDPI) + 4 * j);
+      }
+      if (k < N) {
+        v.dpi = ws_ld(wsc(k, v2::oDPI));
+        v.dt = ws_ld(wsc(k, v2::oDT));
+        v.dlam = ws_ld(wsc(k, v2::oDLAM));
+      }
+    }
+    return v;
+  }
+  __device__ void sweep_resfac(double res[4], double& mu, int nc_mask, bool do_update, double sp, double sd) {
+    constexpr bool kT1 = (kTma & 1) != 0;
+    const double reg = p.a.reg_prim;
+    double* sP = sm + v2::wP;
+    double* sPan = sm + v2::wPAN;
+    const int r = fr, t = ft, pi = fpi;
+    const int gA = (r >> 2) * v2::kGP + 4 * t + (r & 3);
+    const int gB = (pi >> 2) * v2::kGP + 4 * t + (pi & 3);
+    const int prA0 = (25 + r) * 4 + t, prA1 = (r < 4 ? 33 + r : 8 + r) * 4 + t, prA2 = (16 + r) * 4 + t;
+    const int prB0 = (25 + pi) * 4 + t, prB1 = (pi < 4 ? 33 + pi : 8 + pi) * 4 + t, prB2 = (16 + pi) * 4 + t;
+    const int prE0 = r * 4 + t;
+    const int oDt = t * 12 + pi;  // Ac[4kt+t][8I+pi] : + 8 I + 48 kt
+    const int oGT = 4 * pi + t;   // G[4kt+t][8I+pi]  : + 32 I + kGP kt
+    const bool dg0 = (r == t), dg1 = (r == 4 + t);
+    const double regd0 = dg0 ? reg : 0.0, regd1 = dg1 ? reg : 0.0;
+    const int rel0 = ((r >> 2) ? 16 : 0) + (r & 3) + 4 * t;
+    const int rel1 = 48 + (r & 3) + 4 * t;
+    const double qd3 = dg1 ? cQ[t] : 0.0, qd4 = dg0 ? cQ[4 + t] : 0.0, qd5 = dg1 ? cQ[8 + t] : 0.0;
+    const int lc = lane < 24 ? lane : 0;
+    const int j0 = lc < 12 ? 0 : 6;
+    double ng_ = 0.0, nb_ = 0.0, nd_ = 0.0, nm_ = 0.0;
+    // symmetric R block (Q_N at stage N) as B fragments from the lower-triangle tile: element (8I+pi, 4kt+t)
+    auto oRs = [&](int I, int kt) {
+      const int i0 = 8 * I + (I == 1 ? (pi & 3) : pi), c0_ = 4 * kt + t;
+      const int i = i0 >= c0_ ? i0 : c0_, c = i0 >= c0_ ? c0_ : i0;
+      const int pnl = i >> 2;
+      return (pnl == 0 ? 0 : (pnl == 1 ? 16 : 48)) + 4 * c + (i & 3);
+    };
+    // ---- prologue: the R tile of stage N into buffer 1, stage N-1 into buffer 0 ------------------------------------------
+    tiles_begin<kT1>();
+    prefetch_R<kT1>(N, 1);
+    prefetch_G<kT1>(N - 1, 0, 7);
+    prefetch_R<kT1>(N - 1, 0);
+    RFraw raw = load_rf(N, do_update);
+    tiles_wait<kT1>(1);
+    if (kT1) tiles_wait<kT1>(0);   // (cp.async: one wait covers both)
+    __syncwarp();
+    double pk[3];
+    {
+      // stage N: res_g = Q_N z + q_N - pi_{N-1};  P_N = Q_N + reg I, p_N = res_g
+      set_bufs(1);
+      double zN = raw.z;
+      if (do_update) zN += sp * raw.dz;
+      double pp[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { pp[j] = raw.ppi[j]; if (do_update) pp[j] += sd * raw.pdpi[j]; }
+      raw = load_rf(N - 1, do_update);
+      double* zb = sm + v2::wSX;
+      double* pb0 = sm + v2::wXN;   // the vector buffer of trip N-1 (b = 0): [pi | x_{k+1}]
+      if (lane < 24) zb[lane] = lane < 12 ? zN : 0.0;
+      if (lane < 12) pb0[12 + lane] = zN;
+      if (do_update && lane < 12) wsc(N, v2::oZ)[0] = zN;
+      __syncwarp();
+      double zk[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) zk[j] = zb[4 * j + t];
+      double c0[2] = {sR[108 + t], sR[112 + t]}, c1[2] = {sR[116 + t], sR[120 + t]};
+      c1[1] = 0.0;
+#if SRBD_K3_MERGE_HALVES
+      double bdum = 0.0;
+#pragma unroll
+      for (int kt = 0; kt < 3; ++kt) {
+        dmma(c0[0], c0[1], zk[kt], sR[oRs(0, kt)], c0[0], c0[1]);
+        const double r1 = sR[oRs(1, kt)], g1 = sG[oGT + 16 + v2::kGP * kt];
+        dmma(c1[0], bdum, zk[kt], pi < 4 ? r1 : g1, c1[0], bdum);
+      }
+#else
+#pragma unroll
+      for (int kt = 0; kt < 3; ++kt) {
+        dmma(c0[0], c0[1], zk[kt], sR[oRs(0, kt)], c0[0], c0[1]);
+        const double r1 = sR[oRs(1, kt)];
+        dmma(c1[0], c1[1], zk[kt], pi < 4 ? r1 : 0.0, c1[0], c1[1]);
+      }
+#endif
+      c0[0] -= pp[0]; c0[1] -= pp[1]; c1[0] -= pp[2];
+      if (r == 0) { wsf(N, v2::oRG)[0] = c0[0]; wsf(N, v2::oRG)[4] = c0[1]; wsf(N, v2::oRG)[8] = c1[0]; }
+      ng_ = amax_nan(amax_nan(amax_nan(ng_, c0[0]), c0[1]), c1[0]);
+      pk[0] = c0[0]; pk[1] = c0[1]; pk[2] = c1[0];
+      const double* rs = gRecL(N) - kLaneOff * lane;  // Q_N: the R tile of the last stage record
+      if (lane < 12) {
+#pragma unroll
+        for (int c = 0; c < 12; ++c) {
+          if (c <= lane) {
+            double v = __ldg(rs + ((lane >> 2) == 0 ? 0 : ((lane >> 2) == 1 ? 16 : 48)) + 4 * c + (lane & 3));
+            if (c == lane) v += reg;
+            sP[lane * 12 + c] = v;
+            sP[c * 12 + lane] = v;
+          }
+        }
+      }
+      __syncwarp();
+      for (int e = lane; e < 144; e += 32) ws(N - 1, v2::oP)[e] = sP[e];
+      if (r == 0) {
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) wsf(N, v2::oPV)[4 * kt] = pk[kt];
+      }
+    }
+    for (int k = N - 1; k >= 0; --k) {
+      const int b = (N - 1 - k) & 1;
+      const bool xr = k > 0;
+      const int n = xr ? 24 : 12;
+      if (k < N - 1) { tiles_wait<kT1>(b); }
+      __syncwarp();
+      set_bufs(b);
+      // ---- the iterate of stage k (d_update_var_qp on the prefetched vectors) ------------------------------------------
+      double z = raw.z, piv = raw.pi, lam = raw.lam, tt = raw.t;
+      const double lo = raw.lo, mk = raw.mk;
+      double pp[3] = {raw.ppi[0], raw.ppi[1], raw.ppi[2]};
+      if (do_update) {
+        z += sp * raw.dz;
+        piv += sd * raw.dpi;
+        tt += sp * raw.dt;
+        lam += sd * raw.dlam;
+        if (p.a.t_lam_min == 2 && mk != 0.0) {
+          tt = tt < p.a.t_min ? p.a.t_min : tt;
+          lam = lam < p.a.lam_min ? p.a.lam_min : lam;
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) pp[j] += sd * raw.pdpi[j];
+      }
+      if (k > 0) {
+        tiles_begin<kT1>();
+        prefetch_G<kT1>(k - 1, b ^ 1, 7);
+        prefetch_R<kT1>(k - 1, b ^ 1);
+        raw = load_rf(k - 1, do_update);
+      }
+      double* zb = sm + (b ? v2::wSX : v2::wSG);       // z (24)
+      double* lb = sm + (b ? v2::wQX : v2::wqx);       // lam (24)
+      double* pb = sm + v2::wXN + (b ? 24 : 0);        // pi (12) | x_{k+1} (12, written by the previous trip)
+      double* pbn = sm + v2::wXN + (b ? 0 : 24);
+      if (lane < 24) { zb[lane] = lane < n ? z : 0.0; lb[lane] = lam; }
+      if (lane < 12) pb[lane] = piv;
+      if (xr && lane >= 12 && lane < 24) pbn[lane] = z;   // x_k for trip k - 1
+      if (do_update) {
+        if (lane < n) wsc(k, v2::oZ)[0] = z;
+        if (lane < 12) wsc(k, v2::oPI)[0] = piv;
+        if (lane < 24) { wsc(k, v2::oT)[0] = tt; wsc(k, v2::oLAM)[0] = lam; }
+      }
+      __syncwarp();
+      // ---- residuals, fragment form: res_g = H z + g + G pi - [0; pi_{k-1}] - D^T lam ;  res_b = G^T z + b - x_{k+1} -------
+      double c0[2], c1[2], c2[2], rbv[3], rd, rm;
+      {
+        double zk[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) zk[j] = zb[4 * j + t];
+        c0[0] = sR[108 + t]; c0[1] = sR[112 + t]; c1[0] = sR[116 + t]; c1[1] = sR[120 + t]; c2[0] = sR[124 + t]; c2[1] = sR[128 + t];
+        if (!xr) { c1[1] = 0.0; c2[0] = 0.0; c2[1] = 0.0; }
+        const int pbr = (xr ? 6 : 3) * v2::kGP + 4 * t;  // the b row of BAbt: row n
+        double b0[2] = {sG[pbr], sG[pbr + 16]}, b1[2] = {sG[pbr + 32], 0.0};
+#if SRBD_K3_MERGE_HALVES
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {
+          dmma(c0[0], c0[1], zk[kt], sR[oRs(0, kt)], c0[0], c0[1]);
+          const double r1 = sR[oRs(1, kt)], g1 = sG[oGT + 16 + v2::kGP * kt];
+          dmma(c1[0], b1[0], zk[kt], pi < 4 ? r1 : g1, c1[0], b1[0]);
+        }
+#else
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {
+          dmma(c0[0], c0[1], zk[kt], sR[oRs(0, kt)], c0[0], c0[1]);
+          const double r1 = sR[oRs(1, kt)];
+          dmma(c1[0], c1[1], zk[kt], pi < 4 ? r1 : 0.0, c1[0], c1[1]);
+        }
+#endif
+        if (xr) {  // diag(Q) on the x rows 12..23
+          c1[1] = fma(cQ[t], zk[3], c1[1]);
+          c2[0] = fma(cQ[4 + t], zk[4], c2[0]);
+          c2[1] = fma(cQ[8 + t], zk[5], c2[1]);
+        }
+        double pk_[3], nl[6];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) pk_[j] = pb[4 * j + t];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) nl[j] = 0.0 - lb[4 * j + t];
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {  // + G pi
+          dmma(c0[0], c0[1], pk_[kt], sG[gB + 16 * kt], c0[0], c0[1]);
+          dmma(c1[0], c1[1], pk_[kt], sG[gB + 2 * v2::kGP + 16 * kt], c1[0], c1[1]);
+          dmma(c2[0], c2[1], pk_[kt], sG[gB + 4 * v2::kGP + 16 * kt], c2[0], c2[1]);
+        }
+        if (xr) { c1[1] -= pp[0]; c2[0] -= pp[1]; c2[1] -= pp[2]; }
+#pragma unroll
+        for (int kt = 0; kt < 6; ++kt) {  // J^T (lam_u - lam_l) = -D^T lam
+#if SRBD_K3_MERGE_HALVES
+          if (kt < 3) dmma(c0[0], c0[1], nl[kt], cAc[oDt + 48 * kt], c0[0], c0[1]);
+          else dmma(c1[0], c0[1], nl[kt], cAc[oDt + 48 * kt + (pi < 4 ? 8 : 0)], c1[0], c0[1]);
+#else
+          dmma(c0[0], c0[1], nl[kt], cAc[oDt + 48 * kt], c0[0], c0[1]);
+          if (kt >= 3) dmma(c1[0], c1[1], nl[kt], cAc[oDt + 48 * kt + 8], c1[0], c1[1]);
+#endif
+        }
+#if SRBD_K3_MERGE_HALVES
+#pragma unroll
+        for (int kt = 0; kt < 6; ++kt) {
+          dmma(b0[0], b0[1], zk[kt], sG[oGT + v2::kGP * kt], b0[0], b0[1]);  // stage 0: z[12..23] = 0
+          if (kt >= 3) dmma(b1[0], b1[1], zk[kt], sG[oGT + 32 + v2::kGP * kt], b1[0], b1[1]);
+        }
+#else
+#pragma unroll
+        for (int kt = 0; kt < 6; ++kt) {
+          dmma(b0[0], b0[1], zk[kt], sG[oGT + v2::kGP * kt], b0[0], b0[1]);
+          dmma(b1[0], b1[1], zk[kt], sG[oGT + 32 + v2::kGP * kt], b1[0], b1[1]);
+        }
+#endif
+        b0[0] -= pb[12 + t]; b0[1] -= pb[16 + t]; b1[0] -= pb[20 + t];
+        rbv[0] = b0[0]; rbv[1] = b0[1]; rbv[2] = b1[0];
+        if (r == 0) {
+          wsf(k, v2::oRB)[0] = b0[0]; wsf(k, v2::oRB)[4] = b0[1]; wsf(k, v2::oRB)[8] = b1[0];
+          wsf(k, v2::oRG)[0] = c0[0]; wsf(k, v2::oRG)[4] = c0[1]; wsf(k, v2::oRG)[8] = c1[0];
+          if (xr) { wsf(k, v2::oRG)[12] = c1[1]; wsf(k, v2::oRG)[16] = c2[0]; wsf(k, v2::oRG)[20] = c2[1]; }
+        }
+        nb_ = amax_nan(amax_nan(amax_nan(nb_, b0[0]), b0[1]), b1[0]);
+        ng_ = amax_nan(amax_nan(amax_nan(ng_, c0[0]), c0[1]), c1[0]);
+        if (xr) ng_ = amax_nan(amax_nan(amax_nan(ng_, c1[1]), c2[0]), c2[1]);
+        // constraint rows (row-per-lane)
+        double v = 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) v += cAc[lc * 12 + j0 + j] * zb[j0 + j];
+        rd = ((lo - v) + tt) * mk;
+        rm = (lam * tt) * mk;
+        if (lane < 24) {
+          wsc(k, v2::oRD)[0] = rd;
+          wsc(k, v2::oRM)[0] = rm;
+          nd_ = amax_nan(nd_, rd);
+          nm_ = amax_nan(nm_, rm);
+        }
+      }
+      // ---- factorization of stage k (sweep_factor's body on the residuals just formed) -------------------------------------
+      double* gbuf = sm + (b ? v2::wqx : v2::wQX);
+      double* Gbuf = sm + (b ? v2::wSG : v2::wSX);
+      if (lane < 24) {
+        const double ti = 1.0 / tt;
+        Gbuf[lane] = (ti * lam) * mk;
+        gbuf[lane] = (ti * (rm - lam * rd)) * mk;
+      }
+      __syncwarp();
+      double GF[3][3], GPF[3][3], PPF[2][3];
+      {
+        const bool okA1 = xr || r < 4, okB1 = xr || pi < 4;
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {
+          GF[0][kt] = sG[gA + 16 * kt];
+          const double a1 = sG[gA + 2 * v2::kGP + 16 * kt], a2 = sG[gA + 4 * v2::kGP + 16 * kt];
+          GF[1][kt] = okA1 ? a1 : 0.0;
+          GF[2][kt] = xr ? a2 : 0.0;
+          GPF[0][kt] = sG[gB + 16 * kt];
+          const double b1_ = sG[gB + 2 * v2::kGP + 16 * kt], b2_ = sG[gB + 4 * v2::kGP + 16 * kt];
+          GPF[1][kt] = okB1 ? b1_ : 0.0;
+          GPF[2][kt] = xr ? b2_ : 0.0;
+          PPF[0][kt] = sP[pi * 12 + 4 * kt + t];
+          const double p1 = sP[(8 + (pi & 3)) * 12 + 4 * kt + t];
+          PPF[1][kt] = pi < 4 ? p1 : 0.0;
+        }
+      }
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int e2 = lane + 32 * rr;
+        if (e2 < 42) {
+          const int leg = e2 >= 21 ? 1 : 0, e = e2 - 21 * leg;
+          double acc = 0.0;
+#pragma unroll
+          for (int g = 0; g < 12; ++g) acc += Gbuf[12 * leg + g] * cW[(12 * leg + g) * v2::kW2 + e];
+          sm[v2::wS + e2] = acc;
+        }
+      }
+      {
+        double d0[2] = {0.0, 0.0}, d1[2] = {0.0, 0.0};
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {
+          dmma(d0[0], d0[1], rbv[kt], PPF[0][kt], d0[0], d0[1]);
+          dmma(d1[0], d1[1], rbv[kt], PPF[1][kt], d1[0], d1[1]);
+        }
+        if (r == 0) {
+          wsf(k, v2::oPRB)[0] = d0[0]; wsf(k, v2::oPRB)[4] = d0[1]; wsf(k, v2::oPRB)[8] = d1[0];
+        }
+        const double tk[3] = {d0[0] + pk[0], d0[1] + pk[1], d1[0] + pk[2]};
+#pragma unroll
+        for (int kt = 0; kt < 6; ++kt) {
+          const double gam = gbuf[4 * kt + t];
+#if SRBD_K3_MERGE_HALVES
+          if (kt < 3) dmma(c0[0], c0[1], gam, cAc[oDt + 48 * kt], c0[0], c0[1]);
+          else dmma(c1[0], c0[1], gam, cAc[oDt + 48 * kt + (pi < 4 ? 8 : 0)], c1[0], c0[1]);
+#else
+          dmma(c0[0], c0[1], gam, cAc[oDt + 48 * kt], c0[0], c0[1]);
+          if (kt >= 3) dmma(c1[0], c1[1], gam, cAc[oDt + 48 * kt + 8], c1[0], c1[1]);
+#endif
+        }
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {
+          dmma(c0[0], c0[1], tk[kt], GPF[0][kt], c0[0], c0[1]);
+          dmma(c1[0], c1[1], tk[kt], GPF[1][kt], c1[0], c1[1]);
+          dmma(c2[0], c2[1], tk[kt], GPF[2][kt], c2[0], c2[1]);
+        }
+      }
+      double ALF[3][3];
+#pragma unroll
+      for (int I = 0; I < 3; ++I) {
+        double a0 = 0.0, a1 = 0.0, e0 = 0.0, e1 = 0.0;
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {
+          dmma(a0, a1, GF[I][kt], PPF[0][kt], a0, a1);
+          dmma(e0, e1, GF[I][kt], PPF[1][kt], e0, e1);
+        }
+        ALF[I][0] = a0; ALF[I][1] = a1; ALF[I][2] = e0;
+      }
+      double MF[3][6];
+#pragma unroll
+      for (int I = 0; I < 3; ++I)
+#pragma unroll
+        for (int J = 0; J <= I; ++J) {
+          double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+          for (int kt = 0; kt < 3; ++kt) dmma(a0, a1, ALF[I][kt], GPF[J][kt], a0, a1);
+          MF[I][2 * J] = a0; MF[I][2 * J + 1] = a1;
+        }
+      __syncwarp();  // wS visible
+      {
+        double hf[5];
+#pragma unroll
+        for (int f = 0; f < 5; ++f) {
+          const int I = f < 2 ? 0 : 1, pq = f < 2 ? f : f - 2;
+          const bool valid = (8 * I + r < 12) && (4 * pq + t <= 8 * I + r);
+          double v = 0.0;
+          if (valid) v = sR[(I == 0 ? rel0 : rel1) + 16 * pq];
+          if (offS[f] >= 0) v += sm[v2::wS + offS[f]];
+          hf[f] = v;
+        }
+        MF[0][0] = (hf[0] + MF[0][0]) + regd0;
+        MF[0][1] = (hf[1] + MF[0][1]) + regd1;
+        MF[1][0] = hf[2] + MF[1][0];
+        MF[1][1] = hf[3] + MF[1][1];
+        MF[1][2] = (hf[4] + MF[1][2]) + regd0;
+        MF[1][3] = ((xr ? qd3 : 0.0) + MF[1][3]) + regd1;
+        MF[2][4] = ((xr ? qd4 : 0.0) + MF[2][4]) + regd0;
+        MF[2][5] = ((xr ? qd5 : 0.0) + MF[2][5]) + regd1;
+      }
+#pragma unroll
+      for (int pq = 0; pq < 3; ++pq) {
+        double* pan = sPan + pq * v2::kPan;
+        if (pq < 2) pan[prA0] = MF[0][pq];
+        pan[prA1] = MF[1][pq];
+        pan[prA2] = MF[2][pq];
+        pan[prE0] = pq == 0 ? (dg0 ? 1.0 : 0.0) : ((pq == 1 && dg1) ? 1.0 : 0.0);
+        if (r < 4) pan[(8 + r) * 4 + t] = (pq == 2 && dg0) ? 1.0 : 0.0;
+        if (r == 0) pan[96 + t] = pq == 0 ? c0[0] : (pq == 1 ? c0[1] : c1[0]);
+        __syncwarp();
+        const double* dgb = pan + (25 + 4 * pq) * 4;
+        const double a00 = dgb[0];
+        const double2 a1x = *reinterpret_cast<const double2*>(dgb + 4);
+        const double2 a2x = *reinterpret_cast<const double2*>(dgb + 8);
+        const double a22 = dgb[10];
+        const double2 a3x = *reinterpret_cast<const double2*>(dgb + 12);
+        const double2 a3y = *reinterpret_cast<const double2*>(dgb + 14);
+        const int prow = lane < 4 * pq ? 4 + lane : (lane < 12 ? 25 + lane : (lane < 25 ? lane : lane - 25));
+        double2* own = reinterpret_cast<double2*>(pan + prow * 4);
+        const double2 x01 = own[0], x23 = own[1];
+        const double i0 = rsqrt_pivot(a00);
+        const double L10 = a1x.x * i0, L20 = a2x.x * i0, L30 = a3x.x * i0;
+        const double i1 = rsqrt_pivot(fma(-L10, L10, a1x.y));
+        const double L21 = fma(-L20, L10, a2x.y) * i1, L31 = fma(-L30, L10, a3x.y) * i1;
+        const double i2 = rsqrt_pivot(fma(-L21, L21, fma(-L20, L20, a22)));
+        const double L32 = fma(-L31, L21, fma(-L30, L20, a3y.x)) * i2;
+        const double i3 = rsqrt_pivot(fma(-L32, L32, fma(-L31, L31, fma(-L30, L30, a3y.y))));
+        const double l0 = x01.x * i0;
+        const double l1 = fma(-l0, L10, x01.y) * i1;
+        const double l2 = fma(-l1, L21, fma(-l0, L20, x23.x)) * i2;
+        const double l3 = fma(-l2, L32, fma(-l1, L31, fma(-l0, L30, x23.y))) * i3;
+        own[0] = make_double2(l0, l1);
+        own[1] = make_double2(l2, l3);
+        __syncwarp();
+        const double nlv = -pan[96 + t];
+        double dum;
+        if (pq == 0) {
+          const double nA0 = -pan[prA0], nA1 = -pan[prA1], nA2 = -pan[prA2];
+          const double B0 = pan[prB0], B1 = pan[prB1], B2 = pan[prB2];
+          dmma(dum, MF[0][1], nA0, B0, MF[0][0], MF[0][1]);
+          dmma(dum, MF[1][1], nA1, B0, MF[1][0], MF[1][1]);
+          dmma(dum, MF[2][1], nA2, B0, MF[2][0], MF[2][1]);
+          dmma(dum, c0[1], nlv, B0, c0[0], c0[1]);
+          dmma(MF[1][2], MF[1][3], nA1, B1, MF[1][2], MF[1][3]);
+          dmma(MF[2][2], MF[2][3], nA2, B1, MF[2][2], MF[2][3]);
+          dmma(c1[0], c1[1], nlv, B1, c1[0], c1[1]);
+          dmma(MF[2][4], MF[2][5], nA2, B2, MF[2][4], MF[2][5]);
+          dmma(c2[0], c2[1], nlv, B2, c2[0], c2[1]);
+        } else if (pq == 1) {
+          const double nA1 = -pan[prA1], nA2 = -pan[prA2];
+          const double B1 = pan[prB1], B2 = pan[prB2];
+          dmma(MF[1][2], MF[1][3], nA1, B1, MF[1][2], MF[1][3]);
+          dmma(MF[2][2], MF[2][3], nA2, B1, MF[2][2], MF[2][3]);
+          dmma(c1[0], c1[1], nlv, B1, c1[0], c1[1]);
+          dmma(MF[2][4], MF[2][5], nA2, B2, MF[2][4], MF[2][5]);
+          dmma(c2[0], c2[1], nlv, B2, c2[0], c2[1]);
+        } else {
+          const double nA1 = -pan[prA1], nA2 = -pan[prA2];
+          const double B1 = pan[prB1], B2 = pan[prB2];
+          dmma(dum, MF[1][3], nA1, B1, MF[1][2], MF[1][3]);
+          dmma(dum, MF[2][3], nA2, B1, MF[2][2], MF[2][3]);
+          dmma(MF[2][4], MF[2][5], nA2, B2, MF[2][4], MF[2][5]);
+          dmma(dum, c1[1], nlv, B1, c1[0], c1[1]);
+          dmma(c2[0], c2[1], nlv, B2, c2[0], c2[1]);
+        }
+      }
+      if (xr) {
+        if (r >= 4 && t <= r - 4) { sP[(r - 4) * 12 + t] = MF[1][3]; sP[t * 12 + (r - 4)] = MF[1][3]; }
+        sP[(4 + r) * 12 + t] = MF[2][3]; sP[t * 12 + (4 + r)] = MF[2][3];
+        if (t <= r) { sP[(4 + r) * 12 + 4 + t] = MF[2][4]; sP[(4 + t) * 12 + 4 + r] = MF[2][4]; }
+        if (4 + t <= r) { sP[(4 + r) * 12 + 8 + t] = MF[2][5]; sP[(8 + t) * 12 + 4 + r] = MF[2][5]; }
+        pk[0] = c1[1]; pk[1] = c2[0]; pk[2] = c2[1];
+        if (r == 0) {
+          wsf(k, v2::oPV)[0] = pk[0]; wsf(k, v2::oPV)[4] = pk[1]; wsf(k, v2::oPV)[8] = pk[2];
+        }
+        __syncwarp();
+        for (int e = lane; e < 72; e += 32)
+          reinterpret_cast<double2*>(ws(k - 1, v2::oP))[e] = reinterpret_cast<const double2*>(sP)[e];
+      }
+#pragma unroll
+      for (int pq = 0; pq < 3; ++pq) {
+        const double2* src = reinterpret_cast<const double2*>(sPan + pq * v2::kPan);
+        double2* dst = reinterpret_cast<double2*>(ws(k, v2::oFT) + pq * v2::kPanF);
+        const int row = lane >> 1;
+        dst[lane] = src[(row < 12 && row >= 4 * pq + 4) ? lane + 50 : lane];
+        if (lane < 18) dst[32 + lane] = src[32 + lane];
+      }
+    }
+    __syncwarp();
+    const double flag = warp_sum((ng_ != ng_ || nb_ != nb_ || nd_ != nd_ || nm_ != nm_) ? 1.0 : 0.0);
+    res[0] = warp_max(ng_ == ng_ ? ng_ : 0.0);
+    res[1] = warp_max(nb_ == nb_ ? nb_ : 0.0);
+    res[2] = warp_max(nd_ == nd_ ? nd_ : 0.0);
+    res[3] = warp_max(nm_ == nm_ ? nm_ : 0.0);
+    if (flag > 0.0) res[0] = res[0] + __longlong_as_double(0x7ff8000000000000LL);
+    // mu: res_m re-summed in the order of the forward sweep (per row over the stages, then across the rows)
+    double smu = 0.0;
+    if (lane < 24) {
+#pragma unroll 4
+      for (int k = 0; k < N; ++k) smu += ws_ld(wsc(k, v2::oRM));
+    }
+    mu = warp_sum(smu) / (double)nc_mask;
+    __syncwarp();
+  }
+
   __device__ __forceinline__ double shorten(double alpha) const {
     if (alpha < 1.0) {
       if (p.a.alpha_shorten == 0) return alpha * 0.995;
@@ -1715,6 +2201,7 @@ struct SrbdSolver {
     const bool unc = nc_all == 0;
     const int nc_mask = unc ? 1 : nc_all;
     __syncwarp();
+    constexpr bool kFuse = SRBD_K3_FUSE != 0 && !kExp && kTeam == 0;
     double res[4], mu, obj;
     double alpha = 1.0, sp_ = 0.0, sd_ = 0.0;
     int kk = 0;
@@ -1725,7 +2212,8 @@ struct SrbdSolver {
     }
     for (;; ++kk) {
       // residuals of the current iterate (kk > 0: the variable update of the previous iteration is fused in)
-      if (kTeam) SRBD_PROF(0, residuals_team(res, mu, obj, nc_mask, kk > 0, sp_, sd_));
+      if (kFuse) { obj = 0.0; SRBD_PROF(1, sweep_resfac(res, mu, nc_mask, kk > 0, sp_, sd_)); }
+      else if (kTeam) SRBD_PROF(0, residuals_team(res, mu, obj, nc_mask, kk > 0, sp_, sd_));
       else SRBD_PROF(0, residuals(res, mu, obj, nc_mask, kk > 0, sp_, sd_));
       if (kExp && p.stat && lead && (!unc || kk > 0)) {   // row kk: mu, the four residual norms, the objective of iterate kk
         if (!unc) stat_row(kk, 5, &mu, 1);
@@ -1737,7 +2225,7 @@ struct SrbdSolver {
                   (res[0] > a.tol_stat || res[1] > a.tol_eq || res[2] > a.tol_ineq || res[3] > a.tol_comp)))
         break;
       if (lead) {
-      SRBD_PROF(1, sweep_factor());
+      if (!kFuse) SRBD_PROF(1, sweep_factor());
       // KKT solves of this iteration (one call site per sweep: the sweeps are inlined once).  phase 0: affine /
       // only solve (its backward part was done by the factorization sweep), 1: corrector, 2: conditional centering
       double ap, ad;

@@ -82,8 +82,8 @@ int main(int argc, char** argv) {
   std::printf("{\"qps\": %d, \"horizon\": %d, \"ms_per_batch\": %.3f, \"value\": %.1f, \"unit\": \"solves/s\", "
               "\"ms_per_batch_reference_outputs\": %.3f, \"value_reference_outputs\": %.1f, \"converged\": %d, \"iter_mean\": %.3f, "
               "\"h2d_bytes\": %.0f, \"d2h_bytes\": %.0f, "
-              "\"how\": \"hpipm::OcpQpIpmSolver::solveBatch on host std::vector<OcpQp> (setOutputs(false,false): tensor-core kernel; "
-              "_reference_outputs: P,p,K,k + statistics like the reference = generic kernel); best of %d after one warm-up; includes "
+              "\"how\": \"hpipm::OcpQpIpmSolver::solveBatch on host std::vector<OcpQp> (setOutputs(false,false): x, u, pi only; "
+              "_reference_outputs: + P,p,K,k,pi[0] + statistics table like the reference's solve(); both run the tensor-core kernel); best of %d after one warm-up; includes "
               "flattening the Eigen fields into the pinned arena, one H2D copy, pack + structure detection + K3, one D2H copy, scattering "
               "into OcpQpSolution\"}\n",
               B, N, best_fast, B / (best_fast * 1e-3), best_full, B / (best_full * 1e-3), conv, (double)it_sum / B, bytes_up, bytes_down, reps);
