@@ -29,6 +29,8 @@ struct srbd_ctx {
   // NMPC level
   double *d_x = nullptr, *d_u = nullptr, *d_xref = nullptr, *d_x0abs = nullptr, *d_defect = nullptr;
   double* d_srec = nullptr;  // [B][N+1][kSrec] compact stage records (K2 -> SRBD K3 variant)
+  double* d_gdyn = nullptr;  // [B][N][kBabtDyn] stage-dependent chunks of the BAbt records (K1 -> SRBD K3 variant, layout.cuh)
+  bool gdyn_valid = false;   // K1 wrote d_babt and d_gdyn last (not an upload / pack)
   uint8_t* d_contact = nullptr;
   bool have_contact = false;
   double* d_alpha = nullptr; int* d_conv = nullptr; double* d_merit = nullptr;
@@ -272,6 +274,7 @@ int srbd_ctx_create(int device, int batch, const srbd_qp_dims* dims, void* strea
     A(dalloc(&ctx->d_x0abs, B * 12)); A(dalloc(&ctx->d_defect, B * N * 12)); A(dalloc(&ctx->d_contact, B * N * 2));
     A(dalloc(&ctx->d_alpha, B)); A(dalloc(&ctx->d_conv, B)); A(dalloc(&ctx->d_merit, B * 3));
     A(dalloc(&ctx->d_srec, B * S * kSrec));
+    A(dalloc(&ctx->d_gdyn, B * N * kBabtDyn));
   }
   A(dalloc(&ctx->d_babt, B * N * L.babt_stride)); A(dalloc(&ctx->d_rsq, B * S * L.rsq_stride));
   A(dalloc(&ctx->d_dct, B * S * L.dct_stride)); A(dalloc(&ctx->d_d, B * S * L.d_stride));
@@ -333,7 +336,7 @@ int srbd_ctx_destroy(srbd_ctx* ctx) {
                   ctx->d_dmask, ctx->d_raw0, ctx->d_x0, ctx->d_xinit, ctx->d_uinit, ctx->d_out, ctx->d_in, ctx->d_model_qp,
                   ctx->d_flag, ctx->d_P, ctx->d_p, ctx->d_K, ctx->d_k,
                   ctx->d_stat, ctx->d_counter, ctx->d_bstats, ctx->d_ws,
-                  ctx->d_ws2, ctx->d_srec, ctx->d_retry, ctx->d_retry2, ctx->d_active, ctx->d_sqp_iter, ctx->d_r0raw, ctx->d_mpc_x, ctx->d_mpc_u, ctx->d_mpc_xcur,
+                  ctx->d_ws2, ctx->d_srec, ctx->d_gdyn, ctx->d_retry, ctx->d_retry2, ctx->d_active, ctx->d_sqp_iter, ctx->d_r0raw, ctx->d_mpc_x, ctx->d_mpc_u, ctx->d_mpc_xcur,
                   ctx->d_plantA, ctx->d_plantB, ctx->d_plantb, ctx->d_mpc_iter, ctx->d_mpc_status};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -475,6 +478,7 @@ static int launch_linearize(srbd_ctx* ctx, bool raw0) {
   p.B = ctx->B; p.N = ctx->L.N;
   p.x = ctx->d_x; p.u = ctx->d_u; p.x0 = ctx->d_x0abs;
   p.babt = ctx->d_babt; p.defect = ctx->d_defect; p.raw0 = raw0 ? ctx->d_raw0 : nullptr; p.dx0 = ctx->d_x0;
+  p.gdyn = ctx->d_gdyn;
   p.run_gate = ctx->cur_gate;
   const long long total = (long long)p.B * p.N;
   const int grid = (int)((total + kLinThreads - 1) / kLinThreads);
@@ -482,6 +486,7 @@ static int launch_linearize(srbd_ctx* ctx, bool raw0) {
   ctx->launches++;
   CU(cudaGetLastError());
   ctx->raw0_valid = raw0;
+  ctx->gdyn_valid = ctx->d_gdyn != nullptr;
   return SRBD_OK;
 }
 
@@ -730,6 +735,7 @@ int srbd_qp_upload(srbd_ctx* ctx, const srbd_qp_host* qp) {
   CU(cudaGetLastError());
   ctx->packed = true;
   ctx->assembled_mode = -1;
+  ctx->gdyn_valid = false;
   ctx->upload_variant_ok = false;
   if (ctx->is_srbd) {  // SRBD dimensions: does the data have K2's structure?  (decided on the device, aux_kernels.cuh)
     DetectParams dp{};
@@ -805,6 +811,7 @@ static int solve_srbd_variant(srbd_ctx* ctx, const ModelDev* model, const int* g
   const bool team = ctx->B < ctx->sm_count && !(te && te[0] == '0');
   if (!ctx->d_ws2) {
     CU(cudaFuncSetAttribute(ipm_srbd_kernel<SRBD_K3_TMA, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes));
+    CU(cudaFuncSetAttribute(ipm_srbd_kernel<SRBD_K3_TMA, 0, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes));
     CU(cudaFuncSetAttribute(ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes));
     CU(cudaFuncSetAttribute(ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes));
     CU(cudaFuncSetAttribute(ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 0, v2::kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTeamSmem));
@@ -839,7 +846,7 @@ static int solve_srbd_variant(srbd_ctx* ctx, const ModelDev* model, const int* g
   const bool rescue = !(nr && nr[0] == '1');
   SrbdIpmParams p{};
   p.B = ctx->B; p.N = L.N; p.a = ctx->args;
-  p.babt = ctx->d_babt; p.srec = ctx->d_srec; p.x0 = ctx->d_x0;
+  p.babt = ctx->d_babt; p.srec = ctx->d_srec; p.x0 = ctx->d_x0; p.gdyn = ctx->d_gdyn;
   p.model = model; p.ws = ctx->d_ws2;
   p.gate = gate; p.gate_value = 0;
   p.run_gate = ctx->cur_gate; p.frozen = ctx->sqp_loop ? ctx->d_conv : nullptr; p.ws_size = (L.N + 1) * (v2::kStage + v2::kAlt); p.counter = ctx->d_counter;
@@ -868,10 +875,15 @@ static int solve_srbd_variant(srbd_ctx* ctx, const ModelDev* model, const int* g
   // with the facade's exports: the exporting instantiations (cp.async tile engine); their rescue list goes straight to the
   // generic kernel, which exports too
   const bool exports = ctx->export_ric || ctx->export_stat;
+  // QPs linearized by K1 (not QP-level uploads, whose A / B are arbitrary): the BAbt tiles keep the model constants
+  // resident and stream K1's dyn records only (ipm_srbd.cuh: kCG).  SRBD_K3_CG=0: dense records (A/B runs).
+  const char* cge = std::getenv("SRBD_K3_CG");
+  const bool compact = ctx->assembled_mode >= 0 && ctx->gdyn_valid && L.N >= 2 && !(cge && cge[0] == '0');
   if (exports && team) ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 0, v2::kWarps, true><<<ctx->B, 32 * v2::kWarps, kTeamSmem, ctx->stream>>>(p);
   else if (exports) ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 0, 0, true><<<ctx->grid2, 32 * v2::kWarps, v2::kSmemBytes, ctx->stream>>>(p);
   else if (team) ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 0, v2::kWarps><<<ctx->B, 32 * v2::kWarps, kTeamSmem, ctx->stream>>>(p);
   else if (ctx->B < ctx->sm_count) ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 0><<<ctx->grid2, 32 * v2::kWarps, v2::kSmemBytes, ctx->stream>>>(p);
+  else if (compact) ipm_srbd_kernel<SRBD_K3_TMA, 0, 0, false, true><<<ctx->grid2, 32 * v2::kWarps, v2::kSmemBytes, ctx->stream>>>(p);
   else ipm_srbd_kernel<SRBD_K3_TMA, 0><<<ctx->grid2, 32 * v2::kWarps, v2::kSmemBytes, ctx->stream>>>(p);
   ctx->launches++;
   CU(cudaGetLastError());

@@ -48,6 +48,7 @@ struct SrbdIpmParams {
   int B, N;
   srbd_ipm_args a;
   const double* babt;   // [B][N][336]
+  const double* gdyn;   // [B][N][kBabtDyn] stage-dependent chunks of the same records (K1; layout.cuh), kCG instantiations
   const double* srec;   // [B][N+1][kSrec] compact stage records of K2 (srbd_model.cuh: R tile, gradient row, lg, masks)
   const double* x0;     // [B][12]
   const ModelDev* model;
@@ -288,7 +289,14 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b,
 // bit-identical to kTeam = 0 (same operations per element; the duality measure is summed in the original order).
 // kExp: the instantiation that can write the facade's exports (Riccati matrices, pi[0], statistics table); the throughput
 // instantiations carry none of that code.
-template <int kTma, int kPivot, int kTeam, bool kExp>
+// kCG: COMPACT BAbt streaming (QPs linearized by K1 only).  288 of the 336 doubles of a BAbt record are model constants (0, 1,
+// dt, dt/m), the same for every stage of every QP: the warp fills both of its BAbt tiles with them ONCE (from any dense
+// record of a stage >= 1) and then, per stage and sweep, copies only the 36 16-byte chunks that hold a stage-dependent
+// element from K1's dyn record (layout.cuh: babt_dyn_off) over them: 576 instead of 2304 / 2688 bytes per stage and sweep,
+// one or two cp.async per lane instead of six or seven.  The tile is never written by anything else.  Stage 0 takes the
+// same path: its dyn record carries b0 at row 24 (the dense stage-0 record has it at row 12) and finite A^T entries in
+// rows 12..23, which every sweep either masks (xr) or multiplies by dx0 = 0 -- the same exact zeros as before.
+template <int kTma, int kPivot, int kTeam, bool kExp, bool kCG = false>
 struct SrbdSolver {
   const SrbdIpmParams& p;
   int lane, q, N;
@@ -306,6 +314,7 @@ struct SrbdSolver {
   // fragment coordinates of this lane (see the header comment)
   int fr, ft, fpi;
   int offS[5];        // index into the 42 D^T Gamma D sums of this lane's element of the u-block fragments, or -1
+  int gdo;            // kCG: tile offset of dyn chunk `lane`
 
   __device__ SrbdSolver(const SrbdIpmParams& p_, double* cta, double* warp_sm, int warp_global)
       : p(p_), lane(threadIdx.x & 31), q(0), N(p_.N) {
@@ -319,6 +328,7 @@ struct SrbdSolver {
     cred = cta + v2::kCtaShared;
     sG = sm; sF = sm + v2::wF0; sR = sm + v2::wR0;
     fr = lane >> 2; ft = lane & 3; fpi = (fr >> 1) + 4 * (fr & 1);
+    gdo = babt_dyn_off(lane);
 #if SRBD_K3_WBASE
     Wc = W + (lane < 24 ? lane : 0);
     Wf = W + ft;
@@ -363,15 +373,17 @@ struct SrbdSolver {
   const double *qG, *qT;
   __device__ __forceinline__ void set_qp(int qp) {
     q = qp;
-    qG = p.babt + (size_t)q * N * 336 + kLaneOff * lane;
+    qG = kCG ? p.gdyn + (size_t)q * N * kBabtDyn + kLaneOff * lane : p.babt + (size_t)q * N * 336 + kLaneOff * lane;
     qT = p.srec + (size_t)q * (N + 1) * kSrec + kLaneOff * lane;
     asm volatile("" : "+l"(qG), "+l"(qT));
   }
+  __device__ __forceinline__ const double* gDynL(int k) const { return qG + k * kBabtDyn; }   // + 2 * lane
   __device__ __forceinline__ const double* gBAbtL(int k) const { return qG + k * 336; }   // + 2 * lane
   __device__ __forceinline__ const double* gRecL(int k) const { return qT + k * kSrec; }  // + 2 * lane
 #else
   __device__ __forceinline__ void set_qp(int qp) { q = qp; }
   __device__ __forceinline__ const double* gBAbtL(int k) const { return p.babt + ((size_t)q * N + k) * 336 + kLaneOff * lane; }
+  __device__ __forceinline__ const double* gDynL(int k) const { return p.gdyn + ((size_t)q * N + k) * kBabtDyn + kLaneOff * lane; }
   __device__ __forceinline__ const double* gRecL(int k) const {
     return p.srec + ((size_t)q * (N + 1) + k) * kSrec + kLaneOff * lane;
   }
@@ -408,6 +420,7 @@ struct SrbdSolver {
   template <bool TMA>
   __device__ __forceinline__ void tiles_wait(int b) {
     if (TMA) {
+      if (kCG) cp_async_wait_all();   // (the dyn chunks of the BAbt tile travel by cp.async in every sweep)
       if (lane == 0) mbar_arrive(bar(b));
       mbar_wait(bar(b), (tph >> b) & 1u);
       tph ^= 1u << b;
@@ -424,8 +437,14 @@ struct SrbdSolver {
   // BAbt record (panels of 4 rows x 12 = 48 doubles) -> panels of stride kGP; np = 6: rows 0..23, 7: + the b row.
   template <bool TMA>
   __device__ __forceinline__ void prefetch_G(int k, int b, int np = 6) {
-    const double* src = gBAbtL(k);   // + 2 * lane
     double* dst = sm + (b ? v2::wG1 : v2::wG0);
+    if (kCG) {   // the stage-dependent chunks only (chunks 0..11 = the b row: np == 7)
+      const double* dyn = gDynL(k);   // + 2 * lane = chunk `lane`
+      if (np == 7 || lane >= 12) cp_async16(dst + gdo, dyn);
+      if (lane < 4) cp_async16(dst + (lane < 2 ? 210 : 244) + 4 * lane, dyn + 64);   // chunks 32..35
+      return;
+    }
+    const double* src = gBAbtL(k);   // + 2 * lane
     if (TMA) {
       if (lane == 0) {
         mbar_expect_tx(bar(b), np * 384);
@@ -518,6 +537,16 @@ struct SrbdSolver {
     if ((SRBD_K3_L2PF & 4) && lane < 22) l2_prefetch(gBAbtL(k) + 14 * lane);   // BAbt: 2688 B = 21 (+1) lines
     if ((SRBD_K3_L2PF & 8) && with_rec && lane < 12) l2_prefetch(gRecL(k) + 14 * lane);  // stage record: 12 lines
 #endif
+  }
+  // kCG: the constants of a BAbt record into both tiles, once per warp, from a dense record of any stage >= 1 (its
+  // stage-dependent elements are overwritten by the dyn chunks of every stage before the tile is read)
+  __device__ __forceinline__ void fill_G_constants(const double* dense_rec) {
+    for (int e = lane; e < 168; e += 32) {
+      cp_async16(sm + v2::wG0 + 2 * e, dense_rec + 2 * e);
+      cp_async16(sm + v2::wG1 + 2 * e, dense_rec + 2 * e);
+    }
+    cp_async_wait_all();
+    __syncwarp();
   }
   __device__ __forceinline__ void set_bufs(int b) {
     sG = sm + (b ? v2::wG1 : v2::wG0);
@@ -1368,7 +1397,7 @@ struct SrbdSolver {
 #if SRBD_K3_MERGE_HALVES
       // rows 8..11 of H z (first accumulator half) and rows 8..11 of G^T z (res_b, second half) multiply the same z:
       // one DMMA per k-tile for both (at stage N the second half is unused)
-      const int pbr = (k > 0 ? 6 : 3) * v2::kGP + 4 * t;  // the b row of BAbt: row n
+      const int pbr = ((k > 0 || kCG) ? 6 : 3) * v2::kGP + 4 * t;  // the b row of BAbt: row n (kCG: always row 24)
       double b0[2] = {sG[pbr], sG[pbr + 16]}, b1[2] = {sG[pbr + 32], 0.0};
 #pragma unroll
       for (int kt = 0; kt < 3; ++kt) {
@@ -1428,7 +1457,7 @@ struct SrbdSolver {
           if (kt >= 3) dmma(b1[0], b1[1], zk[kt], sG[oGT + 32 + v2::kGP * kt], b1[0], b1[1]);
         }
 #else
-        const int pbr = (k > 0 ? 6 : 3) * v2::kGP + 4 * t;  // the b row of BAbt: row n
+        const int pbr = ((k > 0 || kCG) ? 6 : 3) * v2::kGP + 4 * t;  // the b row of BAbt: row n (kCG: always row 24)
         double b0[2] = {sG[pbr], sG[pbr + 16]}, b1[2] = {sG[pbr + 32], 0.0};
 #pragma unroll
         for (int kt = 0; kt < 6; ++kt) {
@@ -1850,7 +1879,7 @@ struct SrbdSolver {
         for (int j = 0; j < 6; ++j) zk[j] = zb[4 * j + t];
         c0[0] = sR[108 + t]; c0[1] = sR[112 + t]; c1[0] = sR[116 + t]; c1[1] = sR[120 + t]; c2[0] = sR[124 + t]; c2[1] = sR[128 + t];
         if (!xr) { c1[1] = 0.0; c2[0] = 0.0; c2[1] = 0.0; }
-        const int pbr = (xr ? 6 : 3) * v2::kGP + 4 * t;  // the b row of BAbt: row n
+        const int pbr = ((xr || kCG) ? 6 : 3) * v2::kGP + 4 * t;  // the b row of BAbt: row n (kCG: always row 24)
         double b0[2] = {sG[pbr], sG[pbr + 16]}, b1[2] = {sG[pbr + 32], 0.0};
 #if SRBD_K3_MERGE_HALVES
 #pragma unroll
@@ -2342,8 +2371,9 @@ struct SrbdSolver {
 // shared-memory doubles of the team's scratch (between the CTA constants and the warp blocks): [kTeam][6] + 4, whole lines
 constexpr int kTeamShared = 48;
 static_assert(6 * v2::kWarps + 4 <= kTeamShared, "team scratch");
-template <int kTma, int kPivot, int kTeam = 0, bool kExp = false>
+template <int kTma, int kPivot, int kTeam = 0, bool kExp = false, bool kCG = false>
 __global__ void SRBD_K3_BOUNDS ipm_srbd_kernel(const SrbdIpmParams p) {
+  static_assert(!kCG || (kTeam == 0 && !kExp && v2::kGP == 48), "compact BAbt streaming: throughput instantiations, unpadded tile");
   static_assert(kTeam == 0 || kTeam == v2::kWarps, "a team is the whole CTA");
   extern __shared__ __align__(128) double2 smem2[];  // no static shared memory: the tiles start on 128-byte lines
   if (p.gate && *p.gate != p.gate_value) return;
@@ -2370,9 +2400,10 @@ __global__ void SRBD_K3_BOUNDS ipm_srbd_kernel(const SrbdIpmParams p) {
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  SrbdSolver<kTma, kPivot, kTeam, kExp> S(p, smem, smem + v2::kCtaShared + (kTeam ? kTeamShared : 0) + warp * v2::kWarpShared,
+  SrbdSolver<kTma, kPivot, kTeam, kExp, kCG> S(p, smem, smem + v2::kCtaShared + (kTeam ? kTeamShared : 0) + warp * v2::kWarpShared,
                                     kTeam ? blockIdx.x : blockIdx.x * v2::kWarps + warp);
   S.tiles_init();
+  if (kCG) S.fill_G_constants(p.babt + 336);   // (QP 0, stage 1): capi.cu takes this instantiation for N >= 2 only
   if (kTeam) {   // one QP per CTA at a time; the helpers see every solve_one call of their leader
     for (;;) {
       __syncthreads();   // (the previous QP's outputs are written, s_next[0] is free)

@@ -27,6 +27,28 @@ constexpr int kMaxNG = 24;
 constexpr int kMaxNB = 24;
 constexpr int kMaxNC = kMaxNB + kMaxNG;  // per side
 
+// Stage-dependent part of an SRBD BAbt record (K1 -> K3's SRBD variant).  Of the 336 doubles of a dense record only 48
+// depend on the stage (srbd_model.cuh: babt_term); the rest are model constants (0, 1, dt, dt/m) that are the same for
+// every stage of every QP.  K1 therefore also writes a 72-double "dyn" record per (QP, stage): the 36 16-byte chunks of
+// the dense record that contain a stage-dependent element, verbatim (constant neighbours included), chunk c at record
+// offset 2c.  K3 keeps the constants resident in its shared-memory tiles and copies chunk c to tile offset
+// babt_dyn_off(c) (the tile is the dense record as it lies in HBM): 576 instead of 2688 bytes per stage and sweep.
+//   c  0..11 : the b row (24, j), j = c                 c 21..25 : B^T skew block of leg 0, offsets 12..21
+//   c 12..17 : A^T rows 12..15 x columns 0..2           c 26..30 : B^T skew block of leg 1 (rows 6, 7 | row 8)
+//   c 18..20 : A^T rows 16, 17 x columns 0..2           c 31..35 : A^T skew block (rows 18, 19 | row 20)
+constexpr int kBabtDynChunks = 36;
+constexpr int kBabtDyn = 2 * kBabtDynChunks;   // doubles per dyn record
+__host__ __device__ inline int babt_dyn_off(int c) {
+  if (c < 12) return 288 + 4 * c;
+  if (c < 18) return 144 + 2 * (c - 12);
+  if (c < 21) return 192 + 4 * (c - 18);
+  if (c < 26) return 12 + 2 * (c - 21);
+  if (c < 29) return 62 + 4 * (c - 26);
+  if (c < 31) return 108 + 4 * (c - 29);
+  if (c < 34) return 206 + 4 * (c - 31);
+  return 252 + 4 * (c - 34);
+}
+
 __host__ __device__ inline int round4(int v) { return (v + 3) & ~3; }
 __host__ __device__ inline int pm_index(int i, int j, int cn) { return (i >> 2) * 4 * cn + j * 4 + (i & 3); }
 

@@ -207,6 +207,7 @@ struct LinParams {
   const double* u;     // [B][N][12]
   const double* x0;    // [B][12]  (absolute initial state; dx0 = x0 - x[:,0] is embedded into b0)
   double* babt;        // [B][N][28*12] panel-major
+  double* gdyn;        // [B][N][kBabtDyn] stage-dependent chunks of the same records (layout.cuh), or null
   double* defect;      // [B][N][12]
   double* raw0;        // [B][raw0 stride]: A0, B0, b0 (column-major), rest written by K2
   double* dx0;         // [B][12]
@@ -428,6 +429,32 @@ __global__ void __launch_bounds__(kLinThreads, SRBD_K1_MIN_CTAS) linearize_kerne
       for (int e = lane; e < kRec; e += 32) {
         const int pnl = e / 48, rem = e - pnl * 48;
         dst[e] = babt_elem(c, 4 * pnl + (rem & 3), rem >> 2, dt, minv, true);
+      }
+    }
+  }
+  // the dyn records (layout.cuh: babt_dyn_off): the same terms, for the 72 doubles of the 36 stage-dependent chunks.  Stage
+  // 0 is NOT special here: its record carries the b row (b0 with the x0 embedding) at row 24 and finite A^T entries, which
+  // K3 multiplies by dx0 = 0 / masks exactly like the zeros of the dense stage-0 record.
+  if (p.gdyn) {
+    constexpr int kDS = (kBabtDyn + 31) / 32;
+    int dsrc[kDS];
+    double dmul[kDS], dadd[kDS];
+#pragma unroll
+    for (int sl = 0; sl < kDS; ++sl) {
+      const int e = lane + 32 * sl;
+      const int off = babt_dyn_off(e < kBabtDyn ? e >> 1 : 0) + (e & 1), pnl = off / 48, rem = off - pnl * 48;
+      const BabtTerm t = babt_term(4 * pnl + (rem & 3), rem >> 2, dt, minv, false);
+      dsrc[sl] = t.src; dmul[sl] = t.mul; dadd[sl] = t.add;
+    }
+    for (int r = 0; r < 32; ++r) {
+      const long long it = it0 + r;
+      if (it >= total) break;
+      const double* c = sc[warp * 32 + r];
+      double* dst = p.gdyn + (size_t)it * kBabtDyn;
+#pragma unroll
+      for (int sl = 0; sl < kDS; ++sl) {
+        const int e = lane + 32 * sl;
+        if (e < kBabtDyn) dst[e] = fma(dmul[sl], c[dsrc[sl]], dadd[sl]);
       }
     }
   }
