@@ -216,7 +216,10 @@ typedef enum srbd_buf {
   SRBD_BUF_DEFECT = 18,  /* [B][N][12] shooting defect f (SRBD_model.cpp:189-197) */
   SRBD_BUF_STAGE_REC = 19, /* [B][N+1][192] compact stage records written by srbd_assemble next to the dense ones:
                               [R tile 96 | pad 12 | gradient row 24 | pad 12 | lg 24 | lg mask 24], see DESIGN.md section 3 */
-  SRBD_BUF_COUNT = 20
+  SRBD_BUF_BABT_DYN = 20,  /* [B][N][72] the 36 16-byte chunks of each BAbt record that hold a stage-dependent element (written by
+                              srbd_linearize next to the dense records; the SRBD variant of K3 streams these and keeps the model
+                              constants of the record resident in shared memory), see DESIGN.md section 3 */
+  SRBD_BUF_COUNT = 21
 } srbd_buf;
 
 /* ---- defaults ------------------------------------------------------------------------------ */

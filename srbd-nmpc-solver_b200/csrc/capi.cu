@@ -424,6 +424,7 @@ int srbd_ctx_device_ptr(srbd_ctx* ctx, int buf, void** ptr, size_t* bytes) {
     case SRBD_BUF_DMASK: p = ctx->d_dmask; n = B * S * L.d_stride * D; break;
     case SRBD_BUF_DEFECT: p = ctx->d_defect; n = B * N * 12 * D; break;
     case SRBD_BUF_STAGE_REC: p = ctx->d_srec; n = ctx->d_srec ? B * S * kSrec * D : 0; break;
+    case SRBD_BUF_BABT_DYN: p = ctx->gdyn_valid ? ctx->d_gdyn : nullptr; n = p ? B * N * kBabtDyn * D : 0; break;
     default: return fail(ctx, SRBD_ERR_ARG, "unknown buffer id");
   }
   if (buf == SRBD_BUF_RSQRQ || buf == SRBD_BUF_DCT || buf == SRBD_BUF_D || buf == SRBD_BUF_DMASK)

@@ -51,6 +51,21 @@ int main() {
         }
   }
   if (varying != 48) { printf("expected 48 stage-dependent elements, found %d\n", varying); ++bad; }
+  // the dyn chunks of layout.cuh (what K3's compact BAbt streaming copies per stage): 36 disjoint, 16-byte aligned pairs of
+  // the dense record that together contain every stage-dependent element
+  {
+    bool covered[336] = {false};
+    for (int c = 0; c < kBabtDynChunks; ++c) {
+      const int o = babt_dyn_off(c);
+      if (o < 0 || o + 1 >= 336 || (o & 1) || covered[o] || covered[o + 1]) { printf("bad dyn chunk %d at %d\n", c, o); ++bad; continue; }
+      covered[o] = covered[o + 1] = true;
+    }
+    for (int e = 0; e < 336; ++e) {
+      const int pnl = e / 48, rem = e - pnl * 48;
+      const bool dep = babt_term(4 * pnl + (rem & 3), rem >> 2, dt, minv, false).mul != 0.0;
+      if (dep && !covered[e]) { printf("stage-dependent element %d is in no dyn chunk\n", e); ++bad; }
+    }
+  }
   if (bad) { printf("FAIL %d\n", bad); return 1; }
   printf("OK\n");
   return 0;

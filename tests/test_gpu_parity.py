@@ -501,6 +501,56 @@ def test_srbd_ragged_batches_and_tiny_horizons(pkg, orc, N, B):
 
 
 @pytest.mark.gpu
+def test_dyn_records_and_compact_babt_streaming(pkg, monkeypatch):
+    """K1's dyn records (include/srbd_b200.h SRBD_BUF_BABT_DYN; csrc/layout.cuh babt_dyn_off) are a bit-exact excerpt of the
+    dense BAbt records -- every chunk at its offset for stages >= 1; at stage 0 the b row holds what the dense stage-0
+    record keeps in row 12 (b0 with the x0 embedding) -- and everything outside the chunks is the same constant in every
+    record.  K3 with compact BAbt streaming (the default for K1-linearized QPs) and with dense records (SRBD_K3_CG=0)
+    must return bit-identical iterates, iteration counts and residuals."""
+    def off(c):
+        for lo, base, st in ((0, 288, 4), (12, 144, 2), (18, 192, 4), (21, 12, 2), (26, 62, 4), (29, 108, 4), (31, 206, 4),
+                             (34, 252, 4)):
+            nxt = {0: 12, 12: 18, 18: 21, 21: 26, 26: 29, 29: 31, 31: 34, 34: 36}[lo]
+            if lo <= c < nxt:
+                return base + st * (c - lo)
+    B, N = 320, 20          # more QPs than SMs: the throughput instantiations
+    w = perturbed_workload(pkg, B, N, "gait")
+    outs = []
+    for cg in ("1", "0"):
+        monkeypatch.setenv("SRBD_K3_CG", cg)
+        with make_ctx(pkg, B, N) as ctx:
+            ctx.upload_traj(w["x"], w["u"], w["xref"], w["x0"], w["contact"])
+            ctx.linearize(); ctx.assemble(pkg.capi.SRBD_HARD_INEQ); ctx.sync()
+            if cg == "1":
+                dense = ctx.device_tensor(13).reshape(B, N, 336).cpu().numpy()
+                dyn = ctx.device_tensor(20).reshape(B, N, 72).cpu().numpy()
+            ctx.qp_solve()
+            sol = ctx.download_solution(want=("x", "u", "pi", "lam", "t"))
+            st = ctx.download_stats()
+            outs.append((sol, st))
+    inside = np.zeros(336, bool)
+    for c in range(36):
+        o = off(c)
+        inside[o:o + 2] = True
+        if o < 144:      # B^T rows: every stage
+            assert np.array_equal(dyn[:, :, 2 * c:2 * c + 2], dense[:, :, o:o + 2]), c
+        elif c >= 12:    # A^T rows: the dense stage-0 record has no A^T (nx[0] := 0); its dyn record keeps the finite entries
+            assert np.array_equal(dyn[:, 1:, 2 * c:2 * c + 2], dense[:, 1:, o:o + 2]), c
+            assert np.isfinite(dyn[:, 0, 2 * c:2 * c + 2]).all()
+        else:   # the b row: row 24 of an interior record = offsets 288 + 4 j; row 12 of the stage-0 record = 144 + 4 j
+            assert np.array_equal(dyn[:, 1:, 2 * c:2 * c + 2], dense[:, 1:, o:o + 2]), c
+            assert np.array_equal(dyn[:, 0, 2 * c], dense[:, 0, 144 + 4 * c]), c
+    const = dense[:, 1:, ~inside].reshape(-1, int((~inside).sum()))
+    assert (const == const[0]).all()                       # model constants: one pattern for every stage of every QP
+    assert np.array_equal(dense[:, 0, :144][:, ~inside[:144]], const[:B, :int((~inside[:144]).sum())])   # B^T part of stage 0 too
+    (s1, t1), (s0, t0) = outs
+    assert np.array_equal(t1["status"], t0["status"]) and (t1["status"] == 0).mean() > 0.9
+    assert np.array_equal(t1["iter"], t0["iter"]) and np.array_equal(t1["res_max"], t0["res_max"])
+    for k in ("x", "u", "pi", "lam", "t"):
+        assert np.array_equal(s1[k], s0[k]), k
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("mode", [0, 1])
 def test_stage_record_repeats_the_dense_records(pkg, mode):
     """K2's compact stage record (what the SRBD K3 variant reads: include/srbd_b200.h SRBD_BUF_STAGE_REC) must be a
