@@ -281,6 +281,10 @@ int srbd_qp_solve(srbd_ctx* ctx);
  * asking for them returns SRBD_ERR_STATE (never the exports of an earlier solve). */
 int srbd_download_solution(srbd_ctx* ctx, const srbd_sol_host* sol);
 int srbd_download_stats(srbd_ctx* ctx, const srbd_stats_host* st);
+/* Lr of stage 0, [B][nu*nu] column-major lower triangle (zeros above): the Cholesky factor of the last factorization's
+ * stage-0 Hessian, i.e. d_ocp_qp_ipm_get_ric_Lr(qp, arg, ws, 0, Lr) -- what hpipm-cpp's own stage-0 reconstruction reads
+ * (hpipm-cpp/src/ocp_qp_ipm_solver.cpp:352).  Exported together with P, p, K, k (srbd_set_outputs(ctx, 1, ..)). */
+int srbd_download_ric_lr0(srbd_ctx* ctx, double* Lr0);
 /* The same outputs in ONE device-to-host copy: x, u, pi, res_max, iter, status (and lam, t with with_duals = 1) live in one
  * device arena; srbd_out_layout returns their offsets IN DOUBLES inside it (order: x, u, pi, res_max [B][4], iter int32
  * [B], status int32 [B], lam, t) and its total length; srbd_download_packed copies the arena (up to `status` without

@@ -77,6 +77,7 @@ struct srbd_ctx {
   // outputs
   double *d_sol_x = nullptr, *d_sol_u = nullptr, *d_sol_pi = nullptr, *d_sol_lam = nullptr, *d_sol_t = nullptr;
   double *d_P = nullptr, *d_p = nullptr, *d_K = nullptr, *d_k = nullptr, *d_stat = nullptr;
+  double* d_Lr0 = nullptr;   // [B][nu*nu] Cholesky factor of stage 0 (with the Riccati exports; srbd_download_ric_lr0)
   int *d_iter = nullptr, *d_status = nullptr, *d_counter = nullptr;
   double* d_resmax = nullptr;
   srbd_batch_stats* d_bstats = nullptr;
@@ -334,7 +335,7 @@ int srbd_ctx_destroy(srbd_ctx* ctx) {
   void* ptrs[] = {ctx->d_model, ctx->d_x, ctx->d_u, ctx->d_xref, ctx->d_x0abs, ctx->d_defect, ctx->d_contact,
                   ctx->d_alpha, ctx->d_conv, ctx->d_merit, ctx->d_babt, ctx->d_rsq, ctx->d_dct, ctx->d_d,
                   ctx->d_dmask, ctx->d_raw0, ctx->d_x0, ctx->d_xinit, ctx->d_uinit, ctx->d_out, ctx->d_in, ctx->d_model_qp,
-                  ctx->d_flag, ctx->d_P, ctx->d_p, ctx->d_K, ctx->d_k,
+                  ctx->d_flag, ctx->d_P, ctx->d_p, ctx->d_K, ctx->d_k, ctx->d_Lr0,
                   ctx->d_stat, ctx->d_counter, ctx->d_bstats, ctx->d_ws,
                   ctx->d_ws2, ctx->d_srec, ctx->d_gdyn, ctx->d_retry, ctx->d_retry2, ctx->d_active, ctx->d_sqp_iter, ctx->d_r0raw, ctx->d_mpc_x, ctx->d_mpc_u, ctx->d_mpc_xcur,
                   ctx->d_plantA, ctx->d_plantB, ctx->d_plantb, ctx->d_mpc_iter, ctx->d_mpc_status};
@@ -759,6 +760,7 @@ static int launch_generic(srbd_ctx* ctx, const int* qlist, const int* qcount, co
   if (ctx->export_ric && !ctx->d_P) {
     CU(dalloc(&ctx->d_P, B * S * L.nx * L.nx)); CU(dalloc(&ctx->d_p, B * S * L.nx));
     CU(dalloc(&ctx->d_K, B * N * L.nu * L.nx)); CU(dalloc(&ctx->d_k, B * N * L.nu));
+      CU(dalloc(&ctx->d_Lr0, B * L.nu * L.nu));
   }
   if (ctx->export_stat && !ctx->d_stat) CU(dalloc(&ctx->d_stat, B * (size_t)ctx->stat_rows * SRBD_STAT_M));
   IpmParams p{};
@@ -772,7 +774,7 @@ static int launch_generic(srbd_ctx* ctx, const int* qlist, const int* qcount, co
   }
   p.x0 = ctx->d_x0; p.raw0 = ctx->d_raw0; p.ws = ctx->d_ws; p.counter = ctx->d_counter;
   p.sol_x = ctx->d_sol_x; p.sol_u = ctx->d_sol_u; p.sol_pi = ctx->d_sol_pi; p.sol_lam = ctx->d_sol_lam; p.sol_t = ctx->d_sol_t;
-  if (ctx->export_ric) { p.ric_P = ctx->d_P; p.ric_p = ctx->d_p; p.ric_K = ctx->d_K; p.ric_k = ctx->d_k; }
+  if (ctx->export_ric) { p.ric_P = ctx->d_P; p.ric_p = ctx->d_p; p.ric_K = ctx->d_K; p.ric_k = ctx->d_k; p.ric_Lr0 = ctx->d_Lr0; }
   p.iter = ctx->d_iter; p.status = ctx->d_status; p.res_max = ctx->d_resmax;
   p.stat = ctx->export_stat ? ctx->d_stat : nullptr;
   p.stat_rows = ctx->stat_rows;
@@ -862,8 +864,9 @@ static int solve_srbd_variant(srbd_ctx* ctx, const ModelDev* model, const int* g
     if (!ctx->d_P) {
       CU(dalloc(&ctx->d_P, B * S * L.nx * L.nx)); CU(dalloc(&ctx->d_p, B * S * L.nx));
       CU(dalloc(&ctx->d_K, B * N * L.nu * L.nx)); CU(dalloc(&ctx->d_k, B * N * L.nu));
+      CU(dalloc(&ctx->d_Lr0, B * L.nu * L.nu));
     }
-    p.ric_P = ctx->d_P; p.ric_p = ctx->d_p; p.ric_K = ctx->d_K; p.ric_k = ctx->d_k;
+    p.ric_P = ctx->d_P; p.ric_p = ctx->d_p; p.ric_K = ctx->d_K; p.ric_k = ctx->d_k; p.ric_Lr0 = ctx->d_Lr0;
     p.raw0 = ctx->d_raw0; p.raw0_stride = raw0_stride(L);
   }
   if (ctx->export_stat) {
@@ -957,6 +960,17 @@ int srbd_download_solution(srbd_ctx* ctx, const srbd_sol_host* sol) {
   CU(dl(sol->lam, ctx->d_sol_lam, B * (size_t)L.nct)); CU(dl(sol->t, ctx->d_sol_t, B * (size_t)L.nct));
   CU(dl(sol->P, ctx->d_P, B * S * L.nx * L.nx)); CU(dl(sol->p, ctx->d_p, B * S * L.nx));
   CU(dl(sol->K, ctx->d_K, B * N * L.nu * L.nx)); CU(dl(sol->k, ctx->d_k, B * N * L.nu));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SRBD_OK;
+}
+
+int srbd_download_ric_lr0(srbd_ctx* ctx, double* Lr0) {
+  if (!ctx || !Lr0) return SRBD_ERR_ARG;
+  if (!ctx->solved) return fail(ctx, SRBD_ERR_STATE, "solve first");
+  if (!(ctx->d_Lr0 && ctx->ric_valid))
+    return fail(ctx, SRBD_ERR_STATE, "Riccati outputs were not exported by the last solve: call srbd_set_outputs(ctx, 1, ..) first");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(Lr0, ctx->d_Lr0, (size_t)ctx->B * ctx->L.nu * ctx->L.nu * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return SRBD_OK;
 }

@@ -37,6 +37,7 @@ struct IpmParams {
   int* counter;
   double *sol_x, *sol_u, *sol_pi, *sol_lam, *sol_t;
   double *ric_P, *ric_p, *ric_K, *ric_k;  // optional
+  double* ric_Lr0;  // optional (with ric_P): [B][nu*nu] column-major Cholesky factor Lr of stage 0 (d_ocp_qp_ipm_get_ric_Lr(.., 0, ..))
   int* iter;
   int* status;
   double* res_max;
@@ -1012,6 +1013,14 @@ struct Solver {
         }
       }
       __syncwarp();
+    }
+    if (p.ric_Lr0) {   // what hpipm-cpp itself reads for its stage-0 reconstruction (ocp_qp_ipm_solver.cpp:352)
+      const double* Lr = wLr(0);   // row-major
+      double* o = p.ric_Lr0 + (size_t)q * nu * nu;
+      for (int e = lane; e < nu * nu; e += 32) {
+        const int i = e % nu, j = e / nu;
+        o[e] = i >= j ? Lr[i * nu + j] : 0.0;
+      }
     }
     // ---- stage 0 (ocp_qp_ipm_solver.cpp:349-373) from the raw stage-0 blocks -------------------------
     {

@@ -78,6 +78,7 @@ struct SrbdIpmParams {
   // hpipm-cpp/src/ocp_qp_ipm_solver.cpp:337-387): the Riccati matrices of the last factorization, pi[0], and the
   // per-iteration statistics table [B][stat_rows][18]
   double *ric_P, *ric_p, *ric_K, *ric_k;   // null: none
+  double* ric_Lr0;      // optional (with ric_P): [B][144] column-major Cholesky factor Lr of stage 0 (d_ocp_qp_ipm_get_ric_Lr(.., 0, ..))
   const double* raw0;   // [B][raw0_stride] raw stage-0 blocks A0 | B0 | b0 | S0 | Q0 | q0 (column-major), for the stage-0 export
   int raw0_stride;
   double* stat;         // null: none
@@ -1626,6 +1627,22 @@ struct SrbdSolver {
       for (int e = lane; e < 306; e += 32) sPn[e] = ws_ld(ws(0, v2::oFT) + e);
       if (lane < 12) sx_[lane] = ws_ld(zc(0, zs));   // u_0
       __syncwarp();
+      if (p.ric_Lr0 && lane < 12) {
+        // column c = lane of Lr_0 from the factor panels: the rows below the diagonal block are stored as they are, the
+        // diagonal block L_pp is the inverse of X = T_pp^T (T_pp = L_pp^-T is what the blocked solves use)
+        const int pp = lane >> 2, c = lane & 3;
+        double* o = p.ric_Lr0 + (size_t)q * 144 + 12 * lane;
+        for (int i = 0; i < 4 * pp; ++i) o[i] = 0.0;
+        double Lc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int a = c; a < 4; ++a) {
+          double acc = a == c ? 1.0 : 0.0;
+          for (int m = c; m < a; ++m) acc -= pnT(sPn, pp, m, a) * Lc[m];
+          const double d = pnT(sPn, pp, a, a);
+          Lc[a] = d != 0.0 ? acc / d : 0.0;   // (a failed pivot left a zero in the block inverse)
+        }
+        for (int a = 0; a < 4; ++a) o[4 * pp + a] = a >= c ? Lc[a] : 0.0;
+        for (int i = 4 * pp + 4; i < 12; ++i) o[i] = pnL(sPn, i, lane);
+      }
       for (int e = lane; e < 144; e += 32) {
         const int i = e / 12, j = e % 12;
         double a1 = 0.0, a2 = 0.0;
@@ -2164,10 +2181,18 @@ struct SrbdSolver {
     res[3] = warp_max(nm_ == nm_ ? nm_ : 0.0);
     if (flag > 0.0) res[0] = res[0] + __longlong_as_double(0x7ff8000000000000LL);
     // mu: res_m re-summed in the order of the forward sweep (per row over the stages, then across the rows)
+    // (ten loads in flight per trip: the values of the early trips of this sweep have left the L2 -- with four per trip this
+    // loop was 2 % of all stall samples, profiles/r2c)
     double smu = 0.0;
     if (lane < 24) {
-#pragma unroll 4
-      for (int k = 0; k < N; ++k) smu += ws_ld(wsc(k, v2::oRM));
+      for (int k = 0; k < N; k += 10) {
+        double v[10];
+#pragma unroll
+        for (int j = 0; j < 10; ++j) v[j] = k + j < N ? ws_ld(wsc(k + j, v2::oRM)) : 0.0;
+#pragma unroll
+        for (int j = 0; j < 10; ++j)
+          if (k + j < N) smu += v[j];
+      }
     }
     mu = warp_sum(smu) / (double)nc_mask;
     __syncwarp();

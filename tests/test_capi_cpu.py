@@ -27,6 +27,46 @@ def test_every_declared_symbol_is_exported(pkg, lib):
     assert set(names) == set(pkg.capi._EXPORTS)
 
 
+def test_every_hpipm_symbol_is_exported(lib):
+    """include/hpipm_b200_compat.h (SURVEY 8(b) "Option A"): the 54 HPIPM C symbols hpipm-cpp links against -- 7 dim, 10 qp,
+    8 sol, 15 arg, 14 ws / solve / getters -- are exported by the same library, and the ABI-relevant struct sizes are
+    those of the reference's vendored headers on LP64 (13 pointers + int + size_t, ...)."""
+    hdr = open(os.path.join(ROOT, "include", "hpipm_b200_compat.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(d_ocp_qp_[a-z0-9_A-Z]+)\s*\(", hdr)))
+    groups = {"dim": 0, "sol": 0, "arg": 0, "ipm": 0, "qp": 0}
+    for n in names:
+        assert hasattr(lib, n), n
+        key = ("dim" if n.startswith("d_ocp_qp_dim_") else "sol" if n.startswith("d_ocp_qp_sol_") else
+               "arg" if n.startswith("d_ocp_qp_ipm_arg_") else "ipm" if n.startswith("d_ocp_qp_ipm_") else "qp")
+        groups[key] += 1
+    assert groups == {"dim": 7, "qp": 10, "sol": 8, "arg": 15, "ipm": 14}, groups
+    assert hasattr(lib, "hpipm_b200_last_error") and hasattr(lib, "hpipm_b200_pool_size")
+    # no device needed for the host-side objects: memsize / create / setters / getters of the dimensions
+    lib.d_ocp_qp_dim_memsize.restype = C.c_size_t
+    n = lib.d_ocp_qp_dim_memsize(10)
+    assert n >= 13 * 11 * 4
+
+    class Dim(C.Structure):
+        _fields_ = [(f, C.POINTER(C.c_int)) for f in ("nx", "nu", "nb", "nbx", "nbu", "ng", "ns", "nsbx", "nsbu", "nsg",
+                                                      "nbxe", "nbue", "nge")] + [("N", C.c_int), ("memsize", C.c_size_t)]
+    assert C.sizeof(Dim) == 13 * 8 + 8 + 8
+    dim, mem = Dim(), C.create_string_buffer(n)
+    lib.d_ocp_qp_dim_create(10, C.byref(dim), mem)
+    arr = (C.c_int * 11)
+    nx, nu, z = arr(*([12] * 11)), arr(*([4] * 10 + [0])), arr(*([0] * 11))
+    nbx, nbu = arr(*([3] * 11)), arr(*([4] * 10 + [0]))
+    lib.d_ocp_qp_dim_set_all(nx, nu, nbx, nbu, z, z, z, z, C.byref(dim))
+    lib.d_ocp_qp_dim_set_nx(0, 0, C.byref(dim)); lib.d_ocp_qp_dim_set_nbx(0, 0, C.byref(dim)); lib.d_ocp_qp_dim_set_nsbx(0, 0, C.byref(dim))
+    assert dim.N == 10 and dim.nx[0] == 0 and dim.nx[1] == 12 and dim.nb[0] == 4 and dim.nb[1] == 7 and dim.nu[10] == 0
+    lib.d_ocp_qp_memsize.restype = C.c_size_t
+    lib.d_ocp_qp_sol_memsize.restype = C.c_size_t
+    # the quadcopter QP of the reference's test: 10 stages of A, B, Q, S, R (12 x 12, 12 x 4, ...) plus boxes
+    assert lib.d_ocp_qp_memsize(C.byref(dim)) > 10 * (144 + 48 + 144 + 48 + 16) * 8
+    assert lib.d_ocp_qp_sol_memsize(C.byref(dim)) > (11 * 12 * 2 + 10 * 4) * 8
+    assert lib.hpipm_b200_pool_size() == 0   # nothing touched a device
+
+
 def test_defaults_match_oracle(pkg, orc, lib):
     mp, om = pkg.default_model_params(20), orc.model_params(20)
     assert bytes(mp) == bytes(om)

@@ -425,6 +425,24 @@ def test_cpp_host_facades(pkg):
     assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
 
 
+def test_hpipm_c_symbols_in_the_reference_call_order(pkg):
+    """SURVEY 8(b) "Option A": the 54 HPIPM C symbols hpipm-cpp links against (include/hpipm_b200_compat.h), driven in the
+    order of hpipm-cpp/src/ocp_qp_ipm_solver.cpp: the reference's golden vectors at 1e-9, every field equal to the C++
+    facade's (stage 0 reconstructed from Lr0 like the reference does), unconstrained iter == 0, an SRBD-shaped QP through
+    the tensor-core kernel, one pooled device context for fifteen solver objects, status 4 for an unsupported shape."""
+    import importlib.util
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("_srbd_build", os.path.join(root, "srbd-nmpc-solver_b200", "build.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    b.build_host_tests()
+    r = subprocess.run([b.HOST_COMPAT, os.path.join(root, "tests", "golden", "quadcopter_sol.txt")], capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 def test_k3_variants_agree(pkg, monkeypatch):
     """The SRBD throughput variant of K3 (ipm_srbd.cuh, used for K2-assembled HARD_INEQ QPs) and the generic
     kernel (ipm_solve.cuh) run the same algorithm: same iteration counts, iterates within the parity tolerance."""
