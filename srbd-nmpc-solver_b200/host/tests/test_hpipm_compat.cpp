@@ -8,6 +8,8 @@
 // (test/ocp_qp_ipm_solver.cpp:298-314) and, field by field, against the C++ facade of this repository (Option B), which
 // reaches the same kernels through the batch C-ABI.  Needs a CUDA device (run by pytest -m gpu).
 // usage: test_hpipm_compat <tests/golden/quadcopter_sol.txt>
+#include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -333,8 +335,8 @@ static void test_random(bool constrained) {
 
 // an SRBD-shaped QP (nx = nu = 12, 24 general rows with the structure K2 produces): srbd_qp_upload detects the structure and
 // the solve runs in the tensor-core kernel, whose exporting instantiation rebuilds Lr0 from its blocked factor panels
-static void test_srbd_shape() {
-  const int N = 8, nx = 12, nu = 12, ng = 24;
+static std::vector<hpipm::OcpQp> srbdShapedQp(int N) {
+  const int nx = 12, nu = 12, ng = 24;
   std::vector<hpipm::OcpQp> qp(N + 1);
   MatrixXd D(ng, nu);
   for (int leg = 0; leg < 2; ++leg)
@@ -355,6 +357,12 @@ static void test_srbd_shape() {
     qp[i].lg = VectorXd(ng); qp[i].ug = VectorXd(ng); qp[i].ug_mask = VectorXd(ng);   // upper side masked
     for (int g = 0; g < ng; ++g) { qp[i].lg(g) = -1.0 - std::fabs(rnd()); qp[i].ug(g) = 1e10; }
   }
+  return qp;
+}
+
+static void test_srbd_shape() {
+  const int N = 8, nx = 12, nu = 12;
+  std::vector<hpipm::OcpQp> qp = srbdShapedQp(N);
   hpipm::OcpQpIpmSolverSettings s;
   s.ric_alg = 0; s.iter_max = 40; s.split_step = 1;
   for (int pass = 0; pass < 2; ++pass) {
@@ -382,6 +390,31 @@ static void test_srbd_shape() {
   }
 }
 
+// host -> host latency of one solve through the HPIPM symbols (a new solver object per call, like NMPC_solver.cpp:319)
+static void report_latency() {
+  for (int which = 0; which < 2; ++which) {
+    const int N = which == 0 ? 10 : 20;
+    std::vector<hpipm::OcpQp> qp = which == 0 ? quadcopterQp(N) : srbdShapedQp(N);
+    hpipm::OcpQpIpmSolverSettings s;
+    s.ric_alg = 0; s.iter_max = 40; s.split_step = 1;
+    const VectorXd x0(12);
+    std::vector<hpipm::OcpQpSolution> sol(N + 1);
+    std::vector<double> ms;
+    int iters = 0;
+    for (int rep = 0; rep < 60; ++rep) {
+      const auto t0 = std::chrono::steady_clock::now();
+      ReplayedSolver solver(s);
+      CHECK(solver.solve(x0, qp, sol) == hpipm::HpipmStatus::Success);
+      const auto t1 = std::chrono::steady_clock::now();
+      if (rep >= 10) ms.push_back(std::chrono::duration<double, std::milli>(t1 - t0).count());
+      iters = solver.stats.iter;
+    }
+    std::sort(ms.begin(), ms.end());
+    std::printf("latency through the HPIPM symbols, %s N = %d (%d iterations, all exports): p50 %.3f ms, p90 %.3f ms\n",
+                which == 0 ? "quadcopter QP" : "SRBD-shaped QP", N, iters, ms[ms.size() / 2], ms[ms.size() * 9 / 10]);
+  }
+}
+
 static void test_unsupported_shape() {
   const int nx = 4, nu = 2, N = 5;
   auto qp = randomQp(nx, nu, N, 0.5);
@@ -404,6 +437,7 @@ int main(int argc, char** argv) {
   test_random(true);
   test_srbd_shape();
   test_unsupported_shape();
+  report_latency();
   if (g_fail) { std::printf("FAILED: %d checks\n", g_fail); return 1; }
   std::printf("ALL OK\n");
   return 0;
