@@ -849,7 +849,7 @@ static int solve_srbd_variant(srbd_ctx* ctx, const ModelDev* model, const int* g
   const bool rescue = !(nr && nr[0] == '1');
   SrbdIpmParams p{};
   p.B = ctx->B; p.N = L.N; p.a = ctx->args;
-  p.babt = ctx->d_babt; p.srec = ctx->d_srec; p.x0 = ctx->d_x0; p.gdyn = ctx->d_gdyn;
+  p.babt = ctx->d_babt; p.srec = ctx->d_srec; p.x0 = ctx->d_x0; p.gdyn = ctx->d_gdyn; p.asm_mode = ctx->assembled_mode;
   p.model = model; p.ws = ctx->d_ws2;
   p.gate = gate; p.gate_value = 0;
   p.run_gate = ctx->cur_gate; p.frozen = ctx->sqp_loop ? ctx->d_conv : nullptr; p.ws_size = (L.N + 1) * (v2::kStage + v2::kAlt); p.counter = ctx->d_counter;

@@ -48,6 +48,7 @@ struct SrbdIpmParams {
   int B, N;
   srbd_ipm_args a;
   const double* babt;   // [B][N][336]
+  int asm_mode;         // kCG instantiations: the mode srbd_assemble ran in (the row masks follow from it)
   const double* gdyn;   // [B][N][kBabtDyn] stage-dependent chunks of the same records (K1; layout.cuh), kCG instantiations
   const double* srec;   // [B][N+1][kSrec] compact stage records of K2 (srbd_model.cuh: R tile, gradient row, lg, masks)
   const double* x0;     // [B][12]
@@ -394,6 +395,16 @@ struct SrbdSolver {
     return gRecL(k) + 144 + (lane < 24 ? lane : 0) - kLaneOff * lane;
   }
   __device__ __forceinline__ const double* gMaskL(int k) const { return gDL(k) + 24; }
+  // mask of this lane's constraint row.  QPs assembled by K2 (the kCG instantiation): a function of the assemble mode and the
+  // row alone (srbd_model.cuh: 20 hard rows per stage in HARD_INEQ mode -- all but the x^T tau pair of each leg --, none in
+  // BARRIER_SOFT mode), so nothing is loaded; otherwise from the stage record
+  __device__ __forceinline__ double mask_of(int k) const {
+    if (kCG) {
+      const int g = lane < 24 ? lane : 0, rr = g >= 12 ? g - 12 : g;
+      return (p.asm_mode == SRBD_HARD_INEQ && rr < 10) ? 1.0 : 0.0;
+    }
+    return __ldg(gMaskL(k));
+  }
 
   // ---- asynchronous tile prefetch (cp.async, no registers) -------------------------------------------
   // BAbt record (panels of 4 rows x 12 = 48 doubles) -> padded panels; np = 6: rows 0..23, 7: + the b row.
@@ -541,12 +552,24 @@ struct SrbdSolver {
   }
   // kCG: the constants of a BAbt record into both tiles, once per warp, from a dense record of any stage >= 1 (its
   // stage-dependent elements are overwritten by the dyn chunks of every stage before the tile is read)
+  // (one whole contiguous record per tile, once per warp and kernel: the natural job for a TMA bulk copy -- one instruction
+  // per tile from one lane, completion on the warp's mbarrier; the per-stage streams stay on per-lane cp.async, which
+  // measured faster in every sweep, see SRBD_K3_TMA above)
   __device__ __forceinline__ void fill_G_constants(const double* dense_rec) {
-    for (int e = lane; e < 168; e += 32) {
-      cp_async16(sm + v2::wG0 + 2 * e, dense_rec + 2 * e);
-      cp_async16(sm + v2::wG1 + 2 * e, dense_rec + 2 * e);
+    if (kTma) {
+      if (lane == 0) {
+        mbar_expect_tx(bar(0), 2 * 336 * 8);
+        bulk_g2s(sm + v2::wG0, dense_rec, 336 * 8, bar(0));
+        bulk_g2s(sm + v2::wG1, dense_rec, 336 * 8, bar(0));
+      }
+      tiles_wait<true>(0);
+    } else {
+      for (int e = lane; e < 168; e += 32) {
+        cp_async16(sm + v2::wG0 + 2 * e, dense_rec + 2 * e);
+        cp_async16(sm + v2::wG1 + 2 * e, dense_rec + 2 * e);
+      }
+      cp_async_wait_all();
     }
-    cp_async_wait_all();
     __syncwarp();
   }
   __device__ __forceinline__ void set_bufs(int b) {
@@ -564,7 +587,7 @@ struct SrbdSolver {
   struct S1v { double mk, lam, t, rm, rd, rg[6], rb[3]; };
   __device__ __forceinline__ S1v load_s1(int k) const {
     S1v v;
-    v.mk = __ldg(gMaskL(k)); v.lam = ws_ld(wsc(k, v2::oLAM)); v.t = ws_ld(wsc(k, v2::oT));
+    v.mk = mask_of(k); v.lam = ws_ld(wsc(k, v2::oLAM)); v.t = ws_ld(wsc(k, v2::oT));
     v.rm = ws_ld(wsc(k, v2::oRM)); v.rd = ws_ld(wsc(k, v2::oRD));
 #pragma unroll
     for (int j = 0; j < 6; ++j) v.rg[j] = ws_ld(wsf(k, v2::oRG) + 4 * j);
@@ -901,7 +924,7 @@ struct SrbdSolver {
   struct S4v { double mk, dt, dlam, lam, t, rd, rg[6], prb[3]; };
   __device__ __forceinline__ S4v load_s4(int k) const {
     S4v v;
-    v.mk = __ldg(gMaskL(k)); v.dt = ws_ld(wsc(k, v2::oDT));
+    v.mk = mask_of(k); v.dt = ws_ld(wsc(k, v2::oDT));
     v.dlam = ws_ld(wsc(k, v2::oDLAM)); v.lam = ws_ld(wsc(k, v2::oLAM)); v.t = ws_ld(wsc(k, v2::oT));
     v.rd = ws_ld(wsc(k, v2::oRD));
 #pragma unroll
@@ -1047,7 +1070,7 @@ struct SrbdSolver {
   struct S2v { double mk, t, lam, rd, rm, rb[3], pv[3]; };
   __device__ __forceinline__ S2v load_s2(int k) const {
     S2v v;
-    v.mk = __ldg(gMaskL(k)); v.t = ws_ld(wsc(k, v2::oT)); v.lam = ws_ld(wsc(k, v2::oLAM));
+    v.mk = mask_of(k); v.t = ws_ld(wsc(k, v2::oT)); v.lam = ws_ld(wsc(k, v2::oLAM));
     v.rd = ws_ld(wsc(k, v2::oRD)); v.rm = ws_ld(wsc(k, v2::oRM));
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
@@ -1228,7 +1251,7 @@ struct SrbdSolver {
     const int xo = (k + 1 < N ? 12 : 0);
     if (k < N) {
       v.pi = ws_ld(pic(k, zs)); v.lam = ws_ld(wsc(k, v2::oLAM)); v.t = ws_ld(wsc(k, v2::oT));
-      v.xn = ws_ld(zc(k + 1, zs) + xo); v.lo = __ldg(gDL(k)); v.mk = __ldg(gMaskL(k));
+      v.xn = ws_ld(zc(k + 1, zs) + xo); v.lo = __ldg(gDL(k)); v.mk = mask_of(k);
     }
     if (do_update) {
       v.dz = ws_ld(wsc(k, v2::oDZ));
@@ -1733,7 +1756,7 @@ struct SrbdSolver {
     }
     if (k < N) {
       v.pi = ws_ld(wsc(k, v2::oPI)); v.lam = ws_ld(wsc(k, v2::oLAM)); v.t = ws_ld(wsc(k, v2::oT));
-      v.lo = __ldg(gDL(k)); v.mk = __ldg(gMaskL(k));
+      v.lo = __ldg(gDL(k)); v.mk = mask_of(k);
     }
     if (do_update) {
       v.dz = ws_ld(wsc(k, v2::oDZ));
@@ -2228,7 +2251,7 @@ struct SrbdSolver {
       if (k < N) {
         if (lane < 12) wsc(k, v2::oPI)[0] = 0.0;
         if (lane < 24) {
-          const double lo = __ldg(gDL(k)), mk = __ldg(gMaskL(k));
+          const double lo = __ldg(gDL(k)), mk = mask_of(k);
           double tl = 0.0 - lo;
           tl = a.thr0 > tl ? a.thr0 : tl;
           wsc(k, v2::oT)[0] = tl;
