@@ -469,7 +469,7 @@ def main():
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         hbm_peak = json.load(open(peaks_path))["hbm_gbs"] if os.path.exists(peaks_path) else 6650.0
         # HBM view of K1/K2 (write-bound kernels): dense packed records written per step
-        k1_bytes = B * HORIZON * (336 + 72 + 12) * 8 + B * (HORIZON * 2 + 1) * 12 * 8   # dense + dyn records, defect; x, u, x0 read
+        k1_bytes = B * HORIZON * (72 + 12) * 8 + B * (HORIZON * 2 + 1) * 12 * 8   # dyn records + defect written (the dense BAbt records are lazy); x, u, x0 read
         k2_bytes = B * (HORIZON + 1) * 192 * 8  # the compact stage records only (dense RSQrq / DCt / d are materialised lazily)
         roofline["k1_hbm_frac"] = k1_bytes / (roofline["k1_ms"] * 1e-3) / 1e9 / hbm_peak
         roofline["k2_hbm_frac"] = k2_bytes / (roofline["k2_ms"] * 1e-3) / 1e9 / hbm_peak

@@ -31,6 +31,9 @@ struct srbd_ctx {
   double* d_srec = nullptr;  // [B][N+1][kSrec] compact stage records (K2 -> SRBD K3 variant)
   double* d_gdyn = nullptr;  // [B][N][kBabtDyn] stage-dependent chunks of the BAbt records (K1 -> SRBD K3 variant, layout.cuh)
   bool gdyn_valid = false;   // K1 wrote d_babt and d_gdyn last (not an upload / pack)
+  double* d_gconst = nullptr;   // [336] dense BAbt record of (QP 0, stage 1): the model constants of K3's compact BAbt streaming
+  bool babt_dense_valid = false;   // the dense BAbt records of the current linearization exist (else: dyn records only)
+  long long lin_traj_version = -1; // trajectory version K1 last ran on
   uint8_t* d_contact = nullptr;
   bool have_contact = false;
   double* d_alpha = nullptr; int* d_conv = nullptr; double* d_merit = nullptr;
@@ -276,6 +279,7 @@ int srbd_ctx_create(int device, int batch, const srbd_qp_dims* dims, void* strea
     A(dalloc(&ctx->d_alpha, B)); A(dalloc(&ctx->d_conv, B)); A(dalloc(&ctx->d_merit, B * 3));
     A(dalloc(&ctx->d_srec, B * S * kSrec));
     A(dalloc(&ctx->d_gdyn, B * N * kBabtDyn));
+    A(dalloc(&ctx->d_gconst, 336));
   }
   A(dalloc(&ctx->d_babt, B * N * L.babt_stride)); A(dalloc(&ctx->d_rsq, B * S * L.rsq_stride));
   A(dalloc(&ctx->d_dct, B * S * L.dct_stride)); A(dalloc(&ctx->d_d, B * S * L.d_stride));
@@ -337,7 +341,7 @@ int srbd_ctx_destroy(srbd_ctx* ctx) {
                   ctx->d_dmask, ctx->d_raw0, ctx->d_x0, ctx->d_xinit, ctx->d_uinit, ctx->d_out, ctx->d_in, ctx->d_model_qp,
                   ctx->d_flag, ctx->d_P, ctx->d_p, ctx->d_K, ctx->d_k, ctx->d_Lr0,
                   ctx->d_stat, ctx->d_counter, ctx->d_bstats, ctx->d_ws,
-                  ctx->d_ws2, ctx->d_srec, ctx->d_gdyn, ctx->d_retry, ctx->d_retry2, ctx->d_active, ctx->d_sqp_iter, ctx->d_r0raw, ctx->d_mpc_x, ctx->d_mpc_u, ctx->d_mpc_xcur,
+                  ctx->d_ws2, ctx->d_srec, ctx->d_gdyn, ctx->d_gconst, ctx->d_retry, ctx->d_retry2, ctx->d_active, ctx->d_sqp_iter, ctx->d_r0raw, ctx->d_mpc_x, ctx->d_mpc_u, ctx->d_mpc_xcur,
                   ctx->d_plantA, ctx->d_plantB, ctx->d_plantb, ctx->d_mpc_iter, ctx->d_mpc_status};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -397,6 +401,7 @@ int srbd_ctx_sync(srbd_ctx* ctx) {
 }
 
 static int ensure_dense(srbd_ctx* ctx);
+static int ensure_babt(srbd_ctx* ctx);
 
 int srbd_ctx_device_ptr(srbd_ctx* ctx, int buf, void** ptr, size_t* bytes) {
   if (!ctx || !ptr || !bytes) return SRBD_ERR_ARG;
@@ -427,6 +432,11 @@ int srbd_ctx_device_ptr(srbd_ctx* ctx, int buf, void** ptr, size_t* bytes) {
     case SRBD_BUF_STAGE_REC: p = ctx->d_srec; n = ctx->d_srec ? B * S * kSrec * D : 0; break;
     case SRBD_BUF_BABT_DYN: p = ctx->gdyn_valid ? ctx->d_gdyn : nullptr; n = p ? B * N * kBabtDyn * D : 0; break;
     default: return fail(ctx, SRBD_ERR_ARG, "unknown buffer id");
+  }
+  if (buf == SRBD_BUF_BABT) {
+    const long long l0 = ctx->launches;
+    if (int rc = ensure_babt(ctx)) return rc;
+    if (ctx->launches != l0) CU(cudaStreamSynchronize(ctx->stream));
   }
   if (buf == SRBD_BUF_RSQRQ || buf == SRBD_BUF_DCT || buf == SRBD_BUF_D || buf == SRBD_BUF_DMASK)
     if (ctx->packed) {
@@ -474,27 +484,55 @@ int srbd_download_traj(srbd_ctx* ctx, double* x, double* u) {
   return SRBD_OK;
 }
 
-static int launch_linearize(srbd_ctx* ctx, bool raw0) {
+// K1.  raw0: also the raw stage-0 blocks (Riccati exports / getters).  dense: also the dense BAbt records -- the throughput
+// instantiation of the SRBD K3 variant streams the dyn records and takes the model constants from d_gconst, so the dense
+// records (2.7 KB per stage) are written only when something will read them: the generic kernel, the small-batch / exporting
+// instantiations of the variant, a getter (ensure_babt), or -- for the listed QPs only -- the rescue pass (qlist).
+static int launch_linearize(srbd_ctx* ctx, bool raw0, bool dense, const int* qlist = nullptr, const int* qcount = nullptr) {
   CU(cudaSetDevice(ctx->device));
   LinParams p{};
   p.B = ctx->B; p.N = ctx->L.N;
   p.x = ctx->d_x; p.u = ctx->d_u; p.x0 = ctx->d_x0abs;
   p.babt = ctx->d_babt; p.defect = ctx->d_defect; p.raw0 = raw0 ? ctx->d_raw0 : nullptr; p.dx0 = ctx->d_x0;
   p.gdyn = ctx->d_gdyn;
+  p.gconst = qlist ? nullptr : ctx->d_gconst;
+  p.dense = dense ? 1 : 0;
+  p.qlist = qlist; p.qcount = qcount;
   p.run_gate = ctx->cur_gate;
   const long long total = (long long)p.B * p.N;
-  const int grid = (int)((total + kLinThreads - 1) / kLinThreads);
+  const int grid = (int)((total + kLinThreads - 1) / kLinThreads);   // (work list: the blocks beyond it return at once)
   linearize_kernel<<<grid, kLinThreads, 0, ctx->stream>>>(p, ctx->d_model);
   ctx->launches++;
   CU(cudaGetLastError());
-  ctx->raw0_valid = raw0;
-  ctx->gdyn_valid = ctx->d_gdyn != nullptr;
+  if (!qlist) {
+    ctx->raw0_valid = raw0;
+    ctx->gdyn_valid = ctx->d_gdyn != nullptr;
+    ctx->babt_dense_valid = dense;
+    ctx->lin_traj_version = ctx->traj_version;
+  }
   return SRBD_OK;
+}
+
+// does anything read the dense BAbt records of this context's linearizations?  (SRBD_K1_DENSE=1: always write them)
+static bool want_babt_dense(const srbd_ctx* ctx) {
+  const char* d = std::getenv("SRBD_K1_DENSE");
+  const char* cge = std::getenv("SRBD_K3_CG");
+  return (d && d[0] == '1') || (cge && cge[0] == '0') || want_dense(ctx) || ctx->B < ctx->sm_count || ctx->L.N < 2;
+}
+
+// the dense BAbt records for whoever reads them after a dyn-only linearization: re-runs K1 on the unchanged trajectory
+static int ensure_babt(srbd_ctx* ctx) {
+  if (!ctx->gdyn_valid || ctx->babt_dense_valid) return SRBD_OK;   // (uploads: pack_kernel wrote dense records)
+  if (ctx->lin_traj_version != ctx->traj_version)
+    return fail(ctx, SRBD_ERR_STATE, "the dense BAbt records were not written by srbd_linearize (throughput path) and the "
+                                     "trajectory has changed since (line search / upload): read them before, or set "
+                                     "SRBD_K1_DENSE=1");
+  return launch_linearize(ctx, ctx->raw0_valid, true);
 }
 
 int srbd_linearize(srbd_ctx* ctx) {
   if (int rc = require_srbd(ctx)) return rc;
-  return launch_linearize(ctx, want_dense(ctx));
+  return launch_linearize(ctx, want_dense(ctx), want_babt_dense(ctx));
 }
 
 // K2.  dense: also RSQrq / DCt / d / dmask / raw stage-0 blocks; qlist / qcount (device): only those QPs
@@ -545,7 +583,7 @@ static int ensure_dense(srbd_ctx* ctx) {
                                      "trajectory has changed since (line search / upload): read them before, or set "
                                      "SRBD_K2_DENSE=1");
   if (!ctx->raw0_valid)
-    if (int rc = launch_linearize(ctx, true)) return rc;
+    if (int rc = launch_linearize(ctx, true, true)) return rc;
   if (!ctx->dense_valid) {
     if (int rc = launch_assemble(ctx, ctx->assembled_mode, true, nullptr, nullptr)) return rc;
     ctx->dense_valid = true;
@@ -558,8 +596,9 @@ int srbd_download_linearization(srbd_ctx* ctx, double* A, double* Bm, double* b,
   if (!ctx->raw0_valid && (A || b)) {   // stage 0's A and un-embedded b come from the raw blocks
     if (ctx->asm_traj_version != ctx->traj_version && ctx->assembled_mode >= 0)
       return fail(ctx, SRBD_ERR_STATE, "raw stage-0 blocks were not written (throughput path) and the trajectory has changed");
-    if (int rc = launch_linearize(ctx, true)) return rc;
+    if (int rc = launch_linearize(ctx, true, true)) return rc;
   }
+  if (int rc = ensure_babt(ctx)) return rc;
   const QpLayout& L = ctx->L;
   const size_t B = ctx->B, N = L.N;
   std::vector<double> h(B * N * L.babt_stride);
@@ -763,6 +802,8 @@ static int launch_generic(srbd_ctx* ctx, const int* qlist, const int* qcount, co
       CU(dalloc(&ctx->d_Lr0, B * L.nu * L.nu));
   }
   if (ctx->export_stat && !ctx->d_stat) CU(dalloc(&ctx->d_stat, B * (size_t)ctx->stat_rows * SRBD_STAT_M));
+  if (!qlist)
+    if (int rc = ensure_babt(ctx)) return rc;   // (a work list: the caller has linearized the listed QPs densely)
   IpmParams p{};
   p.L = L; p.a = ctx->args; p.B = ctx->B;
   p.babt = ctx->d_babt; p.rsq = ctx->d_rsq; p.dct = ctx->d_dct; p.d = ctx->d_d; p.dmask = ctx->d_dmask;
@@ -849,7 +890,7 @@ static int solve_srbd_variant(srbd_ctx* ctx, const ModelDev* model, const int* g
   const bool rescue = !(nr && nr[0] == '1');
   SrbdIpmParams p{};
   p.B = ctx->B; p.N = L.N; p.a = ctx->args;
-  p.babt = ctx->d_babt; p.srec = ctx->d_srec; p.x0 = ctx->d_x0; p.gdyn = ctx->d_gdyn; p.asm_mode = ctx->assembled_mode;
+  p.babt = ctx->d_babt; p.srec = ctx->d_srec; p.x0 = ctx->d_x0; p.gdyn = ctx->d_gdyn; p.gconst = ctx->d_gconst; p.asm_mode = ctx->assembled_mode;
   p.model = model; p.ws = ctx->d_ws2;
   p.gate = gate; p.gate_value = 0;
   p.run_gate = ctx->cur_gate; p.frozen = ctx->sqp_loop ? ctx->d_conv : nullptr; p.ws_size = (L.N + 1) * (v2::kStage + v2::kAlt); p.counter = ctx->d_counter;
@@ -883,6 +924,8 @@ static int solve_srbd_variant(srbd_ctx* ctx, const ModelDev* model, const int* g
   // resident and stream K1's dyn records only (ipm_srbd.cuh: kCG).  SRBD_K3_CG=0: dense records (A/B runs).
   const char* cge = std::getenv("SRBD_K3_CG");
   const bool compact = ctx->assembled_mode >= 0 && ctx->gdyn_valid && L.N >= 2 && !(cge && cge[0] == '0');
+  if (!compact)
+    if (int rc = ensure_babt(ctx)) return rc;   // every other instantiation streams the dense BAbt records
   if (exports && team) ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 0, v2::kWarps, true><<<ctx->B, 32 * v2::kWarps, kTeamSmem, ctx->stream>>>(p);
   else if (exports) ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 0, 0, true><<<ctx->grid2, 32 * v2::kWarps, v2::kSmemBytes, ctx->stream>>>(p);
   else if (team) ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 0, v2::kWarps><<<ctx->B, 32 * v2::kWarps, kTeamSmem, ctx->stream>>>(p);
@@ -894,6 +937,8 @@ static int solve_srbd_variant(srbd_ctx* ctx, const ModelDev* model, const int* g
   ctx->solved = true;
   ctx->ric_valid = ctx->export_ric;   // (P, p, K, k, pi[0]: only on request; see settings_allow_variant)
   ctx->stat_valid = ctx->export_stat;
+  if (rescue && ctx->gdyn_valid && !ctx->babt_dense_valid)   // the rescue kernels read dense BAbt records: the listed QPs only
+    if (int rc = launch_linearize(ctx, false, true, ctx->d_retry, ctx->d_retry + ctx->B)) return rc;
   if (rescue && exports) {
     if (ctx->assembled_mode >= 0 && !ctx->dense_valid)
       if (int rc = launch_assemble(ctx, ctx->assembled_mode, true, ctx->d_retry, ctx->d_retry + ctx->B)) return rc;

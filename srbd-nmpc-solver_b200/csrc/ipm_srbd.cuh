@@ -49,6 +49,7 @@ struct SrbdIpmParams {
   srbd_ipm_args a;
   const double* babt;   // [B][N][336]
   int asm_mode;         // kCG instantiations: the mode srbd_assemble ran in (the row masks follow from it)
+  const double* gconst; // [336] dense BAbt record of (QP 0, stage 1) (K1): the model constants, kCG instantiations
   const double* gdyn;   // [B][N][kBabtDyn] stage-dependent chunks of the same records (K1; layout.cuh), kCG instantiations
   const double* srec;   // [B][N+1][kSrec] compact stage records of K2 (srbd_model.cuh: R tile, gradient row, lg, masks)
   const double* x0;     // [B][12]
@@ -2451,7 +2452,7 @@ __global__ void SRBD_K3_BOUNDS ipm_srbd_kernel(const SrbdIpmParams p) {
   SrbdSolver<kTma, kPivot, kTeam, kExp, kCG> S(p, smem, smem + v2::kCtaShared + (kTeam ? kTeamShared : 0) + warp * v2::kWarpShared,
                                     kTeam ? blockIdx.x : blockIdx.x * v2::kWarps + warp);
   S.tiles_init();
-  if (kCG) S.fill_G_constants(p.babt + 336);   // (QP 0, stage 1): capi.cu takes this instantiation for N >= 2 only
+  if (kCG) S.fill_G_constants(p.gconst);   // the dense record of (QP 0, stage 1): capi.cu takes this instantiation for N >= 2 only
   if (kTeam) {   // one QP per CTA at a time; the helpers see every solve_one call of their leader
     for (;;) {
       __syncthreads();   // (the previous QP's outputs are written, s_next[0] is free)

@@ -208,6 +208,13 @@ struct LinParams {
   const double* x0;    // [B][12]  (absolute initial state; dx0 = x0 - x[:,0] is embedded into b0)
   double* babt;        // [B][N][28*12] panel-major
   double* gdyn;        // [B][N][kBabtDyn] stage-dependent chunks of the same records (layout.cuh), or null
+  double* gconst;      // [28*12] the dense record of (QP 0, stage 1): the source of the model constants of K3's compact BAbt
+                       // streaming, or null
+  int dense;           // write the dense records (0: only dyn / gconst -- the throughput path of the SRBD K3 variant reads
+                       // nothing else; the dense ones are then materialised lazily, capi.cu: ensure_babt)
+  // optional work list: linearize only the QPs qlist[0 .. *qcount) (dense records for the rescue list of K3, capi.cu)
+  const int* qlist;
+  const int* qcount;
   double* defect;      // [B][N][12]
   double* raw0;        // [B][raw0 stride]: A0, B0, b0 (column-major), rest written by K2
   double* dx0;         // [B][12]
@@ -291,11 +298,14 @@ __global__ void __launch_bounds__(kLinThreads, SRBD_K1_MIN_CTAS) linearize_kerne
     for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
   }
   __syncthreads();
-  const long long total = (long long)p.B * p.N;
+  // items are (QP, stage) pairs; with a work list the QP index is qlist[item / N] and the blocks beyond the list return at once
+  const long long total = (long long)(p.qlist ? *p.qcount : p.B) * p.N;
   const long long item0 = (long long)blockIdx.x * kLinThreads;
+  if (item0 >= total) return;
   const long long item = item0 + threadIdx.x;
   if (item < total) {
-    const int q = (int)(item / p.N), k = (int)(item % p.N);
+    const int qi = (int)(item / p.N), k = (int)(item % p.N);
+    const int q = p.qlist ? p.qlist[qi] : qi;
     double x[12], xn[12], u[12];
     const double* xp = p.x + ((size_t)q * (p.N + 1) + k) * 12;
 #pragma unroll
@@ -413,12 +423,28 @@ __global__ void __launch_bounds__(kLinThreads, SRBD_K1_MIN_CTAS) linearize_kerne
     tsrc[sl] = t.src; tmul[sl] = t.mul; tadd[sl] = t.add;
   }
   const long long it0 = item0 + warp * 32;
+  // record index of item i: (QP, stage) -> q * N + k (with a work list q = qlist[i / N])
+  auto record_of = [&](long long i) -> long long {
+    if (!p.qlist) return i;
+    const long long qi = i / p.N;
+    return (long long)p.qlist[qi] * p.N + (i - qi * p.N);
+  };
   int k = (int)(it0 % p.N);
   for (int r = 0; r < 32; ++r, k = (k + 1 == p.N ? 0 : k + 1)) {
     const long long it = it0 + r;
     if (it >= total) break;
     const double* c = sc[warp * 32 + r];
-    double* dst = p.babt + (size_t)it * kRec;
+    const long long rec = record_of(it);
+    // (the dense record of (QP 0, stage 1) always goes to gconst: K3's compact streaming takes the model constants from it)
+    double* dst = p.dense ? p.babt + (size_t)rec * kRec : ((p.gconst && rec == 1 && k == 1) ? p.gconst : nullptr);
+    if (!dst) continue;
+    if (p.dense && p.gconst && rec == 1 && k == 1) {
+#pragma unroll
+      for (int sl = 0; sl < kSlots; ++sl) {
+        const int e = lane + 32 * sl;
+        if (e < kRec) p.gconst[e] = fma(tmul[sl], c[tsrc[sl]], tadd[sl]);
+      }
+    }
     if (k != 0) {
 #pragma unroll
       for (int sl = 0; sl < kSlots; ++sl) {
@@ -450,7 +476,7 @@ __global__ void __launch_bounds__(kLinThreads, SRBD_K1_MIN_CTAS) linearize_kerne
       const long long it = it0 + r;
       if (it >= total) break;
       const double* c = sc[warp * 32 + r];
-      double* dst = p.gdyn + (size_t)it * kBabtDyn;
+      double* dst = p.gdyn + (size_t)record_of(it) * kBabtDyn;
 #pragma unroll
       for (int sl = 0; sl < kDS; ++sl) {
         const int e = lane + 32 * sl;

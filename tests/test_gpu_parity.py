@@ -638,6 +638,47 @@ def test_rescue_pass_matches_the_generic_kernel(pkg, orc, monkeypatch):
 
 
 @pytest.mark.gpu
+def test_dense_babt_records_are_lazy_on_the_throughput_path(pkg, monkeypatch):
+    """A batch that fills the GPU: srbd_linearize writes the dyn records (+ the constants record) only; the dense BAbt
+    records appear when somebody reads them (getter: K1 re-run on the unchanged trajectory; rescue pass: K1 for the listed
+    QPs only) and a getter after the trajectory has moved fails loudly.  Everything must equal the SRBD_K1_DENSE=1 run bit
+    for bit -- including the knife-edge QP 1007927 (index 20), which the variant alone runs to iter_max and the two-stage
+    rescue re-solves from the lazily written dense records."""
+    from srbd_nmpc_solver_b200.binding import SrbdError
+    B, N, first = 256, 20, 1007927 - 20
+    w = pkg.workload.srbd_batch(B, N=N, contact_mode="stance", start=first)
+    runs = {}
+    for dense in ("1", "0"):
+        monkeypatch.setenv("SRBD_K1_DENSE", dense)
+        with make_ctx(pkg, B, N) as ctx:
+            ctx.upload_traj(w["x"], w["u"], w["xref"], w["x0"], w["contact"])
+            ctx.linearize(); ctx.assemble(pkg.capi.SRBD_HARD_INEQ)
+            l0 = ctx.launch_count
+            ctx.qp_solve()
+            sol = ctx.download_solution(want=("x", "u", "pi", "lam", "t"))
+            st, bs = ctx.download_stats(), ctx.batch_stats()
+            l1 = ctx.launch_count
+            babt = ctx.device_tensor(13).reshape(B, N, 336).cpu().numpy()     # getter: ensure_babt
+            l2 = ctx.launch_count
+            runs[dense] = (sol, st, bs, babt, l1 - l0, l2 - l1)
+        if dense == "0":
+            with make_ctx(pkg, B, N) as ctx:
+                ctx.upload_traj(w["x"], w["u"], w["xref"], w["x0"], w["contact"])
+                ctx.sqp_iterate(pkg.capi.SRBD_HARD_INEQ, do_line_search=True)    # ... and the trajectory moves
+                with pytest.raises(SrbdError, match="dense BAbt records"):
+                    ctx.device_tensor(13)
+    (s1, t1, b1, g1, k1, e1), (s0, t0, b0, g0, k0, e0) = runs["1"], runs["0"]
+    assert t1["status"][20] == 0 and (t1["status"] == 0).all()               # the rescue solved the knife-edge QP
+    assert np.array_equal(t1["iter"], t0["iter"]) and np.array_equal(t1["status"], t0["status"])
+    assert np.array_equal(t1["res_max"], t0["res_max"])
+    for k in ("x", "u", "pi", "lam", "t"):
+        assert np.array_equal(s1[k], s0[k]), k
+    assert b1["solves"] == b0["solves"] == B and b1["iter_sum"] == b0["iter_sum"]
+    assert np.array_equal(g1, g0)                                             # the lazily written dense records
+    assert k0 == k1 + 1 and e1 == 0 and e0 == 1      # one more launch in the solve (K1 for the rescue list), one for the getter
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("generic", ["0", "1"])
 def test_failed_pivot_zeroes_the_component_on_gpu(pkg, orc, monkeypatch, generic):
     """Both K3 kernels on the QP of tests/test_oracle_qp.py::test_failed_pivot_zeroes_the_component (all stance, N=50): a
