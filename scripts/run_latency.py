@@ -20,5 +20,10 @@ ts = []
 for _ in range(reps):
     t0 = time.perf_counter(); ctx.qp_solve(); ctx.sync(); ts.append(time.perf_counter() - t0)
 st = ctx.download_stats()
+if os.environ.get("SRBD_PROF"):   # a -DSRBD_K3_PROFILE=1 build: per-sweep clock64 sums of the last solve (leader warp)
+    h = ctx.batch_stats()["iter_hist"][48:53]
+    it = float(st["iter"].sum()) * N
+    print("cycles per stage and iteration: residual %.0f  factor %.0f  backvec %.0f  forward(pred) %.0f  forward(fin) %.0f  | total %.0f" % (
+        *[v / it for v in h], sum(h) / it))
 print("B=%d N=%d iters=%s status=%s  K3 p50 %.1f us  p99 %.1f us  lib=%s" % (
     B, N, st["iter"][:4], st["status"][:4], 1e6 * np.percentile(ts, 50), 1e6 * np.percentile(ts, 99), os.environ.get("SRBD_LIB", "in-tree")))
