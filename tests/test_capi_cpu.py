@@ -67,6 +67,32 @@ def test_every_hpipm_symbol_is_exported(lib):
     assert lib.hpipm_b200_pool_size() == 0   # nothing touched a device
 
 
+def test_hpipm_struct_layout_matches_the_vendored_headers(tmp_path):
+    """ABI of include/hpipm_b200_compat.h: sizes and member offsets of the five HPIPM structs (and the enum values) equal
+    those of the reference's vendored headers (hpipm-cpp/include/include/hpipm_d_ocp_qp{_dim,,_sol,_ipm}.h, LP64).  The
+    expected lines were produced in the build container by compiling tests/cpu_progs/hpipm_abi_layout.c with -DUSE_VENDORED
+    against those headers (the reference tree is not available where the tests run)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("gcc not available")
+    exe = str(tmp_path / "hpipm_abi_layout")
+    r = subprocess.run([gcc, "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpu_progs", "hpipm_abi_layout.c"),
+                        "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([exe], capture_output=True, text=True).stdout.strip().splitlines()
+    assert out == [
+        "dim 120 N 104 memsize 112",
+        "qp 120 BAbt 8 idxb 80 diag_H_flag 104 memsize 112",
+        "sol 56 ux 8 misc 40 memsize 48",
+        "arg 160 mu0 0 tau_min 72 iter_max 80 stat_max 84 pred_corr 88 warm_start 104 square_root_alg 108 lq_fact 112 "
+        "split_step 132 t_lam_min 140 mode 144 memsize 152",
+        "ws 304 qp_res 0 core_workspace 32 dim 40 stat 232 iter 256 stat_max 260 stat_m 264 status 272 valid_ric_p 292 memsize 296",
+        "enums 0 1 2 3 | 0 1 2 3 4",
+    ], out
+
+
 def test_defaults_match_oracle(pkg, orc, lib):
     mp, om = pkg.default_model_params(20), orc.model_params(20)
     assert bytes(mp) == bytes(om)
