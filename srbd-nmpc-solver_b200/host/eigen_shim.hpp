@@ -2,7 +2,7 @@
 // Eigen is not available in this build image, so the facades compile against this minimal column-major
 // stand-in; when <Eigen/Core> exists the real library is used instead and nothing here is compiled.
 #pragma once
-#if __has_include(<Eigen/Core>)
+#if __has_include(<Eigen/Core>) && !defined(SRBD_FORCE_EIGEN_SHIM)   // (the reference-wrapper build of test_hpipm_compat.cpp puts an empty Eigen/Core stub on the path)
 #include <Eigen/Core>
 #else
 #include <cstddef>

@@ -17,7 +17,25 @@
 #include <string>
 #include <vector>
 
+// Two builds of this file:
+//  * default: against include/hpipm_b200_compat.h, the five HPIPM objects in blocks this file allocates;
+//  * -DSRBD_TEST_REFERENCE_WRAPPERS (the `ref` recipe of the test infrastructure; only where the reference tree exists): against the
+//    reference's VENDORED HPIPM headers, with the five objects owned by the reference's OWN memory-management classes
+//    hpipm::d_ocp_qp_{dim,,sol,ipm_arg,ipm_ws}_wrapper, whose unmodified sources (hpipm-cpp/src/detail/*.cpp) are
+//    compiled from where they lie and linked against libsrbd_b200.so: reference object code running on this library.
+#ifdef SRBD_TEST_REFERENCE_WRAPPERS
+#include "hpipm-cpp/detail/d_ocp_qp_dim_wrapper.hpp"
+#include "hpipm-cpp/detail/d_ocp_qp_ipm_arg_wrapper.hpp"
+#include "hpipm-cpp/detail/d_ocp_qp_ipm_ws_wrapper.hpp"
+#include "hpipm-cpp/detail/d_ocp_qp_sol_wrapper.hpp"
+#include "hpipm-cpp/detail/d_ocp_qp_wrapper.hpp"
+extern "C" {
+const char* hpipm_b200_last_error(void);
+int hpipm_b200_pool_size(void);
+}
+#else
 #include "../../../include/hpipm_b200_compat.h"
+#endif
 #include "../hpipm-cpp/hpipm-cpp.hpp"
 
 using Eigen::MatrixXd;
@@ -46,14 +64,27 @@ static bool approx(const double* a, const double* b, int n, double prec) {  // E
 struct ReplayedSolver {
   hpipm::OcpQpIpmSolverSettings settings;
   hpipm::OcpQpDim dim;
+#ifdef SRBD_TEST_REFERENCE_WRAPPERS
+  // the reference's wrapper_holder_ (ocp_qp_ipm_solver.cpp:15-37): dim and arg shared, qp / sol / ws by value
+  std::shared_ptr<hpipm::d_ocp_qp_dim_wrapper> dim_w = std::make_shared<hpipm::d_ocp_qp_dim_wrapper>();
+  std::shared_ptr<hpipm::d_ocp_qp_ipm_arg_wrapper> arg_w = std::make_shared<hpipm::d_ocp_qp_ipm_arg_wrapper>();
+  hpipm::d_ocp_qp_wrapper qp_w;
+  hpipm::d_ocp_qp_sol_wrapper sol_w;
+  hpipm::d_ocp_qp_ipm_ws_wrapper ws_w;
+#else
   d_ocp_qp_dim dim_h{};
   d_ocp_qp qp_h{};
   d_ocp_qp_sol sol_h{};
   d_ocp_qp_ipm_arg arg_h{};
   d_ocp_qp_ipm_ws ws_h{};
   std::vector<char> dim_mem, qp_mem, sol_mem, arg_mem, ws_mem;
+#endif
+  d_ocp_qp_dim* dim_p = nullptr;
+  d_ocp_qp* qp_p = nullptr;
+  d_ocp_qp_sol* sol_p = nullptr;
+  d_ocp_qp_ipm_arg* arg_p = nullptr;
+  d_ocp_qp_ipm_ws* ws_p = nullptr;
   hpipm::OcpQpIpmSolverStatistics stats;
-  bool sized = false;
 
   explicit ReplayedSolver(const hpipm::OcpQpIpmSolverSettings& s) : settings(s) {}
 
@@ -61,41 +92,56 @@ struct ReplayedSolver {
     const hpipm_mode m = settings.mode == hpipm::HpipmMode::SpeedAbs ? SPEED_ABS
                          : settings.mode == hpipm::HpipmMode::Balance ? BALANCE
                          : settings.mode == hpipm::HpipmMode::Robust ? ROBUST : SPEED;
-    d_ocp_qp_ipm_arg_set_default(m, &arg_h);
-    d_ocp_qp_ipm_arg_set_mu0(&settings.mu0, &arg_h);
-    d_ocp_qp_ipm_arg_set_iter_max(&settings.iter_max, &arg_h);
-    d_ocp_qp_ipm_arg_set_alpha_min(&settings.alpha_min, &arg_h);
-    d_ocp_qp_ipm_arg_set_tol_stat(&settings.tol_stat, &arg_h);
-    d_ocp_qp_ipm_arg_set_tol_eq(&settings.tol_eq, &arg_h);
-    d_ocp_qp_ipm_arg_set_tol_ineq(&settings.tol_ineq, &arg_h);
-    d_ocp_qp_ipm_arg_set_tol_comp(&settings.tol_comp, &arg_h);
-    d_ocp_qp_ipm_arg_set_reg_prim(&settings.reg_prim, &arg_h);
-    d_ocp_qp_ipm_arg_set_warm_start(&settings.warm_start, &arg_h);
-    d_ocp_qp_ipm_arg_set_pred_corr(&settings.pred_corr, &arg_h);
-    d_ocp_qp_ipm_arg_set_ric_alg(&settings.ric_alg, &arg_h);
-    d_ocp_qp_ipm_arg_set_split_step(&settings.split_step, &arg_h);
+    d_ocp_qp_ipm_arg_set_default(m, arg_p);
+    d_ocp_qp_ipm_arg_set_mu0(&settings.mu0, arg_p);
+    d_ocp_qp_ipm_arg_set_iter_max(&settings.iter_max, arg_p);
+    d_ocp_qp_ipm_arg_set_alpha_min(&settings.alpha_min, arg_p);
+    d_ocp_qp_ipm_arg_set_tol_stat(&settings.tol_stat, arg_p);
+    d_ocp_qp_ipm_arg_set_tol_eq(&settings.tol_eq, arg_p);
+    d_ocp_qp_ipm_arg_set_tol_ineq(&settings.tol_ineq, arg_p);
+    d_ocp_qp_ipm_arg_set_tol_comp(&settings.tol_comp, arg_p);
+    d_ocp_qp_ipm_arg_set_reg_prim(&settings.reg_prim, arg_p);
+    d_ocp_qp_ipm_arg_set_warm_start(&settings.warm_start, arg_p);
+    d_ocp_qp_ipm_arg_set_pred_corr(&settings.pred_corr, arg_p);
+    d_ocp_qp_ipm_arg_set_ric_alg(&settings.ric_alg, arg_p);
+    d_ocp_qp_ipm_arg_set_split_step(&settings.split_step, arg_p);
   }
 
   void resize(const std::vector<hpipm::OcpQp>& qp) {   // :120-146 + detail/*_wrapper.cpp (memsize -> malloc -> create)
     dim.resize(qp);
     const int N = (int)dim.N;
+#ifdef SRBD_TEST_REFERENCE_WRAPPERS
+    dim_w->resize(N);
+    dim_p = dim_w->get();
+    arg_p = arg_w->get();
+#else
     dim_mem.assign(d_ocp_qp_dim_memsize(N), 0);
     d_ocp_qp_dim_create(N, &dim_h, dim_mem.data());
+    dim_p = &dim_h;
+    arg_mem.assign(d_ocp_qp_ipm_arg_memsize(dim_p), 0);
+    arg_p = &arg_h;
+    d_ocp_qp_ipm_arg_create(dim_p, arg_p, arg_mem.data());
+#endif
     d_ocp_qp_dim_set_all(dim.nx.data(), dim.nu.data(), dim.nbx.data(), dim.nbu.data(), dim.ng.data(), dim.nsbx.data(),
-                         dim.nsbu.data(), dim.nsg.data(), &dim_h);
-    d_ocp_qp_dim_set_nx(0, 0, &dim_h);
-    d_ocp_qp_dim_set_nbx(0, 0, &dim_h);
-    d_ocp_qp_dim_set_nsbx(0, 0, &dim_h);
-    arg_mem.assign(d_ocp_qp_ipm_arg_memsize(&dim_h), 0);
-    d_ocp_qp_ipm_arg_create(&dim_h, &arg_h, arg_mem.data());
+                         dim.nsbu.data(), dim.nsg.data(), dim_p);
+    d_ocp_qp_dim_set_nx(0, 0, dim_p);
+    d_ocp_qp_dim_set_nbx(0, 0, dim_p);
+    d_ocp_qp_dim_set_nsbx(0, 0, dim_p);
     applySettings();
-    qp_mem.assign(d_ocp_qp_memsize(&dim_h), 0);
-    d_ocp_qp_create(&dim_h, &qp_h, qp_mem.data());
-    sol_mem.assign(d_ocp_qp_sol_memsize(&dim_h), 0);
-    d_ocp_qp_sol_create(&dim_h, &sol_h, sol_mem.data());
-    ws_mem.assign(d_ocp_qp_ipm_ws_memsize(&dim_h, &arg_h), 0);
-    d_ocp_qp_ipm_ws_create(&dim_h, &arg_h, &ws_h, ws_mem.data());
-    sized = true;
+#ifdef SRBD_TEST_REFERENCE_WRAPPERS
+    qp_w.resize(dim_w);
+    sol_w.resize(dim_w);
+    ws_w.resize(dim_w, arg_w);
+    qp_p = qp_w.get(); sol_p = sol_w.get(); ws_p = ws_w.get();
+#else
+    qp_p = &qp_h; sol_p = &sol_h; ws_p = &ws_h;
+    qp_mem.assign(d_ocp_qp_memsize(dim_p), 0);
+    d_ocp_qp_create(dim_p, qp_p, qp_mem.data());
+    sol_mem.assign(d_ocp_qp_sol_memsize(dim_p), 0);
+    d_ocp_qp_sol_create(dim_p, sol_p, sol_mem.data());
+    ws_mem.assign(d_ocp_qp_ipm_ws_memsize(dim_p, arg_p), 0);
+    d_ocp_qp_ipm_ws_create(dim_p, arg_p, ws_p, ws_mem.data());
+#endif
   }
 
   hpipm::HpipmStatus solve(const VectorXd& x0, std::vector<hpipm::OcpQp>& qp, std::vector<hpipm::OcpQpSolution>& sol) {
@@ -131,41 +177,41 @@ struct ReplayedSolver {
     }
     d_ocp_qp_set_all(A.data(), B.data(), b.data(), Q.data(), S.data(), R.data(), q.data(), r.data(), idxbx.data(), lbx.data(),
                      ubx.data(), idxbu.data(), lbu.data(), ubu.data(), C.data(), D.data(), lg.data(), ug.data(), Zl.data(),
-                     Zu.data(), zl.data(), zu.data(), idxs.data(), lls.data(), lus.data(), &qp_h);
+                     Zu.data(), zl.data(), zu.data(), idxs.data(), lls.data(), lus.data(), qp_p);
     // :291-321
     for (int i = 1; i <= N; ++i) {
-      if (qp[i].lbx_mask.size() == dim.nbx[i]) d_ocp_qp_set_lbx_mask(i, qp[i].lbx_mask.data(), &qp_h);
-      if (qp[i].ubx_mask.size() == dim.nbx[i]) d_ocp_qp_set_ubx_mask(i, qp[i].ubx_mask.data(), &qp_h);
+      if (qp[i].lbx_mask.size() == dim.nbx[i]) d_ocp_qp_set_lbx_mask(i, qp[i].lbx_mask.data(), qp_p);
+      if (qp[i].ubx_mask.size() == dim.nbx[i]) d_ocp_qp_set_ubx_mask(i, qp[i].ubx_mask.data(), qp_p);
     }
     for (int i = 0; i < N; ++i) {
-      if (qp[i].lbu_mask.size() == dim.nbu[i]) d_ocp_qp_set_lbu_mask(i, qp[i].lbu_mask.data(), &qp_h);
-      if (qp[i].ubu_mask.size() == dim.nbu[i]) d_ocp_qp_set_ubu_mask(i, qp[i].ubu_mask.data(), &qp_h);
+      if (qp[i].lbu_mask.size() == dim.nbu[i]) d_ocp_qp_set_lbu_mask(i, qp[i].lbu_mask.data(), qp_p);
+      if (qp[i].ubu_mask.size() == dim.nbu[i]) d_ocp_qp_set_ubu_mask(i, qp[i].ubu_mask.data(), qp_p);
     }
     for (int i = 0; i <= N; ++i) {
-      if (qp[i].lg_mask.size() == dim.ng[i]) d_ocp_qp_set_lg_mask(i, qp[i].lg_mask.data(), &qp_h);
-      if (qp[i].ug_mask.size() == dim.ng[i]) d_ocp_qp_set_ug_mask(i, qp[i].ug_mask.data(), &qp_h);
+      if (qp[i].lg_mask.size() == dim.ng[i]) d_ocp_qp_set_lg_mask(i, qp[i].lg_mask.data(), qp_p);
+      if (qp[i].ug_mask.size() == dim.ng[i]) d_ocp_qp_set_ug_mask(i, qp[i].ug_mask.data(), qp_p);
     }
     // :323-345
     if (settings.warm_start)
       for (int i = 0; i < N; ++i) {
-        d_ocp_qp_sol_set_x(i + 1, sol[i + 1].x.data(), &sol_h);
-        d_ocp_qp_sol_set_u(i, sol[i].u.data(), &sol_h);
+        d_ocp_qp_sol_set_x(i + 1, sol[i + 1].x.data(), sol_p);
+        d_ocp_qp_sol_set_u(i, sol[i].u.data(), sol_p);
       }
-    d_ocp_qp_ipm_solve(&qp_h, &sol_h, &arg_h, &ws_h);
+    d_ocp_qp_ipm_solve(qp_p, sol_p, arg_p, ws_p);
     sol[0].x = x0;
     for (int i = 0; i < N; ++i) {
-      d_ocp_qp_sol_get_x(i + 1, &sol_h, sol[i + 1].x.data());
-      d_ocp_qp_sol_get_u(i, &sol_h, sol[i].u.data());
-      d_ocp_qp_sol_get_pi(i, &sol_h, sol[i + 1].pi.data());
-      d_ocp_qp_ipm_get_ric_P(&qp_h, &arg_h, &ws_h, i + 1, sol[i + 1].P.data());
-      d_ocp_qp_ipm_get_ric_p(&qp_h, &arg_h, &ws_h, i + 1, sol[i + 1].p.data());
-      d_ocp_qp_ipm_get_ric_K(&qp_h, &arg_h, &ws_h, i, sol[i].K.data());
-      d_ocp_qp_ipm_get_ric_k(&qp_h, &arg_h, &ws_h, i, sol[i].k.data());
+      d_ocp_qp_sol_get_x(i + 1, sol_p, sol[i + 1].x.data());
+      d_ocp_qp_sol_get_u(i, sol_p, sol[i].u.data());
+      d_ocp_qp_sol_get_pi(i, sol_p, sol[i + 1].pi.data());
+      d_ocp_qp_ipm_get_ric_P(qp_p, arg_p, ws_p, i + 1, sol[i + 1].P.data());
+      d_ocp_qp_ipm_get_ric_p(qp_p, arg_p, ws_p, i + 1, sol[i + 1].p.data());
+      d_ocp_qp_ipm_get_ric_K(qp_p, arg_p, ws_p, i, sol[i].K.data());
+      d_ocp_qp_ipm_get_ric_k(qp_p, arg_p, ws_p, i, sol[i].k.data());
     }
     // :346-373: stage 0 from Lr0 (Lr0^-1 by forward substitution, G0^-1 = Lr0^-T Lr0^-1)
     const int nu = dim.nu[0], nx = dim.nx[0];
     MatrixXd Lr0(nu, nu), Li(nu, nu);
-    d_ocp_qp_ipm_get_ric_Lr(&qp_h, &arg_h, &ws_h, 0, Lr0.data());
+    d_ocp_qp_ipm_get_ric_Lr(qp_p, arg_p, ws_p, 0, Lr0.data());
     for (int c = 0; c < nu; ++c)
       for (int i = c; i < nu; ++i) {
         double s = i == c ? 1.0 : 0.0;
@@ -191,18 +237,18 @@ struct ReplayedSolver {
     sol[0].pi = sol[0].p;
     for (int i = 0; i < nx; ++i) sol[0].pi(i) += Px(i);
     // :375-414
-    d_ocp_qp_ipm_get_iter(&ws_h, &stats.iter);
-    d_ocp_qp_ipm_get_max_res_stat(&ws_h, &stats.max_res_stat);
-    d_ocp_qp_ipm_get_max_res_eq(&ws_h, &stats.max_res_eq);
-    d_ocp_qp_ipm_get_max_res_ineq(&ws_h, &stats.max_res_ineq);
-    d_ocp_qp_ipm_get_max_res_comp(&ws_h, &stats.max_res_comp);
+    d_ocp_qp_ipm_get_iter(ws_p, &stats.iter);
+    d_ocp_qp_ipm_get_max_res_stat(ws_p, &stats.max_res_stat);
+    d_ocp_qp_ipm_get_max_res_eq(ws_p, &stats.max_res_eq);
+    d_ocp_qp_ipm_get_max_res_ineq(ws_p, &stats.max_res_ineq);
+    d_ocp_qp_ipm_get_max_res_comp(ws_p, &stats.max_res_comp);
     stats.clear();
     const int stat_m = 18;
     auto cols = stats.columns();
     for (int i = 0; i <= stats.iter + 1; ++i)
-      for (int c = 0; c < stat_m; ++c) cols[c]->push_back(ws_h.stat[stat_m * i + c]);
+      for (int c = 0; c < stat_m; ++c) cols[c]->push_back(ws_p->stat[stat_m * i + c]);
     int st;
-    d_ocp_qp_ipm_get_status(&ws_h, &st);
+    d_ocp_qp_ipm_get_status(ws_p, &st);
     return 0 <= st && st <= 3 ? static_cast<hpipm::HpipmStatus>(st) : hpipm::HpipmStatus::UnknownFailure;
   }
 };

@@ -443,6 +443,22 @@ def test_hpipm_c_symbols_in_the_reference_call_order(pkg):
     assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
 
 
+def test_reference_wrapper_objects_run_on_the_hpipm_symbols():
+    """oracle/_ref/test_hpipm_compat_refwrap (built by __graft_entry__.build() where the reference tree exists: oracle/Makefile
+    target `ref`): the same program as the previous test, compiled against the reference's VENDORED HPIPM headers, with the
+    five HPIPM objects owned by the reference's own hpipm::d_ocp_qp_*_wrapper classes -- their unmodified object code
+    (hpipm-cpp/src/detail/*.cpp) calling *_memsize / *_create of this library."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "test_hpipm_compat_refwrap")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref was not built (no reference tree at build time)")
+    r = subprocess.run([exe, os.path.join(root, "tests", "golden", "quadcopter_sol.txt")], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 def test_k3_variants_agree(pkg, monkeypatch):
     """The SRBD throughput variant of K3 (ipm_srbd.cuh, used for K2-assembled HARD_INEQ QPs) and the generic
     kernel (ipm_solve.cuh) run the same algorithm: same iteration counts, iterates within the parity tolerance."""
