@@ -535,6 +535,41 @@ def test_srbd_ragged_batches_and_tiny_horizons(pkg, orc, N, B):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("N,B,mode", [(2, 149, 1), (3, 151, 1), (50, 150, 1), (100, 148, 1), (20, 155, 0), (1, 149, 1)])
+def test_throughput_instantiation_edge_shapes(pkg, orc, N, B, mode):
+    """The edge shapes of the tests above again with MORE QPs than SMs, i.e. through the throughput instantiation of K3 (one
+    warp per QP, compact BAbt streaming with K1's dyn records for N >= 2, row masks from the assemble mode, lazy dense
+    records): the shortest horizons (N = 1 falls back to dense streaming, N = 2 has one interior stage), N = 50 / 100
+    (BASELINE configs 5 / 4), batches that are not a multiple of the six QPs of a CTA, and the reference's BARRIER_SOFT
+    assembly (every row masked: the single unconstrained Riccati pass, iter == 0).  Whole pipeline against the oracle's own
+    linearize / assemble / solve: equal iteration counts and statuses, primal iterates within 5e-9 (the bound of
+    test_srbd_ragged_batches_and_tiny_horizons; long horizons: tol_stat 1e-6 and 5e-8 like test_srbd_pipeline_other_horizons)."""
+    long_h = N > 20
+    settings = dict(SETTINGS, iter_max=50, tol_stat=1e-6) if long_h else SETTINGS
+    w = pkg.workload.srbd_batch(B, N=N, contact_mode="gait", start=4000 + 31 * B + N, spread=0.25 if long_h else 1.0)
+    with make_ctx(pkg, B, N, settings=settings) as ctx:
+        ctx.upload_traj(w["x"], w["u"], w["xref"], w["x0"], w["contact"])
+        ctx.sqp_iterate(mode)
+        sol = ctx.download_solution(want=("x", "u", "pi", "lam", "t"))
+        st = ctx.download_stats()
+        bs = ctx.batch_stats()
+    ref = orc.pipeline(orc.model_params(N), orc.ipm_args(**settings), N, mode, w["x"], w["u"], w["xref"], w["x0"],
+                       w["contact"])
+    assert (st["status"] == ref["status"]).all(), (st["status"], ref["status"])
+    if long_h:   # knife-edge QPs may differ by one iteration between two roundings of the QP data (DESIGN.md section 2)
+        assert (np.abs(st["iter"] - ref["iter"]) <= 1).all() and (st["iter"] == ref["iter"]).mean() >= 0.97
+    else:
+        assert (st["iter"] == ref["iter"]).all(), (st["iter"], ref["iter"])
+    if mode == 0:
+        assert (st["iter"] == 0).all() and (sol["lam"] == 0).all() and (sol["t"] == 0).all()
+    ok = st["status"] == 0
+    bound = 5e-8 if long_h else 5e-9
+    for k in ("x", "u") + (("t",) if mode == 1 else ()):
+        assert relerr(sol[k][ok], ref[k][ok]).max() <= bound, (k, relerr(sol[k][ok], ref[k][ok]).max())
+    assert bs["solves"] == B and bs["iter_sum"] == int(st["iter"].sum())
+
+
+@pytest.mark.gpu
 def test_dyn_records_and_compact_babt_streaming(pkg, monkeypatch):
     """K1's dyn records (include/srbd_b200.h SRBD_BUF_BABT_DYN; csrc/layout.cuh babt_dyn_off) are a bit-exact excerpt of the
     dense BAbt records -- every chunk at its offset for stages >= 1; at stage 0 the b row holds what the dense stage-0
@@ -976,7 +1011,7 @@ def test_low_latency_graph_path_config5(pkg, orc):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("N,B,mode,spread", [(20, 48, 0, 0.25), (100, 32, 1, 0.25)])
+@pytest.mark.parametrize("N,B,mode,spread", [(20, 48, 0, 0.25), (100, 32, 1, 0.25), (20, 152, 1, 0.25)])   # 152 > SMs: the throughput instantiation with frozen problems
 def test_device_side_sqp_loop(pkg, N, B, mode, spread):
     """srbd_sqp_solve: the outer SQP loop of NMPCSolver::controlLoop (NMPC_solver.cpp:367-375) on the device, without a host
     round trip per iteration.  Against the host-driven loop (srbd_sqp_iterate + convergence read-back) on the same problems:
