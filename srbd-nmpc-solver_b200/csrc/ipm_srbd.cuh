@@ -331,7 +331,7 @@ struct SrbdSolver {
     cred = cta + v2::kCtaShared;
     sG = sm; sF = sm + v2::wF0; sR = sm + v2::wR0;
     fr = lane >> 2; ft = lane & 3; fpi = (fr >> 1) + 4 * (fr & 1);
-    gdo = babt_dyn_off(lane);
+    gdo = tile_off(babt_dyn_off(lane));
 #if SRBD_K3_WBASE
     Wc = W + (lane < 24 ? lane : 0);
     Wf = W + ft;
@@ -454,7 +454,7 @@ struct SrbdSolver {
     if (kCG) {   // the stage-dependent chunks only (chunks 0..11 = the b row: np == 7)
       const double* dyn = gDynL(k);   // + 2 * lane = chunk `lane`
       if (np == 7 || lane >= 12) cp_async16(dst + gdo, dyn);
-      if (lane < 4) cp_async16(dst + (lane < 2 ? 210 : 244) + 4 * lane, dyn + 64);   // chunks 32..35
+      if (lane < 4) cp_async16(dst + tile_off((lane < 2 ? 210 : 244) + 4 * lane), dyn + 64);   // chunks 32..35
       return;
     }
     const double* src = gBAbtL(k);   // + 2 * lane
@@ -556,18 +556,27 @@ struct SrbdSolver {
   // (one whole contiguous record per tile, once per warp and kernel: the natural job for a TMA bulk copy -- one instruction
   // per tile from one lane, completion on the warp's mbarrier; the per-stage streams stay on per-lane cp.async, which
   // measured faster in every sweep, see SRBD_K3_TMA above)
+  // offset in the BAbt tile (panels of stride kGP) of offset o of the dense record (panels of 48)
+  static __device__ __forceinline__ int tile_off(int o) { return v2::kGP == 48 ? o : (o / 48) * v2::kGP + o % 48; }
   __device__ __forceinline__ void fill_G_constants(const double* dense_rec) {
     if (kTma) {
       if (lane == 0) {
         mbar_expect_tx(bar(0), 2 * 336 * 8);
-        bulk_g2s(sm + v2::wG0, dense_rec, 336 * 8, bar(0));
-        bulk_g2s(sm + v2::wG1, dense_rec, 336 * 8, bar(0));
+        if (v2::kGP == 48) {
+          bulk_g2s(sm + v2::wG0, dense_rec, 336 * 8, bar(0));
+          bulk_g2s(sm + v2::wG1, dense_rec, 336 * 8, bar(0));
+        } else {
+          for (int pnl = 0; pnl < 7; ++pnl) {
+            bulk_g2s(sm + v2::wG0 + pnl * v2::kGP, dense_rec + pnl * 48, 384, bar(0));
+            bulk_g2s(sm + v2::wG1 + pnl * v2::kGP, dense_rec + pnl * 48, 384, bar(0));
+          }
+        }
       }
       tiles_wait<true>(0);
     } else {
       for (int e = lane; e < 168; e += 32) {
-        cp_async16(sm + v2::wG0 + 2 * e, dense_rec + 2 * e);
-        cp_async16(sm + v2::wG1 + 2 * e, dense_rec + 2 * e);
+        cp_async16(sm + v2::wG0 + tile_off(2 * e), dense_rec + 2 * e);
+        cp_async16(sm + v2::wG1 + tile_off(2 * e), dense_rec + 2 * e);
       }
       cp_async_wait_all();
     }
@@ -2422,7 +2431,7 @@ constexpr int kTeamShared = 48;
 static_assert(6 * v2::kWarps + 4 <= kTeamShared, "team scratch");
 template <int kTma, int kPivot, int kTeam = 0, bool kExp = false, bool kCG = false>
 __global__ void SRBD_K3_BOUNDS ipm_srbd_kernel(const SrbdIpmParams p) {
-  static_assert(!kCG || (kTeam == 0 && !kExp && v2::kGP == 48), "compact BAbt streaming: throughput instantiations, unpadded tile");
+  static_assert(!kCG || (kTeam == 0 && !kExp && v2::kGP % 2 == 0), "compact BAbt streaming: throughput instantiations, 16-byte aligned panels");
   static_assert(kTeam == 0 || kTeam == v2::kWarps, "a team is the whole CTA");
   extern __shared__ __align__(128) double2 smem2[];  // no static shared memory: the tiles start on 128-byte lines
   if (p.gate && *p.gate != p.gate_value) return;
