@@ -454,7 +454,8 @@ struct SrbdSolver {
     if (kCG) {   // the stage-dependent chunks only (chunks 0..11 = the b row: np == 7)
       const double* dyn = gDynL(k);   // + 2 * lane = chunk `lane`
       if (np == 7 || lane >= 12) cp_async16(dst + gdo, dyn);
-      if (lane < 4) cp_async16(dst + tile_off((lane < 2 ? 210 : 244) + 4 * lane), dyn + 64);   // chunks 32..35
+      // chunks 32..35: record offsets 210, 214 (panel 4) and 252, 256 (panel 5)
+      if (lane < 4) cp_async16(dst + (lane < 2 ? 210 + 4 * (v2::kGP - 48) : 244 + 5 * (v2::kGP - 48)) + 4 * lane, dyn + 64);
       return;
     }
     const double* src = gBAbtL(k);   // + 2 * lane
