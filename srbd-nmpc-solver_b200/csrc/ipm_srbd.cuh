@@ -36,6 +36,11 @@
 // P / factor panels, the R block of RSQrq) stream into the other half of a shared-memory double buffer with
 // cp.async, and the next stage's per-row vectors are prefetched into registers (raw loads only: arithmetic on a
 // prefetched value would wait for it at the prefetch point), so HBM/L2 latency overlaps the FP64 work.
+// Second half of round 2: the residual sweep is fused backward into the factorization sweep (sweep_resfac: four sweeps per
+// iteration instead of five), and the throughput instantiation streams COMPACT BAbt records (kCG): the 288 model constants
+// of a record stay resident in the shared-memory tiles (filled once per warp by two TMA bulk copies), each stage copies the
+// 36 stage-dependent 16-byte chunks of K1's dyn record over them; the row masks follow from the assemble mode.  All of it
+// bit-identical to the dense path (SRBD_K3_CG=0); DRAM traffic per QP 8.6 -> 5.3 MB (DESIGN.md sections 3 and 5.0).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -140,6 +145,11 @@ namespace v2 {
 // single QP alone (BASELINE config 5) has nothing to overlap the longer latency with: 3.75 ms against 3.59 ms per N = 50
 // solve.  Hence two instantiations: SRBD_K3_TMA (default: S6) for batches that fill the machine, SRBD_K3_TMA_SMALL
 // (default: none) for batches of fewer QPs than SMs (capi.cu picks).
+// Since the residual sweep is fused into the factorization sweep (SRBD_K3_FUSE) the stand-alone S6 no longer runs in the
+// throughput instantiations, so with the default mask (8) their per-stage streams are all cp.async; re-measured after the
+// fusion: bit 1 (the R tile of the fused sweep as one bulk copy) 599.9 k against 608.9 k sustained
+// (profiles/r2c_k3_variants_ab.txt).  A non-zero mask still sets up the per-warp mbarriers, which the one-time constant
+// fill of the compact BAbt tiles uses (fill_G_constants: two whole-record bulk copies per warp and kernel).
 #ifndef SRBD_K3_TMA
 #define SRBD_K3_TMA 8
 #endif
