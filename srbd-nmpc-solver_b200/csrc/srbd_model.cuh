@@ -291,6 +291,10 @@ __global__ void __launch_bounds__(kLinThreads, SRBD_K1_MIN_CTAS) linearize_kerne
   __shared__ double sc[kLinThreads][kLinCompact + 1];
   __shared__ srbd_model_params sm;
   if (p.run_gate && *p.run_gate == 0) return;
+  // items are (QP, stage) pairs; with a work list the QP index is qlist[item / N] and the blocks beyond the list return at once
+  const long long total = (long long)(p.qlist ? *p.qcount : p.B) * p.N;
+  const long long item0 = (long long)blockIdx.x * kLinThreads;
+  if (item0 >= total) return;
   {
     const int nw = sizeof(srbd_model_params) / sizeof(double);
     const double* src = reinterpret_cast<const double*>(&md->m);
@@ -298,10 +302,6 @@ __global__ void __launch_bounds__(kLinThreads, SRBD_K1_MIN_CTAS) linearize_kerne
     for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
   }
   __syncthreads();
-  // items are (QP, stage) pairs; with a work list the QP index is qlist[item / N] and the blocks beyond the list return at once
-  const long long total = (long long)(p.qlist ? *p.qcount : p.B) * p.N;
-  const long long item0 = (long long)blockIdx.x * kLinThreads;
-  if (item0 >= total) return;
   const long long item = item0 + threadIdx.x;
   if (item < total) {
     const int qi = (int)(item / p.N), k = (int)(item % p.N);
