@@ -8,6 +8,10 @@
 // facade calls the C-ABI of include/srbd_b200.h, i.e. the CUDA path.  There is no CPU solve in here.
 // Additions (new, not in the reference): OcpQpIpmSolver::solveBatch for B independent QPs in one launch.
 #pragma once
+#include <atomic>
+#include <chrono>
+#include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <iomanip>
 #include <iostream>
@@ -17,6 +21,10 @@
 #include <string>
 #include <thread>
 #include <vector>
+
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include "../../../include/srbd_b200.h"
 #include "../eigen_shim.hpp"
@@ -231,6 +239,34 @@ class ContextPool {
   std::vector<PooledContext> free_;
   long created_ = 0;
 };
+// Host-side phase times of solve / solveBatch, accumulated when SRBD_FACADE_PROFILE=1 (ms; bench_facade prints them)
+struct FacadeProfile {
+  double validate = 0, flatten = 0, enqueue = 0, wait = 0, scatter = 0;
+  static FacadeProfile& get() { static FacadeProfile p; return p; }
+  static bool on() { static const bool v = [] { const char* e = std::getenv("SRBD_FACADE_PROFILE"); return e && std::atoi(e) != 0; }(); return v; }
+  static double now() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+};
+// Copy of one matrix block into the pinned staging arena.  The arena is written once and read by the DMA engine only:
+// blocks of whole cache lines go out with non-temporal stores (no read-for-ownership of the destination lines, a third
+// less memory traffic per copied byte); SRBD_FACADE_NT=0 falls back to memcpy.
+inline bool streamStores() {
+  static const bool on = [] { const char* e = std::getenv("SRBD_FACADE_NT"); return !e || std::atoi(e) != 0; }();
+  return on;
+}
+inline void copyOut(double* dst, const double* src, size_t n) {
+#if defined(__SSE2__)
+  if (n >= 64 && n % 8 == 0 && (reinterpret_cast<uintptr_t>(dst) & 63) == 0 && streamStores()) {
+    for (size_t e = 0; e < n; e += 2) _mm_stream_pd(dst + e, _mm_loadu_pd(src + e));
+    return;
+  }
+#endif
+  std::memcpy(dst, src, n * sizeof(double));
+}
+inline void storeFence() {
+#if defined(__SSE2__)
+  _mm_sfence();
+#endif
+}
 // Flattening B x (N+1) Eigen objects into the staging arena (and scattering the solutions back) is plain memory
 // traffic: 228 KB per N = 20 SRBD QP.  Large batches split it over a few host threads.
 template <class F>
@@ -270,6 +306,8 @@ class OcpQpIpmSolver {
       solver_settings_ = o.solver_settings_; solver_statistics_ = o.solver_statistics_; dim_ = o.dim_;
       pc_ = o.pc_; device_ = o.device_; want_ric_ = o.want_ric_; want_stat_ = o.want_stat_;
       o.pc_ = detail::PooledContext();
+      worker_[0] = std::move(o.worker_[0]); worker_[1] = std::move(o.worker_[1]);
+      batch_iter_ = std::move(o.batch_iter_); batch_res_ = std::move(o.batch_res_);
     }
     return *this;
   }
@@ -281,6 +319,9 @@ class OcpQpIpmSolver {
   // data, ocp_qp_ipm_solver.cpp:349-373) and lets QPs with the structure NMPCSolver::prepareQpStructures produces take the
   // tensor-core kernel (include/srbd_b200.h: srbd_qp_upload) -- what NMPCSolver::solveQpProblems needs (:322-329).
   void setOutputs(bool riccati, bool statistics) { want_ric_ = riccati; want_stat_ = statistics; }
+  // NEW.  solveBatch pipelines batches of at least two chunks (host flattening / H2D copy / kernels of neighbouring chunks
+  // overlap on two pooled contexts); chunk size in QPs, 0 = one launch for the whole batch.  Default 1024 (SRBD_FACADE_CHUNK).
+  static void setBatchChunk(size_t qps) { pipelineChunk() = qps; }
 
   // sizes the (grow-only, pooled) device workspace like the reference's wrappers do (detail/d_ocp_qp_ipm_ws_wrapper.cpp:141-155)
   void resize(const std::vector<OcpQp>& ocp_qp) {
@@ -358,6 +399,15 @@ class OcpQpIpmSolver {
   bool want_ric_ = true, want_stat_ = true;
   std::vector<int> batch_iter_;
   std::vector<double> batch_res_;
+  // solveBatch on large batches: two worker solvers (each with its own pooled context, stream and pinned arena) take
+  // chunks of the batch alternately, so that flattening / scattering on the host, the H2D copy and the kernels of
+  // neighbouring chunks overlap (solvePipelined)
+  std::unique_ptr<OcpQpIpmSolver> worker_[2];
+  struct Pending {   // what submit() leaves for collect()
+    std::vector<std::vector<OcpQpSolution>*> sols;
+    size_t in_total = 0;
+    bool ric = false, stat = false;
+  } pend_;
 
   void release() {
     detail::ContextPool::instance().release(pc_);
@@ -398,8 +448,79 @@ class OcpQpIpmSolver {
     return pc_.arena;
   }
 
+  // QPs per chunk of the pipelined solveBatch (SRBD_FACADE_CHUNK; 0 = never pipeline).  A chunk of 1024 N = 20 SRBD QPs is
+  // 235 MB of QP fields: a few ms each of host flattening, H2D copy and kernels.
+  static size_t& pipelineChunk() {
+    static size_t c = [] { const char* e = std::getenv("SRBD_FACADE_CHUNK"); return e ? static_cast<size_t>(std::atol(e)) : size_t(1024); }();
+    return c;
+  }
+  static bool anyNonZero(const double* v, size_t n) {
+    bool nz = false;
+    for (size_t e = 0; e < n; ++e) nz |= v[e] != 0.0;
+    return nz;
+  }
+
   void solveImpl(const std::vector<const Eigen::VectorXd*>& x0s, const std::vector<const std::vector<OcpQp>*>& qps,
                  const std::vector<std::vector<OcpQpSolution>*>& sols, std::vector<HpipmStatus>& status, ClosedLoop* loop) {
+    const size_t chunk = pipelineChunk();
+    if (!loop && chunk && qps.size() >= 2 * chunk) { solvePipelined(x0s, qps, sols, status, chunk); return; }
+    submit(x0s, qps, sols, loop);
+    collect(status, loop);
+  }
+
+  // Chunks of the batch go alternately to two worker solvers: while the host scatters chunk c - 2 and flattens chunk c,
+  // the H2D copy and the kernels of chunk c - 1 run on the other worker's stream.  Same results as one big launch (QPs
+  // are independent; every chunk is validated, uploaded and solved exactly like a batch of its own).
+  void solvePipelined(const std::vector<const Eigen::VectorXd*>& x0s, const std::vector<const std::vector<OcpQp>*>& qps,
+                      const std::vector<std::vector<OcpQpSolution>*>& sols, std::vector<HpipmStatus>& status, size_t chunk) {
+    const size_t B = qps.size(), nchunks = (B + chunk - 1) / chunk;
+    for (auto& w : worker_) {
+      if (!w) w.reset(new OcpQpIpmSolver(solver_settings_));
+      w->setSolverSettings(solver_settings_);
+      w->setDevice(device_);
+      w->setOutputs(want_ric_, want_stat_);
+    }
+    status.assign(B, HpipmStatus::UnknownFailure);
+    batch_iter_.assign(B, 0);
+    batch_res_.assign(4 * B, 0.0);
+    std::vector<HpipmStatus> st;
+    auto finish = [&](size_t c) {
+      OcpQpIpmSolver& w = *worker_[c & 1];
+      const size_t lo = c * chunk;
+      w.collect(st, nullptr);
+      std::copy(st.begin(), st.end(), status.begin() + static_cast<long>(lo));
+      std::copy(w.batch_iter_.begin(), w.batch_iter_.end(), batch_iter_.begin() + static_cast<long>(lo));
+      std::copy(w.batch_res_.begin(), w.batch_res_.end(), batch_res_.begin() + static_cast<long>(4 * lo));
+    };
+    try {
+      for (size_t c = 0; c < nchunks; ++c) {
+        if (c >= 2) finish(c - 2);
+        const size_t lo = c * chunk, hi = lo + chunk < B ? lo + chunk : B;
+        const std::vector<const Eigen::VectorXd*> cx(x0s.begin() + static_cast<long>(lo), x0s.begin() + static_cast<long>(hi));
+        const std::vector<const std::vector<OcpQp>*> cq(qps.begin() + static_cast<long>(lo), qps.begin() + static_cast<long>(hi));
+        const std::vector<std::vector<OcpQpSolution>*> cs(sols.begin() + static_cast<long>(lo), sols.begin() + static_cast<long>(hi));
+        worker_[c & 1]->submit(cx, cq, cs, nullptr);
+      }
+      for (size_t c = nchunks >= 2 ? nchunks - 2 : 0; c < nchunks; ++c) finish(c);
+    } catch (...) {   // leave no work in flight on a context that goes back to the pool
+      for (auto& w : worker_) if (w && w->pc_.ctx) srbd_ctx_sync(w->pc_.ctx);
+      throw;
+    }
+    const OcpQpIpmSolver& last = *worker_[(nchunks - 1) & 1];
+    dim_ = last.dim_;
+    solver_statistics_ = last.solver_statistics_;
+  }
+
+  void submit(const std::vector<const Eigen::VectorXd*>& x0s, const std::vector<const std::vector<OcpQp>*>& qps,
+              const std::vector<std::vector<OcpQpSolution>*>& sols, ClosedLoop* loop) {
+    const bool prof = detail::FacadeProfile::on();
+    double t_ = prof ? detail::FacadeProfile::now() : 0.0;
+    auto lap = [&](double detail::FacadeProfile::*m) {
+      if (!prof) return;
+      const double t1 = detail::FacadeProfile::now();
+      detail::FacadeProfile::get().*m += t1 - t_;
+      t_ = t1;
+    };
     solver_settings_.checkSettings();
     const int B = static_cast<int>(qps.size());
     dim_.resize(*qps[0]);  // resize(ocp_qp) on every call like the reference (ocp_qp_ipm_solver.cpp:185)
@@ -433,6 +554,7 @@ class OcpQpIpmSolver {
           throw std::runtime_error("ocp_qp[" + std::to_string(i) + "].idxbu differs between stages / batch entries: the "
                                    "B200 path needs one idxbu for stages 0..N-1");
       }
+    lap(&detail::FacadeProfile::validate);
     // ---- staging arena: every QP field batch-contiguous and column-major (srbd_qp_host), one after the other, then the
     // outputs in the device's own layout: ONE H2D copy up, ONE D2H copy down -------------------------------------------
     size_t out_off[8], out_total = 0;
@@ -444,16 +566,19 @@ class OcpQpIpmSolver {
                                  Bz * N * ng * nx, Bz * N * ng * nu, Bz * N * ng, Bz * N * ng, Bz * N * ng, Bz * N * ng,
                                  Bz * ngN * nx, Bz * ngN, Bz * ngN, Bz * ngN, Bz * ngN, Bz * nx,
                                  warm ? Bz * (N + 1) * nx : 0, warm ? Bz * N * nu : 0};
-    size_t in_off[31];
-    in_off[0] = 0;
-    for (int i = 0; i < 30; ++i) in_off[i + 1] = in_off[i] + in_sizes[i];
-    const size_t in_total = in_off[30];
-    double* ar = arena(in_total + out_total);
-    double* out = ar + in_total;
     enum { fA, fB, fb, fQ, fS, fR, fq, fr, flbx, fubx, flbxm, fubxm, flbu, fubu, flbum, fubum, fC, fD, flg, fug, flgm, fugm,
            fCN, flgN, fugN, flgNm, fugNm, fx0, fxin, fuin };
+    // S and C lie at the END of the input area: when every S_k and C_k of the batch is zero (what
+    // NMPCSolver::prepareQpStructures hands over, NMPC_solver.cpp:277-314) they are passed as "absent" and the single
+    // H2D copy of srbd_qp_upload (the span of the fields that are present) ends before them: 30 % fewer bytes over PCIe
+    const int order[30] = {fA, fB, fb, fQ, fR, fq, fr, flbx, fubx, flbxm, fubxm, flbu, fubu, flbum, fubum, fD, flg, fug, flgm, fugm,
+                           fCN, flgN, fugN, flgNm, fugNm, fx0, fxin, fuin, fS, fC};
+    size_t in_off[30], in_total = 0;
+    for (int i = 0; i < 30; ++i) { in_off[order[i]] = in_total; in_total += in_sizes[order[i]]; }
+    double* ar = arena(in_total + out_total);
+    std::atomic<int> nz_S{0}, nz_C{0};
     auto put = [&](int f, size_t b, size_t stages, size_t i, size_t per, const double* src) {
-      if (per) std::memcpy(ar + in_off[f] + (b * stages + i) * per, src, per * sizeof(double));
+      if (per) detail::copyOut(ar + in_off[f] + (b * stages + i) * per, src, per);
     };
     auto fill = [&](int f, size_t b, size_t stages, size_t i, size_t per, double v) {
       double* dst = ar + in_off[f] + (b * stages + i) * per;
@@ -481,11 +606,14 @@ class OcpQpIpmSolver {
         }
         if (i == N) break;
         put(fA, b, N, i, nx * nx, s.A.data()); put(fB, b, N, i, nx * nu, s.B.data()); put(fb, b, N, i, nx, s.b.data());
-        put(fS, b, N, i, nu * nx, s.S.data()); put(fR, b, N, i, nu * nu, s.R.data()); put(fr, b, N, i, nu, s.r.data());
+        put(fR, b, N, i, nu * nu, s.R.data()); put(fr, b, N, i, nu, s.r.data());
+        // S and C are only LOOKED at here; they are copied by a second pass below if any of them is non-zero
+        if (!nz_S.load(std::memory_order_relaxed) && anyNonZero(s.S.data(), nu * nx)) nz_S.store(1, std::memory_order_relaxed);
         put(flbu, b, N, i, nbu, s.lbu.data()); put(fubu, b, N, i, nbu, s.ubu.data());
         mask(flbum, b, N, i, nbu, s.lbu_mask); mask(fubum, b, N, i, nbu, s.ubu_mask);
         if (ng) {
-          if (s.C.size()) put(fC, b, N, i, ng * nx, s.C.data()); else fill(fC, b, N, i, ng * nx, 0.0);
+          // (C_0 is dropped by the x0 embedding, nx[0] := 0, so it does not count)
+          if (i >= 1 && s.C.size() && !nz_C.load(std::memory_order_relaxed) && anyNonZero(s.C.data(), ng * nx)) nz_C.store(1, std::memory_order_relaxed);
           put(fD, b, N, i, ng * nu, s.D.data());
           put(flg, b, N, i, ng, s.lg.data()); put(fug, b, N, i, ng, s.ug.data());
           mask(flgm, b, N, i, ng, s.lg_mask); mask(fugm, b, N, i, ng, s.ug_mask);
@@ -503,16 +631,28 @@ class OcpQpIpmSolver {
           if (i < N) put(fuin, b, N, i, nu, (*sols[b])[i].u.data());
         }
     }
+    detail::storeFence();
     });
+    if (nz_S.load() || nz_C.load())
+      detail::parallelFor(Bz, 64, [&](size_t b_lo, size_t b_hi) {
+        for (size_t b = b_lo; b < b_hi; ++b)
+          for (size_t i = 0; i < N; ++i) {
+            const OcpQp& s = (*qps[b])[i];
+            if (nz_S.load()) put(fS, b, N, i, nu * nx, s.S.data());
+            if (nz_C.load() && ng) { if (s.C.size()) put(fC, b, N, i, ng * nx, s.C.data()); else fill(fC, b, N, i, ng * nx, 0.0); }
+          }
+        detail::storeFence();
+      });
     auto at = [&](int f) -> const double* { return in_sizes[f] ? ar + in_off[f] : nullptr; };
     srbd_qp_host h{};
-    h.A = at(fA); h.Bm = at(fB); h.b = at(fb); h.Q = at(fQ); h.S = at(fS); h.R = at(fR); h.q = at(fq); h.r = at(fr);
+    h.A = at(fA); h.Bm = at(fB); h.b = at(fb); h.Q = at(fQ); h.S = nz_S.load() ? at(fS) : nullptr; h.R = at(fR); h.q = at(fq); h.r = at(fr);
     h.idxbx = nbx ? (*qps[0])[N].idxbx.data() : nullptr; h.lbx = at(flbx); h.ubx = at(fubx); h.lbx_mask = at(flbxm); h.ubx_mask = at(fubxm);
     h.idxbu = nbu ? (*qps[0])[0].idxbu.data() : nullptr; h.lbu = at(flbu); h.ubu = at(fubu); h.lbu_mask = at(flbum); h.ubu_mask = at(fubum);
-    h.C = at(fC); h.D = at(fD); h.lg = at(flg); h.ug = at(fug); h.lg_mask = at(flgm); h.ug_mask = at(fugm);
+    h.C = nz_C.load() ? at(fC) : nullptr; h.D = at(fD); h.lg = at(flg); h.ug = at(fug); h.lg_mask = at(flgm); h.ug_mask = at(fugm);
     h.CN = at(fCN); h.lgN = at(flgN); h.ugN = at(fugN); h.lgN_mask = at(flgNm); h.ugN_mask = at(fugNm);
     h.x0 = at(fx0);
     if (warm) { h.x_init = at(fxin); h.u_init = at(fuin); }
+    lap(&detail::FacadeProfile::flatten);
 
     srbd_ipm_args a;
     srbd_ipm_args_default(&a);
@@ -551,9 +691,31 @@ class OcpQpIpmSolver {
           o.iter[t][b] = it[t * Bz + b];
         }
     } else {
-      check(srbd_qp_solve(ctx), "srbd_qp_solve");
+      check(srbd_qp_solve(ctx), "srbd_qp_solve");   // (enqueued on the context's stream: collect() waits for it)
     }
+    lap(&detail::FacadeProfile::enqueue);
+    pend_.sols = sols;
+    pend_.in_total = in_total;
+    pend_.ric = ric;
+    pend_.stat = stat;
+  }
+
+  // second half of a solve: the outputs of the submitted batch come down in one D2H copy and are scattered into qp_sol
+  void collect(std::vector<HpipmStatus>& status, ClosedLoop* loop) {
+    (void)loop;
+    srbd_ctx* ctx = pc_.ctx;
+    const srbd_qp_dims d = pc_.dims;
+    const std::vector<std::vector<OcpQpSolution>*>& sols = pend_.sols;
+    const int B = static_cast<int>(sols.size());
+    const size_t N = d.N, nx = d.nx, nu = d.nu, Bz = static_cast<size_t>(B);
+    const bool ric = pend_.ric, stat = pend_.stat;
+    size_t out_off[8], out_total = 0;
+    check(srbd_out_layout(ctx, out_off, &out_total), "srbd_out_layout");
+    double* out = pc_.arena + pend_.in_total;
+    const bool prof = detail::FacadeProfile::on();
+    const double t0_ = prof ? detail::FacadeProfile::now() : 0.0;
     check(srbd_download_packed(ctx, out, 0), "srbd_download_packed");
+    const double t1_ = prof ? detail::FacadeProfile::now() : 0.0;
     const double *x = out + out_off[0], *u = out + out_off[1], *pi = out + out_off[2], *rm = out + out_off[3];
     const int* it = reinterpret_cast<const int*>(out + out_off[4]);
     const int* st = reinterpret_cast<const int*>(out + out_off[5]);
@@ -581,6 +743,7 @@ class OcpQpIpmSolver {
         s[i].x.resize(nx); s[i].pi.resize(nx);
         std::memcpy(s[i].x.data(), x + (b * (N + 1) + i) * nx, nx * sizeof(double));
         std::memcpy(s[i].pi.data(), pi + (b * (N + 1) + i) * nx, nx * sizeof(double));
+        if (i == 0 && !ric) s[0].pi.setZero();   // pi[0] exists only together with the Riccati outputs (srbd_b200.h): not stale data
         if (ric) {
           s[i].P.resize(nx, nx); s[i].p.resize(nx);
           std::memcpy(s[i].P.data(), P.data() + (b * (N + 1) + i) * nx * nx, nx * nx * sizeof(double));
@@ -599,6 +762,10 @@ class OcpQpIpmSolver {
       status[b] = (st[b] >= 0 && st[b] <= 3) ? static_cast<HpipmStatus>(st[b]) : HpipmStatus::UnknownFailure;
     }
     });
+    if (prof) {
+      detail::FacadeProfile::get().wait += t1_ - t0_;
+      detail::FacadeProfile::get().scatter += detail::FacadeProfile::now() - t1_;
+    }
     // statistics of the (last) QP: iter, 4 max residuals, rows 0..iter+1 of the 18-column table (:376-403)
     const size_t bl = Bz - 1;
     solver_statistics_.iter = it[bl];

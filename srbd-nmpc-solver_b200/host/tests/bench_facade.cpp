@@ -78,7 +78,13 @@ int main(int argc, char** argv) {
       if (!full && rep == reps) { for (int v : solver.getBatchIterations()) it_sum += v; for (auto v : st) conv += v == hpipm::HpipmStatus::Success; }
     }
   }
-  const double bytes_up = (double)B * (N * (5 * 144 + 36 + 2 * 288 + 4 * 24) + 144 + 12 + 12) * 8, bytes_down = (double)B * ((N + 1) * 24 + N * 12) * 8;
+  if (hpipm::detail::FacadeProfile::on()) {
+    const auto& pf = hpipm::detail::FacadeProfile::get();
+    std::fprintf(stderr, "facade host phases over all %d calls (ms): validate %.1f flatten %.1f enqueue %.1f wait %.1f scatter %.1f\n",
+                 2 * (reps + 1), pf.validate, pf.flatten, pf.enqueue, pf.wait, pf.scatter);
+  }
+  // S and C of these QPs are all zero: the facade does not send them (hpipm-cpp.hpp, submit)
+  const double bytes_up = (double)B * (N * (4 * 144 + 36 + 288 + 4 * 24) + 144 + 12 + 12) * 8, bytes_down = (double)B * ((N + 1) * 24 + N * 12) * 8;
   std::printf("{\"qps\": %d, \"horizon\": %d, \"ms_per_batch\": %.3f, \"value\": %.1f, \"unit\": \"solves/s\", "
               "\"ms_per_batch_reference_outputs\": %.3f, \"value_reference_outputs\": %.1f, \"converged\": %d, \"iter_mean\": %.3f, "
               "\"h2d_bytes\": %.0f, \"d2h_bytes\": %.0f, "

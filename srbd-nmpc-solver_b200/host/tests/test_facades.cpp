@@ -339,6 +339,119 @@ static void test_srbd_structured_qp_fast_path() {
   std::printf("SRBD-structured QP through the facade: done (%d iterations on both kernels)\n", b.getSolverStatistics().iter);
 }
 
+// NEW: solveBatch splits large batches into chunks that two pooled contexts take alternately (flatten / H2D / kernels of
+// neighbouring chunks overlap).  Same results bit for bit as one launch: generic QPs (boxes, general rows, S != 0), chunks
+// of 3 + 3 + 3 + 2, with and without the optional outputs; SRBD-structured QPs (S = 0, C = 0: the two fields do not travel)
+// with one QP whose S is non-zero in the LAST chunk only (that chunk uploads S and takes the generic kernel).
+static void test_pipelined_batch() {
+  const int nx = 5, nu = 3, ng = 2, N = 8, B = 11;
+  auto absv = [](VectorXd v, double s, double off) { for (int i = 0; i < v.size(); ++i) v(i) = s * (off + std::fabs(v(i))); return v; };
+  std::vector<std::vector<hpipm::OcpQp>> qps;
+  std::vector<VectorXd> x0;
+  for (int b = 0; b < B; ++b) {
+    auto qp = randomQp(nx, nu, N, 0.4, true);
+    for (int i = 0; i < N; ++i) {
+      qp[i].idxbu = {0, 2};
+      qp[i].lbu = absv(RndV(2), -1.0, 0.5); qp[i].ubu = absv(RndV(2), 1.0, 0.5);
+      qp[i].C = Rnd(ng, nx); qp[i].D = Rnd(ng, nu);
+      qp[i].lg = absv(RndV(ng), -10.0, 0.5); qp[i].ug = absv(RndV(ng), 10.0, 0.5);
+    }
+    qps.push_back(qp);
+    x0.push_back(RndV(nx));
+  }
+  hpipm::OcpQpIpmSolverSettings s;
+  s.ric_alg = 0; s.iter_max = 40; s.tol_stat = 1e-6;
+  auto same = [&](const std::vector<std::vector<hpipm::OcpQpSolution>>& a, const std::vector<std::vector<hpipm::OcpQpSolution>>& c) {
+    bool ok = a.size() == c.size();
+    for (size_t b = 0; ok && b < a.size(); ++b)
+      for (size_t i = 0; i < a[b].size(); ++i) {
+        const auto &p = a[b][i], &q = c[b][i];
+        ok = ok && p.x.size() == q.x.size() && p.u.size() == q.u.size() && p.pi.size() == q.pi.size() && p.P.size() == q.P.size() && p.K.size() == q.K.size();
+        if (!ok) break;
+        ok = ok && std::memcmp(p.x.data(), q.x.data(), p.x.size() * 8) == 0 && std::memcmp(p.pi.data(), q.pi.data(), p.pi.size() * 8) == 0;
+        if (p.u.size()) ok = ok && std::memcmp(p.u.data(), q.u.data(), p.u.size() * 8) == 0;
+        if (p.P.size()) ok = ok && std::memcmp(p.P.data(), q.P.data(), p.P.size() * 8) == 0;
+        if (p.K.size()) ok = ok && std::memcmp(p.K.data(), q.K.data(), p.K.size() * 8) == 0;
+      }
+    return ok;
+  };
+  for (int outputs = 0; outputs < 2; ++outputs) {
+    std::vector<std::vector<hpipm::OcpQpSolution>> one, piped;
+    hpipm::OcpQpIpmSolver a(s), b(s);
+    a.setOutputs(outputs != 0, outputs != 0); b.setOutputs(outputs != 0, outputs != 0);
+    hpipm::OcpQpIpmSolver::setBatchChunk(0);
+    const auto st1 = a.solveBatch(x0, qps, one);
+    hpipm::OcpQpIpmSolver::setBatchChunk(3);
+    const auto st2 = b.solveBatch(x0, qps, piped);
+    const auto st3 = b.solveBatch(x0, qps, piped);   // again: the workers' contexts are reused
+    CHECK(st1 == st2 && st1 == st3 && (int)st1.size() == B);
+    for (auto v : st1) CHECK(v == hpipm::HpipmStatus::Success);
+    CHECK(same(one, piped));
+    CHECK(a.getBatchIterations() == b.getBatchIterations() && a.getBatchMaxResiduals() == b.getBatchMaxResiduals());
+    CHECK(a.getSolverStatistics().iter == b.getSolverStatistics().iter && a.getSolverStatistics().mu == b.getSolverStatistics().mu);
+  }
+  // ---- SRBD-structured QPs -------------------------------------------------------------------------------------------
+  {
+    const int Ns = 20, n = 12, g = 24, Bs = 7;
+    MatrixXd D(g, n);
+    for (int leg = 0; leg < 2; ++leg) {
+      const int r0 = 12 * leg, c0 = 6 * leg;
+      D(r0 + 0, c0 + 0) = -1; D(r0 + 0, c0 + 2) = 0.5; D(r0 + 1, c0 + 1) = -1; D(r0 + 1, c0 + 2) = 0.5;
+      D(r0 + 2, c0 + 0) = 1; D(r0 + 2, c0 + 2) = 0.5; D(r0 + 3, c0 + 1) = 1; D(r0 + 3, c0 + 2) = 0.5;
+      D(r0 + 4, c0 + 2) = -1; D(r0 + 5, c0 + 2) = 1;
+      for (int k = 6; k < 12; ++k) { D(r0 + k, c0 + 2) = 0.05; D(r0 + k, c0 + 3 + (k % 3)) = (k % 2) ? 1.0 : -1.0; }
+    }
+    std::vector<std::vector<hpipm::OcpQp>> sq(Bs, std::vector<hpipm::OcpQp>(Ns + 1));
+    std::vector<VectorXd> sx0;
+    for (int b = 0; b < Bs; ++b) {
+      auto& qp = sq[b];
+      for (int i = 0; i <= Ns; ++i) {
+        qp[i].Q = MatrixXd(n, n); for (int k = 0; k < n; ++k) qp[i].Q(k, k) = i < Ns ? (k == 11 ? 10.0 : 0.0) : 20.0 * (1 + k);
+        qp[i].q = RndV(n);
+        if (i == Ns) break;
+        qp[i].A = MatrixXd::Identity(n, n); for (int k = 0; k < 6; ++k) qp[i].A(k, 6 + k) = 0.015;
+        qp[i].B = Rnd(n, n); for (int e = 0; e < n * n; ++e) qp[i].B.data()[e] *= 0.02;
+        qp[i].b = RndV(n); for (int k = 0; k < n; ++k) qp[i].b(k) *= 0.01;
+        qp[i].R = MatrixXd(n, n); for (int k = 0; k < n; ++k) qp[i].R(k, k) = 1e-2;
+        qp[i].S = MatrixXd(n, n); qp[i].r = RndV(n);
+        qp[i].C = MatrixXd(g, n); qp[i].D = D;
+        qp[i].lg = VectorXd(g); for (int k = 0; k < g; ++k) qp[i].lg(k) = -1.0 - 0.1 * k;
+        qp[i].ug = VectorXd(g); qp[i].ug_mask = VectorXd(g);
+        qp[i].lg_mask = VectorXd(g); qp[i].lg_mask.fill(1.0); qp[i].lg_mask(10) = 0.0;
+      }
+      sx0.push_back(RndV(n));
+    }
+    hpipm::OcpQpIpmSolverSettings ss;
+    ss.ric_alg = 0; ss.iter_max = 40; ss.split_step = 1;
+    for (int variant = 0; variant < 2; ++variant) {
+      if (variant == 1) sq[Bs - 1][3].S(2, 5) = 1e-3;   // last chunk only: S travels for that chunk, generic kernel there
+      std::vector<std::vector<hpipm::OcpQpSolution>> one, piped;
+      hpipm::OcpQpIpmSolver a(ss), b(ss);
+      a.setOutputs(false, false); b.setOutputs(false, false);
+      hpipm::OcpQpIpmSolver::setBatchChunk(0);
+      const auto st1 = a.solveBatch(sx0, sq, one);
+      hpipm::OcpQpIpmSolver::setBatchChunk(2);
+      const auto st2 = b.solveBatch(sx0, sq, piped);
+      CHECK(st1 == st2);
+      for (auto v : st1) CHECK(v == hpipm::HpipmStatus::Success);
+      if (variant == 0) CHECK(same(one, piped));
+      else {   // the one-launch batch takes the generic kernel as a whole, the pipelined one only in its last chunk
+        CHECK(a.getBatchIterations() == b.getBatchIterations());
+        for (int b2 = 0; b2 < Bs; ++b2) for (int i = 0; i <= Ns; ++i) CHECK(approxV(one[b2][i].x, piped[b2][i].x, 1e-9));
+        std::vector<std::vector<hpipm::OcpQpSolution>> lone(1);
+        std::vector<std::vector<hpipm::OcpQp>> lq{sq[Bs - 1]};
+        std::vector<VectorXd> lx{sx0[Bs - 1]};
+        hpipm::OcpQpIpmSolver c(ss);
+        c.setOutputs(false, false);
+        c.solveBatch(lx, lq, lone);
+        for (int i = 0; i <= Ns; ++i) CHECK(std::memcmp(lone[0][i].x.data(), piped[Bs - 1][i].x.data(), n * 8) == 0);
+      }
+    }
+  }
+  hpipm::OcpQpIpmSolver::setBatchChunk(1024);
+  std::printf("pipelined solveBatch: done (bit-identical to one launch)\n");
+}
+
 static void test_errors() {
   auto qp = randomQp(5, 3, 4, 1.0, true);
   bool thrown = false;
@@ -401,6 +514,7 @@ int main(int argc, char** argv) {
     test_compare_results(golden);
     test_closed_loop_and_pool(golden);
     test_srbd_structured_qp_fast_path();
+    test_pipelined_batch();
     test_srbd_model();
     test_nmpc_solver();
   } catch (const std::exception& e) {
