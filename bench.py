@@ -243,15 +243,16 @@ def latency_leg(pkg, reps=300):
 def facade_leg(batch, device):
     """The reference's OWN boundary as the measured path: hpipm::OcpQpIpmSolver::solveBatch on host std::vector<OcpQp>
     (srbd-nmpc-solver_b200/host/tests/bench_facade.cpp, built by __graft_entry__.build()).  The QP-level interface moves
-    228 KB per N=20 QP (every A, B, Q, S, R, C, D) against 6 KB for the NMPC-level calls, so a 65536-QP batch would be
-    15 GB of host data: measured at `batch` QPs and reported per second."""
+    228 KB per N=20 QP (every A, B, Q, S, R, C, D; the all-zero S and C stay on the host: 161 KB) against 6 KB for the
+    NMPC-level calls, so a 65536-QP batch would be 15 GB of host data: measured at `batch` QPs and reported per second.
+    solveBatch pipelines the batch in chunks of 1024 QPs over two pooled contexts (hpipm-cpp.hpp: solvePipelined)."""
     exe = os.path.join(ROOT, "srbd-nmpc-solver_b200", "host", "tests", "bench_facade")
     if not os.path.exists(exe):
         return {"unavailable": "bench_facade not built (python -c 'import __graft_entry__ as g; g.build()')"}
     env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[device]
                if os.environ.get("CUDA_VISIBLE_DEVICES") else str(device))
     try:
-        r = subprocess.run([exe, str(batch), "3"], capture_output=True, text=True, timeout=600, env=env)
+        r = subprocess.run([exe, str(batch), "2"], capture_output=True, text=True, timeout=600, env=env)
         return json.loads(r.stdout.strip().splitlines()[-1])
     except Exception as e:  # the headline line must not depend on this leg
         return {"unavailable": repr(e)[:200]}
@@ -270,7 +271,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true", help="skip the single-instance latency leg (BASELINE config 5)")
     ap.add_argument("--no-facade", action="store_true", help="skip the hpipm-cpp facade leg (host/tests/bench_facade)")
-    ap.add_argument("--facade-batch", type=int, default=4096)
+    ap.add_argument("--facade-batch", type=int, default=16384)
     ap.add_argument("--e2e-steps", type=int, default=3)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -13,6 +13,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <iomanip>
 #include <iostream>
 #include <memory>
@@ -139,6 +140,19 @@ struct OcpQpDim {
       nbu[i] = i < N ? static_cast<int>(ocp_qp[i].idxbu.size()) : 0;
       ng[i] = static_cast<int>(ocp_qp[i].lg.size());
       nsbx[i] = static_cast<int>(ocp_qp[i].idxs.size());
+    }
+    checkSize(ocp_qp);
+  }
+  // NEW (solveBatch): another QP of the batch must have exactly these dimensions (the flattened batch is uniform);
+  // same messages as checkSize, no allocation
+  void checkBatchEntry(const std::vector<OcpQp>& ocp_qp) const {
+    if (ocp_qp.size() != N + 1) throw std::runtime_error("ocp_qp.size() must be " + std::to_string(N + 1));
+    for (unsigned int i = 0; i <= N; ++i) {
+      const OcpQp& s = ocp_qp[i];
+      const bool ok = static_cast<int>(s.q.size()) == nx[i] && (i == N || static_cast<int>(s.r.size()) == nu[i]) &&
+                      static_cast<int>(s.idxbx.size()) == nbx[i] && (i == N || static_cast<int>(s.idxbu.size()) == nbu[i]) &&
+                      static_cast<int>(s.lg.size()) == ng[i];
+      if (!ok) throw std::runtime_error("ocp_qp[" + std::to_string(i) + "]: every QP of a batch must have the dimensions of the first");
     }
     checkSize(ocp_qp);
   }
@@ -276,12 +290,17 @@ inline void parallelFor(size_t n, size_t grain, F&& fn) {
   if (nt * grain > n) nt = n / grain;
   if (nt < 2) { fn(size_t(0), n); return; }
   std::vector<std::thread> th;
+  std::exception_ptr err;   // the first exception of a worker is rethrown on the calling thread
+  std::mutex err_m;
   const size_t chunk = (n + nt - 1) / nt;
   for (size_t t = 0; t < nt; ++t) {
     const size_t lo = t * chunk, hi = lo + chunk < n ? lo + chunk : n;
-    if (lo < hi) th.emplace_back([&fn, lo, hi] { fn(lo, hi); });
+    if (lo < hi) th.emplace_back([&fn, &err, &err_m, lo, hi] {
+      try { fn(lo, hi); } catch (...) { std::lock_guard<std::mutex> lock(err_m); if (!err) err = std::current_exception(); }
+    });
   }
   for (auto& t : th) t.join();
+  if (err) std::rethrow_exception(err);
 }
 }  // namespace detail
 
@@ -524,7 +543,10 @@ class OcpQpIpmSolver {
     solver_settings_.checkSettings();
     const int B = static_cast<int>(qps.size());
     dim_.resize(*qps[0]);  // resize(ocp_qp) on every call like the reference (ocp_qp_ipm_solver.cpp:185)
-    for (int b = 1; b < B; ++b) { OcpQpDim chk(*qps[b]); (void)chk; }
+    if (B > 1)
+      detail::parallelFor(static_cast<size_t>(B), 256, [&](size_t lo, size_t hi) {
+        for (size_t b = lo > 0 ? lo : 1; b < hi; ++b) dim_.checkBatchEntry(*qps[b]);
+      });
     ensureContext(B);
     srbd_ctx* ctx = pc_.ctx;
     const srbd_qp_dims d = pc_.dims;
@@ -575,7 +597,20 @@ class OcpQpIpmSolver {
                            fCN, flgN, fugN, flgNm, fugNm, fx0, fxin, fuin, fS, fC};
     size_t in_off[30], in_total = 0;
     for (int i = 0; i < 30; ++i) { in_off[order[i]] = in_total; in_total += in_sizes[order[i]]; }
-    double* ar = arena(in_total + out_total);
+    srbd_ipm_args a;
+    srbd_ipm_args_default(&a);
+    srbd_ipm_args_set_mode(&a, static_cast<int>(solver_settings_.mode));  // d_ocp_qp_ipm_arg_set_default(mode), :103
+    a.iter_max = solver_settings_.iter_max; a.alpha_min = solver_settings_.alpha_min; a.mu0 = solver_settings_.mu0;
+    a.tol_stat = solver_settings_.tol_stat; a.tol_eq = solver_settings_.tol_eq; a.tol_ineq = solver_settings_.tol_ineq;
+    a.tol_comp = solver_settings_.tol_comp; a.reg_prim = solver_settings_.reg_prim; a.warm_start = solver_settings_.warm_start;
+    a.pred_corr = solver_settings_.pred_corr; a.ric_alg = solver_settings_.ric_alg; a.split_step = solver_settings_.split_step;
+    check(srbd_set_ipm_args(ctx, &a), "srbd_set_ipm_args");
+    const bool ric = want_ric_, stat = want_stat_ && !loop;
+    check(srbd_set_outputs(ctx, ric ? 1 : 0, stat ? 1 : 0), "srbd_set_outputs");
+    // the optional outputs come down into the pinned arena as well (behind the packed outputs): no pageable staging
+    const size_t ric_total = ric ? Bz * ((N + 1) * (nx * nx + nx) + N * (nu * nx + nu)) : 0;
+    const size_t tab_total = stat ? Bz * static_cast<size_t>(srbd_ctx_stat_rows(ctx)) * SRBD_STAT_M : 0;
+    double* ar = arena(in_total + out_total + ric_total + tab_total);
     std::atomic<int> nz_S{0}, nz_C{0};
     auto put = [&](int f, size_t b, size_t stages, size_t i, size_t per, const double* src) {
       if (per) detail::copyOut(ar + in_off[f] + (b * stages + i) * per, src, per);
@@ -654,16 +689,6 @@ class OcpQpIpmSolver {
     if (warm) { h.x_init = at(fxin); h.u_init = at(fuin); }
     lap(&detail::FacadeProfile::flatten);
 
-    srbd_ipm_args a;
-    srbd_ipm_args_default(&a);
-    srbd_ipm_args_set_mode(&a, static_cast<int>(solver_settings_.mode));  // d_ocp_qp_ipm_arg_set_default(mode), :103
-    a.iter_max = solver_settings_.iter_max; a.alpha_min = solver_settings_.alpha_min; a.mu0 = solver_settings_.mu0;
-    a.tol_stat = solver_settings_.tol_stat; a.tol_eq = solver_settings_.tol_eq; a.tol_ineq = solver_settings_.tol_ineq;
-    a.tol_comp = solver_settings_.tol_comp; a.reg_prim = solver_settings_.reg_prim; a.warm_start = solver_settings_.warm_start;
-    a.pred_corr = solver_settings_.pred_corr; a.ric_alg = solver_settings_.ric_alg; a.split_step = solver_settings_.split_step;
-    check(srbd_set_ipm_args(ctx, &a), "srbd_set_ipm_args");
-    const bool ric = want_ric_, stat = want_stat_ && !loop;
-    check(srbd_set_outputs(ctx, ric ? 1 : 0, stat ? 1 : 0), "srbd_set_outputs");
     check(srbd_qp_upload(ctx, &h), "srbd_qp_upload");
     if (loop) {
       const int steps = loop->steps;
@@ -719,18 +744,17 @@ class OcpQpIpmSolver {
     const double *x = out + out_off[0], *u = out + out_off[1], *pi = out + out_off[2], *rm = out + out_off[3];
     const int* it = reinterpret_cast<const int*>(out + out_off[4]);
     const int* st = reinterpret_cast<const int*>(out + out_off[5]);
-    std::vector<double> P, p, K, k, tab;
+    double *P = out + out_total, *p = P + Bz * (N + 1) * nx * nx, *K = p + Bz * (N + 1) * nx, *k = K + Bz * N * nu * nx;
+    double* tab = out + out_total + (ric ? Bz * ((N + 1) * (nx * nx + nx) + N * (nu * nx + nu)) : 0);
     if (ric) {
-      P.resize(Bz * (N + 1) * nx * nx); p.resize(Bz * (N + 1) * nx); K.resize(Bz * N * nu * nx); k.resize(Bz * N * nu);
       srbd_sol_host so{};
-      so.P = P.data(); so.p = p.data(); so.K = K.data(); so.k = k.data();
+      so.P = P; so.p = p; so.K = K; so.k = k;
       check(srbd_download_solution(ctx, &so), "srbd_download_solution");
     }
     const int rows = srbd_ctx_stat_rows(ctx);
     if (stat) {
-      tab.resize(Bz * rows * SRBD_STAT_M);
       srbd_stats_host sh{};
-      sh.stat = tab.data();
+      sh.stat = tab;
       check(srbd_download_stats(ctx, &sh), "srbd_download_stats");
     }
     status.resize(B);
@@ -746,16 +770,16 @@ class OcpQpIpmSolver {
         if (i == 0 && !ric) s[0].pi.setZero();   // pi[0] exists only together with the Riccati outputs (srbd_b200.h): not stale data
         if (ric) {
           s[i].P.resize(nx, nx); s[i].p.resize(nx);
-          std::memcpy(s[i].P.data(), P.data() + (b * (N + 1) + i) * nx * nx, nx * nx * sizeof(double));
-          std::memcpy(s[i].p.data(), p.data() + (b * (N + 1) + i) * nx, nx * sizeof(double));
+          std::memcpy(s[i].P.data(), P + (b * (N + 1) + i) * nx * nx, nx * nx * sizeof(double));
+          std::memcpy(s[i].p.data(), p + (b * (N + 1) + i) * nx, nx * sizeof(double));
         }
         if (i < N) {
           s[i].u.resize(nu);
           std::memcpy(s[i].u.data(), u + (b * N + i) * nu, nu * sizeof(double));
           if (ric) {
             s[i].K.resize(nu, nx); s[i].k.resize(nu);
-            std::memcpy(s[i].K.data(), K.data() + (b * N + i) * nu * nx, nu * nx * sizeof(double));
-            std::memcpy(s[i].k.data(), k.data() + (b * N + i) * nu, nu * sizeof(double));
+            std::memcpy(s[i].K.data(), K + (b * N + i) * nu * nx, nu * nx * sizeof(double));
+            std::memcpy(s[i].k.data(), k + (b * N + i) * nu, nu * sizeof(double));
           }
         }
       }

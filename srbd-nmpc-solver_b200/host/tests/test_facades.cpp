@@ -469,6 +469,18 @@ static void test_errors() {
   thrown = false;
   try { hpipm::OcpQpIpmSolverSettings b; b.mu0 = -1; b.checkSettings(); } catch (const std::runtime_error&) { thrown = true; }
   CHECK(thrown);
+  thrown = false;   // NEW: a batch entry with other dimensions than the first is refused (the flattened batch is uniform)
+  const uint64_t seed_keep = g_seed;   // (the later tests keep the random problems they were tuned on)
+  try {
+    std::vector<std::vector<hpipm::OcpQp>> bq{randomQp(5, 3, 4, 1.0, true), randomQp(4, 3, 4, 1.0, true)};
+    std::vector<VectorXd> bx{RndV(5), RndV(4)};
+    std::vector<std::vector<hpipm::OcpQpSolution>> bs;
+    hpipm::OcpQpIpmSolverSettings s2; s2.ric_alg = 0;
+    hpipm::OcpQpIpmSolver solver(s2);
+    solver.solveBatch(bx, bq, bs);
+  } catch (const std::runtime_error& e) { thrown = std::string(e.what()).find("must have the dimensions of the first") != std::string::npos; }
+  CHECK(thrown);
+  g_seed = seed_keep;
   std::printf("errors: done\n");
 }
 
