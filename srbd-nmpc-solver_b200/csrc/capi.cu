@@ -91,6 +91,7 @@ struct srbd_ctx {
   int grid2 = 0;
   int assembled_mode = -1;   // >= 0: the packed QP came from srbd_assemble (K2) in that mode
   int grid = 0, stat_rows = 0;
+  bool spread = false;   // sparse batch: K3's kSpread instantiations on the full grid (solve_srbd_variant)
   bool export_ric = false, export_stat = false;
   bool ric_valid = false, stat_valid = false;
   // K1 / K2 write the dense records (RSQrq, DCt, d, dmask, raw stage-0 blocks) only when something will read them: the
@@ -874,9 +875,19 @@ static int solve_srbd_variant(srbd_ctx* ctx, const ModelDev* model, const int* g
       const long long c = std::atoll(gs);
       if (c >= 1 && c < g) g = c;
     }
+    // Sparse batches (at least as many QPs as SMs, fewer than resident warps; BASELINE config 2: 1024 QPs): the full grid of
+    // the kSpread instantiation, which keeps exactly B warps spread evenly over the SMs (6-8 solves side by side on every
+    // SM instead of 12 on some and 6 on the others: 1024 QPs 3.00 -> 2.55 ms).  Everything else: no more CTAs than needed.
     const long long need = (ctx->B + v2::kWarps - 1) / v2::kWarps;
-    if (g > need) g = need;
+    const char* sp = std::getenv("SRBD_K3_SPREAD");   // =0: CTAs filled one after the other as for full batches (A/B runs)
+    ctx->spread = g > need && ctx->B >= ctx->sm_count && !(sp && sp[0] == '0');
+    if (g > need && !ctx->spread) g = need;
     ctx->grid2 = (int)g;
+    if (ctx->spread) {
+      CU(cudaFuncSetAttribute(ipm_srbd_kernel<SRBD_K3_TMA, 0, 0, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes));
+      CU(cudaFuncSetAttribute(ipm_srbd_kernel<SRBD_K3_TMA, 0, 0, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes));
+      CU(cudaFuncSetAttribute(ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 0, 0, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::kSmemBytes));
+    }
     CU(dalloc(&ctx->d_ws2, (size_t)ctx->grid2 * v2::kWarps * (size_t)(L.N + 1) * (v2::kStage + v2::kAlt)));
     CU(dalloc(&ctx->d_retry, (size_t)ctx->B + 1));
     CU(dalloc(&ctx->d_retry2, (size_t)ctx->B + 1));
@@ -927,9 +938,12 @@ static int solve_srbd_variant(srbd_ctx* ctx, const ModelDev* model, const int* g
   if (!compact)
     if (int rc = ensure_babt(ctx)) return rc;   // every other instantiation streams the dense BAbt records
   if (exports && team) ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 0, v2::kWarps, true><<<ctx->B, 32 * v2::kWarps, kTeamSmem, ctx->stream>>>(p);
+  else if (exports && ctx->spread) ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 0, 0, true, false, true><<<ctx->grid2, 32 * v2::kWarps, v2::kSmemBytes, ctx->stream>>>(p);
   else if (exports) ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 0, 0, true><<<ctx->grid2, 32 * v2::kWarps, v2::kSmemBytes, ctx->stream>>>(p);
   else if (team) ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 0, v2::kWarps><<<ctx->B, 32 * v2::kWarps, kTeamSmem, ctx->stream>>>(p);
   else if (ctx->B < ctx->sm_count) ipm_srbd_kernel<SRBD_K3_TMA_SMALL, 0><<<ctx->grid2, 32 * v2::kWarps, v2::kSmemBytes, ctx->stream>>>(p);
+  else if (compact && ctx->spread) ipm_srbd_kernel<SRBD_K3_TMA, 0, 0, false, true, true><<<ctx->grid2, 32 * v2::kWarps, v2::kSmemBytes, ctx->stream>>>(p);
+  else if (ctx->spread) ipm_srbd_kernel<SRBD_K3_TMA, 0, 0, false, false, true><<<ctx->grid2, 32 * v2::kWarps, v2::kSmemBytes, ctx->stream>>>(p);
   else if (compact) ipm_srbd_kernel<SRBD_K3_TMA, 0, 0, false, true><<<ctx->grid2, 32 * v2::kWarps, v2::kSmemBytes, ctx->stream>>>(p);
   else ipm_srbd_kernel<SRBD_K3_TMA, 0><<<ctx->grid2, 32 * v2::kWarps, v2::kSmemBytes, ctx->stream>>>(p);
   ctx->launches++;

@@ -2440,8 +2440,12 @@ struct SrbdSolver {
 // shared-memory doubles of the team's scratch (between the CTA constants and the warp blocks): [kTeam][6] + 4, whole lines
 constexpr int kTeamShared = 48;
 static_assert(6 * v2::kWarps + 4 <= kTeamShared, "team scratch");
-template <int kTma, int kPivot, int kTeam = 0, bool kExp = false, bool kCG = false>
+// kSpread: the instantiation for SPARSE batches (at least as many QPs as SMs, fewer than resident warps; see below).  A
+// template parameter and not a run-time test because the register allocation of the throughput instantiation has no
+// slack: the same early exit compiled into it costs 16 bytes of spills and 4 % (profiles/r2f_spread_ab.txt).
+template <int kTma, int kPivot, int kTeam = 0, bool kExp = false, bool kCG = false, bool kSpread = false>
 __global__ void SRBD_K3_BOUNDS ipm_srbd_kernel(const SrbdIpmParams p) {
+  static_assert(!kSpread || kTeam == 0, "spreading is for the one-warp-per-QP mode");
   static_assert(!kCG || (kTeam == 0 && !kExp && v2::kGP % 2 == 0), "compact BAbt streaming: throughput instantiations, 16-byte aligned panels");
   static_assert(kTeam == 0 || kTeam == v2::kWarps, "a team is the whole CTA");
   extern __shared__ __align__(128) double2 smem2[];  // no static shared memory: the tiles start on 128-byte lines
@@ -2469,6 +2473,10 @@ __global__ void SRBD_K3_BOUNDS ipm_srbd_kernel(const SrbdIpmParams p) {
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Sparse batches (fewer QPs than resident warps; the host launches the full grid of this instantiation): exactly B warps stay,
+  // numbered slot-major (warp index first, CTA second), so that every SM runs the same number of solves side by side
+  // instead of some SMs carrying two full CTAs and others one (1024 QPs: 6-8 warps on every SM instead of 12 on 23 SMs)
+  if (kSpread && !p.qlist && (long long)warp * gridDim.x + blockIdx.x >= p.B) return;
   SrbdSolver<kTma, kPivot, kTeam, kExp, kCG> S(p, smem, smem + v2::kCtaShared + (kTeam ? kTeamShared : 0) + warp * v2::kWarpShared,
                                     kTeam ? blockIdx.x : blockIdx.x * v2::kWarps + warp);
   S.tiles_init();

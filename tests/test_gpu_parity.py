@@ -730,6 +730,37 @@ def test_dense_babt_records_are_lazy_on_the_throughput_path(pkg, monkeypatch):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("cg", ["1", "0"])
+def test_sparse_batches_are_spread_over_the_sms(pkg, orc, monkeypatch, cg):
+    """Batches of at least as many QPs as SMs but fewer than resident warps (BASELINE config 2: 1024 QPs) run K3's kSpread
+    instantiations on the full grid: exactly B warps stay, spread evenly over the SMs.  Same arithmetic per QP: outputs bit
+    for bit equal to the packed launch (SRBD_K3_SPREAD=0), for the compact (cg = 1) and the dense-streaming (cg = 0)
+    instantiation, on a ragged batch size; iteration counts equal the oracle's on a sample."""
+    B, N = 1000, 20
+    w = pkg.workload.srbd_batch(B, N=N, contact_mode="gait", start=4242)
+    monkeypatch.setenv("SRBD_K3_CG", cg)
+    runs = {}
+    for spread in ("0", "1"):
+        monkeypatch.setenv("SRBD_K3_SPREAD", spread)
+        with make_ctx(pkg, B, N) as ctx:
+            ctx.upload_traj(w["x"], w["u"], w["xref"], w["x0"], w["contact"])
+            ctx.linearize(); ctx.assemble(pkg.capi.SRBD_HARD_INEQ)
+            ctx.qp_solve()
+            runs[spread] = (ctx.download_solution(want=("x", "u", "pi", "lam", "t")), ctx.download_stats(), ctx.batch_stats())
+    (s0, t0, b0), (s1, t1, b1) = runs["0"], runs["1"]
+    assert (t1["status"] == 0).all()
+    assert np.array_equal(t1["iter"], t0["iter"]) and np.array_equal(t1["status"], t0["status"])
+    assert np.array_equal(t1["res_max"], t0["res_max"])
+    for k in ("x", "u", "pi", "lam", "t"):
+        assert np.array_equal(s1[k], s0[k]), k
+    assert b1["solves"] == b0["solves"] == B and b1["iter_sum"] == b0["iter_sum"]
+    n = 48
+    ref = orc.pipeline(orc.model_params(N), orc.ipm_args(**SETTINGS), N, pkg.capi.SRBD_HARD_INEQ,
+                       w["x"][:n], w["u"][:n], w["xref"][:n], w["x0"][:n], w["contact"][:n])
+    assert np.array_equal(t1["iter"][:n], ref["iter"])
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("generic", ["0", "1"])
 def test_failed_pivot_zeroes_the_component_on_gpu(pkg, orc, monkeypatch, generic):
     """Both K3 kernels on the QP of tests/test_oracle_qp.py::test_failed_pivot_zeroes_the_component (all stance, N=50): a
