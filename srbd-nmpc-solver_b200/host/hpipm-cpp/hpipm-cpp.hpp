@@ -363,11 +363,12 @@ class OcpQpIpmSolver {
                                       std::vector<std::vector<OcpQpSolution>>& qp_sol) {
     if (x0.size() != ocp_qp.size()) throw std::runtime_error("x0.size() must be " + std::to_string(ocp_qp.size()));
     if (qp_sol.size() != ocp_qp.size()) qp_sol.resize(ocp_qp.size());
+    std::vector<HpipmStatus> st;
+    if (ocp_qp.empty()) { batch_iter_.clear(); batch_res_.clear(); return st; }   // an empty batch is solved: nothing to do
     std::vector<const std::vector<OcpQp>*> qps;
     std::vector<std::vector<OcpQpSolution>*> sols;
     std::vector<const Eigen::VectorXd*> x0s;
     for (size_t i = 0; i < ocp_qp.size(); ++i) { qps.push_back(&ocp_qp[i]); sols.push_back(&qp_sol[i]); x0s.push_back(&x0[i]); }
-    std::vector<HpipmStatus> st;
     solveImpl(x0s, qps, sols, st, nullptr);
     return st;
   }
@@ -388,6 +389,7 @@ class OcpQpIpmSolver {
     if (x0.size() != ocp_qp.size()) throw std::runtime_error("x0.size() must be " + std::to_string(ocp_qp.size()));
     if (qp_sol.size() != ocp_qp.size()) qp_sol.resize(ocp_qp.size());
     if (sim_steps < 1) throw std::runtime_error("sim_steps must be positive");
+    if (ocp_qp.empty()) throw std::runtime_error("solveClosedLoop needs at least one robot");
     std::vector<const std::vector<OcpQp>*> qps;
     std::vector<std::vector<OcpQpSolution>*> sols;
     std::vector<const Eigen::VectorXd*> x0s;

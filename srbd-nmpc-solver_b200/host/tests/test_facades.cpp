@@ -480,6 +480,11 @@ static void test_errors() {
     solver.solveBatch(bx, bq, bs);
   } catch (const std::runtime_error& e) { thrown = std::string(e.what()).find("must have the dimensions of the first") != std::string::npos; }
   CHECK(thrown);
+  {   // NEW: an empty batch is not an error
+    std::vector<std::vector<hpipm::OcpQp>> bq; std::vector<VectorXd> bx; std::vector<std::vector<hpipm::OcpQpSolution>> bs;
+    hpipm::OcpQpIpmSolver solver;
+    CHECK(solver.solveBatch(bx, bq, bs).empty() && solver.getBatchIterations().empty());
+  }
   g_seed = seed_keep;
   std::printf("errors: done\n");
 }
