@@ -327,6 +327,7 @@ class OcpQpIpmSolver {
       o.pc_ = detail::PooledContext();
       worker_[0] = std::move(o.worker_[0]); worker_[1] = std::move(o.worker_[1]);
       batch_iter_ = std::move(o.batch_iter_); batch_res_ = std::move(o.batch_res_);
+      keep_batch_stats_ = o.keep_batch_stats_; batch_tab_ = std::move(o.batch_tab_); batch_tab_rows_ = o.batch_tab_rows_;
     }
     return *this;
   }
@@ -404,6 +405,22 @@ class OcpQpIpmSolver {
   const OcpQpIpmSolverStatistics& getSolverStatistics() const { return solver_statistics_; }
   const std::vector<int>& getBatchIterations() const { return batch_iter_; }
   const std::vector<double>& getBatchMaxResiduals() const { return batch_res_; }  // [B][4]: stat, eq, ineq, comp
+  // NEW.  The per-iteration statistics table of EVERY QP of a batch (getSolverStatistics() describes the last one only).
+  // Opt-in because the tables are copied out of the staging arena (rows x 18 doubles per QP); needs setOutputs(.., true).
+  void setKeepBatchStatistics(bool keep) { keep_batch_stats_ = keep; }
+  OcpQpIpmSolverStatistics getBatchStatistics(size_t b) const {
+    if (b >= batch_iter_.size()) throw std::runtime_error("getBatchStatistics: the last batch had " + std::to_string(batch_iter_.size()) + " QPs");
+    OcpQpIpmSolverStatistics st;
+    st.iter = batch_iter_[b];
+    st.max_res_stat = batch_res_[4 * b + 0]; st.max_res_eq = batch_res_[4 * b + 1];
+    st.max_res_ineq = batch_res_[4 * b + 2]; st.max_res_comp = batch_res_[4 * b + 3];
+    if (batch_tab_.empty()) throw std::runtime_error("getBatchStatistics: call setKeepBatchStatistics(true) and setOutputs(.., true) before solveBatch");
+    auto cols = st.columns();
+    const size_t rows = static_cast<size_t>(batch_tab_rows_);
+    for (size_t i = 0; i <= static_cast<size_t>(st.iter) + 1 && i < rows; ++i)
+      for (int c = 0; c < SRBD_STAT_M; ++c) cols[c]->push_back(batch_tab_[(b * rows + i) * SRBD_STAT_M + c]);
+    return st;
+  }
 
  private:
   struct ClosedLoop {
@@ -420,6 +437,9 @@ class OcpQpIpmSolver {
   bool want_ric_ = true, want_stat_ = true;
   std::vector<int> batch_iter_;
   std::vector<double> batch_res_;
+  bool keep_batch_stats_ = false;
+  std::vector<double> batch_tab_;   // [B][rows][SRBD_STAT_M] when kept
+  int batch_tab_rows_ = 0;
   // solveBatch on large batches: two worker solvers (each with its own pooled context, stream and pinned arena) take
   // chunks of the batch alternately, so that flattening / scattering on the host, the H2D copy and the kernels of
   // neighbouring chunks overlap (solvePipelined)
@@ -500,7 +520,10 @@ class OcpQpIpmSolver {
       w->setSolverSettings(solver_settings_);
       w->setDevice(device_);
       w->setOutputs(want_ric_, want_stat_);
+      w->setKeepBatchStatistics(keep_batch_stats_);
     }
+    batch_tab_.clear();
+    batch_tab_rows_ = 0;
     status.assign(B, HpipmStatus::UnknownFailure);
     batch_iter_.assign(B, 0);
     batch_res_.assign(4 * B, 0.0);
@@ -512,6 +535,12 @@ class OcpQpIpmSolver {
       std::copy(st.begin(), st.end(), status.begin() + static_cast<long>(lo));
       std::copy(w.batch_iter_.begin(), w.batch_iter_.end(), batch_iter_.begin() + static_cast<long>(lo));
       std::copy(w.batch_res_.begin(), w.batch_res_.end(), batch_res_.begin() + static_cast<long>(4 * lo));
+      if (!w.batch_tab_.empty()) {   // (the number of rows depends on iter_max only: the same in every chunk)
+        batch_tab_rows_ = w.batch_tab_rows_;
+        const size_t per = static_cast<size_t>(batch_tab_rows_) * SRBD_STAT_M;
+        if (batch_tab_.size() != B * per) batch_tab_.assign(B * per, 0.0);
+        std::copy(w.batch_tab_.begin(), w.batch_tab_.end(), batch_tab_.begin() + static_cast<long>(lo * per));
+      }
     };
     try {
       for (size_t c = 0; c < nchunks; ++c) {
@@ -798,6 +827,8 @@ class OcpQpIpmSolver {
     solver_statistics_.max_res_stat = rm[4 * bl + 0]; solver_statistics_.max_res_eq = rm[4 * bl + 1];
     solver_statistics_.max_res_ineq = rm[4 * bl + 2]; solver_statistics_.max_res_comp = rm[4 * bl + 3];
     solver_statistics_.clear();
+    if (stat && keep_batch_stats_) { batch_tab_.assign(tab, tab + Bz * static_cast<size_t>(rows) * SRBD_STAT_M); batch_tab_rows_ = rows; }
+    else { batch_tab_.clear(); batch_tab_rows_ = 0; }
     if (stat) {
       auto cols = solver_statistics_.columns();
       for (int i = 0; i <= it[bl] + 1 && i < rows; ++i)

@@ -389,6 +389,26 @@ static void test_pipelined_batch() {
     CHECK(same(one, piped));
     CHECK(a.getBatchIterations() == b.getBatchIterations() && a.getBatchMaxResiduals() == b.getBatchMaxResiduals());
     CHECK(a.getSolverStatistics().iter == b.getSolverStatistics().iter && a.getSolverStatistics().mu == b.getSolverStatistics().mu);
+    if (outputs) {   // NEW: the statistics table of every QP of the batch (opt-in), one launch == pipelined == one QP per call
+      a.setKeepBatchStatistics(true); b.setKeepBatchStatistics(true);
+      hpipm::OcpQpIpmSolver::setBatchChunk(0);
+      a.solveBatch(x0, qps, one);
+      hpipm::OcpQpIpmSolver::setBatchChunk(3);
+      b.solveBatch(x0, qps, piped);
+      for (int q : {0, 4, B - 1}) {
+        const auto sa = a.getBatchStatistics(q), sb = b.getBatchStatistics(q);
+        std::vector<hpipm::OcpQpSolution> lone;
+        hpipm::OcpQpIpmSolver c(s);
+        c.solve(x0[q], qps[q], lone);
+        const auto& sc = c.getSolverStatistics();
+        CHECK(sa.iter == sb.iter && sa.iter == sc.iter && (int)sa.mu.size() == sa.iter + 2);
+        CHECK(sa.mu == sb.mu && sa.mu == sc.mu && sa.res_stat == sc.res_stat && sa.alpha_prim == sb.alpha_prim && sa.obj == sc.obj);
+        CHECK(sa.max_res_comp == sc.max_res_comp);
+      }
+      bool thrown = false;
+      try { a.getBatchStatistics(B); } catch (const std::runtime_error&) { thrown = true; }
+      CHECK(thrown);
+    }
   }
   // ---- SRBD-structured QPs -------------------------------------------------------------------------------------------
   {
