@@ -492,7 +492,7 @@ class OcpQpIpmSolver {
   // QPs per chunk of the pipelined solveBatch (SRBD_FACADE_CHUNK; 0 = never pipeline).  A chunk of 1024 N = 20 SRBD QPs is
   // 235 MB of QP fields: a few ms each of host flattening, H2D copy and kernels.
   static size_t& pipelineChunk() {
-    static size_t c = [] { const char* e = std::getenv("SRBD_FACADE_CHUNK"); return e ? static_cast<size_t>(std::atol(e)) : size_t(1024); }();
+    static size_t c = [] { const char* e = std::getenv("SRBD_FACADE_CHUNK"); const long v = e ? std::atol(e) : 1024; return static_cast<size_t>(v > 0 ? v : 0); }();
     return c;
   }
   static bool anyNonZero(const double* v, size_t n) {
@@ -504,7 +504,7 @@ class OcpQpIpmSolver {
   void solveImpl(const std::vector<const Eigen::VectorXd*>& x0s, const std::vector<const std::vector<OcpQp>*>& qps,
                  const std::vector<std::vector<OcpQpSolution>*>& sols, std::vector<HpipmStatus>& status, ClosedLoop* loop) {
     const size_t chunk = pipelineChunk();
-    if (!loop && chunk && qps.size() >= 2 * chunk) { solvePipelined(x0s, qps, sols, status, chunk); return; }
+    if (!loop && chunk && qps.size() / 2 >= chunk) { solvePipelined(x0s, qps, sols, status, chunk); return; }
     submit(x0s, qps, sols, loop);
     collect(status, loop);
   }
