@@ -272,6 +272,10 @@ int srbd_download_qp(srbd_ctx* ctx, double* Q, double* S, double* R, double* q, 
  * 12 x 6 blocks, ug masked); srbd_qp_solve then routes it to the tensor-core variant of K3 when the settings allow
  * (cold start, ric_alg = 0, no Riccati / statistics exports) -- the reference's own boundary reaches the fast kernel. */
 int srbd_qp_upload(srbd_ctx* ctx, const srbd_qp_host* qp);
+/* Layout of the host fields of the NEXT uploads of this context (sticky).  d_shared != 0: qp->D is ONE ng x nu matrix
+ * shared by every stage of every QP -- what NMPCSolver::prepareQpStructures hands to hpipm-cpp (the friction-cone / force-box
+ * matrix of SRBDModel::GetConstrain is a constant, NMPC_solver.cpp:290-300) -- instead of B x N copies of it.  Default 0. */
+int srbd_qp_upload_layout(srbd_ctx* ctx, int d_shared);
 /* K3: the whole IPM solve of every QP of the batch (d_ocp_qp_ipm_solve, hpipm_d_ocp_qp_ipm.h:238), asynchronous on
  * the context's stream.  QPs assembled by srbd_assemble() go through the tensor-core variant (one launch) followed by
  * the rescue launch of the generic kernel for the QPs that ran to iter_max (usually none);

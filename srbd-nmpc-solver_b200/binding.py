@@ -157,8 +157,10 @@ class Context:
         return o
 
     # -- QP level ---------------------------------------------------------------------------------
-    def qp_upload(self, arrays):
+    def qp_upload(self, arrays, d_shared=False):
+        """d_shared: arrays["D"] is ONE ng x nu matrix shared by every stage of every QP (srbd_qp_upload_layout)."""
         qp, keep = capi.make_qp_host(arrays)
+        self._ck(self._L.srbd_qp_upload_layout(self._h, 1 if d_shared else 0))
         self._ck(self._L.srbd_qp_upload(self._h, C.byref(qp)))
         del keep
 

@@ -124,7 +124,7 @@ _EXPORTS = [
     "srbd_ctx_stat_rows",
     "srbd_ctx_stream", "srbd_ctx_device_ptr", "srbd_ctx_sync", "srbd_ctx_launch_count",
     "srbd_upload_traj", "srbd_download_traj", "srbd_linearize", "srbd_assemble",
-    "srbd_download_linearization", "srbd_download_qp", "srbd_qp_upload", "srbd_qp_solve",
+    "srbd_download_linearization", "srbd_download_qp", "srbd_qp_upload", "srbd_qp_upload_layout", "srbd_qp_solve",
     "srbd_download_solution", "srbd_download_stats", "srbd_download_ric_lr0", "srbd_batch_stats_get", "srbd_line_search",
     "srbd_download_sqp_state", "srbd_reset_sqp_state", "srbd_sqp_iterate", "srbd_sqp_solve", "srbd_download_sqp_iters", "srbd_solve_host", "srbd_solve_host_async", "srbd_wait", "srbd_solve_host_graph",
     "srbd_fp64_peak", "srbd_mpc_run", "srbd_out_layout", "srbd_download_packed", "srbd_host_alloc", "srbd_host_free",
@@ -172,6 +172,7 @@ def lib():
     L.srbd_download_linearization.argtypes = [vp] + [c_double_p] * 4
     L.srbd_download_qp.argtypes = [vp] + [c_double_p] * 8
     L.srbd_qp_upload.argtypes = [vp, C.POINTER(QpHost)]
+    L.srbd_qp_upload_layout.argtypes = [vp, C.c_int]
     L.srbd_qp_solve.argtypes = [vp]
     L.srbd_download_solution.argtypes = [vp, C.POINTER(SolHost)]
     L.srbd_download_stats.argtypes = [vp, C.POINTER(StatsHost)]

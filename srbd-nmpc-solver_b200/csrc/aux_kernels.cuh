@@ -21,6 +21,7 @@ struct PackParams {
   double *babt, *rsq, *dct, *d, *dmask, *raw0;
   int raw0_stride;
   double* r0raw;  // [B][nu] the un-embedded r0 (the closed-loop driver re-embeds x0 every step) or null
+  int d_stride;   // doubles between the D of consecutive (QP, stage) items: ng * nu, or 0 for ONE shared D (srbd_qp_upload_layout)
 };
 
 __global__ void __launch_bounds__(128) pack_kernel(const PackParams p) {
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(128) pack_kernel(const PackParams p) {
     const int ng = stage_ng(L, k);
     double* dst = p.dct + qS * L.dct_stride;
     const int cn = L.dct_cn;
-    const double* Dm = (k < N && ng > 0) ? p.qp.D + qN * L.ng * nu : nullptr;
+    const double* Dm = (k < N && ng > 0) ? p.qp.D + qN * p.d_stride : nullptr;
     const double* Cm = nullptr;
     int ldc = L.ng;
     if (ng > 0) {
@@ -170,6 +171,7 @@ struct DetectParams {
   double* srec;      // [B][N+1][kSrec]
   ModelDev* model;
   int* bad;
+  int d_stride;      // 288, or 0 for one shared D
 };
 
 __global__ void __launch_bounds__(128) detect_srbd_kernel(const DetectParams p) {
@@ -185,7 +187,7 @@ __global__ void __launch_bounds__(128) detect_srbd_kernel(const DetectParams p) 
       for (int e = lane; e < 144; e += 32) bad |= p.qp.S[qN * 144 + e] != 0.0;
     if (p.qp.C && k > 0)
       for (int e = lane; e < 288; e += 32) bad |= p.qp.C[qN * 288 + e] != 0.0;
-    const double* D = p.qp.D + qN * 288;   // column-major 24 x 12: D(g, j) at g + 24 j
+    const double* D = p.qp.D + qN * p.d_stride;   // column-major 24 x 12: D(g, j) at g + 24 j
     for (int e = lane; e < 288; e += 32) {
       const int g = e % 24, j = e / 24;
       const double v = D[e];

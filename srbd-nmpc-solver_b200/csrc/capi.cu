@@ -92,6 +92,7 @@ struct srbd_ctx {
   int assembled_mode = -1;   // >= 0: the packed QP came from srbd_assemble (K2) in that mode
   int grid = 0, stat_rows = 0;
   bool spread = false;   // sparse batch: K3's kSpread instantiations on the full grid (solve_srbd_variant)
+  bool upload_d_shared = false;   // srbd_qp_upload_layout: qp->D is ONE ng x nu matrix shared by every stage of every QP
   bool export_ric = false, export_stat = false;
   bool ric_valid = false, stat_valid = false;
   // K1 / K2 write the dense records (RSQrq, DCt, d, dmask, raw stage-0 blocks) only when something will read them: the
@@ -682,6 +683,18 @@ int srbd_download_qp(srbd_ctx* ctx, double* Q, double* S, double* R, double* q, 
 }
 
 // ---- QP level -------------------------------------------------------------------------------------
+int srbd_qp_upload_layout(srbd_ctx* ctx, int d_shared) {
+  if (!ctx) return SRBD_ERR_ARG;
+  if (ctx->upload_d_shared != (d_shared != 0) && ctx->raw_alloc) {   // per-field device buffers were sized for the other layout
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (void*& q : ctx->raw_dev) { if (q) cudaFree(q); q = nullptr; }
+    ctx->raw_alloc = false;
+  }
+  ctx->upload_d_shared = d_shared != 0;
+  return SRBD_OK;
+}
+
 int srbd_qp_upload(srbd_ctx* ctx, const srbd_qp_host* qp) {
   if (!ctx || !qp) return SRBD_ERR_ARG;
   const QpLayout& L0 = ctx->L;
@@ -707,7 +720,7 @@ int srbd_qp_upload(srbd_ctx* ctx, const srbd_qp_host* qp) {
       {&srbd_qp_host::lbx_mask, B * S * L.nbx}, {&srbd_qp_host::ubx_mask, B * S * L.nbx},
       {&srbd_qp_host::lbu, B * N * L.nbu}, {&srbd_qp_host::ubu, B * N * L.nbu},
       {&srbd_qp_host::lbu_mask, B * N * L.nbu}, {&srbd_qp_host::ubu_mask, B * N * L.nbu},
-      {&srbd_qp_host::C, B * N * L.ng * nx}, {&srbd_qp_host::D, B * N * L.ng * nu},
+      {&srbd_qp_host::C, B * N * L.ng * nx}, {&srbd_qp_host::D, ctx->upload_d_shared ? (size_t)L.ng * nu : B * N * L.ng * nu},
       {&srbd_qp_host::lg, B * N * L.ng}, {&srbd_qp_host::ug, B * N * L.ng},
       {&srbd_qp_host::lg_mask, B * N * L.ng}, {&srbd_qp_host::ug_mask, B * N * L.ng},
       {&srbd_qp_host::CN, B * L.ngN * nx}, {&srbd_qp_host::lgN, B * L.ngN}, {&srbd_qp_host::ugN, B * L.ngN},
@@ -771,6 +784,7 @@ int srbd_qp_upload(srbd_ctx* ctx, const srbd_qp_host* qp) {
   p.L = L; p.B = ctx->B; p.qp = dq;
   p.babt = ctx->d_babt; p.rsq = ctx->d_rsq; p.dct = ctx->d_dct; p.d = ctx->d_d; p.dmask = ctx->d_dmask;
   p.raw0 = ctx->d_raw0; p.raw0_stride = raw0_stride(L); p.r0raw = ctx->d_r0raw;
+  p.d_stride = ctx->upload_d_shared ? 0 : L.ng * L.nu;
   const long long total = (long long)ctx->B * (L.N + 1);
   pack_kernel<<<(int)((total + 3) / 4), 128, 0, ctx->stream>>>(p);
   ctx->launches++;
@@ -782,6 +796,7 @@ int srbd_qp_upload(srbd_ctx* ctx, const srbd_qp_host* qp) {
   if (ctx->is_srbd) {  // SRBD dimensions: does the data have K2's structure?  (decided on the device, aux_kernels.cuh)
     DetectParams dp{};
     dp.B = ctx->B; dp.N = L.N; dp.qp = dq; dp.srec = ctx->d_srec; dp.model = ctx->d_model_qp; dp.bad = ctx->d_flag;
+    dp.d_stride = ctx->upload_d_shared ? 0 : 288;
     CU(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
     detect_srbd_kernel<<<(int)((total + 3) / 4), 128, 0, ctx->stream>>>(dp);
     ctx->launches++;

@@ -612,22 +612,25 @@ class OcpQpIpmSolver {
     // outputs in the device's own layout: ONE H2D copy up, ONE D2H copy down -------------------------------------------
     size_t out_off[8], out_total = 0;
     check(srbd_out_layout(ctx, out_off, &out_total), "srbd_out_layout");
-    const size_t in_sizes[30] = {Bz * N * nx * nx, Bz * N * nx * nu, Bz * N * nx, Bz * (N + 1) * nx * nx, Bz * N * nu * nx,
+    const size_t in_sizes[31] = {Bz * N * nx * nx, Bz * N * nx * nu, Bz * N * nx, Bz * (N + 1) * nx * nx, Bz * N * nu * nx,
                                  Bz * N * nu * nu, Bz * (N + 1) * nx, Bz * N * nu,
                                  Bz * (N + 1) * nbx, Bz * (N + 1) * nbx, Bz * (N + 1) * nbx, Bz * (N + 1) * nbx,
                                  Bz * N * nbu, Bz * N * nbu, Bz * N * nbu, Bz * N * nbu,
                                  Bz * N * ng * nx, Bz * N * ng * nu, Bz * N * ng, Bz * N * ng, Bz * N * ng, Bz * N * ng,
                                  Bz * ngN * nx, Bz * ngN, Bz * ngN, Bz * ngN, Bz * ngN, Bz * nx,
-                                 warm ? Bz * (N + 1) * nx : 0, warm ? Bz * N * nu : 0};
+                                 warm ? Bz * (N + 1) * nx : 0, warm ? Bz * N * nu : 0, ng * nu};
     enum { fA, fB, fb, fQ, fS, fR, fq, fr, flbx, fubx, flbxm, fubxm, flbu, fubu, flbum, fubum, fC, fD, flg, fug, flgm, fugm,
-           fCN, flgN, fugN, flgNm, fugNm, fx0, fxin, fuin };
+           fCN, flgN, fugN, flgNm, fugNm, fx0, fxin, fuin, fDs };
     // S and C lie at the END of the input area: when every S_k and C_k of the batch is zero (what
     // NMPCSolver::prepareQpStructures hands over, NMPC_solver.cpp:277-314) they are passed as "absent" and the single
     // H2D copy of srbd_qp_upload (the span of the fields that are present) ends before them: 30 % fewer bytes over PCIe
-    const int order[30] = {fA, fB, fb, fQ, fR, fq, fr, flbx, fubx, flbxm, fubxm, flbu, fubu, flbum, fubum, fD, flg, fug, flgm, fugm,
-                           fCN, flgN, fugN, flgNm, fugNm, fx0, fxin, fuin, fS, fC};
-    size_t in_off[30], in_total = 0;
-    for (int i = 0; i < 30; ++i) { in_off[order[i]] = in_total; in_total += in_sizes[order[i]]; }
+    // The same for D: NMPCSolver::prepareQpStructures hands over ONE constraint matrix in every stage of every QP
+    // (NMPC_solver.cpp:290-300).  While every D_k equals the first bit for bit, only that one is staged (slot fDs) and the
+    // upload is told so (srbd_qp_upload_layout); the per-stage copies are written by the second pass otherwise.
+    const int order[31] = {fA, fB, fb, fQ, fR, fq, fr, flbx, fubx, flbxm, fubxm, flbu, fubu, flbum, fubum, fDs, flg, fug, flgm, fugm,
+                           fCN, flgN, fugN, flgNm, fugNm, fx0, fxin, fuin, fD, fS, fC};
+    size_t in_off[31], in_total = 0;
+    for (int i = 0; i < 31; ++i) { in_off[order[i]] = in_total; in_total += in_sizes[order[i]]; }
     srbd_ipm_args a;
     srbd_ipm_args_default(&a);
     srbd_ipm_args_set_mode(&a, static_cast<int>(solver_settings_.mode));  // d_ocp_qp_ipm_arg_set_default(mode), :103
@@ -642,7 +645,9 @@ class OcpQpIpmSolver {
     const size_t ric_total = ric ? Bz * ((N + 1) * (nx * nx + nx) + N * (nu * nx + nu)) : 0;
     const size_t tab_total = stat ? Bz * static_cast<size_t>(srbd_ctx_stat_rows(ctx)) * SRBD_STAT_M : 0;
     double* ar = arena(in_total + out_total + ric_total + tab_total);
-    std::atomic<int> nz_S{0}, nz_C{0};
+    std::atomic<int> nz_S{0}, nz_C{0}, var_D{0};
+    const double* D0 = ng ? (*qps[0])[0].D.data() : nullptr;
+    if (ng) std::memcpy(ar + in_off[fDs], D0, ng * nu * sizeof(double));
     auto put = [&](int f, size_t b, size_t stages, size_t i, size_t per, const double* src) {
       if (per) detail::copyOut(ar + in_off[f] + (b * stages + i) * per, src, per);
     };
@@ -680,7 +685,8 @@ class OcpQpIpmSolver {
         if (ng) {
           // (C_0 is dropped by the x0 embedding, nx[0] := 0, so it does not count)
           if (i >= 1 && s.C.size() && !nz_C.load(std::memory_order_relaxed) && anyNonZero(s.C.data(), ng * nx)) nz_C.store(1, std::memory_order_relaxed);
-          put(fD, b, N, i, ng * nu, s.D.data());
+          if (!var_D.load(std::memory_order_relaxed) && std::memcmp(s.D.data(), D0, ng * nu * sizeof(double)) != 0)
+            var_D.store(1, std::memory_order_relaxed);
           put(flg, b, N, i, ng, s.lg.data()); put(fug, b, N, i, ng, s.ug.data());
           mask(flgm, b, N, i, ng, s.lg_mask); mask(fugm, b, N, i, ng, s.ug_mask);
         }
@@ -699,11 +705,12 @@ class OcpQpIpmSolver {
     }
     detail::storeFence();
     });
-    if (nz_S.load() || nz_C.load())
+    if (nz_S.load() || nz_C.load() || var_D.load())
       detail::parallelFor(Bz, 64, [&](size_t b_lo, size_t b_hi) {
         for (size_t b = b_lo; b < b_hi; ++b)
           for (size_t i = 0; i < N; ++i) {
             const OcpQp& s = (*qps[b])[i];
+            if (var_D.load() && ng) put(fD, b, N, i, ng * nu, s.D.data());
             if (nz_S.load()) put(fS, b, N, i, nu * nx, s.S.data());
             if (nz_C.load() && ng) { if (s.C.size()) put(fC, b, N, i, ng * nx, s.C.data()); else fill(fC, b, N, i, ng * nx, 0.0); }
           }
@@ -714,12 +721,13 @@ class OcpQpIpmSolver {
     h.A = at(fA); h.Bm = at(fB); h.b = at(fb); h.Q = at(fQ); h.S = nz_S.load() ? at(fS) : nullptr; h.R = at(fR); h.q = at(fq); h.r = at(fr);
     h.idxbx = nbx ? (*qps[0])[N].idxbx.data() : nullptr; h.lbx = at(flbx); h.ubx = at(fubx); h.lbx_mask = at(flbxm); h.ubx_mask = at(fubxm);
     h.idxbu = nbu ? (*qps[0])[0].idxbu.data() : nullptr; h.lbu = at(flbu); h.ubu = at(fubu); h.lbu_mask = at(flbum); h.ubu_mask = at(fubum);
-    h.C = nz_C.load() ? at(fC) : nullptr; h.D = at(fD); h.lg = at(flg); h.ug = at(fug); h.lg_mask = at(flgm); h.ug_mask = at(fugm);
+    h.C = nz_C.load() ? at(fC) : nullptr; h.D = var_D.load() ? at(fD) : at(fDs); h.lg = at(flg); h.ug = at(fug); h.lg_mask = at(flgm); h.ug_mask = at(fugm);
     h.CN = at(fCN); h.lgN = at(flgN); h.ugN = at(fugN); h.lgN_mask = at(flgNm); h.ugN_mask = at(fugNm);
     h.x0 = at(fx0);
     if (warm) { h.x_init = at(fxin); h.u_init = at(fuin); }
     lap(&detail::FacadeProfile::flatten);
 
+    check(srbd_qp_upload_layout(ctx, var_D.load() ? 0 : 1), "srbd_qp_upload_layout");
     check(srbd_qp_upload(ctx, &h), "srbd_qp_upload");
     if (loop) {
       const int steps = loop->steps;

@@ -84,14 +84,15 @@ int main(int argc, char** argv) {
                    full ? "reference" : "x/u/pi", pf.validate / reps, pf.flatten / reps, pf.enqueue / reps, pf.wait / reps, pf.scatter / reps);
     }
   }
-  // S and C of these QPs are all zero: the facade does not send them (hpipm-cpp.hpp, submit)
-  const double bytes_up = (double)B * (N * (4 * 144 + 36 + 288 + 4 * 24) + 144 + 12 + 12) * 8, bytes_down = (double)B * ((N + 1) * 24 + N * 12) * 8;
+  // S and C of these QPs are all zero and D is one constant matrix: the facade sends neither S nor C and D once per chunk
+  // (hpipm-cpp.hpp, submit)
+  const double bytes_up = ((double)B * (N * (4 * 144 + 36 + 4 * 24) + 144 + 12 + 12) + 288.0 * ((B + 1023) / 1024)) * 8, bytes_down = (double)B * ((N + 1) * 24 + N * 12) * 8;
   std::printf("{\"qps\": %d, \"horizon\": %d, \"ms_per_batch\": %.3f, \"value\": %.1f, \"unit\": \"solves/s\", "
               "\"ms_per_batch_reference_outputs\": %.3f, \"value_reference_outputs\": %.1f, \"converged\": %d, \"iter_mean\": %.3f, "
               "\"h2d_bytes\": %.0f, \"d2h_bytes\": %.0f, "
               "\"how\": \"hpipm::OcpQpIpmSolver::solveBatch on host std::vector<OcpQp> (setOutputs(false,false): x, u, pi only; "
               "_reference_outputs: + P,p,K,k,pi[0] + statistics table like the reference's solve(); both run the tensor-core kernel); best of %d after one warm-up; includes "
-              "flattening the Eigen fields into the pinned arena (all-zero S / C stay behind), H2D copy, pack + structure detection + K3, D2H copy, scattering "
+              "flattening the Eigen fields into the pinned arena (all-zero S / C stay behind, the constant D travels once), H2D copy, pack + structure detection + K3, D2H copy, scattering "
               "into OcpQpSolution; batches of >= 2048 QPs are pipelined in chunks of 1024 over two pooled contexts\"}\n",
               B, N, best_fast, B / (best_fast * 1e-3), best_full, B / (best_full * 1e-3), conv, (double)it_sum / B, bytes_up, bytes_down, reps);
   return 0;

@@ -919,6 +919,17 @@ def test_uploaded_srbd_qps_reach_the_tensor_core_kernel(pkg, orc):
             del os.environ["SRBD_K3_GENERIC"]
         assert (st_g["iter"] == st["iter"]).all() and not np.array_equal(sol_g["x"], sol["x"])
         ctx.set_outputs(export_ric=False, export_stat=False)
+        # (2b) the constant constraint matrix handed over ONCE (srbd_qp_upload_layout, d_shared) instead of B x N copies,
+        # S and C absent (all zero: what the facade does): the same kernel on the same data
+        assert np.array_equal(arrays["D"], np.broadcast_to(arrays["D"][0, 0], arrays["D"].shape))
+        arrays_s = {k: v for k, v in arrays.items() if k != "S"}
+        arrays_s["D"] = np.ascontiguousarray(arrays["D"][0, 0])
+        ctx.qp_upload(arrays_s, d_shared=True)
+        ctx.qp_solve()
+        sol_s = ctx.download_solution(want=("x", "u", "pi", "lam", "t"))
+        assert (ctx.download_stats()["iter"] == st["iter"]).all()
+        for k in ("x", "u", "lam", "t"):
+            assert np.array_equal(sol_s[k], sol[k]), k
         # (3) structure broken: S != 0 in one stage of one QP
         arrays2 = dict(arrays, S=arrays["S"].copy())
         arrays2["S"][5, 3, 7] = 1e-3
