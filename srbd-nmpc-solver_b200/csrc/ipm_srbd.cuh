@@ -691,6 +691,8 @@ struct SrbdSolver {
     }
 #if SRBD_K3_UNROLL_FAC
 #pragma unroll 2
+#else
+#pragma unroll (kTeam ? 2 : 1)   // latency mode: the leader warp has the SM (and its instruction cache) to itself
 #endif
     for (int k = N - 1; k >= 0; --k) {
       const int b = (N - 1 - k) & 1;
@@ -975,6 +977,8 @@ struct SrbdSolver {
     S4v cur = load_s4(N - 1);
 #if SRBD_K3_UNROLL_BWD
 #pragma unroll 2
+#else
+#pragma unroll (kTeam ? 2 : 1)   // latency mode: the leader warp has the SM (and its instruction cache) to itself
 #endif
     for (int k = N - 1; k >= 0; --k) {
       const int b = (N - 1 - k) & 1;
@@ -1123,6 +1127,8 @@ struct SrbdSolver {
     S2v cur = load_s2(0);
 #if SRBD_K3_UNROLL_FWD
 #pragma unroll 2
+#else
+#pragma unroll (kTeam ? 2 : 1)   // latency mode: the leader warp has the SM (and its instruction cache) to itself
 #endif
     for (int k = 0; k < N; ++k) {
       const int b = k & 1;
