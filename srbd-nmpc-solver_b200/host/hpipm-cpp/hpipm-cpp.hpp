@@ -574,39 +574,39 @@ class OcpQpIpmSolver {
     solver_settings_.checkSettings();
     const int B = static_cast<int>(qps.size());
     dim_.resize(*qps[0]);  // resize(ocp_qp) on every call like the reference (ocp_qp_ipm_solver.cpp:185)
-    if (B > 1)
-      detail::parallelFor(static_cast<size_t>(B), 256, [&](size_t lo, size_t hi) {
-        for (size_t b = lo > 0 ? lo : 1; b < hi; ++b) dim_.checkBatchEntry(*qps[b]);
-      });
     ensureContext(B);
     srbd_ctx* ctx = pc_.ctx;
     const srbd_qp_dims d = pc_.dims;
     const size_t N = d.N, nx = d.nx, nu = d.nu, nbx = d.nbx, nbu = d.nbu, ng = d.ng, ngN = d.ngN, Bz = static_cast<size_t>(B);
     const bool warm = solver_settings_.warm_start != 0;
-    // warm start needs pre-sized solutions (ocp_qp_ipm_solver.cpp:189-208)
-    for (int b = 0; b < B; ++b) {
-      auto& s = *sols[b];
-      if (s.size() != N + 1) s.resize(N + 1);
-      if (warm)
-        for (size_t i = 0; i <= N; ++i) {
-          if (static_cast<size_t>(s[i].x.size()) != nx) throw std::runtime_error("qp_sol[" + std::to_string(i) + "].x.size() must be " + std::to_string(nx));
-          if (i < N && static_cast<size_t>(s[i].u.size()) != nu) throw std::runtime_error("qp_sol[" + std::to_string(i) + "].u.size() must be " + std::to_string(nu));
-        }
-      if (static_cast<size_t>(x0s[b]->size()) != nx) throw std::runtime_error("x0.size() must be " + std::to_string(nx));
-    }
-    // The C-ABI takes ONE index set for idxbx (stages 1..N) and one for idxbu (stages 0..N-1), shared by the batch;
-    // the reference passes them per stage (ocp_qp_ipm_solver.cpp:263-272).  Differing sets would silently put the
-    // bounds on the wrong variables: refuse them.
-    for (int b = 0; b < B; ++b)
-      for (size_t i = 0; i <= N; ++i) {
-        const OcpQp& s = (*qps[b])[i];
-        if (i >= 1 && nbx && s.idxbx != (*qps[0])[N].idxbx)
-          throw std::runtime_error("ocp_qp[" + std::to_string(i) + "].idxbx differs between stages / batch entries: the "
-                                   "B200 path needs one idxbx for stages 1..N");
-        if (i < N && nbu && s.idxbu != (*qps[0])[0].idxbu)
-          throw std::runtime_error("ocp_qp[" + std::to_string(i) + "].idxbu differs between stages / batch entries: the "
-                                   "B200 path needs one idxbu for stages 0..N-1");
+    // Per QP, spread over host threads (an exception of a worker is rethrown here): the dimensions of every batch entry
+    // equal the first's; warm start needs pre-sized solutions (ocp_qp_ipm_solver.cpp:189-208); and the C-ABI takes ONE
+    // index set for idxbx (stages 1..N) and one for idxbu (stages 0..N-1), shared by the batch, where the reference passes
+    // them per stage (ocp_qp_ipm_solver.cpp:263-272) -- differing sets would silently put the bounds on the wrong
+    // variables: refuse them.
+    detail::parallelFor(Bz, 64, [&](size_t lo, size_t hi) {
+      for (size_t b = lo; b < hi; ++b) {
+        if (b > 0) dim_.checkBatchEntry(*qps[b]);
+        auto& s = *sols[b];
+        if (s.size() != N + 1) s.resize(N + 1);
+        if (warm)
+          for (size_t i = 0; i <= N; ++i) {
+            if (static_cast<size_t>(s[i].x.size()) != nx) throw std::runtime_error("qp_sol[" + std::to_string(i) + "].x.size() must be " + std::to_string(nx));
+            if (i < N && static_cast<size_t>(s[i].u.size()) != nu) throw std::runtime_error("qp_sol[" + std::to_string(i) + "].u.size() must be " + std::to_string(nu));
+          }
+        if (static_cast<size_t>(x0s[b]->size()) != nx) throw std::runtime_error("x0.size() must be " + std::to_string(nx));
+        if (nbx || nbu)
+          for (size_t i = 0; i <= N; ++i) {
+            const OcpQp& q = (*qps[b])[i];
+            if (i >= 1 && nbx && q.idxbx != (*qps[0])[N].idxbx)
+              throw std::runtime_error("ocp_qp[" + std::to_string(i) + "].idxbx differs between stages / batch entries: the "
+                                       "B200 path needs one idxbx for stages 1..N");
+            if (i < N && nbu && q.idxbu != (*qps[0])[0].idxbu)
+              throw std::runtime_error("ocp_qp[" + std::to_string(i) + "].idxbu differs between stages / batch entries: the "
+                                       "B200 path needs one idxbu for stages 0..N-1");
+          }
       }
+    });
     lap(&detail::FacadeProfile::validate);
     // ---- staging arena: every QP field batch-contiguous and column-major (srbd_qp_host), one after the other, then the
     // outputs in the device's own layout: ONE H2D copy up, ONE D2H copy down -------------------------------------------
